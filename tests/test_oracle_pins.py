@@ -1,0 +1,123 @@
+"""Pin the CPU restatement (oracle/psa_oracle.c) against the reference's OWN code compiled here
+(oracle/_ref/libref_cpu.so, built by `make -C oracle ref` from /root/reference) and against the
+reference's only deterministic known-answer test (grouping/test/selection_sort.cpp:68-78)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from scanobjectnn_b200.synthetic import make_clouds
+
+needs_ref = pytest.mark.skipif(not orc.refcpu_available(), reason="oracle/_ref/libref_cpu.so not built")
+
+
+def test_selection_sort_kat():
+    # selection_sort.cpp:68-78: b=2,n=4,m=2,k=3, dist[i]=10-i -> each row's first 3 slots are 3,2,1
+    b, n, m, k = 2, 4, 2, 3
+    dist = (10.0 - np.arange(b * m * n, dtype=np.float32)).reshape(b, m, n)
+    outi, out = orc.selection_sort(k, dist)
+    assert (outi[..., :k] == np.array([3, 2, 1])).all()
+    assert (np.diff(out[..., :k], axis=-1) > 0).all()
+    # the full permutation the harness prints: 3 2 1 0 for every row
+    assert (outi == np.array([3, 2, 1, 0])).all()
+
+
+@needs_ref
+def test_selection_sort_matches_reference_cpu():
+    rng = np.random.default_rng(5)
+    dist = rng.random((3, 7, 50), dtype=np.float32)
+    dist[0, 0, 10:20] = dist[0, 0, 3]          # ties: resolved by current array position
+    dist[1, 2, :] = 0.5
+    for k in (1, 5, 50):
+        oi, ov = orc.selection_sort(k, dist)
+        ri, rv = orc.refcpu_selection_sort(k, dist)
+        assert (oi == ri).all() and (ov == rv).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["ball", "shell", "dup"])
+def test_ball_query_matches_reference_cpu(kind):
+    xyz = make_clouds(kind, 4, 512, seed=11)
+    q = xyz[:, ::4, :].copy()
+    for r, k in ((0.1, 64), (0.2, 32), (0.4, 16)):
+        oi, cnt = orc.query_ball_point(r, k, xyz, q, contract=False, fill=-7)
+        ri = orc.refcpu_query_ball_point(r, k, xyz, q, fill=-7)
+        assert (oi == ri).all()
+        assert cnt.min() >= 1          # queries are dataset points: self-distance 1e-20 < r
+
+
+@needs_ref
+def test_ball_query_empty_ball_leaves_row_untouched():
+    xyz = make_clouds("ball", 2, 64, seed=3)
+    q = np.full((2, 5, 3), 9.0, np.float32)
+    oi, cnt = orc.query_ball_point(0.2, 8, xyz, q, contract=False, fill=-7)
+    ri = orc.refcpu_query_ball_point(0.2, 8, xyz, q, fill=-7)
+    assert (oi == -7).all() and (ri == -7).all() and (cnt == 0).all()
+
+
+@needs_ref
+def test_group_point_and_grad_match_reference_cpu():
+    rng = np.random.default_rng(9)
+    pts = rng.standard_normal((3, 40, 7)).astype(np.float32)
+    idx = rng.integers(0, 40, size=(3, 11, 5), dtype=np.int32)
+    assert (orc.group_point(pts, idx) == orc.refcpu_group_point(pts, idx)).all()
+    go = rng.standard_normal((3, 11, 5, 7)).astype(np.float32)
+    assert (orc.group_point_grad(pts.shape, idx, go) == orc.refcpu_group_point_grad(pts.shape, idx, go)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("n,m", [(128, 1), (128, 2), (512, 128), (300, 77)])
+def test_three_nn_matches_reference_cpu(n, m):
+    xyz1 = make_clouds("shell", 3, n, seed=21)
+    xyz2 = make_clouds("dup", 3, max(m, 4), seed=22)[:, :m, :].copy()
+    od, oi = orc.three_nn(xyz1, xyz2)
+    rd, ri = orc.refcpu_three_nn(xyz1, xyz2)
+    assert (oi == ri).all()
+    assert np.array_equal(od, rd)          # inf == inf for the m<3 slots
+    if m < 3:
+        assert np.isinf(od[..., m:]).all() and (oi[..., m:] == 0).all()
+
+
+@needs_ref
+def test_three_interpolate_and_grad_match_reference_cpu():
+    rng = np.random.default_rng(2)
+    pts = rng.standard_normal((2, 30, 9)).astype(np.float32)
+    idx = rng.integers(0, 30, size=(2, 50, 3), dtype=np.int32)
+    w = rng.random((2, 50, 3), dtype=np.float32)
+    assert np.array_equal(orc.three_interpolate(pts, idx, w), orc.refcpu_three_interpolate(pts, idx, w))
+    go = rng.standard_normal((2, 50, 9)).astype(np.float32)
+    assert np.array_equal(orc.three_interpolate_grad(pts.shape, idx, w, go),
+                          orc.refcpu_three_interpolate_grad(pts.shape, idx, w, go))
+
+
+def test_fps_basic_properties():
+    xyz = make_clouds("ball", 2, 700, seed=1)
+    idx = orc.fps(xyz, 64)
+    assert (idx[:, 0] == 0).all()
+    for b in range(2):
+        assert len(set(idx[b].tolist())) == 64          # distinct while distinct points remain
+    # second pick is the farthest from point 0 (no ties in random data)
+    d = ((xyz - xyz[:, :1]) ** 2).sum(-1)
+    assert (idx[:, 1] == d.argmax(1)).all()
+
+
+def test_fps_tie_key_is_kmod512_then_k():
+    # 1100 points: point 0 at origin, every other point at one of two antipodal spots at equal
+    # distance -> all maxima tie; the reference's winner is min over (k mod 512, k).
+    n = 1100
+    xyz = np.zeros((1, n, 3), np.float32)
+    xyz[0, 1:, 0] = 1.0
+    xyz[0, 600:, 0] = -1.0
+    idx = orc.fps(xyz, 3)
+    # round 1: all k>=1 tie at d=1; slots t=k mod 512: slot 0 holds k=512,1024 -> wins -> 512
+    assert idx[0, 1] == 512
+    # round 2: points at -1 (k>=600) have d=4 from x=+1; candidates k in [600,1100): slot (k mod 512):
+    # k=1024 -> slot 0 -> wins
+    assert idx[0, 2] == 1024
+
+
+def test_dgcnn_knn_self_first_and_sorted():
+    x = make_clouds("ball", 2, 100, seed=4)
+    idx, adj = orc.dgcnn_knn(x, 5, want_adj=True)
+    rows = np.take_along_axis(adj, idx, axis=-1)
+    assert (np.diff(rows, axis=-1) >= 0).all()
+    assert (idx == orc.topk_smallest(adj, 5)).all()
