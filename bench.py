@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- clouds/s of the PointNet++ (SSG) point-set-abstraction forward on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one inference forward of pointnet2_cls_ssg (FPS -> fused ball-query/group/MLP/max-pool x2 ->
+group-all MLP -> FC head, BN in moving-average mode) over one batch of B=32 synthetic clouds of N=2048 points
+(BASELINE.json configs[1]).  Prints ONE JSON line (contract in the task statement):
+  value     clouds/s with the batch already resident in HBM (inputs rotate through a pool > L2);
+  e2e       same metric through the public API with HOST (pinned) buffers: H2D of the batch + forward + D2H logits;
+  roofline  the dominant kernel of the step, timed live with CUDA events on the launching stream;
+  cpu_baseline  the oracle port of the same forward on the host cores, on a bounded sample.
+`--impl reference` times only the CPU arm (there is no runnable TensorFlow here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, N, NUM_CLASS = 32, 2048, 15
+WORKLOAD = "pointnet2_cls_ssg inference forward, B=32 N=2048 K=32/64, 15 classes (BASELINE.json configs[1])"
+METRIC = "point-clouds/sec (B=32, N=2048, 15-class)"
+
+# algorithmic work per step (SURVEY.md 8d / DESIGN.md): fp32 flops of the grouped MLPs per 32-cloud batch
+SA_FLOPS = {"sa1": 2 * 524288 * (3 * 64 + 64 * 64 + 64 * 128), "sa2": 2 * 262144 * (131 * 128 + 128 * 128 + 128 * 256),
+            "sa3": 2 * 4096 * (259 * 256 + 256 * 512 + 512 * 1024)}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def cpu_forward_rate(n_clouds: int, repeats: int = 1):
+    """Oracle port of the SSG forward on the host cores: C restatement (OpenMP) for FPS / ball query / group,
+    numpy fp32 (multi-threaded BLAS) for conv+BN+ReLU+max.  Returns (clouds/s, cores, seconds)."""
+    import numpy as np
+
+    from oracle import mlp_oracle as mo
+    from scanobjectnn_b200 import pointnet2_cls_ssg
+    from scanobjectnn_b200.synthetic import make_clouds
+
+    params = pointnet2_cls_ssg.init_params(seed=1, device="cpu", randomize_bn=True)
+    xyz = make_clouds("ball", n_clouds, N, seed=1001)
+    mo.pointnet2_cls_ssg(xyz[:1], params, dtype=np.float32)          # warm-up (page in BLAS, OpenMP pool)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        mo.pointnet2_cls_ssg(xyz, params, dtype=np.float32)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_clouds / best, os.cpu_count() or 1, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    for _ in range(max(args.warmup, 1)):
+        cpu_forward_rate(1)
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, cores, _ = cpu_forward_rate(sample)
+        rates.append(r)
+    dt = time.perf_counter() - t0
+    value = sum(rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample} of the 32 clouds per step"},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} clouds x {args.steps} steps, oracle port (C/OpenMP index ops + numpy fp32 MLP); "
+                                   "the reference's TF1 path is not installable here"},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from scanobjectnn_b200 import _lib, ops, pointnet2_cls_ssg
+    from scanobjectnn_b200.synthetic import make_clouds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()       # fail loudly if the CUDA library is missing
+
+    params = pointnet2_cls_ssg.init_params(seed=1, device=dev, randomize_bn=True)
+    # input pool larger than L2 (126 MB): 192 distinct batches x 786 KB = 151 MB, rotated every step
+    POOL = 192
+    base = make_clouds("ball", B, N, seed=1001 + rank)
+    rng = np.random.default_rng(rank)
+    pool_host = torch.empty((POOL, B, N, 3), dtype=torch.float32).pin_memory()
+    for i in range(POOL):
+        perm = rng.permutation(N)
+        pool_host[i] = torch.from_numpy(base[:, perm, :])          # same geometry, different point order
+    pool_dev = pool_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def forward(x):
+        logits, _ = pointnet2_cls_ssg.get_model(x, False, params=params)
+        return logits
+
+    # ---- CUDA graph of one step on a static input buffer (launch-bound otherwise: ~14 small launches) ----
+    static_in = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    static_in.copy_(pool_dev[0])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            static_out = forward(static_in)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = forward(static_in)
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        static_in.copy_(pool_dev[i % POOL])        # device->device 786 KB: the rotating "already resident" input
+        graph.replay()
+
+    host_out = torch.empty((B, NUM_CLASS), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        static_in.copy_(pool_host[i % POOL], non_blocking=True)     # H2D from pinned memory
+        graph.replay()
+        host_out.copy_(static_out, non_blocking=True)               # D2H logits
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-stage device times (eager launches, CUDA events on the launching stream) ----
+    stages = {}
+    if rank == 0:
+        from scanobjectnn_b200 import tf_util  # noqa: F401
+        x = pool_dev[1].contiguous()
+        p = params
+        mlp1 = p.mlp([f"layer1/conv{i}" for i in range(3)])
+        mlp2 = p.mlp([f"layer2/conv{i}" for i in range(3)])
+        mlp3 = p.mlp([f"layer3/conv{i}" for i in range(3)])
+        head = p.mlp(["fc1", "fc2", "fc3"], [True, True, False])
+        _, l1_xyz = ops.farthest_point_sample_and_gather(512, x)
+        l1_pts, idx1, _ = ops.sa_module_infer(x, l1_xyz, None, 0.2, 32, mlp1, return_idx=True)
+        _, l2_xyz = ops.farthest_point_sample_and_gather(128, l1_xyz)
+        l2_pts, idx2, _ = ops.sa_module_infer(l1_xyz, l2_xyz, l1_pts, 0.4, 64, mlp2, return_idx=True)
+        l3_in = torch.cat([l2_xyz, l2_pts], dim=2).reshape(B * 128, 259)
+        l3 = ops.shared_mlp(l3_in, mlp3, pool_k=128)
+        cases = {
+            "fps1": lambda: ops.farthest_point_sample_and_gather(512, x),
+            "ballq1": lambda: ops.query_ball_point(0.2, 32, x, l1_xyz),
+            "sa1_mlp": lambda: ops.sa_module_infer(x, l1_xyz, None, 0.2, 32, mlp1, idx=idx1),
+            "fps2": lambda: ops.farthest_point_sample_and_gather(128, l1_xyz),
+            "ballq2": lambda: ops.query_ball_point(0.4, 64, l1_xyz, l2_xyz),
+            "sa2_mlp": lambda: ops.sa_module_infer(l1_xyz, l2_xyz, l1_pts, 0.4, 64, mlp2, idx=idx2),
+            "sa3_mlp": lambda: ops.shared_mlp(l3_in, mlp3, pool_k=128),
+            "head": lambda: ops.shared_mlp(l3, head),
+        }
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > L2
+        for name, fn in cases.items():
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(10):
+                flush.zero_()                       # L2 flush between timed launches
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            stages[name] = ts[len(ts) // 2] * 1e3      # median, us
+        del flush
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    clouds = B * world * args.steps
+    value = clouds / (ms_res * 1e-3)
+    e2e_v = clouds / (ms_e2e * 1e-3)
+    # dominant kernel of the step
+    dom = max(stages, key=stages.get)
+    flops = {"sa1_mlp": SA_FLOPS["sa1"], "sa2_mlp": SA_FLOPS["sa2"], "sa3_mlp": SA_FLOPS["sa3"]}.get(dom)
+    if flops:
+        ach = flops / (stages[dom] * 1e-6) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"] + " bf16 burst",
+                    "note": "fp32 FMA path (1e-5 parity mode); fp32 FMA pipe peak = 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",
+                    "fma_pipe_frac": ach / 74.4}
+    else:
+        fps_bytes = B * (12 * N + 4 * 512)
+        ach = fps_bytes / (stages[dom] * 1e-6) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "traffic": None, "peak_source": peaks["src"], "note": "latency-bound dependent arg-max rounds"}
+    # HBM-class kernels of the metric's second half ("FPS+ballq HBM GB/s")
+    kern = {
+        "fps1": {"us": stages["fps1"], "alg_bytes": B * (12 * N + 4 * 512 + 12 * 512), "ns_per_round": stages["fps1"] * 1e3 / 511},
+        "ballq1": {"us": stages["ballq1"], "alg_bytes": B * (12 * N + 12 * 512 + 4 * 512 * 32 + 4 * 512)},
+        "fps2": {"us": stages["fps2"], "alg_bytes": B * (12 * 512 + 4 * 128 + 12 * 128), "ns_per_round": stages["fps2"] * 1e3 / 127},
+        "ballq2": {"us": stages["ballq2"], "alg_bytes": B * (12 * 512 + 12 * 128 + 4 * 128 * 64 + 4 * 128)},
+    }
+    for k, v in kern.items():
+        v["gbs"] = v["alg_bytes"] / (v["us"] * 1e-6) / 1e9
+        v["hbm_frac"] = v["gbs"] / peaks["hbm"]
+    for k in ("sa1_mlp", "sa2_mlp", "sa3_mlp"):
+        kern[k] = {"us": stages[k], "tflops_fp32": SA_FLOPS[k[:3]] / (stages[k] * 1e-6) / 1e12}
+    kern["head"] = {"us": stages["head"]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, cores, secs = cpu_forward_rate(8)
+        cpu = {"value": rate, "unit": "clouds/s", "cores": cores, "kind": "port",
+               "sample": f"8 of the 32 clouds, one forward ({secs:.1f} s): oracle port = C/OpenMP FPS+ball-query+group, numpy fp32 conv/BN/ReLU/max"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "points": N,
+                   "l2_policy": "inputs larger than L2: 192 distinct 786 KB batches (151 MB) rotated every step",
+                   "mode": "inference (BN moving averages folded); CUDA graph replay of one forward per step",
+                   "parallelism": f"dp{world} (independent batches, no data-path collective)"},
+        "e2e": {"value": e2e_v, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * N * 3 * 4,
+                "d2h_bytes_per_step": B * NUM_CLASS * 4},
+        "gpu_launches": 12 * args.steps,
+        "roofline": roofline,
+        "kernels": kern,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,202 @@
+/*
+ * psa.h -- C ABI of libpsa.so: the B200-native (sm_100a) point-set-abstraction hot path.
+ *
+ * This is the drop-in boundary.  The reference (hkust-vgd/scanobjectnn) reaches its native code through
+ * plain C++ "Launcher" functions called from TensorFlow OpKernel::Compute (raw device pointers + int
+ * dims, caller-owned buffers); every entry point below names the reference interface it replaces.
+ * Reference paths are relative to pointnet2/tf_ops/ unless they start with dgcnn/ or pointnet2/.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer to a dense, contiguous, row-major fp32 / int32 buffer owned by
+ *     the caller; nothing is allocated or freed inside the library; outputs must not alias inputs;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what the
+ *     reference's `<<<grid,block>>>` launches use); calls are asynchronous on that stream;
+ *   - return value: PSA_OK (0); PSA_ERR_INVALID_ARGUMENT (-1) for a shape/attribute the reference's
+ *     OP_REQUIRES would reject (message via psa_last_error()); PSA_ERR_UNSUPPORTED (-2) for a shape
+ *     outside the compiled limits; a positive value is the cudaError_t of a failed launch.  Unlike the
+ *     reference (which never checks), launches are checked with cudaGetLastError();
+ *   - b == 0 or an empty extent is a successful no-op;
+ *   - thread-safe: no global mutable state except the thread-local error string.
+ */
+#ifndef PSA_H_
+#define PSA_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSA_OK 0
+#define PSA_ERR_INVALID_ARGUMENT (-1)
+#define PSA_ERR_UNSUPPORTED (-2)
+
+typedef void* psa_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define PSA_API __attribute__((visibility("default")))
+#else
+#define PSA_API
+#endif
+
+/* library identity / diagnostics */
+PSA_API int psa_version(void);                 /* MAJOR*10000 + MINOR*100 + PATCH */
+PSA_API const char* psa_last_error(void);      /* thread-local, valid until the next failing call on this thread */
+PSA_API int psa_sm_arch(void);                 /* 100: the only architecture compiled in (sm_100a) */
+
+/* ---------------------------------------------------------------------------------------------
+ * sampling/  (tf_sampling.cpp, tf_sampling_g.cu)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Farthest point sampling.  Replaces
+ *   void farthestpointsamplingLauncher(int b,int n,int m,const float* inp,float* temp,int* out)
+ *   (sampling/tf_sampling.cpp:94, kernel tf_sampling_g.cu:105-170; op FarthestPointSample :28-40).
+ * xyz (b,n,3) -> idx (b,m) int32; seed index 0; ties between equal maxima resolved exactly as the
+ * reference's 512-thread strided scan + tree do: minimum over (k mod 512, k).  No `temp` scratch is
+ * needed (running distances live in registers).  If new_xyz != NULL the gather of the sampled points
+ * (GatherPoint, below) is fused: new_xyz (b,m,3).  Requires n >= 1 when m >= 1; m may exceed n. */
+PSA_API int psa_farthest_point_sample(int b, int n, int m, const float* xyz, int* idx, float* new_xyz,
+                              psa_stream_t stream);
+
+/* Replaces gatherpointLauncher (sampling/tf_sampling.cpp:125, tf_sampling_g.cu:172-181).
+ * inp (b,n,3), idx (b,m) -> out (b,m,3). */
+PSA_API int psa_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, psa_stream_t stream);
+
+/* Replaces cudaMemset + scatteraddpointLauncher (sampling/tf_sampling.cpp:150,174; tf_sampling_g.cu:183-192).
+ * out_g (b,m,3), idx (b,m) -> inp_g (b,n,3); inp_g is zeroed by this call, then scatter-added. */
+PSA_API int psa_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g,
+                          psa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * grouping/  (tf_grouping.cpp, tf_grouping_g.cu)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces queryBallPointLauncher (grouping/tf_grouping.cpp:66, tf_grouping_g.cu:3-36; op QueryBallPoint :13-30).
+ * xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample), pts_cnt (b,m).
+ * First `nsample` points in index order with max(sqrtf(d2),1e-20f) < radius; unused slots repeat the
+ * first hit.  A query with an empty ball gets idx row = 0 and pts_cnt = 0 (the reference leaves that
+ * row uninitialised).  pts_cnt may be NULL. */
+PSA_API int psa_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                         int* idx, int* pts_cnt, psa_stream_t stream);
+
+/* Replaces groupPointLauncher (grouping/tf_grouping.cpp:142, tf_grouping_g.cu:40-57).
+ * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */
+PSA_API int psa_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out,
+                    psa_stream_t stream);
+
+/* Replaces cudaMemset + groupPointGradLauncher (grouping/tf_grouping.cpp:173,204; tf_grouping_g.cu:61-78).
+ * grad_out (b,m,nsample,c), idx -> grad_points (b,n,c), zeroed by this call first. */
+PSA_API int psa_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
+                         float* grad_points, psa_stream_t stream);
+
+/* Replaces selectionSortLauncher (grouping/tf_grouping.cpp:108, tf_grouping_g.cu:83-123; op SelectionSort).
+ * dist (b,m,n) -> outi (b,m,n) int32, out (b,m,n): full copies whose first k slots per row hold the k
+ * smallest, produced by the reference's swap-based partial selection sort (ties by current position). */
+PSA_API int psa_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, psa_stream_t stream);
+
+/* knn_point (grouping/tf_grouping.py:49-74) without the (b,m,n) matrices: xyz1 (b,n,c) dataset,
+ * xyz2 (b,m,c) queries -> val (b,m,k), idx (b,m,k); same distances (sum_c (a-b)^2, sequential,
+ * un-contracted) and the same swap-based tie order as SelectionSort. */
+PSA_API int psa_knn_point(int b, int n, int m, int c, int k, const float* xyz1, const float* xyz2, float* val, int* idx,
+                  psa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3d_interpolation/  (tf_interpolate.cpp -- CPU-only ops in the reference)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces threenn_cpu (3d_interpolation/tf_interpolate.cpp:60-103; op ThreeNN :12-21).
+ * xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) SQUARED distances ascending, idx (b,n,3).
+ * Strict-< cascade (earlier k wins ties); slots beyond m are dist=+inf, idx=0. */
+PSA_API int psa_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx,
+                 psa_stream_t stream);
+
+/* Replaces threeinterpolate_cpu (tf_interpolate.cpp:107-127).
+ * points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c) = (p1*w1 + p2*w2) + p3*w3. */
+PSA_API int psa_three_interpolate(int b, int m, int c, int n, const float* points, const int* idx, const float* weight,
+                          float* out, psa_stream_t stream);
+
+/* Replaces memset + threeinterpolate_grad_cpu (tf_interpolate.cpp:131-153,258).
+ * grad_out (b,n,c), idx, weight -> grad_points (b,m,c), zeroed by this call first. */
+PSA_API int psa_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx,
+                               const float* weight, float* grad_points, psa_stream_t stream);
+
+/* The interpolation half of pointnet_fp_module (pointnet2/utils/pointnet_util.py:211-216) in one launch:
+ * three_nn -> dist=max(dist,1e-10) -> w=(1/dist)/sum(1/dist) -> three_interpolate.
+ * Optional outputs dist/idx/weight (b,n,3) may be NULL. */
+PSA_API int psa_three_nn_interpolate(int b, int n, int m, int c, const float* xyz1, const float* xyz2,
+                             const float* points2, float* out, float* dist, int* idx, float* weight,
+                             psa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dgcnn graph functions  (dgcnn/utils/tf_util.py:638-706 -- TF library ops in the reference)
+ * ------------------------------------------------------------------------------------------- */
+
+/* pairwise_distance (dgcnn/utils/tf_util.py:638-657): x (b,n,c) -> adj (b,n,n),
+ * adj = (|x_i|^2 + (-2 x_i.x_j)) + |x_j|^2 with fma chains over c (canonical order, oracle/psa_oracle.c). */
+PSA_API int psa_pairwise_distance(int b, int n, int c, const float* x, float* adj, psa_stream_t stream);
+
+/* knn (dgcnn/utils/tf_util.py:660-671): adj (b,n,ncols) -> nn_idx (b,n,k): top_k(-adj), ascending adj,
+ * lower index first on ties. */
+PSA_API int psa_knn_topk(int b, int n, int ncols, int k, const float* adj, int* nn_idx, psa_stream_t stream);
+
+/* pairwise_distance + knn fused, never materialising (b,n,n): x (b,n,c) -> nn_idx (b,n,k). */
+PSA_API int psa_knn_graph(int b, int n, int c, int k, const float* x, int* nn_idx, psa_stream_t stream);
+
+/* get_edge_feature (dgcnn/utils/tf_util.py:674-706): x (b,n,c), nn_idx (b,n,k) -> (b,n,k,2c) = [x_i, x_j-x_i]. */
+PSA_API int psa_get_edge_feature(int b, int n, int c, int k, const float* x, const int* nn_idx, float* out,
+                         psa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * grouped shared MLP  (pointnet2/utils/pointnet_util.py:87-154, tf_util.conv2d 1x1 + BN + ReLU,
+ * dgcnn EdgeConv dgcnn/models/dgcnn.py:31-80) -- TF/cuDNN library ops in the reference
+ * ------------------------------------------------------------------------------------------- */
+
+/* One per-row shared MLP: up to PSA_MAX_MLP_LAYERS layers of  y = relu?( (x . W) * scale + shift ).
+ *   channels[0..n_layers]   C_0 (input) ... C_L
+ *   weight[l]  (C_l, C_{l+1}) row-major  == TF conv kernel (1,1,C_in,C_out) (tf_util.py:162-168)
+ *   scale[l], shift[l]  (C_{l+1}): conv bias + inference-mode batch norm folded by the caller:
+ *        scale = gamma / sqrt(moving_var + 1e-3),  shift = (bias - moving_mean) * scale + beta
+ *        (no BN: scale = 1, shift = bias);  scale[l] may be NULL (= all ones)
+ *   relu[l]    nonzero -> ReLU after layer l */
+#define PSA_MAX_MLP_LAYERS 4
+typedef struct psa_mlp {
+    int n_layers;
+    int channels[PSA_MAX_MLP_LAYERS + 1];
+    const float* weight[PSA_MAX_MLP_LAYERS];
+    const float* scale[PSA_MAX_MLP_LAYERS];
+    const float* shift[PSA_MAX_MLP_LAYERS];
+    int relu[PSA_MAX_MLP_LAYERS];
+} psa_mlp;
+
+/* Dense rows: x (rows, C_0) -> out.  pool_k == 1: out (rows, C_L).  pool_k > 1: rows must be a multiple
+ * of pool_k and out (rows/pool_k, C_L) = channel-wise max over each run of pool_k consecutive rows
+ * (tf.reduce_max over nsample, pointnet_util.py:127); pool_k must divide 128 (>= 8) or be a multiple of 128.
+ * Used for sample_and_group_all (SA3), FP-module convs, DGCNN's point-wise convs and the FC heads.
+ * Layers run one launch each; the (rows, C_l) intermediates ping-pong through the caller's workspace of
+ * psa_shared_mlp_workspace_bytes(rows, mlp) bytes (0 for a single layer; workspace may then be NULL). */
+PSA_API size_t psa_shared_mlp_workspace_bytes(long long rows, const psa_mlp* mlp);
+PSA_API int psa_shared_mlp(long long rows, int pool_k, const float* x, const psa_mlp* mlp, float* out,
+                           void* workspace, size_t workspace_bytes, psa_stream_t stream);
+
+/* Fused set-abstraction level, inference mode (pointnet_sa_module, pointnet_util.py:87-154 with
+ * sample_and_group :22-56 inside): for every query j of new_xyz
+ *   idx_j  = query_ball_point(radius, nsample, xyz, new_xyz)[j]           (or caller-provided idx)
+ *   row_k  = [ xyz[idx_jk] - new_xyz[j]  ,  points[idx_jk] ]               (xyz first, :46-50)
+ *   out_j  = max_k  MLP(row_k)
+ * without materialising the (b,m,nsample,3+c) tensor.  xyz (b,n,3), new_xyz (b,m,3), points (b,n,c) or
+ * NULL with c = 0, mlp->channels[0] must equal 3 + c.  out (b,m,C_L).
+ * idx_in  != NULL: use these neighbourhoods (b,m,nsample) instead of searching;
+ * idx_out != NULL / pts_cnt != NULL: also write the ball-query result. */
+PSA_API int psa_sa_module_infer(int b, int n, int m, int c, float radius, int nsample, const float* xyz,
+                        const float* new_xyz, const float* points, const int* idx_in, const psa_mlp* mlp,
+                        float* out, int* idx_out, int* pts_cnt, psa_stream_t stream);
+
+/* Fused EdgeConv, inference mode (dgcnn/models/dgcnn.py:31-47 pattern): x (b,n,c), nn_idx (b,n,k) ->
+ * out (b,n,C_L) = max_j MLP([x_i, x_j - x_i]); mlp->channels[0] must equal 2c. */
+PSA_API int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
+                       float* out, psa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSA_H_ */

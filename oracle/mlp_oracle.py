@@ -1,0 +1,104 @@
+"""CPU restatement of the TF-library half of the hot path: 1x1 conv + bias + batch norm (inference) + ReLU +
+max-pool, and the model assemblies built from it.  TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+
+PARITY UNPINNED: this arithmetic lives in TensorFlow 1.x (cuDNN conv, contrib batch_norm), which is not part of
+/root/reference and not installable here; the reference holds no golden vectors for it.  What is restated is the
+published semantics at the reference's call sites:
+  conv2d 1x1 + bias_add          pointnet2/utils/tf_util.py:155-176  (NHWC matmul over the channel axis)
+  batch_norm, is_training=False  pointnet2/utils/tf_util.py:512-531  -> (x-mean)*gamma*rsqrt(var+1e-3)+beta
+  relu                           pointnet2/utils/tf_util.py:183-184
+  reduce_max over nsample        pointnet2/utils/pointnet_util.py:127
+The fp64 evaluation is the truth the CUDA path is held to (1e-5); the fp32 one is the "plain fp32" comparison.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as orc
+
+BN_EPS = 1e-3
+
+
+def _np(t, dtype):
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().numpy()
+    return np.asarray(t, dtype=dtype)
+
+
+def conv_bn_relu(x, params, scope, relu=True, dtype=np.float64):
+    """x (..., Cin) -> (..., Cout) for the layer stored under ``scope`` (TF variable names)."""
+    w = _np(params[f"{scope}/weights"], dtype)
+    w = w.reshape(-1, w.shape[-1])
+    y = x.astype(dtype) @ w + _np(params[f"{scope}/biases"], dtype)
+    if f"{scope}/bn/gamma" in params:
+        inv = _np(params[f"{scope}/bn/gamma"], dtype) / np.sqrt(_np(params[f"{scope}/bn/moving_variance"], dtype) + dtype(BN_EPS))
+        y = (y - _np(params[f"{scope}/bn/moving_mean"], dtype)) * inv + _np(params[f"{scope}/bn/beta"], dtype)
+    if relu:
+        y = np.maximum(y, 0)
+    return y
+
+
+def mlp_chain(x, params, scopes, relus=None, dtype=np.float64):
+    relus = relus or [True] * len(scopes)
+    for s, r in zip(scopes, relus):
+        x = conv_bn_relu(x, params, s, r, dtype)
+    return x
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points):
+    """pointnet_util.sample_and_group (pointnet_util.py:22-56) on the C oracle ops."""
+    idx_fps = orc.fps(xyz, npoint)
+    new_xyz = orc.gather_point(xyz, idx_fps)
+    idx, cnt = orc.query_ball_point(radius, nsample, xyz, new_xyz, contract=True)
+    grouped_xyz = orc.group_point(xyz, idx) - new_xyz[:, :, None, :]
+    if points is not None:
+        new_points = np.concatenate([grouped_xyz, orc.group_point(points, idx)], axis=-1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, idx_fps
+
+
+def sa_module(xyz, points, npoint, radius, nsample, mlp, group_all, scope, params, dtype=np.float64):
+    """pointnet_sa_module (pointnet_util.py:87-154), inference, pooling='max'."""
+    scopes = [f"{scope}/conv{i}" for i in range(len(mlp))]
+    if group_all:
+        new_xyz = np.zeros((xyz.shape[0], 1, 3), np.float32)
+        new_points = (np.concatenate([xyz, points], axis=2) if points is not None else xyz)[:, None]
+        idx = None
+    else:
+        new_xyz, new_points, idx, _ = sample_and_group(npoint, radius, nsample, xyz, points)
+    y = mlp_chain(new_points, params, scopes, dtype=dtype)
+    return new_xyz, y.max(axis=2).astype(dtype), idx
+
+
+def fp_module(xyz1, xyz2, points1, points2, mlp, scope, params, dtype=np.float64):
+    """pointnet_fp_module (pointnet_util.py:199-229), inference."""
+    dist, idx = orc.three_nn(xyz1, xyz2)
+    w = orc.three_weights(dist)
+    interp = orc.three_interpolate(np.asarray(points2, np.float32), idx, w)
+    x = np.concatenate([interp, points1], axis=2) if points1 is not None else interp
+    return mlp_chain(x, params, [f"{scope}/conv_{i}" for i in range(len(mlp))], dtype=dtype)
+
+
+def pointnet2_cls_ssg(point_cloud, params, dtype=np.float64):
+    """pointnet2/models/pointnet2_cls_ssg.py:23-47, is_training=False -> logits, end_points."""
+    xyz = np.asarray(point_cloud, np.float32)
+    l1_xyz, l1_points, l1_idx = sa_module(xyz, None, 512, 0.2, 32, [64, 64, 128], False, "layer1", params, dtype)
+    l2_xyz, l2_points, l2_idx = sa_module(l1_xyz, l1_points.astype(np.float32), 128, 0.4, 64, [128, 128, 256], False,
+                                          "layer2", params, dtype)
+    _, l3_points, _ = sa_module(l2_xyz, l2_points.astype(np.float32), None, None, None, [256, 512, 1024], True,
+                                "layer3", params, dtype)
+    net = l3_points.reshape(xyz.shape[0], -1)
+    net = mlp_chain(net, params, ["fc1", "fc2", "fc3"], [True, True, False], dtype)
+    return net, dict(l1_xyz=l1_xyz, l1_points=l1_points, l1_idx=l1_idx, l2_xyz=l2_xyz, l2_points=l2_points,
+                     l2_idx=l2_idx, l3_points=l3_points)
+
+
+def edgeconv(x, nn_idx, params, scopes, dtype=np.float64):
+    """get_edge_feature + conv chain + max over k (dgcnn/utils/tf_util.py:674-706, dgcnn.py:41-47)."""
+    x = np.asarray(x, np.float32)
+    b, n, c = x.shape
+    nb = x[np.arange(b)[:, None, None], np.asarray(nn_idx, np.int64)]
+    ctr = np.broadcast_to(x[:, :, None, :], nb.shape)
+    edge = np.concatenate([ctr, nb - ctr], axis=-1)
+    return mlp_chain(edge, params, scopes, dtype=dtype).max(axis=2)

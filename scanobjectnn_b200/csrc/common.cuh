@@ -1,0 +1,74 @@
+// common.cuh -- shared helpers for libpsa.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/psa.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpsa is written for sm_100a (B200) only"
+#endif
+
+namespace psa {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return PSA_OK;
+}
+
+#define PSA_REQUIRE(cond, ...)                \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::psa::set_error(__VA_ARGS__);    \
+            return PSA_ERR_INVALID_ARGUMENT;  \
+        }                                     \
+    } while (0)
+
+#define PSA_SUPPORTED(cond, ...)              \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::psa::set_error(__VA_ARGS__);    \
+            return PSA_ERR_UNSUPPORTED;       \
+        }                                     \
+    } while (0)
+
+#define PSA_CUDA(call)                                                      \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) {                                            \
+            ::psa::set_error("%s: %s", #call, cudaGetErrorString(e_));      \
+            return (int)e_;                                                 \
+        }                                                                   \
+    } while (0)
+
+static inline cudaStream_t as_stream(psa_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Squared distance exactly as the reference's CUDA kernels evaluate it after nvcc's FMA contraction
+// (SASS of tf_sampling_g.cu / tf_grouping_g.cu: FMUL dy*dy ; FFMA dx,dx ; FFMA dz,dz).
+__device__ __forceinline__ float dist2_ref_gpu(float dx, float dy, float dz) {
+    float t = __fmul_rn(dy, dy);
+    t = __fmaf_rn(dx, dx, t);
+    t = __fmaf_rn(dz, dz, t);
+    return t;
+}
+// Squared distance exactly as the reference's CPU ops (x86-64, no FMA) evaluate it: (dx*dx+dy*dy)+dz*dz.
+__device__ __forceinline__ float dist2_ref_cpu(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace psa

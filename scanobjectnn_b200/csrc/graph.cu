@@ -1,0 +1,230 @@
+// graph.cu -- DGCNN graph functions for sm_100a: pairwise_distance, knn (top-k), the fused kNN graph that never
+// materialises the (B,N,N) matrix, and get_edge_feature.
+//
+// Reference: dgcnn/utils/tf_util.py:638-706 -- tf.matmul + reduce_sum + transpose (a (B,N,N) fp32 matrix, 512 MiB at
+// B=32,N=2048, written and read back five times per forward), tf.nn.top_k, tf.gather/tile/concat.
+// Arithmetic contract (the reference's cuBLAS/top_k order is unpinned; canonical order shared with
+// oracle/psa_oracle.c:orc_dgcnn_knn):  dot = fma chain over c ascending from 0;  sq = fma chain likewise;
+// adj = (sq_i + (-2*dot)) + sq_j;  neighbours ascending by (adj, index), self included.
+#include "common.cuh"
+
+namespace psa {
+
+constexpr int kPdTile = 64;      // 64x64 outputs per CTA, 256 threads, 4x4 per thread
+constexpr int kPdCk = 32;        // channels staged per step
+
+__global__ void __launch_bounds__(256)
+pairwise_distance_kernel(int n, int c, const float* __restrict__ x, float* __restrict__ adj) {
+    __shared__ float Xi[kPdTile][kPdCk + 1];
+    __shared__ float Xj[kPdTile][kPdCk + 1];
+    const int cloud = blockIdx.z;
+    const int i0 = blockIdx.y * kPdTile, j0 = blockIdx.x * kPdTile;
+    const float* xb = x + (size_t)cloud * n * c;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float dot[4][4], sqi[4], sqj[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        sqi[a] = sqj[a] = 0.f;
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) dot[a][b2] = 0.f;
+    }
+    for (int c0 = 0; c0 < c; c0 += kPdCk) {
+        const int cc = min(kPdCk, c - c0);
+        __syncthreads();
+        for (int s = threadIdx.x; s < kPdTile * kPdCk; s += 256) {
+            int r = s / kPdCk, l = s - r * kPdCk;
+            Xi[r][l] = (i0 + r < n && l < cc) ? __ldg(xb + (size_t)(i0 + r) * c + c0 + l) : 0.f;
+            Xj[r][l] = (j0 + r < n && l < cc) ? __ldg(xb + (size_t)(j0 + r) * c + c0 + l) : 0.f;
+        }
+        __syncthreads();
+        for (int l = 0; l < cc; ++l) {
+            float ai[4], bj[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { ai[a] = Xi[ty + 16 * a][l]; bj[a] = Xj[tx + 16 * a][l]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                sqi[a] = __fmaf_rn(ai[a], ai[a], sqi[a]);
+                sqj[a] = __fmaf_rn(bj[a], bj[a], sqj[a]);
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) dot[a][b2] = __fmaf_rn(ai[a], bj[b2], dot[a][b2]);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) {
+            const int j = j0 + tx + 16 * b2;
+            if (j < n)
+                adj[((size_t)cloud * n + i) * n + j] = __fadd_rn(__fadd_rn(sqi[a], __fmul_rn(-2.0f, dot[a][b2])), sqj[b2]);
+        }
+    }
+}
+
+// k rounds of "smallest (value, index) strictly greater than the last pick" over a row resident in shared memory
+__device__ __forceinline__ void topk_rounds(const float* row, int ncols, int k, int* __restrict__ out, int lane) {
+    float lv = 0.f;
+    int li = -1;
+    for (int s = 0; s < k; ++s) {
+        float bv = 0.f;
+        int bi = -1;
+        for (int t = lane; t < ncols; t += 32) {
+            const float v = row[t];
+            const bool after = (li < 0) || (v > lv) || (v == lv && t > li);
+            if (after && (bi < 0 || v < bv)) { bv = v; bi = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) out[s] = bi < 0 ? 0 : bi;
+        lv = bv; li = bi;
+    }
+}
+
+constexpr int kTopkWarps = 4;
+
+__global__ void __launch_bounds__(kTopkWarps * 32)
+knn_topk_kernel(long long rows, int ncols, int k, const float* __restrict__ adj, int* __restrict__ nn_idx) {
+    extern __shared__ float smem_f[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* row = smem_f + (size_t)warp * ncols;
+    for (long long r = (long long)blockIdx.x * kTopkWarps + warp; r < rows; r += (long long)gridDim.x * kTopkWarps) {
+        for (int t = lane; t < ncols; t += 32) row[t] = __ldg(adj + r * ncols + t);
+        __syncwarp();
+        topk_rounds(row, ncols, k, nn_idx + r * k, lane);
+        __syncwarp();
+    }
+}
+
+// Fused kNN graph, first version: CTA = 8 queries of one cloud (one per warp); candidate points are staged through
+// shared memory 32 at a time; each lane owns one candidate per tile and forms the fma-chain dot product with its
+// warp's query (query row broadcast from shared memory); the adj row accumulates in the warp's shared row buffer.
+constexpr int kKgWarps = 8;
+
+__global__ void __launch_bounds__(kKgWarps * 32)
+knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restrict__ nn_idx) {
+    extern __shared__ float smem_f[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.y;
+    const int q0 = blockIdx.x * kKgWarps;
+    const int cp = c + 1;
+    float* rows = smem_f;                               // kKgWarps * n
+    float* qv = rows + (size_t)kKgWarps * n;             // kKgWarps * c
+    float* tile = qv + (size_t)kKgWarps * c;             // 32 * (c+1)
+    float* tsq = tile + 32 * cp;                         // 32
+    const float* xb = x + (size_t)cloud * n * c;
+    const int q = q0 + warp;
+    const bool active = q < n;
+    float sq_q = 0.f;
+    if (active) {
+        for (int l = lane; l < c; l += 32) qv[warp * c + l] = __ldg(xb + (size_t)q * c + l);
+        __syncwarp();
+        for (int l = 0; l < c; ++l) sq_q = __fmaf_rn(qv[warp * c + l], qv[warp * c + l], sq_q);
+    }
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        __syncthreads();
+        for (int s = threadIdx.x; s < 32 * c; s += kKgWarps * 32) {
+            int r = s / c, l = s - r * c;
+            tile[r * cp + l] = (j0 + r < n) ? __ldg(xb + (size_t)(j0 + r) * c + l) : 0.f;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float s = 0.f;
+            for (int l = 0; l < c; ++l) s = __fmaf_rn(tile[lane * cp + l], tile[lane * cp + l], s);
+            tsq[lane] = s;
+        }
+        __syncthreads();
+        if (active && j0 + lane < n) {
+            float dot = 0.f;
+            const float* tj = tile + lane * cp;
+            const float* qq = qv + warp * c;
+            for (int l = 0; l < c; ++l) dot = __fmaf_rn(qq[l], tj[l], dot);
+            rows[(size_t)warp * n + j0 + lane] = __fadd_rn(__fadd_rn(sq_q, __fmul_rn(-2.0f, dot)), tsq[lane]);
+        }
+    }
+    __syncwarp();
+    if (active) topk_rounds(rows + (size_t)warp * n, n, k, nn_idx + ((size_t)cloud * n + q) * k, lane);
+}
+
+// edge[b,i,j,:] = [x_i, x_{nn(i,j)} - x_i]
+__global__ void edge_feature_kernel(int n, int c, int k, long long total, const float* __restrict__ x,
+                                    const int* __restrict__ nn_idx, float* __restrict__ out) {
+    const int c2 = 2 * c;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long row = e / c2;           // (b*n + i)*k + j
+        int l = (int)(e - row * c2);
+        long long pi = row / k;           // b*n + i
+        long long bi = pi / n;
+        if (l < c) {
+            out[e] = __ldg(x + pi * c + l);
+        } else {
+            int j = __ldg(nn_idx + row);
+            out[e] = __ldg(x + (bi * n + j) * c + (l - c)) - __ldg(x + pi * c + (l - c));
+        }
+    }
+}
+
+static inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    long long cap = (long long)kNumSMs * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace psa
+
+using namespace psa;
+
+extern "C" int psa_pairwise_distance(int b, int n, int c, const float* x, float* adj, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0, "pairwise_distance: negative dimension");
+    if (b == 0 || n == 0) return PSA_OK;
+    PSA_REQUIRE((x || c == 0) && adj, "pairwise_distance: null buffer");
+    PSA_SUPPORTED(b <= 65535, "pairwise_distance: b=%d exceeds gridDim.z", b);
+    dim3 grid((n + kPdTile - 1) / kPdTile, (n + kPdTile - 1) / kPdTile, b);
+    pairwise_distance_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, c, x, adj);
+    return check_launch("pairwise_distance_kernel");
+}
+
+extern "C" int psa_knn_topk(int b, int n, int ncols, int k, const float* adj, int* nn_idx, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && ncols >= 0 && k >= 0, "knn: negative dimension");
+    PSA_REQUIRE(k <= ncols, "knn: k=%d exceeds the row length %d (tf.nn.top_k: input must have at least k columns)", k, ncols);
+    long long rows = (long long)b * n;
+    if (rows == 0 || k == 0) return PSA_OK;
+    PSA_REQUIRE(adj && nn_idx, "knn: null buffer");
+    size_t smem = (size_t)kTopkWarps * ncols * sizeof(float);
+    PSA_SUPPORTED(smem <= 200 * 1024, "knn: row length %d exceeds the shared-memory resident limit", ncols);
+    PSA_CUDA(cudaFuncSetAttribute(knn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((rows + kTopkWarps - 1) / kTopkWarps);
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    knn_topk_kernel<<<grid, kTopkWarps * 32, smem, as_stream(stream)>>>(rows, ncols, k, adj, nn_idx);
+    return check_launch("knn_topk_kernel");
+}
+
+extern "C" int psa_knn_graph(int b, int n, int c, int k, const float* x, int* nn_idx, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0 && k >= 0, "knn_graph: negative dimension");
+    PSA_REQUIRE(k <= n || b == 0, "knn_graph: k=%d exceeds the number of points n=%d", k, n);
+    if (b == 0 || n == 0 || k == 0) return PSA_OK;
+    PSA_REQUIRE((x || c == 0) && nn_idx, "knn_graph: null buffer");
+    PSA_SUPPORTED(b <= 65535, "knn_graph: b=%d exceeds gridDim.y", b);
+    size_t smem = ((size_t)kKgWarps * n + (size_t)kKgWarps * c + 32 * (size_t)(c + 1) + 32) * sizeof(float);
+    PSA_SUPPORTED(smem <= 200 * 1024, "knn_graph: n=%d, c=%d exceed the shared-memory resident limit", n, c);
+    PSA_CUDA(cudaFuncSetAttribute(knn_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n + kKgWarps - 1) / kKgWarps, b);
+    knn_graph_kernel<<<grid, kKgWarps * 32, smem, as_stream(stream)>>>(n, c, k, x, nn_idx);
+    return check_launch("knn_graph_kernel");
+}
+
+extern "C" int psa_get_edge_feature(int b, int n, int c, int k, const float* x, const int* nn_idx, float* out,
+                                    psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0 && k >= 0, "get_edge_feature: negative dimension");
+    long long total = (long long)b * n * k * 2 * c;
+    if (total == 0) return PSA_OK;
+    PSA_REQUIRE(x && nn_idx && out, "get_edge_feature: null buffer");
+    edge_feature_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(n, c, k, total, x, nn_idx, out);
+    return check_launch("edge_feature_kernel");
+}

@@ -1,0 +1,302 @@
+// grouping.cu -- ball query, group_point (+grad), SelectionSort / knn_point for sm_100a.
+//
+// Replaces pointnet2/tf_ops/grouping/tf_grouping_g.cu of the reference (one CTA per cloud, one thread per
+// query walking all n points from global memory).  Here: the cloud's coordinates are staged once per CTA in
+// shared memory as SoA, one WARP owns a query and tests 32 consecutive points per step, and the reference's
+// "first nsample in index order" rule is kept by ballot + prefix-popcount compaction, tiles consumed in
+// ascending order, with a per-query early exit.  The sqrt of the reference's `max(sqrtf(d2),1e-20f) < r` test
+// is hoisted to the host: sqrtf is monotone, so the test equals `!(d2 > T)` with T the largest float whose
+// correctly-rounded sqrt is < r (NaN d2 counts as inside, exactly like CUDA's max(NaN,1e-20f) = 1e-20f < r).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace psa {
+
+// Largest t >= 0 with sqrtf(t) < r, or `none` when no distance can satisfy max(sqrtf(d2),1e-20f) < r.
+float ball_query_threshold(float radius, bool* none) {
+    *none = !(radius > 1e-20f);   // also catches NaN
+    if (*none) return 0.f;
+    uint32_t lo = 0u, hi = 0x7f7fffffu;   // sqrtf(+0) = 0 < r holds
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo + 1u) / 2u;
+        float t;
+        memcpy(&t, &mid, 4);
+        if (sqrtf(t) < radius) lo = mid; else hi = mid - 1u;
+    }
+    float t;
+    memcpy(&t, &lo, 4);
+    return t;
+}
+
+constexpr int kBqWarps = 8;
+
+// One warp per query.  sx/sy/sz: the cloud's n points in shared memory.  Writes the idx row (global or shared)
+// and returns the clamped count.  Rows with an empty ball are filled with 0.
+__device__ __forceinline__ int ball_query_warp(int n, int nsample, float thr, bool none, const float* sx,
+                                               const float* sy, const float* sz, float qx, float qy, float qz,
+                                               int* idxrow, int lane) {
+    int cnt = 0, first = -1;
+    if (!none) {
+        for (int base = 0; base < n && cnt < nsample; base += 64) {
+            // two 32-point chunks per step for ILP; order preserved (chunk 0 before chunk 1)
+            const int k0 = base + lane, k1 = base + 32 + lane;
+            bool in0 = false, in1 = false;
+            if (k0 < n) {
+                // reference operand order: x2 (query) - x1 (dataset), tf_grouping_g.cu:18-24
+                float d = dist2_ref_gpu(qx - sx[k0], qy - sy[k0], qz - sz[k0]);
+                in0 = !(d > thr);
+            }
+            if (k1 < n) {
+                float d = dist2_ref_gpu(qx - sx[k1], qy - sy[k1], qz - sz[k1]);
+                in1 = !(d > thr);
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, in0);
+            const unsigned b1 = __ballot_sync(0xffffffffu, in1);
+            if ((b0 | b1) == 0u) continue;
+            const unsigned lt = lanemask_lt();
+            const int c0 = __popc(b0);
+            if (first < 0) first = b0 ? (base + __ffs(b0) - 1) : (base + 32 + __ffs(b1) - 1);
+            if (in0) {
+                int pos = cnt + __popc(b0 & lt);
+                if (pos < nsample) idxrow[pos] = k0;
+            }
+            if (in1) {
+                int pos = cnt + c0 + __popc(b1 & lt);
+                if (pos < nsample) idxrow[pos] = k1;
+            }
+            cnt += c0 + __popc(b1);
+        }
+    }
+    if (cnt > nsample) cnt = nsample;
+    const int fillv = first < 0 ? 0 : first;
+    for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = fillv;   // tf_grouping_g.cu:26-29
+    return cnt;
+}
+
+__global__ void __launch_bounds__(kBqWarps * 32)
+ball_query_kernel(int n, int m, int nsample, float thr, int none, int q_per_cta, const float* __restrict__ xyz1,
+                  const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
+    extern __shared__ float smem_f[];
+    float* sx = smem_f;
+    float* sy = sx + n;
+    float* sz = sy + n;
+    const int cloud = blockIdx.y;
+    const float* p1 = xyz1 + (size_t)cloud * n * 3;
+    for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
+        int k = i / 3, c = i - k * 3;
+        float v = p1[i];
+        if (c == 0) sx[k] = v; else if (c == 1) sy[k] = v; else sz[k] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * q_per_cta;
+    const int q1 = min(m, q0 + q_per_cta);
+    const float* p2 = xyz2 + (size_t)cloud * m * 3;
+    for (int q = q0 + warp; q < q1; q += kBqWarps) {
+        const float qx = __ldg(p2 + q * 3 + 0), qy = __ldg(p2 + q * 3 + 1), qz = __ldg(p2 + q * 3 + 2);
+        int* row = idx + ((size_t)cloud * m + q) * nsample;
+        int cnt = ball_query_warp(n, nsample, thr, none != 0, sx, sy, sz, qx, qy, qz, row, lane);
+        if (pts_cnt != nullptr && lane == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
+    }
+}
+
+// out[b,j,k,:] = points[b, idx[b,j,k], :]
+template <typename VT>
+__global__ void group_point_kernel(int n, int cv, long long rows_per_b, long long total, const VT* __restrict__ points,
+                                   const int* __restrict__ idx, VT* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long row = e / cv;
+        int l = (int)(e - row * cv);
+        long long bi = row / rows_per_b;
+        int ii = __ldg(idx + row);
+        out[e] = __ldg(points + (bi * n + ii) * cv + l);
+    }
+}
+
+__global__ void group_point_grad_kernel(int n, int c, long long rows_per_b, long long total,
+                                        const float* __restrict__ grad_out, const int* __restrict__ idx,
+                                        float* __restrict__ grad_points) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long row = e / c;
+        int l = (int)(e - row * c);
+        long long bi = row / rows_per_b;
+        int ii = __ldg(idx + row);
+        atomicAdd(&grad_points[(bi * n + ii) * c + l], grad_out[e]);
+    }
+}
+
+// ---- SelectionSort (tf_grouping_g.cu:83-123): one warp per (b,j) row, row resident in shared memory ----
+// Round s: position of the FIRST strict minimum in [s,n) (the reference starts min=s and scans t>s with '<',
+// so the earliest position among equal minima wins), swap with slot s carrying indices.
+__device__ __forceinline__ void selection_rounds(int n, int k, float* v, int* id, int lane) {
+    for (int s = 0; s < k && s < n; ++s) {
+        // every lane starts from the reference's `min = s`; a NaN at s can never be displaced (x < NaN is false)
+        float best = v[s];
+        int bpos = s;
+        for (int t = s + 1 + lane; t < n; t += 32) {
+            float x = v[t];
+            if (x < best) { best = x; bpos = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+            if (ob < best || (ob == best && op < bpos)) { best = ob; bpos = op; }
+        }
+        if (lane == 0 && bpos != s) {
+            float tv = v[bpos]; v[bpos] = v[s]; v[s] = tv;
+            int ti = id[bpos]; id[bpos] = id[s]; id[s] = ti;
+        }
+        __syncwarp();
+    }
+}
+
+constexpr int kSelWarps = 4;
+
+__global__ void __launch_bounds__(kSelWarps * 32)
+selection_sort_kernel(long long rows, int n, int k, const float* __restrict__ dist, int* __restrict__ outi,
+                      float* __restrict__ out) {
+    extern __shared__ float smem_f[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* v = smem_f + (size_t)warp * n * 2;
+    int* id = reinterpret_cast<int*>(v + n);
+    for (long long r = (long long)blockIdx.x * kSelWarps + warp; r < rows; r += (long long)gridDim.x * kSelWarps) {
+        const float* d = dist + r * n;
+        for (int t = lane; t < n; t += 32) { v[t] = d[t]; id[t] = t; }
+        __syncwarp();
+        selection_rounds(n, k, v, id, lane);
+        for (int t = lane; t < n; t += 32) { out[r * n + t] = v[t]; outi[r * n + t] = id[t]; }
+        __syncwarp();
+    }
+}
+
+// knn_point (tf_grouping.py:49-74) fused: distances sum_c (x1-x2)^2 (sequential, un-contracted) built straight
+// into the warp's shared-memory row, then the same selection rounds; only the first k are written.
+__global__ void __launch_bounds__(kSelWarps * 32)
+knn_point_kernel(int n, int m, int c, int k, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                 float* __restrict__ val, int* __restrict__ idx, long long rows) {
+    extern __shared__ float smem_f[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* v = smem_f + (size_t)warp * n * 2;
+    int* id = reinterpret_cast<int*>(v + n);
+    for (long long r = (long long)blockIdx.x * kSelWarps + warp; r < rows; r += (long long)gridDim.x * kSelWarps) {
+        const long long bi = r / m;
+        const float* q = xyz2 + r * c;
+        const float* p = xyz1 + bi * n * c;
+        for (int t = lane; t < n; t += 32) {
+            float s = 0.f;
+            for (int l = 0; l < c; ++l) {
+                float df = __fsub_rn(__ldg(p + (size_t)t * c + l), __ldg(q + l));
+                s = __fadd_rn(s, __fmul_rn(df, df));
+            }
+            v[t] = s; id[t] = t;
+        }
+        __syncwarp();
+        selection_rounds(n, k, v, id, lane);
+        for (int t = lane; t < k; t += 32) { val[r * k + t] = v[t]; idx[r * k + t] = id[t]; }
+        __syncwarp();
+    }
+}
+
+static inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    long long cap = (long long)kNumSMs * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace psa
+
+using namespace psa;
+
+extern "C" int psa_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                                    const float* xyz2, int* idx, int* pts_cnt, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && m >= 0, "QueryBallPoint: negative dimension (b=%d n=%d m=%d)", b, n, m);
+    PSA_REQUIRE(nsample >= 0, "QueryBallPoint: nsample=%d", nsample);
+    if (b == 0 || m == 0) return PSA_OK;
+    PSA_REQUIRE(idx != nullptr || nsample == 0, "QueryBallPoint: null idx");
+    PSA_REQUIRE((xyz1 != nullptr || n == 0) && xyz2 != nullptr, "QueryBallPoint: null input");
+    size_t smem = (size_t)n * 3 * sizeof(float);
+    PSA_SUPPORTED(smem <= 200 * 1024, "query_ball_point: n=%d exceeds the shared-memory resident limit", n);
+    bool none = false;
+    float thr = ball_query_threshold(radius, &none);
+    // enough CTAs for ~2 waves of 148 SMs, at least one warp-batch of queries per CTA
+    int chunks = (2 * kNumSMs + b - 1) / b;
+    int q_per_cta = (m + chunks - 1) / chunks;
+    q_per_cta = ((q_per_cta + kBqWarps - 1) / kBqWarps) * kBqWarps;
+    if (q_per_cta < 2 * kBqWarps) q_per_cta = 2 * kBqWarps;
+    dim3 grid((m + q_per_cta - 1) / q_per_cta, b);
+    PSA_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ball_query_kernel<<<grid, kBqWarps * 32, smem, as_stream(stream)>>>(n, m, nsample, thr, none ? 1 : 0, q_per_cta,
+                                                                       xyz1, xyz2, idx, pts_cnt);
+    return check_launch("ball_query_kernel");
+}
+
+extern "C" int psa_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx,
+                               float* out, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0, "GroupPoint: negative dimension");
+    long long rows_per_b = (long long)m * nsample;
+    long long total = (long long)b * rows_per_b * c;
+    if (total == 0) return PSA_OK;
+    PSA_REQUIRE(points && idx && out, "GroupPoint: null buffer");
+    cudaStream_t st = as_stream(stream);
+    bool vec = (c % 4 == 0) && ((uintptr_t)points % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    if (vec) {
+        long long tv = total / 4;
+        group_point_kernel<float4><<<grid_for(tv, 256), 256, 0, st>>>(n, c / 4, rows_per_b, tv,
+                                                                      reinterpret_cast<const float4*>(points), idx,
+                                                                      reinterpret_cast<float4*>(out));
+    } else {
+        group_point_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(n, c, rows_per_b, total, points, idx, out);
+    }
+    return check_launch("group_point_kernel");
+}
+
+extern "C" int psa_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
+                                    float* grad_points, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0, "GroupPointGrad: negative dimension");
+    if ((long long)b * n * c == 0) return PSA_OK;
+    PSA_REQUIRE(grad_points != nullptr, "GroupPointGrad: null buffer");
+    cudaStream_t st = as_stream(stream);
+    PSA_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, st));
+    long long rows_per_b = (long long)m * nsample;
+    long long total = (long long)b * rows_per_b * c;
+    if (total == 0) return PSA_OK;
+    PSA_REQUIRE(grad_out && idx, "GroupPointGrad: null buffer");
+    group_point_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(n, c, rows_per_b, total, grad_out, idx, grad_points);
+    return check_launch("group_point_grad_kernel");
+}
+
+extern "C" int psa_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out,
+                                  psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && m >= 0 && k >= 0, "SelectionSort: negative dimension");
+    long long rows = (long long)b * m;
+    if (rows == 0 || n == 0) return PSA_OK;
+    PSA_REQUIRE(dist && outi && out, "SelectionSort: null buffer");
+    size_t smem = (size_t)kSelWarps * n * 2 * sizeof(float);
+    PSA_SUPPORTED(smem <= 200 * 1024, "selection_sort: n=%d exceeds the shared-memory resident limit", n);
+    PSA_CUDA(cudaFuncSetAttribute(selection_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((rows + kSelWarps - 1) / kSelWarps);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    selection_sort_kernel<<<grid, kSelWarps * 32, smem, as_stream(stream)>>>(rows, n, k, dist, outi, out);
+    return check_launch("selection_sort_kernel");
+}
+
+extern "C" int psa_knn_point(int b, int n, int m, int c, int k, const float* xyz1, const float* xyz2, float* val,
+                             int* idx, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && m >= 0 && c >= 0 && k >= 0, "knn_point: negative dimension");
+    PSA_REQUIRE(k <= n, "knn_point: k=%d exceeds the number of dataset points n=%d", k, n);
+    long long rows = (long long)b * m;
+    if (rows == 0 || k == 0) return PSA_OK;
+    PSA_REQUIRE(xyz1 && xyz2 && val && idx, "knn_point: null buffer");
+    size_t smem = (size_t)kSelWarps * n * 2 * sizeof(float);
+    PSA_SUPPORTED(smem <= 200 * 1024, "knn_point: n=%d exceeds the shared-memory resident limit", n);
+    PSA_CUDA(cudaFuncSetAttribute(knn_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((rows + kSelWarps - 1) / kSelWarps);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    knn_point_kernel<<<grid, kSelWarps * 32, smem, as_stream(stream)>>>(n, m, c, k, xyz1, xyz2, val, idx, rows);
+    return check_launch("knn_point_kernel");
+}

@@ -1,0 +1,54 @@
+"""pointnet2/models/pointnet2_cls_ssg.py on the B200 kernels: get_model(point_cloud, is_training, bn_decay,
+num_class) -> (logits (B,num_class), end_points), same layer hyper-parameters (pointnet2_cls_ssg.py:35-45)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .pointnet_util import add_sa_module_params, pointnet_sa_module
+from .tf_util import VariableStore, _require_inference
+
+NUM_CLASSES = 15
+
+
+def init_params(num_class=NUM_CLASSES, seed=0, device="cuda", randomize_bn=False) -> VariableStore:
+    p = VariableStore(device=device, seed=seed)
+    add_sa_module_params(p, "layer1", 3, [64, 64, 128], randomize_bn=randomize_bn)
+    add_sa_module_params(p, "layer2", 3 + 128, [128, 128, 256], randomize_bn=randomize_bn)
+    add_sa_module_params(p, "layer3", 3 + 256, [256, 512, 1024], randomize_bn=randomize_bn)
+    p.add_fc("fc1", 1024, 512, bn=True, randomize_bn=randomize_bn)
+    p.add_fc("fc2", 512, 256, bn=True, randomize_bn=randomize_bn)
+    p.add_fc("fc3", 256, num_class, bn=False)
+    return p
+
+
+def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
+    """Classification PointNet++ (SSG): input (B,N,3), output (B,num_class)."""
+    _require_inference(is_training)
+    batch_size = point_cloud.shape[0]
+    end_points = {"l0_xyz": point_cloud}
+    l0_xyz, l0_points = point_cloud, None
+    l1_xyz, l1_points, l1_indices = pointnet_sa_module(l0_xyz, l0_points, npoint=512, radius=0.2, nsample=32,
+                                                       mlp=[64, 64, 128], mlp2=None, group_all=False,
+                                                       is_training=is_training, bn_decay=bn_decay, scope="layer1",
+                                                       use_nchw=True, params=params)
+    l2_xyz, l2_points, l2_indices = pointnet_sa_module(l1_xyz, l1_points, npoint=128, radius=0.4, nsample=64,
+                                                       mlp=[128, 128, 256], mlp2=None, group_all=False,
+                                                       is_training=is_training, bn_decay=bn_decay, scope="layer2",
+                                                       params=params)
+    l3_xyz, l3_points, l3_indices = pointnet_sa_module(l2_xyz, l2_points, npoint=None, radius=None, nsample=None,
+                                                       mlp=[256, 512, 1024], mlp2=None, group_all=True,
+                                                       is_training=is_training, bn_decay=bn_decay, scope="layer3",
+                                                       params=params)
+    net = l3_points.reshape(batch_size, -1)
+    # fc1 -> dp1 -> fc2 -> dp2 -> fc3 (dropout is the identity at inference): one 3-layer shared MLP
+    head = params.mlp(["fc1", "fc2", "fc3"], [True, True, False])
+    net = ops.shared_mlp(net, head)
+    end_points.update(l1_xyz=l1_xyz, l1_points=l1_points, l1_indices=l1_indices, l2_xyz=l2_xyz, l2_points=l2_points,
+                      l2_indices=l2_indices, l3_points=l3_points)
+    return net, end_points
+
+
+def get_loss(pred, label, end_points=None):
+    """mean sparse softmax cross-entropy (pointnet2_cls_ssg.py:50-57)."""
+    return torch.nn.functional.cross_entropy(pred, label.long())

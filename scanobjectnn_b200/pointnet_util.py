@@ -1,0 +1,107 @@
+"""PointNet++ layers on the B200 kernels: same names, argument order and return values as
+pointnet2/utils/pointnet_util.py (plus a keyword-only ``params`` variable store, torch being stateless about
+variable scopes).  Inference mode: batch norm uses the moving averages and is folded into the fused kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .tf_grouping import group_point, knn_point, query_ball_point
+from .tf_interpolate import three_interpolate, three_nn
+from .tf_sampling import farthest_point_sample, gather_point
+from .tf_util import VariableStore, _require_inference
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True):
+    """pointnet_util.sample_and_group (pointnet_util.py:22-56), materialising form.
+    -> new_xyz (B,npoint,3), new_points (B,npoint,nsample,3+C), idx (B,npoint,nsample), grouped_xyz."""
+    new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+    if knn:
+        _, idx = knn_point(nsample, xyz, new_xyz)
+    else:
+        idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = group_point(xyz, idx)
+    grouped_xyz = grouped_xyz - new_xyz.unsqueeze(2)
+    if points is not None:
+        grouped_points = group_point(points, idx)
+        new_points = torch.cat([grouped_xyz, grouped_points], dim=-1) if use_xyz else grouped_points
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def sample_and_group_all(xyz, points, use_xyz=True):
+    """pointnet_util.sample_and_group_all (pointnet_util.py:59-84)."""
+    b, n, _ = xyz.shape
+    new_xyz = torch.zeros((b, 1, 3), dtype=torch.float32, device=xyz.device)
+    idx = torch.arange(n, dtype=torch.int32, device=xyz.device).reshape(1, 1, n).repeat(b, 1, 1)
+    grouped_xyz = xyz.reshape(b, 1, n, 3)
+    if points is not None:
+        new_points = torch.cat([xyz, points], dim=2) if use_xyz else points
+        new_points = new_points.unsqueeze(1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def _mlp_scopes(scope, mlp, prefix="conv"):
+    return [f"{scope}/{prefix}{i}" for i in range(len(mlp))]
+
+
+def add_sa_module_params(params: VariableStore, scope, in_channels, mlp, mlp2=None, bn=True, randomize_bn=False):
+    c = in_channels
+    for s, cout in zip(_mlp_scopes(scope, mlp), mlp):
+        params.add_conv2d(s, c, cout, bn=bn, randomize_bn=randomize_bn)
+        c = cout
+    for s, cout in zip(_mlp_scopes(scope, mlp2 or [], "conv_post_"), mlp2 or []):
+        params.add_conv2d(s, c, cout, bn=bn, randomize_bn=randomize_bn)
+        c = cout
+    return c
+
+
+def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training, bn_decay, scope,
+                       bn=True, pooling="max", knn=False, use_xyz=True, use_nchw=False, *, params: VariableStore):
+    """pointnet_util.pointnet_sa_module (pointnet_util.py:87-154) -> (new_xyz, new_points (B,npoint,C_out), idx).
+
+    max-pooling / ball-query / use_xyz levels run as TWO launches: fused FPS+gather, then the fused
+    ball-query -> group -> centre -> MLP -> max kernel pair (no (B,m,K,C) tensor is ever built).
+    ``use_nchw`` only selected a cuDNN layout in the reference and has no effect on results."""
+    _require_inference(is_training)
+    if pooling != "max":
+        raise NotImplementedError("only pooling='max' is used by the in-scope models")
+    scopes = _mlp_scopes(scope, mlp)
+    if group_all:
+        nsample = xyz.shape[1]
+        new_xyz, new_points, idx, _ = sample_and_group_all(xyz, points, use_xyz)
+        b = xyz.shape[0]
+        rows = new_points.reshape(b * nsample, new_points.shape[-1])
+        pooled = ops.shared_mlp(rows, params.mlp(scopes), pool_k=nsample).reshape(b, 1, -1)
+    elif knn or not use_xyz:
+        new_xyz, new_points, idx, _ = sample_and_group(npoint, radius, nsample, xyz, points, knn, use_xyz)
+        b, m, k, c = new_points.shape
+        pooled = ops.shared_mlp(new_points.reshape(b * m * k, c), params.mlp(scopes), pool_k=k).reshape(b, m, -1)
+    else:
+        _, new_xyz = ops.farthest_point_sample_and_gather(npoint, xyz)
+        pooled, idx, _ = ops.sa_module_infer(xyz, new_xyz, points, radius, nsample, params.mlp(scopes), return_idx=True)
+    if mlp2 is not None:
+        pooled = ops.shared_mlp(pooled, params.mlp(_mlp_scopes(scope, mlp2, "conv_post_")))
+    return new_xyz, pooled, idx
+
+
+def add_fp_module_params(params: VariableStore, scope, in_channels, mlp, bn=True, randomize_bn=False):
+    c = in_channels
+    for i, cout in enumerate(mlp):
+        params.add_conv2d(f"{scope}/conv_{i}", c, cout, bn=bn, randomize_bn=randomize_bn)
+        c = cout
+    return c
+
+
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, *,
+                       params: VariableStore):
+    """pointnet_util.pointnet_fp_module (pointnet_util.py:199-229): three_nn + inverse-distance weights +
+    three_interpolate in ONE launch (the reference runs them on the CPU), concat skip features, 1x1 convs."""
+    _require_inference(is_training)
+    interpolated = ops.three_nn_interpolate(xyz1, xyz2, points2)
+    new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
+    scopes = [f"{scope}/conv_{i}" for i in range(len(mlp))]
+    return ops.shared_mlp(new_points1, params.mlp(scopes))

@@ -1,0 +1,123 @@
+"""GPU parity of the fused grouped-MLP kernels and the SSG model against the fp64 restatement
+(oracle/mlp_oracle.py).  Tolerance: 1e-5 absolute on O(1) activations (BASELINE.json north_star);
+the plain-fp32 restatement's own distance from fp64 is printed beside it for scale."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mlp_oracle as mo
+from oracle import oracle as orc
+from scanobjectnn_b200 import ops, pointnet2_cls_ssg
+from scanobjectnn_b200.pointnet_util import add_fp_module_params, add_sa_module_params, pointnet_fp_module, pointnet_sa_module
+from scanobjectnn_b200.synthetic import make_clouds
+from scanobjectnn_b200.tf_util import VariableStore
+
+from . import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _store(seed=0):
+    return VariableStore(device="cuda", seed=seed)
+
+
+@pytest.mark.parametrize("rows,pool_k,chans", [(256, 1, [7, 64]), (4096, 128, [259, 256, 512, 1024]), (32, 1, [1024, 512, 256, 15]),
+                                               (300, 1, [131, 128, 40]), (640, 32, [64, 64]), (2 * 2048, 2048, [320, 1024]),
+                                               (1280, 8, [6, 64, 128])])
+def test_shared_mlp_matches_fp64(rows, pool_k, chans):
+    p = _store(rows)
+    scopes = []
+    for i in range(len(chans) - 1):
+        p.add_conv2d(f"m/conv{i}", chans[i], chans[i + 1], bn=(i % 2 == 0), randomize_bn=True)
+        scopes.append(f"m/conv{i}")
+    relus = [True] * (len(scopes) - 1) + [pool_k > 1]
+    rng = np.random.default_rng(rows)
+    x = rng.standard_normal((rows, chans[0])).astype(np.float32)
+    got = G.npy(ops.shared_mlp(G.cu(x), p.mlp(scopes, relus), pool_k=pool_k))
+    want = mo.mlp_chain(x, p, scopes, relus)
+    if pool_k > 1:
+        want = want.reshape(rows // pool_k, pool_k, -1).max(1)
+    err = np.abs(got - want).max()
+    assert err < TOL * max(1.0, np.abs(want).max()), err
+
+
+@pytest.mark.parametrize("kind", ["ball", "shell"])
+@pytest.mark.parametrize("n,m,r,k,c,mlp", [(2048, 512, 0.2, 32, 0, [64, 64, 128]), (512, 128, 0.4, 64, 128, [128, 128, 256]),
+                                           (2048, 512, 0.2, 64, 0, [64, 64, 128]), (300, 50, 0.3, 20, 5, [32, 48]),
+                                           (256, 64, 0.3, 16, 64, [64])])
+def test_sa_module_infer_matches_fp64(kind, n, m, r, k, c, mlp):
+    p = _store(n + k)
+    add_sa_module_params(p, "sa", 3 + c, mlp, randomize_bn=True)
+    rng = np.random.default_rng(n)
+    xyz = make_clouds(kind, 2, n, seed=n)
+    pts = rng.standard_normal((2, n, c)).astype(np.float32) if c else None
+    new_xyz, got, idx = pointnet_sa_module(G.cu(xyz), G.cu(pts) if c else None, m, r, k, mlp, None, False, False, None, "sa", params=p)
+    oxyz, want, oidx = mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p)
+    assert np.array_equal(G.npy(new_xyz), oxyz)
+    assert np.array_equal(G.npy(idx), oidx)
+    err = np.abs(G.npy(got) - want).max()
+    f32 = np.abs(mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p, dtype=np.float32)[1] - want).max()
+    print(f"sa_module max|err| cuda={err:.3e} numpy-fp32={f32:.3e} max|act|={np.abs(want).max():.3f}")
+    assert err < TOL * max(1.0, np.abs(want).max())
+
+
+def test_sa_module_unfused_paths_agree():
+    """knn=True and group_all go through group_point + shared_mlp instead of the fused kernel."""
+    p = _store(3)
+    add_sa_module_params(p, "sa", 3 + 16, [32, 64], randomize_bn=True)
+    rng = np.random.default_rng(0)
+    xyz = make_clouds("ball", 2, 128, seed=9)
+    pts = rng.standard_normal((2, 128, 16)).astype(np.float32)
+    _, got, _ = pointnet_sa_module(G.cu(xyz), G.cu(pts), None, None, None, [32, 64], None, True, False, None, "sa", params=p)
+    _, want, _ = mo.sa_module(xyz, pts, None, None, None, [32, 64], True, "sa", p)
+    assert np.abs(G.npy(got) - want).max() < TOL * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("n,c,k,mlp", [(1024, 3, 20, [64]), (512, 64, 20, [64]), (256, 64, 20, [128]), (200, 3, 20, [64, 128]),
+                                       (128, 8, 16, [32])])
+def test_edgeconv_infer_matches_fp64(n, c, k, mlp):
+    p = _store(n)
+    scopes = []
+    cin = 2 * c
+    for i, co in enumerate(mlp):
+        p.add_conv2d(f"e/conv{i}", cin, co, bn=True, randomize_bn=True)
+        scopes.append(f"e/conv{i}")
+        cin = co
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n, c)).astype(np.float32)
+    idx = orc.dgcnn_knn(x, k)
+    got = G.npy(ops.edgeconv_infer(G.cu(x), G.cu(idx), p.mlp(scopes)))
+    want = mo.edgeconv(x, idx, p, scopes)
+    assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
+
+
+def test_fp_module_matches_fp64():
+    p = _store(5)
+    add_fp_module_params(p, "fp", 256 + 128, [256, 128], randomize_bn=True)
+    rng = np.random.default_rng(5)
+    xyz1 = make_clouds("ball", 2, 512, seed=1)
+    xyz2 = make_clouds("ball", 2, 128, seed=2)
+    p1 = rng.standard_normal((2, 512, 128)).astype(np.float32)
+    p2 = rng.standard_normal((2, 128, 256)).astype(np.float32)
+    got = G.npy(pointnet_fp_module(G.cu(xyz1), G.cu(xyz2), G.cu(p1), G.cu(p2), [256, 128], False, None, "fp", params=p))
+    want = mo.fp_module(xyz1, xyz2, p1, p2, [256, 128], "fp", p)
+    assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("kind", ["ball", "shell", "dup"])
+def test_pointnet2_cls_ssg_matches_oracle(kind):
+    p = pointnet2_cls_ssg.init_params(seed=1, randomize_bn=True)
+    xyz = make_clouds(kind, 4, 2048, seed=1001)
+    logits, ep = pointnet2_cls_ssg.get_model(G.cu(xyz), False, params=p)
+    want, oep = mo.pointnet2_cls_ssg(xyz, p)
+    assert np.array_equal(G.npy(ep["l1_indices"]), oep["l1_idx"])
+    assert np.array_equal(G.npy(ep["l2_indices"]), oep["l2_idx"])
+    assert np.array_equal(G.npy(ep["l1_xyz"]), oep["l1_xyz"])
+    for name in ("l1_points", "l2_points", "l3_points"):
+        w = oep[name].reshape(G.npy(ep[name]).shape)
+        err = np.abs(G.npy(ep[name]) - w).max()
+        assert err < TOL * max(1.0, np.abs(w).max()), (name, err)
+    err = np.abs(G.npy(logits) - want).max()
+    print(f"logits max|err|={err:.3e} max|logit|={np.abs(want).max():.3f}")
+    assert err < TOL * max(1.0, np.abs(want).max())
