@@ -186,10 +186,23 @@ PSA_API int psa_shared_mlp(long long rows, int pool_k, const float* x, const psa
  * without materialising the (b,m,nsample,3+c) tensor.  xyz (b,n,3), new_xyz (b,m,3), points (b,n,c) or
  * NULL with c = 0, mlp->channels[0] must equal 3 + c.  out (b,m,C_L).
  * idx_in  != NULL: use these neighbourhoods (b,m,nsample) instead of searching;
- * idx_out != NULL / pts_cnt != NULL: also write the ball-query result. */
+ * idx_out != NULL / pts_cnt != NULL: also write the ball-query result (idx_out is REQUIRED when idx_in is NULL).
+ * workspace: psa_sa_module_workspace_bytes() bytes of device scratch (per-point layer-1 products), may be 0/NULL. */
+PSA_API size_t psa_sa_module_workspace_bytes(int b, int n, int m, int c, int nsample, const psa_mlp* mlp);
 PSA_API int psa_sa_module_infer(int b, int n, int m, int c, float radius, int nsample, const float* xyz,
-                        const float* new_xyz, const float* points, const int* idx_in, const psa_mlp* mlp,
-                        float* out, int* idx_out, int* pts_cnt, psa_stream_t stream);
+                                const float* new_xyz, const float* points, const int* idx_in, const psa_mlp* mlp,
+                                float* out, int* idx_out, int* pts_cnt, void* workspace, size_t workspace_bytes,
+                                psa_stream_t stream);
+
+/* Arithmetic of the grouped MLP.  0 (default): layers after the first run on the tcgen05 tensor cores as a
+ * three-term tf32/tf32/bf16 operand split with fp32 accumulation (within 1e-5 of fp64 on O(1) activations) whenever
+ * the shapes allow (widths 64/128, last width 64 or a multiple of 128, nsample 32/64/128), fp32 FMA otherwise.
+ * 1: always the fp32-FMA kernels. */
+PSA_API int psa_set_mlp_mode(int mode);
+PSA_API int psa_get_mlp_mode(void);
+
+/* Diagnostic: one 128-row tile through one tensor-core layer, D[128,N] = A[128,Kd] . W[Kd,N] (Kd, N in {64,128}). */
+PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, psa_stream_t stream);
 
 /* Fused EdgeConv, inference mode (dgcnn/models/dgcnn.py:31-47 pattern): x (b,n,c), nn_idx (b,n,k) ->
  * out (b,n,C_L) = max_j MLP([x_i, x_j - x_i]); mlp->channels[0] must equal 2c. */

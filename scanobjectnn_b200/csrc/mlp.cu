@@ -17,6 +17,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "mlp_internal.cuh"
 
 namespace psa {
 
@@ -362,18 +363,6 @@ fused_group_mlp_kernel(const __grid_constant__ FusedArgs a) {
 // Dense single layer: out = relu?((x . W) * scale + shift) with optional max over runs of pool_k rows.
 // A streamed from global in [BM][BK] chunks (cp.async when the row pitch allows 16-byte copies).
 // ------------------------------------------------------------------------------------------------------------
-struct DenseArgs {
-    long long rows;
-    int K, N;
-    int pool_k;          // 1 = none
-    int relu;
-    const float* x;      // (rows, K)
-    const float* W;      // (K, N)
-    const float* scale;  // (N) or null
-    const float* shift;  // (N)
-    float* out;          // (rows, N) or (rows/pool_k, N)
-};
-
 constexpr int LDA_D = BK + 4;   // 20 floats = 80 B rows: 16-byte aligned, conflict-light
 
 __device__ __forceinline__ void load_a_chunk(float* As, const float* __restrict__ x, long long row0, long long rows,
@@ -446,7 +435,7 @@ dense_layer_kernel(const __grid_constant__ DenseArgs a) {
             for (int j = 0; j < 4; ++j) {
                 if (col + j >= a.N) continue;
                 const float sc = a.scale ? __ldg(a.scale + col + j) : 1.f;
-                const float sh = __ldg(a.shift + col + j);
+                const float sh = a.shift ? __ldg(a.shift + col + j) : 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = ty * 8 + i;
@@ -474,7 +463,7 @@ dense_layer_kernel(const __grid_constant__ DenseArgs a) {
         for (int j = 0; j < 4; ++j) {
             if (col + j >= a.N) continue;
             const float sc = a.scale ? __ldg(a.scale + col + j) : 1.f;
-            const float sh = __ldg(a.shift + col + j);
+            const float sh = a.shift ? __ldg(a.shift + col + j) : 0.f;
             int curg = -1;
             float m = 0.f;
 #pragma unroll
@@ -528,7 +517,7 @@ static int validate_mlp(const psa_mlp* mlp, const char* who) {
     return PSA_OK;
 }
 
-static int launch_dense(const DenseArgs& d, cudaStream_t st) {
+int launch_dense(const DenseArgs& d, cudaStream_t st) {
     const long long tiles_m = (d.rows + BM - 1) / BM;
     PSA_SUPPORTED(tiles_m <= 0x7fffffffLL, "shared_mlp: too many rows");
     if (d.pool_k > 1) {
@@ -619,28 +608,18 @@ extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const 
     return PSA_OK;
 }
 
-extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int nsample, const float* xyz,
-                                   const float* new_xyz, const float* points, const int* idx_in, const psa_mlp* mlp,
-                                   float* out, int* idx_out, int* pts_cnt, psa_stream_t stream) {
-    int rc = validate_mlp(mlp, "sa_module");
-    if (rc != PSA_OK) return rc;
-    PSA_REQUIRE(b >= 0 && n >= 1 && m >= 0 && c >= 0 && nsample >= 1, "sa_module: bad dims b=%d n=%d m=%d c=%d nsample=%d", b, n, m, c, nsample);
-    PSA_REQUIRE(mlp->channels[0] == 3 + c, "sa_module: mlp input width %d != 3 + c (%d)", mlp->channels[0], 3 + c);
-    if (b == 0 || m == 0) return PSA_OK;
-    PSA_REQUIRE(xyz && new_xyz && out && (points || c == 0), "sa_module: null buffer");
-    const int* idx = idx_in;
-    if (idx == nullptr) {
-        PSA_REQUIRE(idx_out != nullptr, "sa_module: idx_out must be provided when idx_in is NULL (it receives the ball query)");
-        rc = psa_query_ball_point(b, n, m, radius, nsample, xyz, new_xyz, idx_out, pts_cnt, stream);
-        if (rc != PSA_OK) return rc;
-        idx = idx_out;
-    }
+namespace psa {
+// fp32-FMA fused set-abstraction level (gather + MLP chain in shared memory + max-pool); idx already computed
+int sa_module_simt(int b, int n, int m, int c, int nsample, const float* xyz, const float* new_xyz, const float* points,
+                   const int* idx, const psa_mlp* mlp, float* out, cudaStream_t st) {
     FusedArgs a;
     a.mlp = *mlp;
     a.groups = (long long)b * m; a.K = nsample; a.n = n; a.m = m; a.c = c;
     a.xyz = xyz; a.new_xyz = new_xyz; a.feat = points; a.idx = idx; a.out = out;
-    return launch_fused<kGatherSA>(a, as_stream(stream), "sa_module");
+    return launch_fused<kGatherSA>(a, st, "sa_module");
 }
+int validate_mlp_public(const psa_mlp* mlp, const char* who) { return validate_mlp(mlp, who); }
+}  // namespace psa
 
 extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
                                   float* out, psa_stream_t stream) {

@@ -1,0 +1,25 @@
+// mlp_internal.cuh -- pieces of mlp.cu shared with tc_mlp.cu
+#pragma once
+#include "common.cuh"
+
+namespace psa {
+
+struct DenseArgs {
+    long long rows;
+    int K, N;
+    int pool_k;          // 1 = none
+    int relu;
+    const float* x;      // (rows, K)
+    const float* W;      // (K, N)
+    const float* scale;  // (N) or null
+    const float* shift;  // (N)
+    float* out;          // (rows, N) or (rows/pool_k, N)
+};
+
+
+int launch_dense(const DenseArgs& d, cudaStream_t st);
+int sa_module_simt(int b, int n, int m, int c, int nsample, const float* xyz, const float* new_xyz, const float* points,
+                   const int* idx, const psa_mlp* mlp, float* out, cudaStream_t st);
+int validate_mlp_public(const psa_mlp* mlp, const char* who);
+
+}  // namespace psa

@@ -19,7 +19,7 @@ __all__ = [
     "farthest_point_sample", "gather_point", "query_ball_point", "group_point", "select_top_k", "knn_point",
     "three_nn", "three_interpolate", "three_nn_interpolate", "pairwise_distance", "knn", "knn_graph",
     "get_edge_feature", "farthest_point_sample_and_gather", "MlpParams", "shared_mlp", "sa_module_infer",
-    "edgeconv_infer",
+    "edgeconv_infer", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
 ]
 
 
@@ -403,9 +403,12 @@ def sa_module_infer(xyz, new_xyz, points, radius: float, nsample: int, mlp: MlpP
         cnt = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
     else:
         idx = _dev(idx, torch.int32, "idx", 3)
-    check(_lib.load().psa_sa_module_infer(b, n, m, c, C.c_float(radius), nsample, _ptr(xyz), _ptr(new_xyz), _ptr(points),
-                                          _ptr(idx), mlp.ref, _ptr(out), _ptr(idx_out), _ptr(cnt), _stream()),
-          "sa_module_infer")
+    lib = _lib.load()
+    need = lib.psa_sa_module_workspace_bytes(b, n, m, c, nsample, mlp.ref)
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=xyz.device) if need else None
+    check(lib.psa_sa_module_infer(b, n, m, c, C.c_float(radius), nsample, _ptr(xyz), _ptr(new_xyz), _ptr(points),
+                                  _ptr(idx), mlp.ref, _ptr(out), _ptr(idx_out), _ptr(cnt), _ptr(ws), C.c_size_t(need),
+                                  _stream()), "sa_module_infer")
     if return_idx:
         return out, (idx if idx is not None else idx_out), cnt
     return out
@@ -420,3 +423,23 @@ def edgeconv_infer(x, nn_idx, mlp: MlpParams) -> torch.Tensor:
     out = torch.empty((b, n, mlp.channels[-1]), dtype=torch.float32, device=x.device)
     check(_lib.load().psa_edgeconv_infer(b, n, c, k, _ptr(x), _ptr(nn_idx), mlp.ref, _ptr(out), _stream()), "edgeconv_infer")
     return out
+
+
+def set_mlp_mode(mode: int) -> None:
+    """0 = auto (tcgen05 tensor cores where the shapes allow), 1 = always the fp32-FMA kernels."""
+    check(_lib.load().psa_set_mlp_mode(int(mode)), "set_mlp_mode")
+
+
+def get_mlp_mode() -> int:
+    return int(_lib.load().psa_get_mlp_mode())
+
+
+def tc_selftest(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Diagnostic: a (128,Kd) . w (Kd,N) through one tensor-core layer (three-term split) -> (128,N)."""
+    a = _dev(a, torch.float32, "a", 2)
+    w = _dev(w, torch.float32, "w", 2)
+    if a.shape[0] != 128 or a.shape[1] != w.shape[0]:
+        raise ValueError("tc_selftest expects a (128,Kd) and w (Kd,N)")
+    d = torch.empty((128, w.shape[1]), dtype=torch.float32, device=a.device)
+    check(_lib.load().psa_tc_selftest(a.shape[1], w.shape[1], _ptr(a), _ptr(w), _ptr(d), _stream()), "tc_selftest")
+    return d

@@ -22,6 +22,14 @@ def _store(seed=0):
     return VariableStore(device="cuda", seed=seed)
 
 
+@pytest.fixture(params=["tensor", "fma"])
+def mlp_mode(request):
+    """0 = auto (tcgen05 three-term split where the shapes allow), 1 = fp32 FMA kernels"""
+    ops.set_mlp_mode(0 if request.param == "tensor" else 1)
+    yield request.param
+    ops.set_mlp_mode(0)
+
+
 @pytest.mark.parametrize("rows,pool_k,chans", [(256, 1, [7, 64]), (4096, 128, [259, 256, 512, 1024]), (32, 1, [1024, 512, 256, 15]),
                                                (300, 1, [131, 128, 40]), (640, 32, [64, 64]), (2 * 2048, 2048, [320, 1024]),
                                                (1280, 8, [6, 64, 128])])
@@ -46,7 +54,7 @@ def test_shared_mlp_matches_fp64(rows, pool_k, chans):
 @pytest.mark.parametrize("n,m,r,k,c,mlp", [(2048, 512, 0.2, 32, 0, [64, 64, 128]), (512, 128, 0.4, 64, 128, [128, 128, 256]),
                                            (2048, 512, 0.2, 64, 0, [64, 64, 128]), (300, 50, 0.3, 20, 5, [32, 48]),
                                            (256, 64, 0.3, 16, 64, [64])])
-def test_sa_module_infer_matches_fp64(kind, n, m, r, k, c, mlp):
+def test_sa_module_infer_matches_fp64(kind, n, m, r, k, c, mlp, mlp_mode):
     p = _store(n + k)
     add_sa_module_params(p, "sa", 3 + c, mlp, randomize_bn=True)
     rng = np.random.default_rng(n)
@@ -58,7 +66,7 @@ def test_sa_module_infer_matches_fp64(kind, n, m, r, k, c, mlp):
     assert np.array_equal(G.npy(idx), oidx)
     err = np.abs(G.npy(got) - want).max()
     f32 = np.abs(mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p, dtype=np.float32)[1] - want).max()
-    print(f"sa_module max|err| cuda={err:.3e} numpy-fp32={f32:.3e} max|act|={np.abs(want).max():.3f}")
+    print(f"sa_module[{mlp_mode}] max|err| cuda={err:.3e} numpy-fp32={f32:.3e} max|act|={np.abs(want).max():.3f}")
     assert err < TOL * max(1.0, np.abs(want).max())
 
 
@@ -106,7 +114,7 @@ def test_fp_module_matches_fp64():
 
 
 @pytest.mark.parametrize("kind", ["ball", "shell", "dup"])
-def test_pointnet2_cls_ssg_matches_oracle(kind):
+def test_pointnet2_cls_ssg_matches_oracle(kind, mlp_mode):
     p = pointnet2_cls_ssg.init_params(seed=1, randomize_bn=True)
     xyz = make_clouds(kind, 4, 2048, seed=1001)
     logits, ep = pointnet2_cls_ssg.get_model(G.cu(xyz), False, params=p)
@@ -119,5 +127,5 @@ def test_pointnet2_cls_ssg_matches_oracle(kind):
         err = np.abs(G.npy(ep[name]) - w).max()
         assert err < TOL * max(1.0, np.abs(w).max()), (name, err)
     err = np.abs(G.npy(logits) - want).max()
-    print(f"logits max|err|={err:.3e} max|logit|={np.abs(want).max():.3f}")
+    print(f"logits[{mlp_mode}] max|err|={err:.3e} max|logit|={np.abs(want).max():.3f}")
     assert err < TOL * max(1.0, np.abs(want).max())
