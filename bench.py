@@ -263,6 +263,7 @@ def main():
             ts = []
             for _ in range(10):
                 flush.zero_()                       # L2 flush between timed launches
+                torch.cuda._sleep(400_000)          # ~0.2 ms spin: the host enqueues e0/kernel/e1 before the GPU gets there
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); fn(); e1.record()
                 torch.cuda.synchronize()

@@ -496,6 +496,67 @@ dense_layer_kernel(const __grid_constant__ DenseArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Small-M layer (rows <= 32: the FC heads, B = 32 rows x 1024 -> 512 -> 256 -> num_class).  A 128-row GEMM tile would
+// leave 3/4 of the MMA rows empty and only N/128 CTAs busy; here a CTA owns 32 output columns, its 8 warps split K,
+// lane = column (coalesced weight rows), the x slice sits transposed in shared memory so 4 rows come per LDS.128,
+// and the 8 partial sums are combined through shared memory in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kFcWarps = 8;
+
+__global__ void __launch_bounds__(kFcWarps * 32)
+fc_small_kernel(const __grid_constant__ DenseArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = (int)a.rows;
+    const int Kc = (a.K + kFcWarps - 1) / kFcWarps;          // k-slice per warp
+    const int k0 = warp * Kc;
+    const int kn = max(0, min(Kc, a.K - k0));
+    float* xs = smem_f + (size_t)warp * Kc * 32;              // [kk][r], r fastest
+    for (int e = lane; e < Kc * 32; e += 32) xs[e] = 0.f;
+    __syncwarp();
+    for (int r = 0; r < rows; ++r)
+        for (int kk = lane; kk < kn; kk += 32) xs[kk * 32 + r] = __ldg(a.x + (size_t)r * a.K + k0 + kk);
+    __syncwarp();
+    const int col = blockIdx.x * 32 + lane;
+    float acc[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+    if (col < a.N) {
+#pragma unroll 2
+        for (int kk = 0; kk < kn; ++kk) {
+            const float wv = __ldg(a.W + (size_t)(k0 + kk) * a.N + col);
+            const float4* xr = reinterpret_cast<const float4*>(xs + kk * 32);
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) {
+                const float4 xv = xr[r4];
+                acc[4 * r4 + 0] = fmaf(xv.x, wv, acc[4 * r4 + 0]);
+                acc[4 * r4 + 1] = fmaf(xv.y, wv, acc[4 * r4 + 1]);
+                acc[4 * r4 + 2] = fmaf(xv.z, wv, acc[4 * r4 + 2]);
+                acc[4 * r4 + 3] = fmaf(xv.w, wv, acc[4 * r4 + 3]);
+            }
+        }
+    }
+    __syncthreads();                                          // everyone is done with xs: reuse it for the partials
+    float* red = smem_f;                                      // [warp][r][lane]
+#pragma unroll
+    for (int r = 0; r < 32; ++r) red[((size_t)warp * 32 + r) * 32 + lane] = acc[r];
+    __syncthreads();
+    if (col < a.N) {
+        const float sc = a.scale ? __ldg(a.scale + col) : 1.f;
+        const float sh = a.shift ? __ldg(a.shift + col) : 0.f;
+        for (int r = warp; r < rows; r += kFcWarps) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kFcWarps; ++w) s += red[((size_t)w * 32 + r) * 32 + lane];
+            float v = fmaf(s, sc, sh);
+            if (a.relu) v = fmaxf(v, 0.f);
+            a.out[(size_t)r * a.N + col] = v;
+        }
+    }
+}
+
 __global__ void fill_ord_neg_inf_kernel(long long total, int* out) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x)
@@ -518,6 +579,15 @@ static int validate_mlp(const psa_mlp* mlp, const char* who) {
 }
 
 int launch_dense(const DenseArgs& d, cudaStream_t st) {
+    if (d.rows <= 32 && d.pool_k == 1) {
+        const int Kc = (d.K + kFcWarps - 1) / kFcWarps;
+        size_t smem = (size_t)kFcWarps * 32 * sizeof(float) * (size_t)max(Kc, 32);
+        if (smem <= 200 * 1024) {
+            PSA_CUDA(cudaFuncSetAttribute(fc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fc_small_kernel<<<(d.N + 31) / 32, kFcWarps * 32, smem, st>>>(d);
+            return check_launch("fc_small_kernel");
+        }
+    }
     const long long tiles_m = (d.rows + BM - 1) / BM;
     PSA_SUPPORTED(tiles_m <= 0x7fffffffLL, "shared_mlp: too many rows");
     if (d.pool_k > 1) {

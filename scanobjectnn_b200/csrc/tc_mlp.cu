@@ -30,7 +30,8 @@ namespace psa {
 
 using namespace tc;
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 512;   // 16 warps: warp w works on TMEM lanes 32*(w%4).. (hardware rule) and column chunks w/4, w/4+4, ..
+constexpr int kTcChunkWarps = kTcThreads / 128;
 constexpr int kTmemCols = 512;
 constexpr uint32_t D_COL = 0, AHI_COL = 128, ALO_COL = 256, ABF_COL = 384;
 constexpr int kMaxTcLayers = 2;
@@ -93,12 +94,14 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t whi_add
     const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, N);
     const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, N);
     const uint32_t blk = (uint32_t)N * 128u;
-    for (int s = 0; s < Kd / 8; ++s)
-        mma_tf32_ts(d, tmem_base + AHI_COL + s * 8, make_smem_desc_sw128(whi_addr + (s >> 2) * blk + (s & 3) * 32), id_tf32, s > 0);
+    // The tensor core truncates (rounds toward zero) every time it adds into D, so the error grows with the number of
+    // accumulation steps taken while D is large: run the two small correction terms first, the main term last.
+    for (int s = 0; s < Kd / 16; ++s)
+        mma_bf16_ts(d, tmem_base + ABF_COL + s * 8, make_smem_desc_sw128(wlo_addr + (s >> 2) * blk + (s & 3) * 32), id_bf16, s > 0);
     for (int s = 0; s < Kd / 8; ++s)
         mma_tf32_ts(d, tmem_base + ALO_COL + s * 8, make_smem_desc_sw128(whi_addr + (s >> 2) * blk + (s & 3) * 32), id_tf32, 1);
-    for (int s = 0; s < Kd / 16; ++s)
-        mma_bf16_ts(d, tmem_base + ABF_COL + s * 8, make_smem_desc_sw128(wlo_addr + (s >> 2) * blk + (s & 3) * 32), id_bf16, 1);
+    for (int s = 0; s < Kd / 8; ++s)
+        mma_tf32_ts(d, tmem_base + AHI_COL + s * 8, make_smem_desc_sw128(whi_addr + (s >> 2) * blk + (s & 3) * 32), id_tf32, 1);
 }
 
 // transposing butterfly: v[q] = column q of this lane's row; afterwards v[0] on lane l = max over the warp's 32 rows of column l
@@ -143,9 +146,11 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tmem;
-    __shared__ float s_red[4][32];
+    __shared__ float s_red[kTcThreads / 32][32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quarter = warp & 3, cs = warp >> 2;      // rows 32*quarter.., column-chunk slot
+    const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const TcSmemLayout L = tc_layout(a);
     const int split = blockIdx.x % a.nsplit;
@@ -185,14 +190,14 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = s_tmem;
-    const uint32_t row_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0;
 
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
     for (long long tile = worker; tile < ntiles; tile += nworkers) {
         const long long g0 = tile * G;
-        const long long gid = g0 + tid / a.K;
+        const long long gid = g0 + row / a.K;
         const bool valid = gid < a.groups;
         // ---- layer 1 on the FMA pipe, straight into the A operand ----
         {
@@ -200,13 +205,13 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
             const float* urow = nullptr;
             if (valid) {
                 const long long bi = gid / a.m;
-                const int j = __ldg(a.idx + gid * a.K + (tid % a.K));
+                const int j = __ldg(a.idx + gid * a.K + (row % a.K));
                 const float* p = a.xyz + ((size_t)bi * a.n + j) * 3;
                 const float* c = a.new_xyz + (size_t)gid * 3;
                 dx = __ldg(p) - __ldg(c); dy = __ldg(p + 1) - __ldg(c + 1); dz = __ldg(p + 2) - __ldg(c + 2);
                 if (a.uf) urow = a.uf + ((size_t)bi * a.n + j) * a.C1;
             }
-            for (int ch = 0; ch < a.C1 / 32; ++ch) {
+            for (int ch = cs; ch < a.C1 / 32; ch += kTcChunkWarps) {
                 float h[32];
                 if (urow) {
 #pragma unroll
@@ -243,7 +248,7 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
             phase ^= 1u;
             fence_after_thread_sync();
             if (l != last) {
-                for (int ch = 0; ch < N / 32; ++ch) {
+                for (int ch = cs; ch < N / 32; ch += kTcChunkWarps) {
                     uint32_t d[32];
                     tmem_ld32(row_taddr + D_COL + ch * 32, d);
                     tmem_ld_wait();
@@ -260,28 +265,34 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
                 fence_before_thread_sync();
                 __syncthreads();
             } else {
-                const int warps_per_group = a.K / 32;           // 1, 2 or 4
-                const long long wg = g0 + (warp * 32) / a.K;    // this warp's neighbourhood
-                for (int ch = 0; ch < N / 32; ++ch) {
-                    uint32_t d[32];
-                    tmem_ld32(row_taddr + D_COL + ch * 32, d);
-                    tmem_ld_wait();
-                    float v[32];
+                // rows of one neighbourhood span K/32 lane-quarters; warps sharing a chunk slot combine through s_red
+                const int quarters_per_group = a.K / 32;        // 1, 2 or 4
+                const long long wg = g0 + (quarter * 32) / a.K; // this warp's neighbourhood
+                const int nch = N / 32;
+                for (int ch0 = 0; ch0 < nch; ch0 += kTcChunkWarps) {      // uniform trip count: barriers inside
+                    const int ch = ch0 + cs;
+                    float mx = -FLT_MAX;
+                    if (ch < nch) {
+                        uint32_t d[32];
+                        tmem_ld32(row_taddr + D_COL + ch * 32, d);
+                        tmem_ld_wait();
+                        float v[32];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        float x = fmaf(__uint_as_float(d[q]), sl[l][ch * 32 + q], tl[l][ch * 32 + q]);
-                        if (a.relu[l]) x = fmaxf(x, 0.f);
-                        v[q] = valid ? x : -FLT_MAX;
+                        for (int q = 0; q < 32; ++q) {
+                            float x = fmaf(__uint_as_float(d[q]), sl[l][ch * 32 + q], tl[l][ch * 32 + q]);
+                            if (a.relu[l]) x = fmaxf(x, 0.f);
+                            v[q] = valid ? x : -FLT_MAX;
+                        }
+                        mx = warp_colmax_32x32(v, lane);
                     }
-                    float mx = warp_colmax_32x32(v, lane);
-                    if (warps_per_group > 1) {
+                    if (quarters_per_group > 1) {
                         s_red[warp][lane] = mx;
                         __syncthreads();
-                        if ((warp % warps_per_group) == 0)
-                            for (int o = 1; o < warps_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
+                        if ((quarter % quarters_per_group) == 0)
+                            for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
                         __syncthreads();
                     }
-                    if ((warp % warps_per_group) == 0 && wg < a.groups)
+                    if (ch < nch && (quarter % quarters_per_group) == 0 && wg < a.groups)
                         a.out[(size_t)wg * a.Ntot[l] + split * Nlast + ch * 32 + lane] = mx;
                 }
                 fence_before_thread_sync();   // D fully read before the next tile's MMAs may overwrite it
@@ -298,7 +309,9 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const float* __re
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3, cs = warp >> 2;
+    const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* whi = base;
     uint8_t* wlo = base + (size_t)N * Kd * 4;
@@ -310,11 +323,11 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const float* __re
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = s_tmem;
-    const uint32_t row_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int ch = 0; ch < Kd / 32; ++ch) {
+    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int ch = cs; ch < Kd / 32; ch += kTcChunkWarps) {
         float h[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) h[q] = A[(size_t)tid * Kd + ch * 32 + q];
+        for (int q = 0; q < 32; ++q) h[q] = A[(size_t)row * Kd + ch * 32 + q];
         store_a_chunk(row_taddr, ch, h);
     }
     tmem_st_wait();
@@ -327,12 +340,12 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const float* __re
     }
     mbar_wait(&s_mbar, 0);
     fence_after_thread_sync();
-    for (int ch = 0; ch < N / 32; ++ch) {
+    for (int ch = cs; ch < N / 32; ch += kTcChunkWarps) {
         uint32_t d[32];
         tmem_ld32(row_taddr + D_COL + ch * 32, d);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) D[(size_t)tid * N + ch * 32 + q] = __uint_as_float(d[q]);
+        for (int q = 0; q < 32; ++q) D[(size_t)row * N + ch * 32 + q] = __uint_as_float(d[q]);
     }
     fence_before_thread_sync();
     __syncthreads();
