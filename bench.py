@@ -147,6 +147,7 @@ def main():
     import torch.distributed as dist
 
     from scanobjectnn_b200 import _lib, ops, pointnet2_cls_ssg
+    from scanobjectnn_b200.shard import max_over_ranks, rank_seed
     from scanobjectnn_b200.synthetic import make_clouds
 
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +163,7 @@ def main():
     params = pointnet2_cls_ssg.init_params(seed=1, device=dev, randomize_bn=True)
     # input pool larger than L2 (126 MB): 192 distinct batches x 786 KB = 151 MB, rotated every step
     POOL = 192
-    base = make_clouds("ball", B, N, seed=1001 + rank)
+    base = make_clouds("ball", B, N, seed=rank_seed(1001, rank))
     rng = np.random.default_rng(rank)
     pool_host = torch.empty((POOL, B, N, 3), dtype=torch.float32).pin_memory()
     for i in range(POOL):
@@ -216,12 +217,7 @@ def main():
             step_fn(warmup + i)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1), device=dev)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

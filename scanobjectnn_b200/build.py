@@ -65,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
     if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
