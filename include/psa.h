@@ -202,7 +202,8 @@ PSA_API int psa_set_mlp_mode(int mode);
 PSA_API int psa_get_mlp_mode(void);
 
 /* Diagnostic: one 128-row tile through one tensor-core layer, D[128,N] = A[128,Kd] . W[Kd,N] (Kd, N in {64,128}). */
-PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, psa_stream_t stream);
+PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, void* scratch /* 6*Kd*N bytes */,
+                            psa_stream_t stream);
 
 /* Fused EdgeConv, inference mode (dgcnn/models/dgcnn.py:31-47 pattern): x (b,n,c), nn_idx (b,n,k) ->
  * out (b,n,C_L) = max_j MLP([x_i, x_j - x_i]); mlp->channels[0] must equal 2c. */

@@ -102,3 +102,28 @@ def edgeconv(x, nn_idx, params, scopes, dtype=np.float64):
     ctr = np.broadcast_to(x[:, :, None, :], nb.shape)
     edge = np.concatenate([ctr, nb - ctr], axis=-1)
     return mlp_chain(edge, params, scopes, dtype=dtype).max(axis=2)
+
+
+def pointnet2_cls_bga(point_cloud, params, dtype=np.float64):
+    """pointnet2/models/pointnet2_cls_bga.py:21-75, is_training=False -> class_pred, seg_pred."""
+    xyz = np.asarray(point_cloud, np.float32)[:, :, :3]
+    b = xyz.shape[0]
+    l1_xyz, l1_points, _ = sa_module(xyz, None, 512, 0.2, 64, [64, 64, 128], False, "layer1", params, dtype)
+    l2_xyz, l2_points, _ = sa_module(l1_xyz, l1_points.astype(np.float32), 128, 0.4, 64, [128, 128, 256], False, "layer2", params, dtype)
+    l3_xyz, l3_points, _ = sa_module(l2_xyz, l2_points.astype(np.float32), None, None, None, [256, 512, 1024], True, "layer3", params, dtype)
+    net = mlp_chain(l3_points.reshape(b, -1), params, ["fc1", "fc2"], dtype=dtype)
+    class_vector = net[:, None, :]
+    class_pred = mlp_chain(net, params, ["fc3"], [False], dtype)
+    l2p = fp_module(l2_xyz, l3_xyz, l2_points.astype(np.float32), class_vector.astype(np.float32), [256, 256], "fa_layer1", params, dtype)
+    l1p = fp_module(l1_xyz, l2_xyz, l1_points.astype(np.float32), l2p.astype(np.float32), [256, 128], "fa_layer2", params, dtype)
+    l0p = fp_module(xyz, l1_xyz, None, l1p.astype(np.float32), [128, 128, 128], "fa_layer3", params, dtype)
+    feats = mlp_chain(l0p, params, ["seg_fc1"], dtype=dtype)
+    seg = mlp_chain(feats, params, ["seg_fc2"], [False], dtype)
+    return class_pred, seg
+
+
+def dgcnn_stage(x, k, params, scopes, dtype=np.float64):
+    """knn graph (canonical fp32 order, C oracle) + EdgeConv + max over k, on the given fp32 features."""
+    x = np.asarray(x, np.float32)
+    idx = orc.dgcnn_knn(x, k)
+    return idx, edgeconv(x, idx, params, scopes, dtype)

@@ -53,7 +53,7 @@ SIGNATURES = {
     "psa_sa_module_infer": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, C.POINTER(PsaMlp), _p, _p, _p, _p, C.c_size_t, _p],
     "psa_set_mlp_mode": [_i],
     "psa_get_mlp_mode": [],
-    "psa_tc_selftest": [_i, _i, _p, _p, _p, _p],
+    "psa_tc_selftest": [_i, _i, _p, _p, _p, _p, _p],
     "psa_edgeconv_infer": [_i, _i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p],
 }
 INFO_SYMBOLS = ("psa_version", "psa_last_error", "psa_sm_arch", "psa_shared_mlp_workspace_bytes",

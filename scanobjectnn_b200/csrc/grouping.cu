@@ -32,41 +32,55 @@ float ball_query_threshold(float radius, bool* none) {
 
 constexpr int kBqWarps = 8;
 
-// One warp per query.  sx/sy/sz: the cloud's n points in shared memory.  Writes the idx row (global or shared)
-// and returns the clamped count.  Rows with an empty ball are filled with 0.
+// squared distances of two dataset points to one query with the packed f32x2 pipe (FADD2/FMUL2/FFMA2): same
+// per-element IEEE operations, same order (dy*dy, then fma dx, then fma dz) as dist2_ref_gpu, half the instructions
+__device__ __forceinline__ float2 dist2_pair(float2 x, float2 y, float2 z, float2 nqx, float2 nqy, float2 nqz) {
+    const float2 dx = __fadd2_rn(x, nqx), dy = __fadd2_rn(y, nqy), dz = __fadd2_rn(z, nqz);   // x_k - q: sign is irrelevant squared
+    float2 t = __fmul2_rn(dy, dy);
+    t = __ffma2_rn(dx, dx, t);
+    t = __ffma2_rn(dz, dz, t);
+    return t;
+}
+
+// One warp per query, 128 points per step (4 consecutive points per lane, float4 from the SoA arrays).  sx/sy/sz hold
+// the cloud padded to a multiple of 128 with +inf (distance +inf: never inside).  The reference's "first nsample in
+// index order" rule is kept by ballot + prefix-popcount compaction: a hit at (lane, j) lands at
+// cnt + #hits in lower lanes + #own hits with j' < j.  Writes the idx row and returns the clamped count; empty -> 0s.
 __device__ __forceinline__ int ball_query_warp(int n, int nsample, float thr, bool none, const float* sx,
                                                const float* sy, const float* sz, float qx, float qy, float qz,
                                                int* idxrow, int lane) {
     int cnt = 0, first = -1;
     if (!none) {
-        for (int base = 0; base < n && cnt < nsample; base += 64) {
-            // two 32-point chunks per step for ILP; order preserved (chunk 0 before chunk 1)
-            const int k0 = base + lane, k1 = base + 32 + lane;
-            bool in0 = false, in1 = false;
-            if (k0 < n) {
-                // reference operand order: x2 (query) - x1 (dataset), tf_grouping_g.cu:18-24
-                float d = dist2_ref_gpu(qx - sx[k0], qy - sy[k0], qz - sz[k0]);
-                in0 = !(d > thr);
+        const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+        const unsigned lt = lanemask_lt();
+        for (int base = 0; base < n && cnt < nsample; base += 128) {
+            const int k = base + lane * 4;
+            const float4 X = *reinterpret_cast<const float4*>(sx + k);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + k);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + k);
+            const float2 d01 = dist2_pair(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
+            const float2 d23 = dist2_pair(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
+            // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
+            bool i0 = !(d01.x > thr), i1 = !(d01.y > thr), i2 = !(d23.x > thr), i3 = !(d23.y > thr);
+            if (base + 128 > n) {   // last chunk: the +inf padding must not count even when the QUERY is NaN (NaN - inf = NaN)
+                i0 = i0 && (k < n); i1 = i1 && (k + 1 < n); i2 = i2 && (k + 2 < n); i3 = i3 && (k + 3 < n);
             }
-            if (k1 < n) {
-                float d = dist2_ref_gpu(qx - sx[k1], qy - sy[k1], qz - sz[k1]);
-                in1 = !(d > thr);
+            const unsigned m4 = (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
+            const unsigned anyb = __ballot_sync(0xffffffffu, m4 != 0u);
+            if (anyb == 0u) continue;
+            const unsigned b0 = __ballot_sync(0xffffffffu, i0), b1 = __ballot_sync(0xffffffffu, i1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, i2), b3 = __ballot_sync(0xffffffffu, i3);
+            if (first < 0) {
+                const int lf = __ffs(anyb) - 1;
+                const unsigned mf = __shfl_sync(0xffffffffu, m4, lf);
+                first = base + lf * 4 + (__ffs(mf) - 1);
             }
-            const unsigned b0 = __ballot_sync(0xffffffffu, in0);
-            const unsigned b1 = __ballot_sync(0xffffffffu, in1);
-            if ((b0 | b1) == 0u) continue;
-            const unsigned lt = lanemask_lt();
-            const int c0 = __popc(b0);
-            if (first < 0) first = b0 ? (base + __ffs(b0) - 1) : (base + 32 + __ffs(b1) - 1);
-            if (in0) {
-                int pos = cnt + __popc(b0 & lt);
-                if (pos < nsample) idxrow[pos] = k0;
-            }
-            if (in1) {
-                int pos = cnt + c0 + __popc(b1 & lt);
-                if (pos < nsample) idxrow[pos] = k1;
-            }
-            cnt += c0 + __popc(b1);
+            int pos = cnt + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+            if (i0) { if (pos < nsample) idxrow[pos] = k; ++pos; }
+            if (i1) { if (pos < nsample) idxrow[pos] = k + 1; ++pos; }
+            if (i2) { if (pos < nsample) idxrow[pos] = k + 2; ++pos; }
+            if (i3) { if (pos < nsample) idxrow[pos] = k + 3; }
+            cnt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
         }
     }
     if (cnt > nsample) cnt = nsample;
@@ -78,10 +92,11 @@ __device__ __forceinline__ int ball_query_warp(int n, int nsample, float thr, bo
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(int n, int m, int nsample, float thr, int none, int q_per_cta, const float* __restrict__ xyz1,
                   const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
-    extern __shared__ float smem_f[];
+    extern __shared__ __align__(16) float smem_f[];
+    const int np = (n + 127) & ~127;          // padded point count
     float* sx = smem_f;
-    float* sy = sx + n;
-    float* sz = sy + n;
+    float* sy = sx + np;
+    float* sz = sy + np;
     const int cloud = blockIdx.y;
     const float* p1 = xyz1 + (size_t)cloud * n * 3;
     for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
@@ -89,6 +104,8 @@ ball_query_kernel(int n, int m, int nsample, float thr, int none, int q_per_cta,
         float v = p1[i];
         if (c == 0) sx[k] = v; else if (c == 1) sy[k] = v; else sz[k] = v;
     }
+    const float inf = __int_as_float(0x7f800000);
+    for (int k = n + threadIdx.x; k < np; k += blockDim.x) { sx[k] = inf; sy[k] = inf; sz[k] = inf; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * q_per_cta;
@@ -219,7 +236,7 @@ extern "C" int psa_query_ball_point(int b, int n, int m, float radius, int nsamp
     if (b == 0 || m == 0) return PSA_OK;
     PSA_REQUIRE(idx != nullptr || nsample == 0, "QueryBallPoint: null idx");
     PSA_REQUIRE((xyz1 != nullptr || n == 0) && xyz2 != nullptr, "QueryBallPoint: null input");
-    size_t smem = (size_t)n * 3 * sizeof(float);
+    size_t smem = (size_t)((n + 127) & ~127) * 3 * sizeof(float);
     PSA_SUPPORTED(smem <= 200 * 1024, "query_ball_point: n=%d exceeds the shared-memory resident limit", n);
     bool none = false;
     float thr = ball_query_threshold(radius, &none);

@@ -498,63 +498,89 @@ dense_layer_kernel(const __grid_constant__ DenseArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Small-M layer (rows <= 32: the FC heads, B = 32 rows x 1024 -> 512 -> 256 -> num_class).  A 128-row GEMM tile would
-// leave 3/4 of the MMA rows empty and only N/128 CTAs busy; here a CTA owns 32 output columns, its 8 warps split K,
-// lane = column (coalesced weight rows), the x slice sits transposed in shared memory so 4 rows come per LDS.128,
-// and the 8 partial sums are combined through shared memory in a fixed order (deterministic).
+// Small-M layer (rows <= 32: the FC heads, B = 32 rows x 1024 -> 512 -> 256 -> num_class).  The work is tiny and a
+// single CTA per column block would be one long L2-latency chain, so K is split over the grid as well:
+//   pass 1  CTA (col block of 32, k slice of 64): x slice staged transposed in shared memory, 4 warps x 16 k,
+//           lane = output column (coalesced weight rows), 32 row-accumulators per thread, warps combined in shared
+//           memory in fixed order, partial (32 x 32) written to the workspace;
+//   pass 2  sums the K-slices in ascending order (deterministic) and applies scale / shift / ReLU.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kFcWarps = 8;
+constexpr int kFcKs = 64;      // k per CTA
+constexpr int kFcWarps = 4;
 
 __global__ void __launch_bounds__(kFcWarps * 32)
-fc_small_kernel(const __grid_constant__ DenseArgs a) {
-    extern __shared__ __align__(16) float smem_f[];
+fc_partial_kernel(const __grid_constant__ DenseArgs a, float* __restrict__ partial) {
+    __shared__ float xs[kFcKs * 33];                  // [kk][r] padded: conflict-free transposed staging
+    __shared__ float red[kFcWarps][32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rows = (int)a.rows;
-    const int Kc = (a.K + kFcWarps - 1) / kFcWarps;          // k-slice per warp
-    const int k0 = warp * Kc;
-    const int kn = max(0, min(Kc, a.K - k0));
-    float* xs = smem_f + (size_t)warp * Kc * 32;              // [kk][r], r fastest
-    for (int e = lane; e < Kc * 32; e += 32) xs[e] = 0.f;
-    __syncwarp();
-    for (int r = 0; r < rows; ++r)
-        for (int kk = lane; kk < kn; kk += 32) xs[kk * 32 + r] = __ldg(a.x + (size_t)r * a.K + k0 + kk);
-    __syncwarp();
+    const int ks = blockIdx.y, k0 = ks * kFcKs;
+    const int kn = min(kFcKs, a.K - k0);
+    for (int e0 = threadIdx.x; e0 < 32 * kFcKs; e0 += kFcWarps * 32 * 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kFcWarps * 32;
+            const int r = e / kFcKs, kk = e - r * kFcKs;
+            v[u] = (e < 32 * kFcKs && r < rows && kk < kn) ? __ldg(a.x + (size_t)r * a.K + k0 + kk) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kFcWarps * 32;
+            if (e < 32 * kFcKs) { const int r = e / kFcKs, kk = e - r * kFcKs; xs[kk * 33 + r] = v[u]; }
+        }
+    }
     const int col = blockIdx.x * 32 + lane;
+    constexpr int KW = kFcKs / kFcWarps;              // 16 k per warp
+    float wv[KW];
+#pragma unroll
+    for (int u = 0; u < KW; ++u) {
+        const int k = k0 + warp * KW + u;
+        wv[u] = (col < a.N && k < a.K) ? __ldg(a.W + (size_t)k * a.N + col) : 0.f;
+    }
+    __syncthreads();
     float acc[32];
 #pragma unroll
     for (int r = 0; r < 32; ++r) acc[r] = 0.f;
-    if (col < a.N) {
-#pragma unroll 2
-        for (int kk = 0; kk < kn; ++kk) {
-            const float wv = __ldg(a.W + (size_t)(k0 + kk) * a.N + col);
-            const float4* xr = reinterpret_cast<const float4*>(xs + kk * 32);
 #pragma unroll
-            for (int r4 = 0; r4 < 8; ++r4) {
-                const float4 xv = xr[r4];
-                acc[4 * r4 + 0] = fmaf(xv.x, wv, acc[4 * r4 + 0]);
-                acc[4 * r4 + 1] = fmaf(xv.y, wv, acc[4 * r4 + 1]);
-                acc[4 * r4 + 2] = fmaf(xv.z, wv, acc[4 * r4 + 2]);
-                acc[4 * r4 + 3] = fmaf(xv.w, wv, acc[4 * r4 + 3]);
-            }
-        }
+    for (int u = 0; u < KW; ++u) {
+        const float* xr = xs + (warp * KW + u) * 33;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) acc[r] = fmaf(xr[r], wv[u], acc[r]);
     }
-    __syncthreads();                                          // everyone is done with xs: reuse it for the partials
-    float* red = smem_f;                                      // [warp][r][lane]
 #pragma unroll
-    for (int r = 0; r < 32; ++r) red[((size_t)warp * 32 + r) * 32 + lane] = acc[r];
+    for (int r = 0; r < 32; ++r) red[warp][r][lane] = acc[r];
     __syncthreads();
-    if (col < a.N) {
-        const float sc = a.scale ? __ldg(a.scale + col) : 1.f;
-        const float sh = a.shift ? __ldg(a.shift + col) : 0.f;
+    if (col < a.N)
         for (int r = warp; r < rows; r += kFcWarps) {
-            float s = 0.f;
+            float s = red[0][r][lane];
 #pragma unroll
-            for (int w = 0; w < kFcWarps; ++w) s += red[((size_t)w * 32 + r) * 32 + lane];
-            float v = fmaf(s, sc, sh);
-            if (a.relu) v = fmaxf(v, 0.f);
-            a.out[(size_t)r * a.N + col] = v;
+            for (int w = 1; w < kFcWarps; ++w) s += red[w][r][lane];
+            partial[((size_t)ks * 32 + r) * a.N + col] = s;
         }
+}
+
+__global__ void fc_reduce_kernel(const __grid_constant__ DenseArgs a, const float* __restrict__ partial, int nks) {
+    const int total = (int)a.rows * a.N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int r = e / a.N, col = e - r * a.N;
+        float s = 0.f;
+        for (int ks = 0; ks < nks; ++ks) s += partial[((size_t)ks * 32 + r) * a.N + col];
+        float v = fmaf(s, a.scale ? __ldg(a.scale + col) : 1.f, a.shift ? __ldg(a.shift + col) : 0.f);
+        if (a.relu) v = fmaxf(v, 0.f);
+        a.out[e] = v;
     }
+}
+
+size_t fc_small_workspace_bytes(int K, int N) { return (size_t)((K + kFcKs - 1) / kFcKs) * 32 * N * sizeof(float); }
+
+int launch_fc_small(const DenseArgs& d, float* partial, cudaStream_t st) {
+    const int nks = (d.K + kFcKs - 1) / kFcKs;
+    dim3 grid((d.N + 31) / 32, nks);
+    fc_partial_kernel<<<grid, kFcWarps * 32, 0, st>>>(d, partial);
+    const int total = (int)d.rows * d.N;
+    fc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(d, partial, nks);
+    return check_launch("fc_small");
 }
 
 __global__ void fill_ord_neg_inf_kernel(long long total, int* out) {
@@ -579,15 +605,6 @@ static int validate_mlp(const psa_mlp* mlp, const char* who) {
 }
 
 int launch_dense(const DenseArgs& d, cudaStream_t st) {
-    if (d.rows <= 32 && d.pool_k == 1) {
-        const int Kc = (d.K + kFcWarps - 1) / kFcWarps;
-        size_t smem = (size_t)kFcWarps * 32 * sizeof(float) * (size_t)max(Kc, 32);
-        if (smem <= 200 * 1024) {
-            PSA_CUDA(cudaFuncSetAttribute(fc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            fc_small_kernel<<<(d.N + 31) / 32, kFcWarps * 32, smem, st>>>(d);
-            return check_launch("fc_small_kernel");
-        }
-    }
     const long long tiles_m = (d.rows + BM - 1) / BM;
     PSA_SUPPORTED(tiles_m <= 0x7fffffffLL, "shared_mlp: too many rows");
     if (d.pool_k > 1) {
@@ -640,43 +657,6 @@ static int launch_fused(FusedArgs& a, cudaStream_t st, const char* who) {
 }  // namespace psa
 
 using namespace psa;
-
-extern "C" size_t psa_shared_mlp_workspace_bytes(long long rows, const psa_mlp* mlp) {
-    if (mlp == nullptr || mlp->n_layers <= 1) return 0;
-    int cmax = 0;
-    for (int l = 1; l < mlp->n_layers; ++l) cmax = max(cmax, mlp->channels[l]);
-    return 2 * (size_t)rows * cmax * sizeof(float);
-}
-
-extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const psa_mlp* mlp, float* out,
-                              void* workspace, size_t workspace_bytes, psa_stream_t stream) {
-    int rc = validate_mlp(mlp, "shared_mlp");
-    if (rc != PSA_OK) return rc;
-    PSA_REQUIRE(rows >= 0 && pool_k >= 1, "shared_mlp: rows=%lld pool_k=%d", rows, pool_k);
-    if (rows == 0) return PSA_OK;
-    PSA_REQUIRE(rows % pool_k == 0, "shared_mlp: rows=%lld is not a multiple of pool_k=%d", rows, pool_k);
-    PSA_REQUIRE(x && out, "shared_mlp: null buffer");
-    const int L = mlp->n_layers;
-    const size_t need = psa_shared_mlp_workspace_bytes(rows, mlp);
-    PSA_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need),
-                "shared_mlp: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
-    float* ws0 = reinterpret_cast<float*>(workspace);
-    float* ws1 = ws0 ? ws0 + need / sizeof(float) / 2 : nullptr;
-    const float* cur = x;
-    cudaStream_t st = as_stream(stream);
-    for (int l = 0; l < L; ++l) {
-        DenseArgs d;
-        d.rows = rows; d.K = mlp->channels[l]; d.N = mlp->channels[l + 1];
-        d.pool_k = (l == L - 1) ? pool_k : 1;
-        d.relu = mlp->relu[l];
-        d.x = cur; d.W = mlp->weight[l]; d.scale = mlp->scale[l]; d.shift = mlp->shift[l];
-        d.out = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
-        rc = launch_dense(d, st);
-        if (rc != PSA_OK) return rc;
-        cur = d.out;
-    }
-    return PSA_OK;
-}
 
 namespace psa {
 // fp32-FMA fused set-abstraction level (gather + MLP chain in shared memory + max-pool); idx already computed

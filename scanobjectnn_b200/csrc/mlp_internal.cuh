@@ -18,6 +18,8 @@ struct DenseArgs {
 
 
 int launch_dense(const DenseArgs& d, cudaStream_t st);
+size_t fc_small_workspace_bytes(int K, int N);
+int launch_fc_small(const DenseArgs& d, float* partial, cudaStream_t st);   // rows <= 32
 int sa_module_simt(int b, int n, int m, int c, int nsample, const float* xyz, const float* new_xyz, const float* points,
                    const int* idx, const psa_mlp* mlp, float* out, cudaStream_t st);
 int validate_mlp_public(const psa_mlp* mlp, const char* who);

@@ -8,8 +8,10 @@
 //             with the dense kernel); each row-thread gathers its U row (512 B), adds the 3-term xyz part in FMAs,
 //             applies the folded BN affine + ReLU, and writes the result straight into TENSOR MEMORY as the A operand
 //             of layer 2 -- the (B,m,K,C) tensors of the reference never exist, not even in shared memory.
-//   layers 2+ tcgen05.mma, A from TMEM (lane = row), B = weights RESIDENT in shared memory for the whole persistent
-//             CTA (canonical K-major SWIZZLE_128B layout built once by the CTA), D in TMEM.  Between layers the
+//   layers 2+ tcgen05.mma, A from TMEM (lane = row), B = weights in shared memory in the canonical K-major SWIZZLE_128B
+//             layout, dropped there by cp.async.bulk from pre-arranged images: RESIDENT for the whole persistent CTA,
+//             except that a last layer too big to fit is streamed one 128-channel tile at a time (L2 -> smem while the
+//             row warps run the previous epilogue), D in TMEM.  Between layers the
 //             four row-warps pull D with tcgen05.ld, apply affine + ReLU, and push the next A operand with tcgen05.st.
 //   max-pool  the last epilogue reduces each neighbourhood's rows with a transposing warp butterfly (31 shuffles per
 //             32 columns) and writes (B,m,C_out) coalesced.
@@ -18,8 +20,7 @@
 //   trunc_tf32(a)*trunc_tf32(w) + tf32(a - trunc(a))*trunc_tf32(w) + bf16(a)*bf16(w - trunc(w))
 // (operands quantised by this code, so the tensor core sees exact values; fp32 accumulation in TMEM).  Operand-split
 // error ~3e-6 relative (tests/test_mlp_gpu.py holds the whole chain to 1e-5 against fp64).  The bf16 third term keeps
-// the resident weights at 6 B/element so that PointNet++'s 128->128->256 level fits in 227 KB when the last layer's
-// output channels are split over two CTAs.
+// the weights at 6 B/element: PointNet++'s 128->128->256 level keeps W2 (96 KB) resident and streams W3 in two 96 KB tiles.
 #include <float.h>
 
 #include "common.cuh"
@@ -35,6 +36,33 @@ constexpr int kTcChunkWarps = kTcThreads / 128;
 constexpr int kTmemCols = 512;
 constexpr uint32_t D_COL = 0, AHI_COL = 128, ALO_COL = 256, ABF_COL = 384;
 constexpr int kMaxTcLayers = 2;
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight images.  A tensor layer W (K x N, row-major, fp32) is pre-arranged ONCE per call (tc_prep_weights_kernel) into
+// blocks that can be dropped into shared memory by a single cp.async.bulk and fed to tcgen05.mma unchanged:
+//   block (nt, kc) covers output channels [nt*Nt, nt*Nt+Nt) x input channels [kc*64, kc*64+64),  Nt = min(N,128):
+//     hi : trunc_tf32(w)              [Nt][64] fp32, K-major SWIZZLE_128B (two 32-wide K blocks)   Nt*256 B
+//     lo : bf16(w - trunc_tf32(w))    [Nt][64] bf16, K-major SWIZZLE_128B (one 64-wide K block)    Nt*128 B
+//   blocks stored in (nt major, kc minor) order.  6 bytes per weight.
+// ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int tc_nt(int N) { return N >= 128 ? 128 : 64; }
+__host__ __device__ inline uint32_t tc_block_bytes(int N) { return (uint32_t)tc_nt(N) * 64u * 6u; }
+__host__ __device__ inline size_t tc_image_bytes(int K, int N) { return (size_t)(N / tc_nt(N)) * (K / 64) * tc_block_bytes(N); }
+
+// K rows of W are zero-padded to Kp (multiple of 64)
+__global__ void tc_prep_weights_kernel(int K, int Kp, int N, const float* __restrict__ W, uint8_t* __restrict__ image) {
+    const int Nt = tc_nt(N), KC = Kp / 64;
+    const uint32_t bb = tc_block_bytes(N);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Kp * N; e += gridDim.x * blockDim.x) {
+        const int n = e % N, k = e / N;                       // coalesced read of W rows
+        const float w = k < K ? __ldg(W + e) : 0.f;
+        const float hi = tf32_trunc(w);
+        uint8_t* blk = image + (size_t)((n / Nt) * KC + (k >> 6)) * bb;
+        const uint32_t nn = n % Nt, kk = k & 63;
+        *reinterpret_cast<float*>(blk + swz_off_f32(nn, kk, Nt)) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blk + (uint32_t)Nt * 256u + swz_off_bf16(nn, kk, Nt)) = __float2bfloat16_rn(w - hi);
+    }
+}
 
 struct TcArgs {
     long long groups;      // neighbourhoods = b*m
@@ -52,12 +80,12 @@ struct TcArgs {
     int C1, relu1;
     // tensor layers
     int nl;
-    const float* W[kMaxTcLayers];
+    const uint8_t* image[kMaxTcLayers];   // weight images (global)
     const float* s[kMaxTcLayers];
     const float* t[kMaxTcLayers];
     int relu[kMaxTcLayers];
     int Kd[kMaxTcLayers], Ntot[kMaxTcLayers];
-    int nsplit;            // CTAs sharing one tile, each owning Ntot[last]/nsplit output channels
+    int stream_last;       // 1: the last layer's weights do not fit next to the others -> one 128-channel tile at a time
 };
 
 // quantise one row-chunk of 32 activations into the three A operands and store them into TMEM
@@ -75,33 +103,24 @@ __device__ __forceinline__ void store_a_chunk(uint32_t row_taddr, int ch, const 
     tmem_st16(row_taddr + ABF_COL + ch * 16, p);
 }
 
-// Build the resident B operand of one tensor layer: W (global, [Kd][Ntot] row-major) columns [n_off, n_off+N) ->
-// whi: trunc_tf32(w) as [N][Kd] K-major SW128 fp32;  wlo: bf16(w - trunc_tf32(w)) as [N][Kd] K-major SW128 bf16.
-__device__ __forceinline__ void stage_weights(uint8_t* whi, uint8_t* wlo, const float* __restrict__ W, int Kd, int Ntot,
-                                              int n_off, int N, int tid, int nthreads) {
-    for (int e = tid; e < N * Kd; e += nthreads) {
-        const int nn = e % N, k = e / N;
-        const float w = __ldg(W + (size_t)k * Ntot + n_off + nn);
-        const float hi = tf32_trunc(w);
-        *reinterpret_cast<float*>(whi + swz_off_f32(nn, k, N)) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(wlo + swz_off_bf16(nn, k, N)) = __float2bfloat16_rn(w - hi);
-    }
-}
-
-// one elected thread: D[128 x N] = A . W^T as the three-term split
-__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t whi_addr, uint32_t wlo_addr, int Kd, int N) {
+// one elected thread: D[128 x Nt] = A[128 x 64*KC] . W_tile^T as the three-term split over KC resident blocks.
+// The tensor core truncates (rounds toward zero) every time it adds into D, so the error grows with the number of
+// accumulation steps taken while D is large: the two small correction terms go first, the main term last.
+__device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t blocks_addr, int KC, int Nt) {
     const uint32_t d = tmem_base + D_COL;
-    const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, N);
-    const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, N);
-    const uint32_t blk = (uint32_t)N * 128u;
-    // The tensor core truncates (rounds toward zero) every time it adds into D, so the error grows with the number of
-    // accumulation steps taken while D is large: run the two small correction terms first, the main term last.
-    for (int s = 0; s < Kd / 16; ++s)
-        mma_bf16_ts(d, tmem_base + ABF_COL + s * 8, make_smem_desc_sw128(wlo_addr + (s >> 2) * blk + (s & 3) * 32), id_bf16, s > 0);
-    for (int s = 0; s < Kd / 8; ++s)
-        mma_tf32_ts(d, tmem_base + ALO_COL + s * 8, make_smem_desc_sw128(whi_addr + (s >> 2) * blk + (s & 3) * 32), id_tf32, 1);
-    for (int s = 0; s < Kd / 8; ++s)
-        mma_tf32_ts(d, tmem_base + AHI_COL + s * 8, make_smem_desc_sw128(whi_addr + (s >> 2) * blk + (s & 3) * 32), id_tf32, 1);
+    const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, Nt);
+    const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, Nt);
+    const uint32_t bb = (uint32_t)Nt * 64u * 6u, kblk = (uint32_t)Nt * 128u, lo_off = (uint32_t)Nt * 256u;
+    uint32_t acc = 0;
+    for (int kc = 0; kc < KC; ++kc)
+        for (int s = 0; s < 4; ++s, acc = 1)
+            mma_bf16_ts(d, tmem_base + ABF_COL + kc * 32 + s * 8, make_smem_desc_sw128(blocks_addr + kc * bb + lo_off + s * 32), id_bf16, acc);
+    for (int kc = 0; kc < KC; ++kc)
+        for (int s = 0; s < 8; ++s)
+            mma_tf32_ts(d, tmem_base + ALO_COL + kc * 64 + s * 8, make_smem_desc_sw128(blocks_addr + kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
+    for (int kc = 0; kc < KC; ++kc)
+        for (int s = 0; s < 8; ++s)
+            mma_tf32_ts(d, tmem_base + AHI_COL + kc * 64 + s * 8, make_smem_desc_sw128(blocks_addr + kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
 }
 
 // transposing butterfly: v[q] = column q of this lane's row; afterwards v[0] on lane l = max over the warp's 32 rows of column l
@@ -120,9 +139,11 @@ __device__ __forceinline__ float warp_colmax_32x32(float (&v)[32], int lane) {
     return v[0];
 }
 
+// shared-memory plan: resident blocks of layers [0, nres) back to back, then (stream_last) a ring that holds ONE
+// 128-channel tile of the last layer (KC blocks), then the per-channel vectors
 struct TcSmemLayout {
-    uint32_t whi[kMaxTcLayers], wlo[kMaxTcLayers];   // byte offsets from the 1024-aligned base
-    uint32_t vec;                                    // float region: w1x[3*C1] s1[C1] t1[C1] then per layer s[N] t[N]
+    uint32_t w[kMaxTcLayers];    // byte offset of layer l's blocks (the ring for a streamed last layer)
+    uint32_t vec;
     uint32_t total;
 };
 
@@ -130,13 +151,13 @@ __host__ __device__ inline TcSmemLayout tc_layout(const TcArgs& a) {
     TcSmemLayout L;
     uint32_t off = 0;
     for (int l = 0; l < a.nl; ++l) {
-        const int N = (l == a.nl - 1) ? a.Ntot[l] / a.nsplit : a.Ntot[l];
-        L.whi[l] = off; off += (uint32_t)N * a.Kd[l] * 4u;
-        L.wlo[l] = off; off += (uint32_t)N * a.Kd[l] * 2u;
+        L.w[l] = off;
+        const bool streamed = a.stream_last && l == a.nl - 1;
+        off += streamed ? (uint32_t)(a.Kd[l] / 64) * tc_block_bytes(a.Ntot[l]) : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
     }
     L.vec = off;
     off += 5u * a.C1 * 4u;
-    for (int l = 0; l < a.nl; ++l) off += 2u * ((l == a.nl - 1) ? a.Ntot[l] / a.nsplit : a.Ntot[l]) * 4u;
+    for (int l = 0; l < a.nl; ++l) off += 2u * a.Ntot[l] * 4u;
     L.total = off;
     return L;
 }
@@ -144,7 +165,8 @@ __host__ __device__ inline TcSmemLayout tc_layout(const TcArgs& a) {
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_sa_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_mbar;     // MMA completion
+    __shared__ __align__(8) uint64_t s_wbar;     // weight bulk copies landed
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kTcThreads / 32][32];
 
@@ -153,14 +175,11 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
     const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const TcSmemLayout L = tc_layout(a);
-    const int split = blockIdx.x % a.nsplit;
-    const int worker = blockIdx.x / a.nsplit, nworkers = gridDim.x / a.nsplit;
     const int last = a.nl - 1;
-    const int Nlast = a.Ntot[last] / a.nsplit;
 
-    // ---- one-time setup: TMEM, barrier, resident weights, per-channel vectors ----
+    // ---- one-time setup: TMEM, barriers, resident weights (bulk copies), per-channel vectors ----
     if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { mbar_init(&s_mbar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar, 1); fence_mbar_init(); }
     float* vec = reinterpret_cast<float*>(base + L.vec);
     float* w1x = vec;                       // 3*C1
     float* s1 = vec + 3 * a.C1;
@@ -169,33 +188,42 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
     float* tl[kMaxTcLayers];
     {
         float* p = t1 + a.C1;
-        for (int l = 0; l < a.nl; ++l) {
-            const int N = (l == last) ? Nlast : a.Ntot[l];
-            sl[l] = p; tl[l] = p + N; p += 2 * N;
-        }
+        for (int l = 0; l < a.nl; ++l) { sl[l] = p; tl[l] = p + a.Ntot[l]; p += 2 * a.Ntot[l]; }
     }
     for (int i = tid; i < 3 * a.C1; i += kTcThreads) w1x[i] = __ldg(a.w1x + i);
     for (int i = tid; i < a.C1; i += kTcThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
-    for (int l = 0; l < a.nl; ++l) {
-        const int N = (l == last) ? Nlast : a.Ntot[l];
-        const int n_off = (l == last) ? split * Nlast : 0;
-        for (int i = tid; i < N; i += kTcThreads) {
-            sl[l][i] = a.s[l] ? __ldg(a.s[l] + n_off + i) : 1.f;
-            tl[l][i] = __ldg(a.t[l] + n_off + i);
+    for (int l = 0; l < a.nl; ++l)
+        for (int i = tid; i < a.Ntot[l]; i += kTcThreads) {
+            sl[l][i] = a.s[l] ? __ldg(a.s[l] + i) : 1.f;
+            tl[l][i] = __ldg(a.t[l] + i);
         }
-        stage_weights(base + L.whi[l], base + L.wlo[l], a.W[l], a.Kd[l], a.Ntot[l], n_off, N, tid, kTcThreads);
+    __syncthreads();                          // barrier inits visible before anybody arms / waits
+    uint32_t wphase = 0;
+    const uint32_t ring_bytes = (uint32_t)(a.Kd[last] / 64) * tc_block_bytes(a.Ntot[last]);   // one n-tile of the last layer
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int l = 0; l < a.nl; ++l) total += (a.stream_last && l == last) ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+        mbar_expect_tx(&s_wbar, total);
+        for (int l = 0; l < a.nl; ++l) {
+            const uint32_t bytes = (a.stream_last && l == last) ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+            for (uint32_t o = 0; o < bytes; o += 32768u)       // bulk copies of <= 32 KB
+                bulk_g2s(base + L.w[l] + o, a.image[l] + o, min(32768u, bytes - o), &s_wbar);
+        }
+        mbar_wait(&s_wbar, wphase);
     }
-    fence_proxy_async_smem();
+    wphase ^= 1u;
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = s_tmem;
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0;
+    int ring_tile = 0;                        // which n-tile of the last layer the ring currently holds / is receiving
+    bool ring_pending = false;                // thread 0: a ring load is in flight
 
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
-    for (long long tile = worker; tile < ntiles; tile += nworkers) {
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long g0 = tile * G;
         const long long gid = g0 + row / a.K;
         const bool valid = gid < a.groups;
@@ -223,13 +251,21 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) h[q] = 0.f;
                 }
+                const float4* wx4 = reinterpret_cast<const float4*>(w1x + ch * 32);
+                const float4* wy4 = reinterpret_cast<const float4*>(w1x + a.C1 + ch * 32);
+                const float4* wz4 = reinterpret_cast<const float4*>(w1x + 2 * a.C1 + ch * 32);
+                const float4* s4 = reinterpret_cast<const float4*>(s1 + ch * 32);
+                const float4* t4 = reinterpret_cast<const float4*>(t1 + ch * 32);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int c = ch * 32 + q;
-                    float pre = fmaf(dz, w1x[2 * a.C1 + c], fmaf(dy, w1x[a.C1 + c], fmaf(dx, w1x[c], h[q])));
-                    float v = fmaf(pre, s1[c], t1[c]);
-                    if (a.relu1) v = fmaxf(v, 0.f);
-                    h[q] = valid ? v : 0.f;
+                for (int q = 0; q < 8; ++q) {
+                    const float4 wx = wx4[q], wy = wy4[q], wz = wz4[q], sc = s4[q], sh = t4[q];
+                    float v0 = fmaf(fmaf(dz, wz.x, fmaf(dy, wy.x, fmaf(dx, wx.x, h[4 * q + 0]))), sc.x, sh.x);
+                    float v1 = fmaf(fmaf(dz, wz.y, fmaf(dy, wy.y, fmaf(dx, wx.y, h[4 * q + 1]))), sc.y, sh.y);
+                    float v2 = fmaf(fmaf(dz, wz.z, fmaf(dy, wy.z, fmaf(dx, wx.z, h[4 * q + 2]))), sc.z, sh.z);
+                    float v3 = fmaf(fmaf(dz, wz.w, fmaf(dy, wy.w, fmaf(dx, wx.w, h[4 * q + 3]))), sc.w, sh.w);
+                    if (a.relu1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                    h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
+                    h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
                 }
                 store_a_chunk(row_taddr, ch, h);
             }
@@ -238,87 +274,121 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
         fence_before_thread_sync();
         __syncthreads();
         for (int l = 0; l < a.nl; ++l) {
-            const int N = (l == last) ? Nlast : a.Ntot[l];
-            if (tid == 0) {
-                fence_after_thread_sync();
-                issue_layer(tmem_base, smem_u32(base + L.whi[l]), smem_u32(base + L.wlo[l]), a.Kd[l], N);
-                mma_commit(&s_mbar);
-            }
-            mbar_wait(&s_mbar, phase);
-            phase ^= 1u;
-            fence_after_thread_sync();
-            if (l != last) {
-                for (int ch = cs; ch < N / 32; ch += kTcChunkWarps) {
-                    uint32_t d[32];
-                    tmem_ld32(row_taddr + D_COL + ch * 32, d);
-                    tmem_ld_wait();
-                    float h[32];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        float v = fmaf(__uint_as_float(d[q]), sl[l][ch * 32 + q], tl[l][ch * 32 + q]);
-                        if (a.relu[l]) v = fmaxf(v, 0.f);
-                        h[q] = valid ? v : 0.f;
-                    }
-                    store_a_chunk(row_taddr, ch, h);
+            const int Nt = tc_nt(a.Ntot[l]);
+            const int NT = a.Ntot[l] / Nt, KC = a.Kd[l] / 64;
+            const bool streamed = a.stream_last && l == last;
+            for (int nt = 0; nt < NT; ++nt) {
+                if (tid == 0) {
+                    if (streamed && ring_pending) { mbar_wait(&s_wbar, wphase); wphase ^= 1u; ring_pending = false; }
+                    fence_after_thread_sync();
+                    const uint32_t blocks = smem_u32(base + L.w[l]) + (streamed ? 0u : (uint32_t)nt * KC * tc_block_bytes(a.Ntot[l]));
+                    issue_tile(tmem_base, blocks, KC, Nt);
+                    mma_commit(&s_mbar);
                 }
-                tmem_st_wait();
-                fence_before_thread_sync();
-                __syncthreads();
-            } else {
-                // rows of one neighbourhood span K/32 lane-quarters; warps sharing a chunk slot combine through s_red
-                const int quarters_per_group = a.K / 32;        // 1, 2 or 4
-                const long long wg = g0 + (quarter * 32) / a.K; // this warp's neighbourhood
-                const int nch = N / 32;
-                for (int ch0 = 0; ch0 < nch; ch0 += kTcChunkWarps) {      // uniform trip count: barriers inside
-                    const int ch = ch0 + cs;
-                    float mx = -FLT_MAX;
-                    if (ch < nch) {
+                mbar_wait(&s_mbar, phase);
+                phase ^= 1u;
+                fence_after_thread_sync();
+                if (tid == 0 && streamed && NT > 1) {
+                    // the ring is free again: fetch the next 128-channel tile (wrapping to tile 0 for the next row tile)
+                    const bool more = (nt + 1 < NT) || (tile + gridDim.x < ntiles);
+                    if (more) {
+                        ring_tile = (nt + 1) % NT;
+                        mbar_expect_tx(&s_wbar, ring_bytes);
+                        for (uint32_t o = 0; o < ring_bytes; o += 32768u)
+                            bulk_g2s(base + L.w[l] + o, a.image[l] + (size_t)ring_tile * ring_bytes + o, min(32768u, ring_bytes - o), &s_wbar);
+                        ring_pending = true;
+                    }
+                }
+                if (l != last) {
+                    for (int ch = cs; ch < Nt / 32; ch += kTcChunkWarps) {
                         uint32_t d[32];
                         tmem_ld32(row_taddr + D_COL + ch * 32, d);
                         tmem_ld_wait();
-                        float v[32];
+                        float h[32];
+                        const float4* s4 = reinterpret_cast<const float4*>(sl[l] + ch * 32);
+                        const float4* t4 = reinterpret_cast<const float4*>(tl[l] + ch * 32);
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            float x = fmaf(__uint_as_float(d[q]), sl[l][ch * 32 + q], tl[l][ch * 32 + q]);
-                            if (a.relu[l]) x = fmaxf(x, 0.f);
-                            v[q] = valid ? x : -FLT_MAX;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 sc = s4[q], sh = t4[q];
+                            float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
+                            float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
+                            if (a.relu[l]) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                            h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
+                            h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
                         }
-                        mx = warp_colmax_32x32(v, lane);
+                        store_a_chunk(row_taddr, ch, h);
                     }
-                    if (quarters_per_group > 1) {
-                        s_red[warp][lane] = mx;
-                        __syncthreads();
-                        if ((quarter % quarters_per_group) == 0)
-                            for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
-                        __syncthreads();
+                    tmem_st_wait();
+                    fence_before_thread_sync();
+                    __syncthreads();
+                } else {
+                    // rows of one neighbourhood span K/32 lane-quarters; warps sharing a chunk slot combine through s_red
+                    const int quarters_per_group = a.K / 32;        // 1, 2 or 4
+                    const long long wg = g0 + (quarter * 32) / a.K; // this warp's neighbourhood
+                    const int nch = Nt / 32;
+                    for (int ch0 = 0; ch0 < nch; ch0 += kTcChunkWarps) {      // uniform trip count: barriers inside
+                        const int ch = ch0 + cs;
+                        float mx = -FLT_MAX;
+                        if (ch < nch) {
+                            uint32_t d[32];
+                            tmem_ld32(row_taddr + D_COL + ch * 32, d);
+                            tmem_ld_wait();
+                            float v[32];
+                            const float4* s4 = reinterpret_cast<const float4*>(sl[l] + nt * Nt + ch * 32);
+                            const float4* t4 = reinterpret_cast<const float4*>(tl[l] + nt * Nt + ch * 32);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 sc = s4[q], sh = t4[q];
+                                float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
+                                float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
+                                if (a.relu[l]) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                                v[4 * q + 0] = valid ? v0 : -FLT_MAX; v[4 * q + 1] = valid ? v1 : -FLT_MAX;
+                                v[4 * q + 2] = valid ? v2 : -FLT_MAX; v[4 * q + 3] = valid ? v3 : -FLT_MAX;
+                            }
+                            mx = warp_colmax_32x32(v, lane);
+                        }
+                        if (quarters_per_group > 1) {
+                            s_red[warp][lane] = mx;
+                            __syncthreads();
+                            if ((quarter % quarters_per_group) == 0)
+                                for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
+                            __syncthreads();
+                        }
+                        if (ch < nch && (quarter % quarters_per_group) == 0 && wg < a.groups)
+                            a.out[(size_t)wg * a.Ntot[l] + nt * Nt + ch * 32 + lane] = mx;
                     }
-                    if (ch < nch && (quarter % quarters_per_group) == 0 && wg < a.groups)
-                        a.out[(size_t)wg * a.Ntot[l] + split * Nlast + ch * 32 + lane] = mx;
+                    // D fully read by every warp before thread 0 may issue the next MMAs into it
+                    fence_before_thread_sync();
+                    __syncthreads();
                 }
-                fence_before_thread_sync();   // D fully read before the next tile's MMAs may overwrite it
             }
         }
     }
+    if (tid == 0 && ring_pending) mbar_wait(&s_wbar, wphase);     // never leave a bulk copy in flight
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- self-test of one tensor layer: D[128 x N] = A[128 x K] . W[K x N] through exactly the device code above ----
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D) {
+tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __restrict__ image, float* __restrict__ D) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_wbar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quarter = warp & 3, cs = warp >> 2;
     const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* whi = base;
-    uint8_t* wlo = base + (size_t)N * Kd * 4;
     if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { mbar_init(&s_mbar, 1); fence_mbar_init(); }
-    stage_weights(whi, wlo, W, Kd, N, 0, N, tid, kTcThreads);
-    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)tc_image_bytes(Kd, N);
+        mbar_expect_tx(&s_wbar, bytes);
+        for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(base + o, image + o, min(32768u, bytes - o), &s_wbar);
+        mbar_wait(&s_wbar, 0);
+    }
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
@@ -335,7 +405,7 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const float* __re
     __syncthreads();
     if (tid == 0) {
         fence_after_thread_sync();
-        issue_layer(tmem_base, smem_u32(whi), smem_u32(wlo), Kd, N);
+        issue_tile(tmem_base, smem_u32(base), Kd / 64, tc_nt(N));
         mma_commit(&s_mbar);
     }
     mbar_wait(&s_mbar, 0);
@@ -352,6 +422,176 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const float* __re
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dense layer on the tensor cores: out = relu?((x . W) * scale + shift), optional max over runs of pool_k rows.
+// CTA = 128 rows x Nt output channels.  K is walked in segments of 128: per segment the row warps quantise their x
+// chunk into the TMEM A operand, one thread issues the three-term MMAs against the segment's weight blocks (bulk-copied
+// into a two-slot shared-memory ring one segment ahead), and the segment's D is added to fp32 register accumulators --
+// so the truncating TMEM accumulation never runs over more than 128 K, however long the dot product is.
+// ------------------------------------------------------------------------------------------------------------------
+struct TcDenseArgs {
+    long long rows;
+    int K, Kp, N;          // Kp = K rounded up to 64
+    int pool_k;            // 1, 32, 64 or 128
+    int relu;
+    const float* x;        // (rows, K)
+    const uint8_t* image;  // weight image for (Kp, N)
+    const float* scale;    // (N) or null
+    const float* shift;    // (N) or null
+    float* out;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_wbar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[kTcThreads / 32][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quarter = warp & 3, cs = warp >> 2;
+    const int row = quarter * 32 + lane;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int Nt = tc_nt(a.N), KCtot = a.Kp / 64;
+    const uint32_t bb = tc_block_bytes(a.N);
+    const uint32_t slot_bytes = 2u * bb;
+    const int nt = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * 128;
+    const long long grow = row0 + row;
+    const bool valid = grow < a.rows;
+    const int nseg = (KCtot + 1) / 2;
+    const uint8_t* img = a.image + (size_t)nt * KCtot * bb;
+
+    if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar[0], 1); mbar_init(&s_wbar[1], 1); fence_mbar_init(); }
+    __syncthreads();
+    auto load_seg = [&](int sg) {       // thread 0 only
+        const int kcs = min(2, KCtot - 2 * sg);
+        const uint32_t bytes = (uint32_t)kcs * bb;
+        uint64_t* bar = &s_wbar[sg & 1];
+        mbar_expect_tx(bar, bytes);
+        for (uint32_t o = 0; o < bytes; o += 32768u)
+            bulk_g2s(base + (sg & 1) * slot_bytes + o, img + (size_t)sg * slot_bytes + o, min(32768u, bytes - o), bar);
+    };
+    if (tid == 0) load_seg(0);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = s_tmem;
+    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t phase = 0;
+    const bool vec_ok = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+    float acc[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+    const bool has_out_chunk = cs < Nt / 32;
+
+    for (int sg = 0; sg < nseg; ++sg) {
+        const int kcs = min(2, KCtot - 2 * sg);
+        // ---- this warp's 32-wide chunk of the segment's x columns -> A operand ----
+        if (cs < kcs * 2) {
+            const int k0 = sg * 128 + cs * 32;
+            float h[32];
+            const float* xr = a.x + (size_t)(valid ? grow : 0) * a.K + k0;
+            if (valid && vec_ok && k0 + 32 <= a.K) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(xr) + q);
+                    h[4 * q] = u.x; h[4 * q + 1] = u.y; h[4 * q + 2] = u.z; h[4 * q + 3] = u.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) h[q] = (valid && k0 + q < a.K) ? __ldg(xr + q) : 0.f;
+            }
+            store_a_chunk(row_taddr, cs, h);
+        }
+        tmem_st_wait();
+        fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&s_wbar[sg & 1], (uint32_t)((sg >> 1) & 1));
+            fence_after_thread_sync();
+            issue_tile(tmem_base, smem_u32(base + (sg & 1) * slot_bytes), kcs, Nt);
+            mma_commit(&s_mbar);
+            if (sg + 1 < nseg) load_seg(sg + 1);    // the other slot's MMAs (segment sg-1) completed before this segment began
+        }
+        mbar_wait(&s_mbar, phase);
+        phase ^= 1u;
+        fence_after_thread_sync();
+        if (has_out_chunk) {
+            uint32_t d[32];
+            tmem_ld32(row_taddr + D_COL + cs * 32, d);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(d[q]);
+        }
+        fence_before_thread_sync();       // D read / A free before the next segment overwrites them (barrier at loop top)
+    }
+    // ---- epilogue ----
+    const int col0 = nt * Nt + cs * 32;
+    float v[32];
+    if (has_out_chunk) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const float sc = a.scale ? __ldg(a.scale + col0 + q) : 1.f;
+            const float sh = a.shift ? __ldg(a.shift + col0 + q) : 0.f;
+            float x = fmaf(acc[q], sc, sh);
+            if (a.relu) x = fmaxf(x, 0.f);
+            v[q] = x;
+        }
+    }
+    if (a.pool_k == 1) {
+        if (has_out_chunk && valid) {
+            float4* o = reinterpret_cast<float4*>(a.out + (size_t)grow * a.N + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    } else {
+        const int quarters_per_group = a.pool_k / 32;
+        const long long wg = (row0 + quarter * 32) / a.pool_k;
+        float mx = -FLT_MAX;
+        if (has_out_chunk) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = valid ? v[q] : -FLT_MAX;
+            mx = warp_colmax_32x32(v, lane);
+        }
+        if (quarters_per_group > 1) {
+            s_red[warp][lane] = mx;
+            __syncthreads();
+            if ((quarter % quarters_per_group) == 0)
+                for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
+        }
+        if (has_out_chunk && (quarter % quarters_per_group) == 0 && row0 + quarter * 32 < a.rows)
+            a.out[(size_t)wg * a.N + col0 + lane] = mx;
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
+    if (rows < 128 || K < 32 || N < 64 || (N % 64) != 0) return false;
+    if (N > 64 && (N % 128) != 0) return false;
+    if (!(pool_k == 1 || pool_k == 32 || pool_k == 64 || pool_k == 128)) return false;
+    if (pool_k > 1 && rows % pool_k != 0) return false;
+    return true;
+}
+size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
+
+int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
+                    const float* shift, float* out, uint8_t* image, cudaStream_t st) {
+    const int Kp = (K + 63) & ~63;
+    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, W, image);
+    TcDenseArgs a;
+    a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
+    a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out;
+    const size_t smem = 4 * (size_t)tc_block_bytes(N) + 1024;      // two slots of two blocks
+    PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem < 120 * 1024 ? 120 * 1024 : smem)));
+    dim3 grid((unsigned)((rows + 127) / 128), N / tc_nt(N));
+    tc_dense_kernel<<<grid, kTcThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
+    return check_launch("tc_dense_kernel");
+}
+
 // Can this MLP / geometry run on the tensor-core kernel?  (otherwise the fp32-FMA fused kernel in mlp.cu is used)
 bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
     if (mlp->n_layers < 2 || mlp->n_layers > 1 + kMaxTcLayers) return false;
@@ -362,19 +602,32 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
     TcArgs a{};
     a.C1 = C1;
     a.nl = mlp->n_layers - 1;
+    size_t all = 0;
     for (int l = 0; l < a.nl; ++l) {
         a.Kd[l] = mlp->channels[1 + l];
         a.Ntot[l] = mlp->channels[2 + l];
         if (!(a.Kd[l] == 64 || a.Kd[l] == 128)) return false;
         const bool is_last = (l == a.nl - 1);
-        if (!is_last && !(a.Ntot[l] == 64 || a.Ntot[l] == 128)) return false;
+        if (!is_last && !(a.Ntot[l] == 64 || a.Ntot[l] == 128)) return false;       // D and the next A operand are one tile wide
         if (is_last && !(a.Ntot[l] == 64 || a.Ntot[l] % 128 == 0)) return false;
+        all += tc_image_bytes(a.Kd[l], a.Ntot[l]);
     }
-    a.nsplit = a.Ntot[a.nl - 1] <= 128 ? 1 : a.Ntot[a.nl - 1] / 128;
-    if (a.nsplit > 4) return false;
-    if (tc_layout(a).total + 1024 > 220 * 1024) return false;
+    const uint32_t budget = 200 * 1024;
+    a.stream_last = 0;
+    if (tc_layout(a).total + 1024 > budget) {
+        a.stream_last = 1;
+        if (tc_layout(a).total + 1024 > budget) return false;
+    }
+    (void)all;
     *out = a;
     return true;
+}
+
+size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
+    size_t bytes = 0;
+    for (int l = 0; l < a.nl; ++l) bytes += (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255;
+    if (c > 0) bytes += (size_t)b * n * a.C1 * sizeof(float);
+    return bytes;
 }
 
 int launch_tc_sa(TcArgs& a, cudaStream_t st) {
@@ -384,10 +637,10 @@ int launch_tc_sa(TcArgs& a, cudaStream_t st) {
     PSA_CUDA(cudaFuncSetAttribute(tc_sa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
-    long long workers = kNumSMs / a.nsplit;
-    if (workers > ntiles) workers = ntiles;
-    if (workers < 1) workers = 1;
-    tc_sa_kernel<<<(int)(workers * a.nsplit), kTcThreads, smem, st>>>(a);
+    long long ctas = kNumSMs;
+    if (ctas > ntiles) ctas = ntiles;
+    if (ctas < 1) ctas = 1;
+    tc_sa_kernel<<<(int)ctas, kTcThreads, smem, st>>>(a);
     return check_launch("tc_sa_kernel");
 }
 
@@ -396,12 +649,16 @@ int launch_tc_sa(TcArgs& a, cudaStream_t st) {
 using namespace psa;
 
 // Diagnostic entry point (not part of the reference's op surface): one 128-row tile through one tensor-core layer.
-extern "C" PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, psa_stream_t stream) {
+// `scratch` must hold 6*Kd*N bytes (the weight image).
+extern "C" PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, void* scratch, psa_stream_t stream) {
     PSA_REQUIRE((Kd == 64 || Kd == 128) && (N == 64 || N == 128), "tc_selftest: Kd, N must be 64 or 128");
-    size_t smem = (size_t)N * Kd * 6 + 1024;
+    PSA_REQUIRE(A && W && D && scratch, "tc_selftest: null buffer");
+    cudaStream_t st = as_stream(stream);
+    tc_prep_weights_kernel<<<(Kd * N + 255) / 256, 256, 0, st>>>(Kd, Kd, N, W, reinterpret_cast<uint8_t*>(scratch));
+    size_t smem = tc_image_bytes(Kd, N) + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;
     PSA_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, kTcThreads, smem, as_stream(stream)>>>(Kd, N, A, W, D);
+    tc_selftest_kernel<<<1, kTcThreads, smem, st>>>(Kd, N, A, reinterpret_cast<const uint8_t*>(scratch), D);
     return check_launch("tc_selftest_kernel");
 }
 
@@ -417,8 +674,7 @@ extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode; }
 extern "C" size_t psa_sa_module_workspace_bytes(int b, int n, int m, int c, int nsample, const psa_mlp* mlp) {
     (void)m;
     TcArgs a;
-    if (g_mlp_mode == 0 && mlp != nullptr && c > 0 && tc_sa_eligible(mlp, c, nsample, &a))
-        return (size_t)b * n * a.C1 * sizeof(float);
+    if (g_mlp_mode == 0 && mlp != nullptr && tc_sa_eligible(mlp, c, nsample, &a)) return tc_sa_workspace_bytes(a, b, n, c);
     return 0;
 }
 
@@ -442,21 +698,29 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
     cudaStream_t st = as_stream(stream);
     TcArgs a;
     if (g_mlp_mode == 0 && tc_sa_eligible(mlp, c, nsample, &a)) {
+        const size_t need = tc_sa_workspace_bytes(a, b, n, c);
+        PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+                    "sa_module: workspace of %zu bytes required (psa_sa_module_workspace_bytes), got %zu", need, workspace_bytes);
+        PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sa_module: workspace must be 256-byte aligned");
         a.groups = (long long)b * m; a.K = nsample; a.n = n; a.m = m;
         a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.out = out; a.uf = nullptr;
         a.w1x = mlp->weight[0]; a.s1 = mlp->scale[0]; a.t1 = mlp->shift[0]; a.relu1 = mlp->relu[0];
+        uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
         for (int l = 0; l < a.nl; ++l) {
-            a.W[l] = mlp->weight[1 + l]; a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
+            a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
+            const int K = a.Kd[l], N = a.Ntot[l];
+            tc_prep_weights_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(K, K, N, mlp->weight[1 + l], ws);
+            a.image[l] = ws;
+            ws += (tc_image_bytes(K, N) + 255) & ~(size_t)255;
         }
+        rc = check_launch("tc_prep_weights_kernel");
+        if (rc != PSA_OK) return rc;
         if (c > 0) {
-            const size_t need = (size_t)b * n * a.C1 * sizeof(float);
-            PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need,
-                        "sa_module: workspace of %zu bytes required (psa_sa_module_workspace_bytes), got %zu", need, workspace_bytes);
             // U = points . W1[3:,:]  once per source point (rows b*n), raw (affine + ReLU are applied after the xyz part)
             DenseArgs d;
             d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
             d.x = points; d.W = mlp->weight[0] + (size_t)3 * a.C1; d.scale = nullptr; d.shift = nullptr;
-            d.out = reinterpret_cast<float*>(workspace);
+            d.out = reinterpret_cast<float*>(ws);
             rc = launch_dense(d, st);
             if (rc != PSA_OK) return rc;
             a.uf = d.out;
@@ -464,4 +728,65 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         return launch_tc_sa(a, st);
     }
     return sa_module_simt(b, n, m, c, nsample, xyz, new_xyz, points, idx, mlp, out, st);
+}
+
+extern "C" size_t psa_shared_mlp_workspace_bytes(long long rows, const psa_mlp* mlp) {
+    if (mlp == nullptr || mlp->n_layers < 1) return 0;
+    size_t bytes = 0;
+    int cmax = 0;
+    for (int l = 1; l < mlp->n_layers; ++l) cmax = cmax > mlp->channels[l] ? cmax : mlp->channels[l];
+    if (mlp->n_layers > 1) bytes += 2 * (((size_t)rows * cmax * sizeof(float) + 255) & ~(size_t)255);
+    for (int l = 0; l < mlp->n_layers; ++l) bytes += tc_dense_image_bytes(mlp->channels[l], mlp->channels[l + 1] < 64 ? 64 : mlp->channels[l + 1]);
+    if (rows <= 32) {
+        size_t fc = 0;
+        for (int l = 0; l < mlp->n_layers; ++l) { size_t f = fc_small_workspace_bytes(mlp->channels[l], mlp->channels[l + 1]); fc = f > fc ? f : fc; }
+        bytes += (fc + 255) & ~(size_t)255;
+    }
+    return bytes;
+}
+
+extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const psa_mlp* mlp, float* out,
+                              void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    int rc = validate_mlp_public(mlp, "shared_mlp");
+    if (rc != PSA_OK) return rc;
+    PSA_REQUIRE(rows >= 0 && pool_k >= 1, "shared_mlp: rows=%lld pool_k=%d", rows, pool_k);
+    if (rows == 0) return PSA_OK;
+    PSA_REQUIRE(rows % pool_k == 0, "shared_mlp: rows=%lld is not a multiple of pool_k=%d", rows, pool_k);
+    PSA_REQUIRE(x && out, "shared_mlp: null buffer");
+    const int L = mlp->n_layers;
+    const size_t need = psa_shared_mlp_workspace_bytes(rows, mlp);
+    PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, "shared_mlp: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+    PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "shared_mlp: workspace must be 256-byte aligned");
+    int cmax = 0;
+    for (int l = 1; l < L; ++l) cmax = cmax > mlp->channels[l] ? cmax : mlp->channels[l];
+    const size_t half = L > 1 ? (((size_t)rows * cmax * sizeof(float) + 255) & ~(size_t)255) : 0;
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+    float* ws0 = reinterpret_cast<float*>(wsb);
+    float* ws1 = reinterpret_cast<float*>(wsb + half);
+    uint8_t* img = wsb + 2 * half;
+    float* fc_partial = nullptr;
+    if (rows <= 32) {   // the K-split partial sums of the small-M kernel sit at the end of the workspace
+        size_t imgs = 0;
+        for (int l = 0; l < L; ++l) imgs += tc_dense_image_bytes(mlp->channels[l], mlp->channels[l + 1] < 64 ? 64 : mlp->channels[l + 1]);
+        fc_partial = reinterpret_cast<float*>(img + imgs);
+    }
+    const float* cur = x;
+    cudaStream_t st = as_stream(stream);
+    for (int l = 0; l < L; ++l) {
+        const int K = mlp->channels[l], N = mlp->channels[l + 1];
+        const int pk = (l == L - 1) ? pool_k : 1;
+        float* dst = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
+        if (g_mlp_mode == 0 && tc_dense_eligible(rows, K, N, pk)) {
+            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, mlp->weight[l], mlp->scale[l], mlp->shift[l], dst, img, st);
+        } else {
+            DenseArgs d;
+            d.rows = rows; d.K = K; d.N = N; d.pool_k = pk; d.relu = mlp->relu[l];
+            d.x = cur; d.W = mlp->weight[l]; d.scale = mlp->scale[l]; d.shift = mlp->shift[l]; d.out = dst;
+            rc = (rows <= 32 && pk == 1) ? launch_fc_small(d, fc_partial, st) : launch_dense(d, st);
+        }
+        if (rc != PSA_OK) return rc;
+        img += tc_dense_image_bytes(K, N < 64 ? 64 : N);
+        cur = dst;
+    }
+    return PSA_OK;
 }

@@ -1,0 +1,102 @@
+"""dgcnn/models/dgcnn.py and dgcnn_bga.py on the B200 kernels (inference mode).
+
+Every `pairwise_distance -> knn -> get_edge_feature -> conv2d -> reduce_max` group of the reference
+(dgcnn.py:31-80) is two launches here: the fused kNN graph (no (B,N,N) matrix) and the fused EdgeConv
+(gather [x_i, x_j - x_i] + MLP + max over k, no (B,N,k,2C) tensor)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .tf_util import VariableStore, _require_inference
+
+NUM_CLASSES = 15
+K_NEIGHBORS = 20
+
+
+def init_params(num_class=NUM_CLASSES, seed=0, device="cuda", randomize_bn=False, bga=False) -> VariableStore:
+    p = VariableStore(device=device, seed=seed)
+    rb = randomize_bn
+    # transform_net1 (dgcnn/models/transform_nets.py:10-55)
+    p.add_conv2d("transform_net1/tconv1", 6, 64, randomize_bn=rb)
+    p.add_conv2d("transform_net1/tconv2", 64, 128, randomize_bn=rb)
+    p.add_conv2d("transform_net1/tconv3", 128, 1024, randomize_bn=rb)
+    p.add_fc("transform_net1/tfc1", 1024, 512, randomize_bn=rb)
+    p.add_fc("transform_net1/tfc2", 512, 256, randomize_bn=rb)
+    # transform_XYZ: weights 0, biases 0 (+ identity added at run time), transform_nets.py:38-50
+    p["transform_net1/transform_XYZ/weights"] = torch.zeros((256, 9), device=p.device)
+    p["transform_net1/transform_XYZ/biases"] = torch.zeros(9, device=p.device)
+    p.add_conv2d("dgcnn1", 6, 64, randomize_bn=rb)
+    p.add_conv2d("dgcnn2", 128, 64, randomize_bn=rb)
+    p.add_conv2d("dgcnn3", 128, 64, randomize_bn=rb)
+    p.add_conv2d("dgcnn4", 128, 128, randomize_bn=rb)
+    p.add_conv2d("agg", 320, 1024, randomize_bn=rb)
+    p.add_fc("fc1", 1024, 512, randomize_bn=rb)
+    p.add_fc("fc2", 512, 256, randomize_bn=rb)
+    p.add_fc("fc3", 256, num_class, bn=False)
+    if bga:
+        p.add_conv2d("seg/conv1", 256 + 1024 + 320, 512, randomize_bn=rb)
+        p.add_conv2d("seg/conv2", 512, 256, randomize_bn=rb)
+        p.add_conv2d("seg/conv3", 256, 2, bn=False)
+    return p
+
+
+def input_transform_net(point_cloud, nn_idx, params: VariableStore, scope="transform_net1", K=3):
+    """transform_nets.input_transform_net on the fused EdgeConv: -> (B,K,K)."""
+    b, n, _ = point_cloud.shape
+    net = ops.edgeconv_infer(point_cloud, nn_idx, params.mlp([f"{scope}/tconv1", f"{scope}/tconv2"]))   # max over k
+    net = ops.shared_mlp(net.reshape(b * n, -1), params.mlp([f"{scope}/tconv3"]), pool_k=n)               # max over N
+    net = ops.shared_mlp(net, params.mlp([f"{scope}/tfc1", f"{scope}/tfc2"]))
+    w = params[f"{scope}/transform_XYZ/weights"]
+    bias = params[f"{scope}/transform_XYZ/biases"] + torch.eye(K, device=w.device).flatten()
+    return (net @ w + bias).reshape(b, K, K)
+
+
+def _backbone(point_cloud, params, end_points, k=K_NEIGHBORS):
+    b, n, _ = point_cloud.shape
+    nn_idx = ops.knn_graph(point_cloud, k)
+    transform = input_transform_net(point_cloud, nn_idx, params)
+    pct = torch.bmm(point_cloud, transform).contiguous()                      # tf.matmul(point_cloud, transform), dgcnn.py:38
+    end_points.update(nn_idx0=nn_idx, transform=transform, point_cloud_transformed=pct)
+    nets = []
+    x = pct
+    for i, scope in enumerate(["dgcnn1", "dgcnn2", "dgcnn3", "dgcnn4"]):
+        idx = ops.knn_graph(x, k)
+        y = ops.edgeconv_infer(x, idx, params.mlp([scope]))
+        end_points[f"nn_idx{i + 1}"] = idx
+        end_points[f"net{i + 1}"] = y
+        nets.append(y)
+        x = y
+    cat = torch.cat(nets, dim=-1)                                             # (B,N,320)
+    agg = ops.shared_mlp(cat.reshape(b * n, 320), params.mlp(["agg"]))        # (B*N,1024)
+    return nets, agg.reshape(b, n, 1024)
+
+
+def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
+    """dgcnn.get_model (dgcnn.py:24-102): (B,N,3) -> (logits (B,num_class), end_points)."""
+    _require_inference(is_training)
+    end_points = {}
+    _, agg = _backbone(point_cloud, params, end_points)
+    net = agg.max(dim=1).values                                               # tf.reduce_max over N
+    end_points["global"] = net
+    net = ops.shared_mlp(net, params.mlp(["fc1", "fc2", "fc3"], [True, True, False]))
+    return net, end_points
+
+
+def get_model_bga(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
+    """dgcnn_bga.get_model (dgcnn_bga.py:27-134): -> (class_pred (B,num_class), seg_pred (B,N,2), end_points)."""
+    _require_inference(is_training)
+    end_points = {}
+    b, n, _ = point_cloud.shape
+    nets, agg = _backbone(point_cloud, params, end_points)
+    out_max = agg.max(dim=1).values                                           # (B,1024)
+    net = ops.shared_mlp(out_max, params.mlp(["fc1", "fc2"], [True, True]))   # class vector (B,256)
+    class_pred = ops.shared_mlp(net, params.mlp(["fc3"], [False]))
+    concat = torch.cat([net.unsqueeze(1).expand(b, n, 256), out_max.unsqueeze(1).expand(b, n, 1024), *nets], dim=-1)
+    seg = ops.shared_mlp(concat.reshape(b * n, -1).contiguous(), params.mlp(["seg/conv1", "seg/conv2", "seg/conv3"], [True, True, False]))
+    return class_pred, seg.reshape(b, n, 2), end_points
+
+
+def get_loss(pred, label, end_points=None, num_class=NUM_CLASSES):
+    """softmax cross-entropy with label smoothing 0.2 (dgcnn.py:105-111)."""
+    return torch.nn.functional.cross_entropy(pred, label.long(), label_smoothing=0.2)

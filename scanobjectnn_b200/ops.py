@@ -405,7 +405,7 @@ def sa_module_infer(xyz, new_xyz, points, radius: float, nsample: int, mlp: MlpP
         idx = _dev(idx, torch.int32, "idx", 3)
     lib = _lib.load()
     need = lib.psa_sa_module_workspace_bytes(b, n, m, c, nsample, mlp.ref)
-    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=xyz.device) if need else None
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=xyz.device) if need else None   # torch allocations are 512-B aligned
     check(lib.psa_sa_module_infer(b, n, m, c, C.c_float(radius), nsample, _ptr(xyz), _ptr(new_xyz), _ptr(points),
                                   _ptr(idx), mlp.ref, _ptr(out), _ptr(idx_out), _ptr(cnt), _ptr(ws), C.c_size_t(need),
                                   _stream()), "sa_module_infer")
@@ -441,5 +441,6 @@ def tc_selftest(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     if a.shape[0] != 128 or a.shape[1] != w.shape[0]:
         raise ValueError("tc_selftest expects a (128,Kd) and w (Kd,N)")
     d = torch.empty((128, w.shape[1]), dtype=torch.float32, device=a.device)
-    check(_lib.load().psa_tc_selftest(a.shape[1], w.shape[1], _ptr(a), _ptr(w), _ptr(d), _stream()), "tc_selftest")
+    scratch = torch.empty(6 * w.numel(), dtype=torch.uint8, device=a.device)
+    check(_lib.load().psa_tc_selftest(a.shape[1], w.shape[1], _ptr(a), _ptr(w), _ptr(d), _ptr(scratch), _stream()), "tc_selftest")
     return d
