@@ -31,10 +31,20 @@ namespace psa {
 
 using namespace tc;
 
-constexpr int kTcThreads = 512;   // 16 warps: warp w works on TMEM lanes 32*(w%4).. (hardware rule) and column chunks w/4, w/4+4, ..
-constexpr int kTcChunkWarps = kTcThreads / 128;
-constexpr int kTmemCols = 512;
-constexpr uint32_t D_COL = 0, AHI_COL = 128, ALO_COL = 256, ABF_COL = 384;
+// Two configurations of every tensor-core kernel:
+//   wide   512 threads (16 warps), all 512 TMEM columns, 128-wide output tiles, A operand up to K = 128: one CTA per SM;
+//   narrow 256 threads ( 8 warps), 256 TMEM columns,      64-wide output tiles, A operand up to K = 64: TWO CTAs per SM,
+//          which hide each other's gather / TMEM / barrier latencies (the kernels are latency- not tensor-bound).
+// Warp w works on TMEM lanes 32*(w%4).. (hardware rule) and on column chunks w/4, w/4 + kChunkWarps, ...
+template <bool NARROW>
+struct TcCfg {
+    static constexpr int kThreads = NARROW ? 256 : 512;
+    static constexpr int kChunkWarps = kThreads / 128;
+    static constexpr int kTmemCols = NARROW ? 256 : 512;
+    static constexpr uint32_t D = 0, AHI = NARROW ? 64 : 128, ALO = NARROW ? 128 : 256, ABF = NARROW ? 192 : 384;
+    static constexpr int kNtCap = NARROW ? 64 : 128;
+    static constexpr int kMinBlocks = NARROW ? 2 : 1;
+};
 constexpr int kMaxTcLayers = 2;
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -45,14 +55,14 @@ constexpr int kMaxTcLayers = 2;
 //     lo : bf16(w - trunc_tf32(w))    [Nt][64] bf16, K-major SWIZZLE_128B (one 64-wide K block)    Nt*128 B
 //   blocks stored in (nt major, kc minor) order.  6 bytes per weight.
 // ------------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline int tc_nt(int N) { return N >= 128 ? 128 : 64; }
-__host__ __device__ inline uint32_t tc_block_bytes(int N) { return (uint32_t)tc_nt(N) * 64u * 6u; }
-__host__ __device__ inline size_t tc_image_bytes(int K, int N) { return (size_t)(N / tc_nt(N)) * (K / 64) * tc_block_bytes(N); }
+__host__ __device__ inline int tc_nt(int N, int cap) { return N >= cap ? cap : 64; }
+__host__ __device__ inline uint32_t tc_block_bytes(int Nt) { return (uint32_t)Nt * 64u * 6u; }
+__host__ __device__ inline size_t tc_image_bytes(int K, int N) { return (size_t)K * N * 6u; }     // independent of the tile width
 
 // K rows of W are zero-padded to Kp (multiple of 64)
-__global__ void tc_prep_weights_kernel(int K, int Kp, int N, const float* __restrict__ W, uint8_t* __restrict__ image) {
-    const int Nt = tc_nt(N), KC = Kp / 64;
-    const uint32_t bb = tc_block_bytes(N);
+__global__ void tc_prep_weights_kernel(int K, int Kp, int N, int Nt, const float* __restrict__ W, uint8_t* __restrict__ image) {
+    const int KC = Kp / 64;
+    const uint32_t bb = tc_block_bytes(Nt);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Kp * N; e += gridDim.x * blockDim.x) {
         const int n = e % N, k = e / N;                       // coalesced read of W rows
         const float w = k < K ? __ldg(W + e) : 0.f;
@@ -86,10 +96,13 @@ struct TcArgs {
     int relu[kMaxTcLayers];
     int Kd[kMaxTcLayers], Ntot[kMaxTcLayers];
     int stream_last;       // 1: the last layer's weights do not fit next to the others -> one 128-channel tile at a time
+    int ntcap;             // 64 (narrow configuration) or 128 (wide)
 };
 
 // quantise one row-chunk of 32 activations into the three A operands and store them into TMEM
+template <class CFG>
 __device__ __forceinline__ void store_a_chunk(uint32_t row_taddr, int ch, const float (&h)[32]) {
+    constexpr uint32_t AHI_COL = CFG::AHI, ALO_COL = CFG::ALO, ABF_COL = CFG::ABF;
     uint32_t v[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(tf32_trunc(h[q]));
@@ -106,7 +119,9 @@ __device__ __forceinline__ void store_a_chunk(uint32_t row_taddr, int ch, const 
 // one elected thread: D[128 x Nt] = A[128 x 64*KC] . W_tile^T as the three-term split over KC resident blocks.
 // The tensor core truncates (rounds toward zero) every time it adds into D, so the error grows with the number of
 // accumulation steps taken while D is large: the two small correction terms go first, the main term last.
+template <class CFG>
 __device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t blocks_addr, int KC, int Nt) {
+    constexpr uint32_t D_COL = CFG::D, AHI_COL = CFG::AHI, ALO_COL = CFG::ALO, ABF_COL = CFG::ABF;
     const uint32_t d = tmem_base + D_COL;
     const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, Nt);
     const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, Nt);
@@ -153,7 +168,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(const TcArgs& a) {
     for (int l = 0; l < a.nl; ++l) {
         L.w[l] = off;
         const bool streamed = a.stream_last && l == a.nl - 1;
-        off += streamed ? (uint32_t)(a.Kd[l] / 64) * tc_block_bytes(a.Ntot[l]) : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+        off += streamed ? (uint32_t)(a.Kd[l] / 64) * tc_block_bytes(tc_nt(a.Ntot[l], a.ntcap)) : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
     }
     L.vec = off;
     off += 5u * a.C1 * 4u;
@@ -162,8 +177,12 @@ __host__ __device__ inline TcSmemLayout tc_layout(const TcArgs& a) {
     return L;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <bool NARROW>
+__global__ void __launch_bounds__(TcCfg<NARROW>::kThreads, TcCfg<NARROW>::kMinBlocks)
 tc_sa_kernel(const __grid_constant__ TcArgs a) {
+    using CFG = TcCfg<NARROW>;
+    constexpr int kTcThreads = CFG::kThreads, kTcChunkWarps = CFG::kChunkWarps, kTmemCols = CFG::kTmemCols;
+    constexpr uint32_t D_COL = CFG::D;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;     // MMA completion
     __shared__ __align__(8) uint64_t s_wbar;     // weight bulk copies landed
@@ -199,7 +218,7 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
         }
     __syncthreads();                          // barrier inits visible before anybody arms / waits
     uint32_t wphase = 0;
-    const uint32_t ring_bytes = (uint32_t)(a.Kd[last] / 64) * tc_block_bytes(a.Ntot[last]);   // one n-tile of the last layer
+    const uint32_t ring_bytes = (uint32_t)(a.Kd[last] / 64) * tc_block_bytes(tc_nt(a.Ntot[last], CFG::kNtCap));   // one n-tile of the last layer
     if (tid == 0) {
         uint32_t total = 0;
         for (int l = 0; l < a.nl; ++l) total += (a.stream_last && l == last) ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
@@ -267,22 +286,22 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
                     h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
                     h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
                 }
-                store_a_chunk(row_taddr, ch, h);
+                store_a_chunk<CFG>(row_taddr, ch, h);
             }
         }
         tmem_st_wait();
         fence_before_thread_sync();
         __syncthreads();
         for (int l = 0; l < a.nl; ++l) {
-            const int Nt = tc_nt(a.Ntot[l]);
+            const int Nt = tc_nt(a.Ntot[l], CFG::kNtCap);
             const int NT = a.Ntot[l] / Nt, KC = a.Kd[l] / 64;
             const bool streamed = a.stream_last && l == last;
             for (int nt = 0; nt < NT; ++nt) {
                 if (tid == 0) {
                     if (streamed && ring_pending) { mbar_wait(&s_wbar, wphase); wphase ^= 1u; ring_pending = false; }
                     fence_after_thread_sync();
-                    const uint32_t blocks = smem_u32(base + L.w[l]) + (streamed ? 0u : (uint32_t)nt * KC * tc_block_bytes(a.Ntot[l]));
-                    issue_tile(tmem_base, blocks, KC, Nt);
+                    const uint32_t blocks = smem_u32(base + L.w[l]) + (streamed ? 0u : (uint32_t)nt * KC * tc_block_bytes(Nt));
+                    issue_tile<CFG>(tmem_base, blocks, KC, Nt);
                     mma_commit(&s_mbar);
                 }
                 mbar_wait(&s_mbar, phase);
@@ -316,7 +335,7 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
                             h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
                             h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
                         }
-                        store_a_chunk(row_taddr, ch, h);
+                        store_a_chunk<CFG>(row_taddr, ch, h);
                     }
                     tmem_st_wait();
                     fence_before_thread_sync();
@@ -370,8 +389,11 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
 }
 
 // ---- self-test of one tensor layer: D[128 x N] = A[128 x K] . W[K x N] through exactly the device code above ----
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(TcCfg<false>::kThreads, 1)
 tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __restrict__ image, float* __restrict__ D) {
+    using CFG = TcCfg<false>;
+    constexpr int kTcChunkWarps = CFG::kChunkWarps, kTmemCols = CFG::kTmemCols;
+    constexpr uint32_t D_COL = CFG::D;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ __align__(8) uint64_t s_wbar;
@@ -398,14 +420,14 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __
         float h[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) h[q] = A[(size_t)row * Kd + ch * 32 + q];
-        store_a_chunk(row_taddr, ch, h);
+        store_a_chunk<CFG>(row_taddr, ch, h);
     }
     tmem_st_wait();
     fence_before_thread_sync();
     __syncthreads();
     if (tid == 0) {
         fence_after_thread_sync();
-        issue_tile(tmem_base, smem_u32(base), Kd / 64, tc_nt(N));
+        issue_tile<CFG>(tmem_base, smem_u32(base), Kd / 64, tc_nt(N, 128));
         mma_commit(&s_mbar);
     }
     mbar_wait(&s_mbar, 0);
@@ -442,8 +464,13 @@ struct TcDenseArgs {
     float* out;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <bool NARROW>
+__global__ void __launch_bounds__(TcCfg<NARROW>::kThreads, TcCfg<NARROW>::kMinBlocks)
 tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
+    using CFG = TcCfg<NARROW>;
+    constexpr int kTcThreads = CFG::kThreads, kTmemCols = CFG::kTmemCols;
+    constexpr uint32_t D_COL = CFG::D;
+    constexpr int SEGB = NARROW ? 1 : 2;              // 64-K weight blocks per segment (A operand capacity)
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ __align__(8) uint64_t s_wbar[2];
@@ -453,21 +480,21 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
     const int quarter = warp & 3, cs = warp >> 2;
     const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int Nt = tc_nt(a.N), KCtot = a.Kp / 64;
-    const uint32_t bb = tc_block_bytes(a.N);
-    const uint32_t slot_bytes = 2u * bb;
+    const int Nt = tc_nt(a.N, CFG::kNtCap), KCtot = a.Kp / 64;
+    const uint32_t bb = tc_block_bytes(Nt);
+    const uint32_t slot_bytes = (uint32_t)SEGB * bb;
     const int nt = blockIdx.y;
     const long long row0 = (long long)blockIdx.x * 128;
     const long long grow = row0 + row;
     const bool valid = grow < a.rows;
-    const int nseg = (KCtot + 1) / 2;
+    const int nseg = (KCtot + SEGB - 1) / SEGB;
     const uint8_t* img = a.image + (size_t)nt * KCtot * bb;
 
     if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
     if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar[0], 1); mbar_init(&s_wbar[1], 1); fence_mbar_init(); }
     __syncthreads();
     auto load_seg = [&](int sg) {       // thread 0 only
-        const int kcs = min(2, KCtot - 2 * sg);
+        const int kcs = min(SEGB, KCtot - SEGB * sg);
         const uint32_t bytes = (uint32_t)kcs * bb;
         uint64_t* bar = &s_wbar[sg & 1];
         mbar_expect_tx(bar, bytes);
@@ -488,10 +515,10 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
     const bool has_out_chunk = cs < Nt / 32;
 
     for (int sg = 0; sg < nseg; ++sg) {
-        const int kcs = min(2, KCtot - 2 * sg);
+        const int kcs = min(SEGB, KCtot - SEGB * sg);
         // ---- this warp's 32-wide chunk of the segment's x columns -> A operand ----
         if (cs < kcs * 2) {
-            const int k0 = sg * 128 + cs * 32;
+            const int k0 = sg * (SEGB * 64) + cs * 32;
             float h[32];
             const float* xr = a.x + (size_t)(valid ? grow : 0) * a.K + k0;
             if (valid && vec_ok && k0 + 32 <= a.K) {
@@ -504,7 +531,7 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
 #pragma unroll
                 for (int q = 0; q < 32; ++q) h[q] = (valid && k0 + q < a.K) ? __ldg(xr + q) : 0.f;
             }
-            store_a_chunk(row_taddr, cs, h);
+            store_a_chunk<CFG>(row_taddr, cs, h);
         }
         tmem_st_wait();
         fence_before_thread_sync();
@@ -512,7 +539,7 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
         if (tid == 0) {
             mbar_wait(&s_wbar[sg & 1], (uint32_t)((sg >> 1) & 1));
             fence_after_thread_sync();
-            issue_tile(tmem_base, smem_u32(base + (sg & 1) * slot_bytes), kcs, Nt);
+            issue_tile<CFG>(tmem_base, smem_u32(base + (sg & 1) * slot_bytes), kcs, Nt);
             mma_commit(&s_mbar);
             if (sg + 1 < nseg) load_seg(sg + 1);    // the other slot's MMAs (segment sg-1) completed before this segment began
         }
@@ -578,17 +605,30 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
 }
 size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
 
+static int g_tc_dense_narrow = 1;
+
 int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
                     const float* shift, float* out, uint8_t* image, cudaStream_t st) {
     const int Kp = (K + 63) & ~63;
-    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, W, image);
+    const bool narrow = g_tc_dense_narrow != 0;
+    const int Nt = tc_nt(N, narrow ? 64 : 128);
+    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, image);
     TcDenseArgs a;
     a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
     a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out;
-    const size_t smem = 4 * (size_t)tc_block_bytes(N) + 1024;      // two slots of two blocks
-    PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem < 120 * 1024 ? 120 * 1024 : smem)));
-    dim3 grid((unsigned)((rows + 127) / 128), N / tc_nt(N));
-    tc_dense_kernel<<<grid, kTcThreads, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
+    dim3 grid((unsigned)((rows + 127) / 128), N / Nt);
+    if (narrow) {
+        // two slots of one block; two CTAs (256 TMEM columns each) per SM
+        const size_t smem = 2 * (size_t)tc_block_bytes(Nt) + 1024;
+        PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_dense_kernel<true><<<grid, TcCfg<true>::kThreads, smem, st>>>(a);
+    } else {
+        // two slots of two blocks; >= 120 KB requested so that only one CTA (all 512 TMEM columns) lands on an SM
+        size_t smem = 4 * (size_t)tc_block_bytes(Nt) + 1024;
+        if (smem < 120 * 1024) smem = 120 * 1024;
+        PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_dense_kernel<false><<<grid, TcCfg<false>::kThreads, smem, st>>>(a);
+    }
     return check_launch("tc_dense_kernel");
 }
 
@@ -612,7 +652,10 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
         if (is_last && !(a.Ntot[l] == 64 || a.Ntot[l] % 128 == 0)) return false;
         all += tc_image_bytes(a.Kd[l], a.Ntot[l]);
     }
-    const uint32_t budget = 200 * 1024;
+    bool all64 = (C1 == 64);
+    for (int l = 0; l < a.nl; ++l) all64 = all64 && a.Kd[l] == 64;
+    a.ntcap = all64 ? 64 : 128;
+    const uint32_t budget = all64 ? 100 * 1024 : 200 * 1024;      // narrow: two CTAs share the SM
     a.stream_last = 0;
     if (tc_layout(a).total + 1024 > budget) {
         a.stream_last = 1;
@@ -633,14 +676,20 @@ size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
 int launch_tc_sa(TcArgs& a, cudaStream_t st) {
     const TcSmemLayout L = tc_layout(a);
     size_t smem = (size_t)L.total + 1024;
-    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
-    PSA_CUDA(cudaFuncSetAttribute(tc_sa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
-    long long ctas = kNumSMs;
+    const bool narrow = a.ntcap == 64;
+    long long ctas = narrow ? 2 * kNumSMs : kNumSMs;
     if (ctas > ntiles) ctas = ntiles;
     if (ctas < 1) ctas = 1;
-    tc_sa_kernel<<<(int)ctas, kTcThreads, smem, st>>>(a);
+    if (narrow) {
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_kernel<true><<<(int)ctas, TcCfg<true>::kThreads, smem, st>>>(a);
+    } else {
+        if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_kernel<false><<<(int)ctas, TcCfg<false>::kThreads, smem, st>>>(a);
+    }
     return check_launch("tc_sa_kernel");
 }
 
@@ -654,11 +703,11 @@ extern "C" PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const floa
     PSA_REQUIRE((Kd == 64 || Kd == 128) && (N == 64 || N == 128), "tc_selftest: Kd, N must be 64 or 128");
     PSA_REQUIRE(A && W && D && scratch, "tc_selftest: null buffer");
     cudaStream_t st = as_stream(stream);
-    tc_prep_weights_kernel<<<(Kd * N + 255) / 256, 256, 0, st>>>(Kd, Kd, N, W, reinterpret_cast<uint8_t*>(scratch));
+    tc_prep_weights_kernel<<<(Kd * N + 255) / 256, 256, 0, st>>>(Kd, Kd, N, tc_nt(N, 128), W, reinterpret_cast<uint8_t*>(scratch));
     size_t smem = tc_image_bytes(Kd, N) + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;
     PSA_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, kTcThreads, smem, st>>>(Kd, N, A, reinterpret_cast<const uint8_t*>(scratch), D);
+    tc_selftest_kernel<<<1, TcCfg<false>::kThreads, smem, st>>>(Kd, N, A, reinterpret_cast<const uint8_t*>(scratch), D);
     return check_launch("tc_selftest_kernel");
 }
 
@@ -709,7 +758,7 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         for (int l = 0; l < a.nl; ++l) {
             a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
             const int K = a.Kd[l], N = a.Ntot[l];
-            tc_prep_weights_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(K, K, N, mlp->weight[1 + l], ws);
+            tc_prep_weights_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(K, K, N, tc_nt(N, a.ntcap), mlp->weight[1 + l], ws);
             a.image[l] = ws;
             ws += (tc_image_bytes(K, N) + 255) & ~(size_t)255;
         }
