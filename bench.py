@@ -251,6 +251,9 @@ def main():
             "sa2_mlp": lambda: ops.sa_module_infer(l1_xyz, l2_xyz, l1_pts, 0.4, 64, mlp2, idx=idx2),
             "sa3_mlp": lambda: ops.shared_mlp(l3_in, mlp3, pool_k=128),
             "head": lambda: ops.shared_mlp(l3, head),
+            # variant F1 (training-mode front of SA1): ball query + group + centre + conv1 -> pre-BN (B,m,K,64) + idx + BN stats
+            "sa1_f1": lambda: ops.sa_conv1_prebn(x, l1_xyz, None, 0.2, 32, p["layer1/conv0/weights"].reshape(3, 64),
+                                                 p["layer1/conv0/biases"], want_stats=True),
         }
         flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > L2
         for name, fn in cases.items():
@@ -304,6 +307,13 @@ def main():
     for k in ("sa1_mlp", "sa2_mlp", "sa3_mlp"):
         kern[k] = {"us": stages[k], "tflops_fp32": SA_FLOPS[k[:3]] / (stages[k] * 1e-6) / 1e12}
     kern["head"] = {"us": stages["head"]}
+    # F1: B*(12n + 12m) in, 4*B*m*K*C1 (pre-BN) + 4*B*m*K (idx) + 4*B*m (pts_cnt) out  (137.3 MB)
+    f1_bytes = B * (12 * N + 12 * 512) + 4 * B * 512 * 32 * 64 + 4 * B * 512 * 32 + 4 * B * 512
+    f1_gbs = f1_bytes / (stages["sa1_f1"] * 1e-6) / 1e9
+    kern["sa1_f1"] = {"us": stages["sa1_f1"], "alg_bytes": f1_bytes, "gbs": f1_gbs, "hbm_frac": f1_gbs / peaks["hbm"]}
+    roofline_f1 = {"kernel": "sa_conv1_prebn_kernel (variant F1: fused ball-query + group + conv1, pre-BN output, SA1 B=32 N=2048 K=32)",
+                   "bound": "hbm", "achieved": f1_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": f1_gbs / peaks["hbm"],
+                   "traffic": None, "peak_source": peaks["src"], "in_timed_step": False}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -323,6 +333,7 @@ def main():
                 "d2h_bytes_per_step": B * NUM_CLASS * 4},
         "gpu_launches": 12 * args.steps,
         "roofline": roofline,
+        "roofline_f1": roofline_f1,
         "kernels": kern,
         "cpu_baseline": cpu,
         "clocks": clocks,

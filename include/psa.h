@@ -205,6 +205,18 @@ PSA_API int psa_get_mlp_mode(void);
 PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, void* scratch /* 6*Kd*N bytes */,
                             psa_stream_t stream);
 
+/* Training-mode front of a set-abstraction level ("variant F1"): ball query + group + centre + first 1x1 conv + bias in
+ * one launch, writing the PRE-batch-norm activations (which training-mode BN needs in HBM once: batch statistics come
+ * before the ReLU, pointnet2/utils/tf_util.py:512-531 with is_training=True) and, optionally, their per-channel sum and
+ * sum of squares.  xyz (b,n,3), new_xyz (b,m,3), points (b,n,c) or NULL, w1 (3+c, C1) (xyz rows first), bias (C1) or
+ * NULL -> pre (b,m,nsample,C1), idx (b,m,nsample), pts_cnt (b,m) or NULL, stats (2,C1) or NULL.  C1 in {64,128,192,256}.
+ * Replaces query_ball_point + group_point x2 + tile/sub + concat + conv2d/bias_add (pointnet_util.py:44-50,117-123). */
+PSA_API size_t psa_sa_conv1_prebn_workspace_bytes(int b, int n, int m, int c, int C1, int want_stats);
+PSA_API int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int nsample, const float* xyz,
+                               const float* new_xyz, const float* points, const float* w1, const float* bias, int C1,
+                               float* pre, int* idx, int* pts_cnt, float* stats, void* workspace,
+                               size_t workspace_bytes, psa_stream_t stream);
+
 /* Fused EdgeConv, inference mode (dgcnn/models/dgcnn.py:31-47 pattern): x (b,n,c), nn_idx (b,n,k) ->
  * out (b,n,C_L) = max_j MLP([x_i, x_j - x_i]); mlp->channels[0] must equal 2c. */
 PSA_API int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,

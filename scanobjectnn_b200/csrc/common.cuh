@@ -65,6 +65,21 @@ __device__ __forceinline__ float dist2_ref_cpu(float dx, float dy, float dz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Cooperative copy of `count` floats global -> shared with 8 independent loads in flight per thread (a plain
+// `for (i) s[i] = g[i]` loop is one L2 round trip per iteration: ~0.35 us each, tens of us for a 24 KB cloud).
+template <int THREADS>
+__device__ __forceinline__ void stage_floats(float* __restrict__ dst, const float* __restrict__ src, int count, int tid) {
+    int i = tid;
+    for (; i + 7 * THREADS < count; i += 8 * THREADS) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i + u * THREADS);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[i + u * THREADS] = v[u];
+    }
+    for (; i < count; i += THREADS) dst[i] = __ldg(src + i);
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -99,10 +99,24 @@ ball_query_kernel(int n, int m, int nsample, float thr, int none, int q_per_cta,
     float* sz = sy + np;
     const int cloud = blockIdx.y;
     const float* p1 = xyz1 + (size_t)cloud * n * 3;
-    for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
-        int k = i / 3, c = i - k * 3;
-        float v = p1[i];
-        if (c == 0) sx[k] = v; else if (c == 1) sy[k] = v; else sz[k] = v;
+    // AoS -> SoA staging, 8 independent loads in flight per thread
+    {
+        const int total = n * 3;
+        int i = threadIdx.x;
+        for (; i + 7 * (kBqWarps * 32) < total; i += 8 * (kBqWarps * 32)) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(p1 + i + u * (kBqWarps * 32));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = i + u * (kBqWarps * 32), k = e / 3, c = e - k * 3;
+                (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v[u];
+            }
+        }
+        for (; i < total; i += kBqWarps * 32) {
+            const int k = i / 3, c = i - k * 3;
+            (c == 0 ? sx : (c == 1 ? sy : sz))[k] = __ldg(p1 + i);
+        }
     }
     const float inf = __int_as_float(0x7f800000);
     for (int k = n + threadIdx.x; k < np; k += blockDim.x) { sx[k] = inf; sy[k] = inf; sz[k] = inf; }

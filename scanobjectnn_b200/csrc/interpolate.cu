@@ -33,9 +33,19 @@ __device__ __forceinline__ void three_nn_scan(int m, const float* __restrict__ p
     for (int base = 0; base < m; base += kNnTile) {
         const int cnt = min(kNnTile, m - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const float* q = p2 + (size_t)(base + i) * 3;
-            tile[i] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+        for (int i0 = threadIdx.x; i0 < cnt; i0 += 4 * kNnThreads) {      // 12 independent loads in flight per thread
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kNnThreads;
+                const float* q = p2 + (size_t)(base + (i < cnt ? i : 0)) * 3;
+                v[u] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kNnThreads;
+                if (i < cnt) tile[i] = v[u];
+            }
         }
         __syncthreads();
         if (active) {

@@ -37,7 +37,7 @@ fps_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_ou
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
     const float* p = xyz + (size_t)cloud * n * 3;
-    for (int i = t; i < n * 3; i += T) sxyz[i] = p[i];
+    stage_floats<T>(sxyz, p, n * 3, t);
     __syncthreads();
 
     float2 px[NP], py[NP], pz[NP], td[NP];

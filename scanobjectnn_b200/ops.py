@@ -19,7 +19,7 @@ __all__ = [
     "farthest_point_sample", "gather_point", "query_ball_point", "group_point", "select_top_k", "knn_point",
     "three_nn", "three_interpolate", "three_nn_interpolate", "pairwise_distance", "knn", "knn_graph",
     "get_edge_feature", "farthest_point_sample_and_gather", "MlpParams", "shared_mlp", "sa_module_infer",
-    "edgeconv_infer", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
+    "edgeconv_infer", "sa_conv1_prebn", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
 ]
 
 
@@ -412,6 +412,38 @@ def sa_module_infer(xyz, new_xyz, points, radius: float, nsample: int, mlp: MlpP
     if return_idx:
         return out, (idx if idx is not None else idx_out), cnt
     return out
+
+
+def sa_conv1_prebn(xyz, new_xyz, points, radius: float, nsample: int, w1, bias=None, want_stats: bool = True):
+    """Training-mode front of a set-abstraction level (variant F1): ball query + group + centre + conv1 + bias in one
+    launch.  -> pre (B,M,nsample,C1) PRE-batch-norm activations, idx (B,M,nsample), pts_cnt (B,M), stats (2,C1) =
+    per-channel [sum, sum of squares] over all rows (None unless want_stats)."""
+    xyz = _dev(xyz, torch.float32, "xyz", 3)
+    new_xyz = _dev(new_xyz, torch.float32, "new_xyz", 3)
+    w1 = _dev(w1, torch.float32, "w1", 2)
+    b, n, _ = xyz.shape
+    m = new_xyz.shape[1]
+    c = 0
+    if points is not None:
+        points = _dev(points, torch.float32, "points", 3)
+        c = points.shape[2]
+    if w1.shape[0] != 3 + c:
+        raise ValueError(f"sa_conv1_prebn: w1 has {w1.shape[0]} rows, expected 3 + {c}")
+    c1 = w1.shape[1]
+    if bias is not None:
+        bias = _dev(bias, torch.float32, "bias", 1)
+    dev = xyz.device
+    pre = torch.empty((b, m, nsample, c1), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=dev)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
+    stats = torch.empty((2, c1), dtype=torch.float32, device=dev) if want_stats else None
+    lib = _lib.load()
+    need = lib.psa_sa_conv1_prebn_workspace_bytes(b, n, m, c, c1, 1 if want_stats else 0)
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dev) if need else None
+    check(lib.psa_sa_conv1_prebn(b, n, m, c, C.c_float(radius), nsample, _ptr(xyz), _ptr(new_xyz), _ptr(points), _ptr(w1),
+                                 _ptr(bias), c1, _ptr(pre), _ptr(idx), _ptr(cnt), _ptr(stats), _ptr(ws), C.c_size_t(need),
+                                 _stream()), "sa_conv1_prebn")
+    return pre, idx, cnt, stats
 
 
 def edgeconv_infer(x, nn_idx, mlp: MlpParams) -> torch.Tensor:

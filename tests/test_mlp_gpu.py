@@ -129,3 +129,27 @@ def test_pointnet2_cls_ssg_matches_oracle(kind, mlp_mode):
     err = np.abs(G.npy(logits) - want).max()
     print(f"logits[{mlp_mode}] max|err|={err:.3e} max|logit|={np.abs(want).max():.3f}")
     assert err < TOL * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("kind,n,m,r,k,c,c1", [("ball", 2048, 512, 0.2, 32, 0, 64), ("shell", 2048, 512, 0.2, 64, 0, 64),
+                                               ("ball", 512, 128, 0.4, 64, 128, 128), ("dup", 300, 40, 0.3, 20, 5, 64)])
+def test_sa_conv1_prebn_training_front(kind, n, m, r, k, c, c1):
+    """variant F1: pre-BN conv1 output + BN batch statistics vs the fp64 restatement of
+    query_ball_point -> group_point -> centre -> concat -> conv2d + bias_add (pointnet_util.py:44-50,117-123)."""
+    rng = np.random.default_rng(n + k)
+    xyz = make_clouds(kind, 3, n, seed=n)
+    pts = rng.standard_normal((3, n, c)).astype(np.float32) if c else None
+    w1 = (rng.uniform(-1, 1, (3 + c, c1)) * np.sqrt(6.0 / (3 + c + c1))).astype(np.float32)
+    bias = rng.uniform(-0.1, 0.1, c1).astype(np.float32)
+    new_xyz = orc.gather_point(xyz, orc.fps(xyz, m))
+    pre, idx, cnt, stats = ops.sa_conv1_prebn(G.cu(xyz), G.cu(new_xyz), G.cu(pts) if c else None, r, k, G.cu(w1), G.cu(bias))
+    oidx, ocnt = orc.query_ball_point(r, k, xyz, new_xyz, contract=True)
+    assert np.array_equal(G.npy(idx), oidx) and np.array_equal(G.npy(cnt), ocnt)
+    rows = orc.group_point(xyz, oidx) - new_xyz[:, :, None, :]
+    if c:
+        rows = np.concatenate([rows, orc.group_point(pts, oidx)], -1)
+    want = rows.astype(np.float64) @ w1.astype(np.float64) + bias
+    got = G.npy(pre)
+    assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
+    s_want = np.stack([want.reshape(-1, c1).sum(0), (want.reshape(-1, c1) ** 2).sum(0)])
+    np.testing.assert_allclose(G.npy(stats), s_want, rtol=2e-5, atol=1e-3)
