@@ -1,0 +1,306 @@
+// ball_query.cuh -- block-level building blocks of the index-exact ball query (shared by grouping.cu and sa_train.cu).
+//
+// Reference semantics (pointnet2/tf_ops/grouping/tf_grouping_g.cu:3-36): for every query scan the dataset in index
+// order, keep the first `nsample` points with max(sqrtf(d2),1e-20f) < radius, fill the unused slots with the first hit,
+// report the (clamped) count.  "First nsample in index order" == "the nsample smallest indices among ALL in-radius
+// points", which is what lets a spatial grid in:
+//
+//   grid path   the CTA bins its cloud (already staged in shared memory) into cells of size 1.001*radius (at most 16 per
+//               axis) with a counting sort; a query only tests the points of its 3x3x3 cell neighbourhood (~5 % of a
+//               uniform cloud instead of 100 %), compacts the hits with ballots, ranks them by index (counting rank) and
+//               emits the nsample smallest in ascending order -- bit-identical output, ~3x fewer instructions;
+//   scan path   the ordered brute-force scan (128 points per warp step, early exit), used when the cloud or the query has a
+//               non-finite coordinate (a NaN distance counts as inside in the reference), when the grid would be
+//               degenerate, when the cloud does not fit the grid's shared-memory budget, or when a query collects more
+//               than kBqHitCap hits (dense neighbourhoods: exactly where the early-exit scan is fast).
+// The distance test is the same arithmetic in both paths: d2 = fma(dz,dz,fma(dx,dx,dy*dy)) and !(d2 > T) with T the largest
+// float whose sqrtf is < radius (see grouping.cu).
+#pragma once
+#include "common.cuh"
+
+namespace psa {
+
+constexpr int kBqWarps = 8;
+constexpr int kBqThreads = kBqWarps * 32;
+constexpr int kBqGridMax = 16;          // cells per axis
+constexpr int kBqMaxCells = kBqGridMax * kBqGridMax * kBqGridMax;
+constexpr int kBqHitCap = 128;          // in-radius candidates a query may collect on the grid path
+constexpr int kBqGridMaxN = 4096;       // clouds larger than this use the scan path only (shared-memory budget)
+
+struct BqGrid {
+    float minx, miny, minz, inv_h;
+    int gx, gy, gz;
+    int use;                            // 0 -> scan path for the whole CTA
+};
+
+struct BqSmem {
+    float* sx; float* sy; float* sz;    // np = round_up(n,128) floats each, padded with +inf
+    float4* sorted;                     // n entries (x, y, z, bits(k)), grouped by cell          (grid only)
+    int* cell_end;                      // kBqMaxCells + 32 ints: end offset of each cell, scratch (grid only)
+    int* hits;                          // kBqWarps * kBqHitCap                                    (grid only)
+};
+
+__host__ __device__ inline size_t bq_smem_bytes(int n, bool grid) {
+    size_t b = (size_t)((n + 127) & ~127) * 3 * sizeof(float);
+    if (grid) b += (size_t)n * 16 + (size_t)(kBqMaxCells + 32) * 4 + (size_t)kBqWarps * kBqHitCap * 4;
+    return b;
+}
+__host__ __device__ inline bool bq_grid_fits(int n) { return n <= kBqGridMaxN; }
+
+__device__ __forceinline__ BqSmem bq_carve(float* base, int n, bool grid) {
+    BqSmem s;
+    const int np = (n + 127) & ~127;
+    s.sx = base; s.sy = base + np; s.sz = base + 2 * np;
+    s.sorted = reinterpret_cast<float4*>(base + 3 * np);       // 3*np*4 bytes is a multiple of 16
+    s.cell_end = reinterpret_cast<int*>(s.sorted + (grid ? n : 0));
+    s.hits = s.cell_end + (grid ? kBqMaxCells + 32 : 0);
+    return s;
+}
+
+__device__ __forceinline__ int bq_cell_coord(float v, float vmin, float inv_h, int g) {
+    const int c = (int)((v - vmin) * inv_h);
+    return c < g - 1 ? c : g - 1;
+}
+
+// Stage one cloud (AoS global -> SoA shared, padded with +inf) and, if asked, build the cell grid.  All kBqThreads call.
+__device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, const float* __restrict__ p1, int n, float radius,
+                                                     bool want_grid) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int np = (n + 127) & ~127;
+    const float inf = __int_as_float(0x7f800000);
+    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+    bool fin = true;
+    {
+        const int total = n * 3;
+        int i = tid;
+        for (; i + 7 * kBqThreads < total; i += 8 * kBqThreads) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(p1 + i + u * kBqThreads);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = i + u * kBqThreads, k = e / 3, c = e - k * 3;
+                (c == 0 ? s.sx : (c == 1 ? s.sy : s.sz))[k] = v[u];
+                fin = fin && (fabsf(v[u]) <= 3.0e38f);
+                mn[c] = fminf(mn[c], v[u]); mx[c] = fmaxf(mx[c], v[u]);
+            }
+        }
+        for (; i < total; i += kBqThreads) {
+            const int k = i / 3, c = i - k * 3;
+            const float v = __ldg(p1 + i);
+            (c == 0 ? s.sx : (c == 1 ? s.sy : s.sz))[k] = v;
+            fin = fin && (fabsf(v) <= 3.0e38f);
+            mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+        }
+    }
+    for (int k = n + tid; k < np; k += kBqThreads) { s.sx[k] = inf; s.sy[k] = inf; s.sz[k] = inf; }
+    BqGrid g;
+    g.use = 0; g.minx = g.miny = g.minz = 0.f; g.inv_h = 0.f; g.gx = g.gy = g.gz = 1;
+    if (!want_grid) { __syncthreads(); return g; }
+    // ---- bounding box + finiteness: warp shuffles, then 8 partials through shared memory ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+    }
+    fin = __all_sync(0xffffffffu, fin);
+    float* scratch = reinterpret_cast<float*>(s.cell_end);
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { scratch[warp * 8 + c] = mn[c]; scratch[warp * 8 + 3 + c] = mx[c]; }
+        scratch[warp * 8 + 6] = fin ? 1.f : 0.f;
+    }
+    __syncthreads();
+    {
+        float bmn[3] = {inf, inf, inf}, bmx[3] = {-inf, -inf, -inf};
+        bool bfin = true;
+#pragma unroll
+        for (int w = 0; w < kBqWarps; ++w) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { bmn[c] = fminf(bmn[c], scratch[w * 8 + c]); bmx[c] = fmaxf(bmx[c], scratch[w * 8 + 3 + c]); }
+            bfin = bfin && scratch[w * 8 + 6] != 0.f;
+        }
+        const float rx = bmx[0] - bmn[0], ry = bmx[1] - bmn[1], rz = bmx[2] - bmn[2];
+        const float rmax = fmaxf(rx, fmaxf(ry, rz));
+        const float h = fmaxf(radius * 1.001f, rmax * (1.0f / kBqGridMax) * 1.001f);   // cell >= 1.001 r, <= 16 cells per axis
+        g.minx = bmn[0]; g.miny = bmn[1]; g.minz = bmn[2];
+        g.inv_h = 1.0f / h;
+        g.gx = min(kBqGridMax, (int)(rx * g.inv_h) + 1);
+        g.gy = min(kBqGridMax, (int)(ry * g.inv_h) + 1);
+        g.gz = min(kBqGridMax, (int)(rz * g.inv_h) + 1);
+        // a grid of fewer than 27 cells prunes nothing; non-finite coordinates need the reference's NaN semantics
+        g.use = (bfin && n >= 1 && h > 0.f && h <= 3.0e38f && g.gx * g.gy * g.gz >= 27) ? 1 : 0;
+    }
+    __syncthreads();                     // scratch (cell_end) is about to be reused
+    if (!g.use) return g;
+    const int ncells = g.gx * g.gy * g.gz;
+    for (int c = tid; c < ncells; c += kBqThreads) s.cell_end[c] = 0;
+    __syncthreads();
+    for (int k = tid; k < n; k += kBqThreads) {
+        const int cx = bq_cell_coord(s.sx[k], g.minx, g.inv_h, g.gx), cy = bq_cell_coord(s.sy[k], g.miny, g.inv_h, g.gy);
+        const int cz = bq_cell_coord(s.sz[k], g.minz, g.inv_h, g.gz);
+        atomicAdd(&s.cell_end[(cz * g.gy + cy) * g.gx + cx], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the cell counts: each thread owns a contiguous run of cells
+    {
+        const int per = (ncells + kBqThreads - 1) / kBqThreads;      // <= 16
+        const int c0 = tid * per;
+        int local = 0;
+        for (int c = c0; c < min(ncells, c0 + per); ++c) local += s.cell_end[c];
+        int incl = local;                                            // warp inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int* wsum = s.cell_end + kBqMaxCells;                        // 8 warp totals
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int off = incl - local;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        for (int c = c0; c < min(ncells, c0 + per); ++c) { const int cnt = s.cell_end[c]; s.cell_end[c] = off; off += cnt; }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += kBqThreads) {
+        const float x = s.sx[k], y = s.sy[k], z = s.sz[k];
+        const int cx = bq_cell_coord(x, g.minx, g.inv_h, g.gx), cy = bq_cell_coord(y, g.miny, g.inv_h, g.gy);
+        const int cz = bq_cell_coord(z, g.minz, g.inv_h, g.gz);
+        const int pos = atomicAdd(&s.cell_end[(cz * g.gy + cy) * g.gx + cx], 1);     // afterwards cell_end[c] = END of cell c
+        s.sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+    __syncthreads();
+    return g;
+}
+
+// squared distances of two dataset points to one query on the packed f32x2 pipe: per element the reference's
+// FMUL(dy*dy), FFMA(dx,dx), FFMA(dz,dz) (x_k - q instead of q - x_k: identical squares)
+__device__ __forceinline__ float2 bq_dist2_pair(float2 x, float2 y, float2 z, float2 nqx, float2 nqy, float2 nqz) {
+    const float2 dx = __fadd2_rn(x, nqx), dy = __fadd2_rn(y, nqy), dz = __fadd2_rn(z, nqz);
+    float2 t = __fmul2_rn(dy, dy);
+    t = __ffma2_rn(dx, dx, t);
+    t = __ffma2_rn(dz, dz, t);
+    return t;
+}
+
+// Ordered scan path: one warp, 128 points per step, ballot + prefix-popcount compaction keeps index order, early exit.
+__device__ __forceinline__ int bq_scan_warp(int n, int nsample, float thr, bool none, const BqSmem& s, float qx, float qy,
+                                            float qz, int* idxrow, int lane) {
+    int cnt = 0, first = -1;
+    if (!none) {
+        const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+        const unsigned lt = lanemask_lt();
+        for (int base = 0; base < n && cnt < nsample; base += 128) {
+            const int k = base + lane * 4;
+            const float4 X = *reinterpret_cast<const float4*>(s.sx + k);
+            const float4 Y = *reinterpret_cast<const float4*>(s.sy + k);
+            const float4 Z = *reinterpret_cast<const float4*>(s.sz + k);
+            const float2 d01 = bq_dist2_pair(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
+            const float2 d23 = bq_dist2_pair(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
+            // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
+            bool i0 = !(d01.x > thr), i1 = !(d01.y > thr), i2 = !(d23.x > thr), i3 = !(d23.y > thr);
+            if (base + 128 > n) {   // last chunk: the +inf padding must not count even when the QUERY is NaN
+                i0 = i0 && (k < n); i1 = i1 && (k + 1 < n); i2 = i2 && (k + 2 < n); i3 = i3 && (k + 3 < n);
+            }
+            const unsigned m4 = (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
+            const unsigned anyb = __ballot_sync(0xffffffffu, m4 != 0u);
+            if (anyb == 0u) continue;
+            const unsigned b0 = __ballot_sync(0xffffffffu, i0), b1 = __ballot_sync(0xffffffffu, i1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, i2), b3 = __ballot_sync(0xffffffffu, i3);
+            if (first < 0) {
+                const int lf = __ffs(anyb) - 1;
+                const unsigned mf = __shfl_sync(0xffffffffu, m4, lf);
+                first = base + lf * 4 + (__ffs(mf) - 1);
+            }
+            int pos = cnt + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+            if (i0) { if (pos < nsample) idxrow[pos] = k; ++pos; }
+            if (i1) { if (pos < nsample) idxrow[pos] = k + 1; ++pos; }
+            if (i2) { if (pos < nsample) idxrow[pos] = k + 2; ++pos; }
+            if (i3) { if (pos < nsample) idxrow[pos] = k + 3; }
+            cnt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        }
+    }
+    if (cnt > nsample) cnt = nsample;
+    const int fillv = first < 0 ? 0 : first;
+    for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = fillv;   // tf_grouping_g.cu:26-29
+    return cnt;
+}
+
+// One warp, one query.  Writes the idx row (global or shared memory) and returns the clamped count.
+__device__ __forceinline__ int bq_query_warp(int n, int nsample, float thr, bool none, const BqSmem& s, const BqGrid& g,
+                                             float qx, float qy, float qz, int* idxrow, int lane, int warp) {
+    const bool qfin = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;
+    if (!g.use || !qfin || none) return bq_scan_warp(n, nsample, thr, none, s, qx, qy, qz, idxrow, lane);
+    // ---- the (up to) nine x-contiguous cell runs of the 3x3x3 neighbourhood, one per lane 0..8 ----
+    const float fx = fminf(fmaxf((qx - g.minx) * g.inv_h, -2.f), (float)(kBqGridMax + 1));
+    const float fy = fminf(fmaxf((qy - g.miny) * g.inv_h, -2.f), (float)(kBqGridMax + 1));
+    const float fz = fminf(fmaxf((qz - g.minz) * g.inv_h, -2.f), (float)(kBqGridMax + 1));
+    const int cqx = (int)floorf(fx), cqy = (int)floorf(fy), cqz = (int)floorf(fz);
+    const int lox = max(cqx - 1, 0), hix = min(cqx + 1, g.gx - 1);
+    int start = 0, len = 0;
+    if (lane < 9 && lox <= hix) {
+        const int cy = cqy + (lane % 3) - 1, cz = cqz + (lane / 3) - 1;
+        if (cy >= 0 && cy < g.gy && cz >= 0 && cz < g.gz) {
+            const int rb = (cz * g.gy + cy) * g.gx;
+            start = (rb + lox == 0) ? 0 : s.cell_end[rb + lox - 1];
+            len = s.cell_end[rb + hix] - start;
+        }
+    }
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 8);
+    int r_start[9], r_end[9];          // candidate slot t belongs to run i iff r_end[i-1] <= t < r_end[i]
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        r_start[i] = __shfl_sync(0xffffffffu, start, i);
+        r_end[i] = __shfl_sync(0xffffffffu, incl, i);
+    }
+    // ---- test the candidates, compact the hits (any order) ----
+    int* hits = s.hits + warp * kBqHitCap;
+    const unsigned lt = lanemask_lt();
+    int nh = 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        bool in = false;
+        int k = 0;
+        if (t < total) {
+            int sel = r_start[0] + t;
+#pragma unroll
+            for (int i = 1; i < 9; ++i)
+                if (t >= r_end[i - 1]) sel = r_start[i] + (t - r_end[i - 1]);
+            const float4 p = s.sorted[sel];
+            k = __float_as_int(p.w);
+            in = !(dist2_ref_gpu(qx - p.x, qy - p.y, qz - p.z) > thr);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, in);
+        if (in) { const int pos = nh + __popc(b & lt); if (pos < kBqHitCap) hits[pos] = k; }
+        nh += __popc(b);
+        if (nh > kBqHitCap) break;       // warp-uniform
+    }
+    __syncwarp();
+    if (nh > kBqHitCap) return bq_scan_warp(n, nsample, thr, none, s, qx, qy, qz, idxrow, lane);
+    // ---- rank the hits by index: the reference keeps the nsample smallest, in ascending order ----
+    int first = 0x7fffffff;
+    for (int h0 = 0; h0 < nh; h0 += 32) {
+        const int h = h0 + lane;
+        const int mine = h < nh ? hits[h] : 0x7fffffff;
+        int rank = 0;
+        for (int j = 0; j < nh; ++j) rank += (hits[j] < mine) ? 1 : 0;     // broadcast reads; indices are distinct
+        if (h < nh && rank < nsample) idxrow[rank] = mine;
+        first = min(first, mine);
+    }
+    first = __reduce_min_sync(0xffffffffu, first);
+    const int cnt = min(nh, nsample);
+    const int fillv = nh > 0 ? first : 0;
+    for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = fillv;
+    return cnt;
+}
+
+}  // namespace psa

@@ -1,7 +1,8 @@
 // grouping.cu -- ball query, group_point (+grad), SelectionSort / knn_point for sm_100a.
 //
 // Replaces pointnet2/tf_ops/grouping/tf_grouping_g.cu of the reference (one CTA per cloud, one thread per
-// query walking all n points from global memory).  Here: the cloud's coordinates are staged once per CTA in
+// query walking all n points from global memory).  The ball query itself lives in ball_query.cuh (spatial grid +
+// ordered-scan fallback, index-exact).  Here: the cloud's coordinates are staged once per CTA in
 // shared memory as SoA, one WARP owns a query and tests 32 consecutive points per step, and the reference's
 // "first nsample in index order" rule is kept by ballot + prefix-popcount compaction, tiles consumed in
 // ascending order, with a per-query early exit.  The sqrt of the reference's `max(sqrtf(d2),1e-20f) < r` test
@@ -10,6 +11,7 @@
 #include <math.h>
 #include <string.h>
 
+#include "ball_query.cuh"
 #include "common.cuh"
 
 namespace psa {
@@ -30,97 +32,14 @@ float ball_query_threshold(float radius, bool* none) {
     return t;
 }
 
-constexpr int kBqWarps = 8;
-
-// squared distances of two dataset points to one query with the packed f32x2 pipe (FADD2/FMUL2/FFMA2): same
-// per-element IEEE operations, same order (dy*dy, then fma dx, then fma dz) as dist2_ref_gpu, half the instructions
-__device__ __forceinline__ float2 dist2_pair(float2 x, float2 y, float2 z, float2 nqx, float2 nqy, float2 nqz) {
-    const float2 dx = __fadd2_rn(x, nqx), dy = __fadd2_rn(y, nqy), dz = __fadd2_rn(z, nqz);   // x_k - q: sign is irrelevant squared
-    float2 t = __fmul2_rn(dy, dy);
-    t = __ffma2_rn(dx, dx, t);
-    t = __ffma2_rn(dz, dz, t);
-    return t;
-}
-
-// One warp per query, 128 points per step (4 consecutive points per lane, float4 from the SoA arrays).  sx/sy/sz hold
-// the cloud padded to a multiple of 128 with +inf (distance +inf: never inside).  The reference's "first nsample in
-// index order" rule is kept by ballot + prefix-popcount compaction: a hit at (lane, j) lands at
-// cnt + #hits in lower lanes + #own hits with j' < j.  Writes the idx row and returns the clamped count; empty -> 0s.
-__device__ __forceinline__ int ball_query_warp(int n, int nsample, float thr, bool none, const float* sx,
-                                               const float* sy, const float* sz, float qx, float qy, float qz,
-                                               int* idxrow, int lane) {
-    int cnt = 0, first = -1;
-    if (!none) {
-        const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
-        const unsigned lt = lanemask_lt();
-        for (int base = 0; base < n && cnt < nsample; base += 128) {
-            const int k = base + lane * 4;
-            const float4 X = *reinterpret_cast<const float4*>(sx + k);
-            const float4 Y = *reinterpret_cast<const float4*>(sy + k);
-            const float4 Z = *reinterpret_cast<const float4*>(sz + k);
-            const float2 d01 = dist2_pair(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
-            const float2 d23 = dist2_pair(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
-            // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
-            bool i0 = !(d01.x > thr), i1 = !(d01.y > thr), i2 = !(d23.x > thr), i3 = !(d23.y > thr);
-            if (base + 128 > n) {   // last chunk: the +inf padding must not count even when the QUERY is NaN (NaN - inf = NaN)
-                i0 = i0 && (k < n); i1 = i1 && (k + 1 < n); i2 = i2 && (k + 2 < n); i3 = i3 && (k + 3 < n);
-            }
-            const unsigned m4 = (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
-            const unsigned anyb = __ballot_sync(0xffffffffu, m4 != 0u);
-            if (anyb == 0u) continue;
-            const unsigned b0 = __ballot_sync(0xffffffffu, i0), b1 = __ballot_sync(0xffffffffu, i1);
-            const unsigned b2 = __ballot_sync(0xffffffffu, i2), b3 = __ballot_sync(0xffffffffu, i3);
-            if (first < 0) {
-                const int lf = __ffs(anyb) - 1;
-                const unsigned mf = __shfl_sync(0xffffffffu, m4, lf);
-                first = base + lf * 4 + (__ffs(mf) - 1);
-            }
-            int pos = cnt + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-            if (i0) { if (pos < nsample) idxrow[pos] = k; ++pos; }
-            if (i1) { if (pos < nsample) idxrow[pos] = k + 1; ++pos; }
-            if (i2) { if (pos < nsample) idxrow[pos] = k + 2; ++pos; }
-            if (i3) { if (pos < nsample) idxrow[pos] = k + 3; }
-            cnt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-        }
-    }
-    if (cnt > nsample) cnt = nsample;
-    const int fillv = first < 0 ? 0 : first;
-    for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = fillv;   // tf_grouping_g.cu:26-29
-    return cnt;
-}
-
-__global__ void __launch_bounds__(kBqWarps * 32)
-ball_query_kernel(int n, int m, int nsample, float thr, int none, int q_per_cta, const float* __restrict__ xyz1,
-                  const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
+__global__ void __launch_bounds__(kBqThreads)
+ball_query_kernel(int n, int m, int nsample, float radius, float thr, int none, int want_grid, int q_per_cta,
+                  const float* __restrict__ xyz1, const float* __restrict__ xyz2, int* __restrict__ idx,
+                  int* __restrict__ pts_cnt) {
     extern __shared__ __align__(16) float smem_f[];
-    const int np = (n + 127) & ~127;          // padded point count
-    float* sx = smem_f;
-    float* sy = sx + np;
-    float* sz = sy + np;
+    const BqSmem s = bq_carve(smem_f, n, want_grid != 0);
     const int cloud = blockIdx.y;
-    const float* p1 = xyz1 + (size_t)cloud * n * 3;
-    // AoS -> SoA staging, 8 independent loads in flight per thread
-    {
-        const int total = n * 3;
-        int i = threadIdx.x;
-        for (; i + 7 * (kBqWarps * 32) < total; i += 8 * (kBqWarps * 32)) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(p1 + i + u * (kBqWarps * 32));
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = i + u * (kBqWarps * 32), k = e / 3, c = e - k * 3;
-                (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v[u];
-            }
-        }
-        for (; i < total; i += kBqWarps * 32) {
-            const int k = i / 3, c = i - k * 3;
-            (c == 0 ? sx : (c == 1 ? sy : sz))[k] = __ldg(p1 + i);
-        }
-    }
-    const float inf = __int_as_float(0x7f800000);
-    for (int k = n + threadIdx.x; k < np; k += blockDim.x) { sx[k] = inf; sy[k] = inf; sz[k] = inf; }
-    __syncthreads();
+    const BqGrid g = bq_stage_and_build(s, xyz1 + (size_t)cloud * n * 3, n, radius, want_grid != 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * q_per_cta;
     const int q1 = min(m, q0 + q_per_cta);
@@ -128,7 +47,7 @@ ball_query_kernel(int n, int m, int nsample, float thr, int none, int q_per_cta,
     for (int q = q0 + warp; q < q1; q += kBqWarps) {
         const float qx = __ldg(p2 + q * 3 + 0), qy = __ldg(p2 + q * 3 + 1), qz = __ldg(p2 + q * 3 + 2);
         int* row = idx + ((size_t)cloud * m + q) * nsample;
-        int cnt = ball_query_warp(n, nsample, thr, none != 0, sx, sy, sz, qx, qy, qz, row, lane);
+        const int cnt = bq_query_warp(n, nsample, thr, none != 0, s, g, qx, qy, qz, row, lane, warp);
         if (pts_cnt != nullptr && lane == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
     }
 }
@@ -250,19 +169,21 @@ extern "C" int psa_query_ball_point(int b, int n, int m, float radius, int nsamp
     if (b == 0 || m == 0) return PSA_OK;
     PSA_REQUIRE(idx != nullptr || nsample == 0, "QueryBallPoint: null idx");
     PSA_REQUIRE((xyz1 != nullptr || n == 0) && xyz2 != nullptr, "QueryBallPoint: null input");
-    size_t smem = (size_t)((n + 127) & ~127) * 3 * sizeof(float);
+    // the spatial grid pays off once a CTA answers enough queries to amortise the counting sort
+    const bool want_grid = bq_grid_fits(n) && n >= 256 && m >= 32;
+    size_t smem = bq_smem_bytes(n, want_grid);
     PSA_SUPPORTED(smem <= 200 * 1024, "query_ball_point: n=%d exceeds the shared-memory resident limit", n);
     bool none = false;
     float thr = ball_query_threshold(radius, &none);
-    // enough CTAs for ~2 waves of 148 SMs, at least one warp-batch of queries per CTA
+    // enough CTAs for ~2 waves of 148 SMs, at least two warp-batches of queries per CTA
     int chunks = (2 * kNumSMs + b - 1) / b;
     int q_per_cta = (m + chunks - 1) / chunks;
     q_per_cta = ((q_per_cta + kBqWarps - 1) / kBqWarps) * kBqWarps;
     if (q_per_cta < 2 * kBqWarps) q_per_cta = 2 * kBqWarps;
     dim3 grid((m + q_per_cta - 1) / q_per_cta, b);
     PSA_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ball_query_kernel<<<grid, kBqWarps * 32, smem, as_stream(stream)>>>(n, m, nsample, thr, none ? 1 : 0, q_per_cta,
-                                                                       xyz1, xyz2, idx, pts_cnt);
+    ball_query_kernel<<<grid, kBqThreads, smem, as_stream(stream)>>>(n, m, nsample, radius, thr, none ? 1 : 0, want_grid ? 1 : 0,
+                                                                     q_per_cta, xyz1, xyz2, idx, pts_cnt);
     return check_launch("ball_query_kernel");
 }
 

@@ -9,67 +9,19 @@
 //   coalesced streaming store of (B,m,K,C1) + idx/pts_cnt + per-channel sum / sum-of-squares for the BN statistics.
 // HBM traffic = algorithmic traffic: B*(12n + 12m) in, 4*B*m*K*(C1+1) + 4*B*m out  (137.3 MB at B=32,N=2048,m=512,K=32,
 // C1=64) -- a pure write-bound kernel, the one BASELINE.json's ">= 70 % of the HBM roofline" target is defined on.
+#include "ball_query.cuh"
 #include "common.cuh"
 
 namespace psa {
 
 float ball_query_threshold(float radius, bool* none);   // grouping.cu
 
-constexpr int kF1Warps = 8;
-
-__device__ __forceinline__ float2 dist2_pair_f1(float2 x, float2 y, float2 z, float2 nqx, float2 nqy, float2 nqz) {
-    const float2 dx = __fadd2_rn(x, nqx), dy = __fadd2_rn(y, nqy), dz = __fadd2_rn(z, nqz);
-    float2 t = __fmul2_rn(dy, dy);
-    t = __ffma2_rn(dx, dx, t);
-    t = __ffma2_rn(dz, dz, t);
-    return t;
-}
-
-// same scan as grouping.cu:ball_query_warp, but the idx row goes to shared memory (the conv stage reads it back)
-__device__ __forceinline__ int ball_query_warp_smem(int n, int nsample, float thr, bool none, const float* sx, const float* sy,
-                                                    const float* sz, float qx, float qy, float qz, int* idxrow, int lane) {
-    int cnt = 0, first = -1;
-    if (!none) {
-        const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
-        const unsigned lt = lanemask_lt();
-        for (int base = 0; base < n && cnt < nsample; base += 128) {
-            const int k = base + lane * 4;
-            const float4 X = *reinterpret_cast<const float4*>(sx + k);
-            const float4 Y = *reinterpret_cast<const float4*>(sy + k);
-            const float4 Z = *reinterpret_cast<const float4*>(sz + k);
-            const float2 d01 = dist2_pair_f1(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
-            const float2 d23 = dist2_pair_f1(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
-            bool i0 = !(d01.x > thr), i1 = !(d01.y > thr), i2 = !(d23.x > thr), i3 = !(d23.y > thr);
-            if (base + 128 > n) { i0 = i0 && (k < n); i1 = i1 && (k + 1 < n); i2 = i2 && (k + 2 < n); i3 = i3 && (k + 3 < n); }
-            const unsigned m4 = (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
-            const unsigned anyb = __ballot_sync(0xffffffffu, m4 != 0u);
-            if (anyb == 0u) continue;
-            const unsigned b0 = __ballot_sync(0xffffffffu, i0), b1 = __ballot_sync(0xffffffffu, i1);
-            const unsigned b2 = __ballot_sync(0xffffffffu, i2), b3 = __ballot_sync(0xffffffffu, i3);
-            if (first < 0) {
-                const int lf = __ffs(anyb) - 1;
-                const unsigned mf = __shfl_sync(0xffffffffu, m4, lf);
-                first = base + lf * 4 + (__ffs(mf) - 1);
-            }
-            int pos = cnt + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-            if (i0) { if (pos < nsample) idxrow[pos] = k; ++pos; }
-            if (i1) { if (pos < nsample) idxrow[pos] = k + 1; ++pos; }
-            if (i2) { if (pos < nsample) idxrow[pos] = k + 2; ++pos; }
-            if (i3) { if (pos < nsample) idxrow[pos] = k + 3; }
-            cnt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-        }
-    }
-    if (cnt > nsample) cnt = nsample;
-    const int fillv = first < 0 ? 0 : first;
-    for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = fillv;
-    __syncwarp();
-    return cnt;
-}
+constexpr int kF1Warps = kBqWarps;
 
 struct F1Args {
     int n, m, nsample, C1, q_per_cta;
-    float thr;
-    int none;
+    float radius, thr;
+    int none, want_grid;
     const float* xyz;      // (b,n,3)
     const float* new_xyz;  // (b,m,3)
     const float* uf;       // (b*n, C1) or null
@@ -81,99 +33,97 @@ struct F1Args {
     float* partial;        // (gridDim.x*gridDim.y, 2, C1) or null
 };
 
-// lane owns channel pairs (2*lane + 64*i, 2*lane + 64*i + 1), i < NP = C1/64
-template <int NP, bool STATS>
+// conv stage mapping: 8 lanes per row, 4 rows per warp step; lane-in-row s owns channels [32*i + 4*s, +4), i < NV = C1/32,
+// so every store instruction writes 128 contiguous bytes per row and a query's K rows take K/4 steps.
+template <int NV, bool STATS>
 __global__ void __launch_bounds__(kF1Warps * 32)
 sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
     extern __shared__ __align__(16) float smem_f[];
-    const int n = a.n, np = (n + 127) & ~127;
-    float* sx = smem_f;
-    float* sy = sx + np;
-    float* sz = sy + np;
-    int* srow = reinterpret_cast<int*>(sz + np);                 // kF1Warps * nsample
-    float* sstat = reinterpret_cast<float*>(srow + kF1Warps * a.nsample);   // kF1Warps * 2 * C1 (STATS)
+    const int n = a.n;
+    const BqSmem s = bq_carve(smem_f, n, a.want_grid != 0);
+    const float* sx = s.sx; const float* sy = s.sy; const float* sz = s.sz;
+    int* srow = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(smem_f) + bq_smem_bytes(n, a.want_grid != 0));   // kF1Warps * nsample
+    float* sstat = reinterpret_cast<float*>(srow + kF1Warps * ((a.nsample + 3) & ~3));   // kF1Warps * 2 * C1 (STATS), 16-B aligned
     const int cloud = blockIdx.y;
-    const float* p1 = a.xyz + (size_t)cloud * n * 3;
-    {
-        const int total = n * 3;
-        int i = threadIdx.x;
-        for (; i + 7 * (kF1Warps * 32) < total; i += 8 * (kF1Warps * 32)) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(p1 + i + u * (kF1Warps * 32));
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = i + u * (kF1Warps * 32), k = e / 3, c = e - k * 3;
-                (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v[u];
-            }
-        }
-        for (; i < total; i += kF1Warps * 32) {
-            const int k = i / 3, c = i - k * 3;
-            (c == 0 ? sx : (c == 1 ? sy : sz))[k] = __ldg(p1 + i);
-        }
-    }
-    const float inf = __int_as_float(0x7f800000);
-    for (int k = n + threadIdx.x; k < np; k += blockDim.x) { sx[k] = inf; sy[k] = inf; sz[k] = inf; }
+    const BqGrid g = bq_stage_and_build(s, a.xyz + (size_t)cloud * n * 3, n, a.radius, a.want_grid != 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // this lane's weight columns and bias
-    float2 wx[NP], wy[NP], wz[NP], bs[NP], ssum[NP], ssq[NP];
+    const int sub = lane & 7, rsub = lane >> 3;
+    float4 wx[NV], wy[NV], wz[NV], bs[NV], ssum[NV], ssq[NV];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const int c = 2 * lane + 64 * i;
-        wx[i] = make_float2(__ldg(a.w1 + c), __ldg(a.w1 + c + 1));
-        wy[i] = make_float2(__ldg(a.w1 + a.C1 + c), __ldg(a.w1 + a.C1 + c + 1));
-        wz[i] = make_float2(__ldg(a.w1 + 2 * a.C1 + c), __ldg(a.w1 + 2 * a.C1 + c + 1));
-        bs[i] = a.bias ? make_float2(__ldg(a.bias + c), __ldg(a.bias + c + 1)) : make_float2(0.f, 0.f);
-        ssum[i] = make_float2(0.f, 0.f);
-        ssq[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < NV; ++i) {
+        const int c = 32 * i + 4 * sub;
+        wx[i] = __ldg(reinterpret_cast<const float4*>(a.w1 + c));
+        wy[i] = __ldg(reinterpret_cast<const float4*>(a.w1 + a.C1 + c));
+        wz[i] = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * a.C1 + c));
+        bs[i] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ssum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ssq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
     const int q0 = blockIdx.x * a.q_per_cta;
     const int q1 = min(a.m, q0 + a.q_per_cta);
     const float* p2 = a.new_xyz + (size_t)cloud * a.m * 3;
     int* row = srow + warp * a.nsample;
     for (int q = q0 + warp; q < q1; q += kF1Warps) {
         const float qx = __ldg(p2 + q * 3 + 0), qy = __ldg(p2 + q * 3 + 1), qz = __ldg(p2 + q * 3 + 2);
-        const int cnt = ball_query_warp_smem(n, a.nsample, a.thr, a.none != 0, sx, sy, sz, qx, qy, qz, row, lane);
+        const int cnt = bq_query_warp(n, a.nsample, a.thr, a.none != 0, s, g, qx, qy, qz, row, lane, warp);
+        __syncwarp();
         const size_t gq = (size_t)cloud * a.m + q;
         for (int l = lane; l < a.nsample; l += 32) a.idx[gq * a.nsample + l] = row[l];
         if (a.pts_cnt != nullptr && lane == 0) a.pts_cnt[gq] = cnt;
         float* outq = a.pre + gq * a.nsample * a.C1;
-        for (int r = 0; r < a.nsample; ++r) {
-            const int j = row[r];                                  // broadcast
-            const float dx = sx[j] - qx, dy = sy[j] - qy, dz = sz[j] - qz;     // grouped_xyz - new_xyz (pointnet_util.py:46)
-            const float* urow = a.uf ? a.uf + ((size_t)cloud * n + j) * a.C1 : nullptr;
+        for (int r0 = 0; r0 < a.nsample; r0 += 4) {
+            const int r = r0 + rsub;
+            if (r < a.nsample) {
+                const int j = row[r];
+                const float dx = sx[j] - qx, dy = sy[j] - qy, dz = sz[j] - qz;     // grouped_xyz - new_xyz (pointnet_util.py:46)
+                const float* urow = a.uf ? a.uf + ((size_t)cloud * n + j) * a.C1 : nullptr;
+                float* orow = outq + (size_t)r * a.C1;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                float2 u = make_float2(0.f, 0.f);
-                if (urow) u = __ldg(reinterpret_cast<const float2*>(urow + 2 * lane + 64 * i));
-                float2 v;
-                v.x = fmaf(dz, wz[i].x, fmaf(dy, wy[i].x, fmaf(dx, wx[i].x, u.x))) + bs[i].x;
-                v.y = fmaf(dz, wz[i].y, fmaf(dy, wy[i].y, fmaf(dx, wx[i].y, u.y))) + bs[i].y;
-                __stcs(reinterpret_cast<float2*>(outq + (size_t)r * a.C1 + 2 * lane + 64 * i), v);   // streaming store
-                if (STATS) {
-                    ssum[i].x += v.x; ssum[i].y += v.y;
-                    ssq[i].x = fmaf(v.x, v.x, ssq[i].x); ssq[i].y = fmaf(v.y, v.y, ssq[i].y);
+                for (int i = 0; i < NV; ++i) {
+                    const int c = 32 * i + 4 * sub;
+                    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (urow) u = __ldg(reinterpret_cast<const float4*>(urow + c));
+                    float4 v;
+                    v.x = fmaf(dz, wz[i].x, fmaf(dy, wy[i].x, fmaf(dx, wx[i].x, u.x))) + bs[i].x;
+                    v.y = fmaf(dz, wz[i].y, fmaf(dy, wy[i].y, fmaf(dx, wx[i].y, u.y))) + bs[i].y;
+                    v.z = fmaf(dz, wz[i].z, fmaf(dy, wy[i].z, fmaf(dx, wx[i].z, u.z))) + bs[i].z;
+                    v.w = fmaf(dz, wz[i].w, fmaf(dy, wy[i].w, fmaf(dx, wx[i].w, u.w))) + bs[i].w;
+                    __stcs(reinterpret_cast<float4*>(orow + c), v);   // streaming store: written once, never re-read here
+                    if (STATS) {
+                        ssum[i].x += v.x; ssum[i].y += v.y; ssum[i].z += v.z; ssum[i].w += v.w;
+                        ssq[i].x = fmaf(v.x, v.x, ssq[i].x); ssq[i].y = fmaf(v.y, v.y, ssq[i].y);
+                        ssq[i].z = fmaf(v.z, v.z, ssq[i].z); ssq[i].w = fmaf(v.w, v.w, ssq[i].w);
+                    }
                 }
             }
         }
         __syncwarp();
     }
     if (STATS) {
+        // the four row-groups of a warp hold partials of the same channels: fold them, then one row-group publishes
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const int c = 2 * lane + 64 * i;
-            float* w = sstat + (size_t)warp * 2 * a.C1;
-            w[c] = ssum[i].x; w[c + 1] = ssum[i].y;
-            w[a.C1 + c] = ssq[i].x; w[a.C1 + c + 1] = ssq[i].y;
+        for (int i = 0; i < NV; ++i) {
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+                ssum[i].x += __shfl_xor_sync(0xffffffffu, ssum[i].x, o); ssum[i].y += __shfl_xor_sync(0xffffffffu, ssum[i].y, o);
+                ssum[i].z += __shfl_xor_sync(0xffffffffu, ssum[i].z, o); ssum[i].w += __shfl_xor_sync(0xffffffffu, ssum[i].w, o);
+                ssq[i].x += __shfl_xor_sync(0xffffffffu, ssq[i].x, o); ssq[i].y += __shfl_xor_sync(0xffffffffu, ssq[i].y, o);
+                ssq[i].z += __shfl_xor_sync(0xffffffffu, ssq[i].z, o); ssq[i].w += __shfl_xor_sync(0xffffffffu, ssq[i].w, o);
+            }
+            if (rsub == 0) {
+                float* w = sstat + (size_t)warp * 2 * a.C1;
+                const int c = 32 * i + 4 * sub;
+                *reinterpret_cast<float4*>(w + c) = ssum[i];
+                *reinterpret_cast<float4*>(w + a.C1 + c) = ssq[i];
+            }
         }
         __syncthreads();
         float* dst = a.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * a.C1;
         for (int e = threadIdx.x; e < 2 * a.C1; e += blockDim.x) {
-            float s = 0.f;
+            float t = 0.f;
 #pragma unroll
-            for (int w = 0; w < kF1Warps; ++w) s += sstat[(size_t)w * 2 * a.C1 + e];   // fixed order: deterministic
-            dst[e] = s;
+            for (int w = 0; w < kF1Warps; ++w) t += sstat[(size_t)w * 2 * a.C1 + e];   // fixed order: deterministic
+            dst[e] = t;
         }
     }
 }
@@ -228,7 +178,7 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
                                   float* pre, int* idx, int* pts_cnt, float* stats, void* workspace,
                                   size_t workspace_bytes, psa_stream_t stream) {
     PSA_REQUIRE(b >= 0 && n >= 1 && m >= 0 && c >= 0 && nsample >= 1, "sa_conv1_prebn: bad dims b=%d n=%d m=%d c=%d nsample=%d", b, n, m, c, nsample);
-    PSA_REQUIRE(C1 >= 64 && C1 % 64 == 0 && C1 <= 256, "sa_conv1_prebn: C1=%d must be 64, 128, 192 or 256", C1);
+    PSA_REQUIRE(C1 == 64 || C1 == 128, "sa_conv1_prebn: C1=%d must be 64 or 128", C1);
     if (b == 0 || m == 0) return PSA_OK;
     PSA_REQUIRE(xyz && new_xyz && w1 && pre && idx && (points || c == 0), "sa_conv1_prebn: null buffer");
     const size_t need = psa_sa_conv1_prebn_workspace_bytes(b, n, m, c, C1, stats != nullptr);
@@ -239,6 +189,8 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
     bool none = false;
     a.thr = ball_query_threshold(radius, &none);
     a.none = none ? 1 : 0;
+    a.radius = radius;
+    a.want_grid = (bq_grid_fits(n) && n >= 256 && m >= 32) ? 1 : 0;
     a.xyz = xyz; a.new_xyz = new_xyz; a.w1 = w1; a.bias = bias; a.pre = pre; a.idx = idx; a.pts_cnt = pts_cnt;
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     a.uf = nullptr;
@@ -251,20 +203,19 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
     dim3 grid;
     f1_grid(b, m, &a.q_per_cta, &grid);
     a.partial = stats ? reinterpret_cast<float*>(ws) : nullptr;
-    const int np = (n + 127) & ~127;
-    size_t smem = (size_t)np * 3 * sizeof(float) + (size_t)kF1Warps * nsample * sizeof(int) + (stats ? (size_t)kF1Warps * 2 * C1 * sizeof(float) : 0);
+    size_t smem = bq_smem_bytes(n, a.want_grid != 0) + (size_t)kF1Warps * ((nsample + 3) & ~3) * sizeof(int) + (stats ? (size_t)kF1Warps * 2 * C1 * sizeof(float) : 0);
     PSA_SUPPORTED(smem <= 200 * 1024, "sa_conv1_prebn: n=%d exceeds the shared-memory resident limit", n);
 #define PSA_F1_LAUNCH(NP_, ST_)                                                                                              \
     do {                                                                                                                     \
         PSA_CUDA(cudaFuncSetAttribute(sa_conv1_prebn_kernel<NP_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         sa_conv1_prebn_kernel<NP_, ST_><<<grid, kF1Warps * 32, smem, st>>>(a);                                               \
     } while (0)
-    const int NP = C1 / 64;
+    // shared memory: ball-query arrays, per-warp idx rows, per-warp statistics (16-byte aligned: nsample rows of ints)
     if (stats) {
-        if (NP == 1) PSA_F1_LAUNCH(1, true); else if (NP == 2) PSA_F1_LAUNCH(2, true); else if (NP == 3) PSA_F1_LAUNCH(3, true); else PSA_F1_LAUNCH(4, true);
+        if (C1 == 64) PSA_F1_LAUNCH(2, true); else PSA_F1_LAUNCH(4, true);
         f1_stats_reduce_kernel<<<(2 * C1 + 127) / 128, 128, 0, st>>>((int)(grid.x * grid.y), 2 * C1, a.partial, stats);
     } else {
-        if (NP == 1) PSA_F1_LAUNCH(1, false); else if (NP == 2) PSA_F1_LAUNCH(2, false); else if (NP == 3) PSA_F1_LAUNCH(3, false); else PSA_F1_LAUNCH(4, false);
+        if (C1 == 64) PSA_F1_LAUNCH(2, false); else PSA_F1_LAUNCH(4, false);
     }
 #undef PSA_F1_LAUNCH
     return check_launch("sa_conv1_prebn_kernel");
