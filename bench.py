@@ -240,8 +240,7 @@ def main():
         l1_pts, idx1, _ = ops.sa_module_infer(x, l1_xyz, None, 0.2, 32, mlp1, return_idx=True)
         _, l2_xyz = ops.farthest_point_sample_and_gather(128, l1_xyz)
         l2_pts, idx2, _ = ops.sa_module_infer(l1_xyz, l2_xyz, l1_pts, 0.4, 64, mlp2, return_idx=True)
-        l3_in = torch.cat([l2_xyz, l2_pts], dim=2).reshape(B * 128, 259)
-        l3 = ops.shared_mlp(l3_in, mlp3, pool_k=128)
+        l3 = ops.sa_group_all_infer(l2_xyz, l2_pts, mlp3)
         cases = {
             "fps1": lambda: ops.farthest_point_sample_and_gather(512, x),
             "ballq1": lambda: ops.query_ball_point(0.2, 32, x, l1_xyz),
@@ -249,7 +248,7 @@ def main():
             "fps2": lambda: ops.farthest_point_sample_and_gather(128, l1_xyz),
             "ballq2": lambda: ops.query_ball_point(0.4, 64, l1_xyz, l2_xyz),
             "sa2_mlp": lambda: ops.sa_module_infer(l1_xyz, l2_xyz, l1_pts, 0.4, 64, mlp2, idx=idx2),
-            "sa3_mlp": lambda: ops.shared_mlp(l3_in, mlp3, pool_k=128),
+            "sa3_mlp": lambda: ops.sa_group_all_infer(l2_xyz, l2_pts, mlp3),
             "head": lambda: ops.shared_mlp(l3, head),
             # variant F1 (training-mode front of SA1): ball query + group + centre + conv1 -> pre-BN (B,m,K,64) + idx + BN stats
             "sa1_f1": lambda: ops.sa_conv1_prebn(x, l1_xyz, None, 0.2, 32, p["layer1/conv0/weights"].reshape(3, 64),

@@ -194,6 +194,14 @@ PSA_API int psa_sa_module_infer(int b, int n, int m, int c, float radius, int ns
                                 float* out, int* idx_out, int* pts_cnt, void* workspace, size_t workspace_bytes,
                                 psa_stream_t stream);
 
+/* pointnet_sa_module with group_all=True (pointnet_util.py:59-84,113-127): rows [xyz, points] (xyz first) -> MLP -> max over
+ * the n points of each cloud, without building the (b,n,3+c) concatenation.  xyz (b,n,3), points (b,n,c), mlp->channels[0]
+ * == 3 + c -> out (b, C_L).  Returns PSA_ERR_UNSUPPORTED when the first layer cannot run on the tensor-core path (then
+ * concatenate and call psa_shared_mlp with pool_k = n). */
+PSA_API size_t psa_sa_group_all_workspace_bytes(int b, int n, int c, const psa_mlp* mlp);
+PSA_API int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, const float* points, const psa_mlp* mlp,
+                                   float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream);
+
 /* Arithmetic of the grouped MLP.  0 (default): layers after the first run on the tcgen05 tensor cores as a
  * three-term tf32/tf32/bf16 operand split with fp32 accumulation (within 1e-5 of fp64 on O(1) activations) whenever
  * the shapes allow (widths 64/128, last width 64 or a multiple of 128, nsample 32/64/128), fp32 FMA otherwise.
@@ -218,9 +226,12 @@ PSA_API int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int nsa
                                size_t workspace_bytes, psa_stream_t stream);
 
 /* Fused EdgeConv, inference mode (dgcnn/models/dgcnn.py:31-47 pattern): x (b,n,c), nn_idx (b,n,k) ->
- * out (b,n,C_L) = max_j MLP([x_i, x_j - x_i]); mlp->channels[0] must equal 2c. */
+ * out (b,n,C_L) = max_j MLP([x_i, x_j - x_i]); mlp->channels[0] must equal 2c.  A single-layer MLP is evaluated as
+ * (W_a - W_b).x_i + W_b.x_j: one GEMM over the b*n POINTS plus a gather-max pass (k-fold fewer FLOPs than a conv over the
+ * b*n*k edges); deeper MLPs use the fused gather + MLP + max kernel.  workspace: psa_edgeconv_workspace_bytes(). */
+PSA_API size_t psa_edgeconv_workspace_bytes(int b, int n, int c, int k, const psa_mlp* mlp);
 PSA_API int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
-                       float* out, psa_stream_t stream);
+                               float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream);
 
 #ifdef __cplusplus
 }

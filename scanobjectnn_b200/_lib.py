@@ -52,13 +52,14 @@ SIGNATURES = {
     "psa_shared_mlp": [C.c_longlong, _i, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
     "psa_sa_module_infer": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, C.POINTER(PsaMlp), _p, _p, _p, _p, C.c_size_t, _p],
     "psa_sa_conv1_prebn": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, C.c_size_t, _p],
+    "psa_sa_group_all_infer": [_i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
     "psa_set_mlp_mode": [_i],
     "psa_get_mlp_mode": [],
     "psa_tc_selftest": [_i, _i, _p, _p, _p, _p, _p],
-    "psa_edgeconv_infer": [_i, _i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p],
+    "psa_edgeconv_infer": [_i, _i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
 }
 INFO_SYMBOLS = ("psa_version", "psa_last_error", "psa_sm_arch", "psa_shared_mlp_workspace_bytes",
-                "psa_sa_module_workspace_bytes", "psa_sa_conv1_prebn_workspace_bytes")
+                "psa_sa_module_workspace_bytes", "psa_sa_conv1_prebn_workspace_bytes", "psa_sa_group_all_workspace_bytes", "psa_edgeconv_workspace_bytes")
 
 _lib = None
 
@@ -81,6 +82,10 @@ def load() -> C.CDLL:
     lib.psa_shared_mlp_workspace_bytes.restype = C.c_size_t
     lib.psa_sa_module_workspace_bytes.argtypes = [_i, _i, _i, _i, _i, C.POINTER(PsaMlp)]
     lib.psa_sa_module_workspace_bytes.restype = C.c_size_t
+    lib.psa_edgeconv_workspace_bytes.argtypes = [_i, _i, _i, _i, C.POINTER(PsaMlp)]
+    lib.psa_edgeconv_workspace_bytes.restype = C.c_size_t
+    lib.psa_sa_group_all_workspace_bytes.argtypes = [_i, _i, _i, C.POINTER(PsaMlp)]
+    lib.psa_sa_group_all_workspace_bytes.restype = C.c_size_t
     lib.psa_sa_conv1_prebn_workspace_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.psa_sa_conv1_prebn_workspace_bytes.restype = C.c_size_t
     lib.psa_version.restype = C.c_int

@@ -101,54 +101,124 @@ knn_topk_kernel(long long rows, int ncols, int k, const float* __restrict__ adj,
     }
 }
 
-// Fused kNN graph, first version: CTA = 8 queries of one cloud (one per warp); candidate points are staged through
-// shared memory 32 at a time; each lane owns one candidate per tile and forms the fma-chain dot product with its
-// warp's query (query row broadcast from shared memory); the adj row accumulates in the warp's shared row buffer.
-constexpr int kKgWarps = 8;
+// Fused kNN graph: CTA = 64 queries of one cloud against all candidates, 64 at a time.
+//   distances  4x4 register tiles over shared-memory channel chunks, dot / |x|^2 as fma chains over c ascending (the
+//              canonical order of oracle/psa_oracle.c:orc_dgcnn_knn), adj = (sq_i + (-2 dot)) + sq_j -> a 64x64 tile in
+//              shared memory: the (B,N,N) matrix never exists, HBM sees B*(4NC + 4Nk) bytes;
+//   selection  each warp owns 8 query rows; a row's current k best sit sorted in one register per lane; a candidate
+//              enters only if it beats the k-th (strict '<': candidates arrive in index order, so equal values keep the
+//              lower index first, like tf.nn.top_k), found by ballot, placed by popc(ballot(list <= cand)) and a
+//              shuffle-up shift.  Expected insertions per row ~ k(1+ln(N/k)).
+constexpr int kKgQ = 64, kKgC = 64, kKgCk = 32;
 
-__global__ void __launch_bounds__(kKgWarps * 32)
+__global__ void __launch_bounds__(256)
 knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restrict__ nn_idx) {
     extern __shared__ float smem_f[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cloud = blockIdx.y;
-    const int q0 = blockIdx.x * kKgWarps;
-    const int cp = c + 1;
-    float* rows = smem_f;                               // kKgWarps * n
-    float* qv = rows + (size_t)kKgWarps * n;             // kKgWarps * c
-    float* tile = qv + (size_t)kKgWarps * c;             // 32 * (c+1)
-    float* tsq = tile + 32 * cp;                         // 32
+    const int cpad = c + 1;
+    float* Xq = smem_f;                                  // [64][c+1]  query features (all channels)
+    float* Xj = Xq + kKgQ * cpad;                        // [64][33]   candidate chunk
+    float* D = Xj + kKgC * (kKgCk + 1);                  // [64][65]   adj tile
+    float* Lv = D + kKgQ * (kKgC + 1);                   // [64][32]   sorted best values
+    int* Li = reinterpret_cast<int*>(Lv + kKgQ * 32);    // [64][32]   and their indices
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int cloud = blockIdx.y, q0 = blockIdx.x * kKgQ;
     const float* xb = x + (size_t)cloud * n * c;
-    const int q = q0 + warp;
-    const bool active = q < n;
-    float sq_q = 0.f;
-    if (active) {
-        for (int l = lane; l < c; l += 32) qv[warp * c + l] = __ldg(xb + (size_t)q * c + l);
-        __syncwarp();
-        for (int l = 0; l < c; ++l) sq_q = __fmaf_rn(qv[warp * c + l], qv[warp * c + l], sq_q);
+    const float inf = __int_as_float(0x7f800000);
+    for (int sidx = tid; sidx < kKgQ * c; sidx += 256) {
+        const int r = sidx / c, l = sidx - r * c;
+        Xq[r * cpad + l] = (q0 + r < n) ? __ldg(xb + (size_t)(q0 + r) * c + l) : 0.f;
     }
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        __syncthreads();
-        for (int s = threadIdx.x; s < 32 * c; s += kKgWarps * 32) {
-            int r = s / c, l = s - r * c;
-            tile[r * cp + l] = (j0 + r < n) ? __ldg(xb + (size_t)(j0 + r) * c + l) : 0.f;
+    for (int sidx = tid; sidx < kKgQ * 32; sidx += 256) { Lv[sidx] = inf; Li[sidx] = 0; }
+    __syncthreads();
+    float sqi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        float sq = 0.f;
+        const float* q = Xq + (ty + 16 * a) * cpad;
+        for (int l = 0; l < c; ++l) sq = __fmaf_rn(q[l], q[l], sq);
+        sqi[a] = sq;
+    }
+    for (int j0 = 0; j0 < n; j0 += kKgC) {
+        float dot[4][4], sqj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            sqj[a] = 0.f;
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) dot[a][b2] = 0.f;
         }
-        __syncthreads();
-        if (warp == 0) {
-            float s = 0.f;
-            for (int l = 0; l < c; ++l) s = __fmaf_rn(tile[lane * cp + l], tile[lane * cp + l], s);
-            tsq[lane] = s;
+        for (int c0 = 0; c0 < c; c0 += kKgCk) {
+            const int cc = min(kKgCk, c - c0);
+            __syncthreads();
+            for (int s0 = tid; s0 < kKgC * kKgCk; s0 += 256 * 4) {        // 4 independent loads in flight per thread
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int sidx = s0 + u * 256, r = sidx / kKgCk, l = sidx - r * kKgCk;
+                    v[u] = (sidx < kKgC * kKgCk && j0 + r < n && l < cc) ? __ldg(xb + (size_t)(j0 + r) * c + c0 + l) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int sidx = s0 + u * 256, r = sidx / kKgCk, l = sidx - r * kKgCk;
+                    if (sidx < kKgC * kKgCk) Xj[r * (kKgCk + 1) + l] = v[u];
+                }
+            }
+            __syncthreads();
+            for (int l = 0; l < cc; ++l) {
+                float ai[4], bj[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { ai[a] = Xq[(ty + 16 * a) * cpad + c0 + l]; bj[a] = Xj[(tx + 16 * a) * (kKgCk + 1) + l]; }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    sqj[a] = __fmaf_rn(bj[a], bj[a], sqj[a]);
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) dot[a][b2] = __fmaf_rn(ai[a], bj[b2], dot[a][b2]);
+                }
+            }
         }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2)
+                D[(ty + 16 * a) * (kKgC + 1) + tx + 16 * b2] = __fadd_rn(__fadd_rn(sqi[a], __fmul_rn(-2.0f, dot[a][b2])), sqj[b2]);
         __syncthreads();
-        if (active && j0 + lane < n) {
-            float dot = 0.f;
-            const float* tj = tile + lane * cp;
-            const float* qq = qv + warp * c;
-            for (int l = 0; l < c; ++l) dot = __fmaf_rn(qq[l], tj[l], dot);
-            rows[(size_t)warp * n + j0 + lane] = __fadd_rn(__fadd_rn(sq_q, __fmul_rn(-2.0f, dot)), tsq[lane]);
+        // ---- selection: warp w owns query rows 8w..8w+7 ----
+        for (int i = 0; i < 8; ++i) {
+            const int r = warp * 8 + i;
+            if (q0 + r >= n) break;                                        // warp-uniform
+            float lv = Lv[r * 32 + lane];
+            int li = Li[r * 32 + lane];
+            float thr = __shfl_sync(0xffffffffu, lv, k - 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int cj = half * 32 + lane;
+                const float cv = D[r * (kKgC + 1) + cj];
+                const int ci = j0 + cj;
+                unsigned mask = __ballot_sync(0xffffffffu, ci < n && cv < thr);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float bv = __shfl_sync(0xffffffffu, cv, src);
+                    const int bi = __shfl_sync(0xffffffffu, ci, src);
+                    if (!(bv < thr)) continue;                             // the k-th best tightened meanwhile
+                    const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && lv <= bv));
+                    const float pv = __shfl_up_sync(0xffffffffu, lv, 1);
+                    const int pi = __shfl_up_sync(0xffffffffu, li, 1);
+                    if (lane > pos) { lv = pv; li = pi; }
+                    else if (lane == pos) { lv = bv; li = bi; }
+                    if (lane >= k) lv = inf;
+                    thr = __shfl_sync(0xffffffffu, lv, k - 1);
+                }
+            }
+            Lv[r * 32 + lane] = lv;
+            Li[r * 32 + lane] = li;
         }
     }
-    __syncwarp();
-    if (active) topk_rounds(rows + (size_t)warp * n, n, k, nn_idx + ((size_t)cloud * n + q) * k, lane);
+    __syncthreads();
+    for (int sidx = tid; sidx < kKgQ * k; sidx += 256) {
+        const int r = sidx / k, l = sidx - r * k;
+        if (q0 + r < n) nn_idx[((size_t)cloud * n + q0 + r) * k + l] = Li[r * 32 + l];
+    }
 }
 
 // edge[b,i,j,:] = [x_i, x_{nn(i,j)} - x_i]
@@ -211,11 +281,12 @@ extern "C" int psa_knn_graph(int b, int n, int c, int k, const float* x, int* nn
     if (b == 0 || n == 0 || k == 0) return PSA_OK;
     PSA_REQUIRE((x || c == 0) && nn_idx, "knn_graph: null buffer");
     PSA_SUPPORTED(b <= 65535, "knn_graph: b=%d exceeds gridDim.y", b);
-    size_t smem = ((size_t)kKgWarps * n + (size_t)kKgWarps * c + 32 * (size_t)(c + 1) + 32) * sizeof(float);
-    PSA_SUPPORTED(smem <= 200 * 1024, "knn_graph: n=%d, c=%d exceed the shared-memory resident limit", n, c);
+    PSA_SUPPORTED(k <= 32, "knn_graph: k=%d exceeds the 32 entries a warp keeps per query", k);
+    size_t smem = ((size_t)kKgQ * (c + 1) + (size_t)kKgC * (kKgCk + 1) + (size_t)kKgQ * (kKgC + 1) + 2 * (size_t)kKgQ * 32) * sizeof(float);
+    PSA_SUPPORTED(smem <= 200 * 1024, "knn_graph: c=%d exceeds the shared-memory resident limit", c);
     PSA_CUDA(cudaFuncSetAttribute(knn_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((n + kKgWarps - 1) / kKgWarps, b);
-    knn_graph_kernel<<<grid, kKgWarps * 32, smem, as_stream(stream)>>>(n, c, k, x, nn_idx);
+    dim3 grid((n + kKgQ - 1) / kKgQ, b);
+    knn_graph_kernel<<<grid, 256, smem, as_stream(stream)>>>(n, c, k, x, nn_idx);
     return check_launch("knn_graph_kernel");
 }
 

@@ -671,17 +671,20 @@ int sa_module_simt(int b, int n, int m, int c, int nsample, const float* xyz, co
 int validate_mlp_public(const psa_mlp* mlp, const char* who) { return validate_mlp(mlp, who); }
 }  // namespace psa
 
-extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
-                                  float* out, psa_stream_t stream) {
-    int rc = validate_mlp(mlp, "edgeconv");
-    if (rc != PSA_OK) return rc;
-    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 1 && k >= 1, "edgeconv: bad dims b=%d n=%d c=%d k=%d", b, n, c, k);
-    PSA_REQUIRE(mlp->channels[0] == 2 * c, "edgeconv: mlp input width %d != 2*c (%d)", mlp->channels[0], 2 * c);
-    if (b == 0 || n == 0) return PSA_OK;
-    PSA_REQUIRE(x && nn_idx && out, "edgeconv: null buffer");
+namespace psa {
+int edgeconv_simt(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp, float* out, cudaStream_t st) {
     FusedArgs a;
     a.mlp = *mlp;
     a.groups = (long long)b * n; a.K = k; a.n = n; a.m = n; a.c = c;
     a.xyz = nullptr; a.new_xyz = nullptr; a.feat = x; a.idx = nn_idx; a.out = out;
-    return launch_fused<kGatherEdge>(a, as_stream(stream), "edgeconv");
+    return launch_fused<kGatherEdge>(a, st, "edgeconv");
 }
+int launch_fill_ord_neg_inf(long long total, float* out, cudaStream_t st) {
+    fill_ord_neg_inf_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, reinterpret_cast<int*>(out));
+    return check_launch("fill_ord_neg_inf_kernel");
+}
+int launch_decode_ord(long long total, float* out, cudaStream_t st) {
+    decode_ord_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, reinterpret_cast<int*>(out));
+    return check_launch("decode_ord_kernel");
+}
+}  // namespace psa

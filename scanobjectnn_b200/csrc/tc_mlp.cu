@@ -461,6 +461,8 @@ struct TcDenseArgs {
     const uint8_t* image;  // weight image for (Kp, N)
     const float* scale;    // (N) or null
     const float* shift;    // (N) or null
+    const float* xyz3;     // optional side input (rows, 3): out += xyz3 . w3 before scale/shift (the xyz rows of a
+    const float* w3;       // (3, N)                          [xyz, features] . W product, kept off the K loop)
     float* out;
 };
 
@@ -559,10 +561,16 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
     const int col0 = nt * Nt + cs * 32;
     float v[32];
     if (has_out_chunk) {
+        float sx3 = 0.f, sy3 = 0.f, sz3 = 0.f;
+        if (a.xyz3 != nullptr && valid) {
+            sx3 = __ldg(a.xyz3 + (size_t)grow * 3); sy3 = __ldg(a.xyz3 + (size_t)grow * 3 + 1); sz3 = __ldg(a.xyz3 + (size_t)grow * 3 + 2);
+        }
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             const float sc = a.scale ? __ldg(a.scale + col0 + q) : 1.f;
             const float sh = a.shift ? __ldg(a.shift + col0 + q) : 0.f;
+            if (a.xyz3 != nullptr)
+                acc[q] = fmaf(sz3, __ldg(a.w3 + 2 * a.N + col0 + q), fmaf(sy3, __ldg(a.w3 + a.N + col0 + q), fmaf(sx3, __ldg(a.w3 + col0 + q), acc[q])));
             float x = fmaf(acc[q], sc, sh);
             if (a.relu) x = fmaxf(x, 0.f);
             v[q] = x;
@@ -575,7 +583,8 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
             for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
     } else {
-        const int quarters_per_group = a.pool_k / 32;
+        const bool big = a.pool_k > 128;                         // the whole 128-row tile lies inside one group
+        const int quarters_per_group = big ? 4 : a.pool_k / 32;
         const long long wg = (row0 + quarter * 32) / a.pool_k;
         float mx = -FLT_MAX;
         if (has_out_chunk) {
@@ -589,8 +598,16 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
             if ((quarter % quarters_per_group) == 0)
                 for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
         }
-        if (has_out_chunk && (quarter % quarters_per_group) == 0 && row0 + quarter * 32 < a.rows)
-            a.out[(size_t)wg * a.N + col0 + lane] = mx;
+        if (has_out_chunk && (quarter % quarters_per_group) == 0 && row0 + quarter * 32 < a.rows) {
+            if (!big) {
+                a.out[(size_t)wg * a.N + col0 + lane] = mx;
+            } else {
+                // out was pre-filled with the order-preserving int code of -inf; decoded after the kernel
+                int code = __float_as_int(mx);
+                code = code >= 0 ? code : code ^ 0x7fffffff;
+                atomicMax(reinterpret_cast<int*>(a.out) + (size_t)wg * a.N + col0 + lane, code);
+            }
+        }
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
@@ -599,7 +616,7 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
 bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
     if (rows < 128 || K < 32 || N < 64 || (N % 64) != 0) return false;
     if (N > 64 && (N % 128) != 0) return false;
-    if (!(pool_k == 1 || pool_k == 32 || pool_k == 64 || pool_k == 128)) return false;
+    if (!(pool_k == 1 || pool_k == 32 || pool_k == 64 || (pool_k >= 128 && pool_k % 128 == 0))) return false;
     if (pool_k > 1 && rows % pool_k != 0) return false;
     return true;
 }
@@ -608,15 +625,17 @@ size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~6
 static int g_tc_dense_narrow = 1;
 
 int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
-                    const float* shift, float* out, uint8_t* image, cudaStream_t st) {
+                    const float* shift, float* out, uint8_t* image, cudaStream_t st, const float* xyz3 = nullptr,
+                    const float* w3 = nullptr) {
     const int Kp = (K + 63) & ~63;
     const bool narrow = g_tc_dense_narrow != 0;
     const int Nt = tc_nt(N, narrow ? 64 : 128);
     tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, image);
     TcDenseArgs a;
     a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
-    a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out;
+    a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out; a.xyz3 = xyz3; a.w3 = w3;
     dim3 grid((unsigned)((rows + 127) / 128), N / Nt);
+    if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
     if (narrow) {
         // two slots of one block; two CTAs (256 TMEM columns each) per SM
         const size_t smem = 2 * (size_t)tc_block_bytes(Nt) + 1024;
@@ -629,6 +648,7 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
         PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_dense_kernel<false><<<grid, TcCfg<false>::kThreads, smem, st>>>(a);
     }
+    if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
     return check_launch("tc_dense_kernel");
 }
 
@@ -669,7 +689,7 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
 size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
     size_t bytes = 0;
     for (int l = 0; l < a.nl; ++l) bytes += (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255;
-    if (c > 0) bytes += (size_t)b * n * a.C1 * sizeof(float);
+    if (c > 0) bytes += (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255) + tc_dense_image_bytes(c, a.C1);
     return bytes;
 }
 
@@ -766,13 +786,19 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         if (rc != PSA_OK) return rc;
         if (c > 0) {
             // U = points . W1[3:,:]  once per source point (rows b*n), raw (affine + ReLU are applied after the xyz part)
-            DenseArgs d;
-            d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
-            d.x = points; d.W = mlp->weight[0] + (size_t)3 * a.C1; d.scale = nullptr; d.shift = nullptr;
-            d.out = reinterpret_cast<float*>(ws);
-            rc = launch_dense(d, st);
+            float* uf = reinterpret_cast<float*>(ws);
+            uint8_t* uimg = ws + (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255);
+            const float* w1f = mlp->weight[0] + (size_t)3 * a.C1;
+            if (tc_dense_eligible((long long)b * n, c, a.C1, 1)) {
+                rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, uf, uimg, st);
+            } else {
+                DenseArgs d;
+                d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
+                d.x = points; d.W = w1f; d.scale = nullptr; d.shift = nullptr; d.out = uf;
+                rc = launch_dense(d, st);
+            }
             if (rc != PSA_OK) return rc;
-            a.uf = d.out;
+            a.uf = uf;
         }
         return launch_tc_sa(a, st);
     }
@@ -838,4 +864,162 @@ extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const 
         cur = dst;
     }
     return PSA_OK;
+}
+
+// pointnet_sa_module(group_all=True) (pointnet_util.py:59-84,113-127): rows = [xyz, points] (xyz first), MLP, max over the
+// n points of each cloud -- without building the (b,n,3+c) concatenation: the feature part [3:,:] of the first layer runs
+// as an aligned K = c GEMM on the tensor cores, the three xyz rows of W1 are folded into its epilogue.
+extern "C" size_t psa_sa_group_all_workspace_bytes(int b, int n, int c, const psa_mlp* mlp) {
+    if (mlp == nullptr || mlp->n_layers < 1) return 0;
+    psa_mlp m2 = *mlp;
+    m2.channels[0] = c;
+    return psa_shared_mlp_workspace_bytes((long long)b * n, &m2);
+}
+
+extern "C" int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, const float* points, const psa_mlp* mlp,
+                                      float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    int rc = validate_mlp_public(mlp, "sa_group_all");
+    if (rc != PSA_OK) return rc;
+    PSA_REQUIRE(b >= 0 && n >= 1 && c >= 1, "sa_group_all: bad dims b=%d n=%d c=%d", b, n, c);
+    PSA_REQUIRE(mlp->channels[0] == 3 + c, "sa_group_all: mlp input width %d != 3 + c (%d)", mlp->channels[0], 3 + c);
+    if (b == 0) return PSA_OK;
+    PSA_REQUIRE(xyz && points && out, "sa_group_all: null buffer");
+    const long long rows = (long long)b * n;
+    const int L = mlp->n_layers;
+    const int N0 = mlp->channels[1];
+    const int pk0 = (L == 1) ? n : 1;
+    PSA_SUPPORTED(g_mlp_mode == 0 && tc_dense_eligible(rows, c, N0, pk0),
+                  "sa_group_all: first layer (%d -> %d over %lld rows) is not eligible for the tensor-core path; concatenate and use shared_mlp", c, N0, rows);
+    const size_t need = psa_sa_group_all_workspace_bytes(b, n, c, mlp);
+    PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, "sa_group_all: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+    PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sa_group_all: workspace must be 256-byte aligned");
+    int cmax = 0;
+    for (int l = 1; l < L; ++l) cmax = cmax > mlp->channels[l] ? cmax : mlp->channels[l];
+    const size_t half = L > 1 ? (((size_t)rows * cmax * sizeof(float) + 255) & ~(size_t)255) : 0;
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+    float* ws0 = reinterpret_cast<float*>(wsb);
+    float* ws1 = reinterpret_cast<float*>(wsb + half);
+    uint8_t* img = wsb + 2 * half;
+    cudaStream_t st = as_stream(stream);
+    const float* cur = points;
+    for (int l = 0; l < L; ++l) {
+        const int K = (l == 0) ? c : mlp->channels[l], N = mlp->channels[l + 1];
+        const int pk = (l == L - 1) ? n : 1;
+        float* dst = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
+        const float* W = (l == 0) ? mlp->weight[0] + (size_t)3 * N : mlp->weight[l];
+        if (tc_dense_eligible(rows, K, N, pk)) {
+            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, W, mlp->scale[l], mlp->shift[l], dst, img, st,
+                                 l == 0 ? xyz : nullptr, l == 0 ? mlp->weight[0] : nullptr);
+        } else {
+            PSA_SUPPORTED(l > 0, "sa_group_all: layer 0 must run on the tensor-core path");
+            DenseArgs d;
+            d.rows = rows; d.K = K; d.N = N; d.pool_k = pk; d.relu = mlp->relu[l];
+            d.x = cur; d.W = W; d.scale = mlp->scale[l]; d.shift = mlp->shift[l]; d.out = dst;
+            rc = launch_dense(d, st);
+        }
+        if (rc != PSA_OK) return rc;
+        img += tc_dense_image_bytes(K, N < 64 ? 64 : N);
+        cur = dst;
+    }
+    return PSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// EdgeConv, single layer (dgcnn/models/dgcnn.py:41-47 etc.):  max_j relu(BN(W . [x_i ; x_j - x_i] + b)).
+//   W . [x_i ; x_j - x_i] = (W_a - W_b) . x_i + W_b . x_j   and, per channel, relu(s*(A_i + B_j) + t) is monotone in B_j
+//   (increasing if s >= 0, decreasing otherwise), so the max over the k edges only needs max_j / min_j of B:
+//   one (B*N) x C x 2C_out GEMM over POINTS (k-fold fewer rows than the reference's conv over B*N*k edges, tensor cores)
+//   + one gather-max pass.  No (B,N,k,2C) edge tensor, no (B,N,k,C_out) activation tensor.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void edge_wc_kernel(int c, int N, const float* __restrict__ W, float* __restrict__ Wc) {
+    const int total = c * 2 * N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int kk = e / (2 * N), j = e - kk * 2 * N;
+        Wc[e] = j < N ? __ldg(W + (size_t)kk * N + j) - __ldg(W + (size_t)(c + kk) * N + j) : __ldg(W + (size_t)(c + kk) * N + j - N);
+    }
+}
+
+template <int VEC>   // channels per lane: N = 32 * VEC
+__global__ void __launch_bounds__(256)
+edge_gather_max_kernel(long long points, int n, int k, int N, const float* __restrict__ AB, const int* __restrict__ nn_idx,
+                       const float* __restrict__ scale, const float* __restrict__ shift, int relu, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        sc[v] = scale ? __ldg(scale + lane * VEC + v) : 1.f;
+        sh[v] = shift ? __ldg(shift + lane * VEC + v) : 0.f;
+    }
+    for (long long p = warp0; p < points; p += (long long)gridDim.x * 8) {
+        const long long base = (p / n) * n;
+        const float* arow = AB + (size_t)p * 2 * N + lane * VEC;
+        float a[VEC], mx[VEC], mn[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { a[v] = __ldg(arow + v); mx[v] = -FLT_MAX; mn[v] = FLT_MAX; }
+        const int myj = lane < k ? __ldg(nn_idx + p * k + lane) : 0;          // k <= 32
+        for (int j = 0; j < k; ++j) {
+            const int nb = __shfl_sync(0xffffffffu, myj, j);
+            const float* brow = AB + (size_t)(base + nb) * 2 * N + N + lane * VEC;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { const float bv = __ldg(brow + v); mx[v] = fmaxf(mx[v], bv); mn[v] = fminf(mn[v], bv); }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float y = fmaf(a[v] + (sc[v] >= 0.f ? mx[v] : mn[v]), sc[v], sh[v]);
+            if (relu) y = fmaxf(y, 0.f);
+            out[(size_t)p * N + lane * VEC + v] = y;
+        }
+    }
+}
+
+static bool edgeconv_algebra_ok(long long rows, int c, int k, const psa_mlp* mlp) {
+    const int N = mlp->channels[1];
+    return g_mlp_mode == 0 && mlp->n_layers == 1 && rows >= 128 && k <= 32 && (N == 32 || N == 64 || N == 128 || N == 256) && c >= 1;
+}
+
+extern "C" size_t psa_edgeconv_workspace_bytes(int b, int n, int c, int k, const psa_mlp* mlp) {
+    if (mlp == nullptr) return 0;
+    const long long rows = (long long)b * n;
+    if (!edgeconv_algebra_ok(rows, c, k, mlp)) return 0;
+    const int N = mlp->channels[1];
+    return (((size_t)c * 2 * N * 4 + 255) & ~(size_t)255) + (((size_t)rows * 2 * N * 4 + 255) & ~(size_t)255) + tc_dense_image_bytes(c, 2 * N);
+}
+
+extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
+                                  float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    int rc = validate_mlp_public(mlp, "edgeconv");
+    if (rc != PSA_OK) return rc;
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 1 && k >= 1, "edgeconv: bad dims b=%d n=%d c=%d k=%d", b, n, c, k);
+    PSA_REQUIRE(mlp->channels[0] == 2 * c, "edgeconv: mlp input width %d != 2*c (%d)", mlp->channels[0], 2 * c);
+    if (b == 0 || n == 0) return PSA_OK;
+    PSA_REQUIRE(x && nn_idx && out, "edgeconv: null buffer");
+    cudaStream_t st = as_stream(stream);
+    const long long rows = (long long)b * n;
+    if (!edgeconv_algebra_ok(rows, c, k, mlp)) return edgeconv_simt(b, n, c, k, x, nn_idx, mlp, out, st);
+    const int N = mlp->channels[1];
+    const size_t need = psa_edgeconv_workspace_bytes(b, n, c, k, mlp);
+    PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, "edgeconv: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+    PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "edgeconv: workspace must be 256-byte aligned");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    float* Wc = reinterpret_cast<float*>(ws);
+    ws += ((size_t)c * 2 * N * 4 + 255) & ~(size_t)255;
+    float* AB = reinterpret_cast<float*>(ws);
+    ws += ((size_t)rows * 2 * N * 4 + 255) & ~(size_t)255;
+    edge_wc_kernel<<<(c * 2 * N + 255) / 256, 256, 0, st>>>(c, N, mlp->weight[0], Wc);
+    if (tc_dense_eligible(rows, c, 2 * N, 1)) {
+        rc = launch_tc_dense(rows, c, 2 * N, 1, 0, x, Wc, nullptr, nullptr, AB, ws, st);
+    } else {
+        DenseArgs d;
+        d.rows = rows; d.K = c; d.N = 2 * N; d.pool_k = 1; d.relu = 0;
+        d.x = x; d.W = Wc; d.scale = nullptr; d.shift = nullptr; d.out = AB;
+        rc = launch_dense(d, st);
+    }
+    if (rc != PSA_OK) return rc;
+    const int grid = (int)((rows + 7) / 8 < (long long)kNumSMs * 8 ? (rows + 7) / 8 : (long long)kNumSMs * 8);
+    const int vec = N / 32;
+#define PSA_EDGE_LAUNCH(V) edge_gather_max_kernel<V><<<grid, 256, 0, st>>>(rows, n, k, N, AB, nn_idx, mlp->scale[0], mlp->shift[0], mlp->relu[0], out)
+    if (vec == 1) PSA_EDGE_LAUNCH(1); else if (vec == 2) PSA_EDGE_LAUNCH(2); else if (vec == 4) PSA_EDGE_LAUNCH(4); else PSA_EDGE_LAUNCH(8);
+#undef PSA_EDGE_LAUNCH
+    return check_launch("edge_gather_max_kernel");
 }

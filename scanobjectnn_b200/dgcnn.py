@@ -68,16 +68,16 @@ def _backbone(point_cloud, params, end_points, k=K_NEIGHBORS):
         nets.append(y)
         x = y
     cat = torch.cat(nets, dim=-1)                                             # (B,N,320)
-    agg = ops.shared_mlp(cat.reshape(b * n, 320), params.mlp(["agg"]))        # (B*N,1024)
-    return nets, agg.reshape(b, n, 1024)
+    # agg conv (320 -> 1024) with the max over the N points folded into its epilogue: the (B,N,1024) tensor is never written
+    glob = ops.shared_mlp(cat.reshape(b * n, 320), params.mlp(["agg"]), pool_k=n)        # (B,1024)
+    return nets, glob
 
 
 def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
     """dgcnn.get_model (dgcnn.py:24-102): (B,N,3) -> (logits (B,num_class), end_points)."""
     _require_inference(is_training)
     end_points = {}
-    _, agg = _backbone(point_cloud, params, end_points)
-    net = agg.max(dim=1).values                                               # tf.reduce_max over N
+    _, net = _backbone(point_cloud, params, end_points)                      # tf.reduce_max over N already applied
     end_points["global"] = net
     net = ops.shared_mlp(net, params.mlp(["fc1", "fc2", "fc3"], [True, True, False]))
     return net, end_points
@@ -88,8 +88,7 @@ def get_model_bga(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES
     _require_inference(is_training)
     end_points = {}
     b, n, _ = point_cloud.shape
-    nets, agg = _backbone(point_cloud, params, end_points)
-    out_max = agg.max(dim=1).values                                           # (B,1024)
+    nets, out_max = _backbone(point_cloud, params, end_points)               # (B,1024)
     net = ops.shared_mlp(out_max, params.mlp(["fc1", "fc2"], [True, True]))   # class vector (B,256)
     class_pred = ops.shared_mlp(net, params.mlp(["fc3"], [False]))
     concat = torch.cat([net.unsqueeze(1).expand(b, n, 256), out_max.unsqueeze(1).expand(b, n, 1024), *nets], dim=-1)

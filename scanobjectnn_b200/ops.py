@@ -19,7 +19,7 @@ __all__ = [
     "farthest_point_sample", "gather_point", "query_ball_point", "group_point", "select_top_k", "knn_point",
     "three_nn", "three_interpolate", "three_nn_interpolate", "pairwise_distance", "knn", "knn_graph",
     "get_edge_feature", "farthest_point_sample_and_gather", "MlpParams", "shared_mlp", "sa_module_infer",
-    "edgeconv_infer", "sa_conv1_prebn", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
+    "edgeconv_infer", "sa_conv1_prebn", "sa_group_all_infer", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
 ]
 
 
@@ -414,6 +414,25 @@ def sa_module_infer(xyz, new_xyz, points, radius: float, nsample: int, mlp: MlpP
     return out
 
 
+def sa_group_all_infer(xyz, points, mlp: MlpParams) -> torch.Tensor:
+    """pointnet_sa_module(group_all=True) fused: rows [xyz, points] -> MLP -> max over each cloud's points, no concat.
+    xyz (B,N,3), points (B,N,C) -> (B, C_L).  Falls back to concat + shared_mlp when the shapes are not eligible."""
+    xyz = _dev(xyz, torch.float32, "xyz", 3)
+    points = _dev(points, torch.float32, "points", 3)
+    b, n, _ = xyz.shape
+    c = points.shape[2]
+    lib = _lib.load()
+    out = torch.empty((b, mlp.channels[-1]), dtype=torch.float32, device=xyz.device)
+    need = lib.psa_sa_group_all_workspace_bytes(b, n, c, mlp.ref)
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=xyz.device) if need else None
+    rc = lib.psa_sa_group_all_infer(b, n, c, _ptr(xyz), _ptr(points), mlp.ref, _ptr(out), _ptr(ws), C.c_size_t(need), _stream())
+    if rc == -2:        # PSA_ERR_UNSUPPORTED: shapes outside the fused path
+        rows = torch.cat([xyz, points], dim=2).reshape(b * n, 3 + c)
+        return shared_mlp(rows, mlp, pool_k=n)
+    check(rc, "sa_group_all_infer")
+    return out
+
+
 def sa_conv1_prebn(xyz, new_xyz, points, radius: float, nsample: int, w1, bias=None, want_stats: bool = True):
     """Training-mode front of a set-abstraction level (variant F1): ball query + group + centre + conv1 + bias in one
     launch.  -> pre (B,M,nsample,C1) PRE-batch-norm activations, idx (B,M,nsample), pts_cnt (B,M), stats (2,C1) =
@@ -453,7 +472,11 @@ def edgeconv_infer(x, nn_idx, mlp: MlpParams) -> torch.Tensor:
     b, n, c = x.shape
     k = nn_idx.shape[2]
     out = torch.empty((b, n, mlp.channels[-1]), dtype=torch.float32, device=x.device)
-    check(_lib.load().psa_edgeconv_infer(b, n, c, k, _ptr(x), _ptr(nn_idx), mlp.ref, _ptr(out), _stream()), "edgeconv_infer")
+    lib = _lib.load()
+    need = lib.psa_edgeconv_workspace_bytes(b, n, c, k, mlp.ref)
+    ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device) if need else None
+    check(lib.psa_edgeconv_infer(b, n, c, k, _ptr(x), _ptr(nn_idx), mlp.ref, _ptr(out), _ptr(ws), C.c_size_t(need), _stream()),
+          "edgeconv_infer")
     return out
 
 

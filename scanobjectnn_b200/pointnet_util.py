@@ -72,10 +72,16 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     scopes = _mlp_scopes(scope, mlp)
     if group_all:
         nsample = xyz.shape[1]
-        new_xyz, new_points, idx, _ = sample_and_group_all(xyz, points, use_xyz)
         b = xyz.shape[0]
-        rows = new_points.reshape(b * nsample, new_points.shape[-1])
-        pooled = ops.shared_mlp(rows, params.mlp(scopes), pool_k=nsample).reshape(b, 1, -1)
+        if points is not None and use_xyz:
+            # sample_and_group_all without the concat: new_xyz = 0, idx = arange, rows = [xyz, points]
+            new_xyz = torch.zeros((b, 1, 3), dtype=torch.float32, device=xyz.device)
+            idx = torch.arange(nsample, dtype=torch.int32, device=xyz.device).reshape(1, 1, nsample).expand(b, 1, nsample)
+            pooled = ops.sa_group_all_infer(xyz, points, params.mlp(scopes)).reshape(b, 1, -1)
+        else:
+            new_xyz, new_points, idx, _ = sample_and_group_all(xyz, points, use_xyz)
+            rows = new_points.reshape(b * nsample, new_points.shape[-1])
+            pooled = ops.shared_mlp(rows, params.mlp(scopes), pool_k=nsample).reshape(b, 1, -1)
     elif knn or not use_xyz:
         new_xyz, new_points, idx, _ = sample_and_group(npoint, radius, nsample, xyz, points, knn, use_xyz)
         b, m, k, c = new_points.shape

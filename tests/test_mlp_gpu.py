@@ -92,6 +92,10 @@ def test_edgeconv_infer_matches_fp64(n, c, k, mlp):
         p.add_conv2d(f"e/conv{i}", cin, co, bn=True, randomize_bn=True)
         scopes.append(f"e/conv{i}")
         cin = co
+    # negative BN scales on a third of the channels: the single-layer algebra path must switch from max_j to min_j there
+    g = p["e/conv0/bn/gamma"]
+    g[::3] = -g[::3]
+    p.invalidate()
     rng = np.random.default_rng(n)
     x = rng.standard_normal((2, n, c)).astype(np.float32)
     idx = orc.dgcnn_knn(x, k)
