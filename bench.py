@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BGA / DGCNN / single-op measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -270,6 +271,72 @@ def main():
             stages[name] = ts[len(ts) // 2] * 1e3      # median, us
         del flush
 
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        from scanobjectnn_b200 import dgcnn, pointnet2_cls_bga
+
+        def time_graph(fn, reps=10):
+            """CUDA-graph one forward on a static input, replay `reps` times, device time per forward in ms."""
+            sx = pool_dev[2].clone()
+            s2 = torch.cuda.Stream()
+            s2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s2):
+                for _ in range(2):
+                    fn(sx)
+            torch.cuda.current_stream().wait_stream(s2)
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                fn(sx)
+            for i in range(3):
+                sx.copy_(pool_dev[(3 + i) % POOL]); g2.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                sx.copy_(pool_dev[(7 + i) % POOL]); g2.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        p_bga = pointnet2_cls_bga.init_params(seed=2, device=dev, randomize_bn=True)
+        ms = time_graph(lambda t: pointnet2_cls_bga.get_model(t, False, params=p_bga))
+        extra["pointnet2_cls_bga"] = {"workload": "inference forward B=32 N=2048 (BASELINE.json configs[3] per-GPU shape)", "ms_per_step": ms,
+                                      "clouds_per_s": B / (ms * 1e-3)}
+        p_dg = dgcnn.init_params(seed=3, device=dev, randomize_bn=True)
+        ms = time_graph(lambda t: dgcnn.get_model(t, False, params=p_dg), reps=5)
+        extra["dgcnn"] = {"workload": "inference forward k=20 B=32 N=2048 (BASELINE.json configs[2])", "ms_per_step": ms,
+                          "clouds_per_s": B / (ms * 1e-3)}
+        # single ops of the remaining scope rows, event-timed with an L2 flush + spin in front
+        xq = pool_dev[5].contiguous()
+        feats64 = torch.randn((B, N, 64), device=dev)
+        nn20 = ops.knn_graph(feats64, 20)
+        _, l1x = ops.farthest_point_sample_and_gather(512, xq)
+        f128 = torch.randn((B, 512, 128), device=dev)
+        mlp_e = ops.MlpParams([(torch.randn((128, 64), device=dev) * 0.1, torch.ones(64, device=dev), torch.zeros(64, device=dev), True)])
+        opcases = {
+            "knn_graph_c3": (lambda: ops.knn_graph(xq, 20), 2.0 * B * N * N * 3, B * (4 * N * 3 + 4 * N * 20)),
+            "knn_graph_c64": (lambda: ops.knn_graph(feats64, 20), 2.0 * B * N * N * 64, B * (4 * N * 64 + 4 * N * 20)),
+            "edgeconv_128to64": (lambda: ops.edgeconv_infer(feats64, nn20, mlp_e), 2.0 * B * N * 64 * 128, B * (4 * N * 64 + 4 * N * 20 + 4 * N * 64)),
+            "three_nn_interp_2048from512_c128": (lambda: ops.three_nn_interpolate(xq, l1x, f128), None, B * (12 * N + 12 * 512 + 4 * 512 * 128 + 4 * N * 128)),
+        }
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        extra["ops"] = {}
+        for name, (fn, flops, nbytes) in opcases.items():
+            for _ in range(2):
+                fn()
+            ts = []
+            for _ in range(5):
+                flush.zero_(); torch.cuda._sleep(400_000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            us = ts[len(ts) // 2] * 1e3
+            extra["ops"][name] = {"us": us, "alg_bytes": nbytes, "gbs": nbytes / (us * 1e-6) / 1e9,
+                                  **({"tflops_fp32": flops / (us * 1e-6) / 1e12} if flops else {})}
+        del flush
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,6 +403,7 @@ def main():
         "kernels": kern,
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "other_workloads": extra,
     }
     print(json.dumps(line))
     if world > 1:
