@@ -166,7 +166,25 @@ typedef struct psa_mlp {
     const float* scale[PSA_MAX_MLP_LAYERS];
     const float* shift[PSA_MAX_MLP_LAYERS];
     int relu[PSA_MAX_MLP_LAYERS];
+    /* Optional, for weights that do not change between calls (inference): tensor-core weight images built ONCE by
+     * psa_prepare_weight_image().  image[l] == NULL -> the entry point builds the image in its workspace on every call
+     * (~45 us per PointNet++ forward).  An image is only used if its tile width / first row match what the entry point
+     * needs (psa_mlp_image_plan() tells); otherwise it is ignored and rebuilt. */
+    const void* image[PSA_MAX_MLP_LAYERS];
+    int image_nt[PSA_MAX_MLP_LAYERS];      /* output-channel tile width the image was built for (64 or 128) */
+    int image_row0[PSA_MAX_MLP_LAYERS];    /* first row of weight[l] covered by the image (3 when the xyz rows are split off) */
 } psa_mlp;
+
+/* Which images would an entry point use for this MLP?  usage: 0 = psa_shared_mlp(rows, pool_k), 1 = psa_sa_group_all_infer
+ * (rows = b*n, c), 2 = psa_sa_module_infer (rows = b*n, c, nsample).  Fills nt/row0/bytes per layer (bytes 0 = that layer
+ * does not run on the tensor cores).  Returns PSA_OK. */
+#define PSA_USAGE_SHARED_MLP 0
+#define PSA_USAGE_SA_GROUP_ALL 1
+#define PSA_USAGE_SA_MODULE 2
+PSA_API int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, int nsample, const psa_mlp* mlp,
+                               int nt[PSA_MAX_MLP_LAYERS], int row0[PSA_MAX_MLP_LAYERS], size_t bytes[PSA_MAX_MLP_LAYERS]);
+/* Build the image of rows [row0, K) of W (K, N) for tile width nt into `image` (bytes from psa_mlp_image_plan). */
+PSA_API int psa_prepare_weight_image(int K, int N, int row0, int nt, const float* W, void* image, psa_stream_t stream);
 
 /* Dense rows: x (rows, C_0) -> out.  pool_k == 1: out (rows, C_L).  pool_k > 1: rows must be a multiple
  * of pool_k and out (rows/pool_k, C_L) = channel-wise max over each run of pool_k consecutive rows

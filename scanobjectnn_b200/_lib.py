@@ -25,6 +25,9 @@ class PsaMlp(C.Structure):
         ("scale", C.c_void_p * PSA_MAX_MLP_LAYERS),
         ("shift", C.c_void_p * PSA_MAX_MLP_LAYERS),
         ("relu", C.c_int * PSA_MAX_MLP_LAYERS),
+        ("image", C.c_void_p * PSA_MAX_MLP_LAYERS),
+        ("image_nt", C.c_int * PSA_MAX_MLP_LAYERS),
+        ("image_row0", C.c_int * PSA_MAX_MLP_LAYERS),
     ]
 
 
@@ -53,6 +56,8 @@ SIGNATURES = {
     "psa_sa_module_infer": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, C.POINTER(PsaMlp), _p, _p, _p, _p, C.c_size_t, _p],
     "psa_sa_conv1_prebn": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, C.c_size_t, _p],
     "psa_sa_group_all_infer": [_i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
+    "psa_mlp_image_plan": [_i, C.c_longlong, _i, _i, _i, C.POINTER(PsaMlp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)],
+    "psa_prepare_weight_image": [_i, _i, _i, _i, _p, _p, _p],
     "psa_set_mlp_mode": [_i],
     "psa_get_mlp_mode": [],
     "psa_tc_selftest": [_i, _i, _p, _p, _p, _p, _p],

@@ -623,14 +623,16 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
 size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
 
 static int g_tc_dense_narrow = 1;
+int tc_dense_nt(int N) { return tc_nt(N, g_tc_dense_narrow ? 64 : 128); }
 
+// `image`: workspace to build the weight image in, or -- when `prebuilt` -- an image that already holds it
 int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
-                    const float* shift, float* out, uint8_t* image, cudaStream_t st, const float* xyz3 = nullptr,
-                    const float* w3 = nullptr) {
+                    const float* shift, float* out, const uint8_t* image, cudaStream_t st, const float* xyz3 = nullptr,
+                    const float* w3 = nullptr, bool prebuilt = false) {
     const int Kp = (K + 63) & ~63;
     const bool narrow = g_tc_dense_narrow != 0;
     const int Nt = tc_nt(N, narrow ? 64 : 128);
-    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, image);
+    if (!prebuilt) tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, const_cast<uint8_t*>(image));
     TcDenseArgs a;
     a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
     a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out; a.xyz3 = xyz3; a.w3 = w3;
@@ -650,6 +652,15 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
     }
     if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
     return check_launch("tc_dense_kernel");
+}
+
+
+// A prebuilt image (psa_prepare_weight_image) is used when it matches; otherwise the image is (re)built into `ws`.
+static const uint8_t* use_or_build_image(const psa_mlp* mlp, int l, int row0, int N, int Nt, uint8_t* ws, cudaStream_t st) {
+    if (mlp->image[l] != nullptr && mlp->image_nt[l] == Nt && mlp->image_row0[l] == row0) return reinterpret_cast<const uint8_t*>(mlp->image[l]);
+    const int K = mlp->channels[l] - row0, Kp = (K + 63) & ~63;
+    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, mlp->weight[l] + (size_t)row0 * N, ws);
+    return ws;
 }
 
 // Can this MLP / geometry run on the tensor-core kernel?  (otherwise the fp32-FMA fused kernel in mlp.cu is used)
@@ -778,8 +789,7 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         for (int l = 0; l < a.nl; ++l) {
             a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
             const int K = a.Kd[l], N = a.Ntot[l];
-            tc_prep_weights_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(K, K, N, tc_nt(N, a.ntcap), mlp->weight[1 + l], ws);
-            a.image[l] = ws;
+            a.image[l] = use_or_build_image(mlp, 1 + l, 0, N, tc_nt(N, a.ntcap), ws, st);
             ws += (tc_image_bytes(K, N) + 255) & ~(size_t)255;
         }
         rc = check_launch("tc_prep_weights_kernel");
@@ -790,7 +800,8 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
             uint8_t* uimg = ws + (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255);
             const float* w1f = mlp->weight[0] + (size_t)3 * a.C1;
             if (tc_dense_eligible((long long)b * n, c, a.C1, 1)) {
-                rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, uf, uimg, st);
+                const uint8_t* im = use_or_build_image(mlp, 0, 3, a.C1, tc_dense_nt(a.C1), uimg, st);
+                rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, uf, im, st, nullptr, nullptr, true);
             } else {
                 DenseArgs d;
                 d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
@@ -852,7 +863,8 @@ extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const 
         const int pk = (l == L - 1) ? pool_k : 1;
         float* dst = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
         if (g_mlp_mode == 0 && tc_dense_eligible(rows, K, N, pk)) {
-            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, mlp->weight[l], mlp->scale[l], mlp->shift[l], dst, img, st);
+            const uint8_t* im = use_or_build_image(mlp, l, 0, N, tc_dense_nt(N), img, st);
+            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, mlp->weight[l], mlp->scale[l], mlp->shift[l], dst, im, st, nullptr, nullptr, true);
         } else {
             DenseArgs d;
             d.rows = rows; d.K = K; d.N = N; d.pool_k = pk; d.relu = mlp->relu[l];
@@ -908,8 +920,9 @@ extern "C" int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, con
         float* dst = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
         const float* W = (l == 0) ? mlp->weight[0] + (size_t)3 * N : mlp->weight[l];
         if (tc_dense_eligible(rows, K, N, pk)) {
-            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, W, mlp->scale[l], mlp->shift[l], dst, img, st,
-                                 l == 0 ? xyz : nullptr, l == 0 ? mlp->weight[0] : nullptr);
+            const uint8_t* im = use_or_build_image(mlp, l, l == 0 ? 3 : 0, N, tc_dense_nt(N), img, st);
+            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, W, mlp->scale[l], mlp->shift[l], dst, im, st,
+                                 l == 0 ? xyz : nullptr, l == 0 ? mlp->weight[0] : nullptr, true);
         } else {
             PSA_SUPPORTED(l > 0, "sa_group_all: layer 0 must run on the tensor-core path");
             DenseArgs d;
@@ -1022,4 +1035,37 @@ extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, co
     if (vec == 1) PSA_EDGE_LAUNCH(1); else if (vec == 2) PSA_EDGE_LAUNCH(2); else if (vec == 4) PSA_EDGE_LAUNCH(4); else PSA_EDGE_LAUNCH(8);
 #undef PSA_EDGE_LAUNCH
     return check_launch("edge_gather_max_kernel");
+}
+
+extern "C" int psa_prepare_weight_image(int K, int N, int row0, int nt, const float* W, void* image, psa_stream_t stream) {
+    PSA_REQUIRE(K >= 1 && N >= 64 && N % 64 == 0 && row0 >= 0 && row0 < K && (nt == 64 || nt == 128) && N % nt == 0,
+                "prepare_weight_image: bad arguments K=%d N=%d row0=%d nt=%d", K, N, row0, nt);
+    PSA_REQUIRE(W && image, "prepare_weight_image: null buffer");
+    const int Ki = K - row0, Kp = (Ki + 63) & ~63;
+    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, as_stream(stream)>>>(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image));
+    return check_launch("tc_prep_weights_kernel");
+}
+
+extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, int nsample, const psa_mlp* mlp,
+                                  int nt[PSA_MAX_MLP_LAYERS], int row0[PSA_MAX_MLP_LAYERS], size_t bytes[PSA_MAX_MLP_LAYERS]) {
+    int rc = validate_mlp_public(mlp, "mlp_image_plan");
+    if (rc != PSA_OK) return rc;
+    for (int l = 0; l < PSA_MAX_MLP_LAYERS; ++l) { nt[l] = 0; row0[l] = 0; bytes[l] = 0; }
+    if (g_mlp_mode != 0) return PSA_OK;
+    const int L = mlp->n_layers;
+    if (usage == PSA_USAGE_SHARED_MLP || usage == PSA_USAGE_SA_GROUP_ALL) {
+        for (int l = 0; l < L; ++l) {
+            const int r0 = (usage == PSA_USAGE_SA_GROUP_ALL && l == 0) ? 3 : 0;
+            const int K = mlp->channels[l] - r0, N = mlp->channels[l + 1];
+            const int pk = (l == L - 1) ? pool_k : 1;
+            if (K >= 1 && tc_dense_eligible(rows, K, N, pk)) { nt[l] = tc_dense_nt(N); row0[l] = r0; bytes[l] = tc_dense_image_bytes(K, N); }
+        }
+        return PSA_OK;
+    }
+    PSA_REQUIRE(usage == PSA_USAGE_SA_MODULE, "mlp_image_plan: unknown usage %d", usage);
+    TcArgs a;
+    if (!tc_sa_eligible(mlp, c, nsample, &a)) return PSA_OK;
+    if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_dense_image_bytes(c, a.C1); }
+    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_nt(a.Ntot[l], a.ntcap); row0[1 + l] = 0; bytes[1 + l] = (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255; }
+    return PSA_OK;
 }

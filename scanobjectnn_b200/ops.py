@@ -358,10 +358,40 @@ class MlpParams:
             self._keep += [w, scale, shift]
         self.struct = s
         self.channels = [s.channels[i] for i in range(len(layers) + 1)]
+        self._weights = [w for (w, _, _, _) in [(self._keep[3 * i], None, None, None) for i in range(len(layers))]]
+        self._prepared = {}
 
     @property
     def ref(self):
         return C.byref(self.struct)
+
+    def prepared(self, usage: int, rows: int, pool_k: int = 1, c: int = 0, nsample: int = 0):
+        """byref of a copy of the struct whose tensor-core weight images were built ONCE (inference: the weights do not
+        change between calls), so the entry points skip the per-call prep kernels.  Keyed by what the C side says it
+        will use for this (usage, shape)."""
+        lib = _lib.load()
+        L = self.struct.n_layers
+        nt = (C.c_int * _lib.PSA_MAX_MLP_LAYERS)()
+        row0 = (C.c_int * _lib.PSA_MAX_MLP_LAYERS)()
+        nbytes = (C.c_size_t * _lib.PSA_MAX_MLP_LAYERS)()
+        check(lib.psa_mlp_image_plan(usage, rows, pool_k, c, nsample, self.ref, nt, row0, nbytes), "mlp_image_plan")
+        key = tuple((nt[l], row0[l]) for l in range(L))
+        hit = self._prepared.get(key)
+        if hit is None:
+            st = PsaMlp()
+            C.memmove(C.byref(st), C.byref(self.struct), C.sizeof(PsaMlp))
+            keep = []
+            for l in range(L):
+                if nbytes[l]:
+                    w = self._weights[l]
+                    img = torch.empty(int(nbytes[l]), dtype=torch.uint8, device=w.device)
+                    check(lib.psa_prepare_weight_image(w.shape[0], w.shape[1], row0[l], nt[l], _ptr(w), _ptr(img), _stream()),
+                          "prepare_weight_image")
+                    st.image[l] = img.data_ptr(); st.image_nt[l] = nt[l]; st.image_row0[l] = row0[l]
+                    keep.append(img)
+            hit = (st, keep)
+            self._prepared[key] = hit
+        return C.byref(hit[0])
 
 
 def shared_mlp(x: torch.Tensor, mlp: MlpParams, pool_k: int = 1) -> torch.Tensor:
@@ -381,7 +411,8 @@ def shared_mlp(x: torch.Tensor, mlp: MlpParams, pool_k: int = 1) -> torch.Tensor
         out = torch.empty((*lead, cl), dtype=torch.float32, device=x.device)
     else:
         out = torch.empty((rows // max(pool_k, 1), cl), dtype=torch.float32, device=x.device)
-    check(lib.psa_shared_mlp(rows, pool_k, _ptr(x), mlp.ref, _ptr(out), _ptr(ws), C.c_size_t(need), _stream()), "shared_mlp")
+    check(lib.psa_shared_mlp(rows, pool_k, _ptr(x), mlp.prepared(0, rows, pool_k), _ptr(out), _ptr(ws), C.c_size_t(need), _stream()),
+          "shared_mlp")
     return out
 
 
@@ -407,8 +438,8 @@ def sa_module_infer(xyz, new_xyz, points, radius: float, nsample: int, mlp: MlpP
     need = lib.psa_sa_module_workspace_bytes(b, n, m, c, nsample, mlp.ref)
     ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=xyz.device) if need else None   # torch allocations are 512-B aligned
     check(lib.psa_sa_module_infer(b, n, m, c, C.c_float(radius), nsample, _ptr(xyz), _ptr(new_xyz), _ptr(points),
-                                  _ptr(idx), mlp.ref, _ptr(out), _ptr(idx_out), _ptr(cnt), _ptr(ws), C.c_size_t(need),
-                                  _stream()), "sa_module_infer")
+                                  _ptr(idx), mlp.prepared(2, b * n, 1, c, nsample), _ptr(out), _ptr(idx_out), _ptr(cnt), _ptr(ws),
+                                  C.c_size_t(need), _stream()), "sa_module_infer")
     if return_idx:
         return out, (idx if idx is not None else idx_out), cnt
     return out
@@ -425,7 +456,8 @@ def sa_group_all_infer(xyz, points, mlp: MlpParams) -> torch.Tensor:
     out = torch.empty((b, mlp.channels[-1]), dtype=torch.float32, device=xyz.device)
     need = lib.psa_sa_group_all_workspace_bytes(b, n, c, mlp.ref)
     ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=xyz.device) if need else None
-    rc = lib.psa_sa_group_all_infer(b, n, c, _ptr(xyz), _ptr(points), mlp.ref, _ptr(out), _ptr(ws), C.c_size_t(need), _stream())
+    rc = lib.psa_sa_group_all_infer(b, n, c, _ptr(xyz), _ptr(points), mlp.prepared(1, b * n, n, c), _ptr(out), _ptr(ws),
+                                    C.c_size_t(need), _stream())
     if rc == -2:        # PSA_ERR_UNSUPPORTED: shapes outside the fused path
         rows = torch.cat([xyz, points], dim=2).reshape(b * n, 3 + c)
         return shared_mlp(rows, mlp, pool_k=n)
