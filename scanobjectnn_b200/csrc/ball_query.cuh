@@ -33,27 +33,35 @@ struct BqGrid {
     int use;                            // 0 -> scan path for the whole CTA
 };
 
+// Shared-memory plan.  scan mode: the cloud as SoA (12 B/point).  grid mode: ONLY the cell-sorted copy (16 B/point) + cell
+// table + hit buffers -- the rare scan fallback then reads the cloud from global memory / L1 -- so that four CTAs fit an SM.
 struct BqSmem {
-    float* sx; float* sy; float* sz;    // np = round_up(n,128) floats each, padded with +inf
-    float4* sorted;                     // n entries (x, y, z, bits(k)), grouped by cell          (grid only)
-    int* cell_end;                      // kBqMaxCells + 32 ints: end offset of each cell, scratch (grid only)
-    int* hits;                          // kBqWarps * kBqHitCap                                    (grid only)
+    float* sx; float* sy; float* sz;    // scan mode: np = round_up(n,128) floats each, padded with +inf; grid mode: null
+    float4* sorted;                     // grid mode: n entries (x, y, z, bits(k)), grouped by cell
+    int* cell_end;                      // grid mode: kBqMaxCells + 32 ints: end offset of each cell, scratch
+    int* hits;                          // grid mode: kBqWarps * kBqHitCap
+    const float* gxyz;                  // the cloud in global memory (AoS), always valid
 };
 
 __host__ __device__ inline size_t bq_smem_bytes(int n, bool grid) {
-    size_t b = (size_t)((n + 127) & ~127) * 3 * sizeof(float);
-    if (grid) b += (size_t)n * 16 + (size_t)(kBqMaxCells + 32) * 4 + (size_t)kBqWarps * kBqHitCap * 4;
-    return b;
+    if (grid) return (size_t)n * 16 + (size_t)(kBqMaxCells + 32) * 4 + (size_t)kBqWarps * kBqHitCap * 4;
+    return (size_t)((n + 127) & ~127) * 3 * sizeof(float);
 }
 __host__ __device__ inline bool bq_grid_fits(int n) { return n <= kBqGridMaxN; }
 
-__device__ __forceinline__ BqSmem bq_carve(float* base, int n, bool grid) {
+__device__ __forceinline__ BqSmem bq_carve(float* base, int n, bool grid, const float* gxyz) {
     BqSmem s;
-    const int np = (n + 127) & ~127;
-    s.sx = base; s.sy = base + np; s.sz = base + 2 * np;
-    s.sorted = reinterpret_cast<float4*>(base + 3 * np);       // 3*np*4 bytes is a multiple of 16
-    s.cell_end = reinterpret_cast<int*>(s.sorted + (grid ? n : 0));
-    s.hits = s.cell_end + (grid ? kBqMaxCells + 32 : 0);
+    s.gxyz = gxyz;
+    if (grid) {
+        s.sx = s.sy = s.sz = nullptr;
+        s.sorted = reinterpret_cast<float4*>(base);
+        s.cell_end = reinterpret_cast<int*>(s.sorted + n);
+        s.hits = s.cell_end + kBqMaxCells + 32;
+    } else {
+        const int np = (n + 127) & ~127;
+        s.sx = base; s.sy = base + np; s.sz = base + 2 * np;
+        s.sorted = nullptr; s.cell_end = nullptr; s.hits = nullptr;
+    }
     return s;
 }
 
@@ -62,15 +70,18 @@ __device__ __forceinline__ int bq_cell_coord(float v, float vmin, float inv_h, i
     return c < g - 1 ? c : g - 1;
 }
 
-// Stage one cloud (AoS global -> SoA shared, padded with +inf) and, if asked, build the cell grid.  All kBqThreads call.
-__device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, const float* __restrict__ p1, int n, float radius,
-                                                     bool want_grid) {
+// scan mode: stage the cloud (AoS global -> SoA shared, padded with +inf).
+// grid mode: each thread keeps its points (k = tid + 256 i) in registers, the CTA computes the bounding box, bins the
+// points with a counting sort and scatters (x, y, z, k) into `sorted`.  All kBqThreads call.
+template <int PPT>   // points per thread in grid mode: n <= PPT * kBqThreads
+__device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, int n, float radius, bool want_grid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int np = (n + 127) & ~127;
+    const float* p1 = s.gxyz;
     const float inf = __int_as_float(0x7f800000);
-    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
-    bool fin = true;
-    {
+    BqGrid g;
+    g.use = 0; g.minx = g.miny = g.minz = 0.f; g.inv_h = 0.f; g.gx = g.gy = g.gz = 1;
+    if (!want_grid) {
+        const int np = (n + 127) & ~127;
         const int total = n * 3;
         int i = tid;
         for (; i + 7 * kBqThreads < total; i += 8 * kBqThreads) {
@@ -81,36 +92,43 @@ __device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, const floa
             for (int u = 0; u < 8; ++u) {
                 const int e = i + u * kBqThreads, k = e / 3, c = e - k * 3;
                 (c == 0 ? s.sx : (c == 1 ? s.sy : s.sz))[k] = v[u];
-                fin = fin && (fabsf(v[u]) <= 3.0e38f);
-                mn[c] = fminf(mn[c], v[u]); mx[c] = fmaxf(mx[c], v[u]);
             }
         }
         for (; i < total; i += kBqThreads) {
             const int k = i / 3, c = i - k * 3;
-            const float v = __ldg(p1 + i);
-            (c == 0 ? s.sx : (c == 1 ? s.sy : s.sz))[k] = v;
-            fin = fin && (fabsf(v) <= 3.0e38f);
-            mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+            (c == 0 ? s.sx : (c == 1 ? s.sy : s.sz))[k] = __ldg(p1 + i);
+        }
+        for (int k = n + tid; k < np; k += kBqThreads) { s.sx[k] = inf; s.sy[k] = inf; s.sz[k] = inf; }
+        __syncthreads();
+        return g;
+    }
+    float px[PPT], py[PPT], pz[PPT];
+    float mnx = inf, mny = inf, mnz = inf, mxx = -inf, mxy = -inf, mxz = -inf;
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * kBqThreads;
+        if (k < n) {
+            px[i] = __ldg(p1 + 3 * k); py[i] = __ldg(p1 + 3 * k + 1); pz[i] = __ldg(p1 + 3 * k + 2);
+            fin = fin && fabsf(px[i]) <= 3.0e38f && fabsf(py[i]) <= 3.0e38f && fabsf(pz[i]) <= 3.0e38f;
+            mnx = fminf(mnx, px[i]); mny = fminf(mny, py[i]); mnz = fminf(mnz, pz[i]);
+            mxx = fmaxf(mxx, px[i]); mxy = fmaxf(mxy, py[i]); mxz = fmaxf(mxz, pz[i]);
+        } else {
+            px[i] = py[i] = pz[i] = 0.f;
         }
     }
-    for (int k = n + tid; k < np; k += kBqThreads) { s.sx[k] = inf; s.sy[k] = inf; s.sz[k] = inf; }
-    BqGrid g;
-    g.use = 0; g.minx = g.miny = g.minz = 0.f; g.inv_h = 0.f; g.gx = g.gy = g.gz = 1;
-    if (!want_grid) { __syncthreads(); return g; }
     // ---- bounding box + finiteness: warp shuffles, then 8 partials through shared memory ----
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
-            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
-        }
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
     }
     fin = __all_sync(0xffffffffu, fin);
     float* scratch = reinterpret_cast<float*>(s.cell_end);
     if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { scratch[warp * 8 + c] = mn[c]; scratch[warp * 8 + 3 + c] = mx[c]; }
+        scratch[warp * 8 + 0] = mnx; scratch[warp * 8 + 1] = mny; scratch[warp * 8 + 2] = mnz;
+        scratch[warp * 8 + 3] = mxx; scratch[warp * 8 + 4] = mxy; scratch[warp * 8 + 5] = mxz;
         scratch[warp * 8 + 6] = fin ? 1.f : 0.f;
     }
     __syncthreads();
@@ -139,10 +157,17 @@ __device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, const floa
     const int ncells = g.gx * g.gy * g.gz;
     for (int c = tid; c < ncells; c += kBqThreads) s.cell_end[c] = 0;
     __syncthreads();
-    for (int k = tid; k < n; k += kBqThreads) {
-        const int cx = bq_cell_coord(s.sx[k], g.minx, g.inv_h, g.gx), cy = bq_cell_coord(s.sy[k], g.miny, g.inv_h, g.gy);
-        const int cz = bq_cell_coord(s.sz[k], g.minz, g.inv_h, g.gz);
-        atomicAdd(&s.cell_end[(cz * g.gy + cy) * g.gx + cx], 1);
+    int cell[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * kBqThreads;
+        cell[i] = 0;
+        if (k < n) {
+            const int cx = bq_cell_coord(px[i], g.minx, g.inv_h, g.gx), cy = bq_cell_coord(py[i], g.miny, g.inv_h, g.gy);
+            const int cz = bq_cell_coord(pz[i], g.minz, g.inv_h, g.gz);
+            cell[i] = (cz * g.gy + cy) * g.gx + cx;
+            atomicAdd(&s.cell_end[cell[i]], 1);
+        }
     }
     __syncthreads();
     // exclusive scan of the cell counts: each thread owns a contiguous run of cells
@@ -165,12 +190,13 @@ __device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, const floa
         for (int c = c0; c < min(ncells, c0 + per); ++c) { const int cnt = s.cell_end[c]; s.cell_end[c] = off; off += cnt; }
     }
     __syncthreads();
-    for (int k = tid; k < n; k += kBqThreads) {
-        const float x = s.sx[k], y = s.sy[k], z = s.sz[k];
-        const int cx = bq_cell_coord(x, g.minx, g.inv_h, g.gx), cy = bq_cell_coord(y, g.miny, g.inv_h, g.gy);
-        const int cz = bq_cell_coord(z, g.minz, g.inv_h, g.gz);
-        const int pos = atomicAdd(&s.cell_end[(cz * g.gy + cy) * g.gx + cx], 1);     // afterwards cell_end[c] = END of cell c
-        s.sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * kBqThreads;
+        if (k < n) {
+            const int pos = atomicAdd(&s.cell_end[cell[i]], 1);      // afterwards cell_end[c] = END of cell c
+            s.sorted[pos] = make_float4(px[i], py[i], pz[i], __int_as_float(k));
+        }
     }
     __syncthreads();
     return g;
@@ -186,18 +212,29 @@ __device__ __forceinline__ float2 bq_dist2_pair(float2 x, float2 y, float2 z, fl
     return t;
 }
 
-// Ordered scan path: one warp, 128 points per step, ballot + prefix-popcount compaction keeps index order, early exit.
+// Ordered scan path: one warp, 128 points per step (4 consecutive points per lane), ballot + prefix-popcount compaction
+// keeps index order, early exit.  The points come from the shared SoA copy (scan mode) or, in grid mode where this is
+// only the rare fallback, straight from global memory.
 __device__ __forceinline__ int bq_scan_warp(int n, int nsample, float thr, bool none, const BqSmem& s, float qx, float qy,
                                             float qz, int* idxrow, int lane) {
     int cnt = 0, first = -1;
     if (!none) {
         const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
         const unsigned lt = lanemask_lt();
+        const float inf = __int_as_float(0x7f800000);
         for (int base = 0; base < n && cnt < nsample; base += 128) {
             const int k = base + lane * 4;
-            const float4 X = *reinterpret_cast<const float4*>(s.sx + k);
-            const float4 Y = *reinterpret_cast<const float4*>(s.sy + k);
-            const float4 Z = *reinterpret_cast<const float4*>(s.sz + k);
+            float4 X, Y, Z;
+            if (s.sx != nullptr) {
+                X = *reinterpret_cast<const float4*>(s.sx + k);
+                Y = *reinterpret_cast<const float4*>(s.sy + k);
+                Z = *reinterpret_cast<const float4*>(s.sz + k);
+            } else {
+                float v[12];
+#pragma unroll
+                for (int u = 0; u < 12; ++u) v[u] = (k + u / 3 < n) ? __ldg(s.gxyz + (size_t)k * 3 + u) : inf;
+                X = make_float4(v[0], v[3], v[6], v[9]); Y = make_float4(v[1], v[4], v[7], v[10]); Z = make_float4(v[2], v[5], v[8], v[11]);
+            }
             const float2 d01 = bq_dist2_pair(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
             const float2 d23 = bq_dist2_pair(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
             // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r

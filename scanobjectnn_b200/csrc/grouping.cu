@@ -32,14 +32,15 @@ float ball_query_threshold(float radius, bool* none) {
     return t;
 }
 
-__global__ void __launch_bounds__(kBqThreads)
+template <int PPT>
+__global__ void __launch_bounds__(kBqThreads, PPT <= 8 ? 3 : 2)
 ball_query_kernel(int n, int m, int nsample, float radius, float thr, int none, int want_grid, int q_per_cta,
                   const float* __restrict__ xyz1, const float* __restrict__ xyz2, int* __restrict__ idx,
                   int* __restrict__ pts_cnt) {
     extern __shared__ __align__(16) float smem_f[];
-    const BqSmem s = bq_carve(smem_f, n, want_grid != 0);
     const int cloud = blockIdx.y;
-    const BqGrid g = bq_stage_and_build(s, xyz1 + (size_t)cloud * n * 3, n, radius, want_grid != 0);
+    const BqSmem s = bq_carve(smem_f, n, want_grid != 0, xyz1 + (size_t)cloud * n * 3);
+    const BqGrid g = bq_stage_and_build<PPT>(s, n, radius, want_grid != 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * q_per_cta;
     const int q1 = min(m, q0 + q_per_cta);
@@ -181,9 +182,15 @@ extern "C" int psa_query_ball_point(int b, int n, int m, float radius, int nsamp
     q_per_cta = ((q_per_cta + kBqWarps - 1) / kBqWarps) * kBqWarps;
     if (q_per_cta < 2 * kBqWarps) q_per_cta = 2 * kBqWarps;
     dim3 grid((m + q_per_cta - 1) / q_per_cta, b);
-    PSA_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ball_query_kernel<<<grid, kBqThreads, smem, as_stream(stream)>>>(n, m, nsample, radius, thr, none ? 1 : 0, want_grid ? 1 : 0,
-                                                                     q_per_cta, xyz1, xyz2, idx, pts_cnt);
+    if (n <= 8 * kBqThreads) {
+        PSA_CUDA(cudaFuncSetAttribute(ball_query_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ball_query_kernel<8><<<grid, kBqThreads, smem, as_stream(stream)>>>(n, m, nsample, radius, thr, none ? 1 : 0, want_grid ? 1 : 0,
+                                                                            q_per_cta, xyz1, xyz2, idx, pts_cnt);
+    } else {
+        PSA_CUDA(cudaFuncSetAttribute(ball_query_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ball_query_kernel<16><<<grid, kBqThreads, smem, as_stream(stream)>>>(n, m, nsample, radius, thr, none ? 1 : 0, want_grid ? 1 : 0,
+                                                                             q_per_cta, xyz1, xyz2, idx, pts_cnt);
+    }
     return check_launch("ball_query_kernel");
 }
 

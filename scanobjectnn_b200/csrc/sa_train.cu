@@ -40,12 +40,12 @@ __global__ void __launch_bounds__(kF1Warps * 32)
 sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
     extern __shared__ __align__(16) float smem_f[];
     const int n = a.n;
-    const BqSmem s = bq_carve(smem_f, n, a.want_grid != 0);
-    const float* sx = s.sx; const float* sy = s.sy; const float* sz = s.sz;
+    const int cloud = blockIdx.y;
+    const float* gx = a.xyz + (size_t)cloud * n * 3;       // neighbour coordinates come from global memory / L1 (24 KB per cloud)
+    const BqSmem s = bq_carve(smem_f, n, a.want_grid != 0, gx);
     int* srow = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(smem_f) + bq_smem_bytes(n, a.want_grid != 0));   // kF1Warps * nsample
     float* sstat = reinterpret_cast<float*>(srow + kF1Warps * ((a.nsample + 3) & ~3));   // kF1Warps * 2 * C1 (STATS), 16-B aligned
-    const int cloud = blockIdx.y;
-    const BqGrid g = bq_stage_and_build(s, a.xyz + (size_t)cloud * n * 3, n, a.radius, a.want_grid != 0);
+    const BqGrid g = bq_stage_and_build<16>(s, n, a.radius, a.want_grid != 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, rsub = lane >> 3;
     float4 wx[NV], wy[NV], wz[NV], bs[NV], ssum[NV], ssq[NV];
@@ -75,7 +75,7 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
             const int r = r0 + rsub;
             if (r < a.nsample) {
                 const int j = row[r];
-                const float dx = sx[j] - qx, dy = sy[j] - qy, dz = sz[j] - qz;     // grouped_xyz - new_xyz (pointnet_util.py:46)
+                const float dx = __ldg(gx + 3 * j) - qx, dy = __ldg(gx + 3 * j + 1) - qy, dz = __ldg(gx + 3 * j + 2) - qz;   // grouped_xyz - new_xyz (pointnet_util.py:46)
                 const float* urow = a.uf ? a.uf + ((size_t)cloud * n + j) * a.C1 : nullptr;
                 float* orow = outq + (size_t)r * a.C1;
 #pragma unroll
