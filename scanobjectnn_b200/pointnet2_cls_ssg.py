@@ -9,6 +9,14 @@ from .pointnet_util import add_sa_module_params, pointnet_sa_module
 from .tf_util import VariableStore, _require_inference
 
 NUM_CLASSES = 15
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
 
 
 def init_params(num_class=NUM_CLASSES, seed=0, device="cuda", randomize_bn=False) -> VariableStore:
@@ -28,14 +36,28 @@ def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *,
     batch_size = point_cloud.shape[0]
     end_points = {"l0_xyz": point_cloud}
     l0_xyz, l0_points = point_cloud, None
+    # Sampling of BOTH levels up front: level 2's FPS needs level 1's centroids only, so it runs on a side stream while
+    # the main stream does level 1's ball query + MLP (the FPS kernels occupy one CTA per cloud: 32 of 148 SMs).
+    _, l1_new = ops.farthest_point_sample_and_gather(512, l0_xyz)
+    main = torch.cuda.current_stream()
+    side = _side_stream(point_cloud.device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        _, l2_new = ops.farthest_point_sample_and_gather(128, l1_new)
+        join = torch.cuda.Event()
+        join.record(side)
     l1_xyz, l1_points, l1_indices = pointnet_sa_module(l0_xyz, l0_points, npoint=512, radius=0.2, nsample=32,
                                                        mlp=[64, 64, 128], mlp2=None, group_all=False,
                                                        is_training=is_training, bn_decay=bn_decay, scope="layer1",
-                                                       use_nchw=True, params=params)
+                                                       use_nchw=True, params=params, new_xyz=l1_new)
+    main.wait_event(join)
+    l2_new.record_stream(main)
     l2_xyz, l2_points, l2_indices = pointnet_sa_module(l1_xyz, l1_points, npoint=128, radius=0.4, nsample=64,
                                                        mlp=[128, 128, 256], mlp2=None, group_all=False,
                                                        is_training=is_training, bn_decay=bn_decay, scope="layer2",
-                                                       params=params)
+                                                       params=params, new_xyz=l2_new)
     l3_xyz, l3_points, l3_indices = pointnet_sa_module(l2_xyz, l2_points, npoint=None, radius=None, nsample=None,
                                                        mlp=[256, 512, 1024], mlp2=None, group_all=True,
                                                        is_training=is_training, bn_decay=bn_decay, scope="layer3",

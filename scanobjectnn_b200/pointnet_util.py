@@ -60,12 +60,15 @@ def add_sa_module_params(params: VariableStore, scope, in_channels, mlp, mlp2=No
 
 
 def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training, bn_decay, scope,
-                       bn=True, pooling="max", knn=False, use_xyz=True, use_nchw=False, *, params: VariableStore):
+                       bn=True, pooling="max", knn=False, use_xyz=True, use_nchw=False, *, params: VariableStore,
+                       new_xyz=None):
     """pointnet_util.pointnet_sa_module (pointnet_util.py:87-154) -> (new_xyz, new_points (B,npoint,C_out), idx).
 
     max-pooling / ball-query / use_xyz levels run as TWO launches: fused FPS+gather, then the fused
     ball-query -> group -> centre -> MLP -> max kernel pair (no (B,m,K,C) tensor is ever built).
-    ``use_nchw`` only selected a cuDNN layout in the reference and has no effect on results."""
+    ``use_nchw`` only selected a cuDNN layout in the reference and has no effect on results.
+    ``new_xyz`` (extension): centroids already sampled by the caller (= gather_point(xyz, farthest_point_sample(npoint,
+    xyz))), e.g. on a side stream -- FPS of level l+1 only depends on level l's centroids, not on its features."""
     _require_inference(is_training)
     if pooling != "max":
         raise NotImplementedError("only pooling='max' is used by the in-scope models")
@@ -87,7 +90,8 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
         b, m, k, c = new_points.shape
         pooled = ops.shared_mlp(new_points.reshape(b * m * k, c), params.mlp(scopes), pool_k=k).reshape(b, m, -1)
     else:
-        _, new_xyz = ops.farthest_point_sample_and_gather(npoint, xyz)
+        if new_xyz is None:
+            _, new_xyz = ops.farthest_point_sample_and_gather(npoint, xyz)
         pooled, idx, _ = ops.sa_module_infer(xyz, new_xyz, points, radius, nsample, params.mlp(scopes), return_idx=True)
     if mlp2 is not None:
         pooled = ops.shared_mlp(pooled, params.mlp(_mlp_scopes(scope, mlp2, "conv_post_")))
