@@ -97,6 +97,8 @@ struct TcArgs {
     int Kd[kMaxTcLayers], Ntot[kMaxTcLayers];
     int stream_last;       // 1: the last layer's weights do not fit next to the others -> one 128-channel tile at a time
     int ntcap;             // 64 (narrow configuration) or 128 (wide)
+    unsigned int* tile_counter;   // zeroed before the launch: tiles are handed out dynamically (CTAs that start late or
+                                  // share their SM with another stream's kernels simply take fewer)
 };
 
 // quantise one row-chunk of 32 activations into the three A operands and store them into TMEM
@@ -242,7 +244,15 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
 
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __shared__ unsigned int s_tile[2];
+    if (tid == 0) s_tile[0] = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    int tpar = 0;
+    for (long long tile = s_tile[0]; tile < ntiles; tile = s_tile[tpar]) {
+        // thread 0 claims the NEXT tile now; everybody reads it after this tile's barriers (s_tile is double-buffered)
+        long long next_tile = 0;
+        if (tid == 0) { const unsigned int t = atomicAdd(a.tile_counter, 1u); s_tile[tpar ^ 1] = t; next_tile = t; }
+        tpar ^= 1;
         const long long g0 = tile * G;
         const long long gid = g0 + row / a.K;
         const bool valid = gid < a.groups;
@@ -309,7 +319,7 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
                 fence_after_thread_sync();
                 if (tid == 0 && streamed && NT > 1) {
                     // the ring is free again: fetch the next 128-channel tile (wrapping to tile 0 for the next row tile)
-                    const bool more = (nt + 1 < NT) || (tile + gridDim.x < ntiles);
+                    const bool more = (nt + 1 < NT) || (next_tile < ntiles);
                     if (more) {
                         ring_tile = (nt + 1) % NT;
                         mbar_expect_tx(&s_wbar, ring_bytes);
@@ -698,7 +708,7 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
 }
 
 size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
-    size_t bytes = 0;
+    size_t bytes = 256;       // dynamic tile counter
     for (int l = 0; l < a.nl; ++l) bytes += (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255;
     if (c > 0) bytes += (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255) + tc_dense_image_bytes(c, a.C1);
     return bytes;
@@ -786,6 +796,9 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.out = out; a.uf = nullptr;
         a.w1x = mlp->weight[0]; a.s1 = mlp->scale[0]; a.t1 = mlp->shift[0]; a.relu1 = mlp->relu[0];
         uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+        a.tile_counter = reinterpret_cast<unsigned int*>(ws);
+        PSA_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+        ws += 256;
         for (int l = 0; l < a.nl; ++l) {
             a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
             const int K = a.Kd[l], N = a.Ntot[l];
