@@ -35,8 +35,8 @@ struct F1Args {
 
 // conv stage mapping: 8 lanes per row, 4 rows per warp step; lane-in-row s owns channels [32*i + 4*s, +4), i < NV = C1/32,
 // so every store instruction writes 128 contiguous bytes per row and a query's K rows take K/4 steps.
-template <int NV, bool STATS>
-__global__ void __launch_bounds__(kF1Warps * 32)
+template <int NV, bool STATS, int PPT>
+__global__ void __launch_bounds__(kF1Warps * 32, PPT <= 8 ? 3 : 2)
 sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
     extern __shared__ __align__(16) float smem_f[];
     const int n = a.n;
@@ -45,24 +45,31 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
     const BqSmem s = bq_carve(smem_f, n, a.want_grid != 0, gx);
     int* srow = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(smem_f) + bq_smem_bytes(n, a.want_grid != 0));   // kF1Warps * nsample
     float* sstat = reinterpret_cast<float*>(srow + kF1Warps * ((a.nsample + 3) & ~3));   // kF1Warps * 2 * C1 (STATS), 16-B aligned
-    const BqGrid g = bq_stage_and_build<16>(s, n, a.radius, a.want_grid != 0);
+    const BqGrid g = bq_stage_and_build<PPT>(s, n, a.radius, a.want_grid != 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, rsub = lane >> 3;
-    float4 wx[NV], wy[NV], wz[NV], bs[NV], ssum[NV], ssq[NV];
+    // packed f32x2 registers: pair p of vector i covers channels 32*i + 4*sub + 2*p, +1
+    constexpr int NPK = 2 * NV;
+    float2 wx[NPK], wy[NPK], wz[NPK], bs[NPK], ssum[NPK], ssq[NPK];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = 32 * i + 4 * sub;
-        wx[i] = __ldg(reinterpret_cast<const float4*>(a.w1 + c));
-        wy[i] = __ldg(reinterpret_cast<const float4*>(a.w1 + a.C1 + c));
-        wz[i] = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * a.C1 + c));
-        bs[i] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ssum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ssq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.w1 + c));
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.w1 + a.C1 + c));
+        const float4 z4 = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * a.C1 + c));
+        const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wx[2 * i] = make_float2(x4.x, x4.y); wx[2 * i + 1] = make_float2(x4.z, x4.w);
+        wy[2 * i] = make_float2(y4.x, y4.y); wy[2 * i + 1] = make_float2(y4.z, y4.w);
+        wz[2 * i] = make_float2(z4.x, z4.y); wz[2 * i + 1] = make_float2(z4.z, z4.w);
+        bs[2 * i] = make_float2(b4.x, b4.y); bs[2 * i + 1] = make_float2(b4.z, b4.w);
+        ssum[2 * i] = ssum[2 * i + 1] = make_float2(0.f, 0.f);
+        ssq[2 * i] = ssq[2 * i + 1] = make_float2(0.f, 0.f);
     }
     const int q0 = blockIdx.x * a.q_per_cta;
     const int q1 = min(a.m, q0 + a.q_per_cta);
     const float* p2 = a.new_xyz + (size_t)cloud * a.m * 3;
     int* row = srow + warp * a.nsample;
+    const float* ucloud = a.uf ? a.uf + (size_t)cloud * n * a.C1 + 4 * sub : nullptr;
     for (int q = q0 + warp; q < q1; q += kF1Warps) {
         const float qx = __ldg(p2 + q * 3 + 0), qy = __ldg(p2 + q * 3 + 1), qz = __ldg(p2 + q * 3 + 2);
         const int cnt = bq_query_warp(n, a.nsample, a.thr, a.none != 0, s, g, qx, qy, qz, row, lane, warp);
@@ -70,29 +77,30 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
         const size_t gq = (size_t)cloud * a.m + q;
         for (int l = lane; l < a.nsample; l += 32) a.idx[gq * a.nsample + l] = row[l];
         if (a.pts_cnt != nullptr && lane == 0) a.pts_cnt[gq] = cnt;
-        float* outq = a.pre + gq * a.nsample * a.C1;
+        float* outl = a.pre + gq * a.nsample * a.C1 + 4 * sub;          // this lane's column offset inside the query's block
         for (int r0 = 0; r0 < a.nsample; r0 += 4) {
             const int r = r0 + rsub;
             if (r < a.nsample) {
                 const int j = row[r];
-                const float dx = __ldg(gx + 3 * j) - qx, dy = __ldg(gx + 3 * j + 1) - qy, dz = __ldg(gx + 3 * j + 2) - qz;   // grouped_xyz - new_xyz (pointnet_util.py:46)
-                const float* urow = a.uf ? a.uf + ((size_t)cloud * n + j) * a.C1 : nullptr;
-                float* orow = outq + (size_t)r * a.C1;
+                // grouped_xyz - new_xyz (pointnet_util.py:46), broadcast into both halves of a packed register
+                const float dxs = __ldg(gx + 3 * j) - qx, dys = __ldg(gx + 3 * j + 1) - qy, dzs = __ldg(gx + 3 * j + 2) - qz;
+                const float2 dx = make_float2(dxs, dxs), dy = make_float2(dys, dys), dz = make_float2(dzs, dzs);
+                const float* urow = ucloud ? ucloud + (unsigned)j * (unsigned)a.C1 : nullptr;
+                float* orow = outl + (unsigned)r * (unsigned)a.C1;
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
-                    const int c = 32 * i + 4 * sub;
-                    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (urow) u = __ldg(reinterpret_cast<const float4*>(urow + c));
-                    float4 v;
-                    v.x = fmaf(dz, wz[i].x, fmaf(dy, wy[i].x, fmaf(dx, wx[i].x, u.x))) + bs[i].x;
-                    v.y = fmaf(dz, wz[i].y, fmaf(dy, wy[i].y, fmaf(dx, wx[i].y, u.y))) + bs[i].y;
-                    v.z = fmaf(dz, wz[i].z, fmaf(dy, wy[i].z, fmaf(dx, wx[i].z, u.z))) + bs[i].z;
-                    v.w = fmaf(dz, wz[i].w, fmaf(dy, wy[i].w, fmaf(dx, wx[i].w, u.w))) + bs[i].w;
-                    __stcs(reinterpret_cast<float4*>(orow + c), v);   // streaming store: written once, never re-read here
+                    float2 s0 = bs[2 * i], s1 = bs[2 * i + 1];
+                    if (urow) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(urow + 32 * i));
+                        s0 = __fadd2_rn(s0, make_float2(u.x, u.y)); s1 = __fadd2_rn(s1, make_float2(u.z, u.w));
+                    }
+                    // FFMA2: two channels per instruction
+                    const float2 v0 = __ffma2_rn(dz, wz[2 * i], __ffma2_rn(dy, wy[2 * i], __ffma2_rn(dx, wx[2 * i], s0)));
+                    const float2 v1 = __ffma2_rn(dz, wz[2 * i + 1], __ffma2_rn(dy, wy[2 * i + 1], __ffma2_rn(dx, wx[2 * i + 1], s1)));
+                    __stcs(reinterpret_cast<float4*>(orow + 32 * i), make_float4(v0.x, v0.y, v1.x, v1.y));   // streaming store
                     if (STATS) {
-                        ssum[i].x += v.x; ssum[i].y += v.y; ssum[i].z += v.z; ssum[i].w += v.w;
-                        ssq[i].x = fmaf(v.x, v.x, ssq[i].x); ssq[i].y = fmaf(v.y, v.y, ssq[i].y);
-                        ssq[i].z = fmaf(v.z, v.z, ssq[i].z); ssq[i].w = fmaf(v.w, v.w, ssq[i].w);
+                        ssum[2 * i] = __fadd2_rn(ssum[2 * i], v0); ssum[2 * i + 1] = __fadd2_rn(ssum[2 * i + 1], v1);
+                        ssq[2 * i] = __ffma2_rn(v0, v0, ssq[2 * i]); ssq[2 * i + 1] = __ffma2_rn(v1, v1, ssq[2 * i + 1]);
                     }
                 }
             }
@@ -102,19 +110,17 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
     if (STATS) {
         // the four row-groups of a warp hold partials of the same channels: fold them, then one row-group publishes
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
+        for (int p = 0; p < NPK; ++p) {
 #pragma unroll
             for (int o = 8; o < 32; o <<= 1) {
-                ssum[i].x += __shfl_xor_sync(0xffffffffu, ssum[i].x, o); ssum[i].y += __shfl_xor_sync(0xffffffffu, ssum[i].y, o);
-                ssum[i].z += __shfl_xor_sync(0xffffffffu, ssum[i].z, o); ssum[i].w += __shfl_xor_sync(0xffffffffu, ssum[i].w, o);
-                ssq[i].x += __shfl_xor_sync(0xffffffffu, ssq[i].x, o); ssq[i].y += __shfl_xor_sync(0xffffffffu, ssq[i].y, o);
-                ssq[i].z += __shfl_xor_sync(0xffffffffu, ssq[i].z, o); ssq[i].w += __shfl_xor_sync(0xffffffffu, ssq[i].w, o);
+                ssum[p].x += __shfl_xor_sync(0xffffffffu, ssum[p].x, o); ssum[p].y += __shfl_xor_sync(0xffffffffu, ssum[p].y, o);
+                ssq[p].x += __shfl_xor_sync(0xffffffffu, ssq[p].x, o); ssq[p].y += __shfl_xor_sync(0xffffffffu, ssq[p].y, o);
             }
             if (rsub == 0) {
                 float* w = sstat + (size_t)warp * 2 * a.C1;
-                const int c = 32 * i + 4 * sub;
-                *reinterpret_cast<float4*>(w + c) = ssum[i];
-                *reinterpret_cast<float4*>(w + a.C1 + c) = ssq[i];
+                const int c = 32 * (p >> 1) + 4 * sub + 2 * (p & 1);
+                *reinterpret_cast<float2*>(w + c) = ssum[p];
+                *reinterpret_cast<float2*>(w + a.C1 + c) = ssq[p];
             }
         }
         __syncthreads();
@@ -205,18 +211,24 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
     a.partial = stats ? reinterpret_cast<float*>(ws) : nullptr;
     size_t smem = bq_smem_bytes(n, a.want_grid != 0) + (size_t)kF1Warps * ((nsample + 3) & ~3) * sizeof(int) + (stats ? (size_t)kF1Warps * 2 * C1 * sizeof(float) : 0);
     PSA_SUPPORTED(smem <= 200 * 1024, "sa_conv1_prebn: n=%d exceeds the shared-memory resident limit", n);
-#define PSA_F1_LAUNCH(NP_, ST_)                                                                                              \
+#define PSA_F1_LAUNCH(NV_, ST_, PPT_)                                                                                        \
     do {                                                                                                                     \
-        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_prebn_kernel<NP_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        sa_conv1_prebn_kernel<NP_, ST_><<<grid, kF1Warps * 32, smem, st>>>(a);                                               \
+        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_prebn_kernel<NV_, ST_, PPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sa_conv1_prebn_kernel<NV_, ST_, PPT_><<<grid, kF1Warps * 32, smem, st>>>(a);                                         \
+    } while (0)
+#define PSA_F1_DISPATCH(ST_)                                                                                                 \
+    do {                                                                                                                     \
+        if (n <= 8 * kBqThreads) { if (C1 == 64) PSA_F1_LAUNCH(2, ST_, 8); else PSA_F1_LAUNCH(4, ST_, 8); }                  \
+        else { if (C1 == 64) PSA_F1_LAUNCH(2, ST_, 16); else PSA_F1_LAUNCH(4, ST_, 16); }                                    \
     } while (0)
     // shared memory: ball-query arrays, per-warp idx rows, per-warp statistics (16-byte aligned: nsample rows of ints)
     if (stats) {
-        if (C1 == 64) PSA_F1_LAUNCH(2, true); else PSA_F1_LAUNCH(4, true);
+        PSA_F1_DISPATCH(true);
         f1_stats_reduce_kernel<<<(2 * C1 + 127) / 128, 128, 0, st>>>((int)(grid.x * grid.y), 2 * C1, a.partial, stats);
     } else {
-        if (C1 == 64) PSA_F1_LAUNCH(2, false); else PSA_F1_LAUNCH(4, false);
+        PSA_F1_DISPATCH(false);
     }
+#undef PSA_F1_DISPATCH
 #undef PSA_F1_LAUNCH
     return check_launch("sa_conv1_prebn_kernel");
 }
