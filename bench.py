@@ -278,36 +278,31 @@ def main():
     if rank == 0 and not args.no_extra:
         from scanobjectnn_b200 import dgcnn, pointnet2_cls_bga
 
-        def time_graph(fn, reps=10):
-            """CUDA-graph one forward on a static input, replay `reps` times, device time per forward in ms."""
-            sx = pool_dev[2].clone()
-            s2 = torch.cuda.Stream()
-            s2.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s2):
-                for _ in range(2):
-                    fn(sx)
-            torch.cuda.current_stream().wait_stream(s2)
+        from scanobjectnn_b200.engine import InferenceEngine
+
+        def time_graph(fn, out_shape, reps=12):
+            """The same engine as the main workload (CUDA graph per slot, NSTREAMS batches in flight): ms per forward."""
+            eng = InferenceEngine(fn, (B, N, 3), out_shape, slots=NSTREAMS, device=dev)
+            for i in range(NSTREAMS):
+                eng.submit(pool_dev[(3 + i) % POOL])
             torch.cuda.synchronize()
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                fn(sx)
-            for i in range(3):
-                sx.copy_(pool_dev[(3 + i) % POOL]); g2.replay()
-            torch.cuda.synchronize()
+            main = torch.cuda.current_stream()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0.record(main)
+            eng.fence_begin(e0)
             for i in range(reps):
-                sx.copy_(pool_dev[(7 + i) % POOL]); g2.replay()
-            e1.record()
+                eng.submit(pool_dev[(7 + i) % POOL])
+            eng.fence_end(main)
+            e1.record(main)
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
 
         p_bga = pointnet2_cls_bga.init_params(seed=2, device=dev, randomize_bn=True)
-        ms = time_graph(lambda t: pointnet2_cls_bga.get_model(t, False, params=p_bga))
+        ms = time_graph(lambda t: pointnet2_cls_bga.get_model(t, False, params=p_bga)[0], (B, NUM_CLASS))
         extra["pointnet2_cls_bga"] = {"workload": "inference forward B=32 N=2048 (BASELINE.json configs[3] per-GPU shape)", "ms_per_step": ms,
                                       "clouds_per_s": B / (ms * 1e-3)}
         p_dg = dgcnn.init_params(seed=3, device=dev, randomize_bn=True)
-        ms = time_graph(lambda t: dgcnn.get_model(t, False, params=p_dg), reps=5)
+        ms = time_graph(lambda t: dgcnn.get_model(t, False, params=p_dg)[0], (B, NUM_CLASS), reps=8)
         extra["dgcnn"] = {"workload": "inference forward k=20 B=32 N=2048 (BASELINE.json configs[2])", "ms_per_step": ms,
                           "clouds_per_s": B / (ms * 1e-3)}
         # single ops of the remaining scope rows, event-timed with an L2 flush + spin in front

@@ -102,24 +102,25 @@ knn_topk_kernel(long long rows, int ncols, int k, const float* __restrict__ adj,
 }
 
 // Fused kNN graph: CTA = 64 queries of one cloud against all candidates, 64 at a time.
-//   distances  4x4 register tiles over shared-memory channel chunks, dot / |x|^2 as fma chains over c ascending (the
-//              canonical order of oracle/psa_oracle.c:orc_dgcnn_knn), adj = (sq_i + (-2 dot)) + sq_j -> a 64x64 tile in
-//              shared memory: the (B,N,N) matrix never exists, HBM sees B*(4NC + 4Nk) bytes;
-//   selection  each warp owns 8 query rows; a row's current k best sit sorted in one register per lane; a candidate
-//              enters only if it beats the k-th (strict '<': candidates arrive in index order, so equal values keep the
-//              lower index first, like tf.nn.top_k), found by ballot, placed by popc(ballot(list <= cand)) and a
-//              shuffle-up shift.  Expected insertions per row ~ k(1+ln(N/k)).
-constexpr int kKgQ = 64, kKgC = 64, kKgCk = 32;
+//   distances  4x4 register tiles (4 consecutive rows x 4 consecutive columns per thread) over TRANSPOSED shared-memory
+//              channel chunks, so one LDS.128 feeds four rows / columns; dot and |x|^2 are fma chains over c ascending
+//              (the canonical order of oracle/psa_oracle.c:orc_dgcnn_knn), adj = (sq_i + (-2 dot)) + sq_j -> a 64x64 tile
+//              in shared memory: the (B,N,N) matrix never exists, HBM sees B*(4NC + 4Nk) bytes;
+//   selection  each warp owns 8 query rows whose current k best stay sorted in REGISTERS (one list element per lane) for the
+//              whole kernel.  The first tile is ranked by counting (no insertions); afterwards a candidate enters only if
+//              it beats the k-th (strict '<': candidates arrive in index order, so equal values keep the lower index first,
+//              like tf.nn.top_k), found by ballot, placed by popc(ballot(list <= cand)) and a shuffle-up shift.
+constexpr int kKgQ = 64, kKgC = 64, kKgCk = 32, kKgLd = 68;
 
 __global__ void __launch_bounds__(256)
 knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restrict__ nn_idx) {
-    extern __shared__ float smem_f[];
-    const int cpad = c + 1;
-    float* Xq = smem_f;                                  // [64][c+1]  query features (all channels)
-    float* Xj = Xq + kKgQ * cpad;                        // [64][33]   candidate chunk
-    float* D = Xj + kKgC * (kKgCk + 1);                  // [64][65]   adj tile
-    float* Lv = D + kKgQ * (kKgC + 1);                   // [64][32]   sorted best values
-    int* Li = reinterpret_cast<int*>(Lv + kKgQ * 32);    // [64][32]   and their indices
+    extern __shared__ __align__(16) float smem_f[];
+    const int cq = (c + 3) & ~3;
+    float* XqT = smem_f;                                 // [cq][68]  query features, transposed
+    float* XjT = XqT + (size_t)cq * kKgLd;               // [32][68]  candidate chunk, transposed
+    float* D = XjT + kKgCk * kKgLd;                      // [64][65]  adj tile
+    float* Tv = D + kKgQ * (kKgC + 1);                   // [8 warps][64] scratch for the first-tile ranking
+    int* Ti = reinterpret_cast<int*>(Tv + 8 * 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ty = tid >> 4, tx = tid & 15;
     const int cloud = blockIdx.y, q0 = blockIdx.x * kKgQ;
@@ -127,18 +128,21 @@ knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restri
     const float inf = __int_as_float(0x7f800000);
     for (int sidx = tid; sidx < kKgQ * c; sidx += 256) {
         const int r = sidx / c, l = sidx - r * c;
-        Xq[r * cpad + l] = (q0 + r < n) ? __ldg(xb + (size_t)(q0 + r) * c + l) : 0.f;
+        XqT[l * kKgLd + r] = (q0 + r < n) ? __ldg(xb + (size_t)(q0 + r) * c + l) : 0.f;
     }
-    for (int sidx = tid; sidx < kKgQ * 32; sidx += 256) { Lv[sidx] = inf; Li[sidx] = 0; }
     __syncthreads();
     float sqi[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         float sq = 0.f;
-        const float* q = Xq + (ty + 16 * a) * cpad;
-        for (int l = 0; l < c; ++l) sq = __fmaf_rn(q[l], q[l], sq);
+        for (int l = 0; l < c; ++l) { const float v = XqT[l * kKgLd + ty * 4 + a]; sq = __fmaf_rn(v, v, sq); }
         sqi[a] = sq;
     }
+    float lv[8];          // this lane's element of the sorted list of row warp*8+i
+    int li[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { lv[i] = inf; li[i] = 0; }
+
     for (int j0 = 0; j0 < n; j0 += kKgC) {
         float dot[4][4], sqj[4];
 #pragma unroll
@@ -160,14 +164,14 @@ knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restri
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int sidx = s0 + u * 256, r = sidx / kKgCk, l = sidx - r * kKgCk;
-                    if (sidx < kKgC * kKgCk) Xj[r * (kKgCk + 1) + l] = v[u];
+                    if (sidx < kKgC * kKgCk) XjT[l * kKgLd + r] = v[u];
                 }
             }
             __syncthreads();
             for (int l = 0; l < cc; ++l) {
-                float ai[4], bj[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) { ai[a] = Xq[(ty + 16 * a) * cpad + c0 + l]; bj[a] = Xj[(tx + 16 * a) * (kKgCk + 1) + l]; }
+                const float4 a4 = *reinterpret_cast<const float4*>(XqT + (c0 + l) * kKgLd + ty * 4);
+                const float4 b4 = *reinterpret_cast<const float4*>(XjT + l * kKgLd + tx * 4);
+                const float ai[4] = {a4.x, a4.y, a4.z, a4.w}, bj[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     sqj[a] = __fmaf_rn(bj[a], bj[a], sqj[a]);
@@ -180,20 +184,39 @@ knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restri
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b2 = 0; b2 < 4; ++b2)
-                D[(ty + 16 * a) * (kKgC + 1) + tx + 16 * b2] = __fadd_rn(__fadd_rn(sqi[a], __fmul_rn(-2.0f, dot[a][b2])), sqj[b2]);
+                D[(ty * 4 + a) * (kKgC + 1) + tx * 4 + b2] = __fadd_rn(__fadd_rn(sqi[a], __fmul_rn(-2.0f, dot[a][b2])), sqj[b2]);
         __syncthreads();
         // ---- selection: warp w owns query rows 8w..8w+7 ----
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = warp * 8 + i;
-            if (q0 + r >= n) break;                                        // warp-uniform
-            float lv = Lv[r * 32 + lane];
-            int li = Li[r * 32 + lane];
-            float thr = __shfl_sync(0xffffffffu, lv, k - 1);
+            if (q0 + r >= n) continue;                                     // warp-uniform
+            const float cv0 = D[r * (kKgC + 1) + lane], cv1 = D[r * (kKgC + 1) + 32 + lane];
+            const int ci0 = j0 + lane, ci1 = j0 + 32 + lane;
+            if (j0 == 0) {
+                // first tile: rank every candidate by counting (value, then index) and drop the k best into the list
+                float* tv = Tv + warp * 64;
+                int* ti = Ti + warp * 64;
+                int r0 = 0, r1 = 0;
+                const float v0 = ci0 < n ? cv0 : inf, v1 = ci1 < n ? cv1 : inf;
+                for (int j = 0; j < 64; ++j) {
+                    const float o = (j0 + j < n) ? D[r * (kKgC + 1) + j] : inf;      // broadcast
+                    r0 += (o < v0 || (o == v0 && j < lane)) ? 1 : 0;
+                    r1 += (o < v1 || (o == v1 && j < 32 + lane)) ? 1 : 0;
+                }
+                tv[r0] = v0; ti[r0] = ci0;
+                tv[r1] = v1; ti[r1] = ci1;
+                __syncwarp();
+                lv[i] = lane < k ? tv[lane] : inf;
+                li[i] = lane < k ? ti[lane] : 0;
+                __syncwarp();
+                continue;
+            }
+            float thr = __shfl_sync(0xffffffffu, lv[i], k - 1);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int cj = half * 32 + lane;
-                const float cv = D[r * (kKgC + 1) + cj];
-                const int ci = j0 + cj;
+                const float cv = half ? cv1 : cv0;
+                const int ci = half ? ci1 : ci0;
                 unsigned mask = __ballot_sync(0xffffffffu, ci < n && cv < thr);
                 while (mask) {
                     const int src = __ffs(mask) - 1;
@@ -201,23 +224,21 @@ knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restri
                     const float bv = __shfl_sync(0xffffffffu, cv, src);
                     const int bi = __shfl_sync(0xffffffffu, ci, src);
                     if (!(bv < thr)) continue;                             // the k-th best tightened meanwhile
-                    const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && lv <= bv));
-                    const float pv = __shfl_up_sync(0xffffffffu, lv, 1);
-                    const int pi = __shfl_up_sync(0xffffffffu, li, 1);
-                    if (lane > pos) { lv = pv; li = pi; }
-                    else if (lane == pos) { lv = bv; li = bi; }
-                    if (lane >= k) lv = inf;
-                    thr = __shfl_sync(0xffffffffu, lv, k - 1);
+                    const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && lv[i] <= bv));
+                    const float pv = __shfl_up_sync(0xffffffffu, lv[i], 1);
+                    const int pi = __shfl_up_sync(0xffffffffu, li[i], 1);
+                    if (lane > pos) { lv[i] = pv; li[i] = pi; }
+                    else if (lane == pos) { lv[i] = bv; li[i] = bi; }
+                    if (lane >= k) lv[i] = inf;
+                    thr = __shfl_sync(0xffffffffu, lv[i], k - 1);
                 }
             }
-            Lv[r * 32 + lane] = lv;
-            Li[r * 32 + lane] = li;
         }
     }
-    __syncthreads();
-    for (int sidx = tid; sidx < kKgQ * k; sidx += 256) {
-        const int r = sidx / k, l = sidx - r * k;
-        if (q0 + r < n) nn_idx[((size_t)cloud * n + q0 + r) * k + l] = Li[r * 32 + l];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = warp * 8 + i;
+        if (q0 + r < n && lane < k) nn_idx[((size_t)cloud * n + q0 + r) * k + lane] = li[i];
     }
 }
 
@@ -282,7 +303,7 @@ extern "C" int psa_knn_graph(int b, int n, int c, int k, const float* x, int* nn
     PSA_REQUIRE((x || c == 0) && nn_idx, "knn_graph: null buffer");
     PSA_SUPPORTED(b <= 65535, "knn_graph: b=%d exceeds gridDim.y", b);
     PSA_SUPPORTED(k <= 32, "knn_graph: k=%d exceeds the 32 entries a warp keeps per query", k);
-    size_t smem = ((size_t)kKgQ * (c + 1) + (size_t)kKgC * (kKgCk + 1) + (size_t)kKgQ * (kKgC + 1) + 2 * (size_t)kKgQ * 32) * sizeof(float);
+    size_t smem = ((size_t)((c + 3) & ~3) * kKgLd + (size_t)kKgCk * kKgLd + (size_t)kKgQ * (kKgC + 1) + 2 * 8 * 64) * sizeof(float);
     PSA_SUPPORTED(smem <= 200 * 1024, "knn_graph: c=%d exceeds the shared-memory resident limit", c);
     PSA_CUDA(cudaFuncSetAttribute(knn_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + kKgQ - 1) / kKgQ, b);
