@@ -279,10 +279,14 @@ def main():
         from scanobjectnn_b200 import dgcnn, pointnet2_cls_bga
 
         from scanobjectnn_b200.engine import InferenceEngine
+        from scanobjectnn_b200 import pointnet_cls
 
-        def time_graph(fn, out_shape, reps=12):
+        pool_dev_full = pool_dev
+
+        def time_graph(fn, out_shape, reps=12, bs=B, n=N):
             """The same engine as the main workload (CUDA graph per slot, NSTREAMS batches in flight): ms per forward."""
-            eng = InferenceEngine(fn, (B, N, 3), out_shape, slots=NSTREAMS, device=dev)
+            eng = InferenceEngine(fn, (bs, n, 3), out_shape, slots=NSTREAMS, device=dev)
+            pool_dev = [t[:bs, :n].contiguous() for t in pool_dev_full] if (bs, n) != (B, N) else pool_dev_full
             for i in range(NSTREAMS):
                 eng.submit(pool_dev[(3 + i) % POOL])
             torch.cuda.synchronize()
@@ -305,6 +309,10 @@ def main():
         ms = time_graph(lambda t: dgcnn.get_model(t, False, params=p_dg)[0], (B, NUM_CLASS), reps=8)
         extra["dgcnn"] = {"workload": "inference forward k=20 B=32 N=2048 (BASELINE.json configs[2])", "ms_per_step": ms,
                           "clouds_per_s": B / (ms * 1e-3)}
+        p_pn = pointnet_cls.init_params(seed=4, device=dev, randomize_bn=True)
+        ms = time_graph(lambda t: pointnet_cls.get_model(t, False, params=p_pn)[0], (8, NUM_CLASS), reps=24, bs=8, n=1024)
+        extra["pointnet_cls_vanilla"] = {"workload": "inference forward B=8 N=1024 (BASELINE.json configs[0])", "ms_per_step": ms,
+                                         "clouds_per_s": 8 / (ms * 1e-3)}
         # single ops of the remaining scope rows, event-timed with an L2 flush + spin in front
         xq = pool_dev[5].contiguous()
         feats64 = torch.randn((B, N, 64), device=dev)
@@ -312,7 +320,23 @@ def main():
         _, l1x = ops.farthest_point_sample_and_gather(512, xq)
         f128 = torch.randn((B, 512, 128), device=dev)
         mlp_e = ops.MlpParams([(torch.randn((128, 64), device=dev) * 0.1, torch.ones(64, device=dev), torch.zeros(64, device=dev), True)])
+        f64_512 = torch.randn((B, 512, 64), device=dev)
+        bidx, _ = ops.query_ball_point(0.2, 32, xq, l1x)
+        fidx = ops.farthest_point_sample(512, xq)
+        nn3_d, nn3_i = ops.three_nn(xq, l1x)
+        w3 = torch.full((B, N, 3), 1.0 / 3, device=dev)
+        adj = ops.pairwise_distance(xq)
         opcases = {
+            "farthest_point_sample_2048to512": (lambda: ops.farthest_point_sample(512, xq), None, B * (12 * N + 4 * 512)),
+            "gather_point_512": (lambda: ops.gather_point(xq, fidx), None, B * (12 * N + 4 * 512 + 12 * 512)),
+            "query_ball_point_r0.2_k32": (lambda: ops.query_ball_point(0.2, 32, xq, l1x), None, B * (12 * N + 12 * 512 + 4 * 512 * 32 + 4 * 512)),
+            "group_point_c64_k32": (lambda: ops.group_point(feats64, bidx), None, B * (4 * N * 64 + 4 * 512 * 32 + 4 * 512 * 32 * 64)),
+            "knn_point_k32": (lambda: ops.knn_point(32, xq, l1x), None, B * (12 * N + 12 * 512 + 8 * 512 * 32)),
+            "three_nn_2048from512": (lambda: ops.three_nn(xq, l1x), None, B * (12 * N + 12 * 512 + 24 * N)),
+            "three_interpolate_c128": (lambda: ops.three_interpolate(f128, nn3_i, w3), None, B * (4 * 512 * 128 + 24 * N + 4 * N * 128)),
+            "pairwise_distance_c3": (lambda: ops.pairwise_distance(xq), 2.0 * B * N * N * 3, B * (12 * N + 4 * N * N)),
+            "knn_top20_of_adj": (lambda: ops.knn(adj, 20), None, B * (4 * N * N + 4 * N * 20)),
+            "get_edge_feature_c64_k20": (lambda: ops.get_edge_feature(feats64, nn20, 20), None, B * (4 * N * 64 + 4 * N * 20 + 4 * N * 20 * 128)),
             "knn_graph_c3": (lambda: ops.knn_graph(xq, 20), 2.0 * B * N * N * 3, B * (4 * N * 3 + 4 * N * 20)),
             "knn_graph_c64": (lambda: ops.knn_graph(feats64, 20), 2.0 * B * N * N * 64, B * (4 * N * 64 + 4 * N * 20)),
             "edgeconv_128to64": (lambda: ops.edgeconv_infer(feats64, nn20, mlp_e), 2.0 * B * N * 64 * 128, B * (4 * N * 64 + 4 * N * 20 + 4 * N * 64)),

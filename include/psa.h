@@ -171,7 +171,7 @@ typedef struct psa_mlp {
      * (~45 us per PointNet++ forward).  An image is only used if its tile width / first row match what the entry point
      * needs (psa_mlp_image_plan() tells); otherwise it is ignored and rebuilt. */
     const void* image[PSA_MAX_MLP_LAYERS];
-    int image_nt[PSA_MAX_MLP_LAYERS];      /* output-channel tile width the image was built for (64 or 128) */
+    int image_nt[PSA_MAX_MLP_LAYERS];      /* tile width the image was built for, as returned by psa_mlp_image_plan (64 or 128, | 0x100 = bf16x3 format) */
     int image_row0[PSA_MAX_MLP_LAYERS];    /* first row of weight[l] covered by the image (3 when the xyz rows are split off) */
 } psa_mlp;
 
@@ -222,8 +222,9 @@ PSA_API int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, const 
 
 /* Arithmetic of the grouped MLP.  0 (default): layers after the first run on the tcgen05 tensor cores as a
  * three-term tf32/tf32/bf16 operand split with fp32 accumulation (within 1e-5 of fp64 on O(1) activations) whenever
- * the shapes allow (widths 64/128, last width 64 or a multiple of 128, nsample 32/64/128), fp32 FMA otherwise.
- * 1: always the fp32-FMA kernels. */
+ * the shapes allow (widths 64/128, last width 64 or a multiple of 128, nsample 32/64/128), fp32 FMA otherwise; levels
+ * with a 128-wide layer use the dual-group kernel (three bf16 pieces per operand, six MMAs per product).
+ * 1: always the fp32-FMA kernels.  2: like 0, but 128-wide levels use the older one-tile-per-CTA kernel (A/B runs). */
 PSA_API int psa_set_mlp_mode(int mode);
 PSA_API int psa_get_mlp_mode(void);
 

@@ -127,3 +127,24 @@ def dgcnn_stage(x, k, params, scopes, dtype=np.float64):
     x = np.asarray(x, np.float32)
     idx = orc.dgcnn_knn(x, k)
     return idx, edgeconv(x, idx, params, scopes, dtype)
+
+
+def _tnet(x, params, scope, K, dtype):
+    g = mlp_chain(x, params, [f"{scope}/tconv1", f"{scope}/tconv2", f"{scope}/tconv3"], dtype=dtype).max(axis=1)
+    g = mlp_chain(g, params, [f"{scope}/tfc1", f"{scope}/tfc2"], dtype=dtype)
+    name = "transform_XYZ" if K == 3 else "transform_feat"
+    w = _np(params[f"{scope}/{name}/weights"], dtype)
+    b = _np(params[f"{scope}/{name}/biases"], dtype) + np.eye(K, dtype=dtype).flatten()
+    return (g @ w + b).reshape(-1, K, K)
+
+
+def pointnet_cls(point_cloud, params, dtype=np.float64):
+    """pointnet/models/pointnet_cls.py:21-75, is_training=False -> logits, feature transform."""
+    x = np.asarray(point_cloud, np.float32).astype(dtype)
+    t1 = _tnet(x, params, "transform_net1", 3, dtype)
+    x = x @ t1
+    net = mlp_chain(x, params, ["conv1", "conv2"], dtype=dtype)
+    t2 = _tnet(net, params, "transform_net2", 64, dtype)
+    net = net @ t2
+    net = mlp_chain(net, params, ["conv3", "conv4", "conv5"], dtype=dtype).max(axis=1)
+    return mlp_chain(net, params, ["fc1", "fc2", "fc3"], [True, True, False], dtype), t2

@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
+    *os.environ.get("PSA_EXTRA_NVCC_FLAGS", "").split(),      # debug builds only, e.g. -DPSA_TC_TIMING (tools/tc_timing.py)
 ]
 
 

@@ -6,7 +6,8 @@
 //   * the B operand (weights, [N][K] "K-major") lives in shared memory in the canonical 128-byte-swizzle layout:
 //     8-row x 128-byte atoms, 16-byte chunk index XOR (row % 8), atoms of consecutive 8-row groups 1024 B apart (SBO),
 //     consecutive 128-byte K blocks N*128 B apart;
-//   * one elected thread issues tcgen05.mma and commits to an mbarrier; everybody else waits on its parity.
+//   * one warp runs the issue code converged, its elected lane issues tcgen05.mma and commits to an mbarrier (see MMA
+//     ISSUE CONVENTION below); everybody else waits on the barrier's parity.
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -49,9 +50,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// all previously issued tcgen05.mma of this thread arrive on `bar` when they complete
+// MMA ISSUE CONVENTION.  tcgen05.mma takes its operands from UNIFORM registers.  Issued from `if (tid == 0)` the
+// compiler cannot prove uniformity and wraps every MMA in an ELECT / R2UR.BROADCAST loop (~17 instructions, ~110 cycles
+// per MMA measured -- slower than the 32 / 64 cycles the tensor pipe needs for an N = 64 / 128 instruction,
+// tools/microbench/mma_rate.cu).  So: the WHOLE issuer warp runs the issue code converged, with operands derived from
+// warp-uniform values (kernel parameters, loop counters, `warp_uniform(...)`), and elect.sync picks the lane that
+// executes the instruction.  The elected lane is the same every time (lowest active), so tcgen05.commit tracks its MMAs.
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// all previously issued tcgen05.mma of the elected lane arrive on `bar` when they complete (converged warp)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+        : "memory");
 }
 
 // ---- bulk async copy global -> shared (TMA engine, 1-D, no tensor map), completion on an mbarrier ----
@@ -74,6 +87,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
+// The same descriptor as base + byte offset: the start-address field is (address >> 4), so moving the tile by `off`
+// bytes (a multiple of 16, same 256 KB window) is one add on the low word -- per-MMA descriptor math stays uniform.
+struct SmemDescBase { uint32_t lo, hi; };
+__device__ __forceinline__ SmemDescBase smem_desc_base(uint32_t smem_addr) {
+    SmemDescBase b;
+    b.lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+    b.hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return b;
+}
+__device__ __forceinline__ uint64_t smem_desc_at(SmemDescBase b, uint32_t off) { return ((uint64_t)b.hi << 32) | (uint64_t)(b.lo + (off >> 4)); }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A/B format (2 = tf32, 1 = bf16), both K-major,
 // N >> 3 at [17,23), M >> 4 at [24,29).
 __device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t M, uint32_t N) {
@@ -81,20 +104,22 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t M, u
 }
 constexpr uint32_t kFmtBF16 = 1, kFmtTF32 = 2;
 
-// D[tmem] (+)= A[tmem] * B[smem desc]; accumulate = 0 overwrites D
+// D[tmem] (+)= A[tmem] * B[smem desc]; accumulate = 0 overwrites D.  Call from a CONVERGED warp (see above).
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }

@@ -97,6 +97,7 @@ struct TcArgs {
     int Kd[kMaxTcLayers], Ntot[kMaxTcLayers];
     int stream_last;       // 1: the last layer's weights do not fit next to the others -> one 128-channel tile at a time
     int ntcap;             // 64 (narrow configuration) or 128 (wide)
+    int dual;              // 1: tc_sa_dual_kernel (two row groups per CTA, bf16x3 operands, 64-wide output tiles)
     unsigned int* tile_counter;   // zeroed before the launch: tiles are handed out dynamically (CTAs that start late or
                                   // share their SM with another stream's kernels simply take fewer)
 };
@@ -118,26 +119,41 @@ __device__ __forceinline__ void store_a_chunk(uint32_t row_taddr, int ch, const 
     tmem_st16(row_taddr + ABF_COL + ch * 16, p);
 }
 
-// one elected thread: D[128 x Nt] = A[128 x 64*KC] . W_tile^T as the three-term split over KC resident blocks.
+template <class CFG, int KC, int NT_>
+__device__ __forceinline__ void issue_tile_c(uint32_t tmem_base, uint32_t blocks_addr) {
+    constexpr uint32_t D_COL = CFG::D, AHI_COL = CFG::AHI, ALO_COL = CFG::ALO, ABF_COL = CFG::ABF;
+    // the bases go through a shuffle right here and every offset is a compile-time constant: the operands are provably
+    // warp-uniform and the per-MMA work is a couple of uniform adds
+    const uint32_t tb = warp_uniform(tmem_base);
+    const uint32_t d = tb + D_COL;
+    const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, NT_);
+    const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, NT_);
+    const SmemDescBase b0 = smem_desc_base(warp_uniform(blocks_addr));
+    constexpr uint32_t bb = NT_ * 64u * 6u, kblk = NT_ * 128u, lo_off = NT_ * 256u;
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            mma_bf16_ts(d, tb + ABF_COL + kc * 32 + s * 8, smem_desc_at(b0, kc * bb + lo_off + s * 32), id_bf16, (kc | s) ? 1u : 0u);
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            mma_tf32_ts(d, tb + ALO_COL + kc * 64 + s * 8, smem_desc_at(b0, kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            mma_tf32_ts(d, tb + AHI_COL + kc * 64 + s * 8, smem_desc_at(b0, kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
+}
+
+// issuer warp (converged): D[128 x Nt] = A[128 x 64*KC] . W_tile^T as the three-term split over KC resident blocks.
 // The tensor core truncates (rounds toward zero) every time it adds into D, so the error grows with the number of
 // accumulation steps taken while D is large: the two small correction terms go first, the main term last.
 template <class CFG>
 __device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t blocks_addr, int KC, int Nt) {
-    constexpr uint32_t D_COL = CFG::D, AHI_COL = CFG::AHI, ALO_COL = CFG::ALO, ABF_COL = CFG::ABF;
-    const uint32_t d = tmem_base + D_COL;
-    const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, Nt);
-    const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, Nt);
-    const uint32_t bb = (uint32_t)Nt * 64u * 6u, kblk = (uint32_t)Nt * 128u, lo_off = (uint32_t)Nt * 256u;
-    uint32_t acc = 0;
-    for (int kc = 0; kc < KC; ++kc)
-        for (int s = 0; s < 4; ++s, acc = 1)
-            mma_bf16_ts(d, tmem_base + ABF_COL + kc * 32 + s * 8, make_smem_desc_sw128(blocks_addr + kc * bb + lo_off + s * 32), id_bf16, acc);
-    for (int kc = 0; kc < KC; ++kc)
-        for (int s = 0; s < 8; ++s)
-            mma_tf32_ts(d, tmem_base + ALO_COL + kc * 64 + s * 8, make_smem_desc_sw128(blocks_addr + kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
-    for (int kc = 0; kc < KC; ++kc)
-        for (int s = 0; s < 8; ++s)
-            mma_tf32_ts(d, tmem_base + AHI_COL + kc * 64 + s * 8, make_smem_desc_sw128(blocks_addr + kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
+    if (Nt == 64) { if (KC == 1) issue_tile_c<CFG, 1, 64>(tmem_base, blocks_addr); else issue_tile_c<CFG, 2, 64>(tmem_base, blocks_addr); }
+    else          { if (KC == 1) issue_tile_c<CFG, 1, 128>(tmem_base, blocks_addr); else issue_tile_c<CFG, 2, 128>(tmem_base, blocks_addr); }
 }
 
 // transposing butterfly: v[q] = column q of this lane's row; afterwards v[0] on lane l = max over the warp's 32 rows of column l
@@ -179,6 +195,14 @@ __host__ __device__ inline TcSmemLayout tc_layout(const TcArgs& a) {
     return L;
 }
 
+#ifdef PSA_TC_TIMING
+// debug build only (tools/tc_timing.py): cycles thread 0 of every CTA spends in each phase of tc_sa_kernel
+__device__ unsigned long long g_tc_timing[8];
+#define TC_STAMP(i) do { if (tid == 0) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tprev); tprev = now_; } } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
+
 template <bool NARROW>
 __global__ void __launch_bounds__(TcCfg<NARROW>::kThreads, TcCfg<NARROW>::kMinBlocks)
 tc_sa_kernel(const __grid_constant__ TcArgs a) {
@@ -187,12 +211,14 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
     constexpr uint32_t D_COL = CFG::D;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;     // MMA completion
-    __shared__ __align__(8) uint64_t s_wbar;     // weight bulk copies landed
+    __shared__ __align__(8) uint64_t s_wbar;     // a tile of the streamed last layer landed in the ring
+    __shared__ __align__(8) uint64_t s_rbar;     // resident weights landed (once)
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kTcThreads / 32][32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quarter = warp & 3, cs = warp >> 2;      // rows 32*quarter.., column-chunk slot
+    const int warp_u = (int)warp_uniform((uint32_t)warp);   // provably warp-uniform copy: warp 0 is the MMA issuer
+    const int quarter = warp_u & 3, cs = warp_u >> 2;  // rows 32*quarter.., column-chunk slot
     const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const TcSmemLayout L = tc_layout(a);
@@ -200,7 +226,7 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
 
     // ---- one-time setup: TMEM, barriers, resident weights (bulk copies), per-channel vectors ----
     if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar, 1); mbar_init(&s_rbar, 1); fence_mbar_init(); }
     float* vec = reinterpret_cast<float*>(base + L.vec);
     float* w1x = vec;                       // 3*C1
     float* s1 = vec + 3 * a.C1;
@@ -219,28 +245,33 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
             tl[l][i] = __ldg(a.t[l] + i);
         }
     __syncthreads();                          // barrier inits visible before anybody arms / waits
+    // Ring protocol (streamed last layer): exactly one fill is outstanding or landed before every issue of that layer --
+    // the first one starts here, each later one right after the MMAs that read the ring have completed, and only if
+    // another issue follows (`more`), so nothing is in flight when the CTA exits.  No "pending" flag: the issuer warp's
+    // control flow stays trivially uniform (a loop-carried flag made the compiler clone the issue code onto a path it
+    // treats as divergent, which costs ~4 R2UR + ELECT per MMA).
     uint32_t wphase = 0;
     const uint32_t ring_bytes = (uint32_t)(a.Kd[last] / 64) * tc_block_bytes(tc_nt(a.Ntot[last], CFG::kNtCap));   // one n-tile of the last layer
     if (tid == 0) {
         uint32_t total = 0;
-        for (int l = 0; l < a.nl; ++l) total += (a.stream_last && l == last) ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
-        mbar_expect_tx(&s_wbar, total);
+        for (int l = 0; l < a.nl; ++l)
+            if (!(a.stream_last && l == last)) total += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+        if (total) mbar_expect_tx(&s_rbar, total);
+        if (a.stream_last) mbar_expect_tx(&s_wbar, ring_bytes);
         for (int l = 0; l < a.nl; ++l) {
-            const uint32_t bytes = (a.stream_last && l == last) ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+            const bool st_ = a.stream_last && l == last;
+            const uint32_t bytes = st_ ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
             for (uint32_t o = 0; o < bytes; o += 32768u)       // bulk copies of <= 32 KB
-                bulk_g2s(base + L.w[l] + o, a.image[l] + o, min(32768u, bytes - o), &s_wbar);
+                bulk_g2s(base + L.w[l] + o, a.image[l] + o, min(32768u, bytes - o), st_ ? &s_wbar : &s_rbar);
         }
-        mbar_wait(&s_wbar, wphase);
+        if (total) mbar_wait(&s_rbar, 0);
     }
-    wphase ^= 1u;
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
-    const uint32_t tmem_base = s_tmem;
+    const uint32_t tmem_base = warp_uniform(s_tmem);
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0;
-    int ring_tile = 0;                        // which n-tile of the last layer the ring currently holds / is receiving
-    bool ring_pending = false;                // thread 0: a ring load is in flight
 
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
@@ -248,7 +279,15 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
     if (tid == 0) s_tile[0] = atomicAdd(a.tile_counter, 1u);
     __syncthreads();
     int tpar = 0;
-    for (long long tile = s_tile[0]; tile < ntiles; tile = s_tile[tpar]) {
+#ifdef PSA_TC_TIMING
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#endif
+    // (the tile index goes through a shuffle so that the compiler sees a warp-uniform loop: MMA issue stays on the uniform path)
+    for (long long tile = warp_uniform(s_tile[0]); tile < ntiles; tile = warp_uniform(s_tile[tpar])) {
+#ifdef PSA_TC_TIMING
+        if (tid == 0) tacc[7] += 1;
+#endif
         // thread 0 claims the NEXT tile now; everybody reads it after this tile's barriers (s_tile is double-buffered)
         long long next_tile = 0;
         if (tid == 0) { const unsigned int t = atomicAdd(a.tile_counter, 1u); s_tile[tpar ^ 1] = t; next_tile = t; }
@@ -302,30 +341,38 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
         tmem_st_wait();
         fence_before_thread_sync();
         __syncthreads();
+        TC_STAMP(0);
         for (int l = 0; l < a.nl; ++l) {
-            const int Nt = tc_nt(a.Ntot[l], CFG::kNtCap);
-            const int NT = a.Ntot[l] / Nt, KC = a.Kd[l] / 64;
+            // (per-layer shapes are indexed dynamically out of the parameter struct: through a shuffle, so that the
+            //  branches on them -- and the MMA issue inside -- stay on the warp-uniform path)
+            const int Nt = (int)warp_uniform((uint32_t)tc_nt(a.Ntot[l], CFG::kNtCap));
+            const int NT = (int)warp_uniform((uint32_t)a.Ntot[l]) / Nt, KC = (int)warp_uniform((uint32_t)a.Kd[l]) / 64;
             const bool streamed = a.stream_last && l == last;
             for (int nt = 0; nt < NT; ++nt) {
-                if (tid == 0) {
-                    if (streamed && ring_pending) { mbar_wait(&s_wbar, wphase); wphase ^= 1u; ring_pending = false; }
+                if (warp_u == 0) {                  // converged warp, elected lane issues (tc_common.cuh)
+                    // this tile's weights are in the ring / resident (an UNCONDITIONAL wait -- on the long-completed
+                    // resident barrier when nothing is streamed -- keeps the compiler's view of this warp converged)
+                    mbar_wait(streamed ? &s_wbar : &s_rbar, streamed ? wphase : 0u);
+                    wphase ^= streamed ? 1u : 0u;
+                    __syncwarp();
                     fence_after_thread_sync();
                     const uint32_t blocks = smem_u32(base + L.w[l]) + (streamed ? 0u : (uint32_t)nt * KC * tc_block_bytes(Nt));
                     issue_tile<CFG>(tmem_base, blocks, KC, Nt);
                     mma_commit(&s_mbar);
                 }
+                TC_STAMP(l == last ? 4 : 1);
                 mbar_wait(&s_mbar, phase);
                 phase ^= 1u;
                 fence_after_thread_sync();
-                if (tid == 0 && streamed && NT > 1) {
-                    // the ring is free again: fetch the next 128-channel tile (wrapping to tile 0 for the next row tile)
-                    const bool more = (nt + 1 < NT) || (next_tile < ntiles);
-                    if (more) {
-                        ring_tile = (nt + 1) % NT;
+                TC_STAMP(l == last ? 5 : 2);
+                if (warp_u == 0 && streamed) {
+                    // the ring is free again: fetch the next tile (wrapping to tile 0 for the next row tile) if one follows
+                    const bool more = (nt + 1 < NT) || (__shfl_sync(0xffffffffu, next_tile, 0) < ntiles);
+                    if (more && lane == 0) {
+                        const int ring_tile = (nt + 1) % NT;
                         mbar_expect_tx(&s_wbar, ring_bytes);
                         for (uint32_t o = 0; o < ring_bytes; o += 32768u)
                             bulk_g2s(base + L.w[l] + o, a.image[l] + (size_t)ring_tile * ring_bytes + o, min(32768u, ring_bytes - o), &s_wbar);
-                        ring_pending = true;
                     }
                 }
                 if (l != last) {
@@ -350,6 +397,7 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
                     tmem_st_wait();
                     fence_before_thread_sync();
                     __syncthreads();
+                    TC_STAMP(3);
                 } else {
                     // rows of one neighbourhood span K/32 lane-quarters; warps sharing a chunk slot combine through s_red
                     const int quarters_per_group = a.K / 32;        // 1, 2 or 4
@@ -389,13 +437,372 @@ tc_sa_kernel(const __grid_constant__ TcArgs a) {
                     // D fully read by every warp before thread 0 may issue the next MMAs into it
                     fence_before_thread_sync();
                     __syncthreads();
+                    TC_STAMP(6);
                 }
             }
         }
     }
-    if (tid == 0 && ring_pending) mbar_wait(&s_wbar, wphase);     // never leave a bulk copy in flight
-    __syncthreads();
+#ifdef PSA_TC_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_timing[i], tacc[i]);
+#endif
+    __syncthreads();                          // (no ring fill is in flight here: see the ring protocol above)
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// tc_sa_dual_kernel -- levels with 128-wide layers (PointNet++ SA2: 131 -> 128 -> 128 -> 256 over 64-point neighbourhoods).
+//
+// tc_sa_kernel serialises "row work" (gather, BN/ReLU, operand split, max-pool: ~56 % of a tile) and the MMAs (~44 %),
+// and hides one behind the other only by putting TWO CTAs on an SM -- which needs the level to fit twice: 256 TMEM
+// columns and half the shared memory per CTA.  A 128-wide layer does not (A operand = 320 columns, W2 = 96 KB), so
+// the wide configuration ran one CTA per SM with the tensor pipe idle during row work and vice versa.
+// This kernel gets the overlap back inside ONE CTA:
+//   * two independent ROW GROUPS of 8 warps, each with its own 128-row tile, its own 256 TMEM columns, its own MMA
+//     issuer (thread 0 of the group), mbarriers, named barrier and tile claims; while one group gathers / pools, the
+//     other group's MMAs run;
+//   * the weights of the inner layer are resident ONCE and shared by both groups; a last layer that does not fit is
+//     streamed per group, one 64-channel tile (48 KB) at a time, L2 -> shared memory during the previous epilogue;
+//   * operands are split into three bf16 pieces each (a = a1 + a2 + a3, w = w1 + w2 + w3, every piece exact): the A
+//     operand of a K = 128 layer is 192 TMEM columns instead of 320, so that A + a 64-column D fit in a group's 256.
+//     Six bf16 MMAs  a1w3 + a2w2 + a3w1 + a1w2 + a2w1 + a1w1  (small terms first: the accumulator add truncates)
+//     reproduce the fp32 product to ~2^-25; weights stay at 6 bytes per element.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kImageBf16x3 = 0x100;      // flag in psa_mlp.image_nt / psa_mlp_image_plan: image holds three bf16 pieces
+
+__global__ void tc_prep_weights3_kernel(int K, int Kp, int N, int Nt, const float* __restrict__ W, uint8_t* __restrict__ image) {
+    const int KC = Kp / 64;
+    const uint32_t bb = tc_block_bytes(Nt), piece = (uint32_t)Nt * 128u;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Kp * N; e += gridDim.x * blockDim.x) {
+        const int n = e % N, k = e / N;
+        const float w = k < K ? __ldg(W + e) : 0.f;
+        const __nv_bfloat16 c1 = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(c1);
+        const __nv_bfloat16 c2 = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(c2);
+        const __nv_bfloat16 c3 = __float2bfloat16_rn(r2);
+        uint8_t* blk = image + (size_t)((n / Nt) * KC + (k >> 6)) * bb;
+        const uint32_t off = swz_off_bf16(n % Nt, k & 63, Nt);
+        *reinterpret_cast<__nv_bfloat16*>(blk + off) = c1;
+        *reinterpret_cast<__nv_bfloat16*>(blk + piece + off) = c2;
+        *reinterpret_cast<__nv_bfloat16*>(blk + 2u * piece + off) = c3;
+    }
+}
+
+struct TcDual {
+    static constexpr int kThreads = 512, kGroupThreads = 256, kGroupCols = 256, kNt = 64;
+    static constexpr uint32_t D = 0, A1 = 64, A2 = 128, A3 = 192;
+};
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;\n" ::"r"(g + 1) : "memory"); }
+
+// split 32 activations into three bf16 pieces and store them as the A operand (h is clobbered)
+__device__ __forceinline__ void store_a3_chunk(uint32_t row_taddr, int ch, float (&h)[32]) {
+    uint32_t p[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+        h[2 * q] -= __uint_as_float(p[q] << 16);
+        h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
+    }
+    tmem_st16(row_taddr + TcDual::A1 + ch * 16, p);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+        h[2 * q] -= __uint_as_float(p[q] << 16);
+        h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
+    }
+    tmem_st16(row_taddr + TcDual::A2 + ch * 16, p);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+    tmem_st16(row_taddr + TcDual::A3 + ch * 16, p);
+}
+
+// issuer warp (converged): D[128 x 64] = sum over the six piece pairs, KC resident blocks of 64 input channels
+template <int KC>
+__device__ __forceinline__ void issue_tile3_c(uint32_t gbase, uint32_t blocks_addr) {
+    constexpr uint32_t Nt = TcDual::kNt, bb = Nt * 384u, piece = Nt * 128u;
+    const uint32_t tb = warp_uniform(gbase);
+    const uint32_t d = tb + TcDual::D;
+    const uint32_t idesc = make_idesc(kFmtBF16, 128, Nt);
+    const SmemDescBase b0 = smem_desc_base(warp_uniform(blocks_addr));
+    constexpr uint32_t acol[6] = {TcDual::A1, TcDual::A2, TcDual::A3, TcDual::A1, TcDual::A2, TcDual::A1};
+    constexpr uint32_t wp[6] = {2, 1, 0, 1, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 6; ++t)
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4)
+                mma_bf16_ts(d, tb + acol[t] + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + wp[t] * piece + s4 * 32), idesc, (t | kc | s4) ? 1u : 0u);
+}
+__device__ __forceinline__ void issue_tile3(uint32_t gbase, uint32_t blocks_addr, int KC) {
+    if (KC == 1) issue_tile3_c<1>(gbase, blocks_addr); else issue_tile3_c<2>(gbase, blocks_addr);
+}
+
+struct TcDualLayout {
+    uint32_t w[kMaxTcLayers];    // resident layers
+    uint32_t ring[2];            // per-group ring (one 64-channel tile of the streamed last layer)
+    uint32_t ring_bytes;
+    uint32_t vec, total;
+};
+
+__host__ __device__ inline TcDualLayout tc_dual_layout(const TcArgs& a) {
+    TcDualLayout L;
+    uint32_t off = 0;
+    for (int l = 0; l < a.nl; ++l) {
+        L.w[l] = off;
+        if (!(a.stream_last && l == a.nl - 1)) off += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+    }
+    L.ring_bytes = a.stream_last ? (uint32_t)(a.Kd[a.nl - 1] / 64) * tc_block_bytes(TcDual::kNt) : 0u;
+    L.ring[0] = off; off += L.ring_bytes;
+    L.ring[1] = off; off += L.ring_bytes;
+    L.vec = off;
+    off += 5u * a.C1 * 4u;
+    for (int l = 0; l < a.nl; ++l) off += 2u * a.Ntot[l] * 4u;
+    L.total = off;
+    return L;
+}
+
+// D chunk (32 columns of this lane's row) -> relu?(d * scale + shift), `fill` for rows past the end
+__device__ __forceinline__ void affine_chunk(const uint32_t (&d)[32], const float* __restrict__ sc_, const float* __restrict__ sh_, int relu,
+                                             bool valid, float fill, float (&h)[32]) {
+    const float4* s4 = reinterpret_cast<const float4*>(sc_);
+    const float4* t4 = reinterpret_cast<const float4*>(sh_);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 sc = s4[q], sh = t4[q];
+        float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
+        float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
+        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        h[4 * q + 0] = valid ? v0 : fill; h[4 * q + 1] = valid ? v1 : fill;
+        h[4 * q + 2] = valid ? v2 : fill; h[4 * q + 3] = valid ? v3 : fill;
+    }
+}
+
+__global__ void __launch_bounds__(TcDual::kThreads, 1)
+tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
+    constexpr int kNt = TcDual::kNt;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar[2];  // MMA completion, per group
+    __shared__ __align__(8) uint64_t s_wbar[2];  // ring tile landed, per group
+    __shared__ __align__(8) uint64_t s_rbar;     // resident weights landed
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[TcDual::kThreads / 32][32];
+    __shared__ unsigned int s_tile[2][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_u = (int)warp_uniform((uint32_t)warp);
+    const int g = warp_u >> 3, gtid = tid & 255;
+    const bool issuer = (warp_u & 7) == 0;    // first warp of each group: converged MMA issue (tc_common.cuh), ring refills
+    const int quarter = warp_u & 3, cs = (warp_u >> 2) & 1;
+    const int row = quarter * 32 + lane;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const TcDualLayout L = tc_dual_layout(a);
+    const int last = a.nl - 1;
+
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_init(&s_wbar[0], 1); mbar_init(&s_wbar[1], 1); mbar_init(&s_rbar, 1);
+        fence_mbar_init();
+    }
+    float* vec = reinterpret_cast<float*>(base + L.vec);
+    float* w1x = vec;
+    float* s1 = vec + 3 * a.C1;
+    float* t1 = s1 + a.C1;
+    float* sl[kMaxTcLayers];
+    float* tl[kMaxTcLayers];
+    {
+        float* p = t1 + a.C1;
+        for (int l = 0; l < a.nl; ++l) { sl[l] = p; tl[l] = p + a.Ntot[l]; p += 2 * a.Ntot[l]; }
+    }
+    for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) w1x[i] = __ldg(a.w1x + i);
+    for (int i = tid; i < a.C1; i += TcDual::kThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
+    for (int l = 0; l < a.nl; ++l)
+        for (int i = tid; i < a.Ntot[l]; i += TcDual::kThreads) {
+            sl[l][i] = a.s[l] ? __ldg(a.s[l] + i) : 1.f;
+            tl[l][i] = __ldg(a.t[l] + i);
+        }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int l = 0; l < a.nl; ++l)
+            if (!(a.stream_last && l == last)) total += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+        if (total) {
+            mbar_expect_tx(&s_rbar, total);
+            for (int l = 0; l < a.nl; ++l) {
+                if (a.stream_last && l == last) continue;
+                const uint32_t bytes = (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+                for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(base + L.w[l] + o, a.image[l] + o, min(32768u, bytes - o), &s_rbar);
+            }
+            mbar_wait(&s_rbar, 0);
+        }
+    }
+    // ring protocol as in tc_sa_kernel: one fill outstanding or landed before every issue of the streamed layer
+    uint32_t wphase = 0;
+    if (issuer && a.stream_last && lane == 0) {
+        mbar_expect_tx(&s_wbar[g], L.ring_bytes);
+        for (uint32_t o = 0; o < L.ring_bytes; o += 32768u) bulk_g2s(base + L.ring[g] + o, a.image[last] + o, min(32768u, L.ring_bytes - o), &s_wbar[g]);
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = warp_uniform(s_tmem) + (uint32_t)g * TcDual::kGroupCols;
+    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t phase = 0;
+
+    const int G = 128 / a.K;
+    const long long ntiles = (a.groups + G - 1) / G;
+    if (gtid == 0) s_tile[g][0] = atomicAdd(a.tile_counter, 1u);
+    group_bar(g);
+    int tpar = 0;
+#ifdef PSA_TC_TIMING
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#endif
+    for (long long tile = warp_uniform(s_tile[g][0]); tile < ntiles; tile = warp_uniform(s_tile[g][tpar])) {
+#ifdef PSA_TC_TIMING
+        if (tid == 0) tacc[7] += 1;
+#endif
+        long long next_tile = 0;
+        if (gtid == 0) { const unsigned int t = atomicAdd(a.tile_counter, 1u); s_tile[g][tpar ^ 1] = t; next_tile = t; }
+        tpar ^= 1;
+        const long long g0 = tile * G;
+        const long long gid = g0 + row / a.K;
+        const bool valid = gid < a.groups;
+        // ---- layer 1 on the FMA pipe, straight into the A operand ----
+        {
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            const float* urow = nullptr;
+            if (valid) {
+                const long long bi = gid / a.m;
+                const int j = __ldg(a.idx + gid * a.K + (row % a.K));
+                const float* p = a.xyz + ((size_t)bi * a.n + j) * 3;
+                const float* c = a.new_xyz + (size_t)gid * 3;
+                dx = __ldg(p) - __ldg(c); dy = __ldg(p + 1) - __ldg(c + 1); dz = __ldg(p + 2) - __ldg(c + 2);
+                if (a.uf) urow = a.uf + ((size_t)bi * a.n + j) * a.C1;
+            }
+            for (int ch = cs; ch < a.C1 / 32; ch += 2) {
+                float h[32];
+                if (urow) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(urow + ch * 32) + q);
+                        h[4 * q] = u.x; h[4 * q + 1] = u.y; h[4 * q + 2] = u.z; h[4 * q + 3] = u.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) h[q] = 0.f;
+                }
+                const float4* wx4 = reinterpret_cast<const float4*>(w1x + ch * 32);
+                const float4* wy4 = reinterpret_cast<const float4*>(w1x + a.C1 + ch * 32);
+                const float4* wz4 = reinterpret_cast<const float4*>(w1x + 2 * a.C1 + ch * 32);
+                const float4* s4 = reinterpret_cast<const float4*>(s1 + ch * 32);
+                const float4* t4 = reinterpret_cast<const float4*>(t1 + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 wx = wx4[q], wy = wy4[q], wz = wz4[q], sc = s4[q], sh = t4[q];
+                    float v0 = fmaf(fmaf(dz, wz.x, fmaf(dy, wy.x, fmaf(dx, wx.x, h[4 * q + 0]))), sc.x, sh.x);
+                    float v1 = fmaf(fmaf(dz, wz.y, fmaf(dy, wy.y, fmaf(dx, wx.y, h[4 * q + 1]))), sc.y, sh.y);
+                    float v2 = fmaf(fmaf(dz, wz.z, fmaf(dy, wy.z, fmaf(dx, wx.z, h[4 * q + 2]))), sc.z, sh.z);
+                    float v3 = fmaf(fmaf(dz, wz.w, fmaf(dy, wy.w, fmaf(dx, wx.w, h[4 * q + 3]))), sc.w, sh.w);
+                    if (a.relu1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                    h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
+                    h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
+                }
+                store_a3_chunk(row_taddr, ch, h);
+            }
+        }
+        tmem_st_wait();
+        fence_before_thread_sync();
+        group_bar(g);
+        TC_STAMP(0);
+        for (int l = 0; l < a.nl; ++l) {
+            const int NT = (int)warp_uniform((uint32_t)a.Ntot[l]) / kNt, KC = (int)warp_uniform((uint32_t)a.Kd[l]) / 64;
+            if (l != last) {
+                // inner layer, one or two 64-wide tiles: the next A operand may only be written once ALL MMAs of this
+                // layer are done reading the current one, so the first tile's activations wait in registers
+                float h0[32], h1[32];
+                for (int nt = 0; nt < NT; ++nt) {
+                    if (issuer) {
+                        fence_after_thread_sync();
+                        issue_tile3(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt), KC);
+                        mma_commit(&s_mbar[g]);
+                    }
+                    TC_STAMP(1);
+                    mbar_wait(&s_mbar[g], phase);
+                    phase ^= 1u;
+                    fence_after_thread_sync();
+                    TC_STAMP(2);
+                    uint32_t d[32];
+                    tmem_ld32(row_taddr + TcDual::D + cs * 32, d);
+                    tmem_ld_wait();
+                    if (nt == 0) affine_chunk(d, sl[l] + cs * 32, tl[l] + cs * 32, a.relu[l], valid, 0.f, h0);
+                    else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], valid, 0.f, h1);
+                    if (nt + 1 < NT) { fence_before_thread_sync(); group_bar(g); }       // D drained before the next tile lands in it
+                }
+                store_a3_chunk(row_taddr, cs, h0);
+                if (NT == 2) store_a3_chunk(row_taddr, 2 + cs, h1);
+                tmem_st_wait();
+                fence_before_thread_sync();
+                group_bar(g);
+                TC_STAMP(3);
+            } else {
+                const bool streamed = a.stream_last != 0;
+                const int quarters_per_group = a.K / 32;        // 1, 2 or 4
+                const long long wg = g0 + (quarter * 32) / a.K; // this warp's neighbourhood
+                for (int nt = 0; nt < NT; ++nt) {
+                    if (issuer) {
+                        if (streamed) { mbar_wait(&s_wbar[g], wphase); wphase ^= 1u; }
+                        __syncwarp();               // re-converge after the spin wait: the issue below must be warp-uniform
+                        fence_after_thread_sync();
+                        const uint32_t blocks = streamed ? smem_u32(base + L.ring[g]) : smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt);
+                        issue_tile3(tmem_base, blocks, KC);
+                        mma_commit(&s_mbar[g]);
+                    }
+                    TC_STAMP(4);
+                    mbar_wait(&s_mbar[g], phase);
+                    phase ^= 1u;
+                    fence_after_thread_sync();
+                    TC_STAMP(5);
+                    if (issuer && streamed) {
+                        // the ring is free again: fetch the next tile (wrapping to tile 0 for the group's next row tile)
+                        const bool more = (nt + 1 < NT) || (__shfl_sync(0xffffffffu, next_tile, 0) < ntiles);
+                        if (more && lane == 0) {
+                            const int rt = (nt + 1) % NT;
+                            mbar_expect_tx(&s_wbar[g], L.ring_bytes);
+                            for (uint32_t o = 0; o < L.ring_bytes; o += 32768u)
+                                bulk_g2s(base + L.ring[g] + o, a.image[l] + (size_t)rt * L.ring_bytes + o, min(32768u, L.ring_bytes - o), &s_wbar[g]);
+                        }
+                    }
+                    uint32_t d[32];
+                    tmem_ld32(row_taddr + TcDual::D + cs * 32, d);
+                    tmem_ld_wait();
+                    float v[32];
+                    affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], valid, -FLT_MAX, v);
+                    float mx = warp_colmax_32x32(v, lane);
+                    if (quarters_per_group > 1) {
+                        s_red[warp][lane] = mx;
+                        group_bar(g);
+                        if ((quarter % quarters_per_group) == 0)
+                            for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
+                    }
+                    if ((quarter % quarters_per_group) == 0 && wg < a.groups)
+                        a.out[(size_t)wg * a.Ntot[l] + nt * kNt + cs * 32 + lane] = mx;
+                    // D fully read (and s_red consumed) by every warp of the group before the next MMAs / maxima land
+                    fence_before_thread_sync();
+                    group_bar(g);
+                    TC_STAMP(6);
+                }
+            }
+        }
+    }
+#ifdef PSA_TC_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_timing[i], tacc[i]);
+#endif
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(s_tmem, 512);
 }
 
 // ---- self-test of one tensor layer: D[128 x N] = A[128 x K] . W[K x N] through exactly the device code above ----
@@ -409,7 +816,8 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __
     __shared__ __align__(8) uint64_t s_wbar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quarter = warp & 3, cs = warp >> 2;
+    const int warp_u = (int)warp_uniform((uint32_t)warp);
+    const int quarter = warp_u & 3, cs = warp_u >> 2;
     const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
@@ -424,7 +832,7 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
-    const uint32_t tmem_base = s_tmem;
+    const uint32_t tmem_base = warp_uniform(s_tmem);
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int ch = cs; ch < Kd / 32; ch += kTcChunkWarps) {
         float h[32];
@@ -435,7 +843,7 @@ tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __
     tmem_st_wait();
     fence_before_thread_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {
         fence_after_thread_sync();
         issue_tile<CFG>(tmem_base, smem_u32(base), Kd / 64, tc_nt(N, 128));
         mma_commit(&s_mbar);
@@ -489,7 +897,8 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kTcThreads / 32][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int quarter = warp & 3, cs = warp >> 2;
+    const int warp_u = (int)warp_uniform((uint32_t)warp);
+    const int quarter = warp_u & 3, cs = warp_u >> 2;
     const int row = quarter * 32 + lane;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int Nt = tc_nt(a.N, CFG::kNtCap), KCtot = a.Kp / 64;
@@ -517,7 +926,7 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
-    const uint32_t tmem_base = s_tmem;
+    const uint32_t tmem_base = warp_uniform(s_tmem);
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0;
     const bool vec_ok = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
@@ -548,12 +957,12 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
         tmem_st_wait();
         fence_before_thread_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {                      // converged warp, elected lane issues (tc_common.cuh)
             mbar_wait(&s_wbar[sg & 1], (uint32_t)((sg >> 1) & 1));
             fence_after_thread_sync();
             issue_tile<CFG>(tmem_base, smem_u32(base + (sg & 1) * slot_bytes), kcs, Nt);
             mma_commit(&s_mbar);
-            if (sg + 1 < nseg) load_seg(sg + 1);    // the other slot's MMAs (segment sg-1) completed before this segment began
+            if (lane == 0 && sg + 1 < nseg) load_seg(sg + 1);    // the other slot's MMAs (segment sg-1) completed before this segment began
         }
         mbar_wait(&s_mbar, phase);
         phase ^= 1u;
@@ -633,6 +1042,7 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
 size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
 
 static int g_tc_dense_narrow = 1;
+static int g_tc_sa_dual = 1;      // 0: 128-wide levels fall back to the one-tile-per-CTA wide kernel (psa_set_mlp_mode(2), A/B runs)
 int tc_dense_nt(int N) { return tc_nt(N, g_tc_dense_narrow ? 64 : 128); }
 
 // `image`: workspace to build the weight image in, or -- when `prebuilt` -- an image that already holds it
@@ -666,10 +1076,15 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
 
 
 // A prebuilt image (psa_prepare_weight_image) is used when it matches; otherwise the image is (re)built into `ws`.
+// `Nt` may carry kImageBf16x3 (three-bf16-piece image for tc_sa_dual_kernel).
+static void build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st) {
+    if (Nt & kImageBf16x3) tc_prep_weights3_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt & ~kImageBf16x3, W, image);
+    else tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, image);
+}
 static const uint8_t* use_or_build_image(const psa_mlp* mlp, int l, int row0, int N, int Nt, uint8_t* ws, cudaStream_t st) {
     if (mlp->image[l] != nullptr && mlp->image_nt[l] == Nt && mlp->image_row0[l] == row0) return reinterpret_cast<const uint8_t*>(mlp->image[l]);
     const int K = mlp->channels[l] - row0, Kp = (K + 63) & ~63;
-    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, mlp->weight[l] + (size_t)row0 * N, ws);
+    build_image(K, Kp, N, Nt, mlp->weight[l] + (size_t)row0 * N, ws, st);
     return ws;
 }
 
@@ -695,6 +1110,13 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
     }
     bool all64 = (C1 == 64);
     for (int l = 0; l < a.nl; ++l) all64 = all64 && a.Kd[l] == 64;
+    if (g_tc_sa_dual) {
+        // two row groups per CTA, bf16x3 operands, 64-wide tiles; the last layer is streamed per group if it does not fit
+        a.dual = 1; a.ntcap = 64; a.stream_last = 0;
+        if (tc_dual_layout(a).total + 1024 > 226u * 1024u) a.stream_last = 1;
+        if (tc_dual_layout(a).total + 1024 <= 226u * 1024u) { *out = a; return true; }
+        a.dual = 0;
+    }
     a.ntcap = all64 ? 64 : 128;
     const uint32_t budget = all64 ? 100 * 1024 : 200 * 1024;      // narrow: two CTAs share the SM
     a.stream_last = 0;
@@ -714,11 +1136,23 @@ size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
     return bytes;
 }
 
+// tile width (with the image-format flag) of the tensor layers of a level
+static int tc_sa_image_nt(const TcArgs& a, int N) { return a.dual ? (TcDual::kNt | kImageBf16x3) : tc_nt(N, a.ntcap); }
+
 int launch_tc_sa(TcArgs& a, cudaStream_t st) {
-    const TcSmemLayout L = tc_layout(a);
-    size_t smem = (size_t)L.total + 1024;
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
+    if (a.dual) {
+        const size_t smem = (size_t)tc_dual_layout(a).total + 1024;
+        long long ctas = (ntiles + 1) / 2;
+        if (ctas > kNumSMs) ctas = kNumSMs;
+        if (ctas < 1) ctas = 1;
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_dual_kernel<<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+        return check_launch("tc_sa_dual_kernel");
+    }
+    const TcSmemLayout L = tc_layout(a);
+    size_t smem = (size_t)L.total + 1024;
     const bool narrow = a.ntcap == 64;
     long long ctas = narrow ? 2 * kNumSMs : kNumSMs;
     if (ctas > ntiles) ctas = ntiles;
@@ -753,13 +1187,15 @@ extern "C" PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const floa
 }
 
 // 0 = auto (tensor cores where the shapes allow, fp32 FMA otherwise); 1 = always the fp32-FMA kernels
+// 2 = like 0, but 128-wide levels use the one-tile-per-CTA wide kernel instead of the dual-group kernel (A/B measurements)
 static int g_mlp_mode = 0;
 extern "C" PSA_API int psa_set_mlp_mode(int mode) {
-    PSA_REQUIRE(mode == 0 || mode == 1, "set_mlp_mode: mode must be 0 (auto) or 1 (fp32 FMA)");
-    g_mlp_mode = mode;
+    PSA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_mlp_mode: mode must be 0 (auto), 1 (fp32 FMA) or 2 (auto, legacy wide kernel)");
+    g_mlp_mode = (mode == 1) ? 1 : 0;
+    g_tc_sa_dual = (mode == 2) ? 0 : 1;
     return PSA_OK;
 }
-extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode; }
+extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode ? 1 : (g_tc_sa_dual ? 0 : 2); }
 
 extern "C" size_t psa_sa_module_workspace_bytes(int b, int n, int m, int c, int nsample, const psa_mlp* mlp) {
     (void)m;
@@ -802,7 +1238,7 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         for (int l = 0; l < a.nl; ++l) {
             a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
             const int K = a.Kd[l], N = a.Ntot[l];
-            a.image[l] = use_or_build_image(mlp, 1 + l, 0, N, tc_nt(N, a.ntcap), ws, st);
+            a.image[l] = use_or_build_image(mlp, 1 + l, 0, N, tc_sa_image_nt(a, N), ws, st);
             ws += (tc_image_bytes(K, N) + 255) & ~(size_t)255;
         }
         rc = check_launch("tc_prep_weights_kernel");
@@ -1051,11 +1487,12 @@ extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, co
 }
 
 extern "C" int psa_prepare_weight_image(int K, int N, int row0, int nt, const float* W, void* image, psa_stream_t stream) {
-    PSA_REQUIRE(K >= 1 && N >= 64 && N % 64 == 0 && row0 >= 0 && row0 < K && (nt == 64 || nt == 128) && N % nt == 0,
+    const int ntw = nt & ~kImageBf16x3;       // nt as returned by psa_mlp_image_plan (may carry the bf16x3 format flag)
+    PSA_REQUIRE(K >= 1 && N >= 64 && N % 64 == 0 && row0 >= 0 && row0 < K && (ntw == 64 || ntw == 128) && N % ntw == 0,
                 "prepare_weight_image: bad arguments K=%d N=%d row0=%d nt=%d", K, N, row0, nt);
     PSA_REQUIRE(W && image, "prepare_weight_image: null buffer");
     const int Ki = K - row0, Kp = (Ki + 63) & ~63;
-    tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, as_stream(stream)>>>(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image));
+    build_image(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image), as_stream(stream));
     return check_launch("tc_prep_weights_kernel");
 }
 
@@ -1079,6 +1516,15 @@ extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, 
     TcArgs a;
     if (!tc_sa_eligible(mlp, c, nsample, &a)) return PSA_OK;
     if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_dense_image_bytes(c, a.C1); }
-    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_nt(a.Ntot[l], a.ntcap); row0[1 + l] = 0; bytes[1 + l] = (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255; }
+    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(a, a.Ntot[l]); row0[1 + l] = 0; bytes[1 + l] = (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255; }
     return PSA_OK;
 }
+
+#ifdef PSA_TC_TIMING
+extern "C" __attribute__((visibility("default"))) int psa_debug_tc_timing(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    if (out8) cudaMemcpyFromSymbol(out8, psa::g_tc_timing, 8 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(psa::g_tc_timing, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -22,10 +22,11 @@ def _store(seed=0):
     return VariableStore(device="cuda", seed=seed)
 
 
-@pytest.fixture(params=["tensor", "fma"])
+@pytest.fixture(params=["tensor", "fma", "tensor_wide"])
 def mlp_mode(request):
-    """0 = auto (tcgen05 three-term split where the shapes allow), 1 = fp32 FMA kernels"""
-    ops.set_mlp_mode(0 if request.param == "tensor" else 1)
+    """0 = auto (tcgen05 operand-split kernels where the shapes allow), 1 = fp32 FMA kernels, 2 = auto with the legacy
+    one-tile-per-CTA kernel for 128-wide levels instead of the dual-group one"""
+    ops.set_mlp_mode({"tensor": 0, "fma": 1, "tensor_wide": 2}[request.param])
     yield request.param
     ops.set_mlp_mode(0)
 
@@ -53,7 +54,8 @@ def test_shared_mlp_matches_fp64(rows, pool_k, chans):
 @pytest.mark.parametrize("kind", ["ball", "shell"])
 @pytest.mark.parametrize("n,m,r,k,c,mlp", [(2048, 512, 0.2, 32, 0, [64, 64, 128]), (512, 128, 0.4, 64, 128, [128, 128, 256]),
                                            (2048, 512, 0.2, 64, 0, [64, 64, 128]), (300, 50, 0.3, 20, 5, [32, 48]),
-                                           (256, 64, 0.3, 16, 64, [64])])
+                                           (256, 64, 0.3, 16, 64, [64]), (512, 100, 0.4, 32, 64, [128, 64, 128]),
+                                           (512, 37, 0.5, 128, 16, [128, 256]), (1024, 333, 0.3, 32, 128, [128, 128, 128])])
 def test_sa_module_infer_matches_fp64(kind, n, m, r, k, c, mlp, mlp_mode):
     p = _store(n + k)
     add_sa_module_params(p, "sa", 3 + c, mlp, randomize_bn=True)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import mlp_oracle as mo
 from oracle import oracle as orc
-from scanobjectnn_b200 import dgcnn, ops, pointnet2_cls_bga
+from scanobjectnn_b200 import dgcnn, ops, pointnet2_cls_bga, pointnet_cls
 from scanobjectnn_b200.synthetic import make_clouds
 
 from . import gpu_util as G
@@ -89,3 +89,17 @@ def test_dgcnn_stagewise_matches_oracle(bga):
     else:
         _close(G.npy(ep["global"]), glob, what="global")
         _close(G.npy(cls), mo.mlp_chain(glob, p, ["fc1", "fc2", "fc3"], [True, True, False]), what="logits")
+
+
+def test_pointnet_cls_vanilla_matches_oracle():
+    """BASELINE.json configs[0]: PointNet vanilla, B=8 N=1024 (the reference's plumbing case)."""
+    p = pointnet_cls.init_params(seed=6, randomize_bn=True)
+    for name in ("transform_net1/transform_XYZ/weights", "transform_net2/transform_feat/weights"):
+        p[name] = 0.01 * torch.randn(p[name].shape, device="cuda")        # non-identity transforms
+    xyz = make_clouds("shell", 8, 1024, seed=4003)
+    logits, ep = pointnet_cls.get_model(G.cu(xyz), False, params=p)
+    want, t2 = mo.pointnet_cls(xyz, p)
+    _close(G.npy(ep["transform"]), t2, what="feature transform")
+    _close(G.npy(logits), want, what="logits")
+    loss = pointnet_cls.get_loss(logits, torch.zeros(8, dtype=torch.int64, device="cuda"), ep)
+    assert torch.isfinite(loss)
