@@ -496,8 +496,8 @@ struct TcDual {
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;\n" ::"r"(g + 1) : "memory"); }
 
-// split 32 activations into three bf16 pieces and store them as the A operand (h is clobbered)
-__device__ __forceinline__ void store_a3_chunk(uint32_t row_taddr, int ch, float (&h)[32]) {
+// split 32 activations into three bf16 pieces and store them as 16 columns each at a1, a1 + 64, a1 + 128 (h is clobbered)
+__device__ __forceinline__ void store_a3_at(uint32_t a1, float (&h)[32]) {
     uint32_t p[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -505,28 +505,31 @@ __device__ __forceinline__ void store_a3_chunk(uint32_t row_taddr, int ch, float
         h[2 * q] -= __uint_as_float(p[q] << 16);
         h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
     }
-    tmem_st16(row_taddr + TcDual::A1 + ch * 16, p);
+    tmem_st16(a1, p);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
         h[2 * q] -= __uint_as_float(p[q] << 16);
         h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
     }
-    tmem_st16(row_taddr + TcDual::A2 + ch * 16, p);
+    tmem_st16(a1 + 64, p);
 #pragma unroll
     for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
-    tmem_st16(row_taddr + TcDual::A3 + ch * 16, p);
+    tmem_st16(a1 + 128, p);
 }
+__device__ __forceinline__ void store_a3_chunk(uint32_t row_taddr, int ch, float (&h)[32]) { store_a3_at(row_taddr + TcDual::A1 + ch * 16, h); }
 
-// issuer warp (converged): D[128 x 64] = sum over the six piece pairs, KC resident blocks of 64 input channels
-template <int KC>
-__device__ __forceinline__ void issue_tile3_c(uint32_t gbase, uint32_t blocks_addr) {
-    constexpr uint32_t Nt = TcDual::kNt, bb = Nt * 384u, piece = Nt * 128u;
-    const uint32_t tb = warp_uniform(gbase);
-    const uint32_t d = tb + TcDual::D;
-    const uint32_t idesc = make_idesc(kFmtBF16, 128, Nt);
+// issuer warp (converged): D[128 x NT_] (+)= sum over the six piece pairs, KC blocks of 64 input channels.
+// a1_col: TMEM column of piece 1 of the A operand (pieces 64 columns apart); d_col: accumulator; `first`: overwrite D.
+template <int KC, int NT_>
+__device__ __forceinline__ void issue_tile3_c(uint32_t tmem_base, uint32_t d_col, uint32_t a1_col, uint32_t blocks_addr) {
+    constexpr uint32_t bb = NT_ * 384u, piece = NT_ * 128u;
+    const uint32_t tb = warp_uniform(tmem_base);
+    const uint32_t d = tb + d_col;
+    const uint32_t a1 = tb + a1_col;
+    const uint32_t idesc = make_idesc(kFmtBF16, 128, NT_);
     const SmemDescBase b0 = smem_desc_base(warp_uniform(blocks_addr));
-    constexpr uint32_t acol[6] = {TcDual::A1, TcDual::A2, TcDual::A3, TcDual::A1, TcDual::A2, TcDual::A1};
+    constexpr uint32_t ap[6] = {0, 1, 2, 0, 1, 0};     // A piece / W piece of the six terms, small products first
     constexpr uint32_t wp[6] = {2, 1, 0, 1, 0, 0};
 #pragma unroll
     for (int t = 0; t < 6; ++t)
@@ -534,10 +537,11 @@ __device__ __forceinline__ void issue_tile3_c(uint32_t gbase, uint32_t blocks_ad
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4)
-                mma_bf16_ts(d, tb + acol[t] + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + wp[t] * piece + s4 * 32), idesc, (t | kc | s4) ? 1u : 0u);
+                mma_bf16_ts(d, a1 + ap[t] * 64 + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + wp[t] * piece + s4 * 32), idesc, (t | kc | s4) ? 1u : 0u);
 }
 __device__ __forceinline__ void issue_tile3(uint32_t gbase, uint32_t blocks_addr, int KC) {
-    if (KC == 1) issue_tile3_c<1>(gbase, blocks_addr); else issue_tile3_c<2>(gbase, blocks_addr);
+    if (KC == 1) issue_tile3_c<1, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+    else issue_tile3_c<2, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
 }
 
 struct TcDualLayout {
@@ -590,6 +594,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[TcDual::kThreads / 32][32];
     __shared__ unsigned int s_tile[2][2];
+    __shared__ __align__(16) float4 s_geo[2][128];   // per group: (dx, dy, dz, source row) of the NEXT tile's rows, prefetched
+    __shared__ int s_nonneg;                         // every scale of the last layer >= 0: pool first, affine + ReLU after
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_u = (int)warp_uniform((uint32_t)warp);
@@ -618,10 +624,13 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     }
     for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) w1x[i] = __ldg(a.w1x + i);
     for (int i = tid; i < a.C1; i += TcDual::kThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
+    if (tid == 0) s_nonneg = 1;
+    __syncthreads();
     for (int l = 0; l < a.nl; ++l)
         for (int i = tid; i < a.Ntot[l]; i += TcDual::kThreads) {
             sl[l][i] = a.s[l] ? __ldg(a.s[l] + i) : 1.f;
             tl[l][i] = __ldg(a.t[l] + i);
+            if (l == last && !(sl[l][i] >= 0.f)) s_nonneg = 0;
         }
     __syncthreads();
     if (tid == 0) {
@@ -650,6 +659,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     const uint32_t tmem_base = warp_uniform(s_tmem) + (uint32_t)g * TcDual::kGroupCols;
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0;
+    const bool pool_first = s_nonneg != 0;    // relu(s*d + t) is non-decreasing in d when s >= 0: max over rows commutes with it
+    bool have_geo = false;                    // s_geo[g] holds this tile's geometry (written during the previous tile)
 
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
@@ -670,11 +681,16 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
         const long long g0 = tile * G;
         const long long gid = g0 + row / a.K;
         const bool valid = gid < a.groups;
+        const bool tile_full = g0 + G <= a.groups;
         // ---- layer 1 on the FMA pipe, straight into the A operand ----
         {
             float dx = 0.f, dy = 0.f, dz = 0.f;
             const float* urow = nullptr;
-            if (valid) {
+            if (have_geo) {
+                const float4 gq = s_geo[g][row];
+                dx = gq.x; dy = gq.y; dz = gq.z;
+                if (a.uf && valid) urow = a.uf + (size_t)__float_as_int(gq.w) * a.C1;
+            } else if (valid) {
                 const long long bi = gid / a.m;
                 const int j = __ldg(a.idx + gid * a.K + (row % a.K));
                 const float* p = a.xyz + ((size_t)bi * a.n + j) * 3;
@@ -761,6 +777,24 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                         mma_commit(&s_mbar[g]);
                     }
                     TC_STAMP(4);
+                    if (nt == NT - 1) {
+                        // the next tile's index -> point -> offset chain (two dependent L2 round trips) runs under these MMAs
+                        const long long ntile = (long long)s_tile[g][tpar];
+                        have_geo = ntile < ntiles;
+                        if (have_geo && cs == 0) {
+                            const long long ngid = ntile * G + row / a.K;
+                            float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ngid < a.groups) {
+                                const long long bi = ngid / a.m;
+                                const int j = __ldg(a.idx + ngid * a.K + (row % a.K));
+                                const float* p = a.xyz + ((size_t)bi * a.n + j) * 3;
+                                const float* c = a.new_xyz + (size_t)ngid * 3;
+                                gq.x = __ldg(p) - __ldg(c); gq.y = __ldg(p + 1) - __ldg(c + 1); gq.z = __ldg(p + 2) - __ldg(c + 2);
+                                gq.w = __int_as_float((int)(bi * a.n + j));
+                            }
+                            s_geo[g][row] = gq;       // read after this tile's closing group barriers
+                        }
+                    }
                     mbar_wait(&s_mbar[g], phase);
                     phase ^= 1u;
                     fence_after_thread_sync();
@@ -779,13 +813,22 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     tmem_ld32(row_taddr + TcDual::D + cs * 32, d);
                     tmem_ld_wait();
                     float v[32];
-                    affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], valid, -FLT_MAX, v);
+                    if (pool_first) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = (tile_full || valid) ? __uint_as_float(d[q]) : -FLT_MAX;
+                    } else {
+                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], valid, -FLT_MAX, v);
+                    }
                     float mx = warp_colmax_32x32(v, lane);
                     if (quarters_per_group > 1) {
                         s_red[warp][lane] = mx;
                         group_bar(g);
                         if ((quarter % quarters_per_group) == 0)
                             for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
+                    }
+                    if (pool_first) {
+                        mx = fmaf(mx, sl[l][nt * kNt + cs * 32 + lane], tl[l][nt * kNt + cs * 32 + lane]);
+                        if (a.relu[l]) mx = fmaxf(mx, 0.f);
                     }
                     if ((quarter % quarters_per_group) == 0 && wg < a.groups)
                         a.out[(size_t)wg * a.Ntot[l] + nt * kNt + cs * 32 + lane] = mx;
@@ -1032,6 +1075,238 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// tc_dense2_kernel -- the dense layer as a software pipeline (replaces tc_dense_kernel on the default path).
+//   CTA = 128 rows x Nt output channels (Nt = 128, or 64 for a 64-wide layer), 17 warps, one CTA per SM:
+//   * 16 ROW warps (quarter = w & 3 -> TMEM lanes, slot = w >> 2 -> 32-column chunk) quantise their chunk of the next
+//     K = 128 segment of x into bf16x3 pieces in one of TWO A-operand buffers in TMEM, while
+//   * the ISSUER warp (converged, tc_common.cuh) waits for that buffer, the segment's weight blocks (cp.async.bulk
+//     into a two-slot shared-memory ring, refilled as soon as the MMAs that read a slot have completed) and for D to
+//     be drained, then issues the segment's six-term MMAs and commits;
+//   * the row warps add each segment's D to fp32 register accumulators (the truncating TMEM accumulation never runs
+//     over more than 128 K), then run the epilogue of tc_dense_kernel (affine, ReLU, xyz side input, max-pool).
+//   A-preparation of segment s+1 overlaps the MMAs of segment s; all hand-offs are mbarriers, no CTA-wide barrier
+//   inside the K loop.   TMEM: D 128 | A[0] 192 | A[1] 192 columns.
+// ------------------------------------------------------------------------------------------------------------------
+struct TcDense2 {
+    static constexpr int kRowWarps = 16, kThreads = 17 * 32;
+    static constexpr uint32_t D = 0, A0 = 128, ABUF = 192;     // A buffer b at A0 + b * ABUF, pieces 64 columns apart
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int NT_>
+__global__ void __launch_bounds__(TcDense2::kThreads, 1)
+tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_wfull[2];     // weight slot landed (tx)
+    __shared__ __align__(8) uint64_t s_afull[2];     // A buffer written by all 16 row warps
+    __shared__ __align__(8) uint64_t s_mma;          // segment's MMAs complete
+    __shared__ __align__(8) uint64_t s_dfree;        // D drained by all 16 row warps
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[TcDense2::kRowWarps][32];
+    __shared__ __align__(16) float s_vec[5][NT_];    // scale, shift, three xyz rows of W for this CTA's output channels
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int KCtot = a.Kp / 64;
+    constexpr uint32_t bb = NT_ * 384u, slot_bytes = 2u * bb;
+    const int nt = blockIdx.y;
+    for (int i = tid; i < NT_; i += TcDense2::kThreads) {
+        const int c = nt * NT_ + i;
+        s_vec[0][i] = a.scale ? __ldg(a.scale + c) : 1.f;
+        s_vec[1][i] = a.shift ? __ldg(a.shift + c) : 0.f;
+        s_vec[2][i] = a.xyz3 ? __ldg(a.w3 + c) : 0.f;
+        s_vec[3][i] = a.xyz3 ? __ldg(a.w3 + a.N + c) : 0.f;
+        s_vec[4][i] = a.xyz3 ? __ldg(a.w3 + 2 * a.N + c) : 0.f;
+    }
+    const long long row0 = (long long)blockIdx.x * 128;
+    const int nseg = (KCtot + 1) / 2;
+    const uint8_t* img = a.image + (size_t)nt * KCtot * bb;
+
+    if (warp_u == 0) tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        mbar_init(&s_wfull[0], 1); mbar_init(&s_wfull[1], 1);
+        mbar_init(&s_afull[0], TcDense2::kRowWarps); mbar_init(&s_afull[1], TcDense2::kRowWarps);
+        mbar_init(&s_mma, 1); mbar_init(&s_dfree, TcDense2::kRowWarps);
+        fence_mbar_init();
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = warp_uniform(s_tmem);
+#ifdef PSA_TC_TIMING
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+    long long tprev = clock64();
+#endif
+
+    if (warp_u == TcDense2::kRowWarps) {
+        // ================= issuer warp =================
+        auto load_seg = [&](int sg) {       // one lane
+            const int kcs = min(2, KCtot - 2 * sg);
+            const uint32_t bytes = (uint32_t)kcs * bb;
+            uint64_t* bar = &s_wfull[sg & 1];
+            mbar_expect_tx(bar, bytes);
+            for (uint32_t o = 0; o < bytes; o += 32768u)
+                bulk_g2s(base + (sg & 1) * slot_bytes + o, img + (size_t)sg * slot_bytes + o, min(32768u, bytes - o), bar);
+        };
+        if (lane == 0) { load_seg(0); if (nseg > 1) load_seg(1); }
+        __syncwarp();
+        for (int sg = 0; sg < nseg; ++sg) {
+            const int b = sg & 1;
+            const uint32_t par = (uint32_t)((sg >> 1) & 1);
+            mbar_wait(&s_wfull[b], par);
+            mbar_wait(&s_afull[b], par);
+            if (sg > 0) {
+                mbar_wait(&s_dfree, (uint32_t)((sg - 1) & 1));        // D drained => MMAs of segment sg-1 completed too
+                if (lane == 0 && sg + 1 < nseg) load_seg(sg + 1);     // their weight slot is free again
+            }
+            __syncwarp();
+            fence_after_thread_sync();
+            const uint32_t blocks = smem_u32(base) + (uint32_t)b * slot_bytes;
+            const uint32_t a1 = TcDense2::A0 + (uint32_t)b * TcDense2::ABUF;
+            if (KCtot - 2 * sg >= 2) issue_tile3_c<2, NT_>(tmem_base, TcDense2::D, a1, blocks);
+            else issue_tile3_c<1, NT_>(tmem_base, TcDense2::D, a1, blocks);
+            mma_commit(&s_mma);
+        }
+    } else {
+        // ================= row warps =================
+        const int quarter = warp_u & 3, cs = warp_u >> 2;
+        const int row = quarter * 32 + lane;
+        const long long grow = row0 + row;
+        const bool valid = grow < a.rows;
+        const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const bool vec_ok = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+        const bool has_out_chunk = cs < NT_ / 32;
+        float acc[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+
+        // this warp's 32-wide chunk of segment sg of x, raw (loads only: issued early, consumed a segment later)
+        auto load_x = [&](int sg, float (&h)[32]) {
+            const int kcs = min(2, KCtot - 2 * sg);
+            if (cs < kcs * 2) {
+                const int k0 = sg * 128 + cs * 32;
+                const float* xr = a.x + (size_t)(valid ? grow : 0) * a.K + k0;
+                if (valid && vec_ok && k0 + 32 <= a.K) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(xr) + q);
+                        h[4 * q] = u.x; h[4 * q + 1] = u.y; h[4 * q + 2] = u.z; h[4 * q + 3] = u.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) h[q] = (valid && k0 + q < a.K) ? __ldg(xr + q) : 0.f;
+                }
+            }
+        };
+        // split into bf16x3 pieces -> A buffer sg & 1, then tell the issuer
+        auto store_x = [&](int sg, float (&h)[32]) {
+            const int kcs = min(2, KCtot - 2 * sg);
+            if (cs < kcs * 2) {
+                store_a3_at(row_taddr + TcDense2::A0 + (uint32_t)(sg & 1) * TcDense2::ABUF + cs * 16, h);
+                tmem_st_wait();
+            }
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_afull[sg & 1]);
+        };
+
+        TC_STAMP(0);
+        float h[32];
+        load_x(0, h);
+        store_x(0, h);
+        if (nseg > 1) load_x(1, h);
+        TC_STAMP(1);
+        for (int sg = 0; sg < nseg; ++sg) {
+            if (sg + 1 < nseg) {
+                store_x(sg + 1, h);                   // buffer (sg+1)&1 was released by the MMAs of segment sg-1 (waited below)
+                if (sg + 2 < nseg) load_x(sg + 2, h); // in flight across this segment's MMA wait and drain
+            }
+            TC_STAMP(2);
+            mbar_wait(&s_mma, (uint32_t)(sg & 1));
+            fence_after_thread_sync();
+            TC_STAMP(3);
+            if (has_out_chunk) {
+                uint32_t d[32];
+                tmem_ld32(row_taddr + TcDense2::D + cs * 32, d);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(d[q]);
+            }
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_dfree);
+            TC_STAMP(4);
+        }
+        // ---- epilogue (as tc_dense_kernel) ----
+        const int col0 = nt * NT_ + cs * 32;
+        float v[32];
+        if (has_out_chunk) {
+            float sx3 = 0.f, sy3 = 0.f, sz3 = 0.f;
+            if (a.xyz3 != nullptr && valid) {
+                sx3 = __ldg(a.xyz3 + (size_t)grow * 3); sy3 = __ldg(a.xyz3 + (size_t)grow * 3 + 1); sz3 = __ldg(a.xyz3 + (size_t)grow * 3 + 2);
+            }
+            const float* vs = &s_vec[0][cs * 32];
+            if (a.xyz3 != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    acc[q] = fmaf(sz3, vs[4 * NT_ + q], fmaf(sy3, vs[3 * NT_ + q], fmaf(sx3, vs[2 * NT_ + q], acc[q])));
+            }
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                float x = fmaf(acc[q], vs[q], vs[NT_ + q]);
+                if (a.relu) x = fmaxf(x, 0.f);
+                v[q] = x;
+            }
+        }
+        if (a.pool_k == 1) {
+            if (has_out_chunk && valid) {
+                float4* o = reinterpret_cast<float4*>(a.out + (size_t)grow * a.N + col0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+        } else {
+            const bool big = a.pool_k > 128;                         // the whole 128-row tile lies inside one group
+            const int quarters_per_group = big ? 4 : a.pool_k / 32;
+            const long long wg = (row0 + quarter * 32) / a.pool_k;
+            float mx = -FLT_MAX;
+            if (has_out_chunk) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = valid ? v[q] : -FLT_MAX;
+                mx = warp_colmax_32x32(v, lane);
+            }
+            if (quarters_per_group > 1) {
+                s_red[warp_u][lane] = mx;
+                named_bar_sync(1, TcDense2::kRowWarps * 32);
+                if ((quarter % quarters_per_group) == 0)
+                    for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp_u + o][lane]);
+            }
+            if (has_out_chunk && (quarter % quarters_per_group) == 0 && row0 + quarter * 32 < a.rows) {
+                if (!big) {
+                    a.out[(size_t)wg * a.N + col0 + lane] = mx;
+                } else {
+                    int code = __float_as_int(mx);
+                    code = code >= 0 ? code : code ^ 0x7fffffff;
+                    atomicMax(reinterpret_cast<int*>(a.out) + (size_t)wg * a.N + col0 + lane, code);
+                }
+            }
+        }
+    }
+    TC_STAMP(5);
+    fence_before_thread_sync();
+    __syncthreads();
+    TC_STAMP(6);
+#ifdef PSA_TC_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_timing[i], tacc[i]);
+#endif
+    if (warp_u == 0) tmem_dealloc(tmem_base, 512);
+}
+
 bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
     if (rows < 128 || K < 32 || N < 64 || (N % 64) != 0) return false;
     if (N > 64 && (N % 128) != 0) return false;
@@ -1042,8 +1317,14 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
 size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
 
 static int g_tc_dense_narrow = 1;
+static int g_tc_dense_v2 = 1;     // 1: pipelined tc_dense2_kernel (bf16x3 images); 0: tc_dense_kernel (psa_set_mlp_mode(2))
 static int g_tc_sa_dual = 1;      // 0: 128-wide levels fall back to the one-tile-per-CTA wide kernel (psa_set_mlp_mode(2), A/B runs)
-int tc_dense_nt(int N) { return tc_nt(N, g_tc_dense_narrow ? 64 : 128); }
+int tc_dense_nt(int N) {
+    if (g_tc_dense_v2) return ((N % 128) == 0 ? 128 : 64) | kImageBf16x3;
+    return tc_nt(N, g_tc_dense_narrow ? 64 : 128);
+}
+
+static void build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st);
 
 // `image`: workspace to build the weight image in, or -- when `prebuilt` -- an image that already holds it
 int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
@@ -1051,11 +1332,26 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
                     const float* w3 = nullptr, bool prebuilt = false) {
     const int Kp = (K + 63) & ~63;
     const bool narrow = g_tc_dense_narrow != 0;
-    const int Nt = tc_nt(N, narrow ? 64 : 128);
-    if (!prebuilt) tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, const_cast<uint8_t*>(image));
+    const int nt_img = tc_dense_nt(N);
+    const int Nt = nt_img & ~kImageBf16x3;
+    if (!prebuilt) build_image(K, Kp, N, nt_img, W, const_cast<uint8_t*>(image), st);
     TcDenseArgs a;
     a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
     a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out; a.xyz3 = xyz3; a.w3 = w3;
+    if (g_tc_dense_v2) {
+        dim3 grid2((unsigned)((rows + 127) / 128), N / Nt);
+        if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
+        const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt) + 1024;      // two slots of two 64-K blocks
+        if (Nt == 128) {
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc_dense2_kernel<128><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
+        } else {
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc_dense2_kernel<64><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
+        }
+        if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
+        return check_launch("tc_dense2_kernel");
+    }
     dim3 grid((unsigned)((rows + 127) / 128), N / Nt);
     if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
     if (narrow) {
@@ -1193,6 +1489,7 @@ extern "C" PSA_API int psa_set_mlp_mode(int mode) {
     PSA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_mlp_mode: mode must be 0 (auto), 1 (fp32 FMA) or 2 (auto, legacy wide kernel)");
     g_mlp_mode = (mode == 1) ? 1 : 0;
     g_tc_sa_dual = (mode == 2) ? 0 : 1;
+    g_tc_dense_v2 = (mode == 2) ? 0 : 1;
     return PSA_OK;
 }
 extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode ? 1 : (g_tc_sa_dual ? 0 : 2); }
