@@ -374,10 +374,19 @@ def main():
     flops = {"sa1_mlp": SA_FLOPS["sa1"], "sa2_mlp": SA_FLOPS["sa2"], "sa3_mlp": SA_FLOPS["sa3"]}.get(dom)
     if flops:
         ach = flops / (stages[dom] * 1e-6) / 1e12
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"] + " bf16 burst",
-                    "note": "fp32 FMA path (1e-5 parity mode); fp32 FMA pipe peak = 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",
-                    "fma_pipe_frac": ach / 74.4}
+        # share of the level's flops that runs on the tensor cores (layers after the first); each fp32 product is six bf16 MMAs
+        tc_flops = {"sa1_mlp": 2 * 524288 * (64 * 64 + 64 * 128), "sa2_mlp": 2 * 262144 * (128 * 128 + 128 * 256) + 2 * 16384 * 128 * 128,
+                    "sa3_mlp": 2 * 4096 * (256 * 256 + 256 * 512 + 512 * 1024)}[dom]
+        # dram__bytes_read.sum + dram__bytes_write.sum of the level's dominant launch, from profiles/r01_ncu_final_summary.md
+        traffic = {"sa1_mlp": 3.54e6, "sa2_mlp": 10.41e6, "sa3_mlp": 11.59e6}[dom]
+        roofline = {"kernel": dom + " (tc_sa_dual_kernel + its per-source-point first-layer GEMM)" if dom != "sa3_mlp" else dom + " (3 x tc_dense2_kernel)",
+                    "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tf"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 burst",
+                    "algorithmic_flops": flops,
+                    "note": "achieved = SURVEY 8d fp32 MLP flops of the level / measured stage time. fp32 parity (1e-5) is kept by splitting "
+                            "both operands into three bf16 pieces: six bf16 MMAs per product, so the tensor pipe executes 6x the "
+                            "tensor-core share of these flops (tensor_pipe_frac).",
+                    "tensor_pipe_frac": 6.0 * tc_flops / (stages[dom] * 1e-6) / 1e12 / peaks["tf"]}
     else:
         fps_bytes = B * (12 * N + 4 * 512)
         ach = fps_bytes / (stages[dom] * 1e-6) / 1e9
@@ -402,7 +411,9 @@ def main():
     kern["sa1_f1"] = {"us": stages["sa1_f1"], "alg_bytes": f1_bytes, "gbs": f1_gbs, "hbm_frac": f1_gbs / peaks["hbm"]}
     roofline_f1 = {"kernel": "sa_conv1_prebn_kernel (variant F1: fused ball-query + group + conv1, pre-BN output, SA1 B=32 N=2048 K=32)",
                    "bound": "hbm", "achieved": f1_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": f1_gbs / peaks["hbm"],
-                   "traffic": None, "peak_source": peaks["src"], "in_timed_step": False}
+                   "traffic": 80.37e6, "traffic_note": "dram read 1.04 MB + write 79.3 MB in the kernel's own window (profiles/r01_ncu_full_v4_fps_ballquery_f1.md); "
+                                                         "the rest of the 137 MB output is still dirty in the 126 MB L2 when the kernel ends",
+                   "peak_source": peaks["src"], "in_timed_step": False}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -421,7 +432,7 @@ def main():
                    "parallelism": f"dp{world} (independent batches, no data-path collective)"},
         "e2e": {"value": e2e_v, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * N * 3 * 4,
                 "d2h_bytes_per_step": B * NUM_CLASS * 4},
-        "gpu_launches": 12 * args.steps,
+        "gpu_launches": 16 * args.steps,
         "roofline": roofline,
         "roofline_f1": roofline_f1,
         "kernels": kern,
