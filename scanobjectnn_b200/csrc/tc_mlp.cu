@@ -496,8 +496,8 @@ struct TcDual {
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;\n" ::"r"(g + 1) : "memory"); }
 
-// split 32 activations into three bf16 pieces and store them as 16 columns each at a1, a1 + 64, a1 + 128 (h is clobbered)
-__device__ __forceinline__ void store_a3_at(uint32_t a1, float (&h)[32]) {
+// split 32 activations into three bf16 pieces and store them as 16 columns each at a1, a1 + ps, a1 + 2 ps (h is clobbered)
+__device__ __forceinline__ void store_a3_at(uint32_t a1, float (&h)[32], uint32_t ps = 64) {
     uint32_t p[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -512,16 +512,15 @@ __device__ __forceinline__ void store_a3_at(uint32_t a1, float (&h)[32]) {
         h[2 * q] -= __uint_as_float(p[q] << 16);
         h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
     }
-    tmem_st16(a1 + 64, p);
+    tmem_st16(a1 + ps, p);
 #pragma unroll
     for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
-    tmem_st16(a1 + 128, p);
+    tmem_st16(a1 + 2 * ps, p);
 }
-__device__ __forceinline__ void store_a3_chunk(uint32_t row_taddr, int ch, float (&h)[32]) { store_a3_at(row_taddr + TcDual::A1 + ch * 16, h); }
 
 // issuer warp (converged): D[128 x NT_] (+)= sum over the six piece pairs, KC blocks of 64 input channels.
 // a1_col: TMEM column of piece 1 of the A operand (pieces 64 columns apart); d_col: accumulator; `first`: overwrite D.
-template <int KC, int NT_>
+template <int KC, int NT_, int PS = 64>
 __device__ __forceinline__ void issue_tile3_c(uint32_t tmem_base, uint32_t d_col, uint32_t a1_col, uint32_t blocks_addr) {
     constexpr uint32_t bb = NT_ * 384u, piece = NT_ * 128u;
     const uint32_t tb = warp_uniform(tmem_base);
@@ -537,10 +536,14 @@ __device__ __forceinline__ void issue_tile3_c(uint32_t tmem_base, uint32_t d_col
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4)
-                mma_bf16_ts(d, a1 + ap[t] * 64 + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + wp[t] * piece + s4 * 32), idesc, (t | kc | s4) ? 1u : 0u);
+                mma_bf16_ts(d, a1 + ap[t] * PS + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + wp[t] * piece + s4 * 32), idesc, (t | kc | s4) ? 1u : 0u);
 }
-__device__ __forceinline__ void issue_tile3(uint32_t gbase, uint32_t blocks_addr, int KC) {
-    if (KC == 1) issue_tile3_c<1, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+// dbuf (levels whose layers are all <= 64 wide): A pieces 32 columns apart at 128.., two D slots at 0 and 64
+__device__ __forceinline__ void issue_tile3(uint32_t gbase, uint32_t blocks_addr, int KC, bool dbuf, int dslot) {
+    if (dbuf) {
+        if (dslot == 0) issue_tile3_c<1, TcDual::kNt, 32>(gbase, 0, 128, blocks_addr);
+        else issue_tile3_c<1, TcDual::kNt, 32>(gbase, 64, 128, blocks_addr);
+    } else if (KC == 1) issue_tile3_c<1, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
     else issue_tile3_c<2, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
 }
 
@@ -584,11 +587,16 @@ __device__ __forceinline__ void affine_chunk(const uint32_t (&d)[32], const floa
     }
 }
 
+// DBUF (levels whose layers are all <= 64 wide, nothing streamed): the A operand is 3 x 32 columns (at 128..), which leaves
+// room for two D slots (0, 64) -- the last layer's tiles are issued in pairs and the second tile's MMAs run under the
+// first tile's pooled epilogue.
+template <bool DBUF>
 __global__ void __launch_bounds__(TcDual::kThreads, 1)
 tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     constexpr int kNt = TcDual::kNt;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[2];  // MMA completion, per group
+    __shared__ __align__(8) uint64_t s_mbar2[2]; // MMA completion of the second D slot (dbuf levels), per group
     __shared__ __align__(8) uint64_t s_wbar[2];  // ring tile landed, per group
     __shared__ __align__(8) uint64_t s_rbar;     // resident weights landed
     __shared__ uint32_t s_tmem;
@@ -609,7 +617,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
 
     if (warp == 0) tmem_alloc(&s_tmem, 512);
     if (tid == 0) {
-        mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_init(&s_wbar[0], 1); mbar_init(&s_wbar[1], 1); mbar_init(&s_rbar, 1);
+        mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_init(&s_mbar2[0], 1); mbar_init(&s_mbar2[1], 1); mbar_init(&s_wbar[0], 1); mbar_init(&s_wbar[1], 1); mbar_init(&s_rbar, 1);
         fence_mbar_init();
     }
     float* vec = reinterpret_cast<float*>(base + L.vec);
@@ -658,7 +666,9 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     fence_after_thread_sync();
     const uint32_t tmem_base = warp_uniform(s_tmem) + (uint32_t)g * TcDual::kGroupCols;
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase2 = 0;
+    constexpr bool dbuf = DBUF;
+    constexpr uint32_t a1_col = DBUF ? 128u : TcDual::A1, a_ps = DBUF ? 32u : 64u;
     const bool pool_first = s_nonneg != 0;    // relu(s*d + t) is non-decreasing in d when s >= 0: max over rows commutes with it
     bool have_geo = false;                    // s_geo[g] holds this tile's geometry (written during the previous tile)
 
@@ -726,7 +736,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
                     h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
                 }
-                store_a3_chunk(row_taddr, ch, h);
+                store_a3_at(row_taddr + a1_col + ch * 16, h, a_ps);
             }
         }
         tmem_st_wait();
@@ -742,7 +752,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 for (int nt = 0; nt < NT; ++nt) {
                     if (issuer) {
                         fence_after_thread_sync();
-                        issue_tile3(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt), KC);
+                        issue_tile3(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt), KC, dbuf, 0);
                         mma_commit(&s_mbar[g]);
                     }
                     TC_STAMP(1);
@@ -757,8 +767,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], valid, 0.f, h1);
                     if (nt + 1 < NT) { fence_before_thread_sync(); group_bar(g); }       // D drained before the next tile lands in it
                 }
-                store_a3_chunk(row_taddr, cs, h0);
-                if (NT == 2) store_a3_chunk(row_taddr, 2 + cs, h1);
+                store_a3_at(row_taddr + a1_col + cs * 16, h0, a_ps);
+                if (NT == 2) store_a3_at(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps);
                 tmem_st_wait();
                 fence_before_thread_sync();
                 group_bar(g);
@@ -767,17 +777,48 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 const bool streamed = a.stream_last != 0;
                 const int quarters_per_group = a.K / 32;        // 1, 2 or 4
                 const long long wg = g0 + (quarter * 32) / a.K; // this warp's neighbourhood
-                for (int nt = 0; nt < NT; ++nt) {
+                // pooled epilogue of output tile `nt` out of D slot `dslot`
+                auto pooled_epilogue = [&](int nt, int dslot) {
+                    uint32_t d[32];
+                    tmem_ld32(row_taddr + TcDual::D + dslot * 64 + cs * 32, d);
+                    tmem_ld_wait();
+                    float v[32];
+                    if (pool_first) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = (tile_full || valid) ? __uint_as_float(d[q]) : -FLT_MAX;
+                    } else {
+                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], valid, -FLT_MAX, v);
+                    }
+                    float mx = warp_colmax_32x32(v, lane);
+                    if (quarters_per_group > 1) {
+                        s_red[warp][lane] = mx;
+                        group_bar(g);
+                        if ((quarter % quarters_per_group) == 0)
+                            for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
+                    }
+                    if (pool_first) {
+                        mx = fmaf(mx, sl[l][nt * kNt + cs * 32 + lane], tl[l][nt * kNt + cs * 32 + lane]);
+                        if (a.relu[l]) mx = fmaxf(mx, 0.f);
+                    }
+                    if ((quarter % quarters_per_group) == 0 && wg < a.groups)
+                        a.out[(size_t)wg * a.Ntot[l] + nt * kNt + cs * 32 + lane] = mx;
+                };
+                constexpr int kStep = DBUF ? 2 : 1;
+                for (int nt = 0; nt < NT; nt += kStep) {
                     if (issuer) {
                         if (streamed) { mbar_wait(&s_wbar[g], wphase); wphase ^= 1u; }
                         __syncwarp();               // re-converge after the spin wait: the issue below must be warp-uniform
                         fence_after_thread_sync();
                         const uint32_t blocks = streamed ? smem_u32(base + L.ring[g]) : smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt);
-                        issue_tile3(tmem_base, blocks, KC);
+                        issue_tile3(tmem_base, blocks, KC, dbuf, 0);
                         mma_commit(&s_mbar[g]);
+                        if (DBUF && nt + 1 < NT) {  // the pair's second tile goes to the other D slot right away
+                            issue_tile3(tmem_base, blocks + (uint32_t)KC * tc_block_bytes(kNt), KC, true, 1);
+                            mma_commit(&s_mbar2[g]);
+                        }
                     }
                     TC_STAMP(4);
-                    if (nt == NT - 1) {
+                    if (nt + kStep >= NT) {
                         // the next tile's index -> point -> offset chain (two dependent L2 round trips) runs under these MMAs
                         const long long ntile = (long long)s_tile[g][tpar];
                         have_geo = ntile < ntiles;
@@ -809,29 +850,14 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                                 bulk_g2s(base + L.ring[g] + o, a.image[l] + (size_t)rt * L.ring_bytes + o, min(32768u, L.ring_bytes - o), &s_wbar[g]);
                         }
                     }
-                    uint32_t d[32];
-                    tmem_ld32(row_taddr + TcDual::D + cs * 32, d);
-                    tmem_ld_wait();
-                    float v[32];
-                    if (pool_first) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = (tile_full || valid) ? __uint_as_float(d[q]) : -FLT_MAX;
-                    } else {
-                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], valid, -FLT_MAX, v);
+                    pooled_epilogue(nt, 0);
+                    if (DBUF && nt + 1 < NT) {
+                        if (quarters_per_group > 1) group_bar(g);       // s_red is reused by the second tile
+                        mbar_wait(&s_mbar2[g], phase2);
+                        phase2 ^= 1u;
+                        fence_after_thread_sync();
+                        pooled_epilogue(nt + 1, 1);
                     }
-                    float mx = warp_colmax_32x32(v, lane);
-                    if (quarters_per_group > 1) {
-                        s_red[warp][lane] = mx;
-                        group_bar(g);
-                        if ((quarter % quarters_per_group) == 0)
-                            for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
-                    }
-                    if (pool_first) {
-                        mx = fmaf(mx, sl[l][nt * kNt + cs * 32 + lane], tl[l][nt * kNt + cs * 32 + lane]);
-                        if (a.relu[l]) mx = fmaxf(mx, 0.f);
-                    }
-                    if ((quarter % quarters_per_group) == 0 && wg < a.groups)
-                        a.out[(size_t)wg * a.Ntot[l] + nt * kNt + cs * 32 + lane] = mx;
                     // D fully read (and s_red consumed) by every warp of the group before the next MMAs / maxima land
                     fence_before_thread_sync();
                     group_bar(g);
@@ -1443,8 +1469,15 @@ int launch_tc_sa(TcArgs& a, cudaStream_t st) {
         long long ctas = (ntiles + 1) / 2;
         if (ctas > kNumSMs) ctas = kNumSMs;
         if (ctas < 1) ctas = 1;
-        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_sa_dual_kernel<<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+        bool dbuf = a.C1 <= 64 && !a.stream_last;
+        for (int l = 0; l < a.nl; ++l) dbuf = dbuf && a.Kd[l] <= 64;
+        if (dbuf) {
+            PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_sa_dual_kernel<true><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+        } else {
+            PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_sa_dual_kernel<false><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+        }
         return check_launch("tc_sa_dual_kernel");
     }
     const TcSmemLayout L = tc_layout(a);
