@@ -590,6 +590,37 @@ __device__ __forceinline__ void affine_chunk(const uint32_t (&d)[32], const floa
 // DBUF (levels whose layers are all <= 64 wide, nothing streamed): the A operand is 3 x 32 columns (at 128..), which leaves
 // room for two D slots (0, 64) -- the last layer's tiles are issued in pairs and the second tile's MMAs run under the
 // first tile's pooled epilogue.
+// The two row groups of a CTA have identical phase lengths, so left alone they run in lock-step: both in row work
+// (fighting for issue slots), then both in their MMA batch (each at half the tensor rate).  A token makes the batches
+// run one after the other: the first group finishes at full rate and its row work then overlaps the second group's
+// MMAs -- the groups fall into anti-phase.  Released right after the batch is ISSUED (the pipe executes in order).
+// (branch-free at the source level -- predicated atomics + a shuffle -- so the issuer warp's control flow stays uniform)
+__device__ __forceinline__ void pipe_acquire(int* token, int lane) {
+    (void)lane;
+    uint32_t busy;
+    do {
+        uint32_t r;
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "mov.b32 %0, 1;\n\t"
+            "@q atom.shared.cas.b32 %0, [%1], 0, 1;\n\t}\n"
+            : "=r"(r)
+            : "r"(smem_u32(token))
+            : "memory");
+        busy = __shfl_sync(0xffffffffu, r, 0);
+    } while (busy != 0u);
+    __syncwarp();
+}
+__device__ __forceinline__ void pipe_release(int* token, int lane) {
+    (void)lane;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q atom.shared.exch.b32 t, [%0], 0;\n\t}\n" ::"r"(smem_u32(token))
+        : "memory");
+}
+
 template <bool DBUF>
 __global__ void __launch_bounds__(TcDual::kThreads, 1)
 tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
@@ -603,6 +634,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     __shared__ float s_red[TcDual::kThreads / 32][32];
     __shared__ unsigned int s_tile[2][2];
     __shared__ __align__(16) float4 s_geo[2][128];   // per group: (dx, dy, dz, source row) of the NEXT tile's rows, prefetched
+    __shared__ int s_token;                          // tensor-pipe token: the two groups' MMA batches run one after the other
     __shared__ int s_nonneg;                         // every scale of the last layer >= 0: pool first, affine + ReLU after
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -632,7 +664,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     }
     for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) w1x[i] = __ldg(a.w1x + i);
     for (int i = tid; i < a.C1; i += TcDual::kThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
-    if (tid == 0) s_nonneg = 1;
+    if (tid == 0) { s_nonneg = 1; s_token = 0; }
     __syncthreads();
     for (int l = 0; l < a.nl; ++l)
         for (int i = tid; i < a.Ntot[l]; i += TcDual::kThreads) {
@@ -751,9 +783,11 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 float h0[32], h1[32];
                 for (int nt = 0; nt < NT; ++nt) {
                     if (issuer) {
+                        pipe_acquire(&s_token, lane);
                         fence_after_thread_sync();
                         issue_tile3(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt), KC, dbuf, 0);
                         mma_commit(&s_mbar[g]);
+                        pipe_release(&s_token, lane);
                     }
                     TC_STAMP(1);
                     mbar_wait(&s_mbar[g], phase);
@@ -807,15 +841,16 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 for (int nt = 0; nt < NT; nt += kStep) {
                     if (issuer) {
                         if (streamed) { mbar_wait(&s_wbar[g], wphase); wphase ^= 1u; }
-                        __syncwarp();               // re-converge after the spin wait: the issue below must be warp-uniform
+                        pipe_acquire(&s_token, lane);   // (ends in __syncwarp: the issue below must be warp-uniform)
                         fence_after_thread_sync();
                         const uint32_t blocks = streamed ? smem_u32(base + L.ring[g]) : smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt);
                         issue_tile3(tmem_base, blocks, KC, dbuf, 0);
                         mma_commit(&s_mbar[g]);
-                        if (DBUF && nt + 1 < NT) {  // the pair's second tile goes to the other D slot right away
+                        if (DBUF) {                 // the pair's second tile goes to the other D slot right away (NT is even)
                             issue_tile3(tmem_base, blocks + (uint32_t)KC * tc_block_bytes(kNt), KC, true, 1);
                             mma_commit(&s_mbar2[g]);
                         }
+                        pipe_release(&s_token, lane);
                     }
                     TC_STAMP(4);
                     if (nt + kStep >= NT) {
@@ -851,7 +886,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                         }
                     }
                     pooled_epilogue(nt, 0);
-                    if (DBUF && nt + 1 < NT) {
+                    if (DBUF) {
                         if (quarters_per_group > 1) group_bar(g);       // s_red is reused by the second tile
                         mbar_wait(&s_mbar2[g], phase2);
                         phase2 ^= 1u;
@@ -1469,7 +1504,7 @@ int launch_tc_sa(TcArgs& a, cudaStream_t st) {
         long long ctas = (ntiles + 1) / 2;
         if (ctas > kNumSMs) ctas = kNumSMs;
         if (ctas < 1) ctas = 1;
-        bool dbuf = a.C1 <= 64 && !a.stream_last;
+        bool dbuf = a.C1 <= 64 && !a.stream_last && (a.Ntot[a.nl - 1] % 128) == 0;     // tile pairs: an even number of 64-wide tiles
         for (int l = 0; l < a.nl; ++l) dbuf = dbuf && a.Kd[l] <= 64;
         if (dbuf) {
             PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
