@@ -1368,6 +1368,221 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
     if (warp_u == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// tc_dense3_kernel -- the dense layer in TRANSPOSED form, both operands from shared memory:
+//      D^T[channel][row] = sum_k W^T[channel][k] . x^T[k][row]
+//   M = 128 output channels (TMEM lanes), N = 128 rows (TMEM columns), K walked in 64-wide blocks, two stages.
+//   * A operand = the weight image block exactly as tc_dense2 uses it as B ([128 ch][64 k] K-major SWIZZLE_128B, three
+//     bf16 pieces, 48 KB, one cp.async.bulk);
+//   * B operand = x quantised into the same layout by 16 prep warps: each warp reads 8 rows x 256 B fully COALESCED
+//     (lane = two consecutive k), splits into bf16x3 and writes 4-byte words into the swizzled rows -- conflict-free.
+//     (tc_dense2's lane = row loads cost 4096 L1 wavefronts per K = 128 segment; here 256 per 64-K block.)
+//   * the issuer warp waits for a stage's two operands and issues its 24 MMAs; the commit frees the stage;
+//   * accumulation: K-block kb goes to accumulator kb & 3 (4 x 128 TMEM columns), so no accumulator takes more than 48
+//     truncating adds at K = 512 (the bound tc_dense2 keeps with its register sums); the epilogue adds the four;
+//   * epilogue with lane = CHANNEL: scale / shift / xyz-side weights are per-thread scalars, a max over rows is an
+//     in-thread reduction (no shuffles), and every global store is a coalesced 128-byte row segment.
+// ------------------------------------------------------------------------------------------------------------------
+struct TcDense3 {
+    static constexpr int kPrepWarps = 16, kThreads = 17 * 32;
+    static constexpr uint32_t kPiece = 128u * 128u;          // one bf16 piece of a 128 x 64 block: 16 KB
+    static constexpr uint32_t kBlock = 3u * kPiece;          // 48 KB
+};
+
+__global__ void __launch_bounds__(TcDense3::kThreads, 1)
+tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_wfull[2];     // weight block landed (tx)
+    __shared__ __align__(8) uint64_t s_xfull[2];     // x block written by the 16 prep warps
+    __shared__ __align__(8) uint64_t s_free[2];      // the MMAs that read a stage completed
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[TcDense3::kPrepWarps][32];
+    __shared__ float s_xyz[128][3];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* wslot = base;                                   // 2 x 48 KB
+    uint8_t* xslot = base + 2 * TcDense3::kBlock;            // 2 x 48 KB
+    const int KB = a.Kp / 64;
+    const int nt = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * 128;
+    const uint8_t* img = a.image + (size_t)nt * KB * TcDense3::kBlock;
+
+    if (warp_u == 0) tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        mbar_init(&s_wfull[0], 1); mbar_init(&s_wfull[1], 1);
+        mbar_init(&s_xfull[0], TcDense3::kPrepWarps); mbar_init(&s_xfull[1], TcDense3::kPrepWarps);
+        mbar_init(&s_free[0], 1); mbar_init(&s_free[1], 1);
+        fence_mbar_init();
+    }
+    if (a.xyz3 != nullptr)
+        for (int i = tid; i < 128 * 3; i += TcDense3::kThreads) {
+            const long long r = row0 + i / 3;
+            s_xyz[i / 3][i % 3] = r < a.rows ? __ldg(a.xyz3 + (size_t)r * 3 + i % 3) : 0.f;
+        }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = warp_uniform(s_tmem);
+#ifdef PSA_TC_TIMING
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+    long long tprev = clock64();
+#endif
+
+    if (warp_u == TcDense3::kPrepWarps) {
+        // ================= issuer warp =================
+        const uint32_t idesc = make_idesc(kFmtBF16, 128, 128);
+        constexpr uint32_t xp[6] = {0, 1, 2, 0, 1, 0};     // x piece / W piece of the six terms, small products first
+        constexpr uint32_t wp[6] = {2, 1, 0, 1, 0, 0};
+        for (int kb = 0; kb < KB; ++kb) {
+            const int st = kb & 1;
+            const uint32_t par = (uint32_t)((kb >> 1) & 1);
+            mbar_wait(&s_wfull[st], par);
+            mbar_wait(&s_xfull[st], par);
+            __syncwarp();
+            fence_after_thread_sync();
+            const uint32_t d = tmem_base + (uint32_t)(kb & 3) * 128u;
+            const SmemDescBase wa = smem_desc_base(warp_uniform(smem_u32(wslot) + (uint32_t)st * TcDense3::kBlock));
+            const SmemDescBase xb = smem_desc_base(warp_uniform(smem_u32(xslot) + (uint32_t)st * TcDense3::kBlock));
+            const uint32_t first = kb < 4 ? 0u : 1u;         // an accumulator's first block overwrites it
+#pragma unroll
+            for (int t = 0; t < 6; ++t)
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4)
+                    mma_bf16_ss(d, smem_desc_at(wa, wp[t] * TcDense3::kPiece + s4 * 32), smem_desc_at(xb, xp[t] * TcDense3::kPiece + s4 * 32), idesc,
+                                (t | s4) ? 1u : first);
+            mma_commit(&s_free[st]);
+        }
+    } else {
+        // ================= prep warps: x block -> B operand; then the epilogue =================
+        const bool vec2 = ((a.K & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 7) == 0);
+        float2 v[8];
+        // this warp's 8 rows x 64 k of block kb, raw: issued a block ahead, before the stage is known to be free
+        auto load_x = [&](int kb) {
+            const int k = kb * 64 + 2 * lane;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long r = row0 + warp_u * 8 + i;
+                v[i] = make_float2(0.f, 0.f);
+                if (r < a.rows) {
+                    const float* xr = a.x + (size_t)r * a.K + k;
+                    if (vec2 && k + 1 < a.K) v[i] = __ldg(reinterpret_cast<const float2*>(xr));
+                    else { if (k < a.K) v[i].x = __ldg(xr); if (k + 1 < a.K) v[i].y = __ldg(xr + 1); }
+                }
+            }
+        };
+        load_x(0);
+        TC_STAMP(0);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int st = kb & 1;
+            if (kb >= 2) mbar_wait(&s_free[st], (uint32_t)(((kb - 2) >> 1) & 1));      // stage released by block kb-2's MMAs
+            TC_STAMP(1);
+            if (warp_u == 0 && lane == 0) {                                             // its weight slot is free too
+                mbar_expect_tx(&s_wfull[st], TcDense3::kBlock);
+                for (uint32_t o = 0; o < TcDense3::kBlock; o += 16384u)
+                    bulk_g2s(wslot + (uint32_t)st * TcDense3::kBlock + o, img + (size_t)kb * TcDense3::kBlock + o, 16384u, &s_wfull[st]);
+            }
+            uint8_t* xs = xslot + (uint32_t)st * TcDense3::kBlock;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t rr = (uint32_t)(warp_u * 8 + i);
+                const uint32_t off = swz_off_bf16(rr, 2u * (uint32_t)lane, 128u);
+                float h0 = v[i].x, h1 = v[i].y;
+                uint32_t p1 = pack_bf16x2(h0, h1);
+                h0 -= __uint_as_float(p1 << 16); h1 -= __uint_as_float(p1 & 0xffff0000u);
+                uint32_t p2 = pack_bf16x2(h0, h1);
+                h0 -= __uint_as_float(p2 << 16); h1 -= __uint_as_float(p2 & 0xffff0000u);
+                uint32_t p3 = pack_bf16x2(h0, h1);
+                *reinterpret_cast<uint32_t*>(xs + off) = p1;
+                *reinterpret_cast<uint32_t*>(xs + TcDense3::kPiece + off) = p2;
+                *reinterpret_cast<uint32_t*>(xs + 2u * TcDense3::kPiece + off) = p3;
+            }
+            fence_proxy_async_smem();            // generic-proxy writes -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_xfull[st]);
+            if (kb + 1 < KB) load_x(kb + 1);
+            TC_STAMP(2);
+        }
+        // all MMAs done: the last block's commit covers every earlier one (in-order completion)
+        mbar_wait(&s_free[(KB - 1) & 1], (uint32_t)(((KB - 1) >> 1) & 1));
+        fence_after_thread_sync();
+        TC_STAMP(3);
+
+        // ---- epilogue: lane = channel ----
+        const int quarter = warp_u & 3, slot = warp_u >> 2;          // channels 32*quarter.., rows 32*slot..
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)slot * 32u;
+        const int ch = nt * 128 + quarter * 32 + lane;
+        float acc[32];
+        {
+            uint32_t d[32];
+            tmem_ld32(taddr, d);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(d[q]);
+            const int nacc = KB < 4 ? KB : 4;
+            for (int c = 1; c < nacc; ++c) {
+                tmem_ld32(taddr + (uint32_t)c * 128u, d);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(d[q]);
+            }
+        }
+        const float sc = a.scale ? __ldg(a.scale + ch) : 1.f;
+        const float sh = a.shift ? __ldg(a.shift + ch) : 0.f;
+        if (a.xyz3 != nullptr) {
+            const float w0 = __ldg(a.w3 + ch), w1 = __ldg(a.w3 + a.N + ch), w2 = __ldg(a.w3 + 2 * a.N + ch);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const float* xq = s_xyz[slot * 32 + q];
+                acc[q] = fmaf(xq[2], w2, fmaf(xq[1], w1, fmaf(xq[0], w0, acc[q])));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            float x = fmaf(acc[q], sc, sh);
+            if (a.relu) x = fmaxf(x, 0.f);
+            acc[q] = x;
+        }
+        const long long rbase = row0 + slot * 32;
+        if (a.pool_k == 1) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if (rbase + q < a.rows) a.out[(size_t)(rbase + q) * a.N + ch] = acc[q];       // 32 lanes = 128 contiguous bytes
+        } else {
+            float mx = -FLT_MAX;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) mx = (rbase + q < a.rows) ? fmaxf(mx, acc[q]) : mx;
+            const bool big = a.pool_k > 128;
+            const int slots_per_group = big ? 4 : a.pool_k / 32;         // 1, 2 or 4 row slots per pooling group
+            if (slots_per_group > 1) {
+                s_red[warp_u][lane] = mx;
+                named_bar_sync(1, TcDense3::kPrepWarps * 32);
+                if ((slot % slots_per_group) == 0)
+                    for (int o = 1; o < slots_per_group; ++o) mx = fmaxf(mx, s_red[warp_u + 4 * o][lane]);
+            }
+            if ((slot % slots_per_group) == 0 && rbase < a.rows) {
+                const long long wg = rbase / a.pool_k;
+                if (!big) {
+                    a.out[(size_t)wg * a.N + ch] = mx;
+                } else {
+                    int code = __float_as_int(mx);
+                    code = code >= 0 ? code : code ^ 0x7fffffff;
+                    atomicMax(reinterpret_cast<int*>(a.out) + (size_t)wg * a.N + ch, code);
+                }
+            }
+        }
+    }
+    TC_STAMP(4);
+    fence_before_thread_sync();
+    __syncthreads();
+    TC_STAMP(5);
+#ifdef PSA_TC_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_timing[i], tacc[i]);
+#endif
+    if (warp_u == 0) tmem_dealloc(tmem_base, 512);
+}
+
 bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
     if (rows < 128 || K < 32 || N < 64 || (N % 64) != 0) return false;
     if (N > 64 && (N % 128) != 0) return false;
@@ -1379,6 +1594,7 @@ size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~6
 
 static int g_tc_dense_narrow = 1;
 static int g_tc_dense_v2 = 1;     // 1: pipelined tc_dense2_kernel (bf16x3 images); 0: tc_dense_kernel (psa_set_mlp_mode(2))
+static int g_tc_dense_v3 = 1;     // 1: 128-wide layers with K <= 512 use the transposed tc_dense3_kernel (psa_set_mlp_mode(3): off)
 static int g_tc_sa_dual = 1;      // 0: 128-wide levels fall back to the one-tile-per-CTA wide kernel (psa_set_mlp_mode(2), A/B runs)
 int tc_dense_nt(int N) {
     if (g_tc_dense_v2) return ((N % 128) == 0 ? 128 : 64) | kImageBf16x3;
@@ -1402,6 +1618,13 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
     if (g_tc_dense_v2) {
         dim3 grid2((unsigned)((rows + 127) / 128), N / Nt);
         if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
+        if (Nt == 128 && Kp <= 512 && g_tc_dense_v3) {
+            const size_t smem3 = 4 * (size_t)TcDense3::kBlock + 1024;
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            tc_dense3_kernel<<<grid2, TcDense3::kThreads, smem3, st>>>(a);
+            if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
+            return check_launch("tc_dense3_kernel");
+        }
         const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt) + 1024;      // two slots of two 64-K blocks
         if (Nt == 128) {
             PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

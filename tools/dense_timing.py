@@ -33,7 +33,7 @@ lib = _lib.load()
 if hasattr(lib, "psa_debug_tc_timing"):
     fn_t = lib.psa_debug_tc_timing
     fn_t.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
-    names = ["setup", "prep0", "prep_next", "mma_wait", "drain", "epilogue", "final_sync"]
+    names = ["setup+first x load", "wait stage free", "split+store+next load", "final mma wait", "epilogue", "final_sync", "-"]
     for rows, K, N, pk in [(4096, 256, 256, 1), (4096, 512, 1024, 128)]:
         x = torch.randn((rows, K), device=dev)
         mlp = ops.MlpParams([(torch.randn((K, N), device=dev) * 0.05, torch.ones(N, device=dev), torch.zeros(N, device=dev), True)])
