@@ -20,14 +20,15 @@ pairwise_distance_kernel(int n, int c, const float* __restrict__ x, float* __res
     const int cloud = blockIdx.z;
     const int i0 = blockIdx.y * kPdTile, j0 = blockIdx.x * kPdTile;
     const float* xb = x + (size_t)cloud * n * c;
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    float dot[4][4], sqi[4], sqj[4];
+    // thread = 8 rows (ty + 8a) x 2 columns (tx + 32 b2): a warp's stores are 128 contiguous bytes of one adj row
+    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    float dot[8][2], sqi[8], sqj[2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        sqi[a] = sqj[a] = 0.f;
-#pragma unroll
-        for (int b2 = 0; b2 < 4; ++b2) dot[a][b2] = 0.f;
+    for (int a = 0; a < 8; ++a) {
+        sqi[a] = 0.f;
+        dot[a][0] = dot[a][1] = 0.f;
     }
+    sqj[0] = sqj[1] = 0.f;
     for (int c0 = 0; c0 < c; c0 += kPdCk) {
         const int cc = min(kPdCk, c - c0);
         __syncthreads();
@@ -38,27 +39,27 @@ pairwise_distance_kernel(int n, int c, const float* __restrict__ x, float* __res
         }
         __syncthreads();
         for (int l = 0; l < cc; ++l) {
-            float ai[4], bj[4];
+            const float b0 = Xj[tx][l], b1 = Xj[tx + 32][l];
+            sqj[0] = __fmaf_rn(b0, b0, sqj[0]);
+            sqj[1] = __fmaf_rn(b1, b1, sqj[1]);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { ai[a] = Xi[ty + 16 * a][l]; bj[a] = Xj[tx + 16 * a][l]; }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                sqi[a] = __fmaf_rn(ai[a], ai[a], sqi[a]);
-                sqj[a] = __fmaf_rn(bj[a], bj[a], sqj[a]);
-#pragma unroll
-                for (int b2 = 0; b2 < 4; ++b2) dot[a][b2] = __fmaf_rn(ai[a], bj[b2], dot[a][b2]);
+            for (int a = 0; a < 8; ++a) {
+                const float ai = Xi[ty + 8 * a][l];             // warp-uniform address: broadcast
+                sqi[a] = __fmaf_rn(ai, ai, sqi[a]);
+                dot[a][0] = __fmaf_rn(ai, b0, dot[a][0]);
+                dot[a][1] = __fmaf_rn(ai, b1, dot[a][1]);
             }
         }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int i = i0 + ty + 16 * a;
+    for (int a = 0; a < 8; ++a) {
+        const int i = i0 + ty + 8 * a;
         if (i >= n) continue;
 #pragma unroll
-        for (int b2 = 0; b2 < 4; ++b2) {
-            const int j = j0 + tx + 16 * b2;
-            if (j < n)
-                adj[((size_t)cloud * n + i) * n + j] = __fadd_rn(__fadd_rn(sqi[a], __fmul_rn(-2.0f, dot[a][b2])), sqj[b2]);
+        for (int b2 = 0; b2 < 2; ++b2) {
+            const int j = j0 + tx + 32 * b2;
+            if (j < n)     // streaming store: the (B,N,N) matrix is larger than L2 and read once
+                __stcs(adj + ((size_t)cloud * n + i) * n + j, __fadd_rn(__fadd_rn(sqi[a], __fmul_rn(-2.0f, dot[a][b2])), sqj[b2]));
         }
     }
 }
@@ -87,6 +88,46 @@ __device__ __forceinline__ void topk_rounds(const float* row, int ncols, int k, 
 }
 
 constexpr int kTopkWarps = 4;
+
+// top-k of a row streamed ONCE from global memory (k <= 32): the warp keeps the k best as a sorted list, one (value, index)
+// per lane; a candidate enters only if it beats the k-th by (value, index) -- candidates arrive in index order, so equal
+// values keep the lower index first like tf.nn.top_k -- placed by popc(ballot(list < cand)) and a shuffle-up shift.
+// Expected k(1 + ln(n/k)) insertions per row instead of k full passes.
+constexpr int kTopk2Warps = 8;
+__global__ void __launch_bounds__(kTopk2Warps * 32)
+knn_topk_stream_kernel(long long rows, int ncols, int k, const float* __restrict__ adj, int* __restrict__ nn_idx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    for (long long r = (long long)blockIdx.x * kTopk2Warps + warp; r < rows; r += (long long)gridDim.x * kTopk2Warps) {
+        const float* row = adj + r * ncols;
+        float lv = inf;
+        int li = 0x7fffffff;                               // empty slot: loses against every real (value, index)
+        float thr_v = inf;
+        int thr_i = 0x7fffffff;
+        float nxt = lane < ncols ? __ldcs(row + lane) : 0.f;
+        for (int t0 = 0; t0 < ncols; t0 += 32) {
+            const float cv = nxt;
+            const int ci = t0 + lane;
+            if (t0 + 32 + lane < ncols) nxt = __ldcs(row + t0 + 32 + lane);
+            unsigned mask = __ballot_sync(0xffffffffu, ci < ncols && (cv < thr_v || (cv == thr_v && ci < thr_i)));
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float bv = __shfl_sync(0xffffffffu, cv, src);
+                const int bi = __shfl_sync(0xffffffffu, ci, src);
+                if (!(bv < thr_v || (bv == thr_v && bi < thr_i))) continue;          // the k-th best tightened meanwhile
+                const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && (lv < bv || (lv == bv && li < bi))));
+                const float pv = __shfl_up_sync(0xffffffffu, lv, 1);
+                const int pi = __shfl_up_sync(0xffffffffu, li, 1);
+                if (lane > pos) { lv = pv; li = pi; }
+                else if (lane == pos) { lv = bv; li = bi; }
+                thr_v = __shfl_sync(0xffffffffu, lv, k - 1);
+                thr_i = __shfl_sync(0xffffffffu, li, k - 1);
+            }
+        }
+        if (lane < k) nn_idx[r * k + lane] = li == 0x7fffffff ? 0 : li;
+    }
+}
 
 __global__ void __launch_bounds__(kTopkWarps * 32)
 knn_topk_kernel(long long rows, int ncols, int k, const float* __restrict__ adj, int* __restrict__ nn_idx) {
@@ -242,6 +283,29 @@ knn_graph_kernel(int n, int c, int k, const float* __restrict__ x, int* __restri
     }
 }
 
+// edge[b,i,j,:] = [x_i, x_{nn(i,j)} - x_i], vectorised: 2c/4 threads per edge row, one index computation per row,
+// float4 streaming stores (the (B,N,k,2C) tensor is written once and is larger than L2)
+__global__ void __launch_bounds__(256)
+edge_feature_vec_kernel(int n, int c4, int k, long long rows, const float4* __restrict__ x, const int* __restrict__ nn_idx,
+                        float4* __restrict__ out) {
+    const int tpr = 2 * c4;                                   // threads per edge row
+    const int rpb = 256 / tpr;                                // rows per block iteration
+    const int lr = threadIdx.x / tpr, l = threadIdx.x - lr * tpr;
+    if (lr >= rpb) return;
+    for (long long row = (long long)blockIdx.x * rpb + lr; row < rows; row += (long long)gridDim.x * rpb) {
+        const long long pi = row / k;                         // b*n + i
+        const float4 xi = __ldg(x + pi * c4 + (l < c4 ? l : l - c4));
+        float4 v = xi;
+        if (l >= c4) {
+            const long long bi = pi / n;
+            const int j = __ldg(nn_idx + row);
+            const float4 xj = __ldg(x + (bi * n + j) * c4 + (l - c4));
+            v = make_float4(xj.x - xi.x, xj.y - xi.y, xj.z - xi.z, xj.w - xi.w);
+        }
+        __stcs(out + row * tpr + l, v);
+    }
+}
+
 // edge[b,i,j,:] = [x_i, x_{nn(i,j)} - x_i]
 __global__ void edge_feature_kernel(int n, int c, int k, long long total, const float* __restrict__ x,
                                     const int* __restrict__ nn_idx, float* __restrict__ out) {
@@ -287,6 +351,12 @@ extern "C" int psa_knn_topk(int b, int n, int ncols, int k, const float* adj, in
     long long rows = (long long)b * n;
     if (rows == 0 || k == 0) return PSA_OK;
     PSA_REQUIRE(adj && nn_idx, "knn: null buffer");
+    if (k <= 32) {
+        long long g2 = (rows + kTopk2Warps - 1) / kTopk2Warps;
+        if (g2 > (long long)kNumSMs * 16) g2 = (long long)kNumSMs * 16;
+        knn_topk_stream_kernel<<<(int)g2, kTopk2Warps * 32, 0, as_stream(stream)>>>(rows, ncols, k, adj, nn_idx);
+        return check_launch("knn_topk_stream_kernel");
+    }
     size_t smem = (size_t)kTopkWarps * ncols * sizeof(float);
     PSA_SUPPORTED(smem <= 200 * 1024, "knn: row length %d exceeds the shared-memory resident limit", ncols);
     PSA_CUDA(cudaFuncSetAttribute(knn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -317,6 +387,15 @@ extern "C" int psa_get_edge_feature(int b, int n, int c, int k, const float* x, 
     long long total = (long long)b * n * k * 2 * c;
     if (total == 0) return PSA_OK;
     PSA_REQUIRE(x && nn_idx && out, "get_edge_feature: null buffer");
+    if ((c % 4) == 0 && c <= 512 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const long long rows = (long long)b * n * k;
+        const int rpb = 256 / (c / 2);
+        long long g = (rows + rpb - 1) / rpb;
+        if (g > (long long)kNumSMs * 32) g = (long long)kNumSMs * 32;
+        edge_feature_vec_kernel<<<(int)g, 256, 0, as_stream(stream)>>>(n, c / 4, k, rows, reinterpret_cast<const float4*>(x), nn_idx,
+                                                                       reinterpret_cast<float4*>(out));
+        return check_launch("edge_feature_vec_kernel");
+    }
     edge_feature_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(n, c, k, total, x, nn_idx, out);
     return check_launch("edge_feature_kernel");
 }
