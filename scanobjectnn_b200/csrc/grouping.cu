@@ -125,26 +125,134 @@ selection_sort_kernel(long long rows, int n, int k, const float* __restrict__ di
     }
 }
 
+// One streaming pass over a row of distances keeps the k smallest (value, index) sorted, one per lane (k <= 32), and the
+// smallest value that did NOT make the list (rejected on arrival or evicted later) = the (k+1)-th smallest of the row.
+// If the k list values are pairwise distinct and the k-th is strictly below that runner-up, the selection sort's result
+// does not depend on its swaps -- it IS this list -- and it is written; any tie (duplicate points), NaN or unfilled slot
+// returns false and the exact swap-by-swap rounds decide, as in the reference.  `dist(t)` = this lane's candidate t < n.
+template <class DistFn>
+__device__ __forceinline__ bool knn_fast_path(int n, int k, DistFn dist, int lane, float* __restrict__ val_out, int* __restrict__ idx_out) {
+    const float inf = __int_as_float(0x7f800000);
+    float lv = inf, thr_v = inf;
+    int li = 0x7fffffff, thr_i = 0x7fffffff;
+    float rej = inf;                  // per lane: smallest candidate this lane saw rejected; lane-uniform part folded in below
+    float ev = inf;                   // uniform: smallest value evicted from / re-checked out of the list
+    bool bad = false;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int ci = t0 + lane;
+        const float cv = ci < n ? dist(ci) : inf;
+        bad = bad || (cv != cv);
+        const bool want = ci < n && (cv < thr_v || (cv == thr_v && ci < thr_i));
+        if (ci < n && !want) rej = fminf(rej, cv);
+        unsigned mask = __ballot_sync(0xffffffffu, want);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float bv = __shfl_sync(0xffffffffu, cv, src);
+            const int bi = __shfl_sync(0xffffffffu, ci, src);
+            if (!(bv < thr_v || (bv == thr_v && bi < thr_i))) { ev = fminf(ev, bv); continue; }
+            ev = fminf(ev, thr_v);                                // the current k-th falls out (inf while the list is filling)
+            const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && (lv < bv || (lv == bv && li < bi))));
+            const float pv = __shfl_up_sync(0xffffffffu, lv, 1);
+            const int pi = __shfl_up_sync(0xffffffffu, li, 1);
+            if (lane > pos) { lv = pv; li = pi; }
+            else if (lane == pos) { lv = bv; li = bi; }
+            thr_v = __shfl_sync(0xffffffffu, lv, k - 1);
+            thr_i = __shfl_sync(0xffffffffu, li, k - 1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rej = fminf(rej, __shfl_xor_sync(0xffffffffu, rej, o));
+    const float runner_up = fminf(rej, ev);
+    const float nv = __shfl_down_sync(0xffffffffu, lv, 1);
+    const bool tie = (lane + 1 < k) && !(lv < nv);            // equal neighbours: not provably distinct
+    const bool unfilled = lane < k && li == 0x7fffffff;
+    const bool edge = !(thr_v < runner_up) && n > k;           // the k-th ties with (or is inf like) the best outsider
+    if (__any_sync(0xffffffffu, tie || unfilled || bad) || edge) return false;
+    if (lane < k) { val_out[lane] = lv; idx_out[lane] = li; }
+    return true;
+}
+
+// Fast pass of knn_point: CTA = one cloud (staged in shared memory) x a chunk of its queries, 8 warps, distances computed
+// on the fly, no per-row buffers -> many warps per SM hide the serial shuffle chains of the list insertions.
+// Rows it cannot decide (ties) are flagged with idx[r*k] = -1 for knn_point_kernel.
+constexpr int kKnnFastWarps = 8;
+__global__ void __launch_bounds__(kKnnFastWarps * 32)
+knn_point_fast_kernel(int n, int m, int c, int k, int q_per_cta, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                      float* __restrict__ val, int* __restrict__ idx) {
+    extern __shared__ float smem_f[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = blockIdx.y;
+    const float* pg = xyz1 + (size_t)bi * n * c;
+    for (int t = threadIdx.x; t < n * c; t += kKnnFastWarps * 32) smem_f[t] = __ldg(pg + t);
+    __syncthreads();
+    const float* p = smem_f;
+    const int q0 = blockIdx.x * q_per_cta;
+    const int q1 = min(m, q0 + q_per_cta);
+    for (int qi = q0 + warp; qi < q1; qi += kKnnFastWarps) {
+        const long long r = (long long)bi * m + qi;
+        const float* q = xyz2 + r * c;
+        bool done;
+        if (c == 3) {
+            const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+            done = knn_fast_path(n, k, [&](int t) {
+                const float dx = __fsub_rn(p[3 * t], qx), dy = __fsub_rn(p[3 * t + 1], qy), dz = __fsub_rn(p[3 * t + 2], qz);
+                return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            }, lane, val + r * k, idx + r * k);
+        } else {
+            done = knn_fast_path(n, k, [&](int t) {
+                float sacc = 0.f;
+                for (int l = 0; l < c; ++l) {
+                    const float df = __fsub_rn(p[(size_t)t * c + l], __ldg(q + l));
+                    sacc = __fadd_rn(sacc, __fmul_rn(df, df));
+                }
+                return sacc;
+            }, lane, val + r * k, idx + r * k);
+        }
+        if (!done && lane == 0) idx[r * k] = -1;
+    }
+}
+
 // knn_point (tf_grouping.py:49-74) fused: distances sum_c (x1-x2)^2 (sequential, un-contracted) built straight
-// into the warp's shared-memory row, then the same selection rounds; only the first k are written.
+// into the warp's shared-memory row, then the fast path above or the reference's selection rounds; only the first k
+// are written.  CTA = one cloud (staged once in shared memory) x a chunk of its queries, one query per warp at a time.
 __global__ void __launch_bounds__(kSelWarps * 32)
-knn_point_kernel(int n, int m, int c, int k, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                 float* __restrict__ val, int* __restrict__ idx, long long rows) {
+knn_point_kernel(int n, int m, int c, int k, int q_per_cta, int stage_cloud, int only_flagged, const float* __restrict__ xyz1,
+                 const float* __restrict__ xyz2, float* __restrict__ val, int* __restrict__ idx) {
     extern __shared__ float smem_f[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* v = smem_f + (size_t)warp * n * 2;
     int* id = reinterpret_cast<int*>(v + n);
-    for (long long r = (long long)blockIdx.x * kSelWarps + warp; r < rows; r += (long long)gridDim.x * kSelWarps) {
-        const long long bi = r / m;
+    float* cloud = smem_f + (size_t)kSelWarps * n * 2;           // (n, c) when staged
+    const int bi = blockIdx.y;
+    const float* p = xyz1 + (size_t)bi * n * c;
+    if (stage_cloud) {
+        for (int t = threadIdx.x; t < n * c; t += kSelWarps * 32) cloud[t] = __ldg(p + t);
+        __syncthreads();
+        p = cloud;
+    }
+    const int q0 = blockIdx.x * q_per_cta;
+    const int q1 = min(m, q0 + q_per_cta);
+    for (int qi = q0 + warp; qi < q1; qi += kSelWarps) {
+        const long long r = (long long)bi * m + qi;
+        if (only_flagged && idx[r * k] != -1) continue;          // decided by knn_point_fast_kernel (warp-uniform)
         const float* q = xyz2 + r * c;
-        const float* p = xyz1 + bi * n * c;
-        for (int t = lane; t < n; t += 32) {
-            float s = 0.f;
-            for (int l = 0; l < c; ++l) {
-                float df = __fsub_rn(__ldg(p + (size_t)t * c + l), __ldg(q + l));
-                s = __fadd_rn(s, __fmul_rn(df, df));
+        if (c == 3) {
+            const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+            for (int t = lane; t < n; t += 32) {
+                const float dx = __fsub_rn(p[3 * t], qx), dy = __fsub_rn(p[3 * t + 1], qy), dz = __fsub_rn(p[3 * t + 2], qz);
+                v[t] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                id[t] = t;
             }
-            v[t] = s; id[t] = t;
+        } else {
+            for (int t = lane; t < n; t += 32) {
+                float sacc = 0.f;
+                for (int l = 0; l < c; ++l) {
+                    float df = __fsub_rn(p[(size_t)t * c + l], __ldg(q + l));
+                    sacc = __fadd_rn(sacc, __fmul_rn(df, df));
+                }
+                v[t] = sacc; id[t] = t;
+            }
         }
         __syncwarp();
         selection_rounds(n, k, v, id, lane);
@@ -253,9 +361,22 @@ extern "C" int psa_knn_point(int b, int n, int m, int c, int k, const float* xyz
     PSA_REQUIRE(xyz1 && xyz2 && val && idx, "knn_point: null buffer");
     size_t smem = (size_t)kSelWarps * n * 2 * sizeof(float);
     PSA_SUPPORTED(smem <= 200 * 1024, "knn_point: n=%d exceeds the shared-memory resident limit", n);
+    PSA_SUPPORTED(b <= 65535, "knn_point: b=%d exceeds gridDim.y", b);
+    const size_t cloud_bytes = (size_t)n * c * sizeof(float);
+    const int stage_cloud = (smem + cloud_bytes <= 100 * 1024) ? 1 : 0;      // keep two CTAs per SM
+    if (stage_cloud) smem += cloud_bytes;
     PSA_CUDA(cudaFuncSetAttribute(knn_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (int)((rows + kSelWarps - 1) / kSelWarps);
-    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    knn_point_kernel<<<grid, kSelWarps * 32, smem, as_stream(stream)>>>(n, m, c, k, xyz1, xyz2, val, idx, rows);
+    int chunks = (2 * kNumSMs + b - 1) / b;
+    int q_per_cta = (m + chunks - 1) / chunks;
+    q_per_cta = ((q_per_cta + kKnnFastWarps - 1) / kKnnFastWarps) * kKnnFastWarps;
+    dim3 grid((m + q_per_cta - 1) / q_per_cta, b);
+    // fast pass first (distinct distances: the common case), then the reference's selection rounds for the rows it flagged
+    const int fast = (k <= 32 && cloud_bytes <= 48 * 1024) ? 1 : 0;
+    if (fast) {
+        knn_point_fast_kernel<<<grid, kKnnFastWarps * 32, cloud_bytes, as_stream(stream)>>>(n, m, c, k, q_per_cta, xyz1, xyz2, val, idx);
+        int rc = check_launch("knn_point_fast_kernel");
+        if (rc != PSA_OK) return rc;
+    }
+    knn_point_kernel<<<grid, kSelWarps * 32, smem, as_stream(stream)>>>(n, m, c, k, q_per_cta, stage_cloud, fast, xyz1, xyz2, val, idx);
     return check_launch("knn_point_kernel");
 }
