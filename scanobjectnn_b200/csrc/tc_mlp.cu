@@ -1,26 +1,30 @@
-// tc_mlp.cu -- the grouped shared MLP of a set-abstraction level on the 5th-gen tensor cores (tcgen05 + TMEM).
+// tc_mlp.cu -- the grouped shared MLP of a set-abstraction level and the dense layers on the 5th-gen tensor cores
+// (tcgen05 + TMEM), hand-written PTX wrappers in tc_common.cuh.
 //
 // What the reference does (pointnet2/utils/pointnet_util.py:113-127): group_point -> (B,m,K,3+C) tensor -> three
-// cuDNN 1x1 convs over B*m*K rows -> reduce_max.  What this kernel does per 128-row tile (128/K neighbourhoods):
+// cuDNN 1x1 convs over B*m*K rows -> reduce_max.  What the kernels here do per 128-row tile (128/K neighbourhoods):
 //
 //   layer 1   is never a GEMM over grouped rows.  (x_j - c) . Wx + f_j . Wf  =  U[j] + (x_j - c) . Wx   with
-//             U = points . W1[3:,:] computed ONCE per source point (K-fold fewer rows, psa_sa_module_infer does it
-//             with the dense kernel); each row-thread gathers its U row (512 B), adds the 3-term xyz part in FMAs,
-//             applies the folded BN affine + ReLU, and writes the result straight into TENSOR MEMORY as the A operand
-//             of layer 2 -- the (B,m,K,C) tensors of the reference never exist, not even in shared memory.
+//             U = points . W1[3:,:] computed ONCE per source point (K-fold fewer rows, a dense-layer launch); each
+//             row-thread gathers its U row (512 B), adds the 3-term xyz part in FMAs, applies the folded BN affine + ReLU
+//             and writes the result straight into TENSOR MEMORY as the A operand of layer 2 -- the (B,m,K,C) tensors of
+//             the reference never exist, not even in shared memory.
 //   layers 2+ tcgen05.mma, A from TMEM (lane = row), B = weights in shared memory in the canonical K-major SWIZZLE_128B
-//             layout, dropped there by cp.async.bulk from pre-arranged images: RESIDENT for the whole persistent CTA,
-//             except that a last layer too big to fit is streamed one 128-channel tile at a time (L2 -> smem while the
-//             row warps run the previous epilogue), D in TMEM.  Between layers the
-//             four row-warps pull D with tcgen05.ld, apply affine + ReLU, and push the next A operand with tcgen05.st.
-//   max-pool  the last epilogue reduces each neighbourhood's rows with a transposing warp butterfly (31 shuffles per
-//             32 columns) and writes (B,m,C_out) coalesced.
+//             layout, dropped there by cp.async.bulk from pre-arranged images; D in TMEM.  Between layers the row warps
+//             pull D with tcgen05.ld, apply affine + ReLU and push the next A operand with tcgen05.st.
+//   max-pool  the last epilogue reduces each neighbourhood's rows with a transposing warp butterfly and writes
+//             (B,m,C_out) coalesced.
 //
-// fp32 parity on tf32/bf16 tensor cores: every product a*w is evaluated as three exactly-representable pieces
-//   trunc_tf32(a)*trunc_tf32(w) + tf32(a - trunc(a))*trunc_tf32(w) + bf16(a)*bf16(w - trunc(w))
-// (operands quantised by this code, so the tensor core sees exact values; fp32 accumulation in TMEM).  Operand-split
-// error ~3e-6 relative (tests/test_mlp_gpu.py holds the whole chain to 1e-5 against fp64).  The bf16 third term keeps
-// the weights at 6 B/element: PointNet++'s 128->128->256 level keeps W2 (96 KB) resident and streams W3 in two 96 KB tiles.
+// Kernels (default path first):
+//   tc_sa_dual_kernel<DBUF>   SA level, two row groups per CTA, bf16x3 operands (three exact bf16 pieces per operand, six
+//                             MMAs per product), per-group streamed last layer, tensor-pipe token, two D slots (DBUF)
+//   tc_dense3_kernel          dense layer, transposed (lane = channel), both operands from shared memory
+//   tc_dense2_kernel          dense layer, A from TMEM, warp-specialised pipeline (N = 64 or K > 512)
+//   tc_sa_kernel<NARROW>, tc_dense_kernel<NARROW>   the round's first generation (tf32/tf32/bf16 three-term split:
+//                             trunc_tf32(a)*trunc_tf32(w) + tf32(a-trunc a)*trunc_tf32(w) + bf16(a)*bf16(w-trunc w)),
+//                             kept behind psa_set_mlp_mode(2) for A/B runs and as a second implementation in the tests
+// fp32 parity: operands are quantised by this code, so the tensor core only ever sees exactly representable values; fp32
+// accumulation in TMEM truncates, hence small terms first and K cut into <= 128-wide pieces (tests hold 1e-5 vs fp64).
 #include <float.h>
 
 #include "common.cuh"
