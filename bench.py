@@ -326,7 +326,9 @@ def main():
         nn3_d, nn3_i = ops.three_nn(xq, l1x)
         w3 = torch.full((B, N, 3), 1.0 / 3, device=dev)
         adj = ops.pairwise_distance(xq)
+        aug = ops.draw_augmentation(B, N, N, dev)
         opcases = {
+            "augment_batch_subset_rotate_jitter": (lambda: ops.augment_batch(xq, N, **aug), None, B * (12 * N + 12 * N + 12 * N) + 4 * N),
             "farthest_point_sample_2048to512": (lambda: ops.farthest_point_sample(512, xq), None, B * (12 * N + 4 * 512)),
             "gather_point_512": (lambda: ops.gather_point(xq, fidx), None, B * (12 * N + 4 * 512 + 12 * 512)),
             "query_ball_point_r0.2_k32": (lambda: ops.query_ball_point(0.2, 32, xq, l1x), None, B * (12 * N + 12 * 512 + 4 * 512 * 32 + 4 * 512)),

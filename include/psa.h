@@ -128,6 +128,18 @@ PSA_API int psa_three_nn_interpolate(int b, int n, int m, int c, const float* xy
                              psa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * input pipeline  (data_utils.py:133-186, pointnet2/utils/provider.py:34-52,189-236, train.py:246-252 -- numpy on the
+ * host in the reference, one kernel here).  src (b,n_src,3) -> out (b,n,3):
+ *   [center over all n_src points] -> [divide by the max norm] -> gather perm[0..n) (same subset for every cloud; NULL =
+ *   the first n points) -> [dropout: dropped points := the cloud's first batch point] -> [rotate about the up axis by
+ *   (cos,sin) given in double, float64 product] -> [scale (b)] -> [shift (b,3)] -> [+ clip(sigma * noise, -clip, clip),
+ *   float64 sum].  Every optional input may be NULL (step skipped).  The random numbers are inputs; see ops.augment_batch.
+ * ------------------------------------------------------------------------------------------- */
+PSA_API int psa_augment_batch(int b, int n_src, int n, const float* src, const int* perm, const double* cos_sin,
+                              const float* scale, const float* shift, const float* noise, float sigma, float clip,
+                              const unsigned char* drop, int center, int normalize, float* out, psa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * dgcnn graph functions  (dgcnn/utils/tf_util.py:638-706 -- TF library ops in the reference)
  * ------------------------------------------------------------------------------------------- */
 

@@ -192,6 +192,57 @@ def knn_point(k: int, xyz1: torch.Tensor, xyz2: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------------
+# input pipeline (data_utils.py / provider.py of the reference, numpy on the host there)
+# ------------------------------------------------------------------------------------------------
+def augment_batch(src: torch.Tensor, n: int | None = None, *, perm=None, angles=None, scale=None, shift=None, noise=None,
+                  sigma: float = 0.01, clip: float = 0.05, drop=None, center: bool = False, normalize: bool = False) -> torch.Tensor:
+    """center_data / normalize_data (data_utils.py:133-168) over the whole source cloud, the epoch's point subset
+    (get_current_data_h5, data_utils.py:171-186: ``perm[:n]``, the same for every cloud), then per batch
+    rotate_point_cloud about the up axis (provider.py:34-52, ``angles`` (B,) radians), [random_scale / shift_point_cloud,
+    provider.py:202-227], jitter_point_cloud (provider.py:189-200, ``noise`` (B,n,3) standard normal) and
+    [random_point_dropout, provider.py:229-236, ``drop`` (B,n) bool] -- in one launch, same order and precisions.
+    src (B,N_src,3) float32 -> (B,n,3).  The random numbers are arguments: draw them with ``draw_augmentation``."""
+    src = _dev(src, torch.float32, "src", 3)
+    if src.shape[2] != 3:
+        raise ValueError("augment_batch expects (batch, num_points, 3) input")
+    b, n_src, _ = src.shape
+    n = n_src if n is None else int(n)
+    dev = src.device
+    cs = None
+    if angles is not None:
+        ang = torch.as_tensor(angles, dtype=torch.float64).reshape(b).cpu()            # cos / sin in float64 like numpy
+        cs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).contiguous().to(dev)
+    perm_t = None if perm is None else _dev(torch.as_tensor(perm, device=dev), torch.int32, "perm", 1)
+    if perm_t is not None and perm_t.numel() < n:
+        raise ValueError("augment_batch: perm is shorter than n")
+    if perm_t is None and n > n_src:
+        raise ValueError("augment_batch: n exceeds the source cloud")
+    scale_t = None if scale is None else _dev(torch.as_tensor(scale, device=dev), torch.float32, "scale", 1)
+    shift_t = None if shift is None else _dev(torch.as_tensor(shift, device=dev), torch.float32, "shift", 2)
+    noise_t = None if noise is None else _dev(torch.as_tensor(noise, device=dev), torch.float32, "noise", 3)
+    drop_t = None if drop is None else torch.as_tensor(drop, device=dev).to(torch.uint8).contiguous()
+    if noise_t is not None and not clip > 0:
+        raise ValueError("jitter_point_cloud: clip must be positive")                  # provider.py:196 assert(clip > 0)
+    out = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+    check(_lib.load().psa_augment_batch(b, n_src, n, _ptr(src), _ptr(perm_t), _ptr(cs), _ptr(scale_t), _ptr(shift_t), _ptr(noise_t),
+                                        C.c_float(sigma), C.c_float(clip), _ptr(drop_t), int(bool(center)), int(bool(normalize)),
+                                        _ptr(out), _stream()), "augment_batch")
+    return out
+
+
+def draw_augmentation(b: int, n_src: int, n: int, device, generator: torch.Generator | None = None, jitter: bool = True):
+    """The random numbers of one training batch as the reference draws them (one point subset per epoch, one angle per
+    cloud, one normal sample per coordinate), on the device: dict for ``augment_batch(**...)``."""
+    g = generator
+    perm = torch.randperm(n_src, device=device, generator=g)[:n].to(torch.int32)
+    angles = torch.rand(b, device=device, generator=g, dtype=torch.float64) * (2.0 * 3.141592653589793)
+    out = {"perm": perm, "angles": angles}
+    if jitter:
+        out["noise"] = torch.randn((b, n, 3), device=device, generator=g)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # 3d interpolation
 # ------------------------------------------------------------------------------------------------
 def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):

@@ -33,7 +33,11 @@ def mlp_mode(request):
 
 @pytest.mark.parametrize("rows,pool_k,chans", [(256, 1, [7, 64]), (4096, 128, [259, 256, 512, 1024]), (32, 1, [1024, 512, 256, 15]),
                                                (300, 1, [131, 128, 40]), (640, 32, [64, 64]), (2 * 2048, 2048, [320, 1024]),
-                                               (1280, 8, [6, 64, 128])])
+                                               (1280, 8, [6, 64, 128]),
+                                               # dense tensor-core kernels, edge shapes: partial row tile + K tail; odd K (scalar x loads);
+                                               # pool 32 / 64 / 256 (atomicMax path); K > 512 and N = 64 (TMEM-A kernel); 8 K-blocks x 3 n-tiles
+                                               (1000, 1, [100, 128]), (1000, 1, [99, 256]), (1024, 32, [64, 128, 256]), (1024, 64, [128, 128]),
+                                               (512, 256, [200, 128]), (384, 1, [576, 128]), (384, 1, [64, 64]), (130, 1, [512, 384])])
 def test_shared_mlp_matches_fp64(rows, pool_k, chans):
     p = _store(rows)
     scopes = []
