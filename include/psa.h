@@ -136,7 +136,7 @@ PSA_API int psa_three_nn_interpolate(int b, int n, int m, int c, const float* xy
  *   float64 sum].  Every optional input may be NULL (step skipped).  The random numbers are inputs; see ops.augment_batch.
  * ------------------------------------------------------------------------------------------- */
 PSA_API int psa_augment_batch(int b, int n_src, int n, const float* src, const int* perm, const double* cos_sin,
-                              const float* scale, const float* shift, const float* noise, float sigma, float clip,
+                              const float* scale, const float* shift, const float* noise, double sigma, double clip,
                               const unsigned char* drop, int center, int normalize, float* out, psa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

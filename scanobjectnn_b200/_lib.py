@@ -48,7 +48,7 @@ SIGNATURES = {
     "psa_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "psa_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "psa_three_nn_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
-    "psa_augment_batch": [_i, _i, _i, _p, _p, _p, _p, _p, _p, C.c_float, C.c_float, _p, _i, _i, _p, _p],
+    "psa_augment_batch": [_i, _i, _i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, _p, _i, _i, _p, _p],
     "psa_pairwise_distance": [_i, _i, _i, _p, _p, _p],
     "psa_knn_topk": [_i, _i, _i, _i, _p, _p, _p],
     "psa_knn_graph": [_i, _i, _i, _i, _p, _p, _p],

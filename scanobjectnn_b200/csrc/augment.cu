@@ -29,7 +29,7 @@ struct AugArgs {
     const float* shift;      // (b, 3) or null
     const float* noise;      // (b, n, 3) standard normal, or null
     const unsigned char* drop;   // (b, n) 1 = dropped (replaced by the cloud's first output point before scaling), or null
-    float sigma, clip;
+    double sigma, clip;      // Python floats in the reference (float64)
     int center, normalize;
     float* out;              // (b, n, 3)
 };
@@ -100,7 +100,7 @@ augment_kernel(const AugArgs a) {
         if (a.noise) {
             // float64 jitter added to the float32 data in float64, then fed as float32 (provider.py:197-199)
             const float* nz = a.noise + ((size_t)bi * a.n + i) * 3;
-            const double sg = (double)a.sigma, cl = (double)a.clip;
+            const double sg = a.sigma, cl = a.clip;
             const double jx = fmin(fmax(sg * (double)__ldg(nz), -cl), cl), jy = fmin(fmax(sg * (double)__ldg(nz + 1), -cl), cl),
                          jz = fmin(fmax(sg * (double)__ldg(nz + 2), -cl), cl);
             x = (float)(jx + (double)x); y = (float)(jy + (double)y); z = (float)(jz + (double)z);
@@ -114,11 +114,11 @@ augment_kernel(const AugArgs a) {
 using namespace psa;
 
 extern "C" int psa_augment_batch(int b, int n_src, int n, const float* src, const int* perm, const double* cos_sin,
-                                 const float* scale, const float* shift, const float* noise, float sigma, float clip,
+                                 const float* scale, const float* shift, const float* noise, double sigma, double clip,
                                  const unsigned char* drop, int center, int normalize, float* out, psa_stream_t stream) {
     PSA_REQUIRE(b >= 0 && n_src >= 1 && n >= 0, "augment_batch: bad dims b=%d n_src=%d n=%d", b, n_src, n);
     PSA_REQUIRE(perm != nullptr || n <= n_src, "augment_batch: n=%d exceeds the source cloud (%d points) and no index list is given", n, n_src);
-    PSA_REQUIRE(noise == nullptr || clip > 0.f, "augment_batch: clip must be positive (provider.py:196)");
+    PSA_REQUIRE(noise == nullptr || clip > 0.0, "augment_batch: clip must be positive (provider.py:196)");
     if (b == 0 || n == 0) return PSA_OK;
     PSA_REQUIRE(src && out, "augment_batch: null buffer");
     AugArgs a;

@@ -210,8 +210,11 @@ def augment_batch(src: torch.Tensor, n: int | None = None, *, perm=None, angles=
     dev = src.device
     cs = None
     if angles is not None:
-        ang = torch.as_tensor(angles, dtype=torch.float64).reshape(b).cpu()            # cos / sin in float64 like numpy
-        cs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).contiguous().to(dev)
+        if isinstance(angles, torch.Tensor) and angles.is_cuda:                        # stay on the device: no host sync per batch
+            ang = angles.to(torch.float64).reshape(b)
+        else:
+            ang = torch.as_tensor(angles, dtype=torch.float64).reshape(b)              # host libm, bit-identical to numpy's
+        cs = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).contiguous().to(dev)  # cos / sin in float64 like numpy
     perm_t = None if perm is None else _dev(torch.as_tensor(perm, device=dev), torch.int32, "perm", 1)
     if perm_t is not None and perm_t.numel() < n:
         raise ValueError("augment_batch: perm is shorter than n")
@@ -225,7 +228,7 @@ def augment_batch(src: torch.Tensor, n: int | None = None, *, perm=None, angles=
         raise ValueError("jitter_point_cloud: clip must be positive")                  # provider.py:196 assert(clip > 0)
     out = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
     check(_lib.load().psa_augment_batch(b, n_src, n, _ptr(src), _ptr(perm_t), _ptr(cs), _ptr(scale_t), _ptr(shift_t), _ptr(noise_t),
-                                        C.c_float(sigma), C.c_float(clip), _ptr(drop_t), int(bool(center)), int(bool(normalize)),
+                                        C.c_double(sigma), C.c_double(clip), _ptr(drop_t), int(bool(center)), int(bool(normalize)),
                                         _ptr(out), _stream()), "augment_batch")
     return out
 
