@@ -379,7 +379,7 @@ def main():
         # share of the level's flops that runs on the tensor cores (layers after the first); each fp32 product is six bf16 MMAs
         tc_flops = {"sa1_mlp": 2 * 524288 * (64 * 64 + 64 * 128), "sa2_mlp": 2 * 262144 * (128 * 128 + 128 * 256) + 2 * 16384 * 128 * 128,
                     "sa3_mlp": 2 * 4096 * (256 * 256 + 256 * 512 + 512 * 1024)}[dom]
-        # dram__bytes_read.sum + dram__bytes_write.sum of the level's dominant launch, from profiles/r01_ncu_final_summary.md
+        # dram__bytes_read.sum + dram__bytes_write.sum of the level's dominant launch, from profiles/r01_ncu_final2_tensor_kernels.md
         traffic = {"sa1_mlp": 3.54e6, "sa2_mlp": 10.41e6, "sa3_mlp": 11.59e6}[dom]
         roofline = {"kernel": dom + " (tc_sa_dual_kernel + its per-source-point first-layer GEMM)" if dom != "sa3_mlp" else dom + " (3 x tc_dense2_kernel)",
                     "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
