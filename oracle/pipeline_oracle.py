@@ -61,11 +61,14 @@ def augment(src, n, perm=None, angles=None, scale=None, shift=None, noise=None, 
     if angles is not None:
         x = rotate_point_cloud(x, np.asarray(angles, np.float64))
     if scale is not None:
+        # provider.py:222-226 `batch_data[b] *= scales[b]` with a float64 scalar: numpy >= 2 (the one that runs the reference here)
+        # multiplies in float64 and rounds to float32; numpy 1.x demoted the scalar and multiplied in float32 (<= 1 ulp apart)
         for b in range(x.shape[0]):
-            x[b, :, :] *= np.float32(scale[b])
+            x[b, :, :] *= np.float64(scale[b])
     if shift is not None:
+        # provider.py:210-213 `batch_data[b] += shifts[b, :]`: float32 array += float64 array -> float64 add, rounded
         for b in range(x.shape[0]):
-            x[b, :, :] += np.asarray(shift[b], np.float32)
+            x[b, :, :] += np.asarray(shift[b], np.float64)
     if noise is not None:
         x = jitter_point_cloud(x, noise, sigma, clip)
     return x
