@@ -1,0 +1,69 @@
+"""SASS-level regression checks on the built library (cuobjdump, no GPU needed).
+
+The tensor-core kernels depend on two code-generation properties that a harmless-looking source change can lose:
+  * tcgen05.mma must be issued on the UNIFORM datapath.  When the compiler cannot prove the issuer warp converged and the
+    operands warp-uniform, it wraps every UTCHMMA in ELECT / R2UR(.BROADCAST) sequences -- measured ~110 cycles per MMA
+    instead of the 32 / 64 the tensor pipe needs (tools/microbench/mma_rate.cu).  Guard: the kernel-wide R2UR count stays near one per UTCHMMA (the broken state is 4-5 per UTCHMMA).
+  * the hot kernels really contain the Blackwell instructions they are written for (UTCHMMA, TMEM loads/stores, bulk
+    copies, mbarrier waits), i.e. nothing fell back to a generic path."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "scanobjectnn_b200", "libpsa.so")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    from scanobjectnn_b200.build import build_library
+    build_library()
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name is not None:
+            funcs[name].append(line)
+    return funcs
+
+
+def _count(lines, mnemonic):
+    return sum(1 for l in lines if re.search(r"\b" + mnemonic + r"\b", l))
+
+
+def _kernels(sass, pattern):
+    ks = {k: v for k, v in sass.items() if pattern in k}
+    assert ks, f"no kernel matching {pattern}"
+    return ks
+
+
+@pytest.mark.parametrize("pattern,max_ratio", [("tc_sa_dual_kernel", 1.5), ("tc_dense3_kernel", 1.0), ("tc_dense2_kernel", 1.0)])
+def test_mma_issue_stays_on_the_uniform_datapath(sass, pattern, max_ratio):
+    for name, lines in _kernels(sass, pattern).items():
+        mma, r2ur = _count(lines, "UTCHMMA"), _count(lines, r"R2UR(\.\w+)*")
+        assert mma >= 20, (name, mma)
+        assert r2ur <= max_ratio * mma, f"{name}: {r2ur} R2UR for {mma} UTCHMMA -- the MMA operands left the uniform datapath"
+
+
+def test_default_kernels_contain_the_blackwell_instructions(sass):
+    for pattern, needed in {"tc_sa_dual_kernel": ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS", "UTCBAR"],
+                            "tc_dense3_kernel": ["UTCHMMA", "LDTM", "UBLKCP", "SYNCS", "UTCBAR"],
+                            "tc_dense2_kernel": ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "SYNCS", "UTCBAR"]}.items():
+        for name, lines in _kernels(sass, pattern).items():
+            text = "\n".join(lines)
+            for mn in needed:
+                assert re.search(r"\b" + mn, text), f"{name}: no {mn} in SASS"
+
+
+def test_index_kernels_use_packed_f32x2_and_redux(sass):
+    fps = "\n".join(l for k, v in _kernels(sass, "fps_kernel").items() for l in v)
+    assert re.search(r"\bFFMA2\b|\bFMUL2\b|\bFADD2\b", fps), "FPS lost its packed f32x2 distance math"
+    assert re.search(r"\bREDUX\b|\bCREDUX\b", fps), "FPS lost its warp REDUX arg-max"
