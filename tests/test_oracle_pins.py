@@ -121,3 +121,24 @@ def test_dgcnn_knn_self_first_and_sorted():
     rows = np.take_along_axis(adj, idx, axis=-1)
     assert (np.diff(rows, axis=-1) >= 0).all()
     assert (idx == orc.topk_smallest(adj, 5)).all()
+
+
+def test_dgcnn_knn_agrees_with_torch_topk_at_the_reference_call_site():
+    """dgcnn/utils/tf_util.py:638-671 evaluated by an independent library (torch CPU, float64): adj = |x|^2 - 2 x x^T + |x|^2^T,
+    top_k(-adj, k).  On tie-free data the oracle's float32 canonical-order evaluation must select the same neighbours."""
+    import torch
+    for c, n, k in [(3, 300, 20), (64, 200, 20)]:
+        x = np.random.default_rng(c).standard_normal((2, n, c)).astype(np.float32)
+        idx = orc.dgcnn_knn(x, k)
+        t = torch.from_numpy(x).double()
+        inner = -2 * torch.matmul(t, t.transpose(2, 1))
+        sq = (t * t).sum(-1, keepdim=True)
+        adj = sq + inner + sq.transpose(2, 1)
+        ref = torch.topk(-adj, k).indices.numpy()
+        # float32 rounding can swap two neighbours whose float64 distances differ by less than a few ulp: compare as sets per row,
+        # and require exact order wherever the float64 gaps are clear
+        gaps = np.diff(np.sort(adj.numpy(), axis=-1)[..., : k + 1], axis=-1).min(-1)
+        scale = float((sq.max() * 4).item())                      # magnitude of the terms that cancel in adj
+        clear = gaps > 64 * np.finfo(np.float32).eps * scale         # well above the float32 evaluation error
+        assert clear.mean() > 0.5, clear.mean()
+        assert np.array_equal(idx[clear], ref[clear])
