@@ -1598,7 +1598,7 @@ size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~6
 
 static int g_tc_dense_narrow = 1;
 static int g_tc_dense_v2 = 1;     // 1: pipelined tc_dense2_kernel (bf16x3 images); 0: tc_dense_kernel (psa_set_mlp_mode(2))
-static int g_tc_dense_v3 = 1;     // 1: 128-wide layers with K <= 512 use the transposed tc_dense3_kernel (psa_set_mlp_mode(3): off)
+static int g_tc_dense_v3 = 1;     // 1: 128-wide layers with K <= 512 use the transposed tc_dense3_kernel (off together with v2 in mode 2)
 static int g_tc_sa_dual = 1;      // 0: 128-wide levels fall back to the one-tile-per-CTA wide kernel (psa_set_mlp_mode(2), A/B runs)
 int tc_dense_nt(int N) {
     if (g_tc_dense_v2) return ((N % 128) == 0 ? 128 : 64) | kImageBf16x3;
