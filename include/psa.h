@@ -264,6 +264,114 @@ PSA_API size_t psa_edgeconv_workspace_bytes(int b, int n, int c, int k, const ps
 PSA_API int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
                                float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Training mode: batch-statistics batch norm through every layer of a level and the
+ * backward pass.  Reference semantics: pointnet2/utils/tf_util.py:155-185 (conv2d = matmul + bias, then
+ * batch norm, then relu), :512-531 (tf.contrib.layers.batch_norm, is_training=True: batch mean, BIASED batch
+ * variance, eps = 1e-3, moving averages updated in place with `decay`), pointnet_util.py:113-127 (MLP +
+ * reduce_max), gradients tf_grouping.py:43-47 (GroupPointGrad = scatter-add by idx; index ops carry no
+ * gradient, tf_sampling.py:23,58, tf_grouping.py:22,33), optimiser pointnet2/train.py:139-146 (Adam).
+ * A level keeps ONE tensor per layer, the PRE-batch-norm activations y_l; everything else is recomputed
+ * inside the GEMM operand loads (csrc/train_gemm.cuh).  All reductions (statistics, bias/BN gradients, weight
+ * gradients, the GroupPointGrad scatter) are evaluated in a fixed order: results are bit-reproducible run to
+ * run, unlike the reference's float atomicAdd scatters.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Forward input of a layer: h[r][c] = relu(x[r][c] * scale[c] + shift[c]) * mask[r][c].
+ * scale == NULL: identity (raw input, no relu).  mask == NULL: no dropout. */
+typedef struct psa_act_in {
+    const float* x;      /* (rows, ld) */
+    long long ld;
+    const float* scale;  /* (C) batch-norm scale = gamma / sqrt(var + eps) of the layer that produced x, or NULL */
+    const float* shift;  /* (C) beta - mean * scale */
+    const float* mask;   /* (rows, ld) dropout mask holding 0 or 1/keep_prob, or NULL */
+    int relu;
+} psa_act_in;
+
+/* Gradient w.r.t. a layer's PRE-batch-norm output: dy[r][c] = ca[c] * dz[r][c] + cb[c] * y[r][c] + cc[c]
+ * (the batch-norm backward with the batch sums folded into three per-channel constants, see
+ * psa_bn_bwd_coeffs), dz = gradient w.r.t. the batch-norm output after the relu mask [y*s+t > 0]:
+ *   mode 0: dz = dh[r][c] (* mask[r][c])                      dense incoming gradient
+ *   mode 1: dz = dp[g][c] if argk[g][c] == r - g*pool_k and pv[g][c] > 0 else 0,  g = r / pool_k
+ *           (max-pool routing: dp = gradient of the pooled output, pv = pooled value, argk = winning row).
+ * ca == NULL: dy = dz (layer without batch norm).  s == NULL: no relu mask. */
+typedef struct psa_grad_in {
+    const float* y;      /* (rows, ld) pre-BN activations of this layer */
+    long long ld;
+    const float* s;      /* (C) BN scale / shift of this layer, or NULL */
+    const float* t;
+    int relu;
+    const float* ca;     /* (C) or NULL */
+    const float* cb;
+    const float* cc;
+    const float* dh;     /* mode 0: (rows, ld_dh) */
+    long long ld_dh;
+    const float* mask;   /* mode 0: dropout mask on dh, or NULL */
+    const float* dp;     /* mode 1: (rows / pool_k, C) */
+    const float* pv;
+    const int* argk;
+    int pool_k;
+    int C;
+    int mode;
+} psa_grad_in;
+
+/* y (rows, N) = in (rows, K) . W (K, N) + bias; stats (2, N) = per-channel [sum, sum of squares] of y (or NULL).
+ * workspace: psa_train_dense_workspace_bytes(rows, K, N). */
+PSA_API size_t psa_train_dense_workspace_bytes(long long rows, int K, int N);
+PSA_API int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_in* in, const float* W, const float* bias,
+                                float* y, float* stats, void* workspace, size_t workspace_bytes, psa_stream_t stream);
+/* dx (rows, K - col_skip) = dy (rows, N) . W^T restricted to input channels >= col_skip (the xyz channels of a
+ * concatenated input carry no gradient that anyone consumes). */
+PSA_API int psa_train_dense_bwd_input(long long rows, int K, int N, const psa_grad_in* g, const float* W, float* dx,
+                                      long long ld_dx, int col_skip, psa_stream_t stream);
+/* dW (K, N) = in^T . dy, contraction over the rows in fixed split order (deterministic). */
+PSA_API int psa_train_dense_bwd_weight(long long rows, int K, int N, const psa_act_in* in, const psa_grad_in* g,
+                                       float* dW, void* workspace, size_t workspace_bytes, psa_stream_t stream);
+
+/* Bias gradient of a layer that is NOT followed by batch norm: db (N) = sum_r dy[r][:].  (Under batch norm the conv / fc bias
+ * has an identically zero gradient -- sum_r dy = 0 -- and the training path writes exact zeros there.) */
+PSA_API int psa_train_bias_grad(long long rows, int N, const psa_grad_in* g, float* db, psa_stream_t stream);
+
+/* Batch statistics -> BN affine.  stats (2, C) sums over `count` rows; gamma, beta (C) ->
+ * scale = gamma / sqrt(var + 1e-3), shift = beta - mean * scale, mean_inv (2, C) = [mean, 1/sqrt(var + eps)];
+ * moving_mean / moving_var (C, may be NULL) <- decay * moving + (1 - decay) * batch  (tf_util.py:526-531). */
+PSA_API int psa_bn_finalize(int C, long long count, const float* stats, const float* gamma, const float* beta,
+                            float decay, float* moving_mean, float* moving_var, float* scale, float* shift,
+                            float* mean_inv, psa_stream_t stream);
+
+/* relu(BN(y)) then max over each run of pool_k rows: pooled (groups, C), argk (groups, C) = first winning row. */
+PSA_API int psa_train_pool_fwd(long long groups, int pool_k, int C, const float* y, const float* scale,
+                               const float* shift, float* pooled, int* argk, psa_stream_t stream);
+
+/* Batch-norm backward sums of a layer: dbeta[c] = sum_r dz, dgamma[c] = sum_r dz * xhat (g->ca/cb/cc are ignored),
+ * and the coefficients ca = gamma*inv, cb = -gamma*inv^2*dgamma/rows, cc = gamma*inv*(mean*inv*dgamma - dbeta)/rows
+ * that make psa_grad_in evaluate dy.  workspace: psa_bn_bwd_workspace_bytes(C). */
+PSA_API size_t psa_bn_bwd_workspace_bytes(int C);
+PSA_API int psa_bn_bwd_coeffs(long long rows, int C, const psa_grad_in* g, const float* gamma, const float* mean_inv,
+                              float* dgamma, float* dbeta, float* ca, float* cb, float* cc, void* workspace,
+                              size_t workspace_bytes, psa_stream_t stream);
+
+/* Backward of the fused first layer of a set-abstraction level (psa_sa_conv1_prebn): with dy0 = g over the
+ * b*m*nsample grouped rows,  dW_xyz (3, C1) = sum_r (xyz[idx_r] - new_xyz[q_r])^T dy0[r]  and, if dU != NULL,
+ * dU (b*n, C1) = GroupPointGrad(dy0, idx) (tf_grouping_g.cu:61-78) as an ordered gather (each source point adds its
+ * rows in ascending row order: deterministic).  The feature part of the layer then is two dense products on the b*n
+ * POINTS: dpoints = dU . W1[3:]^T and dW1[3:] = points^T . dU.  workspace: psa_sa_conv1_bwd_workspace_bytes(C1). */
+PSA_API size_t psa_sa_conv1_bwd_workspace_bytes(int C1);
+PSA_API int psa_sa_conv1_bwd(int b, int n, int m, int nsample, int C1, const float* xyz, const float* new_xyz,
+                             const int* idx, const psa_grad_in* g, float* dW_xyz, float* dU, void* workspace,
+                             size_t workspace_bytes, psa_stream_t stream);
+
+/* Mean sparse softmax cross-entropy (pointnet2_cls_ssg.py:50-57) and its gradient: logits (b, c), labels (b) int32 ->
+ * loss (1), dlogits (b, c) = (softmax - onehot) / b. */
+PSA_API int psa_softmax_xent(int b, int c, const float* logits, const int* labels, float* loss, float* dlogits,
+                             psa_stream_t stream);
+
+/* tf.train.AdamOptimizer step over one flat parameter vector (pointnet2/train.py:139-146):
+ * g = grad * grad_scale; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps). */
+PSA_API int psa_adam_step(long long count, float* params, const float* grads, float* m, float* v, float lr, float beta1,
+                          float beta2, float eps, int step, float grad_scale, psa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

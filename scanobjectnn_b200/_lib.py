@@ -31,7 +31,23 @@ class PsaMlp(C.Structure):
     ]
 
 
+class PsaActIn(C.Structure):
+    """psa_act_in (include/psa.h): forward input of a training-mode layer."""
+    _fields_ = [("x", C.c_void_p), ("ld", C.c_longlong), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mask", C.c_void_p),
+                ("relu", C.c_int)]
+
+
+class PsaGradIn(C.Structure):
+    """psa_grad_in (include/psa.h): gradient w.r.t. a layer's pre-batch-norm output, evaluated on the fly."""
+    _fields_ = [("y", C.c_void_p), ("ld", C.c_longlong), ("s", C.c_void_p), ("t", C.c_void_p), ("relu", C.c_int),
+                ("ca", C.c_void_p), ("cb", C.c_void_p), ("cc", C.c_void_p), ("dh", C.c_void_p), ("ld_dh", C.c_longlong),
+                ("mask", C.c_void_p), ("dp", C.c_void_p), ("pv", C.c_void_p), ("argk", C.c_void_p), ("pool_k", C.c_int),
+                ("C", C.c_int), ("mode", C.c_int)]
+
+
 _i, _f, _p = C.c_int, C.c_float, C.c_void_p
+_ll, _sz = C.c_longlong, C.c_size_t
+_ain, _gin = C.POINTER(PsaActIn), C.POINTER(PsaGradIn)
 
 # name -> argtypes; every entry point returns int.  Mirrors include/psa.h one to one
 # (tests/test_abi.py checks header <-> this table <-> exported symbols).
@@ -63,9 +79,21 @@ SIGNATURES = {
     "psa_get_mlp_mode": [],
     "psa_tc_selftest": [_i, _i, _p, _p, _p, _p, _p],
     "psa_edgeconv_infer": [_i, _i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
+    # training mode
+    "psa_train_dense_fwd": [_ll, _i, _i, _ain, _p, _p, _p, _p, _p, _sz, _p],
+    "psa_train_dense_bwd_input": [_ll, _i, _i, _gin, _p, _p, _ll, _i, _p],
+    "psa_train_dense_bwd_weight": [_ll, _i, _i, _ain, _gin, _p, _p, _sz, _p],
+    "psa_train_bias_grad": [_ll, _i, _gin, _p, _p],
+    "psa_bn_finalize": [_i, _ll, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
+    "psa_train_pool_fwd": [_ll, _i, _i, _p, _p, _p, _p, _p, _p],
+    "psa_bn_bwd_coeffs": [_ll, _i, _gin, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
+    "psa_sa_conv1_bwd": [_i, _i, _i, _i, _i, _p, _p, _p, _gin, _p, _p, _p, _sz, _p],
+    "psa_softmax_xent": [_i, _i, _p, _p, _p, _p, _p],
+    "psa_adam_step": [_ll, _p, _p, _p, _p, _f, _f, _f, _f, _i, _f, _p],
 }
 INFO_SYMBOLS = ("psa_version", "psa_last_error", "psa_sm_arch", "psa_shared_mlp_workspace_bytes",
-                "psa_sa_module_workspace_bytes", "psa_sa_conv1_prebn_workspace_bytes", "psa_sa_group_all_workspace_bytes", "psa_edgeconv_workspace_bytes")
+                "psa_sa_module_workspace_bytes", "psa_sa_conv1_prebn_workspace_bytes", "psa_sa_group_all_workspace_bytes", "psa_edgeconv_workspace_bytes",
+                "psa_train_dense_workspace_bytes", "psa_bn_bwd_workspace_bytes", "psa_sa_conv1_bwd_workspace_bytes")
 
 _lib = None
 
@@ -94,6 +122,12 @@ def load() -> C.CDLL:
     lib.psa_sa_group_all_workspace_bytes.restype = C.c_size_t
     lib.psa_sa_conv1_prebn_workspace_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.psa_sa_conv1_prebn_workspace_bytes.restype = C.c_size_t
+    lib.psa_train_dense_workspace_bytes.argtypes = [_ll, _i, _i]
+    lib.psa_train_dense_workspace_bytes.restype = C.c_size_t
+    lib.psa_bn_bwd_workspace_bytes.argtypes = [_i]
+    lib.psa_bn_bwd_workspace_bytes.restype = C.c_size_t
+    lib.psa_sa_conv1_bwd_workspace_bytes.argtypes = [_i]
+    lib.psa_sa_conv1_bwd_workspace_bytes.restype = C.c_size_t
     lib.psa_version.restype = C.c_int
     lib.psa_sm_arch.restype = C.c_int
     lib.psa_last_error.restype = C.c_char_p

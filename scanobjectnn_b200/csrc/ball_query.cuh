@@ -39,12 +39,19 @@ struct BqSmem {
     float* sx; float* sy; float* sz;    // scan mode: np = round_up(n,128) floats each, padded with +inf; grid mode: null
     float4* sorted;                     // grid mode: n entries (x, y, z, bits(k)), grouped by cell
     int* cell_end;                      // grid mode: kBqMaxCells + 32 ints: end offset of each cell, scratch
-    int* hits;                          // grid mode: kBqWarps * kBqHitCap
+    int* hits;                          // grid mode: kBqWarps * bq_warp_scratch_words(n)
     const float* gxyz;                  // the cloud in global memory (AoS), always valid
 };
 
+constexpr int kBqSlabQueries = 8;      // queries a warp searches at a time on the lane-per-slab path (3 lanes each)
+__host__ __device__ inline int bq_bitmap_words_per_lane(int n) { return ((n + 31) / 32 + 31) / 32; }   // a query's bitmap = 32 * this words
+// per-warp scratch in grid mode: the hit list of the warp-per-query search or the 8 bitmaps of the lane-per-slab search
+__host__ __device__ inline int bq_warp_scratch_words(int n) {
+    const int bm = kBqSlabQueries * 32 * bq_bitmap_words_per_lane(n);
+    return bm > kBqHitCap ? bm : kBqHitCap;
+}
 __host__ __device__ inline size_t bq_smem_bytes(int n, bool grid) {
-    if (grid) return (size_t)n * 16 + (size_t)(kBqMaxCells + 32) * 4 + (size_t)kBqWarps * kBqHitCap * 4;
+    if (grid) return (size_t)n * 16 + (size_t)(kBqMaxCells + 32) * 4 + (size_t)kBqWarps * bq_warp_scratch_words(n) * 4;
     return (size_t)((n + 127) & ~127) * 3 * sizeof(float);
 }
 __host__ __device__ inline bool bq_grid_fits(int n) { return n <= kBqGridMaxN; }
@@ -300,7 +307,7 @@ __device__ __forceinline__ int bq_query_warp(int n, int nsample, float thr, bool
         r_end[i] = __shfl_sync(0xffffffffu, incl, i);
     }
     // ---- test the candidates, compact the hits (any order) ----
-    int* hits = s.hits + warp * kBqHitCap;
+    int* hits = s.hits + warp * bq_warp_scratch_words(n);
     const unsigned lt = lanemask_lt();
     int nh = 0;
     for (int t0 = 0; t0 < total; t0 += 32) {
@@ -337,6 +344,86 @@ __device__ __forceinline__ int bq_query_warp(int n, int nsample, float thr, bool
     const int cnt = min(nh, nsample);
     const int fillv = nh > 0 ? first : 0;
     for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = fillv;
+    return cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Lane-per-slab search (used by the streaming F1 kernel and ball_query_kernel v3).
+//
+// The warp-per-query search above spends most of its instructions on warp-uniform bookkeeping (run table, slot -> run
+// selection, ranking): ~600 warp instructions per query.  Here THREE lanes own a query: lane t walks the three x-runs of
+// the z-slab cqz + t - 1 of the 3x3x3 cell neighbourhood point by point and sets bit k of the query's bitmap (n bits in
+// shared memory) for every in-radius point k.  The reference's "first nsample in index order" is then the nsample lowest
+// set bits -- read out by the whole warp (bq_extract_bitmap) in ascending order with popcount prefix sums, independent of
+// how many points are inside the ball (no hit cap, no ranking).  Same distance arithmetic, same cell geometry (cells
+// >= 1.001 r), so the set of hits is the one the scan finds: index-exact.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBqSlabLanes = 3;
+
+
+// One lane, one z-slab (t = 0,1,2) of the neighbourhood of a FINITE query on a usable grid.
+__device__ __forceinline__ void bq_search_slab(const BqSmem& s, const BqGrid& g, float thr, float qx, float qy, float qz, int t,
+                                               unsigned* __restrict__ bitmap) {
+    const float fx = fminf(fmaxf((qx - g.minx) * g.inv_h, -2.f), (float)(kBqGridMax + 1));
+    const float fy = fminf(fmaxf((qy - g.miny) * g.inv_h, -2.f), (float)(kBqGridMax + 1));
+    const float fz = fminf(fmaxf((qz - g.minz) * g.inv_h, -2.f), (float)(kBqGridMax + 1));
+    const int cqx = (int)floorf(fx), cqy = (int)floorf(fy), cz = (int)floorf(fz) + t - 1;
+    const int lox = max(cqx - 1, 0), hix = min(cqx + 1, g.gx - 1);
+    if (lox > hix || cz < 0 || cz >= g.gz) return;
+#pragma unroll 1
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int cy = cqy + dy;
+        if (cy < 0 || cy >= g.gy) continue;
+        const int rb = (cz * g.gy + cy) * g.gx;
+        int p = (rb + lox == 0) ? 0 : s.cell_end[rb + lox - 1];
+        const int e = s.cell_end[rb + hix];
+        // two candidates per trip: the second load is clamped into the run and masked
+        for (; p < e; p += 2) {
+            const float4 a = s.sorted[p];
+            const float4 b = s.sorted[min(p + 1, e - 1)];
+            const bool ia = !(dist2_ref_gpu(qx - a.x, qy - a.y, qz - a.z) > thr);
+            const bool ib = !(dist2_ref_gpu(qx - b.x, qy - b.y, qz - b.z) > thr) && (p + 1 < e);
+            if (ia) { const int k = __float_as_int(a.w); atomicOr(bitmap + (k >> 5), 1u << (k & 31)); }
+            if (ib) { const int k = __float_as_int(b.w); atomicOr(bitmap + (k >> 5), 1u << (k & 31)); }
+        }
+    }
+}
+
+// Whole warp: the nsample lowest set bits of `bitmap` (32 * wpl words, lane l owns words [l*wpl, (l+1)*wpl)) in ascending
+// order -> idxrow[0..cnt), remaining slots filled with the first hit (0 if none: tf_grouping_g.cu:26-29); clears the bitmap.
+__device__ __forceinline__ int bq_extract_bitmap(unsigned* __restrict__ bitmap, int wpl, int nsample, int* __restrict__ idxrow, int lane) {
+    unsigned w[4];
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        w[i] = 0u;
+        if (i < wpl) { w[i] = bitmap[lane * wpl + i]; bitmap[lane * wpl + i] = 0u; c += __popc(w[i]); }
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned have = __ballot_sync(0xffffffffu, c > 0);
+    int firstbit = 0;
+#pragma unroll
+    for (int i = 3; i >= 0; --i)
+        if (w[i] != 0u) firstbit = (lane * wpl + i) * 32 + __ffs(w[i]) - 1;
+    const int first = have ? __shfl_sync(0xffffffffu, firstbit, __ffs(have) - 1) : 0;
+    int pos = incl - c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        unsigned x = w[i];
+        while (x != 0u && pos < nsample) {
+            const int bit = __ffs(x) - 1;
+            x &= x - 1u;
+            idxrow[pos++] = (lane * wpl + i) * 32 + bit;
+        }
+    }
+    const int cnt = min(total, nsample);
+    for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = first;
     return cnt;
 }
 

@@ -45,10 +45,42 @@ ball_query_kernel(int n, int m, int nsample, float radius, float thr, int none, 
     const int q0 = blockIdx.x * q_per_cta;
     const int q1 = min(m, q0 + q_per_cta);
     const float* p2 = xyz2 + (size_t)cloud * m * 3;
+    if (g.use && !none) {
+        // lane-per-slab search: three lanes per query, eight queries per warp step, hits as bits of a per-query bitmap, the
+        // nsample lowest bits read out in order (ball_query.cuh); non-finite queries take the ordered scan
+        const int wpl = bq_bitmap_words_per_lane(n);
+        unsigned* bm = reinterpret_cast<unsigned*>(s.hits) + (size_t)warp * bq_warp_scratch_words(n);
+        for (int i = lane; i < kBqSlabQueries * 32 * wpl; i += 32) bm[i] = 0u;
+        __syncwarp();
+        const int qi = lane / kBqSlabLanes, tsl = lane - qi * kBqSlabLanes;
+        for (int q = q0 + warp * kBqSlabQueries; q < q1; q += kBqWarps * kBqSlabQueries) {
+            const int nq = min(kBqSlabQueries, q1 - q);
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (qi < nq) { qx = __ldg(p2 + (q + qi) * 3 + 0); qy = __ldg(p2 + (q + qi) * 3 + 1); qz = __ldg(p2 + (q + qi) * 3 + 2); }
+            const bool qfin = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;
+            if (qi < nq && qfin) bq_search_slab(s, g, thr, qx, qy, qz, tsl, bm + (size_t)qi * 32 * wpl);
+            __syncwarp();
+            for (int i = 0; i < nq; ++i) {
+                const bool fin_i = __shfl_sync(0xffffffffu, qfin ? 1 : 0, i * kBqSlabLanes) != 0;
+                int* row = idx + ((size_t)cloud * m + q + i) * nsample;
+                int cnt;
+                if (fin_i) {
+                    cnt = bq_extract_bitmap(bm + (size_t)i * 32 * wpl, wpl, nsample, row, lane);
+                } else {
+                    const float cx = __shfl_sync(0xffffffffu, qx, i * kBqSlabLanes), cy = __shfl_sync(0xffffffffu, qy, i * kBqSlabLanes);
+                    const float cz = __shfl_sync(0xffffffffu, qz, i * kBqSlabLanes);
+                    cnt = bq_scan_warp(n, nsample, thr, false, s, cx, cy, cz, row, lane);
+                }
+                if (pts_cnt != nullptr && lane == 0) pts_cnt[(size_t)cloud * m + q + i] = cnt;
+            }
+            __syncwarp();
+        }
+        return;
+    }
     for (int q = q0 + warp; q < q1; q += kBqWarps) {
         const float qx = __ldg(p2 + q * 3 + 0), qy = __ldg(p2 + q * 3 + 1), qz = __ldg(p2 + q * 3 + 2);
         int* row = idx + ((size_t)cloud * m + q) * nsample;
-        const int cnt = bq_query_warp(n, nsample, thr, none != 0, s, g, qx, qy, qz, row, lane, warp);
+        const int cnt = bq_scan_warp(n, nsample, thr, none != 0, s, qx, qy, qz, row, lane);
         if (pts_cnt != nullptr && lane == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
     }
 }
@@ -287,8 +319,9 @@ extern "C" int psa_query_ball_point(int b, int n, int m, float radius, int nsamp
     // enough CTAs for ~2 waves of 148 SMs, at least two warp-batches of queries per CTA
     int chunks = (2 * kNumSMs + b - 1) / b;
     int q_per_cta = (m + chunks - 1) / chunks;
-    q_per_cta = ((q_per_cta + kBqWarps - 1) / kBqWarps) * kBqWarps;
-    if (q_per_cta < 2 * kBqWarps) q_per_cta = 2 * kBqWarps;
+    // a CTA answers a multiple of 64 queries (8 warps x 8 queries per lane-per-slab step)
+    const int qstep = kBqWarps * kBqSlabQueries;
+    q_per_cta = ((q_per_cta + qstep - 1) / qstep) * qstep;
     dim3 grid((m + q_per_cta - 1) / q_per_cta, b);
     if (n <= 8 * kBqThreads) {
         PSA_CUDA(cudaFuncSetAttribute(ball_query_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

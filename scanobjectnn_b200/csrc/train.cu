@@ -1,0 +1,472 @@
+// train.cu -- training mode of the point-set-abstraction path: batch-statistics BN, max-pool with arg routing, the
+// backward pass of a level and of the FC head, loss, Adam.  See include/psa.h ("Training mode") for the contract and
+// train_gemm.cuh for the fused GEMM all the dense products run on.
+//
+// Determinism: every reduction here (column statistics, BN backward sums, split-K weight gradients, the GroupPointGrad
+// scatter) is a fixed-order sum -- per-CTA partials in a fixed thread order, partials added in index order in fp64.  The
+// reference's gradient kernels are float atomicAdd scatters (tf_grouping_g.cu:61-78, tf_sampling_g.cu:183-192).
+#include <math.h>
+
+#include "train_gemm.cuh"
+
+namespace psa {
+
+// out[e] = sum_p partial[p * len + e], p ascending, fp64 accumulator
+__global__ void reduce_partials_kernel(int nparts, int len, const float* __restrict__ partial, float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * len + e];
+    out[e] = (float)s;
+}
+
+static int reduce_partials(int nparts, int len, const float* partial, float* out, cudaStream_t st) {
+    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, st>>>(nparts, len, partial, out);
+    return check_launch("reduce_partials_kernel");
+}
+
+template <int BM, int BN, bool A_KC, bool B_NC, class FA, class FB>
+static int launch_gemm(const FA& fa, const FB& fb, const GemmOut& o, long long M, int N, long long Kc, int splits, long long k_per_split,
+                       cudaStream_t st) {
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
+    train_gemm_kernel<BM, BN, A_KC, B_NC, FA, FB><<<grid, kGemmThreads, 0, st>>>(fa, fb, o, M, N, Kc, k_per_split);
+    return check_launch("train_gemm_kernel");
+}
+
+// ---- batch-norm finalize ----
+__global__ void bn_finalize_kernel(int C, double inv_count, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float decay, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_inv) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = (double)stats[c] * inv_count;
+    double var = (double)stats[C + c] * inv_count - mean * mean;       // biased (tf.nn.moments / contrib batch_norm)
+    if (var < 0.0) var = 0.0;
+    const double inv = 1.0 / sqrt(var + 1e-3);
+    const float sc = (float)((double)gamma[c] * inv);
+    scale[c] = sc;
+    shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * inv);
+    if (mean_inv != nullptr) { mean_inv[c] = (float)mean; mean_inv[C + c] = (float)inv; }
+    if (moving_mean != nullptr) moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * (float)mean;
+    if (moving_var != nullptr) moving_var[c] = decay * moving_var[c] + (1.f - decay) * (float)var;
+}
+
+// ---- max-pool over runs of pool_k rows with the first winning row ----
+__global__ void train_pool_fwd_kernel(long long groups, int pool_k, int C4, const float4* __restrict__ y, const float4* __restrict__ scale,
+                                      const float4* __restrict__ shift, float4* __restrict__ pooled, int4* __restrict__ argk) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= groups * C4) return;
+    const long long g = e / C4;
+    const int c4 = (int)(e - g * C4);
+    const float4 s = __ldg(scale + c4), t = __ldg(shift + c4);
+    float4 best = make_float4(-1.f, -1.f, -1.f, -1.f);                 // relu output is >= 0: row 0 always beats the sentinel
+    int4 arg = make_int4(0, 0, 0, 0);
+    const float4* row = y + (size_t)g * pool_k * C4 + c4;
+    for (int k = 0; k < pool_k; ++k) {
+        const float4 v = __ldg(row + (size_t)k * C4);
+        const float zx = fmaxf(fmaf(v.x, s.x, t.x), 0.f), zy = fmaxf(fmaf(v.y, s.y, t.y), 0.f);
+        const float zz = fmaxf(fmaf(v.z, s.z, t.z), 0.f), zw = fmaxf(fmaf(v.w, s.w, t.w), 0.f);
+        if (zx > best.x) { best.x = zx; arg.x = k; }
+        if (zy > best.y) { best.y = zy; arg.y = k; }
+        if (zz > best.z) { best.z = zz; arg.z = k; }
+        if (zw > best.w) { best.w = zw; arg.w = k; }
+    }
+    pooled[e] = best;
+    argk[e] = arg;
+}
+
+// ---- batch-norm backward sums ----
+// block = (C/4 channel quads) x RL row lanes; each block owns a contiguous chunk of rows; partial (blocks, 2, C)
+constexpr int kBnbThreads = 256;
+
+__global__ void __launch_bounds__(kBnbThreads)
+bn_bwd_partial_kernel(const GradIn g, long long rows, int C, const float* __restrict__ mean_inv, long long rows_per_block,
+                      float* __restrict__ partial) {
+    __shared__ float red[kBnbThreads * 8];
+    const int C4 = C / 4;
+    const int RL = kBnbThreads / C4;                                  // row lanes (>= 1 for C <= 1024)
+    const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = sb;
+    if (rl < RL) {
+        const int c = cq * 4;
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(mean_inv + c)), inv = __ldg(reinterpret_cast<const float4*>(mean_inv + C + c));
+        const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+        if (g.mode == 0) {
+            for (long long r = r0 + rl; r < r1; r += RL) {
+                const float4 yv = g.y4(r, c);
+                const float4 dz = g.dz4(r, c, yv);
+                sb.x += dz.x; sb.y += dz.y; sb.z += dz.z; sb.w += dz.w;
+                sg.x = fmaf(dz.x, (yv.x - mu.x) * inv.x, sg.x); sg.y = fmaf(dz.y, (yv.y - mu.y) * inv.y, sg.y);
+                sg.z = fmaf(dz.z, (yv.z - mu.z) * inv.z, sg.z); sg.w = fmaf(dz.w, (yv.w - mu.w) * inv.w, sg.w);
+            }
+        } else {
+            // pooled routing: `rows` counts GROUPS here; only the winning row of each (group, channel) carries gradient
+            for (long long gi = r0 + rl; gi < r1; gi += RL) {
+                const size_t o = (size_t)gi * C + c;
+                const int4 a = __ldg(reinterpret_cast<const int4*>(g.argk + o));
+                const float4 p = __ldg(reinterpret_cast<const float4*>(g.pv + o)), d = __ldg(reinterpret_cast<const float4*>(g.dp + o));
+                const float* yb = g.y + (size_t)gi * g.pool_k * g.ld + c;
+                if (p.x > 0.f) { const float yv = __ldg(yb + (size_t)a.x * g.ld + 0); sb.x += d.x; sg.x = fmaf(d.x, (yv - mu.x) * inv.x, sg.x); }
+                if (p.y > 0.f) { const float yv = __ldg(yb + (size_t)a.y * g.ld + 1); sb.y += d.y; sg.y = fmaf(d.y, (yv - mu.y) * inv.y, sg.y); }
+                if (p.z > 0.f) { const float yv = __ldg(yb + (size_t)a.z * g.ld + 2); sb.z += d.z; sg.z = fmaf(d.z, (yv - mu.z) * inv.z, sg.z); }
+                if (p.w > 0.f) { const float yv = __ldg(yb + (size_t)a.w * g.ld + 3); sb.w += d.w; sg.w = fmaf(d.w, (yv - mu.w) * inv.w, sg.w); }
+            }
+        }
+    }
+    float* mine = red + threadIdx.x * 8;
+    mine[0] = sb.x; mine[1] = sb.y; mine[2] = sb.z; mine[3] = sb.w; mine[4] = sg.x; mine[5] = sg.y; mine[6] = sg.z; mine[7] = sg.w;
+    __syncthreads();
+    float* dst = partial + (size_t)blockIdx.x * 2 * C;
+    for (int e = threadIdx.x; e < 2 * C; e += kBnbThreads) {
+        const int which = e / C, c = e - which * C;
+        float t = 0.f;
+        for (int r = 0; r < RL; ++r) t += red[(r * C4 + (c >> 2)) * 8 + which * 4 + (c & 3)];      // row lanes in order
+        dst[e] = t;
+    }
+}
+
+__global__ void bn_bwd_final_kernel(int nparts, int C, double inv_rows, const float* __restrict__ partial, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean_inv, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double db = 0.0, dg = 0.0;
+    for (int p = 0; p < nparts; ++p) { db += (double)partial[(size_t)p * 2 * C + c]; dg += (double)partial[(size_t)p * 2 * C + C + c]; }
+    dbeta[c] = (float)db;
+    dgamma[c] = (float)dg;
+    const double gm = gamma[c], mu = mean_inv[c], inv = mean_inv[C + c];
+    // dy = gamma*inv/R * (R dz - dbeta - xhat dgamma),  xhat = (y - mu) inv
+    ca[c] = (float)(gm * inv);
+    cb[c] = (float)(-gm * inv * inv * dg * inv_rows);
+    cc[c] = (float)(gm * inv * (mu * inv * dg - db) * inv_rows);
+}
+
+// ---- first-layer backward of a set-abstraction level ----
+// dW_xyz partials: block = (C1/4 quads) x row lanes over a contiguous chunk of grouped rows
+__global__ void __launch_bounds__(kBnbThreads)
+conv1_dwxyz_partial_kernel(const GradIn g, long long rows, int nsample, long long rows_per_cloud, int n, int m, int C1,
+                           const float* __restrict__ xyz, const float* __restrict__ new_xyz, const int* __restrict__ idx,
+                           long long rows_per_block, float* __restrict__ partial) {
+    __shared__ float red[kBnbThreads * 12];
+    const int C4 = C1 / 4, RL = kBnbThreads / C4;
+    const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    if (rl < RL) {
+        const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+        for (long long r = r0 + rl; r < r1; r += RL) {
+            const long long cloud = r / rows_per_cloud;
+            const long long q = r / nsample;                               // global query id
+            const int j = __ldg(idx + r);
+            const float* p = xyz + ((size_t)cloud * n + j) * 3;
+            const float* cq3 = new_xyz + (size_t)q * 3;
+            const float dx = __ldg(p) - __ldg(cq3), dy = __ldg(p + 1) - __ldg(cq3 + 1), dz = __ldg(p + 2) - __ldg(cq3 + 2);
+            const float4 gy = g.get4(r, cq * 4);
+            acc[0] = fmaf(dx, gy.x, acc[0]); acc[1] = fmaf(dx, gy.y, acc[1]); acc[2] = fmaf(dx, gy.z, acc[2]); acc[3] = fmaf(dx, gy.w, acc[3]);
+            acc[4] = fmaf(dy, gy.x, acc[4]); acc[5] = fmaf(dy, gy.y, acc[5]); acc[6] = fmaf(dy, gy.z, acc[6]); acc[7] = fmaf(dy, gy.w, acc[7]);
+            acc[8] = fmaf(dz, gy.x, acc[8]); acc[9] = fmaf(dz, gy.y, acc[9]); acc[10] = fmaf(dz, gy.z, acc[10]); acc[11] = fmaf(dz, gy.w, acc[11]);
+        }
+    }
+    (void)m;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) red[threadIdx.x * 12 + i] = acc[i];
+    __syncthreads();
+    float* dst = partial + (size_t)blockIdx.x * 3 * C1;
+    for (int e = threadIdx.x; e < 3 * C1; e += kBnbThreads) {
+        const int ax = e / C1, c = e - ax * C1;
+        float t = 0.f;
+        for (int r = 0; r < RL; ++r) t += red[(r * C4 + (c >> 2)) * 12 + ax * 4 + (c & 3)];
+        dst[e] = t;
+    }
+}
+
+// GroupPointGrad as an ordered gather: warp = 4 consecutive source points of one cloud; the warp scans the cloud's idx
+// array (m*nsample entries, L1/L2 resident) 32 entries per step and adds the matching rows' dy0 in ascending row order.
+// lane = 4 channels (C1 <= 128).
+constexpr int kScatJ = 4;
+__global__ void __launch_bounds__(256)
+group_grad_gather_kernel(const GradIn g, int n, int mk, int C1, const int* __restrict__ idx, float* __restrict__ dU) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.y;
+    const int j0 = (blockIdx.x * 8 + warp) * kScatJ;
+    if (j0 >= n) return;
+    const int* ic = idx + (size_t)cloud * mk;
+    const bool chan = lane * 4 < C1;
+    float4 acc[kScatJ];
+#pragma unroll
+    for (int u = 0; u < kScatJ; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < mk; base += 32) {
+        const int e = base + lane;
+        const int v = e < mk ? __ldg(ic + e) : -1;
+#pragma unroll
+        for (int u = 0; u < kScatJ; ++u) {
+            unsigned mt = __ballot_sync(0xffffffffu, v == j0 + u);
+            while (mt) {
+                const int r = base + __ffs(mt) - 1;
+                mt &= mt - 1u;
+                if (chan) {
+                    const float4 d = g.get4((long long)cloud * mk + r, lane * 4);
+                    acc[u].x += d.x; acc[u].y += d.y; acc[u].z += d.z; acc[u].w += d.w;
+                }
+            }
+        }
+    }
+    if (chan) {
+#pragma unroll
+        for (int u = 0; u < kScatJ; ++u)
+            if (j0 + u < n) *reinterpret_cast<float4*>(dU + ((size_t)cloud * n + j0 + u) * C1 + lane * 4) = acc[u];
+    }
+}
+
+// ---- bias gradient of a layer WITHOUT batch norm: db[c] = sum_r dy[r][c]; block = one column, fixed-order tree ----
+__global__ void __launch_bounds__(256) bias_grad_kernel(const GradIn g, long long rows, float* __restrict__ db) {
+    __shared__ float red[256];
+    const int c = blockIdx.x;
+    float t = 0.f;
+    for (long long r = threadIdx.x; r < rows; r += 256) t += g.get(r, c);
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) db[c] = red[0];
+}
+
+// ---- loss ----
+__global__ void softmax_xent_kernel(int b, int c, const float* __restrict__ logits, const int* __restrict__ labels, float* __restrict__ loss,
+                                    float* __restrict__ dlogits) {
+    __shared__ float rowloss[1024];
+    const int r = threadIdx.x;
+    if (r < b) {
+        const float* l = logits + (size_t)r * c;
+        float mx = l[0];
+        for (int i = 1; i < c; ++i) mx = fmaxf(mx, l[i]);
+        float se = 0.f;
+        for (int i = 0; i < c; ++i) se += expf(l[i] - mx);
+        const int lab = labels[r];
+        rowloss[r] = (logf(se) + mx) - l[lab];
+        const float invb = 1.f / (float)b;
+        for (int i = 0; i < c; ++i) dlogits[(size_t)r * c + i] = (expf(l[i] - mx) / se - (i == lab ? 1.f : 0.f)) * invb;
+    }
+    __syncthreads();
+    if (r == 0) {
+        double s = 0.0;
+        for (int i = 0; i < b; ++i) s += (double)rowloss[i];
+        loss[0] = (float)(s / b);
+    }
+}
+
+// ---- Adam ----
+__global__ void adam_kernel(long long count, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            float lr_t, float b1, float b2, float eps, float gscale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+static int weight_grad_splits(long long rows, int tiles, long long* k_per_split) {
+    long long want = (2LL * kNumSMs + tiles - 1) / tiles;
+    long long maxs = (rows + 255) / 256;                       // at least 256 rows of contraction per split
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    long long kps = (rows + want - 1) / want;
+    kps = (kps + kGemmBK - 1) / kGemmBK * kGemmBK;
+    *k_per_split = kps;
+    return (int)((rows + kps - 1) / kps);
+}
+
+}  // namespace psa
+
+using namespace psa;
+
+extern "C" size_t psa_train_dense_workspace_bytes(long long rows, int K, int N) {
+    // forward: (tiles_m, 2, N) statistics partials; weight gradient: (splits, K, N) partial products
+    const size_t fwd = (size_t)((rows + 127) / 128) * 2 * (size_t)N * sizeof(float);
+    const int bm = (K <= 64 && N <= 64) ? 64 : 128, bn = N <= 64 ? 64 : 128;
+    const int tiles = ((K + bm - 1) / bm) * ((N + bn - 1) / bn);
+    long long kps;
+    const int splits = weight_grad_splits(rows, tiles, &kps);
+    const size_t bwd = splits > 1 ? (size_t)splits * K * N * sizeof(float) : 0;
+    return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+extern "C" int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_in* in, const float* W, const float* bias, float* y,
+                                   float* stats, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    PSA_REQUIRE(rows >= 0 && K >= 1 && N >= 1, "train_dense_fwd: bad dims rows=%lld K=%d N=%d", rows, K, N);
+    if (rows == 0) return PSA_OK;
+    PSA_REQUIRE(in && in->x && W && y, "train_dense_fwd: null buffer");
+    cudaStream_t st = as_stream(stream);
+    const long long tiles_m = (rows + 127) / 128;
+    GemmOut o;
+    o.out = y; o.ld_out = N; o.bias = bias; o.col_skip = 0; o.stat_partial = nullptr;
+    if (stats != nullptr) {
+        PSA_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)tiles_m * 2 * N * sizeof(float), "train_dense_fwd: workspace too small");
+        o.stat_partial = reinterpret_cast<float*>(workspace);
+    }
+    const ActIn fa(*in);
+    const MatIn fb{W, N};
+    int rc;
+    if (N <= 64) rc = launch_gemm<128, 64, true, true>(fa, fb, o, rows, N, K, 1, (long long)K + kGemmBK, st);
+    else rc = launch_gemm<128, 128, true, true>(fa, fb, o, rows, N, K, 1, (long long)K + kGemmBK, st);
+    if (rc != PSA_OK) return rc;
+    if (stats != nullptr) return reduce_partials((int)tiles_m, 2 * N, o.stat_partial, stats, st);
+    return PSA_OK;
+}
+
+extern "C" int psa_train_dense_bwd_input(long long rows, int K, int N, const psa_grad_in* g, const float* W, float* dx, long long ld_dx,
+                                         int col_skip, psa_stream_t stream) {
+    PSA_REQUIRE(rows >= 0 && K >= 1 && N >= 1 && col_skip >= 0 && col_skip < K, "train_dense_bwd_input: bad dims");
+    if (rows == 0) return PSA_OK;
+    PSA_REQUIRE(g && W && dx, "train_dense_bwd_input: null buffer");
+    GemmOut o;
+    o.out = dx; o.ld_out = ld_dx; o.bias = nullptr; o.col_skip = col_skip; o.stat_partial = nullptr;
+    const GradIn fa(*g);
+    const MatIn fb{W, N};                                    // B(kc = n, col = k) = W[k][n]: contraction-contiguous
+    cudaStream_t st = as_stream(stream);
+    if (K <= 64) return launch_gemm<128, 64, true, false>(fa, fb, o, rows, K, N, 1, (long long)N + kGemmBK, st);
+    return launch_gemm<128, 128, true, false>(fa, fb, o, rows, K, N, 1, (long long)N + kGemmBK, st);
+}
+
+extern "C" int psa_train_dense_bwd_weight(long long rows, int K, int N, const psa_act_in* in, const psa_grad_in* g, float* dW,
+                                          void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    PSA_REQUIRE(rows >= 1 && K >= 1 && N >= 1, "train_dense_bwd_weight: bad dims");
+    PSA_REQUIRE(in && in->x && g && dW, "train_dense_bwd_weight: null buffer");
+    cudaStream_t st = as_stream(stream);
+    const int bm = (K <= 64 && N <= 64) ? 64 : 128, bn = N <= 64 ? 64 : 128;
+    const int tiles = ((K + bm - 1) / bm) * ((N + bn - 1) / bn);
+    long long kps;
+    const int splits = weight_grad_splits(rows, tiles, &kps);
+    GemmOut o;
+    o.ld_out = N; o.bias = nullptr; o.col_skip = 0; o.stat_partial = nullptr;
+    if (splits > 1) {
+        PSA_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)splits * K * N * sizeof(float), "train_dense_bwd_weight: workspace too small");
+        o.out = reinterpret_cast<float*>(workspace);
+    } else {
+        o.out = dW;
+    }
+    const ActIn fa(*in);
+    const GradIn fb(*g);
+    int rc;
+    if (bm == 64) rc = launch_gemm<64, 64, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
+    else if (bn == 64) rc = launch_gemm<128, 64, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
+    else rc = launch_gemm<128, 128, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
+    if (rc != PSA_OK) return rc;
+    if (splits > 1) return reduce_partials(splits, K * N, o.out, dW, st);
+    return PSA_OK;
+}
+
+extern "C" int psa_bn_finalize(int C, long long count, const float* stats, const float* gamma, const float* beta, float decay,
+                               float* moving_mean, float* moving_var, float* scale, float* shift, float* mean_inv, psa_stream_t stream) {
+    PSA_REQUIRE(C >= 1 && count >= 1 && stats && gamma && beta && scale && shift, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(C, 1.0 / (double)count, stats, gamma, beta, decay, moving_mean, moving_var,
+                                                                        scale, shift, mean_inv);
+    return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int psa_train_pool_fwd(long long groups, int pool_k, int C, const float* y, const float* scale, const float* shift, float* pooled,
+                                  int* argk, psa_stream_t stream) {
+    PSA_REQUIRE(groups >= 0 && pool_k >= 1 && C >= 4 && C % 4 == 0, "train_pool_fwd: C=%d must be a multiple of 4", C);
+    if (groups == 0) return PSA_OK;
+    PSA_REQUIRE(y && scale && shift && pooled && argk, "train_pool_fwd: null buffer");
+    const long long total = groups * (C / 4);
+    train_pool_fwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, as_stream(stream)>>>(
+        groups, pool_k, C / 4, reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(scale), reinterpret_cast<const float4*>(shift),
+        reinterpret_cast<float4*>(pooled), reinterpret_cast<int4*>(argk));
+    return check_launch("train_pool_fwd_kernel");
+}
+
+static const int kBnbMaxBlocks = 4 * kNumSMs;
+
+extern "C" size_t psa_bn_bwd_workspace_bytes(int C) { return (size_t)kBnbMaxBlocks * 2 * C * sizeof(float); }
+
+extern "C" int psa_bn_bwd_coeffs(long long rows, int C, const psa_grad_in* g, const float* gamma, const float* mean_inv, float* dgamma,
+                                 float* dbeta, float* ca, float* cb, float* cc, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    PSA_REQUIRE(rows >= 1 && C >= 4, "bn_bwd_coeffs: bad dims");
+    PSA_SUPPORTED(C % 4 == 0 && C <= 1024, "bn_bwd_coeffs: C=%d must be a multiple of 4, at most 1024", C);
+    PSA_REQUIRE(g && gamma && mean_inv && dgamma && dbeta && ca && cb && cc, "bn_bwd_coeffs: null buffer");
+    PSA_REQUIRE(workspace && workspace_bytes >= psa_bn_bwd_workspace_bytes(C), "bn_bwd_coeffs: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    GradIn gi(*g);
+    gi.ca = gi.cb = gi.cc = nullptr;
+    PSA_REQUIRE(gi.y != nullptr && gi.ld % 4 == 0, "bn_bwd_coeffs: y must be given with a row stride that is a multiple of 4");
+    // units the blocks iterate over: rows (dense dz) or pooled groups (max-pool routing)
+    const long long units = gi.mode == 0 ? rows : rows / gi.pool_k;
+    if (gi.mode == 1) PSA_REQUIRE(gi.pool_k >= 1 && rows % gi.pool_k == 0 && gi.C == C, "bn_bwd_coeffs: pooled routing needs rows %% pool_k == 0");
+    const int RL = kBnbThreads / (C / 4);
+    long long blocks = (units + (long long)RL * 8 - 1) / ((long long)RL * 8);
+    if (blocks > kBnbMaxBlocks) blocks = kBnbMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    const long long upb = (units + blocks - 1) / blocks;
+    blocks = (units + upb - 1) / upb;
+    float* partial = reinterpret_cast<float*>(workspace);
+    bn_bwd_partial_kernel<<<(unsigned)blocks, kBnbThreads, 0, st>>>(gi, units, C, mean_inv, upb, partial);
+    int rc = check_launch("bn_bwd_partial_kernel");
+    if (rc != PSA_OK) return rc;
+    bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>((int)blocks, C, 1.0 / (double)rows, partial, gamma, mean_inv, dgamma, dbeta, ca, cb, cc);
+    return check_launch("bn_bwd_final_kernel");
+}
+
+extern "C" size_t psa_sa_conv1_bwd_workspace_bytes(int C1) { return (size_t)kBnbMaxBlocks * 3 * C1 * sizeof(float); }
+
+extern "C" int psa_sa_conv1_bwd(int b, int n, int m, int nsample, int C1, const float* xyz, const float* new_xyz, const int* idx,
+                                const psa_grad_in* g, float* dW_xyz, float* dU, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 1 && n >= 1 && m >= 1 && nsample >= 1, "sa_conv1_bwd: bad dims");
+    PSA_SUPPORTED(C1 % 4 == 0 && C1 <= 1024, "sa_conv1_bwd: C1=%d", C1);
+    PSA_REQUIRE(xyz && new_xyz && idx && g && dW_xyz, "sa_conv1_bwd: null buffer");
+    PSA_REQUIRE(workspace && workspace_bytes >= psa_sa_conv1_bwd_workspace_bytes(C1), "sa_conv1_bwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const GradIn gi(*g);
+    const long long rows = (long long)b * m * nsample;
+    const int RL = kBnbThreads / (C1 / 4);
+    long long blocks = (rows + (long long)RL * 8 - 1) / ((long long)RL * 8);
+    if (blocks > kBnbMaxBlocks) blocks = kBnbMaxBlocks;
+    const long long rpb = (rows + blocks - 1) / blocks;
+    blocks = (rows + rpb - 1) / rpb;
+    float* partial = reinterpret_cast<float*>(workspace);
+    conv1_dwxyz_partial_kernel<<<(unsigned)blocks, kBnbThreads, 0, st>>>(gi, rows, nsample, (long long)m * nsample, n, m, C1, xyz, new_xyz, idx,
+                                                                         rpb, partial);
+    int rc = check_launch("conv1_dwxyz_partial_kernel");
+    if (rc != PSA_OK) return rc;
+    rc = reduce_partials((int)blocks, 3 * C1, partial, dW_xyz, st);
+    if (rc != PSA_OK) return rc;
+    if (dU != nullptr) {
+        PSA_SUPPORTED(C1 <= 128, "sa_conv1_bwd: the ordered GroupPointGrad gather handles C1 <= 128 (got %d)", C1);
+        dim3 grid((unsigned)((n + 8 * kScatJ - 1) / (8 * kScatJ)), (unsigned)b);
+        group_grad_gather_kernel<<<grid, 256, 0, st>>>(gi, n, m * nsample, C1, idx, dU);
+        return check_launch("group_grad_gather_kernel");
+    }
+    return PSA_OK;
+}
+
+extern "C" int psa_train_bias_grad(long long rows, int N, const psa_grad_in* g, float* db, psa_stream_t stream) {
+    PSA_REQUIRE(rows >= 1 && N >= 1 && g && db, "train_bias_grad: bad arguments");
+    const GradIn gi(*g);
+    bias_grad_kernel<<<N, 256, 0, as_stream(stream)>>>(gi, rows, db);
+    return check_launch("bias_grad_kernel");
+}
+
+extern "C" int psa_softmax_xent(int b, int c, const float* logits, const int* labels, float* loss, float* dlogits, psa_stream_t stream) {
+    PSA_REQUIRE(b >= 1 && c >= 1 && logits && labels && loss && dlogits, "softmax_xent: bad arguments");
+    PSA_SUPPORTED(b <= 1024, "softmax_xent: batch %d > 1024", b);
+    softmax_xent_kernel<<<1, ((b + 31) / 32) * 32, 0, as_stream(stream)>>>(b, c, logits, labels, loss, dlogits);
+    return check_launch("softmax_xent_kernel");
+}
+
+extern "C" int psa_adam_step(long long count, float* params, const float* grads, float* m, float* v, float lr, float beta1, float beta2,
+                             float eps, int step, float grad_scale, psa_stream_t stream) {
+    PSA_REQUIRE(count >= 0 && step >= 1, "adam_step: bad arguments");
+    if (count == 0) return PSA_OK;
+    PSA_REQUIRE(params && grads && m && v, "adam_step: null buffer");
+    const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step)));
+    long long blocks = (count + 255) / 256;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(count, params, grads, m, v, lr_t, beta1, beta2, eps, grad_scale);
+    return check_launch("adam_kernel");
+}

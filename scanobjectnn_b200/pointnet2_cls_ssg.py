@@ -31,8 +31,19 @@ def init_params(num_class=NUM_CLASSES, seed=0, device="cuda", randomize_bn=False
 
 
 def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
-    """Classification PointNet++ (SSG): input (B,N,3), output (B,num_class)."""
-    _require_inference(is_training)
+    """Classification PointNet++ (SSG): input (B,N,3), output (B,num_class).
+
+    is_training=True: batch-statistics batch norm in every layer (moving averages updated with ``bn_decay``), dropout in
+    the head, and logits that carry a grad_fn -- ``get_loss(...).backward()`` runs the hand-written backward kernels and
+    leaves the gradient of every variable in ``params._flat.grad_of(name)`` (training.py)."""
+    if is_training:
+        from .training import get_model_training
+        logits, tr = get_model_training(point_cloud, bn_decay, num_class, params)
+        lv = tr.levels
+        end_points = {"l0_xyz": point_cloud, "l1_xyz": lv[0].new_xyz, "l1_points": lv[0].pooled.view(point_cloud.shape[0], lv[0].m, -1),
+                      "l1_indices": lv[0].idx, "l2_xyz": lv[1].new_xyz, "l2_points": lv[1].pooled.view(point_cloud.shape[0], lv[1].m, -1),
+                      "l2_indices": lv[1].idx, "l3_points": lv[2].pooled.view(point_cloud.shape[0], 1, -1)}
+        return logits, end_points
     batch_size = point_cloud.shape[0]
     end_points = {"l0_xyz": point_cloud}
     l0_xyz, l0_points = point_cloud, None

@@ -141,14 +141,18 @@ def test_pointnet2_cls_ssg_matches_oracle(kind, mlp_mode):
     assert err < TOL * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("kind,n,m,r,k,c,c1", [("ball", 2048, 512, 0.2, 32, 0, 64), ("shell", 2048, 512, 0.2, 64, 0, 64),
-                                               ("ball", 512, 128, 0.4, 64, 128, 128), ("dup", 300, 40, 0.3, 20, 5, 64)])
-def test_sa_conv1_prebn_training_front(kind, n, m, r, k, c, c1):
+@pytest.mark.parametrize("kind,n,m,r,k,c,c1,b", [("ball", 2048, 512, 0.2, 32, 0, 64, 3), ("shell", 2048, 512, 0.2, 64, 0, 64, 3),
+                                                 ("ball", 512, 128, 0.4, 64, 128, 128, 3), ("dup", 300, 40, 0.3, 20, 5, 64, 3),
+                                                 # CTA ranges that cross cloud boundaries (grid rebuilt mid-CTA), odd nsample
+                                                 ("ball", 500, 37, 0.3, 13, 0, 64, 41), ("shell", 700, 333, 0.25, 32, 7, 128, 5),
+                                                 # scan mode (cloud too small for the grid) and a 4096-point cloud (16 points per thread)
+                                                 ("ball", 200, 20, 0.4, 16, 0, 64, 4), ("ball", 4096, 1024, 0.15, 32, 0, 64, 2)])
+def test_sa_conv1_prebn_training_front(kind, n, m, r, k, c, c1, b):
     """variant F1: pre-BN conv1 output + BN batch statistics vs the fp64 restatement of
     query_ball_point -> group_point -> centre -> concat -> conv2d + bias_add (pointnet_util.py:44-50,117-123)."""
     rng = np.random.default_rng(n + k)
-    xyz = make_clouds(kind, 3, n, seed=n)
-    pts = rng.standard_normal((3, n, c)).astype(np.float32) if c else None
+    xyz = make_clouds(kind, b, n, seed=n)
+    pts = rng.standard_normal((b, n, c)).astype(np.float32) if c else None
     w1 = (rng.uniform(-1, 1, (3 + c, c1)) * np.sqrt(6.0 / (3 + c + c1))).astype(np.float32)
     bias = rng.uniform(-0.1, 0.1, c1).astype(np.float32)
     new_xyz = orc.gather_point(xyz, orc.fps(xyz, m))
@@ -163,3 +167,25 @@ def test_sa_conv1_prebn_training_front(kind, n, m, r, k, c, c1):
     assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
     s_want = np.stack([want.reshape(-1, c1).sum(0), (want.reshape(-1, c1) ** 2).sum(0)])
     np.testing.assert_allclose(G.npy(stats), s_want, rtol=2e-5, atol=1e-3)
+
+
+def test_sa_conv1_prebn_nonfinite_inputs_keep_reference_indices():
+    """NaN / inf coordinates: the reference's max(sqrtf(NaN),1e-20f) < r counts a NaN distance as inside.  The streaming
+    kernel answers such queries (and whole clouds with a non-finite point) with the ordered scan: idx / pts_cnt exact."""
+    n, m, k = 1024, 64, 32
+    xyz = make_clouds("ball", 4, n, seed=77)
+    xyz[1, 5, 1] = np.nan                      # cloud 1: grid unusable, every query scans
+    xyz[2, 100, 0] = np.inf
+    new_xyz = orc.gather_point(xyz, orc.fps(np.nan_to_num(xyz, nan=0.0, posinf=0.0), m))
+    new_xyz[0, 3, 2] = np.nan                  # cloud 0: one NaN query on a finite cloud
+    new_xyz[3, 7, 0] = -np.inf
+    w1 = np.random.default_rng(5).uniform(-1, 1, (3, 64)).astype(np.float32)
+    pre, idx, cnt, _ = ops.sa_conv1_prebn(G.cu(xyz), G.cu(new_xyz), None, 0.25, k, G.cu(w1), None)
+    oidx, ocnt = orc.query_ball_point(0.25, k, xyz, new_xyz, contract=True)
+    assert np.array_equal(G.npy(idx), oidx) and np.array_equal(G.npy(cnt), ocnt)
+    # finite rows of the finite clouds still carry the conv output
+    rows = orc.group_point(xyz, oidx) - new_xyz[:, :, None, :]
+    want = rows.astype(np.float64) @ w1.astype(np.float64)
+    ok = np.isfinite(want)
+    assert ok[0].mean() > 0.9
+    assert np.abs(G.npy(pre)[ok] - want[ok]).max() < TOL * max(1.0, np.abs(want[ok]).max())

@@ -1,0 +1,256 @@
+"""GPU parity of the training path (forward with batch statistics, backward, Adam) against the float64 restatements
+oracle/train_oracle.py / oracle/train_model_oracle.py.  Bound: 1e-4 relative to the largest entry of each gradient tensor
+-- the reference's own gradient tests use 1e-4 (pointnet2/tf_ops/grouping/tf_grouping_op_test.py:25,
+3d_interpolation/tf_interpolate_op_test.py:21)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from oracle import train_model_oracle as M
+from oracle import train_oracle as T
+from scanobjectnn_b200 import _lib, pointnet2_cls_ssg
+from scanobjectnn_b200._lib import PsaActIn, PsaGradIn
+from scanobjectnn_b200.pointnet_util import add_sa_module_params
+from scanobjectnn_b200.synthetic import make_clouds
+from scanobjectnn_b200.tf_util import VariableStore
+from scanobjectnn_b200.training import LevelSpec, PointNet2ClsTrainer, _plain_grad, _raw_in
+
+from . import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+GTOL = 1e-4
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _vp(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _rel(got, want):
+    return float(np.abs(got - want).max() / max(1e-30, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("rows,K,N", [(1000, 64, 64), (4096, 64, 128), (777, 259, 256), (32, 256, 15), (640, 128, 1024)])
+def test_dense_forward_backward_products(rows, K, N):
+    """the three products of a layer on the fused GEMM: y = relu(bn(x)).W + b (+ column statistics), dx = dy.W^T, dW = h^T.dy"""
+    lib = _lib.load()
+    rng = np.random.default_rng(rows + K)
+    x = rng.standard_normal((rows, K)).astype(np.float32)
+    s = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    t = rng.standard_normal(K).astype(np.float32) * 0.3
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32) * 0.1
+    xd, sd, td, Wd, bd = map(G.cu, (x, s, t, W, b))
+    y = torch.empty((rows, N), device="cuda")
+    stats = torch.empty((2, N), device="cuda")
+    need = lib.psa_train_dense_workspace_bytes(rows, K, N)
+    ws = torch.empty(need // 4 + 16, device="cuda")
+    a = PsaActIn()
+    a.x = xd.data_ptr(); a.ld = K; a.mask = None; a.relu = 1
+    if K % 4 == 0:
+        a.scale = sd.data_ptr(); a.shift = td.data_ptr()
+        h = np.maximum(x.astype(np.float64) * s + t, 0)
+    else:
+        a.scale = None; a.shift = None; a.relu = 0
+        h = x.astype(np.float64)
+    assert lib.psa_train_dense_fwd(rows, K, N, C.byref(a), _vp(Wd), _vp(bd), _vp(y), _vp(stats), _vp(ws), C.c_size_t(need), _st()) == 0
+    want = h @ W.astype(np.float64) + b
+    assert _rel(G.npy(y), want) < 2e-6
+    np.testing.assert_allclose(G.npy(stats)[0], want.sum(0), rtol=1e-5, atol=1e-3 * np.sqrt(rows))
+    np.testing.assert_allclose(G.npy(stats)[1], (want ** 2).sum(0), rtol=1e-5, atol=1e-3)
+    # backward products with a plain incoming gradient
+    dy = rng.standard_normal((rows, N)).astype(np.float32)
+    dyd = G.cu(dy)
+    g = _plain_grad(dyd)
+    dx = torch.empty((rows, K), device="cuda")
+    assert lib.psa_train_dense_bwd_input(rows, K, N, C.byref(g), _vp(Wd), _vp(dx), K, 0, _st()) == 0
+    assert _rel(G.npy(dx), dy.astype(np.float64) @ W.astype(np.float64).T) < 2e-6
+    if K > 3:
+        dxs = torch.empty((rows, K - 3), device="cuda")
+        assert lib.psa_train_dense_bwd_input(rows, K, N, C.byref(g), _vp(Wd), _vp(dxs), K - 3, 3, _st()) == 0
+        assert _rel(G.npy(dxs), (dy.astype(np.float64) @ W.astype(np.float64).T)[:, 3:]) < 2e-6
+    dW = torch.empty((K, N), device="cuda")
+    assert lib.psa_train_dense_bwd_weight(rows, K, N, C.byref(a), C.byref(g), _vp(dW), _vp(ws), C.c_size_t(need), _st()) == 0
+    assert _rel(G.npy(dW), h.T @ dy.astype(np.float64)) < 5e-6
+    dW2 = torch.empty((K, N), device="cuda")
+    assert lib.psa_train_dense_bwd_weight(rows, K, N, C.byref(a), C.byref(g), _vp(dW2), _vp(ws), C.c_size_t(need), _st()) == 0
+    assert torch.equal(dW, dW2), "weight gradient is not bit-reproducible"
+
+
+@pytest.mark.parametrize("groups,pool_k,Cc", [(96, 32, 128), (40, 20, 64)])
+def test_bn_relu_pool_layer_backward(groups, pool_k, Cc):
+    """batch-norm finalize, max-pool with arg routing, BN backward sums / coefficients and the on-the-fly dy (both dz sources)"""
+    lib = _lib.load()
+    rng = np.random.default_rng(groups)
+    rows = groups * pool_k
+    y = rng.standard_normal((rows, Cc)).astype(np.float32) * 1.3 + 0.2
+    gamma = rng.uniform(0.5, 1.5, Cc).astype(np.float32)
+    beta = rng.standard_normal(Cc).astype(np.float32) * 0.2
+    yd, gd, bd = map(G.cu, (y, gamma, beta))
+    stats = G.cu(np.stack([y.astype(np.float64).sum(0), (y.astype(np.float64) ** 2).sum(0)]).astype(np.float32))
+    f = lambda *s: torch.empty(s, device="cuda")  # noqa: E731
+    scale, shift, mean_inv, mm, mv = f(Cc), f(Cc), f(2, Cc), torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    assert lib.psa_bn_finalize(Cc, rows, _vp(stats), _vp(gd), _vp(bd), C.c_float(0.9), _vp(mm), _vp(mv), _vp(scale), _vp(shift), _vp(mean_inv), _st()) == 0
+    z64, c_bn, mean, var = T.bn_train_fwd(y.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64))
+    np.testing.assert_allclose(G.npy(mean_inv)[0], mean, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(G.npy(mean_inv)[1], 1 / np.sqrt(var + 1e-3), rtol=1e-5)
+    np.testing.assert_allclose(G.npy(mm), 0.1 * mean, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(G.npy(mv), 0.9 + 0.1 * var, rtol=1e-5)
+    pooled, argk = f(groups, Cc), torch.empty((groups, Cc), dtype=torch.int32, device="cuda")
+    assert lib.psa_train_pool_fwd(groups, pool_k, Cc, _vp(yd), _vp(scale), _vp(shift), _vp(pooled), _vp(argk), _st()) == 0
+    h64, rmask = T.relu_fwd(z64)
+    p64, c_pool = T.maxpool_fwd(h64.reshape(groups, pool_k, Cc), axis=1)
+    assert np.abs(G.npy(pooled) - p64).max() < 1e-5
+    assert (G.npy(argk) == c_pool[0]).mean() > 0.999            # near-ties may pick the other row in fp32
+    # ---- backward through pool + relu + BN ----
+    dp = rng.standard_normal((groups, Cc)).astype(np.float32)
+    dpd = G.cu(dp)
+    g = PsaGradIn()
+    g.y = yd.data_ptr(); g.ld = Cc; g.s = scale.data_ptr(); g.t = shift.data_ptr(); g.relu = 1
+    g.ca = None; g.cb = None; g.cc = None; g.dh = None; g.ld_dh = 0; g.mask = None
+    g.dp = dpd.data_ptr(); g.pv = pooled.data_ptr(); g.argk = argk.data_ptr(); g.pool_k = pool_k; g.C = Cc; g.mode = 1
+    dgamma, dbeta, ca, cb, cc = f(Cc), f(Cc), f(Cc), f(Cc), f(Cc)
+    need = lib.psa_bn_bwd_workspace_bytes(Cc)
+    ws = torch.empty(need // 4 + 16, device="cuda")
+    assert lib.psa_bn_bwd_coeffs(rows, Cc, C.byref(g), _vp(gd), _vp(mean_inv), _vp(dgamma), _vp(dbeta), _vp(ca), _vp(cb), _vp(cc), _vp(ws),
+                                 C.c_size_t(need), _st()) == 0
+    # oracle with the GPU's own argmax (so near-tie flips do not enter the comparison)
+    dh64 = np.zeros((groups, pool_k, Cc))
+    np.put_along_axis(dh64, G.npy(argk)[:, None, :].astype(np.int64), dp[:, None, :].astype(np.float64), axis=1)
+    dz64 = dh64.reshape(rows, Cc) * rmask
+    dy64, dg64, db64 = T.bn_train_bwd(dz64, c_bn)
+    assert _rel(G.npy(dgamma), dg64) < GTOL and _rel(G.npy(dbeta), db64) < GTOL
+    g.ca = ca.data_ptr(); g.cb = cb.data_ptr(); g.cc = cc.data_ptr()
+    # dy through an identity-weight input-gradient product
+    eye = torch.eye(Cc, device="cuda")
+    dy = f(rows, Cc)
+    assert lib.psa_train_dense_bwd_input(rows, Cc, Cc, C.byref(g), _vp(eye), _vp(dy), Cc, 0, _st()) == 0
+    assert _rel(G.npy(dy), dy64) < GTOL
+    # dense dz source: same layer fed with the materialised dh
+    dhd = G.cu(dh64.reshape(rows, Cc).astype(np.float32))
+    g.mode = 0; g.dh = dhd.data_ptr(); g.ld_dh = Cc; g.ca = None; g.cb = None; g.cc = None
+    dgamma2, dbeta2 = f(Cc), f(Cc)
+    assert lib.psa_bn_bwd_coeffs(rows, Cc, C.byref(g), _vp(gd), _vp(mean_inv), _vp(dgamma2), _vp(dbeta2), _vp(ca), _vp(cb), _vp(cc), _vp(ws),
+                                 C.c_size_t(need), _st()) == 0
+    assert _rel(G.npy(dgamma2), dg64) < GTOL and _rel(G.npy(dbeta2), db64) < GTOL
+
+
+def test_first_layer_backward_ordered_group_point_grad():
+    """psa_sa_conv1_bwd: dW_xyz and the ordered-gather GroupPointGrad against np.add.at (tf_grouping_g.cu:61-78)"""
+    lib = _lib.load()
+    b, n, m, k, c1 = 3, 300, 40, 24, 128
+    rng = np.random.default_rng(1)
+    xyz = make_clouds("dup", b, n, seed=5)
+    new_xyz = orc.gather_point(xyz, orc.fps(xyz, m))
+    idx, _ = orc.query_ball_point(0.35, k, xyz, new_xyz, contract=True)
+    dy0 = rng.standard_normal((b, m, k, c1)).astype(np.float32)
+    dyd = G.cu(dy0.reshape(-1, c1))
+    g = _plain_grad(dyd)
+    dW = torch.empty((3, c1), device="cuda")
+    dU = torch.empty((b * n, c1), device="cuda")
+    need = lib.psa_sa_conv1_bwd_workspace_bytes(c1)
+    ws = torch.empty(need // 4 + 16, device="cuda")
+    args = (b, n, m, k, c1, _vp(G.cu(xyz)), _vp(G.cu(new_xyz)), _vp(G.cu(idx)), C.byref(g))
+    assert lib.psa_sa_conv1_bwd(*args, _vp(dW), _vp(dU), _vp(ws), C.c_size_t(need), _st()) == 0
+    d = (orc.group_point(xyz, idx) - new_xyz[:, :, None, :]).astype(np.float64)
+    want_dW = np.einsum("bmka,bmkc->ac", d, dy0.astype(np.float64))
+    assert _rel(G.npy(dW), want_dW) < 1e-5
+    want_dU = T.group_bwd(dy0.astype(np.float64), idx.astype(np.int64), n).reshape(b * n, c1)
+    assert _rel(G.npy(dU), want_dU) < 1e-5
+    dU2 = torch.empty_like(dU)
+    assert lib.psa_sa_conv1_bwd(*args, _vp(dW), _vp(dU2), _vp(ws), C.c_size_t(need), _st()) == 0
+    assert torch.equal(dU, dU2), "ordered GroupPointGrad must be bit-reproducible"
+
+
+SMALL_LEVELS = [LevelSpec("layer1", 64, 0.3, 16, [64, 64, 128]), LevelSpec("layer2", 16, 0.6, 16, [128, 128, 256]),
+                LevelSpec("layer3", None, None, None, [256, 512, 1024], group_all=True)]
+
+
+def _small_model(seed=0):
+    return pointnet2_cls_ssg.init_params(seed=seed, randomize_bn=True)
+
+
+def _np_params(p):
+    return {k: v.detach().cpu().numpy().astype(np.float64) for k, v in p.items()}
+
+
+def test_training_step_gradients_match_float64_restatement():
+    """whole classifier: forward (batch-stat BN everywhere), loss, every parameter gradient, moving averages, one Adam step"""
+    B, N = 8, 256
+    p = _small_model(seed=3)
+    tr = PointNet2ClsTrainer(p, B, N, 15, levels=SMALL_LEVELS)
+    xyz = make_clouds("ball", B, N, seed=11)
+    labels = np.random.default_rng(0).integers(0, 15, B).astype(np.int32)
+    before = _np_params(p)
+    tr.draw_dropout()
+    masks = {ly.scope: ly.mask.cpu().numpy().astype(np.float64) for ly in tr.head if ly.mask is not None}
+    logits = tr.forward(G.cu(xyz), bn_decay=0.7)
+    loss, dl = tr.loss_and_grad(logits, G.cu(labels))
+    tr.backward(dl)
+    torch.cuda.synchronize()
+    levels = [(s.scope, s.npoint, s.radius, s.nsample, s.mlp, s.group_all) for s in SMALL_LEVELS]
+    head = [("fc1", 512, True, 0.5), ("fc2", 256, True, 0.5), ("fc3", None, False, None)]
+    want = M.cls_train_step(xyz, labels, before, levels, head, masks, 15)
+    for lv, oidx in zip(tr.levels[:2], want["idx"][:2]):
+        assert np.array_equal(G.npy(lv.idx), oidx)
+    assert np.abs(G.npy(logits) - want["logits"]).max() < 1e-4 * max(1.0, np.abs(want["logits"]).max())
+    assert abs(float(loss.item()) - want["loss"]) < 1e-5 * max(1.0, abs(want["loss"]))
+    worst = {}
+    for name, gw in want["grads"].items():
+        got = G.npy(tr.fp.grad_of(name)).reshape(gw.shape).astype(np.float64)
+        if name.endswith("/biases") and f"{name[:-7]}/bn/gamma" in before:
+            assert np.abs(got).max() == 0.0 and np.abs(gw).max() < 1e-9       # exact zero here, rounding noise there
+            continue
+        worst[name] = _rel(got, gw)
+    bad = {k: v for k, v in worst.items() if v > GTOL}
+    print("max relative gradient error:", max(worst.values()), "over", len(worst), "tensors")
+    assert not bad, bad
+    # moving averages: decay * old + (1 - decay) * batch statistic (tf_util.py:526-531)
+    for scope, (mean, var) in want["batch_stats"].items():
+        np.testing.assert_allclose(G.npy(p[f"{scope}/bn/moving_mean"]), 0.7 * before[f"{scope}/bn/moving_mean"] + 0.3 * mean, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(G.npy(p[f"{scope}/bn/moving_variance"]), 0.7 * before[f"{scope}/bn/moving_variance"] + 0.3 * var, rtol=2e-4, atol=1e-6)
+    # Adam
+    g_before = {k: G.npy(tr.fp.grad_of(k)).astype(np.float64) for k in want["grads"]}
+    tr.adam(1e-3)
+    for name in ("layer1/conv1/weights", "layer3/conv2/bn/gamma", "fc3/weights", "fc3/biases"):
+        pw, _, _ = M.adam_update(before[name], g_before[name].reshape(before[name].shape), 0.0, 0.0, 1, 1e-3)
+        np.testing.assert_allclose(G.npy(p[name]).astype(np.float64), pw, rtol=1e-6, atol=1e-7)
+
+
+def test_training_step_is_bit_reproducible_and_learns():
+    B, N = 8, 256
+    xyz = G.cu(make_clouds("shell", B, N, seed=2))
+    labels = G.cu(np.arange(B, dtype=np.int32) % 15)
+    grads = []
+    for _ in range(2):
+        p = _small_model(seed=5)
+        tr = PointNet2ClsTrainer(p, B, N, 15, levels=SMALL_LEVELS)
+        tr._gen.manual_seed(7)
+        tr.draw_dropout()
+        tr.backward(tr.loss_and_grad(tr.forward(xyz, 0.5), labels)[1])
+        grads.append(tr.fp.grad.clone())
+    assert torch.equal(grads[0], grads[1]), "two runs of the same step must give bit-identical gradients (no atomics)"
+    losses = [float(tr.train_step(xyz, labels, lr=2e-3, bn_decay=0.5).item()) for _ in range(30)]
+    print("loss", losses[0], "->", losses[-1])
+    assert losses[-1] < 0.5 * losses[0]
+
+
+def test_get_model_is_training_autograd_path():
+    """pointnet2_cls_ssg.get_model(is_training=True) no longer raises: logits carry a grad_fn whose backward fills the flat bucket"""
+    B, N = 4, 2048
+    p = pointnet2_cls_ssg.init_params(seed=1)
+    xyz = G.cu(make_clouds("ball", B, N, seed=4))
+    labels = G.cu(np.array([1, 3, 5, 7], dtype=np.int32))
+    logits, end_points = pointnet2_cls_ssg.get_model(xyz, True, bn_decay=0.5, params=p)
+    assert logits.shape == (B, 15) and logits.requires_grad
+    loss = pointnet2_cls_ssg.get_loss(logits, labels)
+    loss.backward()
+    flat = p._flat
+    assert flat.flat.grad is not None and torch.isfinite(flat.flat.grad).all() and float(flat.flat.grad.abs().max()) > 0
+    assert end_points["l1_indices"].shape == (B, 512, 32)
