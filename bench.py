@@ -136,6 +136,181 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _ev_time(fn, reps, flush=None, sink=None, spin=400_000):
+    """median CUDA-event time (us) of fn(); with `flush`, L2 is flushed by READING it (clean lines) before every launch and
+    a ~0.2 ms spin kernel sits in front so the host has enqueued e0 / fn / e1 before the GPU gets there"""
+    import torch
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            sink.copy_(flush.sum())
+            torch.cuda._sleep(spin)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def run_training_bench(args, dev, rank, world, local_rank):
+    """Second workload of the line: one TRAINING step of pointnet2_cls_ssg per B=32 batch and GPU (pointnet2/train.py:246-252:
+    forward with batch-statistics BN, loss, backward, one flat-bucket NCCL all-reduce of the gradients, Adam).  Returns the
+    `train` object (rank 0) or None."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from scanobjectnn_b200 import pointnet2_cls_ssg
+    from scanobjectnn_b200.shard import max_over_ranks, rank_seed
+    from scanobjectnn_b200.synthetic import make_clouds
+    from scanobjectnn_b200.training import PointNet2ClsTrainer
+
+    if args.no_train:
+        return None
+    params = pointnet2_cls_ssg.init_params(seed=1, device=dev)          # identical initial weights on every rank
+    tr = PointNet2ClsTrainer(params, B, N, NUM_CLASS, device=dev)
+    NPOOL = 8
+    pool = [torch.from_numpy(make_clouds("ball", B, N, seed=rank_seed(2001 + i, rank))).to(dev) for i in range(NPOOL)]
+    labels = torch.from_numpy(np.random.default_rng(rank).integers(0, NUM_CLASS, B).astype(np.int32)).to(dev)
+    steps = max(4, min(args.steps, args.train_steps))
+    warm = 3
+
+    def step(i):
+        return tr.train_step(pool[i % NPOOL], labels, lr=1e-3, bn_decay=0.5)
+
+    for i in range(warm):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(warm + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), device=dev)
+    # the all-reduce alone (the only data-path collective of the whole framework): flat fp32 bucket, NCCL over NVLink
+    ar_us = None
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(tr.fp.grad)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(tr.fp.grad)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_us = max_over_ranks(a0.elapsed_time(a1) * 1e3 / 20, device=dev)
+    # phases of one step on rank 0 (device time, eager launches)
+    phases = {}
+    if rank == 0 and world == 1:
+        x = pool[0]
+        tr.draw_dropout()
+        torch.cuda.synchronize()
+        out = {}
+        phases["forward_us"] = _ev_time(lambda: out.__setitem__("l", tr.forward(x, 0.5)), 5)
+        dl = tr.loss_and_grad(out["l"], labels)[1]
+        phases["backward_us"] = _ev_time(lambda: tr.backward(dl), 5)
+        phases["adam_us"] = _ev_time(lambda: tr.adam(1e-3), 5)
+    if rank != 0:
+        return None
+    flops_fwd = sum(SA_FLOPS.values()) + 2 * B * (1024 * 512 + 512 * 256 + 256 * NUM_CLASS)
+    return {"workload": "pointnet2_cls_ssg TRAINING step (fwd with batch-stat BN + loss + bwd + grad all-reduce + Adam), B=32 N=2048 per GPU",
+            "clouds_per_s": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "n_gpus": world,
+            "allreduce_us": ar_us, "allreduce_bytes": int(tr.fp.total * 4), "params": int(tr.fp.total),
+            "loss_last": float(loss.item()), "dtype": "f32 (fp32 FMA GEMMs, fixed-order reductions: bit-reproducible gradients)",
+            "approx_tflops_fp32": 3 * flops_fwd / (ms / steps * 1e-3) / 1e12, **phases}
+
+
+def run_sweep(dev, peaks):
+    """BASELINE.json configs[4]: FPS + ball-query sweep N x B on one GPU -- us, algorithmic GB/s vs the measured HBM peak,
+    ns per FPS round.  m = N/4, r = 0.2, K = 32, uniform-ball clouds."""
+    import torch
+
+    from scanobjectnn_b200 import ops
+    from scanobjectnn_b200.synthetic import make_clouds
+    rows = []
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    sink = torch.zeros((), dtype=torch.float32, device=dev)
+    for n in (1024, 2048, 4096, 8192):
+        base = torch.from_numpy(make_clouds("ball", 4, n, seed=1004 + n)).to(dev)
+        for b in (1, 4, 16, 64, 256):
+            x = base.repeat((b + 3) // 4, 1, 1)[:b].contiguous()
+            m = n // 4
+            _, q = ops.farthest_point_sample_and_gather(m, x)
+            ops.query_ball_point(0.2, 32, x, q)
+            t_fps = _ev_time(lambda: ops.farthest_point_sample_and_gather(m, x), 3, flush, sink)
+            t_bq = _ev_time(lambda: ops.query_ball_point(0.2, 32, x, q), 3, flush, sink)
+            by_fps = b * (12 * n + 4 * m + 12 * m)
+            by_bq = b * (12 * n + 12 * m + 4 * m * 32 + 4 * m)
+            rows.append({"N": n, "B": b, "fps_us": round(t_fps, 1), "fps_ns_per_round": round(t_fps * 1e3 / max(m - 1, 1), 1),
+                         "fps_gbs": round(by_fps / t_fps / 1e3, 2), "ballq_us": round(t_bq, 1), "ballq_gbs": round(by_bq / t_bq / 1e3, 1),
+                         "ballq_hbm_frac": round(by_bq / t_bq / 1e3 / peaks["hbm"], 4)})
+    del flush
+    return {"config": "FPS (m=N/4) + ball query (r=0.2, K=32), uniform-ball clouds, L2 read-flushed before every launch, median of 3",
+            "note": "FPS is bound by its m-1 dependent arg-max rounds (ns_per_round), the ball query by issue/latency: both far below "
+                    "the HBM roofline by construction -- their algorithmic bytes are a few MB", "rows": rows}
+
+
+def run_ref_gpu(dev, x, l1_xyz, l2_xyz, l1_pts_shape_c=128):
+    """R-GPU contender: the reference's own CUDA kernels, compiled unmodified for sm_100a by oracle/Makefile into
+    oracle/_ref/libref_tfops.so, timed on the same tensors in the same run.  Reported baseline only (like cpu_baseline)."""
+    import ctypes as C
+
+    import torch
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_tfops.so")
+    if not os.path.exists(path):
+        return None
+    ref = C.CDLL(path)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    out = {}
+    temp = torch.empty((32, N), dtype=torch.float32, device=dev)
+    i1 = torch.zeros((B, 512), dtype=torch.int32, device=dev)
+    g1 = torch.zeros((B, 512, 3), dtype=torch.float32, device=dev)
+
+    def fps1():
+        ref.ref_fps(B, N, 512, p(x), p(temp), p(i1), 0)
+        ref.ref_gather_point(B, N, 512, p(x), p(i1), p(g1), 0)
+    out["fps1"] = _ev_time(fps1, 5)
+    i2 = torch.zeros((B, 128), dtype=torch.int32, device=dev)
+    g2 = torch.zeros((B, 128, 3), dtype=torch.float32, device=dev)
+
+    def fps2():
+        ref.ref_fps(B, 512, 128, p(l1_xyz), p(temp), p(i2), 0)
+        ref.ref_gather_point(B, 512, 128, p(l1_xyz), p(i2), p(g2), 0)
+    out["fps2"] = _ev_time(fps2, 5)
+    q1 = torch.zeros((B, 512, 32), dtype=torch.int32, device=dev)
+    c1 = torch.zeros((B, 512), dtype=torch.int32, device=dev)
+    out["ballq1"] = _ev_time(lambda: ref.ref_query_ball_point(B, N, 512, C.c_float(0.2), 32, p(x), p(l1_xyz), p(q1), p(c1), 0), 5)
+    q2 = torch.zeros((B, 128, 64), dtype=torch.int32, device=dev)
+    c2 = torch.zeros((B, 128), dtype=torch.int32, device=dev)
+    out["ballq2"] = _ev_time(lambda: ref.ref_query_ball_point(B, 512, 128, C.c_float(0.4), 64, p(l1_xyz), p(l2_xyz), p(q2), p(c2), 0), 5)
+    # the grouping the reference needs in front of its convolutions (group_point of xyz at SA1, of xyz + features at SA2)
+    gx = torch.empty((B, 512, 32, 3), dtype=torch.float32, device=dev)
+    out["group_sa1"] = _ev_time(lambda: ref.ref_group_point(B, N, 3, 512, 32, p(x), p(q1), p(gx), 0), 5)
+    feats = torch.randn((B, 512, l1_pts_shape_c), device=dev)
+    gf = torch.empty((B, 128, 64, l1_pts_shape_c), dtype=torch.float32, device=dev)
+    out["group_sa2"] = _ev_time(lambda: ref.ref_group_point(B, 512, l1_pts_shape_c, 128, 64, p(feats), p(q2), p(gf), 0), 5)
+    return {k: round(v, 1) for k, v in out.items()}
+
+
+def _traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu summary (profiles/traffic.json), else None"""
+    pth = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(pth):
+        return None, None
+    with open(pth) as f:
+        d = json.load(f)
+    e = d.get(kernel_key)
+    return (e["bytes"], e["source"]) if e else (None, None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,7 +319,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="batches kept in flight (1 = strictly one step at a time)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the BGA / DGCNN / single-op measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BGA / DGCNN / single-op / sweep measurements")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--train-steps", type=int, default=20)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -162,12 +339,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)      # communicator bound to this rank's GPU up front
     _lib.load()       # fail loudly if the CUDA library is missing
+    solo = world == 1  # the side measurements (per-kernel times, other models, sweep, CPU arm) run on the single-GPU line only
 
     params = pointnet2_cls_ssg.init_params(seed=1, device=dev, randomize_bn=True)
     # input pool larger than L2 (126 MB): 192 distinct batches x 786 KB = 151 MB, rotated every step
@@ -181,57 +359,57 @@ def main():
     pool_dev = pool_host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
-    def forward(x):
-        logits, _ = pointnet2_cls_ssg.get_model(x, False, params=params)
-        return logits
-
     # ---- the public inference API: CUDA graph of one forward per slot, `slots` independent batches in flight ----
     # (step i -> slot i % slots; the next step's FPS -- one CTA per cloud, latency-bound -- overlaps the current step's
     #  tensor-core kernels, which hand their tiles out dynamically)
     from scanobjectnn_b200.engine import pointnet2_cls_ssg_engine
     NSTREAMS = max(1, args.streams)
-    engine = pointnet2_cls_ssg_engine(params, batch=B, npoints=N, num_class=NUM_CLASS, slots=NSTREAMS, device=dev)
-    streams = engine.streams
-
-    def step_resident(i):
-        engine.submit(pool_dev[i % POOL])                   # device-resident batch (rotating pool > L2)
-
-    def step_e2e(i):
-        engine.submit(pool_host[i % POOL], to_host=True)    # pinned host batch in, logits back to pinned host memory
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup):
+    def timed(engine, host, steps, warmup):
+        def step_fn(i):
+            if host:
+                engine.submit(pool_host[i % POOL], to_host=True)    # pinned host batch in, logits back to pinned host memory
+            else:
+                engine.submit(pool_dev[i % POOL])                   # device-resident batch (rotating pool > L2)
         for i in range(warmup):
             step_fn(i)
         barrier()
         main = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
-        for st in streams:
-            st.wait_event(e0)
+        engine.fence_begin(e0)
         for i in range(steps):
             step_fn(warmup + i)
-        for st in streams:
-            main.wait_stream(st)
+        engine.fence_end(main)
         e1.record(main)
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), device=dev)
 
+    engine = pointnet2_cls_ssg_engine(params, batch=B, npoints=N, num_class=NUM_CLASS, slots=NSTREAMS, device=dev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res = timed(step_resident, args.steps, args.warmup)
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_res = timed(engine, False, args.steps, args.warmup)
+    ms_e2e = timed(engine, True, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    ms_res_1 = None
+    if solo and NSTREAMS > 1:
+        engine1 = pointnet2_cls_ssg_engine(params, batch=B, npoints=N, num_class=NUM_CLASS, slots=1, device=dev)
+        n1 = max(args.steps // 4, 8)
+        ms_res_1 = timed(engine1, False, n1, args.warmup) / n1
+        del engine1
+
+    train = run_training_bench(args, dev, rank, world, local_rank)
 
     # ---- per-stage device times (eager launches, CUDA events on the launching stream) ----
-    stages = {}
-    if rank == 0:
-        from scanobjectnn_b200 import tf_util  # noqa: F401
+    stages, ref_gpu, f1 = {}, None, {}
+    if rank == 0 and solo:
+        import ctypes as C
         x = pool_dev[1].contiguous()
         p = params
         mlp1 = p.mlp([f"layer1/conv{i}" for i in range(3)])
@@ -252,34 +430,51 @@ def main():
             "sa2_mlp": lambda: ops.sa_module_infer(l1_xyz, l2_xyz, l1_pts, 0.4, 64, mlp2, idx=idx2),
             "sa3_mlp": lambda: ops.sa_group_all_infer(l2_xyz, l2_pts, mlp3),
             "head": lambda: ops.shared_mlp(l3, head),
-            # variant F1 (training-mode front of SA1): ball query + group + centre + conv1 -> pre-BN (B,m,K,64) + idx + BN stats
-            "sa1_f1": lambda: ops.sa_conv1_prebn(x, l1_xyz, None, 0.2, 32, p["layer1/conv0/weights"].reshape(3, 64),
-                                                 p["layer1/conv0/biases"], want_stats=True),
         }
         flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > L2
         flush_sink = torch.zeros((), dtype=torch.float32, device=dev)
         for name, fn in cases.items():
             for _ in range(3):
                 fn()
-            ts = []
-            for _ in range(10):
-                flush_sink.copy_(flush.sum())       # L2 flush between timed launches by READING 256 MB: the lines left behind are
-                                                    # clean, so a write-heavy kernel is not charged for evicting the flush's dirty data
-                torch.cuda._sleep(400_000)          # ~0.2 ms spin: the host enqueues e0/kernel/e1 before the GPU gets there
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(); e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ts.sort()
-            stages[name] = ts[len(ts) // 2] * 1e3      # median, us
+            stages[name] = _ev_time(fn, 10, flush, flush_sink)
+        # variant F1 (training-mode front of SA1): ball query + group + centre + conv1 -> pre-BN (B,m,K,64) + idx + BN stats.
+        # Timed through the C ABI with preallocated buffers (one ctypes call per launch): (a) isolated, L2 read-flushed in
+        # front; (b) steady state, 50 launches back to back into the same buffers (every byte has to reach HBM).
+        lib = _lib.load()
+        w1 = p["layer1/conv0/weights"].reshape(3, 64).contiguous()
+        b1 = p["layer1/conv0/biases"]
+        pre = torch.empty((B, 512, 32, 64), device=dev)
+        fidx = torch.empty((B, 512, 32), dtype=torch.int32, device=dev)
+        fcnt = torch.empty((B, 512), dtype=torch.int32, device=dev)
+        fstats = torch.empty((2, 64), device=dev)
+        need = lib.psa_sa_conv1_prebn_workspace_bytes(B, N, 512, 0, 64, 1)
+        fws = torch.empty(need // 4 + 1, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+        def f1_launch():
+            rc = lib.psa_sa_conv1_prebn(B, N, 512, 0, C.c_float(0.2), 32, vp(x), vp(l1_xyz), C.c_void_p(0), vp(w1), vp(b1), 64, vp(pre), vp(fidx),
+                                        vp(fcnt), vp(fstats), vp(fws), C.c_size_t(need), st)
+            assert rc == 0, rc
+        for _ in range(3):
+            f1_launch()
+        f1["isolated_us"] = _ev_time(f1_launch, 15, flush, flush_sink)
+        torch.cuda._sleep(2_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            f1_launch()
+        e1.record()
+        torch.cuda.synchronize()
+        f1["steady_us"] = e0.elapsed_time(e1) * 1e3 / 50
+        assert torch.equal(fidx, idx1), "F1 neighbourhoods differ from the ball query's"
         del flush
+        ref_gpu = run_ref_gpu(dev, x, l1_xyz, l2_xyz)
 
     extra = {}
-    if rank == 0 and not args.no_extra:
-        from scanobjectnn_b200 import dgcnn, pointnet2_cls_bga
-
+    if rank == 0 and solo and not args.no_extra:
+        from scanobjectnn_b200 import dgcnn, pointnet2_cls_bga, pointnet_cls
         from scanobjectnn_b200.engine import InferenceEngine
-        from scanobjectnn_b200 import pointnet_cls
 
         pool_dev_full = pool_dev
 
@@ -320,18 +515,15 @@ def main():
         _, l1x = ops.farthest_point_sample_and_gather(512, xq)
         f128 = torch.randn((B, 512, 128), device=dev)
         mlp_e = ops.MlpParams([(torch.randn((128, 64), device=dev) * 0.1, torch.ones(64, device=dev), torch.zeros(64, device=dev), True)])
-        f64_512 = torch.randn((B, 512, 64), device=dev)
         bidx, _ = ops.query_ball_point(0.2, 32, xq, l1x)
-        fidx = ops.farthest_point_sample(512, xq)
+        fidx2 = ops.farthest_point_sample(512, xq)
         nn3_d, nn3_i = ops.three_nn(xq, l1x)
         w3 = torch.full((B, N, 3), 1.0 / 3, device=dev)
         adj = ops.pairwise_distance(xq)
         aug = ops.draw_augmentation(B, N, N, dev)
         opcases = {
             "augment_batch_subset_rotate_jitter": (lambda: ops.augment_batch(xq, N, **aug), None, B * (12 * N + 12 * N + 12 * N) + 4 * N),
-            "farthest_point_sample_2048to512": (lambda: ops.farthest_point_sample(512, xq), None, B * (12 * N + 4 * 512)),
-            "gather_point_512": (lambda: ops.gather_point(xq, fidx), None, B * (12 * N + 4 * 512 + 12 * 512)),
-            "query_ball_point_r0.2_k32": (lambda: ops.query_ball_point(0.2, 32, xq, l1x), None, B * (12 * N + 12 * 512 + 4 * 512 * 32 + 4 * 512)),
+            "gather_point_512": (lambda: ops.gather_point(xq, fidx2), None, B * (12 * N + 4 * 512 + 12 * 512)),
             "group_point_c64_k32": (lambda: ops.group_point(feats64, bidx), None, B * (4 * N * 64 + 4 * 512 * 32 + 4 * 512 * 32 * 64)),
             "knn_point_k32": (lambda: ops.knn_point(32, xq, l1x), None, B * (12 * N + 12 * 512 + 8 * 512 * 32)),
             "three_nn_2048from512": (lambda: ops.three_nn(xq, l1x), None, B * (12 * N + 12 * 512 + 24 * N)),
@@ -350,17 +542,11 @@ def main():
         for name, (fn, flops, nbytes) in opcases.items():
             for _ in range(2):
                 fn()
-            ts = []
-            for _ in range(5):
-                flush_sink.copy_(flush.sum()); torch.cuda._sleep(400_000)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ts.sort()
-            us = ts[len(ts) // 2] * 1e3
+            us = _ev_time(fn, 5, flush, flush_sink)
             extra["ops"][name] = {"us": us, "alg_bytes": nbytes, "gbs": nbytes / (us * 1e-6) / 1e9,
                                   **({"tflops_fp32": flops / (us * 1e-6) / 1e12} if flops else {})}
         del flush
+        extra["fps_ballq_sweep"] = run_sweep(dev, _peaks())
 
     if rank != 0:
         if world > 1:
@@ -371,54 +557,66 @@ def main():
     clouds = B * world * args.steps
     value = clouds / (ms_res * 1e-3)
     e2e_v = clouds / (ms_e2e * 1e-3)
-    # dominant kernel of the step
-    dom = max(stages, key=stages.get)
-    flops = {"sa1_mlp": SA_FLOPS["sa1"], "sa2_mlp": SA_FLOPS["sa2"], "sa3_mlp": SA_FLOPS["sa3"]}.get(dom)
-    if flops:
-        ach = flops / (stages[dom] * 1e-6) / 1e12
-        # share of the level's flops that runs on the tensor cores (layers after the first); each fp32 product is six bf16 MMAs
-        tc_flops = {"sa1_mlp": 2 * 524288 * (64 * 64 + 64 * 128), "sa2_mlp": 2 * 262144 * (128 * 128 + 128 * 256) + 2 * 16384 * 128 * 128,
-                    "sa3_mlp": 2 * 4096 * (256 * 256 + 256 * 512 + 512 * 1024)}[dom]
-        # dram__bytes_read.sum + dram__bytes_write.sum of the level's dominant launch, from profiles/r01_ncu_final2_tensor_kernels.md
-        traffic = {"sa1_mlp": 3.54e6, "sa2_mlp": 10.41e6, "sa3_mlp": 11.59e6}[dom]
-        roofline = {"kernel": dom + " (tc_sa_dual_kernel + its per-source-point first-layer GEMM)" if dom != "sa3_mlp" else dom + " (3 x tc_dense2_kernel)",
-                    "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tf"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 burst",
-                    "algorithmic_flops": flops,
-                    "note": "achieved = SURVEY 8d fp32 MLP flops of the level / measured stage time. fp32 parity (1e-5) is kept by splitting "
-                            "both operands into three bf16 pieces: six bf16 MMAs per product, so the tensor pipe executes 6x the "
-                            "tensor-core share of these flops (tensor_pipe_frac).",
-                    "tensor_pipe_frac": 6.0 * tc_flops / (stages[dom] * 1e-6) / 1e12 / peaks["tf"]}
-    else:
-        fps_bytes = B * (12 * N + 4 * 512)
-        ach = fps_bytes / (stages[dom] * 1e-6) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                    "traffic": None, "peak_source": peaks["src"], "note": "latency-bound dependent arg-max rounds"}
-    # HBM-class kernels of the metric's second half ("FPS+ballq HBM GB/s")
-    kern = {
-        "fps1": {"us": stages["fps1"], "alg_bytes": B * (12 * N + 4 * 512 + 12 * 512), "ns_per_round": stages["fps1"] * 1e3 / 511},
-        "ballq1": {"us": stages["ballq1"], "alg_bytes": B * (12 * N + 12 * 512 + 4 * 512 * 32 + 4 * 512)},
-        "fps2": {"us": stages["fps2"], "alg_bytes": B * (12 * 512 + 4 * 128 + 12 * 128), "ns_per_round": stages["fps2"] * 1e3 / 127},
-        "ballq2": {"us": stages["ballq2"], "alg_bytes": B * (12 * 512 + 12 * 128 + 4 * 128 * 64 + 4 * 128)},
-    }
-    for k, v in kern.items():
-        v["gbs"] = v["alg_bytes"] / (v["us"] * 1e-6) / 1e9
-        v["hbm_frac"] = v["gbs"] / peaks["hbm"]
-    for k in ("sa1_mlp", "sa2_mlp", "sa3_mlp"):
-        kern[k] = {"us": stages[k], "tflops_fp32": SA_FLOPS[k[:3]] / (stages[k] * 1e-6) / 1e12}
-    kern["head"] = {"us": stages["head"]}
-    # F1: B*(12n + 12m) in, 4*B*m*K*C1 (pre-BN) + 4*B*m*K (idx) + 4*B*m (pts_cnt) out  (137.3 MB)
-    f1_bytes = B * (12 * N + 12 * 512) + 4 * B * 512 * 32 * 64 + 4 * B * 512 * 32 + 4 * B * 512
-    f1_gbs = f1_bytes / (stages["sa1_f1"] * 1e-6) / 1e9
-    kern["sa1_f1"] = {"us": stages["sa1_f1"], "alg_bytes": f1_bytes, "gbs": f1_gbs, "hbm_frac": f1_gbs / peaks["hbm"]}
-    roofline_f1 = {"kernel": "sa_conv1_prebn_kernel (variant F1: fused ball-query + group + conv1, pre-BN output, SA1 B=32 N=2048 K=32)",
-                   "bound": "hbm", "achieved": f1_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": f1_gbs / peaks["hbm"],
-                   "traffic": 80.37e6, "traffic_note": "dram read 1.04 MB + write 79.3 MB in the kernel's own window (profiles/r01_ncu_full_v4_fps_ballquery_f1.md); "
-                                                         "the rest of the 137 MB output is still dirty in the 126 MB L2 when the kernel ends",
-                   "peak_source": peaks["src"], "in_timed_step": False}
+    roofline = roofline_f1 = None
+    kern = {}
+    if stages:
+        # dominant kernel of the step
+        dom = max(stages, key=stages.get)
+        flops = {"sa1_mlp": SA_FLOPS["sa1"], "sa2_mlp": SA_FLOPS["sa2"], "sa3_mlp": SA_FLOPS["sa3"]}.get(dom)
+        if flops:
+            ach = flops / (stages[dom] * 1e-6) / 1e12
+            # share of the level's flops that runs on the tensor cores (layers after the first); each fp32 product is six bf16 MMAs
+            tc_flops = {"sa1_mlp": 2 * 524288 * (64 * 64 + 64 * 128), "sa2_mlp": 2 * 262144 * (128 * 128 + 128 * 256) + 2 * 16384 * 128 * 128,
+                        "sa3_mlp": 2 * 4096 * (256 * 256 + 256 * 512 + 512 * 1024)}[dom]
+            traffic, tsrc = _traffic(dom)
+            roofline = {"kernel": dom + " (tc_sa_dual_kernel + its per-source-point first-layer GEMM)" if dom != "sa3_mlp" else dom + " (3 x tc_dense3_kernel)",
+                        "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tf"], "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["src"] + " bf16 burst",
+                        "algorithmic_flops": flops,
+                        "note": "achieved = SURVEY 8d fp32 MLP flops of the level / measured stage time. fp32 parity (1e-5) is kept by splitting "
+                                "both operands into three bf16 pieces: six bf16 MMAs per product, so the tensor pipe executes 6x the "
+                                "tensor-core share of these flops (tensor_pipe_frac).",
+                        "tensor_pipe_frac": 6.0 * tc_flops / (stages[dom] * 1e-6) / 1e12 / peaks["tf"]}
+        else:
+            fps_bytes = B * (12 * N + 4 * 512)
+            ach = fps_bytes / (stages[dom] * 1e-6) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                        "traffic": None, "peak_source": peaks["src"], "note": "latency-bound dependent arg-max rounds"}
+        # HBM-class kernels of the metric's second half ("FPS+ballq HBM GB/s")
+        kern = {
+            "fps1": {"us": stages["fps1"], "alg_bytes": B * (12 * N + 4 * 512 + 12 * 512), "ns_per_round": stages["fps1"] * 1e3 / 511},
+            "ballq1": {"us": stages["ballq1"], "alg_bytes": B * (12 * N + 12 * 512 + 4 * 512 * 32 + 4 * 512)},
+            "fps2": {"us": stages["fps2"], "alg_bytes": B * (12 * 512 + 4 * 128 + 12 * 128), "ns_per_round": stages["fps2"] * 1e3 / 127},
+            "ballq2": {"us": stages["ballq2"], "alg_bytes": B * (12 * 512 + 12 * 128 + 4 * 128 * 64 + 4 * 128)},
+        }
+        for k, v in kern.items():
+            v["gbs"] = v["alg_bytes"] / (v["us"] * 1e-6) / 1e9
+            v["hbm_frac"] = v["gbs"] / peaks["hbm"]
+            if ref_gpu and k in ref_gpu:
+                v["ref_gpu_us"] = ref_gpu[k]          # the reference's own kernel (sm_100a build) on the same tensors
+        for k in ("sa1_mlp", "sa2_mlp", "sa3_mlp"):
+            kern[k] = {"us": stages[k], "tflops_fp32": SA_FLOPS[k[:3]] / (stages[k] * 1e-6) / 1e12}
+        if ref_gpu:
+            kern["sa1_mlp"]["ref_gpu_us_group_point_only"] = ref_gpu["group_sa1"]    # the reference's convs are cuDNN (TF absent):
+            kern["sa2_mlp"]["ref_gpu_us_group_point_only"] = ref_gpu["group_sa2"]    # its grouping alone is a lower bound
+        kern["head"] = {"us": stages["head"]}
+        # F1: B*(12n + 12m) in, 4*B*m*K*C1 (pre-BN) + 4*B*m*K (idx) + 4*B*m (pts_cnt) out  (137.3 MB)
+        f1_bytes = B * (12 * N + 12 * 512) + 4 * B * 512 * 32 * 64 + 4 * B * 512 * 32 + 4 * B * 512
+        gbs_iso = f1_bytes / (f1["isolated_us"] * 1e-6) / 1e9
+        gbs_std = f1_bytes / (f1["steady_us"] * 1e-6) / 1e9
+        kern["sa1_f1"] = {"us": f1["isolated_us"], "steady_us": f1["steady_us"], "alg_bytes": f1_bytes, "gbs": gbs_iso, "hbm_frac": gbs_iso / peaks["hbm"],
+                          "steady_gbs": gbs_std, "steady_hbm_frac": gbs_std / peaks["hbm"]}
+        traffic, tsrc = _traffic("sa1_f1")
+        roofline_f1 = {"kernel": "sa_conv1_stream_kernel (variant F1: fused ball-query + group + conv1, pre-BN output + BN statistics, SA1 B=32 N=2048 K=32)",
+                       "bound": "hbm", "achieved": gbs_iso, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_iso / peaks["hbm"],
+                       "steady_state": {"achieved": gbs_std, "frac": gbs_std / peaks["hbm"],
+                                        "note": "50 launches back to back into the same 137 MB of outputs: every byte reaches HBM inside the window"},
+                       "timing": "CUDA events around one C-ABI call (memset node + kernel), L2 read-flushed (clean lines) and a spin kernel in front; median of 15",
+                       "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["src"],
+                       "in_timed_step": "training step only (train object); the inference step never writes the (B,m,K,C) tensor"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if solo and not args.no_cpu_baseline:
         rate, cores, secs = cpu_forward_rate(B, repeats=3)
         cpu = {"value": rate, "unit": "clouds/s", "cores": cores, "kind": "port",
                "sample": f"the full 32-cloud batch, best of 3 forwards ({secs:.1f} s each): oracle port = C/OpenMP FPS+ball-query+group, numpy fp32 conv/BN/ReLU/max"}
@@ -431,13 +629,16 @@ def main():
                    "l2_policy": "inputs larger than L2: 192 distinct 786 KB batches (151 MB) rotated every step",
                    "mode": "inference (BN moving averages folded); CUDA graph replay of one forward per step",
                    "streams": NSTREAMS, "in_flight": f"{NSTREAMS} independent B=32 steps in flight on {NSTREAMS} streams (step i on stream i % {NSTREAMS})",
-                   "parallelism": f"dp{world} (independent batches, no data-path collective)"},
+                   "parallelism": f"dp{world} (independent batches, no data-path collective; training adds one gradient all-reduce)"},
+        "one_step_at_a_time": None if ms_res_1 is None else {"ms_per_step": ms_res_1, "clouds_per_s": B / (ms_res_1 * 1e-3),
+                                                             "note": "same engine with ONE slot: a step starts when the previous one has finished"},
         "e2e": {"value": e2e_v, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * N * 3 * 4,
                 "d2h_bytes_per_step": B * NUM_CLASS * 4},
         "gpu_launches": 16 * args.steps,
         "roofline": roofline,
         "roofline_f1": roofline_f1,
         "kernels": kern,
+        "train": train,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "other_workloads": extra,

@@ -329,6 +329,12 @@ PSA_API int psa_train_dense_bwd_input(long long rows, int K, int N, const psa_gr
 PSA_API int psa_train_dense_bwd_weight(long long rows, int K, int N, const psa_act_in* in, const psa_grad_in* g,
                                        float* dW, void* workspace, size_t workspace_bytes, psa_stream_t stream);
 
+/* Pooling of (groups*pool_k, C) rows over each run of pool_k rows, the modes of pointnet_sa_module other than the fused max
+ * (pointnet2/utils/pointnet_util.py:126-146): mode 0 max, 1 avg (reduce_mean), 2 weighted_avg with weights
+ * exp(-5 d) / sum exp(-5 d), d = dist (groups*pool_k) = the norm of each row's centred coordinates.  out (groups, C). */
+PSA_API int psa_pool_rows(long long groups, int pool_k, int C, int mode, const float* x, const float* dist, float* out,
+                          psa_stream_t stream);
+
 /* Bias gradient of a layer that is NOT followed by batch norm: db (N) = sum_r dy[r][:].  (Under batch norm the conv / fc bias
  * has an identically zero gradient -- sum_r dy = 0 -- and the training path writes exact zeros there.) */
 PSA_API int psa_train_bias_grad(long long rows, int N, const psa_grad_in* g, float* db, psa_stream_t stream);

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsa.so")
+LIB_PATH = os.environ.get("PSA_LIB_PATH") or os.path.join(_HERE, "libpsa.so")   # PSA_LIB_PATH: instrumented builds of tools/
 
 PSA_MAX_MLP_LAYERS = 4
 
@@ -89,6 +89,7 @@ SIGNATURES = {
     "psa_bn_bwd_coeffs": [_ll, _i, _gin, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "psa_sa_conv1_bwd": [_i, _i, _i, _i, _i, _p, _p, _p, _gin, _p, _p, _p, _sz, _p],
     "psa_softmax_xent": [_i, _i, _p, _p, _p, _p, _p],
+    "psa_pool_rows": [_ll, _i, _i, _i, _p, _p, _p, _p],
     "psa_adam_step": [_ll, _p, _p, _p, _p, _f, _f, _f, _f, _i, _f, _p],
 }
 INFO_SYMBOLS = ("psa_version", "psa_last_error", "psa_sm_arch", "psa_shared_mlp_workspace_bytes",

@@ -8,6 +8,9 @@
 //   provider.py:215-227    random_scale_point_cloud, shift_point_cloud (per cloud)
 //   provider.py:189-200    jitter_point_cloud     p + clip(sigma * randn, -clip, clip)   (float64 sum, fed as float32)
 //   provider.py:229-236    random_point_dropout   dropped points := point 0
+// Order inside the kernel: dropout substitution -> rotate -> scale -> shift -> jitter.  rotate -> jitter is the composition the
+// training scripts run (pointnet2/train.py:246-252); the order of the optional scale / shift / dropout relative to the jitter is
+// this kernel's own (the reference composes them only in commented-out code, dgcnn/train.py:274-278, jitter first).
 // Here: one CTA per cloud, pass 1 (optional) reduces the centroid and the max norm over the source cloud, pass 2
 // gathers the subset and applies the chain in the reference's order and precisions, writing the (b,n,3) batch the
 // first FPS reads.  Random numbers are INPUTS (permutation, angles as cos/sin in double, scales, shifts, standard

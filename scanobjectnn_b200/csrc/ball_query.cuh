@@ -41,6 +41,7 @@ struct BqSmem {
     int* cell_end;                      // grid mode: kBqMaxCells + 32 ints: end offset of each cell, scratch
     int* hits;                          // grid mode: kBqWarps * bq_warp_scratch_words(n)
     const float* gxyz;                  // the cloud in global memory (AoS), always valid
+    unsigned short* pos_of;             // optional (grid mode): pos_of[k] = slot of point k in `sorted`; null = not kept
 };
 
 constexpr int kBqSlabQueries = 8;      // queries a warp searches at a time on the lane-per-slab path (3 lanes each)
@@ -59,6 +60,7 @@ __host__ __device__ inline bool bq_grid_fits(int n) { return n <= kBqGridMaxN; }
 __device__ __forceinline__ BqSmem bq_carve(float* base, int n, bool grid, const float* gxyz) {
     BqSmem s;
     s.gxyz = gxyz;
+    s.pos_of = nullptr;
     if (grid) {
         s.sx = s.sy = s.sz = nullptr;
         s.sorted = reinterpret_cast<float4*>(base);
@@ -203,6 +205,7 @@ __device__ __forceinline__ BqGrid bq_stage_and_build(const BqSmem& s, int n, flo
         if (k < n) {
             const int pos = atomicAdd(&s.cell_end[cell[i]], 1);      // afterwards cell_end[c] = END of cell c
             s.sorted[pos] = make_float4(px[i], py[i], pz[i], __int_as_float(k));
+            if (s.pos_of != nullptr) s.pos_of[k] = (unsigned short)pos;
         }
     }
     __syncthreads();
@@ -424,6 +427,48 @@ __device__ __forceinline__ int bq_extract_bitmap(unsigned* __restrict__ bitmap, 
     }
     const int cnt = min(total, nsample);
     for (int l = cnt + lane; l < nsample; l += 32) idxrow[l] = first;
+    return cnt;
+}
+
+// Eight lanes per query, four queries per warp at once: the nsample lowest set bits of a bitmap of `words` words (a multiple
+// of 8; lane `sub` of the group owns words [sub*words/8, (sub+1)*words/8)) in ascending order -> idxrow[0..cnt), rest filled
+// with the first hit (0 if none).  Every lane of the warp must call (shuffles); groups with active == false do nothing else.
+__device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict__ bitmap, int words, int nsample, int* __restrict__ idxrow,
+                                                      int lane, bool active) {
+    const int sub = lane & 7;
+    const int wps = words >> 3;                      // words per lane: 4 (n <= 1024), 8 (n <= 2048), 16 (n <= 4096)
+    int c = 0;
+    if (active)
+        for (int i = 0; i < wps; ++i) c += __popc(bitmap[sub * wps + i]);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o, 8);
+        if (sub >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 7, 8);
+    const unsigned have = (__ballot_sync(0xffffffffu, c > 0) >> (lane & 24)) & 0xffu;
+    int firstbit = 0;
+    if (active && c > 0) {
+        for (int i = wps - 1; i >= 0; --i) {
+            const unsigned w = bitmap[sub * wps + i];
+            if (w != 0u) firstbit = (sub * wps + i) * 32 + __ffs(w) - 1;
+        }
+    }
+    const int first = __shfl_sync(0xffffffffu, firstbit, have ? __ffs(have) - 1 : 0, 8);
+    if (!active) return 0;
+    int pos = incl - c;
+    for (int i = 0; i < wps && pos < nsample; ++i) {
+        unsigned x = bitmap[sub * wps + i];
+        while (x != 0u && pos < nsample) {
+            const int bit = __ffs(x) - 1;
+            x &= x - 1u;
+            idxrow[pos++] = (sub * wps + i) * 32 + bit;
+        }
+    }
+    const int cnt = min(total, nsample);
+    const int fillv = have ? first : 0;
+    for (int l = cnt + sub; l < nsample; l += 8) idxrow[l] = fillv;
     return cnt;
 }
 

@@ -11,6 +11,8 @@
 // C1=64) -- a pure write-bound kernel, the one BASELINE.json's ">= 70 % of the HBM roofline" target is defined on.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "ball_query.cuh"
 #include "common.cuh"
 
@@ -140,27 +142,34 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
 // ---------------------------------------------------------------------------------------------------------------------
 // Streaming F1 kernel (round 2): the same front as above, organised so that the only thing the SMs do for most of the
 // launch is stream the (B,m,K,C1) tensor out.
-//   * persistent CTAs (2 per SM), each owning an equal contiguous range of the B*m queries (ranges may cross clouds; the
-//     grid of a cloud is rebuilt at a crossing);
-//   * warp 0 = PRODUCER: lane-per-slab grid search into per-query bitmaps (ball_query.cuh), bitmap -> ordered idx rows,
-//     idx/pts_cnt to global memory, and the centred neighbour coordinates (dx,dy,dz,j) of every row of the batch into a
-//     shared-memory ring slot -- ~150 warp instructions per query instead of ~600;
-//   * warps 1..7 = CONSUMERS: per step 4 rows x C1 channels -- one LDS.128 for the row's (dx,dy,dz,j), 6 FFMA2 per 4
+//   * persistent CTAs (2 per SM), each owning an equal contiguous range of the B*m queries (ranges may cross clouds);
+//   * warps 0..NP-1 = PRODUCERS.  No spatial grid: at these sizes (n <= 4096, ~100 queries per CTA) an exhaustive test
+//     out of REGISTERS is cheaper than building one -- a producer thread keeps PPTP points of the cloud in registers, and
+//     for every query of a batch tests them on the packed f32x2 pipe (same arithmetic as the reference, NaN counts as
+//     inside); lane l of a warp owns point 32*w + l of each 32-point word, so one ballot per word IS that word of the
+//     query's hit bitmap -- no atomics, no compaction.  The nsample lowest set bits are the reference's "first nsample in
+//     index order" (8 lanes per query read them out with popcount prefix sums), then idx / pts_cnt go to global memory
+//     and the centred coordinates (dx,dy,dz,j) of every row of the batch into a shared-memory ring slot;
+//   * the other warps = CONSUMERS: per step 4 rows x C1 channels -- one LDS.128 for the row's (dx,dy,dz,j), 6 FFMA2 per 4
 //     channels with the weights resident in registers, 128-byte streaming stores, BN statistics in registers;
 //   * ring of kF1Ring batches of kF1Batch queries, named barriers FULL/EMPTY per slot: the search of batch t+2 runs
-//     under the stores of batch t.
-// Statistics: per-CTA partials in a fixed order, the last CTA to finish (atomic ticket) adds them in fp64 in CTA order:
-// deterministic, one launch (+ a 4-byte memset node for the ticket).
+//     under the stores of batch t.  No CTA-wide barrier inside the main loop.
+// Statistics: per-CTA partials in a fixed order, the last CTA to finish (ticket) adds them in fp64 in CTA order:
+// deterministic, one launch.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kF1SThreads = 256;
-constexpr int kF1SConsWarps = 7;
 constexpr int kF1Batch = 8;
 constexpr int kF1Ring = 3;
+constexpr int kF1Tickets = 64;
+
+// completion tickets of the statistics reduction: zero at load, reset by the last CTA of every launch; a launch uses
+// ticket (call number mod 64), so up to 64 launches may be in flight at once (different streams / CUDA graphs)
+__device__ unsigned g_f1_tickets[kF1Tickets];
 
 struct F1SArgs {
     int b, n, m, nsample, C1;
-    float radius, thr;
-    int none, want_grid;
+    float thr;
+    int none;
     const float* xyz;
     const float* new_xyz;
     const float* uf;
@@ -170,40 +179,43 @@ struct F1SArgs {
     int* idx;
     int* pts_cnt;
     float* partial;        // (gridDim.x, 2, C1)
-    float* stats;          // (2, C1)
-    unsigned* ticket;      // zeroed by the launcher
+    float* stats;          // (2, C1) or null
+    int ticket;            // index into g_f1_tickets
+    unsigned long long* tlog;   // PSA_F1_TIMING builds: (gridDim.x, 8) globaltimer stamps, else null
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-__host__ __device__ inline size_t f1s_slot_bytes(int nsample) { return (size_t)kF1Batch * nsample * (sizeof(int) + sizeof(float4)); }
-// grid mode: cell-sorted cloud + cell table + ONE warp's bitmaps (the producer's; ball_query.cuh lays a per-warp scratch
-// area out right behind the cell table); scan mode: the SoA copy
-__host__ __device__ inline size_t f1s_bq_bytes(int n, bool grid) {
-    const size_t b = grid ? (size_t)n * 16 + (size_t)(kBqMaxCells + 32) * 4 + (size_t)bq_warp_scratch_words(n) * 4 : bq_smem_bytes(n, false);
-    return (b + 15) & ~(size_t)15;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
-__host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, bool grid) { return f1s_bq_bytes(n, grid) + kF1Ring * f1s_slot_bytes(nsample); }
 
-template <int NV, bool STATS, bool HAS_U, int PPT>
+// shared memory: cloud as float4 (x,y,z,bits(k)) | kF1Batch bitmaps of bw words | ring slots (idx rows | centred rows)
+__host__ __device__ inline int f1s_bitmap_words(int np, int pptp) { const int w = np * pptp; return w < 32 ? 32 : w; }
+__host__ __device__ inline size_t f1s_slot_bytes(int nsample) { return (size_t)kF1Batch * nsample * (sizeof(int) + sizeof(float4)); }
+__host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, int np, int pptp) {
+    return (size_t)n * 16 + (size_t)kF1Batch * f1s_bitmap_words(np, pptp) * 4 + kF1Ring * f1s_slot_bytes(nsample);
+}
+
+template <int NV, bool HAS_U, int NP, int PPTP>
 __global__ void __launch_bounds__(kF1SThreads, 2)
 sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
+    constexpr int NC = kF1SThreads / 32 - NP;              // consumer warps
+    constexpr int PT = NP * 32;                            // producer threads
+    constexpr int BW = NP * PPTP < 32 ? 32 : NP * PPTP;    // bitmap words per query
     extern __shared__ __align__(16) float smem_f[];
     const int n = a.n, K = a.nsample, C1 = a.C1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool want_grid = a.want_grid != 0;
-    uint8_t* sm = reinterpret_cast<uint8_t*>(smem_f);
-    const size_t bq_bytes = f1s_bq_bytes(n, want_grid);
-    const int wpl = bq_bitmap_words_per_lane(n);
-    unsigned* bitmaps = reinterpret_cast<unsigned*>(bq_carve(smem_f, n, want_grid, nullptr).hits);   // kF1Batch x (32*wpl) words (grid mode)
-    uint8_t* ring = sm + bq_bytes;
+    float4* cloud4 = reinterpret_cast<float4*>(smem_f);
+    unsigned* bitmaps = reinterpret_cast<unsigned*>(cloud4 + n);                                  // kF1Batch x BW
+    uint8_t* ring = reinterpret_cast<uint8_t*>(bitmaps + kF1Batch * BW);
     const size_t slot_bytes = f1s_slot_bytes(K);
-    static_assert(kF1Batch == kBqSlabQueries, "the producer's bitmaps are one warp's scratch area");
-    if (want_grid)
-        for (int i = tid; i < kF1Batch * 32 * wpl; i += kF1SThreads) bitmaps[i] = 0u;
+#ifdef PSA_F1_TIMING
+    if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 0] = gtime();
+#endif
 
-    // ---- consumer registers: lane-in-row `sub` owns channels [32 i + 4 sub, +4), i < NV ----
     const int sub = lane & 7, rsub = lane >> 3;
     constexpr int NPK = 2 * NV;
     float2 ssum[NPK], ssq[NPK];
@@ -220,88 +232,121 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         total_batches += (int)((seg_end - q + kF1Batch - 1) / kF1Batch);
         q = seg_end;
     }
-    int ring_pos = 0;
 
-    for (long long q = q_begin; q < q_end;) {
-        const long long cloud = q / a.m;
-        const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-        const int nseg = (int)(seg_end - q);
-        const int nb = (nseg + kF1Batch - 1) / kF1Batch;
-        const float* gx = a.xyz + (size_t)cloud * n * 3;
-        __syncthreads();                                   // the previous cloud's grid is no longer read
-        const BqSmem s = bq_carve(smem_f, n, want_grid, gx);
-        const BqGrid g = bq_stage_and_build<PPT>(s, n, a.radius, want_grid);
-
-        if (warp == 0) {
-            // =========================== PRODUCER ===========================
+    if (warp < NP) {
+        // =========================================== PRODUCERS ===========================================
+        for (int i = tid; i < kF1Batch * BW; i += PT) bitmaps[i] = 0u;       // words no warp owns (BW > NP*PPTP) stay zero
+        int ring_pos = 0;
+        for (long long q = q_begin; q < q_end;) {
+            const long long cloud = q / a.m;
+            const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
+            const int nb = (int)((seg_end - q + kF1Batch - 1) / kF1Batch);
+            const float* gx = a.xyz + (size_t)cloud * n * 3;
+            // ---- this cloud: PPTP points per thread in registers (point k = 32*(warp + NP*i) + lane), float4 copy in smem ----
+            named_bar_sync(15, PT);                                          // the previous cloud's float4 copy is no longer read
+            float2 px[PPTP / 2], py[PPTP / 2], pz[PPTP / 2];
+            unsigned valid = 0u;
+#pragma unroll
+            for (int i = 0; i < PPTP; ++i) {
+                const int k = 32 * (warp + NP * i) + lane;
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (k < n) {
+                    x = __ldg(gx + 3 * k); y = __ldg(gx + 3 * k + 1); z = __ldg(gx + 3 * k + 2);
+                    cloud4[k] = make_float4(x, y, z, __int_as_float(k));
+                    valid |= 1u << i;
+                }
+                if (i & 1) { px[i >> 1].y = x; py[i >> 1].y = y; pz[i >> 1].y = z; }
+                else { px[i >> 1].x = x; py[i >> 1].x = y; pz[i >> 1].x = z; }
+            }
+            named_bar_sync(15, PT);
+#ifdef PSA_F1_TIMING
+            if (tid == 0 && a.tlog && q == q_begin) a.tlog[blockIdx.x * 8 + 1] = gtime();
+#endif
             for (int bi = 0; bi < nb; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
-                if (ring_pos >= kF1Ring) named_bar_sync(1 + kF1Ring + slot, kF1SThreads);      // slot drained by the consumers
+                if (ring_pos >= kF1Ring) named_bar_sync(1 + kF1Ring + slot, kF1SThreads);   // slot drained by the consumers
                 int* sidx = reinterpret_cast<int*>(ring + slot * slot_bytes);
                 float4* sd = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
                 const long long gq0 = q + (long long)bi * kF1Batch;                        // global query id of the batch
                 const int nqb = min(kF1Batch, (int)(seg_end - gq0));
-                // lane 3*i + t: query i of the batch, z-slab t
-                const int qi = lane / kBqSlabLanes, tsl = lane - qi * kBqSlabLanes;
-                const bool act = qi < nqb;
-                float qx = 0.f, qy = 0.f, qz = 0.f;
-                if (act) {
-                    const float* p2 = a.new_xyz + (size_t)(gq0 + qi) * 3;
-                    qx = __ldg(p2); qy = __ldg(p2 + 1); qz = __ldg(p2 + 2);
-                }
-                const bool qfin = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;
-                const bool fast = g.use && !a.none;
-                if (fast && act && qfin) bq_search_slab(s, g, a.thr, qx, qy, qz, tsl, bitmaps + (size_t)qi * 32 * wpl);
-                __syncwarp();
-                for (int i = 0; i < nqb; ++i) {
-                    const float cx = __shfl_sync(0xffffffffu, qx, i * kBqSlabLanes), cy = __shfl_sync(0xffffffffu, qy, i * kBqSlabLanes);
-                    const float cz = __shfl_sync(0xffffffffu, qz, i * kBqSlabLanes);
-                    const bool fin_i = __shfl_sync(0xffffffffu, qfin ? 1 : 0, i * kBqSlabLanes) != 0;
-                    int* row = sidx + i * K;
-                    int cnt;
-                    if (fast && fin_i) cnt = bq_extract_bitmap(bitmaps + (size_t)i * 32 * wpl, wpl, K, row, lane);
-                    else cnt = bq_scan_warp(n, K, a.thr, a.none != 0, s, cx, cy, cz, row, lane);
-                    __syncwarp();
-                    if (a.pts_cnt != nullptr && lane == 0) a.pts_cnt[gq0 + i] = cnt;
-                    // grouped_xyz - new_xyz (pointnet_util.py:46) of the query's K rows, + the source index for the U gather
-                    int* gidx = a.idx + (size_t)(gq0 + i) * K;
-                    for (int l = lane; l < K; l += 32) {
-                        const int j = row[l];
-                        gidx[l] = j;
-                        const float px = __ldg(gx + 3 * j), py = __ldg(gx + 3 * j + 1), pz = __ldg(gx + 3 * j + 2);
-                        sd[i * K + l] = make_float4(px - cx, py - cy, pz - cz, __int_as_float(j));
+                // ---- exhaustive test: one ballot per 32-point word = that word of the query's bitmap ----
+                if (!a.none) {
+                    for (int qi = 0; qi < nqb; ++qi) {
+                        const float* p2 = a.new_xyz + (size_t)(gq0 + qi) * 3;
+                        const float qx = __ldg(p2), qy = __ldg(p2 + 1), qz = __ldg(p2 + 2);
+                        const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+                        unsigned* bm = bitmaps + qi * BW;
+#pragma unroll
+                        for (int i = 0; i < PPTP; i += 2) {
+                            const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
+                            // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
+                            const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr) && ((valid >> i) & 1u));
+                            const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr) && ((valid >> (i + 1)) & 1u));
+                            if (lane == 0) { bm[warp + NP * i] = w0; bm[warp + NP * (i + 1)] = w1; }
+                        }
                     }
+                }
+                named_bar_sync(15, PT);                                                     // bitmaps complete
+                // ---- bitmaps -> ordered idx rows: 8 lanes per query, 4 queries per warp pass ----
+                for (int q0 = warp * 4; q0 < kF1Batch; q0 += NP * 4) {
+                    const int qi = q0 + (lane >> 3);
+                    const bool act = qi < nqb;
+                    const int cnt = bq_extract_bitmap_sub8(bitmaps + qi * BW, BW, K, sidx + qi * K, lane, act);
+                    if (act && a.pts_cnt != nullptr && (lane & 7) == 0) a.pts_cnt[gq0 + qi] = cnt;
+                }
+                named_bar_sync(15, PT);                                                     // idx rows complete
+                // ---- grouped_xyz - new_xyz (pointnet_util.py:46) of the batch's rows + the source index for the U gather ----
+                const int nrows = nqb * K;
+                int* gidx = a.idx + (size_t)gq0 * K;
+                for (int r = tid; r < nrows; r += PT) {
+                    const int j = sidx[r];
+                    const float* p2 = a.new_xyz + (size_t)(gq0 + r / K) * 3;
+                    const float4 pt = cloud4[j];
+                    gidx[r] = j;
+                    sd[r] = make_float4(pt.x - __ldg(p2), pt.y - __ldg(p2 + 1), pt.z - __ldg(p2 + 2), __int_as_float(j));
                 }
                 __threadfence_block();
                 named_bar_arrive(1 + slot, kF1SThreads);                                    // FULL
+#ifdef PSA_F1_TIMING
+                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 2] = gtime();
+#endif
             }
-        } else {
-            // =========================== CONSUMERS ===========================
-            const int cw = warp - 1;
-            // first-layer weights of this lane's channels, resident in registers (loaded after the grid build: the build
-            // keeps the thread's points in registers)
-            float2 wx[NPK], wy[NPK], wz[NPK], bs[NPK];
+            q = seg_end;
+        }
+#ifdef PSA_F1_TIMING
+        if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 3] = gtime();
+#endif
+    } else {
+        // =========================================== CONSUMERS ===========================================
+        const int cw = warp - NP;
+        // first-layer weights of this lane's channels, resident in registers: lane-in-row `sub` owns channels [32 i + 4 sub, +4)
+        float2 wx[NPK], wy[NPK], wz[NPK], bs[NPK];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = 32 * i + 4 * sub;
-                const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.w1 + c));
-                const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + c));
-                const float4 z4 = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * C1 + c));
-                const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                wx[2 * i] = make_float2(x4.x, x4.y); wx[2 * i + 1] = make_float2(x4.z, x4.w);
-                wy[2 * i] = make_float2(y4.x, y4.y); wy[2 * i + 1] = make_float2(y4.z, y4.w);
-                wz[2 * i] = make_float2(z4.x, z4.y); wz[2 * i + 1] = make_float2(z4.z, z4.w);
-                bs[2 * i] = make_float2(b4.x, b4.y); bs[2 * i + 1] = make_float2(b4.z, b4.w);
-            }
+        for (int i = 0; i < NV; ++i) {
+            const int c = 32 * i + 4 * sub;
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.w1 + c));
+            const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + c));
+            const float4 z4 = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * C1 + c));
+            const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wx[2 * i] = make_float2(x4.x, x4.y); wx[2 * i + 1] = make_float2(x4.z, x4.w);
+            wy[2 * i] = make_float2(y4.x, y4.y); wy[2 * i + 1] = make_float2(y4.z, y4.w);
+            wz[2 * i] = make_float2(z4.x, z4.y); wz[2 * i + 1] = make_float2(z4.z, z4.w);
+            bs[2 * i] = make_float2(b4.x, b4.y); bs[2 * i + 1] = make_float2(b4.z, b4.w);
+        }
+        int ring_pos = 0;
+        for (long long q = q_begin; q < q_end;) {
+            const long long cloud = q / a.m;
+            const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
+            const int nb = (int)((seg_end - q + kF1Batch - 1) / kF1Batch);
+            const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + 4 * sub : nullptr;
             for (int bi = 0; bi < nb; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
                 const float4* sd = reinterpret_cast<const float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
                 const long long gq0 = q + (long long)bi * kF1Batch;
                 const int nrows = min(kF1Batch, (int)(seg_end - gq0)) * K;
                 float* outl = a.pre + (size_t)gq0 * K * C1 + 4 * sub;
-                const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + 4 * sub : nullptr;
                 named_bar_sync(1 + slot, kF1SThreads);                                      // FULL
-                for (int r = 4 * cw + rsub; r < nrows; r += 4 * kF1SConsWarps) {
+                for (int r = 4 * cw + rsub; r < nrows; r += 4 * NC) {
                     const float4 d = sd[r];
                     const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
                     float* orow = outl + (unsigned)r * (unsigned)C1;
@@ -316,21 +361,22 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                         const float2 v0 = __ffma2_rn(dz, wz[2 * i], __ffma2_rn(dy, wy[2 * i], __ffma2_rn(dx, wx[2 * i], s0)));
                         const float2 v1 = __ffma2_rn(dz, wz[2 * i + 1], __ffma2_rn(dy, wy[2 * i + 1], __ffma2_rn(dx, wx[2 * i + 1], s1)));
                         __stcs(reinterpret_cast<float4*>(orow + 32 * i), make_float4(v0.x, v0.y, v1.x, v1.y));
-                        if (STATS) {
-                            ssum[2 * i] = __fadd2_rn(ssum[2 * i], v0); ssum[2 * i + 1] = __fadd2_rn(ssum[2 * i + 1], v1);
-                            ssq[2 * i] = __ffma2_rn(v0, v0, ssq[2 * i]); ssq[2 * i + 1] = __ffma2_rn(v1, v1, ssq[2 * i + 1]);
-                        }
+                        ssum[2 * i] = __fadd2_rn(ssum[2 * i], v0); ssum[2 * i + 1] = __fadd2_rn(ssum[2 * i + 1], v1);
+                        ssq[2 * i] = __ffma2_rn(v0, v0, ssq[2 * i]); ssq[2 * i + 1] = __ffma2_rn(v1, v1, ssq[2 * i + 1]);
                     }
                 }
                 if (ring_pos + kF1Ring < total_batches) named_bar_arrive(1 + kF1Ring + slot, kF1SThreads);   // EMPTY
             }
+            q = seg_end;
         }
-        q = seg_end;
+#ifdef PSA_F1_TIMING
+        if (tid == NP * 32 && a.tlog) a.tlog[blockIdx.x * 8 + 5] = gtime();
+#endif
     }
 
-    if (STATS) {
+    if (a.stats != nullptr) {
         __syncthreads();                                   // ring memory is free: reuse it for the per-warp partials
-        float* sstat = reinterpret_cast<float*>(ring);     // kF1SConsWarps x 2 x C1
+        float* sstat = reinterpret_cast<float*>(ring);     // NC x 2 x C1
 #pragma unroll
         for (int p = 0; p < NPK; ++p) {
 #pragma unroll
@@ -338,8 +384,8 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                 ssum[p].x += __shfl_xor_sync(0xffffffffu, ssum[p].x, o); ssum[p].y += __shfl_xor_sync(0xffffffffu, ssum[p].y, o);
                 ssq[p].x += __shfl_xor_sync(0xffffffffu, ssq[p].x, o); ssq[p].y += __shfl_xor_sync(0xffffffffu, ssq[p].y, o);
             }
-            if (warp > 0 && rsub == 0) {
-                float* w = sstat + (size_t)(warp - 1) * 2 * C1;
+            if (warp >= NP && rsub == 0) {
+                float* w = sstat + (size_t)(warp - NP) * 2 * C1;
                 const int c = 32 * (p >> 1) + 4 * sub + 2 * (p & 1);
                 *reinterpret_cast<float2*>(w + c) = ssum[p];
                 *reinterpret_cast<float2*>(w + C1 + c) = ssq[p];
@@ -350,24 +396,49 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         for (int e = tid; e < 2 * C1; e += kF1SThreads) {
             float t = 0.f;
 #pragma unroll
-            for (int w = 0; w < kF1SConsWarps; ++w) t += sstat[(size_t)w * 2 * C1 + e];      // fixed order
+            for (int w = 0; w < NC; ++w) t += sstat[(size_t)w * 2 * C1 + e];      // fixed order
             dst[e] = t;
         }
-        // last CTA to arrive adds the CTA partials in CTA order (fp64): deterministic whatever the finishing order
+        // last CTA to arrive adds the CTA partials (fp64) in a fixed tree: deterministic whatever the finishing order
         __shared__ unsigned s_last;
+        __shared__ double s_half[kF1SThreads];
         __threadfence();
         __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (tid == 0) s_last = (atomicAdd(&g_f1_tickets[a.ticket], 1u) == gridDim.x - 1) ? 1u : 0u;
         __syncthreads();
         if (s_last) {
             __threadfence();
-            for (int e = tid; e < 2 * C1; e += kF1SThreads) {
-                double t = 0.0;
-                for (unsigned p = 0; p < gridDim.x; ++p) t += (double)__ldcg(a.partial + (size_t)p * 2 * C1 + e);
-                a.stats[e] = (float)t;
+            // thread (h, e): partials p = h, h + H, ... of value e, four independent accumulators; then the H halves in order
+            const int E = 2 * C1;
+            const int H = kF1SThreads / E > 0 ? kF1SThreads / E : 1;      // 2 (C1 = 64) or 1 (C1 = 128)
+            for (int e0 = 0; e0 < E; e0 += kF1SThreads / H) {
+                const int e = e0 + tid % (kF1SThreads / H), h = tid / (kF1SThreads / H);
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                if (e < E) {
+                    unsigned p = h;
+                    for (; p + 3 * H < gridDim.x; p += 4 * H) {
+                        t0 += (double)__ldcg(a.partial + (size_t)p * E + e);
+                        t1 += (double)__ldcg(a.partial + (size_t)(p + H) * E + e);
+                        t2 += (double)__ldcg(a.partial + (size_t)(p + 2 * H) * E + e);
+                        t3 += (double)__ldcg(a.partial + (size_t)(p + 3 * H) * E + e);
+                    }
+                    for (; p < gridDim.x; p += H) t0 += (double)__ldcg(a.partial + (size_t)p * E + e);
+                }
+                s_half[tid] = (t0 + t1) + (t2 + t3);
+                __syncthreads();
+                if (h == 0 && e < E) {
+                    double t = 0.0;
+                    for (int hh = 0; hh < H; ++hh) t += s_half[hh * (kF1SThreads / H) + tid];
+                    a.stats[e] = (float)t;
+                }
+                __syncthreads();
             }
+            if (tid == 0) g_f1_tickets[a.ticket] = 0u;     // ready for the next launch that draws this ticket
         }
     }
+#ifdef PSA_F1_TIMING
+    if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 6] = gtime();
+#endif
 }
 
 // stats[0..C1) = sum, stats[C1..2C1) = sum of squares, over all rows; CTA partials added in index order in fp64
@@ -409,15 +480,17 @@ static void f1_grid(int b, int m, int* q_per_cta, dim3* grid) {
 
 using namespace psa;
 
-// streaming kernel: grid, shared memory, applicability
-static bool f1s_plan(int b, int n, int m, int nsample, bool want_grid, int* ctas, size_t* smem) {
-    if (n > (want_grid ? kBqGridMaxN : 8192) || nsample > 128) return false;
-    *smem = f1s_smem_bytes(n, nsample, want_grid);
-    if (*smem > 200 * 1024) return false;
+// streaming kernel: producer layout (NP warps x PPTP points per thread), grid, shared memory, applicability
+static bool f1s_plan(int b, int n, int m, int nsample, int* np, int* pptp, int* ctas, size_t* smem) {
+    if (n > 4096 || nsample > 128) return false;
+    // 32 * np * pptp >= n; at most 16 points per thread up to n = 2048 (48 registers of coordinates next to the consumers' weights)
+    *np = n <= 1024 ? 2 : 4;
+    *pptp = n <= 512 ? 8 : (n <= 2048 ? 16 : 32);
+    *smem = f1s_smem_bytes(n, nsample, *np, *pptp);
+    if (*smem > 110 * 1024) return false;
     const long long T = (long long)b * m;
     const long long batches = (T + kF1Batch - 1) / kF1Batch;
-    const int per_sm = (*smem <= 110 * 1024) ? 2 : 1;
-    *ctas = (int)(batches < (long long)per_sm * kNumSMs ? batches : (long long)per_sm * kNumSMs);
+    *ctas = (int)(batches < 2LL * kNumSMs ? batches : 2LL * kNumSMs);
     return true;
 }
 static bool f1_want_grid(int n, int m) { return bq_grid_fits(n) && n >= 256 && m >= 32; }
@@ -430,7 +503,7 @@ extern "C" size_t psa_sa_conv1_prebn_workspace_bytes(int b, int n, int m, int c,
         f1_grid(b, m, &q, &g);
         size_t parts = (size_t)g.x * g.y;
         if (parts < 2 * (size_t)kNumSMs) parts = 2 * (size_t)kNumSMs;
-        bytes += parts * 2 * C1 * sizeof(float) + 256;          // CTA partials + the completion ticket
+        bytes += parts * 2 * C1 * sizeof(float) + 256 + 2 * (size_t)kNumSMs * 8 * sizeof(unsigned long long);   // CTA partials (+ timing stamps of debug builds)
     }
     return bytes;
 }
@@ -463,28 +536,36 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
         ws += ((size_t)b * n * C1 * sizeof(float) + 255) & ~(size_t)255;
     }
     {   // ---- streaming kernel (persistent CTAs, producer/consumer warps) whenever the cloud fits its shared-memory plan ----
-        int ctas = 0;
+        int ctas = 0, np = 0, pptp = 0;
         size_t ssm = 0;
-        if (f1_variant() != 1 && f1s_plan(b, n, m, nsample, a.want_grid != 0, &ctas, &ssm)) {
+        if (f1_variant() != 1 && f1s_plan(b, n, m, nsample, &np, &pptp, &ctas, &ssm)) {
             F1SArgs s;
-            s.b = b; s.n = n; s.m = m; s.nsample = nsample; s.C1 = C1; s.radius = radius; s.thr = a.thr; s.none = a.none;
-            s.want_grid = a.want_grid; s.xyz = xyz; s.new_xyz = new_xyz; s.uf = a.uf; s.w1 = w1; s.bias = bias; s.pre = pre;
-            s.idx = idx; s.pts_cnt = pts_cnt; s.partial = nullptr; s.stats = stats; s.ticket = nullptr;
+            s.b = b; s.n = n; s.m = m; s.nsample = nsample; s.C1 = C1; s.thr = a.thr; s.none = a.none;
+            s.xyz = xyz; s.new_xyz = new_xyz; s.uf = a.uf; s.w1 = w1; s.bias = bias; s.pre = pre;
+            s.idx = idx; s.pts_cnt = pts_cnt; s.partial = nullptr; s.stats = stats; s.ticket = 0; s.tlog = nullptr;
             if (stats) {
-                s.ticket = reinterpret_cast<unsigned*>(ws);
+                static std::atomic<unsigned> call_no{0};
+                s.ticket = (int)(call_no.fetch_add(1u) % kF1Tickets);
                 s.partial = reinterpret_cast<float*>(ws + 256);
-                PSA_CUDA(cudaMemsetAsync(s.ticket, 0, sizeof(unsigned), st));
+#ifdef PSA_F1_TIMING
+                s.tlog = reinterpret_cast<unsigned long long*>(ws + 256 + (size_t)2 * kNumSMs * 2 * C1 * sizeof(float));
+#endif
             }
-#define PSA_F1S_LAUNCH(NV_, ST_, U_, PPT_)                                                                                    \
+#define PSA_F1S_LAUNCH(NV_, U_, NP_, PP_)                                                                                     \
     do {                                                                                                                     \
-        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_stream_kernel<NV_, ST_, U_, PPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm)); \
-        sa_conv1_stream_kernel<NV_, ST_, U_, PPT_><<<ctas, kF1SThreads, ssm, st>>>(s);                                       \
+        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_stream_kernel<NV_, U_, NP_, PP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm)); \
+        sa_conv1_stream_kernel<NV_, U_, NP_, PP_><<<ctas, kF1SThreads, ssm, st>>>(s);                                        \
     } while (0)
-#define PSA_F1S_U(NV_, ST_, PPT_) do { if (s.uf) PSA_F1S_LAUNCH(NV_, ST_, true, PPT_); else PSA_F1S_LAUNCH(NV_, ST_, false, PPT_); } while (0)
-#define PSA_F1S_ST(NV_, PPT_) do { if (stats) PSA_F1S_U(NV_, true, PPT_); else PSA_F1S_U(NV_, false, PPT_); } while (0)
-            if (n <= 8 * kBqThreads) { if (C1 == 64) PSA_F1S_ST(2, 8); else PSA_F1S_ST(4, 8); }
-            else { if (C1 == 64) PSA_F1S_ST(2, 16); else PSA_F1S_ST(4, 16); }
-#undef PSA_F1S_ST
+#define PSA_F1S_U(NV_, NP_, PP_) do { if (s.uf) PSA_F1S_LAUNCH(NV_, true, NP_, PP_); else PSA_F1S_LAUNCH(NV_, false, NP_, PP_); } while (0)
+#define PSA_F1S_P(NV_)                                                                                                       \
+    do {                                                                                                                     \
+        if (np == 4 && pptp == 32) PSA_F1S_U(NV_, 4, 32);                                                                    \
+        else if (np == 4) PSA_F1S_U(NV_, 4, 16);                                                                             \
+        else if (pptp == 16) PSA_F1S_U(NV_, 2, 16);                                                                          \
+        else PSA_F1S_U(NV_, 2, 8);                                                                                           \
+    } while (0)
+            if (C1 == 64) PSA_F1S_P(2); else PSA_F1S_P(4);
+#undef PSA_F1S_P
 #undef PSA_F1S_U
 #undef PSA_F1S_LAUNCH
             return check_launch("sa_conv1_stream_kernel");

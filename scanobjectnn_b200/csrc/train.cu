@@ -76,6 +76,37 @@ __global__ void train_pool_fwd_kernel(long long groups, int pool_k, int C4, cons
     argk[e] = arg;
 }
 
+// ---- pooling over runs of pool_k rows, the modes of pointnet_util.py:126-146 other than the fused max ----
+// mode 0: max, 1: avg (reduce_mean), 2: weighted_avg with w_k = exp(-5 d_k) / sum_k exp(-5 d_k), d = |grouped_xyz| per row
+__global__ void pool_rows_kernel(long long groups, int pool_k, int C4, int mode, const float4* __restrict__ x, const float* __restrict__ dist,
+                                 float4* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= groups * C4) return;
+    const long long g = e / C4;
+    const int c4 = (int)(e - g * C4);
+    const float4* row = x + (size_t)g * pool_k * C4 + c4;
+    float4 acc;
+    if (mode == 0) {
+        acc = __ldg(row);
+        for (int k = 1; k < pool_k; ++k) {
+            const float4 v = __ldg(row + (size_t)k * C4);
+            acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+        }
+    } else {
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float wsum = 0.f;
+        for (int k = 0; k < pool_k; ++k) {
+            const float4 v = __ldg(row + (size_t)k * C4);
+            const float w = mode == 2 ? expf(-5.f * __ldg(dist + (size_t)g * pool_k + k)) : 1.f;
+            wsum += w;
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        }
+        const float inv = 1.f / wsum;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    out[e] = acc;
+}
+
 // ---- batch-norm backward sums ----
 // block = (C/4 channel quads) x RL row lanes; each block owns a contiguous chunk of rows; partial (blocks, 2, C)
 constexpr int kBnbThreads = 256;
@@ -380,6 +411,17 @@ extern "C" int psa_train_pool_fwd(long long groups, int pool_k, int C, const flo
         groups, pool_k, C / 4, reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(scale), reinterpret_cast<const float4*>(shift),
         reinterpret_cast<float4*>(pooled), reinterpret_cast<int4*>(argk));
     return check_launch("train_pool_fwd_kernel");
+}
+
+extern "C" int psa_pool_rows(long long groups, int pool_k, int C, int mode, const float* x, const float* dist, float* out, psa_stream_t stream) {
+    PSA_REQUIRE(groups >= 0 && pool_k >= 1 && C >= 4 && C % 4 == 0, "pool_rows: C=%d must be a multiple of 4", C);
+    PSA_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || dist != nullptr), "pool_rows: mode %d", mode);
+    if (groups == 0) return PSA_OK;
+    PSA_REQUIRE(x && out, "pool_rows: null buffer");
+    const long long total = groups * (C / 4);
+    pool_rows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, as_stream(stream)>>>(groups, pool_k, C / 4, mode, reinterpret_cast<const float4*>(x), dist,
+                                                                                       reinterpret_cast<float4*>(out));
+    return check_launch("pool_rows_kernel");
 }
 
 static const int kBnbMaxBlocks = 4 * kNumSMs;

@@ -58,12 +58,14 @@ def convert_to_binary_mask(masks):
     return out
 
 
-def get_current_data_h5(pcs, labels, num_points, rng: np.random.Generator | None = None):
-    """data_utils.py:171-186: one random point subset shared by all clouds, then a random cloud order.  Returns
-    (sampled, labels, idx_pts[:num_points], cloud_order) -- the index lists are what ``ops.augment_batch(perm=...)``
-    takes when the subset is applied on the device instead."""
+def get_current_data_h5(pcs, labels, num_points, rng: np.random.Generator | None = None, return_indices: bool = False):
+    """data_utils.py:171-186: one random point subset shared by all clouds, then a random cloud order.  Returns the
+    reference's (sampled, labels); with ``return_indices`` also (idx_pts[:num_points], cloud_order) -- the index lists
+    ``ops.augment_batch(perm=...)`` takes when the subset is applied on the device instead."""
     rng = np.random.default_rng() if rng is None else rng
     idx_pts = rng.permutation(pcs.shape[1])
     order = rng.permutation(len(labels))
     sampled = pcs[:, idx_pts[:num_points], :][order]
-    return sampled, np.asarray(labels)[order], idx_pts[:num_points].astype(np.int32), order
+    if return_indices:
+        return sampled, np.asarray(labels)[order], idx_pts[:num_points].astype(np.int32), order
+    return sampled, np.asarray(labels)[order]

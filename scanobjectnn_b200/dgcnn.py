@@ -83,7 +83,7 @@ def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *,
     return net, end_points
 
 
-def get_model_bga(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
+def get_model_bga(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore, return_end_points: bool = False):
     """dgcnn_bga.get_model (dgcnn_bga.py:27-134): -> (class_pred (B,num_class), seg_pred (B,N,2), end_points)."""
     _require_inference(is_training)
     end_points = {}
@@ -93,7 +93,8 @@ def get_model_bga(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES
     class_pred = ops.shared_mlp(net, params.mlp(["fc3"], [False]))
     concat = torch.cat([net.unsqueeze(1).expand(b, n, 256), out_max.unsqueeze(1).expand(b, n, 1024), *nets], dim=-1)
     seg = ops.shared_mlp(concat.reshape(b * n, -1).contiguous(), params.mlp(["seg/conv1", "seg/conv2", "seg/conv3"], [True, True, False]))
-    return class_pred, seg.reshape(b, n, 2), end_points
+    # reference arity (dgcnn_bga.py:134); the intermediate tensors only on request
+    return (class_pred, seg.reshape(b, n, 2), end_points) if return_end_points else (class_pred, seg.reshape(b, n, 2))
 
 
 def get_loss(pred, label, end_points=None, num_class=NUM_CLASSES):

@@ -44,6 +44,11 @@ class InferenceEngine:
         The previous result of that slot is overwritten: read it (``result``) before the slot comes round again."""
         j = self._n % self.slots
         self._n += 1
+        if batch.is_cuda:
+            # the producer of a device batch ran on the caller's current stream: order the slot stream behind it, and keep the
+            # caching allocator from recycling the (possibly temporary) tensor while the copy is still pending
+            self.streams[j].wait_stream(torch.cuda.current_stream(self.device))
+            batch.record_stream(self.streams[j])
         with torch.cuda.stream(self.streams[j]):
             self.static_in[j].copy_(batch, non_blocking=True)
             self.graphs[j].replay()
@@ -52,7 +57,8 @@ class InferenceEngine:
         return j
 
     def result(self, slot: int, host: bool = False) -> torch.Tensor:
-        """Wait for the slot's stream and return its logits (device tensor, or the pinned host copy)."""
+        """Wait for the slot's stream and return its logits (device tensor, or the pinned host copy).  Both are the slot's
+        STATIC buffers: they are overwritten when the slot comes round again (after ``slots`` further submits) -- clone to keep."""
         self.streams[slot].synchronize()
         return self.host_out[slot] if host else self.static_out[slot]
 

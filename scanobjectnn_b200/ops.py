@@ -19,7 +19,7 @@ __all__ = [
     "farthest_point_sample", "gather_point", "query_ball_point", "group_point", "select_top_k", "knn_point",
     "three_nn", "three_interpolate", "three_nn_interpolate", "pairwise_distance", "knn", "knn_graph",
     "get_edge_feature", "farthest_point_sample_and_gather", "MlpParams", "shared_mlp", "sa_module_infer",
-    "edgeconv_infer", "sa_conv1_prebn", "sa_group_all_infer", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
+    "edgeconv_infer", "sa_conv1_prebn", "pool_rows", "sa_group_all_infer", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
 ]
 
 
@@ -198,9 +198,13 @@ def augment_batch(src: torch.Tensor, n: int | None = None, *, perm=None, angles=
                   sigma: float = 0.01, clip: float = 0.05, drop=None, center: bool = False, normalize: bool = False) -> torch.Tensor:
     """center_data / normalize_data (data_utils.py:133-168) over the whole source cloud, the epoch's point subset
     (get_current_data_h5, data_utils.py:171-186: ``perm[:n]``, the same for every cloud), then per batch
-    rotate_point_cloud about the up axis (provider.py:34-52, ``angles`` (B,) radians), [random_scale / shift_point_cloud,
-    provider.py:202-227], jitter_point_cloud (provider.py:189-200, ``noise`` (B,n,3) standard normal) and
-    [random_point_dropout, provider.py:229-236, ``drop`` (B,n) bool] -- in one launch, same order and precisions.
+    rotate_point_cloud about the up axis (provider.py:34-52, ``angles`` (B,) radians) and jitter_point_cloud
+    (provider.py:189-200, ``noise`` (B,n,3) standard normal) -- the composition the training scripts run
+    (pointnet2/train.py:246-252), same order and precisions, in one launch.
+    Optional extras, each with its provider.py arithmetic but in THIS kernel's fixed order (the reference only composes them
+    in a commented-out block, dgcnn/train.py:274-278, which jitters BEFORE scaling): dropped slots (``drop`` (B,n) bool,
+    provider.py:229-236) read source point 0, then rotate -> scale -> shift (provider.py:202-227) -> jitter; every output
+    slot gets its own jitter noise, so dropped slots equal point 0 only up to that noise.
     src (B,N_src,3) float32 -> (B,n,3).  The random numbers are arguments: draw them with ``draw_augmentation``."""
     src = _dev(src, torch.float32, "src", 3)
     if src.shape[2] != 3:
@@ -549,6 +553,21 @@ def sa_conv1_prebn(xyz, new_xyz, points, radius: float, nsample: int, w1, bias=N
                                  _ptr(bias), c1, _ptr(pre), _ptr(idx), _ptr(cnt), _ptr(stats), _ptr(ws), C.c_size_t(need),
                                  _stream()), "sa_conv1_prebn")
     return pre, idx, cnt, stats
+
+
+def pool_rows(x, pool_k: int, mode: str = "max", dist=None) -> torch.Tensor:
+    """x (G*pool_k, C) -> (G, C): 'max', 'avg' or 'weighted_avg' (weights exp(-5 d)/sum, dist (G*pool_k,)) over each run of
+    pool_k rows -- the pooling modes of pointnet_sa_module (pointnet_util.py:126-146)."""
+    x = _dev(x, torch.float32, "x", 2)
+    rows, c = x.shape
+    if rows % pool_k:
+        raise ValueError(f"pool_rows: {rows} rows are not a multiple of pool_k={pool_k}")
+    code = {"max": 0, "avg": 1, "weighted_avg": 2}[mode]
+    if dist is not None:
+        dist = _dev(dist.reshape(-1), torch.float32, "dist", 1)
+    out = torch.empty((rows // pool_k, c), dtype=torch.float32, device=x.device)
+    check(_lib.load().psa_pool_rows(rows // pool_k, pool_k, c, code, _ptr(x), _ptr(dist), _ptr(out), _stream()), "pool_rows")
+    return out
 
 
 def edgeconv_infer(x, nn_idx, mlp: MlpParams) -> torch.Tensor:

@@ -28,7 +28,7 @@ def init_params(num_class=NUM_CLASSES, seed=0, device="cuda", randomize_bn=False
     return p
 
 
-def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
+def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore, return_end_points: bool = False):
     _require_inference(is_training)
     batch_size = point_cloud.shape[0]
     end_points = {}
@@ -59,7 +59,8 @@ def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *,
     end_points["feats"] = feats
     seg_pred = ops.shared_mlp(feats, params.mlp(["seg_fc2"], [False]))
     end_points.update(l1_xyz=l1_xyz, l2_xyz=l2_xyz, l1_points=l1_points, l2_points=l2_points, l3_points=l3_points)
-    return class_pred, seg_pred, end_points
+    # reference arity (pointnet2_cls_bga.py:75); the intermediate tensors only on request
+    return (class_pred, seg_pred, end_points) if return_end_points else (class_pred, seg_pred)
 
 
 def get_loss(class_pred, seg_pred, gt_label, gt_mask, seg_weight=0.5):

@@ -70,9 +70,29 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     ``new_xyz`` (extension): centroids already sampled by the caller (= gather_point(xyz, farthest_point_sample(npoint,
     xyz))), e.g. on a side stream -- FPS of level l+1 only depends on level l's centroids, not on its features."""
     _require_inference(is_training)
-    if pooling != "max":
-        raise NotImplementedError("only pooling='max' is used by the in-scope models")
+    if pooling not in ("max", "avg", "weighted_avg", "max_and_avg"):
+        raise ValueError(f"unknown pooling {pooling!r}")
     scopes = _mlp_scopes(scope, mlp)
+    if pooling != "max":
+        # pointnet_util.py:128-146 -- unused by the in-scope models, so the grouped rows are materialised: group -> per-row
+        # MLP (dense tensor-core kernels) -> row pooling kernel
+        if group_all:
+            new_xyz, new_points, idx, grouped_xyz = sample_and_group_all(xyz, points, use_xyz)
+        else:
+            new_xyz, new_points, idx, grouped_xyz = sample_and_group(npoint, radius, nsample, xyz, points, knn, use_xyz)
+        b, m, k, c = new_points.shape
+        rows = ops.shared_mlp(new_points.reshape(b * m * k, c).contiguous(), params.mlp(scopes))
+        if pooling == "avg":
+            pooled = ops.pool_rows(rows, k, "avg")
+        elif pooling == "weighted_avg":
+            dist = torch.linalg.vector_norm(grouped_xyz.reshape(b * m * k, 3), dim=-1)       # tf.norm(grouped_xyz, axis=-1)
+            pooled = ops.pool_rows(rows, k, "weighted_avg", dist)
+        else:
+            pooled = torch.cat([ops.pool_rows(rows, k, "avg"), ops.pool_rows(rows, k, "max")], dim=-1)   # [avg, max] (:146)
+        pooled = pooled.reshape(b, m, -1)
+        if mlp2 is not None:
+            pooled = ops.shared_mlp(pooled, params.mlp(_mlp_scopes(scope, mlp2, "conv_post_")))
+        return new_xyz, pooled, idx
     if group_all:
         nsample = xyz.shape[1]
         b = xyz.shape[0]
@@ -96,6 +116,40 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     if mlp2 is not None:
         pooled = ops.shared_mlp(pooled, params.mlp(_mlp_scopes(scope, mlp2, "conv_post_")))
     return new_xyz, pooled, idx
+
+
+def add_sa_module_msg_params(params: VariableStore, scope, in_channels, mlp_list, bn=True, randomize_bn=False):
+    """variables of pointnet_sa_module_msg: scale i, layer j -> ``scope/conv{i}_{j}``; first-layer rows ordered
+    [features, xyz] as the reference concatenates them (pointnet_util.py:184).  -> total output channels"""
+    total = 0
+    for i, mlp in enumerate(mlp_list):
+        c = in_channels
+        for j, cout in enumerate(mlp):
+            params.add_conv2d(f"{scope}/conv{i}_{j}", c, cout, bn=bn, randomize_bn=randomize_bn)
+            c = cout
+        total += c
+    return total
+
+
+def pointnet_sa_module_msg(xyz, points, npoint, radius_list, nsample_list, mlp_list, is_training, bn_decay, scope, bn=True,
+                           use_xyz=True, use_nchw=False, *, params: VariableStore):
+    """pointnet_util.pointnet_sa_module_msg (pointnet_util.py:156-196): multi-scale grouping -> (new_xyz, new_points
+    (B,npoint,sum_k mlp[k][-1])).  One FPS, then per scale the fused ball-query + group + MLP + max kernel
+    (psa_sa_module_infer) and a concat of the pooled features; no (B,m,K,C) tensor is built."""
+    _require_inference(is_training)
+    _, new_xyz = ops.farthest_point_sample_and_gather(npoint, xyz)
+    outs = []
+    for i, (radius, nsample, mlp) in enumerate(zip(radius_list, nsample_list, mlp_list)):
+        scopes = [f"{scope}/conv{i}_{j}" for j in range(len(mlp))]
+        if points is not None and not use_xyz:
+            idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
+            g = group_point(points, idx)
+            b, m, k, c = g.shape
+            outs.append(ops.shared_mlp(g.reshape(b * m * k, c), params.mlp(scopes), pool_k=k).reshape(b, m, -1))
+        else:
+            # [grouped_points, grouped_xyz] (:184): coordinate rows last in the stored weights
+            outs.append(ops.sa_module_infer(xyz, new_xyz, points, radius, nsample, params.mlp(scopes, xyz_last=points is not None)))
+    return new_xyz, torch.cat(outs, dim=-1)
 
 
 def add_fp_module_params(params: VariableStore, scope, in_channels, mlp, bn=True, randomize_bn=False):

@@ -75,15 +75,41 @@ class VariableStore(dict):
                 self._cache[key] = (w2, None, b.contiguous(), relu)
         return self._cache[key]
 
-    def mlp(self, scopes, relus=None) -> ops.MlpParams:
+    def mlp(self, scopes, relus=None, xyz_last: bool = False) -> ops.MlpParams:
+        """``xyz_last``: the first layer's input is [features, xyz] (pointnet_sa_module_msg concatenates that way,
+        pointnet_util.py:184) -- its last three weight rows are rotated to the front, which is where the fused kernels
+        expect the coordinate rows."""
         relus = relus if relus is not None else [True] * len(scopes)
-        key = ("mlp", tuple(scopes), tuple(relus))
+        key = ("mlp", tuple(scopes), tuple(relus), xyz_last)
         if key not in self._cache:
-            self._cache[key] = ops.MlpParams([self.folded(s, r) for s, r in zip(scopes, relus)])
+            layers = [self.folded(s, r) for s, r in zip(scopes, relus)]
+            if xyz_last:
+                w, sc, sh, r = layers[0]
+                layers[0] = (torch.cat([w[-3:], w[:-3]], dim=0).contiguous(), sc, sh, r)
+            self._cache[key] = ops.MlpParams(layers)
         return self._cache[key]
 
     def invalidate(self):
+        """Drop the folded conv+BN tensors / prepared weight images.  Called automatically when a variable is assigned,
+        updated or deleted; call it yourself after an IN-PLACE edit of a weight tensor.  Inference engines / CUDA graphs
+        captured earlier keep the old images: rebuild them after a weight change."""
         self._cache.clear()
+
+    # assigning variables (e.g. loading a checkpoint after a forward) must not leave stale folded weights behind
+    def __setitem__(self, key, value):
+        if getattr(self, "_cache", None):
+            self._cache.clear()
+        super().__setitem__(key, value)
+
+    def __delitem__(self, key):
+        if getattr(self, "_cache", None):
+            self._cache.clear()
+        super().__delitem__(key)
+
+    def update(self, *args, **kwargs):
+        if getattr(self, "_cache", None):
+            self._cache.clear()
+        super().update(*args, **kwargs)
 
 
 def _require_inference(is_training):

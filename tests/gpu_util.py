@@ -72,3 +72,21 @@ def ref_gather_point(inp_t, idx_t):
     rc = orc.refgpu().ref_gather_point(b, n, m, _p(inp_t), _p(idx_t), _p(out), 1)
     assert rc == 0, rc
     return out
+
+
+CONTRACT_TOL = 1e-5   # BASELINE.json north_star: grouped-MLP activations within 1e-5 (fp32)
+
+
+def contract_close(got, want, what=""):
+    """The floating-point contract of the path.  Activations of magnitude <= 1: max|got - want| < 1e-5 ABSOLUTE.  Larger
+    activations: 1e-5 relative to the largest activation (fp32 itself resolves no better), with the scale printed so the
+    log shows which bound was applied.  Returns the error."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    err = float(np.abs(got - want).max()) if want.size else 0.0
+    scale = float(np.abs(want).max()) if want.size else 0.0
+    if scale <= 1.0:
+        assert err < CONTRACT_TOL, f"{what}: max|err| = {err:.3e} >= 1e-5 absolute (max|act| = {scale:.3f})"
+    else:
+        print(f"[contract] {what}: max|act| = {scale:.3f} > 1 -> bound 1e-5 * {scale:.3f}; max|err| = {err:.3e}")
+        assert err < CONTRACT_TOL * scale, f"{what}: max|err| = {err:.3e} >= 1e-5 * max|act| ({scale:.3f})"
+    return err

@@ -33,7 +33,7 @@ def test_masks_and_epoch_subset():
     assert np.array_equal(du.convert_to_binary_mask(m), [[0, 1, 1, 0], [1, 1, 0, 1]])
     pcs = np.arange(4 * 10 * 3, dtype=np.float32).reshape(4, 10, 3)
     labels = np.arange(4)
-    sampled, lab, idx_pts, order = du.get_current_data_h5(pcs, labels, 6, np.random.default_rng(1))
+    sampled, lab, idx_pts, order = du.get_current_data_h5(pcs, labels, 6, np.random.default_rng(1), return_indices=True)
     assert sampled.shape == (4, 6, 3) and np.array_equal(lab, labels[order])
     assert np.array_equal(sampled, pcs[order][:, idx_pts, :])        # the same subset for every cloud
 

@@ -15,7 +15,7 @@ from scanobjectnn_b200.tf_util import VariableStore
 from . import gpu_util as G
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-5
+TOL = G.CONTRACT_TOL
 
 
 def _store(seed=0):
@@ -51,8 +51,7 @@ def test_shared_mlp_matches_fp64(rows, pool_k, chans):
     want = mo.mlp_chain(x, p, scopes, relus)
     if pool_k > 1:
         want = want.reshape(rows // pool_k, pool_k, -1).max(1)
-    err = np.abs(got - want).max()
-    assert err < TOL * max(1.0, np.abs(want).max()), err
+    G.contract_close(got, want, f"shared_mlp {chans} pool {pool_k}")
 
 
 @pytest.mark.parametrize("kind", ["ball", "shell"])
@@ -73,7 +72,29 @@ def test_sa_module_infer_matches_fp64(kind, n, m, r, k, c, mlp, mlp_mode):
     err = np.abs(G.npy(got) - want).max()
     f32 = np.abs(mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p, dtype=np.float32)[1] - want).max()
     print(f"sa_module[{mlp_mode}] max|err| cuda={err:.3e} numpy-fp32={f32:.3e} max|act|={np.abs(want).max():.3f}")
-    assert err < TOL * max(1.0, np.abs(want).max())
+    G.contract_close(G.npy(got), want, f"sa_module[{mlp_mode}]")
+
+
+@pytest.mark.parametrize("n,m,r,k,c,mlp", [(2048, 512, 0.2, 32, 0, [64, 64, 128]), (512, 128, 0.4, 64, 128, [128, 128, 256])])
+def test_sa_module_unit_scale_absolute_bound(n, m, r, k, c, mlp, mlp_mode):
+    """the contract's absolute form: weights scaled until every activation of the level is <= 1, then max|err| < 1e-5 flat"""
+    p = _store(n + 1)
+    add_sa_module_params(p, "sa", 3 + c, mlp, randomize_bn=True)
+    rng = np.random.default_rng(n + 7)
+    xyz = make_clouds("ball", 2, n, seed=n + 3)
+    pts = (rng.standard_normal((2, n, c)) * 0.3).astype(np.float32) if c else None
+    want = mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p)[1]
+    last = f"sa/conv{len(mlp) - 1}"
+    shrink = 0.9 / max(1e-6, float(np.abs(want).max()))
+    if shrink < 1.0:       # relu((x.W)*scale + shift) is positively homogeneous in (gamma, beta) of the last layer
+        p[f"{last}/bn/gamma"] = p[f"{last}/bn/gamma"] * shrink
+        p[f"{last}/bn/beta"] = p[f"{last}/bn/beta"] * shrink
+    _, got, _ = pointnet_sa_module(G.cu(xyz), G.cu(pts) if c else None, m, r, k, mlp, None, False, False, None, "sa", params=p)
+    want = mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p)[1]
+    assert np.abs(want).max() <= 1.0
+    err = np.abs(G.npy(got) - want).max()
+    print(f"unit-scale sa_module[{mlp_mode}] max|err|={err:.3e} (absolute bound 1e-5)")
+    assert err < 1e-5
 
 
 def test_sa_module_unfused_paths_agree():
@@ -85,7 +106,7 @@ def test_sa_module_unfused_paths_agree():
     pts = rng.standard_normal((2, 128, 16)).astype(np.float32)
     _, got, _ = pointnet_sa_module(G.cu(xyz), G.cu(pts), None, None, None, [32, 64], None, True, False, None, "sa", params=p)
     _, want, _ = mo.sa_module(xyz, pts, None, None, None, [32, 64], True, "sa", p)
-    assert np.abs(G.npy(got) - want).max() < TOL * max(1.0, np.abs(want).max())
+    G.contract_close(G.npy(got), want, "activations")
 
 
 @pytest.mark.parametrize("n,c,k,mlp", [(1024, 3, 20, [64]), (512, 64, 20, [64]), (256, 64, 20, [128]), (200, 3, 20, [64, 128]),
@@ -107,7 +128,7 @@ def test_edgeconv_infer_matches_fp64(n, c, k, mlp):
     idx = orc.dgcnn_knn(x, k)
     got = G.npy(ops.edgeconv_infer(G.cu(x), G.cu(idx), p.mlp(scopes)))
     want = mo.edgeconv(x, idx, p, scopes)
-    assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
+    G.contract_close(got, want, "activations")
 
 
 def test_fp_module_matches_fp64():
@@ -120,7 +141,7 @@ def test_fp_module_matches_fp64():
     p2 = rng.standard_normal((2, 128, 256)).astype(np.float32)
     got = G.npy(pointnet_fp_module(G.cu(xyz1), G.cu(xyz2), G.cu(p1), G.cu(p2), [256, 128], False, None, "fp", params=p))
     want = mo.fp_module(xyz1, xyz2, p1, p2, [256, 128], "fp", p)
-    assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
+    G.contract_close(got, want, "activations")
 
 
 @pytest.mark.parametrize("kind", ["ball", "shell", "dup"])
@@ -134,11 +155,10 @@ def test_pointnet2_cls_ssg_matches_oracle(kind, mlp_mode):
     assert np.array_equal(G.npy(ep["l1_xyz"]), oep["l1_xyz"])
     for name in ("l1_points", "l2_points", "l3_points"):
         w = oep[name].reshape(G.npy(ep[name]).shape)
-        err = np.abs(G.npy(ep[name]) - w).max()
-        assert err < TOL * max(1.0, np.abs(w).max()), (name, err)
+        G.contract_close(G.npy(ep[name]), w, name)
     err = np.abs(G.npy(logits) - want).max()
     print(f"logits[{mlp_mode}] max|err|={err:.3e} max|logit|={np.abs(want).max():.3f}")
-    assert err < TOL * max(1.0, np.abs(want).max())
+    G.contract_close(G.npy(logits), want, "logits")
 
 
 @pytest.mark.parametrize("kind,n,m,r,k,c,c1,b", [("ball", 2048, 512, 0.2, 32, 0, 64, 3), ("shell", 2048, 512, 0.2, 64, 0, 64, 3),
@@ -164,7 +184,7 @@ def test_sa_conv1_prebn_training_front(kind, n, m, r, k, c, c1, b):
         rows = np.concatenate([rows, orc.group_point(pts, oidx)], -1)
     want = rows.astype(np.float64) @ w1.astype(np.float64) + bias
     got = G.npy(pre)
-    assert np.abs(got - want).max() < TOL * max(1.0, np.abs(want).max())
+    G.contract_close(got, want, "activations")
     s_want = np.stack([want.reshape(-1, c1).sum(0), (want.reshape(-1, c1) ** 2).sum(0)])
     np.testing.assert_allclose(G.npy(stats), s_want, rtol=2e-5, atol=1e-3)
 
@@ -188,4 +208,4 @@ def test_sa_conv1_prebn_nonfinite_inputs_keep_reference_indices():
     want = rows.astype(np.float64) @ w1.astype(np.float64)
     ok = np.isfinite(want)
     assert ok[0].mean() > 0.9
-    assert np.abs(G.npy(pre)[ok] - want[ok]).max() < TOL * max(1.0, np.abs(want[ok]).max())
+    G.contract_close(G.npy(pre)[ok], want[ok], "pre-BN rows")

@@ -17,6 +17,8 @@ TOL = 1e-5
 
 
 def _close(got, want, tol=TOL, what=""):
+    if tol == TOL:
+        return G.contract_close(got, want, what)        # 1e-5 absolute up to |act| = 1, 1e-5 * max|act| above (printed)
     err = float(np.abs(got - want).max())
     scale = max(1.0, float(np.abs(want).max()))
     assert err < tol * scale, (what, err, scale)
@@ -27,7 +29,8 @@ def _close(got, want, tol=TOL, what=""):
 def test_pointnet2_cls_bga_matches_oracle(kind):
     p = pointnet2_cls_bga.init_params(seed=3, randomize_bn=True)
     xyz = make_clouds(kind, 2, 2048, seed=4001)
-    cls, seg, ep = pointnet2_cls_bga.get_model(G.cu(xyz), False, params=p)
+    cls, seg, ep = pointnet2_cls_bga.get_model(G.cu(xyz), False, params=p, return_end_points=True)
+    assert len(pointnet2_cls_bga.get_model(G.cu(xyz), False, params=p)) == 2      # the reference's (class_pred, seg_pred)
     wcls, wseg = mo.pointnet2_cls_bga(xyz, p)
     assert seg.shape == (2, 2048, 2) and cls.shape == (2, 15)
     e1 = _close(G.npy(cls), wcls, what="class_pred")
@@ -58,7 +61,7 @@ def test_dgcnn_stagewise_matches_oracle(bga):
     xyz = make_clouds("ball", 2, n, seed=4002)
     x = G.cu(xyz)
     if bga:
-        cls, seg, ep = dgcnn.get_model_bga(x, False, params=p)
+        cls, seg, ep = dgcnn.get_model_bga(x, False, params=p, return_end_points=True)
         assert seg.shape == (2, n, 2)
     else:
         cls, ep = dgcnn.get_model(x, False, params=p)

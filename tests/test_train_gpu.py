@@ -156,7 +156,8 @@ def test_first_layer_backward_ordered_group_point_grad():
     dU = torch.empty((b * n, c1), device="cuda")
     need = lib.psa_sa_conv1_bwd_workspace_bytes(c1)
     ws = torch.empty(need // 4 + 16, device="cuda")
-    args = (b, n, m, k, c1, _vp(G.cu(xyz)), _vp(G.cu(new_xyz)), _vp(G.cu(idx)), C.byref(g))
+    xyz_d, new_d, idx_d = G.cu(xyz), G.cu(new_xyz), G.cu(idx)       # named: the pointers must outlive the launches
+    args = (b, n, m, k, c1, _vp(xyz_d), _vp(new_d), _vp(idx_d), C.byref(g))
     assert lib.psa_sa_conv1_bwd(*args, _vp(dW), _vp(dU), _vp(ws), C.c_size_t(need), _st()) == 0
     d = (orc.group_point(xyz, idx) - new_xyz[:, :, None, :]).astype(np.float64)
     want_dW = np.einsum("bmka,bmkc->ac", d, dy0.astype(np.float64))
