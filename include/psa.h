@@ -324,7 +324,8 @@ PSA_API int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_in* 
 /* dx (rows, K - col_skip) = dy (rows, N) . W^T restricted to input channels >= col_skip (the xyz channels of a
  * concatenated input carry no gradient that anyone consumes). */
 PSA_API int psa_train_dense_bwd_input(long long rows, int K, int N, const psa_grad_in* g, const float* W, float* dx,
-                                      long long ld_dx, int col_skip, psa_stream_t stream);
+                                      long long ld_dx, int col_skip, void* workspace, size_t workspace_bytes,
+                                      psa_stream_t stream);
 /* dW (K, N) = in^T . dy, contraction over the rows in fixed split order (deterministic). */
 PSA_API int psa_train_dense_bwd_weight(long long rows, int K, int N, const psa_act_in* in, const psa_grad_in* g,
                                        float* dW, void* workspace, size_t workspace_bytes, psa_stream_t stream);
@@ -360,10 +361,10 @@ PSA_API int psa_bn_bwd_coeffs(long long rows, int C, const psa_grad_in* g, const
 
 /* Backward of the fused first layer of a set-abstraction level (psa_sa_conv1_prebn): with dy0 = g over the
  * b*m*nsample grouped rows,  dW_xyz (3, C1) = sum_r (xyz[idx_r] - new_xyz[q_r])^T dy0[r]  and, if dU != NULL,
- * dU (b*n, C1) = GroupPointGrad(dy0, idx) (tf_grouping_g.cu:61-78) as an ordered gather (each source point adds its
- * rows in ascending row order: deterministic).  The feature part of the layer then is two dense products on the b*n
- * POINTS: dpoints = dU . W1[3:]^T and dW1[3:] = points^T . dU.  workspace: psa_sa_conv1_bwd_workspace_bytes(C1). */
-PSA_API size_t psa_sa_conv1_bwd_workspace_bytes(int C1);
+ * dU (b*n, C1) = GroupPointGrad(dy0, idx) (tf_grouping_g.cu:61-78) as a stable counting sort of the (row -> point)
+ * entries followed by an ordered gather (each source point adds its rows in ascending row order: deterministic).  The feature part of the layer then is two dense products on the b*n
+ * POINTS: dpoints = dU . W1[3:]^T and dW1[3:] = points^T . dU.  workspace: psa_sa_conv1_bwd_workspace_bytes(...). */
+PSA_API size_t psa_sa_conv1_bwd_workspace_bytes(int b, int n, int m, int nsample, int C1, int want_dU);
 PSA_API int psa_sa_conv1_bwd(int b, int n, int m, int nsample, int C1, const float* xyz, const float* new_xyz,
                              const int* idx, const psa_grad_in* g, float* dW_xyz, float* dU, void* workspace,
                              size_t workspace_bytes, psa_stream_t stream);

@@ -58,17 +58,46 @@ def sample_and_group(npoint, radius, nsample, xyz, points):
     return new_xyz, new_points, idx, idx_fps
 
 
-def sa_module(xyz, points, npoint, radius, nsample, mlp, group_all, scope, params, dtype=np.float64):
-    """pointnet_sa_module (pointnet_util.py:87-154), inference, pooling='max'."""
+def sa_module(xyz, points, npoint, radius, nsample, mlp, group_all, scope, params, dtype=np.float64, pooling="max", mlp2=None):
+    """pointnet_sa_module (pointnet_util.py:87-154), inference; pooling modes :126-146, post-MLP :148-157."""
     scopes = [f"{scope}/conv{i}" for i in range(len(mlp))]
     if group_all:
         new_xyz = np.zeros((xyz.shape[0], 1, 3), np.float32)
         new_points = (np.concatenate([xyz, points], axis=2) if points is not None else xyz)[:, None]
+        grouped_xyz = xyz[:, None]
         idx = None
     else:
         new_xyz, new_points, idx, _ = sample_and_group(npoint, radius, nsample, xyz, points)
+        grouped_xyz = new_points[..., :3]
     y = mlp_chain(new_points, params, scopes, dtype=dtype)
-    return new_xyz, y.max(axis=2).astype(dtype), idx
+    if pooling == "max":
+        out = y.max(axis=2)
+    elif pooling == "avg":
+        out = y.mean(axis=2)
+    elif pooling == "weighted_avg":
+        w = np.exp(-np.linalg.norm(grouped_xyz.astype(dtype), axis=-1, keepdims=True) * 5)
+        out = (y * (w / w.sum(axis=2, keepdims=True))).sum(axis=2)
+    elif pooling == "max_and_avg":
+        out = np.concatenate([y.mean(axis=2), y.max(axis=2)], axis=-1)
+    else:
+        raise ValueError(pooling)
+    if mlp2 is not None:
+        out = mlp_chain(out, params, [f"{scope}/conv_post_{i}" for i in range(len(mlp2))], dtype=dtype)
+    return new_xyz, out.astype(dtype), idx
+
+
+def sa_module_msg(xyz, points, npoint, radius_list, nsample_list, mlp_list, scope, params, dtype=np.float64):
+    """pointnet_sa_module_msg (pointnet_util.py:156-196): per scale ball query, rows [features, xyz] (xyz LAST, :184),
+    MLP conv{i}_{j}, max over nsample; concat over scales."""
+    new_xyz = orc.gather_point(xyz, orc.fps(xyz, npoint))
+    outs = []
+    for i, (radius, nsample, mlp) in enumerate(zip(radius_list, nsample_list, mlp_list)):
+        idx, _ = orc.query_ball_point(radius, nsample, xyz, new_xyz, contract=True)
+        g = orc.group_point(xyz, idx) - new_xyz[:, :, None, :]
+        rows = g if points is None else np.concatenate([orc.group_point(points, idx), g], axis=-1)
+        y = mlp_chain(rows, params, [f"{scope}/conv{i}_{j}" for j in range(len(mlp))], dtype=dtype)
+        outs.append(y.max(axis=2))
+    return new_xyz, np.concatenate(outs, axis=-1).astype(dtype)
 
 
 def fp_module(xyz1, xyz2, points1, points2, mlp, scope, params, dtype=np.float64):

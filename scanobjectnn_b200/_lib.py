@@ -81,7 +81,7 @@ SIGNATURES = {
     "psa_edgeconv_infer": [_i, _i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
     # training mode
     "psa_train_dense_fwd": [_ll, _i, _i, _ain, _p, _p, _p, _p, _p, _sz, _p],
-    "psa_train_dense_bwd_input": [_ll, _i, _i, _gin, _p, _p, _ll, _i, _p],
+    "psa_train_dense_bwd_input": [_ll, _i, _i, _gin, _p, _p, _ll, _i, _p, _sz, _p],
     "psa_train_dense_bwd_weight": [_ll, _i, _i, _ain, _gin, _p, _p, _sz, _p],
     "psa_train_bias_grad": [_ll, _i, _gin, _p, _p],
     "psa_bn_finalize": [_i, _ll, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
@@ -127,7 +127,7 @@ def load() -> C.CDLL:
     lib.psa_train_dense_workspace_bytes.restype = C.c_size_t
     lib.psa_bn_bwd_workspace_bytes.argtypes = [_i]
     lib.psa_bn_bwd_workspace_bytes.restype = C.c_size_t
-    lib.psa_sa_conv1_bwd_workspace_bytes.argtypes = [_i]
+    lib.psa_sa_conv1_bwd_workspace_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.psa_sa_conv1_bwd_workspace_bytes.restype = C.c_size_t
     lib.psa_version.restype = C.c_int
     lib.psa_sm_arch.restype = C.c_int

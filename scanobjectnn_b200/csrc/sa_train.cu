@@ -192,11 +192,21 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 
+// Batches of a cloud segment: 2, 4, then kF1Batch queries -- the first stores of a CTA start after a 2-query search.
+__host__ __device__ inline int f1s_batch_size(int t) { return t == 0 ? 2 : (t == 1 ? 4 : kF1Batch); }
+__host__ __device__ inline int f1s_num_batches(long long nq) {
+    int t = 0;
+    for (long long done = 0; done < nq; ++t) done += f1s_batch_size(t);
+    return t;
+}
+
 // shared memory: cloud as float4 (x,y,z,bits(k)) | kF1Batch bitmaps of bw words | ring slots (idx rows | centred rows)
 __host__ __device__ inline int f1s_bitmap_words(int np, int pptp) { const int w = np * pptp; return w < 32 ? 32 : w; }
 __host__ __device__ inline size_t f1s_slot_bytes(int nsample) { return (size_t)kF1Batch * nsample * (sizeof(int) + sizeof(float4)); }
 __host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, int np, int pptp) {
-    return (size_t)n * 16 + (size_t)kF1Batch * f1s_bitmap_words(np, pptp) * 4 + kF1Ring * f1s_slot_bytes(nsample);
+    size_t ring = kF1Ring * f1s_slot_bytes(nsample);
+    if (ring < 8192) ring = 8192;                   // the statistics epilogue reuses the ring: up to 8 KB of partials
+    return (size_t)n * 16 + (size_t)kF1Batch * f1s_bitmap_words(np, pptp) * 4 + ring;
 }
 
 template <int NV, bool HAS_U, int NP, int PPTP>
@@ -229,7 +239,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
     for (long long q = q_begin; q < q_end;) {
         const long long cloud = q / a.m;
         const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-        total_batches += (int)((seg_end - q + kF1Batch - 1) / kF1Batch);
+        total_batches += f1s_num_batches(seg_end - q);
         q = seg_end;
     }
 
@@ -240,7 +250,6 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         for (long long q = q_begin; q < q_end;) {
             const long long cloud = q / a.m;
             const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-            const int nb = (int)((seg_end - q + kF1Batch - 1) / kF1Batch);
             const float* gx = a.xyz + (size_t)cloud * n * 3;
             // ---- this cloud: PPTP points per thread in registers (point k = 32*(warp + NP*i) + lane), float4 copy in smem ----
             named_bar_sync(15, PT);                                          // the previous cloud's float4 copy is no longer read
@@ -262,13 +271,13 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
 #ifdef PSA_F1_TIMING
             if (tid == 0 && a.tlog && q == q_begin) a.tlog[blockIdx.x * 8 + 1] = gtime();
 #endif
-            for (int bi = 0; bi < nb; ++bi, ++ring_pos) {
+            long long gq0 = q;                                                             // global query id of the batch
+            for (int bi = 0; gq0 < seg_end; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
                 if (ring_pos >= kF1Ring) named_bar_sync(1 + kF1Ring + slot, kF1SThreads);   // slot drained by the consumers
                 int* sidx = reinterpret_cast<int*>(ring + slot * slot_bytes);
                 float4* sd = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
-                const long long gq0 = q + (long long)bi * kF1Batch;                        // global query id of the batch
-                const int nqb = min(kF1Batch, (int)(seg_end - gq0));
+                const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
                 // ---- exhaustive test: one ballot per 32-point word = that word of the query's bitmap ----
                 if (!a.none) {
                     for (int qi = 0; qi < nqb; ++qi) {
@@ -287,6 +296,9 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                     }
                 }
                 named_bar_sync(15, PT);                                                     // bitmaps complete
+#ifdef PSA_F1_TIMING
+                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 4] = gtime();
+#endif
                 // ---- bitmaps -> ordered idx rows: 8 lanes per query, 4 queries per warp pass ----
                 for (int q0 = warp * 4; q0 < kF1Batch; q0 += NP * 4) {
                     const int qi = q0 + (lane >> 3);
@@ -295,6 +307,9 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                     if (act && a.pts_cnt != nullptr && (lane & 7) == 0) a.pts_cnt[gq0 + qi] = cnt;
                 }
                 named_bar_sync(15, PT);                                                     // idx rows complete
+#ifdef PSA_F1_TIMING
+                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 7] = gtime();
+#endif
                 // ---- grouped_xyz - new_xyz (pointnet_util.py:46) of the batch's rows + the source index for the U gather ----
                 const int nrows = nqb * K;
                 int* gidx = a.idx + (size_t)gq0 * K;
@@ -310,6 +325,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
 #ifdef PSA_F1_TIMING
                 if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 2] = gtime();
 #endif
+                gq0 += nqb;
             }
             q = seg_end;
         }
@@ -337,13 +353,13 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         for (long long q = q_begin; q < q_end;) {
             const long long cloud = q / a.m;
             const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-            const int nb = (int)((seg_end - q + kF1Batch - 1) / kF1Batch);
             const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + 4 * sub : nullptr;
-            for (int bi = 0; bi < nb; ++bi, ++ring_pos) {
+            long long gq0 = q;
+            for (int bi = 0; gq0 < seg_end; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
                 const float4* sd = reinterpret_cast<const float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
-                const long long gq0 = q + (long long)bi * kF1Batch;
-                const int nrows = min(kF1Batch, (int)(seg_end - gq0)) * K;
+                const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
+                const int nrows = nqb * K;
                 float* outl = a.pre + (size_t)gq0 * K * C1 + 4 * sub;
                 named_bar_sync(1 + slot, kF1SThreads);                                      // FULL
                 for (int r = 4 * cw + rsub; r < nrows; r += 4 * NC) {
@@ -366,6 +382,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                     }
                 }
                 if (ring_pos + kF1Ring < total_batches) named_bar_arrive(1 + kF1Ring + slot, kF1SThreads);   // EMPTY
+                gq0 += nqb;
             }
             q = seg_end;
         }
@@ -401,37 +418,37 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         }
         // last CTA to arrive adds the CTA partials (fp64) in a fixed tree: deterministic whatever the finishing order
         __shared__ unsigned s_last;
-        __shared__ double s_half[kF1SThreads];
         __threadfence();
         __syncthreads();
         if (tid == 0) s_last = (atomicAdd(&g_f1_tickets[a.ticket], 1u) == gridDim.x - 1) ? 1u : 0u;
         __syncthreads();
         if (s_last) {
             __threadfence();
-            // thread (h, e): partials p = h, h + H, ... of value e, four independent accumulators; then the H halves in order
-            const int E = 2 * C1;
-            const int H = kF1SThreads / E > 0 ? kF1SThreads / E : 1;      // 2 (C1 = 64) or 1 (C1 = 128)
-            for (int e0 = 0; e0 < E; e0 += kF1SThreads / H) {
-                const int e = e0 + tid % (kF1SThreads / H), h = tid / (kF1SThreads / H);
-                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-                if (e < E) {
-                    unsigned p = h;
-                    for (; p + 3 * H < gridDim.x; p += 4 * H) {
-                        t0 += (double)__ldcg(a.partial + (size_t)p * E + e);
-                        t1 += (double)__ldcg(a.partial + (size_t)(p + H) * E + e);
-                        t2 += (double)__ldcg(a.partial + (size_t)(p + 2 * H) * E + e);
-                        t3 += (double)__ldcg(a.partial + (size_t)(p + 3 * H) * E + e);
-                    }
-                    for (; p < gridDim.x; p += H) t0 += (double)__ldcg(a.partial + (size_t)p * E + e);
+            // thread (rl, e4): partial rows p = rl, rl + RL, ... of float4 column e4, sixteen loads in flight (the loop is
+            // L2-latency-bound), fp64 accumulators in ascending p; then the RL row lanes in order through shared memory
+            const int E4 = 2 * C1 / 4;                                     // 32 (C1 = 64) or 64 (C1 = 128)
+            const int RL = kF1SThreads / E4;                               // 8 or 4
+            const int e4 = tid % E4, rl = tid / E4;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const float4* part4 = reinterpret_cast<const float4*>(a.partial);
+            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 16 * RL) {
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const unsigned p = p0 + u * RL;
+                    v[u] = p < gridDim.x ? __ldcg(part4 + (size_t)p * E4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                s_half[tid] = (t0 + t1) + (t2 + t3);
-                __syncthreads();
-                if (h == 0 && e < E) {
-                    double t = 0.0;
-                    for (int hh = 0; hh < H; ++hh) t += s_half[hh * (kF1SThreads / H) + tid];
-                    a.stats[e] = (float)t;
-                }
-                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+            }
+            double* sred = reinterpret_cast<double*>(ring);                // RL x 2*C1 doubles <= 8 KB (the ring is >= 15 KB)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sred[(size_t)rl * 2 * C1 + e4 * 4 + c] = acc[c];
+            __syncthreads();
+            for (int e = tid; e < 2 * C1; e += kF1SThreads) {
+                double t = 0.0;
+                for (int r = 0; r < RL; ++r) t += sred[(size_t)r * 2 * C1 + e];
+                a.stats[e] = (float)t;
             }
             if (tid == 0) g_f1_tickets[a.ticket] = 0u;     // ready for the next launch that draws this ticket
         }

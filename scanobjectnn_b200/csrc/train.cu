@@ -11,17 +11,39 @@
 
 namespace psa {
 
-// out[e] = sum_p partial[p * len + e], p ascending, fp64 accumulator
-__global__ void reduce_partials_kernel(int nparts, int len, const float* __restrict__ partial, float* __restrict__ out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= len) return;
+// out[e] = sum_p partial[p * len + e] in a FIXED tree: block = 32 outputs x 32 chunk lanes; lane c adds its contiguous range of
+// partials in ascending order (fp64, eight loads in flight), the 32 chunk sums are added in lane order.  Deterministic, and
+// ~32x shorter dependent chains than one thread per output (4096 tile partials took 290 us that way).
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(int nparts, int len, const float* __restrict__ partial, float* __restrict__ out) {
+    __shared__ double red[32][33];
+    const int ex = threadIdx.x & 31, cl = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + ex;
+    const int per = (nparts + 31) / 32;
+    const int p0 = cl * per, p1 = min(nparts, p0 + per);
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * len + e];
-    out[e] = (float)s;
+    if (e < len) {
+        int p = p0;
+        for (; p + 7 < p1; p += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (size_t)(p + u) * len + e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
+        for (; p < p1; ++p) s += (double)__ldcg(partial + (size_t)p * len + e);
+    }
+    red[cl][ex] = s;
+    __syncthreads();
+    if (cl == 0 && e < len) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) t += red[c][ex];
+        out[e] = (float)t;
+    }
 }
 
 static int reduce_partials(int nparts, int len, const float* partial, float* out, cudaStream_t st) {
-    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, st>>>(nparts, len, partial, out);
+    reduce_partials_kernel<<<(len + 31) / 32, 1024, 0, st>>>(nparts, len, partial, out);
     return check_launch("reduce_partials_kernel");
 }
 
@@ -31,6 +53,37 @@ static int launch_gemm(const FA& fa, const FB& fb, const GemmOut& o, long long M
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
     train_gemm_kernel<BM, BN, A_KC, B_NC, FA, FB><<<grid, kGemmThreads, 0, st>>>(fa, fb, o, M, N, Kc, k_per_split);
     return check_launch("train_gemm_kernel");
+}
+
+// ---- small-M products (the FC head: rows = batch): contraction split over CTAs, finished here in split order ----
+// out[m][n - col_skip] = sum_z partial[z][m][n] (+ bias[n]);  grid over M*N elements
+__global__ void splitk_finish_kernel(int splits, long long M, int N, const float* __restrict__ partial, const float* __restrict__ bias,
+                                     float* __restrict__ out, long long ld_out, int col_skip) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * N) return;
+    const long long m = e / N;
+    const int n = (int)(e - m * N);
+    float t = 0.f;
+    for (int z = 0; z < splits; ++z) t += partial[(size_t)z * M * N + e];
+    if (bias != nullptr) t += __ldg(bias + n);
+    if (n >= col_skip) out[m * ld_out + (n - col_skip)] = t;
+}
+// stats (2, N) of y (M, N), M small: block = 32 columns x 32 row lanes, fixed-order tree
+__global__ void __launch_bounds__(1024) col_stats_kernel(long long M, int N, const float* __restrict__ y, float* __restrict__ stats) {
+    __shared__ double red[2][32][33];
+    const int ex = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + ex;
+    double s = 0.0, q = 0.0;
+    if (n < N)
+        for (long long m = rl; m < M; m += 32) { const double v = y[m * N + n]; s += v; q += v * v; }
+    red[0][rl][ex] = s; red[1][rl][ex] = q;
+    __syncthreads();
+    if (rl == 0 && n < N) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { a += red[0][k][ex]; b += red[1][k][ex]; }
+        stats[n] = (float)a; stats[N + n] = (float)b;
+    }
 }
 
 // ---- batch-norm finalize ----
@@ -157,13 +210,34 @@ bn_bwd_partial_kernel(const GradIn g, long long rows, int C, const float* __rest
     }
 }
 
-__global__ void bn_bwd_final_kernel(int nparts, int C, double inv_rows, const float* __restrict__ partial, const float* __restrict__ gamma,
-                                    const float* __restrict__ mean_inv, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(1024)
+bn_bwd_final_kernel(int nparts, int C, double inv_rows, const float* __restrict__ partial, const float* __restrict__ gamma,
+                    const float* __restrict__ mean_inv, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc) {
+    __shared__ double red[2][32][33];
+    const int ex = threadIdx.x & 31, cl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + ex;
+    const int per = (nparts + 31) / 32;
+    const int p0 = cl * per, p1 = min(nparts, p0 + per);
+    double sb = 0.0, sg = 0.0;
+    if (c < C) {
+        int p = p0;
+        for (; p + 3 < p1; p += 4) {
+            float vb[4], vg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { vb[u] = __ldcg(partial + (size_t)(p + u) * 2 * C + c); vg[u] = __ldcg(partial + (size_t)(p + u) * 2 * C + C + c); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { sb += (double)vb[u]; sg += (double)vg[u]; }
+        }
+        for (; p < p1; ++p) { sb += (double)__ldcg(partial + (size_t)p * 2 * C + c); sg += (double)__ldcg(partial + (size_t)p * 2 * C + C + c); }
+    }
+    red[0][cl][ex] = sb;
+    red[1][cl][ex] = sg;
+    __syncthreads();
+    if (cl != 0 || c >= C) return;
     double db = 0.0, dg = 0.0;
-    for (int p = 0; p < nparts; ++p) { db += (double)partial[(size_t)p * 2 * C + c]; dg += (double)partial[(size_t)p * 2 * C + C + c]; }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { db += red[0][k][ex]; dg += red[1][k][ex]; }
     dbeta[c] = (float)db;
     dgamma[c] = (float)dg;
     const double gm = gamma[c], mu = mean_inv[c], inv = mean_inv[C + c];
@@ -213,41 +287,89 @@ conv1_dwxyz_partial_kernel(const GradIn g, long long rows, int nsample, long lon
     }
 }
 
-// GroupPointGrad as an ordered gather: warp = 4 consecutive source points of one cloud; the warp scans the cloud's idx
-// array (m*nsample entries, L1/L2 resident) 32 entries per step and adds the matching rows' dy0 in ascending row order.
-// lane = 4 channels (C1 <= 128).
-constexpr int kScatJ = 4;
-__global__ void __launch_bounds__(256)
-group_grad_gather_kernel(const GradIn g, int n, int mk, int C1, const int* __restrict__ idx, float* __restrict__ dU) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cloud = blockIdx.y;
-    const int j0 = (blockIdx.x * 8 + warp) * kScatJ;
-    if (j0 >= n) return;
+// GroupPointGrad (tf_grouping_g.cu:61-78) without atomics, in two kernels:
+//  1. group_csr_kernel (one CTA per cloud): a STABLE counting sort of the cloud's m*nsample (row -> source point) entries:
+//     counts (shared-memory integer atomics: order-free), exclusive scan, then one warp walks the entries in row order, 32 at
+//     a time -- __match_any_sync groups the lanes that reference the same point, the rank inside the group is a popcount of
+//     the lower lanes, the group leader advances that point's cursor -- so list[] holds, per source point, its rows in
+//     ascending order;
+//  2. group_grad_csr_kernel (one warp per source point, lane = 4 channels): adds the rows of the point in list order.
+// Fixed order => bit-reproducible, unlike the reference's float atomicAdd.
+__global__ void __launch_bounds__(256) group_csr_kernel(int n, int mk, const int* __restrict__ idx, int* __restrict__ offsets, int* __restrict__ list) {
+    extern __shared__ int sm_i[];                 // n counters / cursors
+    const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int* ic = idx + (size_t)cloud * mk;
-    const bool chan = lane * 4 < C1;
-    float4 acc[kScatJ];
+    int* off = offsets + (size_t)cloud * (n + 1);
+    int* lst = list + (size_t)cloud * mk;
+    for (int j = tid; j < n; j += 256) sm_i[j] = 0;
+    __syncthreads();
+    for (int e = tid; e < mk; e += 256) atomicAdd(&sm_i[__ldg(ic + e)], 1);
+    __syncthreads();
+    // exclusive scan by one warp (n <= a few thousand): lane owns a contiguous run of counters
+    if (tid < 32) {
+        const int per = (n + 31) / 32;
+        const int j0 = lane * per, j1 = min(n, j0 + per);
+        int local = 0;
+        for (int j = j0; j < j1; ++j) local += sm_i[j];
+        int incl = local;
 #pragma unroll
-    for (int u = 0; u < kScatJ; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = 0; base < mk; base += 32) {
-        const int e = base + lane;
-        const int v = e < mk ? __ldg(ic + e) : -1;
-#pragma unroll
-        for (int u = 0; u < kScatJ; ++u) {
-            unsigned mt = __ballot_sync(0xffffffffu, v == j0 + u);
-            while (mt) {
-                const int r = base + __ffs(mt) - 1;
-                mt &= mt - 1u;
-                if (chan) {
-                    const float4 d = g.get4((long long)cloud * mk + r, lane * 4);
-                    acc[u].x += d.x; acc[u].y += d.y; acc[u].z += d.z; acc[u].w += d.w;
-                }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - local;
+        for (int j = j0; j < j1; ++j) { const int c = sm_i[j]; sm_i[j] = run; off[j] = run; run += c; }
+        if (lane == 31) off[n] = incl;
+        __syncwarp();
+        // stable placement: entries in row order, 32 per step
+        for (int base = 0; base < mk; base += 32) {
+            const int e = base + lane;
+            const bool act = e < mk;
+            const int v = act ? __ldg(ic + e) : -1 - lane;             // inactive lanes: distinct dummies
+            const unsigned grp = __match_any_sync(0xffffffffu, v);
+            const int rank = __popc(grp & lanemask_lt());
+            int cur = 0;
+            if (act) cur = sm_i[v];
+            __syncwarp();
+            if (act) {
+                lst[cur + rank] = e;
+                if (rank == 0) sm_i[v] = cur + __popc(grp);             // the group's lowest lane advances the cursor
             }
+            __syncwarp();
         }
     }
-    if (chan) {
-#pragma unroll
-        for (int u = 0; u < kScatJ; ++u)
-            if (j0 + u < n) *reinterpret_cast<float4*>(dU + ((size_t)cloud * n + j0 + u) * C1 + lane * 4) = acc[u];
+}
+
+__global__ void __launch_bounds__(256)
+group_grad_csr_kernel(const GradIn g, int n, int mk, int C1, long long total_points, const int* __restrict__ offsets, const int* __restrict__ list,
+                      float* __restrict__ dU) {
+    const int lane = threadIdx.x & 31;
+    const long long pt = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);           // global source point b*n + j
+    if (pt >= total_points) return;
+    const long long cloud = pt / n;
+    const int j = (int)(pt - cloud * n);
+    const int* off = offsets + (size_t)cloud * (n + 1);
+    const int* lst = list + (size_t)cloud * mk;
+    const int t0 = __ldg(off + j), t1 = __ldg(off + j + 1);
+    for (int c0 = 0; c0 < C1; c0 += 128) {
+        const int c = c0 + lane * 4;
+        if (c >= C1) break;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int t = t0;
+        for (; t + 3 < t1; t += 4) {                                              // four rows in flight, added in list order
+            const int r0 = __ldg(lst + t), r1 = __ldg(lst + t + 1), r2 = __ldg(lst + t + 2), r3 = __ldg(lst + t + 3);
+            const float4 d0 = g.get4(cloud * mk + r0, c), d1 = g.get4(cloud * mk + r1, c);
+            const float4 d2 = g.get4(cloud * mk + r2, c), d3 = g.get4(cloud * mk + r3, c);
+            acc.x += d0.x; acc.y += d0.y; acc.z += d0.z; acc.w += d0.w;
+            acc.x += d1.x; acc.y += d1.y; acc.z += d1.z; acc.w += d1.w;
+            acc.x += d2.x; acc.y += d2.y; acc.z += d2.z; acc.w += d2.w;
+            acc.x += d3.x; acc.y += d3.y; acc.z += d3.z; acc.w += d3.w;
+        }
+        for (; t < t1; ++t) {
+            const float4 d = g.get4(cloud * mk + __ldg(lst + t), c);
+            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+        }
+        *reinterpret_cast<float4*>(dU + (size_t)pt * C1 + c) = acc;
     }
 }
 
@@ -302,6 +424,12 @@ __global__ void adam_kernel(long long count, float* __restrict__ p, const float*
     }
 }
 
+constexpr long long kSmallM = 1024;        // rows up to this use the split-contraction path in forward / input gradient
+static int small_m_splits(long long contraction) {
+    long long s = contraction / 64;
+    return (int)(s < 1 ? 1 : (s > 16 ? 16 : s));
+}
+
 static int weight_grad_splits(long long rows, int tiles, long long* k_per_split) {
     long long want = (2LL * kNumSMs + tiles - 1) / tiles;
     long long maxs = (rows + 255) / 256;                       // at least 256 rows of contraction per split
@@ -320,12 +448,16 @@ using namespace psa;
 extern "C" size_t psa_train_dense_workspace_bytes(long long rows, int K, int N) {
     // forward: (tiles_m, 2, N) statistics partials; weight gradient: (splits, K, N) partial products
     const size_t fwd = (size_t)((rows + 127) / 128) * 2 * (size_t)N * sizeof(float);
-    const int bm = (K <= 64 && N <= 64) ? 64 : 128, bn = N <= 64 ? 64 : 128;
+    const int bm = K <= 64 ? 64 : 128, bn = N <= 64 ? 64 : 128;
     const int tiles = ((K + bm - 1) / bm) * ((N + bn - 1) / bn);
     long long kps;
     const int splits = weight_grad_splits(rows, tiles, &kps);
     const size_t bwd = splits > 1 ? (size_t)splits * K * N * sizeof(float) : 0;
-    return (fwd > bwd ? fwd : bwd) + 256;
+    // small-M forward / input-gradient products split their contraction: (splits <= 16, rows, max(K, N)) partial outputs
+    const size_t small = rows <= kSmallM ? (size_t)16 * rows * (K > N ? K : N) * sizeof(float) : 0;
+    size_t mx = fwd > bwd ? fwd : bwd;
+    if (small > mx) mx = small;
+    return mx + 256;
 }
 
 extern "C" int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_in* in, const float* W, const float* bias, float* y,
@@ -344,6 +476,24 @@ extern "C" int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_i
     const ActIn fa(*in);
     const MatIn fb{W, N};
     int rc;
+    const int splits = rows <= kSmallM ? small_m_splits(K) : 1;
+    if (splits > 1) {
+        // few row tiles, long contraction (the FC head): split K over CTAs, finish in split order, statistics from the result
+        PSA_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)splits * rows * N * sizeof(float), "train_dense_fwd: workspace too small");
+        GemmOut po;
+        po.out = reinterpret_cast<float*>(workspace); po.ld_out = N; po.bias = nullptr; po.col_skip = 0; po.stat_partial = nullptr;
+        const long long kps = ((K + splits - 1) / splits + kGemmBK - 1) / kGemmBK * kGemmBK;
+        const int nz = (int)((K + kps - 1) / kps);
+        if (N <= 64) rc = launch_gemm<128, 64, true, true>(fa, fb, po, rows, N, K, nz, kps, st);
+        else rc = launch_gemm<128, 128, true, true>(fa, fb, po, rows, N, K, nz, kps, st);
+        if (rc != PSA_OK) return rc;
+        const long long total = rows * N;
+        splitk_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(nz, rows, N, po.out, bias, y, N, 0);
+        rc = check_launch("splitk_finish_kernel");
+        if (rc != PSA_OK || stats == nullptr) return rc;
+        col_stats_kernel<<<(N + 31) / 32, 1024, 0, st>>>(rows, N, y, stats);
+        return check_launch("col_stats_kernel");
+    }
     if (N <= 64) rc = launch_gemm<128, 64, true, true>(fa, fb, o, rows, N, K, 1, (long long)K + kGemmBK, st);
     else rc = launch_gemm<128, 128, true, true>(fa, fb, o, rows, N, K, 1, (long long)K + kGemmBK, st);
     if (rc != PSA_OK) return rc;
@@ -352,7 +502,7 @@ extern "C" int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_i
 }
 
 extern "C" int psa_train_dense_bwd_input(long long rows, int K, int N, const psa_grad_in* g, const float* W, float* dx, long long ld_dx,
-                                         int col_skip, psa_stream_t stream) {
+                                         int col_skip, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
     PSA_REQUIRE(rows >= 0 && K >= 1 && N >= 1 && col_skip >= 0 && col_skip < K, "train_dense_bwd_input: bad dims");
     if (rows == 0) return PSA_OK;
     PSA_REQUIRE(g && W && dx, "train_dense_bwd_input: null buffer");
@@ -361,6 +511,20 @@ extern "C" int psa_train_dense_bwd_input(long long rows, int K, int N, const psa
     const GradIn fa(*g);
     const MatIn fb{W, N};                                    // B(kc = n, col = k) = W[k][n]: contraction-contiguous
     cudaStream_t st = as_stream(stream);
+    const int splits = rows <= kSmallM ? small_m_splits(N) : 1;
+    if (splits > 1 && workspace != nullptr && workspace_bytes >= (size_t)splits * rows * K * sizeof(float)) {
+        GemmOut po;
+        po.out = reinterpret_cast<float*>(workspace); po.ld_out = K; po.bias = nullptr; po.col_skip = 0; po.stat_partial = nullptr;
+        const long long kps = ((N + splits - 1) / splits + kGemmBK - 1) / kGemmBK * kGemmBK;
+        const int nz = (int)((N + kps - 1) / kps);
+        int rc;
+        if (K <= 64) rc = launch_gemm<128, 64, true, false>(fa, fb, po, rows, K, N, nz, kps, st);
+        else rc = launch_gemm<128, 128, true, false>(fa, fb, po, rows, K, N, nz, kps, st);
+        if (rc != PSA_OK) return rc;
+        const long long total = rows * K;
+        splitk_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(nz, rows, K, po.out, nullptr, dx, ld_dx, col_skip);
+        return check_launch("splitk_finish_kernel");
+    }
     if (K <= 64) return launch_gemm<128, 64, true, false>(fa, fb, o, rows, K, N, 1, (long long)N + kGemmBK, st);
     return launch_gemm<128, 128, true, false>(fa, fb, o, rows, K, N, 1, (long long)N + kGemmBK, st);
 }
@@ -370,7 +534,7 @@ extern "C" int psa_train_dense_bwd_weight(long long rows, int K, int N, const ps
     PSA_REQUIRE(rows >= 1 && K >= 1 && N >= 1, "train_dense_bwd_weight: bad dims");
     PSA_REQUIRE(in && in->x && g && dW, "train_dense_bwd_weight: null buffer");
     cudaStream_t st = as_stream(stream);
-    const int bm = (K <= 64 && N <= 64) ? 64 : 128, bn = N <= 64 ? 64 : 128;
+    const int bm = K <= 64 ? 64 : 128, bn = N <= 64 ? 64 : 128;
     const int tiles = ((K + bm - 1) / bm) * ((N + bn - 1) / bn);
     long long kps;
     const int splits = weight_grad_splits(rows, tiles, &kps);
@@ -385,7 +549,8 @@ extern "C" int psa_train_dense_bwd_weight(long long rows, int K, int N, const ps
     const ActIn fa(*in);
     const GradIn fb(*g);
     int rc;
-    if (bm == 64) rc = launch_gemm<64, 64, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
+    if (bm == 64 && bn == 64) rc = launch_gemm<64, 64, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
+    else if (bm == 64) rc = launch_gemm<64, 128, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
     else if (bn == 64) rc = launch_gemm<128, 64, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
     else rc = launch_gemm<128, 128, false, true>(fa, fb, o, K, N, rows, splits, kps, st);
     if (rc != PSA_OK) return rc;
@@ -451,18 +616,23 @@ extern "C" int psa_bn_bwd_coeffs(long long rows, int C, const psa_grad_in* g, co
     bn_bwd_partial_kernel<<<(unsigned)blocks, kBnbThreads, 0, st>>>(gi, units, C, mean_inv, upb, partial);
     int rc = check_launch("bn_bwd_partial_kernel");
     if (rc != PSA_OK) return rc;
-    bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>((int)blocks, C, 1.0 / (double)rows, partial, gamma, mean_inv, dgamma, dbeta, ca, cb, cc);
+    bn_bwd_final_kernel<<<(C + 31) / 32, 1024, 0, st>>>((int)blocks, C, 1.0 / (double)rows, partial, gamma, mean_inv, dgamma, dbeta, ca, cb, cc);
     return check_launch("bn_bwd_final_kernel");
 }
 
-extern "C" size_t psa_sa_conv1_bwd_workspace_bytes(int C1) { return (size_t)kBnbMaxBlocks * 3 * C1 * sizeof(float); }
+static size_t conv1_bwd_partial_bytes(int C1) { return ((size_t)kBnbMaxBlocks * 3 * C1 * sizeof(float) + 255) & ~(size_t)255; }
+extern "C" size_t psa_sa_conv1_bwd_workspace_bytes(int b, int n, int m, int nsample, int C1, int want_dU) {
+    size_t bytes = conv1_bwd_partial_bytes(C1);
+    if (want_dU) bytes += ((size_t)b * (n + 1) + (size_t)b * m * nsample) * sizeof(int);     // CSR offsets + row lists
+    return bytes;
+}
 
 extern "C" int psa_sa_conv1_bwd(int b, int n, int m, int nsample, int C1, const float* xyz, const float* new_xyz, const int* idx,
                                 const psa_grad_in* g, float* dW_xyz, float* dU, void* workspace, size_t workspace_bytes, psa_stream_t stream) {
     PSA_REQUIRE(b >= 1 && n >= 1 && m >= 1 && nsample >= 1, "sa_conv1_bwd: bad dims");
     PSA_SUPPORTED(C1 % 4 == 0 && C1 <= 1024, "sa_conv1_bwd: C1=%d", C1);
     PSA_REQUIRE(xyz && new_xyz && idx && g && dW_xyz, "sa_conv1_bwd: null buffer");
-    PSA_REQUIRE(workspace && workspace_bytes >= psa_sa_conv1_bwd_workspace_bytes(C1), "sa_conv1_bwd: workspace too small");
+    PSA_REQUIRE(workspace && workspace_bytes >= psa_sa_conv1_bwd_workspace_bytes(b, n, m, nsample, C1, dU != nullptr), "sa_conv1_bwd: workspace too small");
     cudaStream_t st = as_stream(stream);
     const GradIn gi(*g);
     const long long rows = (long long)b * m * nsample;
@@ -479,10 +649,19 @@ extern "C" int psa_sa_conv1_bwd(int b, int n, int m, int nsample, int C1, const 
     rc = reduce_partials((int)blocks, 3 * C1, partial, dW_xyz, st);
     if (rc != PSA_OK) return rc;
     if (dU != nullptr) {
-        PSA_SUPPORTED(C1 <= 128, "sa_conv1_bwd: the ordered GroupPointGrad gather handles C1 <= 128 (got %d)", C1);
-        dim3 grid((unsigned)((n + 8 * kScatJ - 1) / (8 * kScatJ)), (unsigned)b);
-        group_grad_gather_kernel<<<grid, 256, 0, st>>>(gi, n, m * nsample, C1, idx, dU);
-        return check_launch("group_grad_gather_kernel");
+        // CSR scratch behind the dW partials: offsets (b, n+1) + list (b, m*nsample)
+        uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace) + conv1_bwd_partial_bytes(C1);
+        PSA_SUPPORTED((size_t)n * sizeof(int) <= 160 * 1024, "sa_conv1_bwd: n=%d too large for the per-cloud counters", n);
+        int* offsets = reinterpret_cast<int*>(wsb);
+        int* list = offsets + (size_t)b * (n + 1);
+        const size_t smem = (size_t)n * sizeof(int);
+        PSA_CUDA(cudaFuncSetAttribute(group_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_csr_kernel<<<b, 256, smem, st>>>(n, m * nsample, idx, offsets, list);
+        rc = check_launch("group_csr_kernel");
+        if (rc != PSA_OK) return rc;
+        const long long pts = (long long)b * n;
+        group_grad_csr_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(gi, n, m * nsample, C1, pts, offsets, list, dU);
+        return check_launch("group_grad_csr_kernel");
     }
     return PSA_OK;
 }

@@ -229,7 +229,7 @@ class PointNet2ClsTrainer:
                 lv.idx = torch.empty((batch, m, k), dtype=torch.int32, device=dev)
                 lv.cnt = torch.empty((batch, m), dtype=torch.int32, device=dev)
                 c1 = sp.mlp[0]
-                ws_bytes = max(ws_bytes, lib.psa_sa_conv1_prebn_workspace_bytes(batch, n, m, c, c1, 1), lib.psa_sa_conv1_bwd_workspace_bytes(c1))
+                ws_bytes = max(ws_bytes, lib.psa_sa_conv1_prebn_workspace_bytes(batch, n, m, c, c1, 1), lib.psa_sa_conv1_bwd_workspace_bytes(batch, n, m, k, c1, 1 if c else 0))
                 if c:
                     lv.dU = torch.empty((batch * n, c1), **f32)
                     lv.d_in = torch.empty((batch * n, c), **f32)
@@ -334,8 +334,8 @@ class PointNet2ClsTrainer:
             self._c(lib.psa_train_dense_bwd_weight(ly.rows, ly.K, ly.N, C.byref(a_in), C.byref(g), _p(ly.dW), _p(self.ws), C.c_size_t(self.ws_bytes),
                                                    _stream()), "train_dense_bwd_weight")
         if dx is not None:
-            self._c(lib.psa_train_dense_bwd_input(ly.rows, ly.K, ly.N, C.byref(g), _p(ly.W), _p(dx), dx.shape[-1], col_skip, _stream()),
-                    "train_dense_bwd_input")
+            self._c(lib.psa_train_dense_bwd_input(ly.rows, ly.K, ly.N, C.byref(g), _p(ly.W), _p(dx), dx.shape[-1], col_skip, _p(self.ws),
+                                                  C.c_size_t(self.ws_bytes), _stream()), "train_dense_bwd_input")
 
     def backward(self, dlogits: torch.Tensor):
         """Gradients of every trainable variable for d(loss)/d(logits) = dlogits, into the flat gradient bucket."""
@@ -387,8 +387,8 @@ class PointNet2ClsTrainer:
                     wf = L0.W[3:]
                     self._c(lib.psa_train_dense_bwd_weight(B * lv.n, lv.c_in, L0.N, C.byref(_raw_in(pts)), C.byref(gU), _p(L0.dW[3:]), _p(self.ws),
                                                            C.c_size_t(self.ws_bytes), _stream()), "train_dense_bwd_weight")
-                    self._c(lib.psa_train_dense_bwd_input(B * lv.n, lv.c_in, L0.N, C.byref(gU), _p(wf), _p(lv.d_in), lv.c_in, 0, _stream()),
-                            "train_dense_bwd_input")
+                    self._c(lib.psa_train_dense_bwd_input(B * lv.n, lv.c_in, L0.N, C.byref(gU), _p(wf), _p(lv.d_in), lv.c_in, 0, _p(self.ws),
+                                                          C.c_size_t(self.ws_bytes), _stream()), "train_dense_bwd_input")
             dpool = lv.d_in
 
     # ------------------------------------------------------------------------------------------------

@@ -8,7 +8,8 @@ import torch
 from oracle import mlp_oracle as mo
 from oracle import oracle as orc
 from scanobjectnn_b200 import ops, pointnet2_cls_ssg
-from scanobjectnn_b200.pointnet_util import add_fp_module_params, add_sa_module_params, pointnet_fp_module, pointnet_sa_module
+from scanobjectnn_b200.pointnet_util import (add_fp_module_params, add_sa_module_msg_params, add_sa_module_params, pointnet_fp_module,
+                                              pointnet_sa_module, pointnet_sa_module_msg)
 from scanobjectnn_b200.synthetic import make_clouds
 from scanobjectnn_b200.tf_util import VariableStore
 
@@ -95,6 +96,42 @@ def test_sa_module_unit_scale_absolute_bound(n, m, r, k, c, mlp, mlp_mode):
     err = np.abs(G.npy(got) - want).max()
     print(f"unit-scale sa_module[{mlp_mode}] max|err|={err:.3e} (absolute bound 1e-5)")
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("pooling,mlp2", [("avg", None), ("weighted_avg", None), ("max_and_avg", [64]), ("max", [96, 32])])
+def test_sa_module_pooling_modes_and_post_mlp(pooling, mlp2):
+    """pointnet_sa_module's other pooling modes and the mlp2 post-MLP (pointnet_util.py:126-157)"""
+    n, m, r, k, c, mlp = 512, 64, 0.35, 24, 16, [32, 64]
+    p = _store(11)
+    cl = add_sa_module_params(p, "sa", 3 + c, mlp, randomize_bn=True)
+    if mlp2 is not None:
+        cin = 2 * cl if pooling == "max_and_avg" else cl
+        for i, co in enumerate(mlp2):
+            p.add_conv2d(f"sa/conv_post_{i}", cin, co, bn=True, randomize_bn=True)
+            cin = co
+    rng = np.random.default_rng(5)
+    xyz = make_clouds("ball", 2, n, seed=21)
+    pts = rng.standard_normal((2, n, c)).astype(np.float32)
+    new_xyz, got, idx = pointnet_sa_module(G.cu(xyz), G.cu(pts), m, r, k, mlp, mlp2, False, False, None, "sa", pooling=pooling, params=p)
+    oxyz, want, oidx = mo.sa_module(xyz, pts, m, r, k, mlp, False, "sa", p, pooling=pooling, mlp2=mlp2)
+    assert np.array_equal(G.npy(new_xyz), oxyz) and np.array_equal(G.npy(idx), oidx)
+    G.contract_close(G.npy(got), want, f"sa_module pooling={pooling} mlp2={mlp2}")
+
+
+@pytest.mark.parametrize("c", [0, 32])
+def test_sa_module_msg_matches_fp64(c):
+    """multi-scale grouping (pointnet_util.py:156-196): rows are [features, xyz] there; the fused kernel gets the rotated weights"""
+    n, m = 1024, 128
+    radii, ks, mlps = [0.1, 0.2, 0.4], [16, 32, 64], [[32, 32, 64], [64, 64, 128], [64, 96, 128]]
+    p = _store(13 + c)
+    total = add_sa_module_msg_params(p, "msg", 3 + c, mlps, randomize_bn=True)
+    rng = np.random.default_rng(c)
+    xyz = make_clouds("shell", 2, n, seed=31)
+    pts = rng.standard_normal((2, n, c)).astype(np.float32) if c else None
+    new_xyz, got = pointnet_sa_module_msg(G.cu(xyz), G.cu(pts) if c else None, m, radii, ks, mlps, False, None, "msg", params=p)
+    oxyz, want = mo.sa_module_msg(xyz, pts, m, radii, ks, mlps, "msg", p)
+    assert got.shape == (2, m, total) and np.array_equal(G.npy(new_xyz), oxyz)
+    G.contract_close(G.npy(got), want, f"sa_module_msg c={c}")
 
 
 def test_sa_module_unfused_paths_agree():

@@ -69,11 +69,11 @@ def test_dense_forward_backward_products(rows, K, N):
     dyd = G.cu(dy)
     g = _plain_grad(dyd)
     dx = torch.empty((rows, K), device="cuda")
-    assert lib.psa_train_dense_bwd_input(rows, K, N, C.byref(g), _vp(Wd), _vp(dx), K, 0, _st()) == 0
+    assert lib.psa_train_dense_bwd_input(rows, K, N, C.byref(g), _vp(Wd), _vp(dx), K, 0, _vp(ws), C.c_size_t(need), _st()) == 0
     assert _rel(G.npy(dx), dy.astype(np.float64) @ W.astype(np.float64).T) < 2e-6
     if K > 3:
         dxs = torch.empty((rows, K - 3), device="cuda")
-        assert lib.psa_train_dense_bwd_input(rows, K, N, C.byref(g), _vp(Wd), _vp(dxs), K - 3, 3, _st()) == 0
+        assert lib.psa_train_dense_bwd_input(rows, K, N, C.byref(g), _vp(Wd), _vp(dxs), K - 3, 3, _vp(ws), C.c_size_t(need), _st()) == 0
         assert _rel(G.npy(dxs), (dy.astype(np.float64) @ W.astype(np.float64).T)[:, 3:]) < 2e-6
     dW = torch.empty((K, N), device="cuda")
     assert lib.psa_train_dense_bwd_weight(rows, K, N, C.byref(a), C.byref(g), _vp(dW), _vp(ws), C.c_size_t(need), _st()) == 0
@@ -130,7 +130,7 @@ def test_bn_relu_pool_layer_backward(groups, pool_k, Cc):
     # dy through an identity-weight input-gradient product
     eye = torch.eye(Cc, device="cuda")
     dy = f(rows, Cc)
-    assert lib.psa_train_dense_bwd_input(rows, Cc, Cc, C.byref(g), _vp(eye), _vp(dy), Cc, 0, _st()) == 0
+    assert lib.psa_train_dense_bwd_input(rows, Cc, Cc, C.byref(g), _vp(eye), _vp(dy), Cc, 0, None, C.c_size_t(0), _st()) == 0
     assert _rel(G.npy(dy), dy64) < GTOL
     # dense dz source: same layer fed with the materialised dh
     dhd = G.cu(dh64.reshape(rows, Cc).astype(np.float32))
@@ -154,7 +154,7 @@ def test_first_layer_backward_ordered_group_point_grad():
     g = _plain_grad(dyd)
     dW = torch.empty((3, c1), device="cuda")
     dU = torch.empty((b * n, c1), device="cuda")
-    need = lib.psa_sa_conv1_bwd_workspace_bytes(c1)
+    need = lib.psa_sa_conv1_bwd_workspace_bytes(b, n, m, k, c1, 1)
     ws = torch.empty(need // 4 + 16, device="cuda")
     xyz_d, new_d, idx_d = G.cu(xyz), G.cu(new_xyz), G.cu(idx)       # named: the pointers must outlive the launches
     args = (b, n, m, k, c1, _vp(xyz_d), _vp(new_d), _vp(idx_d), C.byref(g))
