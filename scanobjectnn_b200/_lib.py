@@ -69,6 +69,7 @@ SIGNATURES = {
     "psa_knn_topk": [_i, _i, _i, _i, _p, _p, _p],
     "psa_knn_graph": [_i, _i, _i, _i, _p, _p, _p],
     "psa_get_edge_feature": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "psa_knn_graph_ws": [_i, _i, _i, _i, _p, _p, _p, C.c_size_t, _p],
     "psa_shared_mlp": [C.c_longlong, _i, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
     "psa_sa_module_infer": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, C.POINTER(PsaMlp), _p, _p, _p, _p, C.c_size_t, _p],
     "psa_sa_conv1_prebn": [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, C.c_size_t, _p],
@@ -94,7 +95,7 @@ SIGNATURES = {
 }
 INFO_SYMBOLS = ("psa_version", "psa_last_error", "psa_sm_arch", "psa_shared_mlp_workspace_bytes",
                 "psa_sa_module_workspace_bytes", "psa_sa_conv1_prebn_workspace_bytes", "psa_sa_group_all_workspace_bytes", "psa_edgeconv_workspace_bytes",
-                "psa_train_dense_workspace_bytes", "psa_bn_bwd_workspace_bytes", "psa_sa_conv1_bwd_workspace_bytes")
+                "psa_train_dense_workspace_bytes", "psa_bn_bwd_workspace_bytes", "psa_sa_conv1_bwd_workspace_bytes", "psa_knn_graph_workspace_bytes")
 
 _lib = None
 
@@ -129,6 +130,8 @@ def load() -> C.CDLL:
     lib.psa_bn_bwd_workspace_bytes.restype = C.c_size_t
     lib.psa_sa_conv1_bwd_workspace_bytes.argtypes = [_i, _i, _i, _i, _i, _i]
     lib.psa_sa_conv1_bwd_workspace_bytes.restype = C.c_size_t
+    lib.psa_knn_graph_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.psa_knn_graph_workspace_bytes.restype = C.c_size_t
     lib.psa_version.restype = C.c_int
     lib.psa_sm_arch.restype = C.c_int
     lib.psa_last_error.restype = C.c_char_p

@@ -430,16 +430,19 @@ __device__ __forceinline__ int bq_extract_bitmap(unsigned* __restrict__ bitmap, 
     return cnt;
 }
 
-// Eight lanes per query, four queries per warp at once: the nsample lowest set bits of a bitmap of `words` words (a multiple
-// of 8; lane `sub` of the group owns words [sub*words/8, (sub+1)*words/8)) in ascending order -> idxrow[0..cnt), rest filled
+// Eight lanes per query, four queries per warp at once: the nsample lowest set bits of a bitmap of 8*WPS words (lane `sub`
+// of the group owns words [sub*WPS, (sub+1)*WPS), read ONCE into registers) in ascending order -> idxrow[0..cnt), rest filled
 // with the first hit (0 if none).  Every lane of the warp must call (shuffles); groups with active == false do nothing else.
-__device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict__ bitmap, int words, int nsample, int* __restrict__ idxrow,
-                                                      int lane, bool active) {
+template <int WPS>
+__device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict__ bitmap, int nsample, int* __restrict__ idxrow, int lane, bool active) {
     const int sub = lane & 7;
-    const int wps = words >> 3;                      // words per lane: 4 (n <= 1024), 8 (n <= 2048), 16 (n <= 4096)
+    unsigned w[WPS];
     int c = 0;
-    if (active)
-        for (int i = 0; i < wps; ++i) c += __popc(bitmap[sub * wps + i]);
+#pragma unroll
+    for (int i = 0; i < WPS; ++i) {
+        w[i] = active ? bitmap[sub * WPS + i] : 0u;
+        c += __popc(w[i]);
+    }
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -449,21 +452,19 @@ __device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict
     const int total = __shfl_sync(0xffffffffu, incl, 7, 8);
     const unsigned have = (__ballot_sync(0xffffffffu, c > 0) >> (lane & 24)) & 0xffu;
     int firstbit = 0;
-    if (active && c > 0) {
-        for (int i = wps - 1; i >= 0; --i) {
-            const unsigned w = bitmap[sub * wps + i];
-            if (w != 0u) firstbit = (sub * wps + i) * 32 + __ffs(w) - 1;
-        }
-    }
+#pragma unroll
+    for (int i = WPS - 1; i >= 0; --i)
+        if (w[i] != 0u) firstbit = (sub * WPS + i) * 32 + __ffs(w[i]) - 1;
     const int first = __shfl_sync(0xffffffffu, firstbit, have ? __ffs(have) - 1 : 0, 8);
     if (!active) return 0;
     int pos = incl - c;
-    for (int i = 0; i < wps && pos < nsample; ++i) {
-        unsigned x = bitmap[sub * wps + i];
+#pragma unroll
+    for (int i = 0; i < WPS; ++i) {
+        unsigned x = w[i];
         while (x != 0u && pos < nsample) {
             const int bit = __ffs(x) - 1;
             x &= x - 1u;
-            idxrow[pos++] = (sub * wps + i) * 32 + bit;
+            idxrow[pos++] = (sub * WPS + i) * 32 + bit;
         }
     }
     const int cnt = min(total, nsample);

@@ -1,0 +1,394 @@
+// knn_tc.cu -- DGCNN's kNN graph (pairwise_distance + top_k, dgcnn/utils/tf_util.py:638-671) with the X.X^T contraction on
+// the tcgen05 tensor cores and an EXACT refine, so the neighbour indices stay bit-identical to the canonical fp32 evaluation
+// (oracle/psa_oracle.c orc_dgcnn_knn: dot as an fma chain over the channels, adj = (|p|^2 + (-2 dot)) + |q|^2, k smallest,
+// lower index first on ties).
+//
+//   prep      every point row is split once into three bf16 pieces and laid out as [128 rows][64 k] K-major SWIZZLE_128B
+//             blocks (the weight-image layout of tc_mlp.cu), + the canonical |x|^2 per row;
+//   main      CTA = 128 query rows of one cloud (TMEM lane = query row).  The query block is the A operand, candidate blocks
+//             stream through a two-stage ring (cp.async.bulk) as the B operand, D[128 x 128] = G tile in TMEM, two D slots.
+//             Thread q owns row q and reads ITS distances with tcgen05.ld -- selection needs no cross-lane traffic:
+//     pass 1  one bf16 MMA term (4 MMAs per tile): coarse distances (error <= E1) -> per-row histogram over logarithmic bins
+//             (float exponent + 4 mantissa bits) in shared memory -> tau = upper edge of the bin that holds the k-th smallest;
+//     pass 2  six MMA terms (bf16x3, error <= E2): every candidate with d < tau + E1 + E2 -- a superset of the true top-k --
+//             is appended to the row's list (typically k + 10..30 entries);
+//     refine  canonical fp32 distances of the listed candidates only, then k rounds of lexicographic (d, index) minimum.
+//   fallback  rows whose list overflows (many equidistant points) or whose cloud holds non-finite values are written to a
+//             worklist and done exhaustively in fp32 by knn_rows_exact_kernel (same canonical arithmetic).
+#include <float.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace psa {
+using namespace tc;
+
+constexpr int kKtThreads = 160;                   // 4 row warps + 1 issuer warp
+constexpr uint32_t kKtPiece = 128u * 128u;        // one bf16 piece of a [128 rows][64 k] block: 16 KB
+constexpr uint32_t kKtBlock = 3u * kKtPiece;      // 48 KB
+constexpr int kKtBins = 256;
+constexpr int kKtCap = 96;                        // list entries per row
+constexpr int kKtMaxN = 2048;                     // candidates per cloud on this path (shared-memory budget)
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- prep: thread = point row ----
+__global__ void __launch_bounds__(128) knn_prep_kernel(int n, int npad, int c, const float* __restrict__ x, uint8_t* __restrict__ image,
+                                                       float* __restrict__ sq) {
+    const int cloud = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x;
+    const int r = rb * 128 + tid;
+    uint8_t* blk = image + ((size_t)cloud * (npad / 128) + rb) * kKtBlock;
+    float s = 0.f;
+    const float* xr = x + ((size_t)cloud * n + r) * c;
+    for (int l = 0; l < 64; ++l) {
+        float v = 0.f;
+        if (r < n && l < c) { v = __ldg(xr + l); s = fmaf(v, v, s); }
+        const __nv_bfloat16 c1 = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(c1);
+        const __nv_bfloat16 c2 = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(c2);
+        const __nv_bfloat16 c3 = __float2bfloat16_rn(r2);
+        const uint32_t off = swz_off_bf16((uint32_t)tid, (uint32_t)l, 128u);
+        *reinterpret_cast<__nv_bfloat16*>(blk + off) = c1;
+        *reinterpret_cast<__nv_bfloat16*>(blk + kKtPiece + off) = c2;
+        *reinterpret_cast<__nv_bfloat16*>(blk + 2u * kKtPiece + off) = c3;
+    }
+    sq[(size_t)cloud * npad + r] = r < n ? s : __int_as_float(0x7f800000);
+}
+
+struct KnnTcArgs {
+    int n, npad, c, k;
+    const float* x;
+    const uint8_t* image;
+    const float* sq;
+    int* nn_idx;
+    int* flag_rows;            // (b * n) worklist of global row ids for the exhaustive kernel
+    unsigned* flag_count;
+};
+
+// canonical distance of the oracle: dot = fma chain over the channels, adj = (sq_p + (-2 dot)) + sq_q
+__device__ __forceinline__ float knn_canonical(const float* __restrict__ xp, const float* __restrict__ xq, int c, float sqp, float sqq) {
+    float dot = 0.f;
+    if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(xq)) & 15) == 0) {
+        for (int l = 0; l < c; l += 4) {                 // same ascending-channel fma chain, 16-byte loads
+            const float4 u = __ldg(reinterpret_cast<const float4*>(xp + l)), v = __ldg(reinterpret_cast<const float4*>(xq + l));
+            dot = fmaf(u.x, v.x, dot); dot = fmaf(u.y, v.y, dot); dot = fmaf(u.z, v.z, dot); dot = fmaf(u.w, v.w, dot);
+        }
+    } else {
+        for (int l = 0; l < c; ++l) dot = fmaf(__ldg(xp + l), __ldg(xq + l), dot);
+    }
+    return __fadd_rn(__fadd_rn(sqp, __fmul_rn(-2.0f, dot)), sqq);
+}
+
+__global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_constant__ KnnTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_qfull, s_full[2], s_dfull[2], s_dfree[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_wmax[5];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
+    const int cloud = blockIdx.y;
+    const int n = a.n, npad = a.npad, NT = npad / 128;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* qblk = base;                                        // 48 KB
+    uint8_t* cstage = base + kKtBlock;                           // 2 x 48 KB
+    float* s_sq = reinterpret_cast<float*>(base + 3 * kKtBlock); // npad floats
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(s_sq + npad);  // pass 1: u16 hist[256][128]; pass 2: u16 idx[96][128] | float adj[96][128]
+    unsigned short* hist = reinterpret_cast<unsigned short*>(scratch);
+    unsigned short* lidx = reinterpret_cast<unsigned short*>(scratch);
+    float* ladj = reinterpret_cast<float*>(scratch + (size_t)kKtCap * 128 * 2);
+    const uint8_t* img = a.image + (size_t)cloud * NT * kKtBlock;
+    const float* sqc = a.sq + (size_t)cloud * npad;
+
+    if (warp_u == 4) tmem_alloc(&s_tmem, 256);
+    if (tid == 0) {
+        mbar_init(&s_qfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_dfull[i], 1); mbar_init(&s_dfree[i], 4); }
+        fence_mbar_init();
+    }
+    // candidate norms -> shared memory; the cloud's largest finite-or-not norm over the real points
+    float mx = 0.f;
+    for (int i = tid; i < npad; i += kKtThreads) {
+        const float v = __ldg(sqc + i);
+        s_sq[i] = v;
+        if (i < n) mx = fmaxf(mx, fabsf(v) <= FLT_MAX ? v : __int_as_float(0x7f800000));     // NaN -> +inf: the cloud is flagged
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_wmax[warp_u] = mx;
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = warp_uniform(s_tmem);
+    const int J = 2 * NT;                            // jobs: pass 0 tiles, then pass 1 tiles
+
+    if (warp_u == 4) {
+        // ================= issuer / loader warp =================
+        auto load = [&](int j) {
+            const int s = j & 1, t = j % NT;
+            const uint32_t bytes = j < NT ? kKtPiece : kKtBlock;                   // pass 0 needs the leading piece only
+            if (lane == 0) {
+                mbar_expect_tx(&s_full[s], bytes);
+                for (uint32_t o = 0; o < bytes; o += 16384u) bulk_g2s(cstage + (uint32_t)s * kKtBlock + o, img + (size_t)t * kKtBlock + o, 16384u, &s_full[s]);
+            }
+        };
+        if (lane == 0) {
+            mbar_expect_tx(&s_qfull, kKtBlock);
+            for (uint32_t o = 0; o < kKtBlock; o += 16384u) bulk_g2s(qblk + o, img + (size_t)blockIdx.x * kKtBlock + o, 16384u, &s_qfull);
+        }
+        load(0);
+        if (J > 1) load(1);
+        mbar_wait(&s_qfull, 0);
+        const uint32_t idesc = make_idesc(kFmtBF16, 128, 128);
+        constexpr uint32_t qp[6] = {0, 1, 2, 0, 1, 0};       // query piece / candidate piece of the six terms, small products first
+        constexpr uint32_t cp[6] = {2, 1, 0, 1, 0, 0};
+        const SmemDescBase qa = smem_desc_base(warp_uniform(smem_u32(qblk)));
+        for (int j = 0; j < J; ++j) {
+            const int s = j & 1;
+            const uint32_t par = (uint32_t)((j >> 1) & 1);
+            mbar_wait(&s_full[s], par);
+            if (j >= 2) mbar_wait(&s_dfree[s], (uint32_t)(((j - 2) >> 1) & 1));      // rows finished reading this D slot
+            __syncwarp();
+            fence_after_thread_sync();
+            const uint32_t d = tmem_base + (uint32_t)s * 128u;
+            const SmemDescBase cb = smem_desc_base(warp_uniform(smem_u32(cstage) + (uint32_t)s * kKtBlock));
+            if (j < NT) {
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) mma_bf16_ss(d, smem_desc_at(qa, s4 * 32), smem_desc_at(cb, s4 * 32), idesc, s4 ? 1u : 0u);
+            } else {
+#pragma unroll
+                for (int t6 = 0; t6 < 6; ++t6)
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        mma_bf16_ss(d, smem_desc_at(qa, qp[t6] * kKtPiece + s4 * 32), smem_desc_at(cb, cp[t6] * kKtPiece + s4 * 32), idesc, (t6 | s4) ? 1u : 0u);
+            }
+            mma_commit(&s_dfull[s]);
+            if (j + 2 < J) {
+                mbar_wait(&s_dfull[s], par);             // this stage's operands are consumed: refill it two jobs ahead
+                load(j + 2);
+            }
+        }
+    } else {
+        // ================= row threads: thread = query row =================
+        const int q = blockIdx.x * 128 + tid;
+        const bool valid = q < n;
+        const float sqmax = fmaxf(fmaxf(fmaxf(s_wmax[0], s_wmax[1]), fmaxf(s_wmax[2], s_wmax[3])), s_wmax[4]);
+        const float sqq = s_sq[valid ? q : 0];
+        bool ok = valid && fabsf(sqq) <= FLT_MAX && fabsf(sqmax) <= FLT_MAX;
+        const float sgeo = sqrtf(sqq * sqmax);
+        const float dmax = 2.0f * (sqq + sqmax);
+        const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp_u * 32) << 16);
+        for (int b = 0; b < kKtBins; ++b) hist[b * 128 + tid] = 0;
+        // ---- pass 1: coarse distances -> histogram ----
+        for (int t = 0; t < NT; ++t) {
+            const int s = t & 1;
+            mbar_wait(&s_dfull[s], (uint32_t)((t >> 1) & 1));
+            fence_after_thread_sync();
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t d[32];
+                tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
+                tmem_ld_wait();
+                const float* sc = s_sq + t * 128 + ch * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
+                    const int key = (int)(__float_as_uint(fmaxf(dist, 1e-30f)) >> 19);      // NaN -> 1e-30: lands in the last bin
+                    const int bin = min(max(keymax - key, 0), kKtBins - 1);
+                    hist[bin * 128 + tid] += 1;
+                }
+            }
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&s_dfree[s]);
+        }
+        // ---- threshold: upper edge of the bin that holds the k-th smallest coarse distance, widened by the error bounds ----
+        float T;
+        {
+            int cum = 0, b = kKtBins - 1;
+            for (; b >= 0; --b) { cum += hist[b * 128 + tid]; if (cum >= a.k) break; }
+            const float tau = b < 0 ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(keymax - b + 1) << 19);
+            // |coarse - exact| <= E1 (one bf16 term: 2^-8 relative on every product), |fine - exact| <= E2 (bf16x3 + fp32 sums)
+            const float E1 = 0.01f * sgeo, E2 = 1e-4f * sgeo + 2e-6f * (sqq + sqmax);
+            T = tau + E1 + E2 + 1e-6f * tau;
+        }
+        // every row thread is done with its histogram before anybody's candidate list / distances overwrite the scratch area
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        // ---- pass 2: fine distances -> candidate list ----
+        int cnt = 0;
+        for (int t = 0; t < NT; ++t) {
+            const int j = NT + t, s = j & 1;
+            mbar_wait(&s_dfull[s], (uint32_t)((j >> 1) & 1));
+            fence_after_thread_sync();
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t d[32];
+                tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
+                tmem_ld_wait();
+                const float* sc = s_sq + t * 128 + ch * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
+                    if (dist < T) {
+                        if (cnt < kKtCap) lidx[cnt * 128 + tid] = (unsigned short)(t * 128 + ch * 32 + i);
+                        ++cnt;
+                    }
+                }
+            }
+            fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&s_dfree[s]);
+        }
+        if (valid && (!ok || cnt > kKtCap || cnt < a.k)) {
+            // exhaustive kernel takes this row (overflow: many equidistant candidates; non-finite coordinates; or fewer than k real points below T)
+            a.flag_rows[atomicAdd(a.flag_count, 1u)] = cloud * n + q;
+            ok = false;
+        }
+        if (ok) {
+            // ---- refine: canonical fp32 distances of the listed candidates ----
+            const float* xc = a.x + (size_t)cloud * n * a.c;
+            const float* xq = xc + (size_t)q * a.c;
+            for (int e = 0; e < cnt; ++e) {
+                const int col = lidx[e * 128 + tid];
+                ladj[e * 128 + tid] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
+            }
+            // ---- k rounds of lexicographic (distance, index) minimum: ascending distance, lower index first on ties ----
+            float pd = -__int_as_float(0x7f800000);
+            int pi = -1;
+            int* out = a.nn_idx + ((size_t)cloud * n + q) * a.k;
+            for (int r = 0; r < a.k; ++r) {
+                float bd = __int_as_float(0x7f800000);
+                int bi = 0x7fffffff;
+                for (int e = 0; e < cnt; ++e) {
+                    const float dd = ladj[e * 128 + tid];
+                    const int ii = lidx[e * 128 + tid];
+                    const bool after = dd > pd || (dd == pd && ii > pi);
+                    const bool better = dd < bd || (dd == bd && ii < bi);
+                    if (after && better) { bd = dd; bi = ii; }
+                }
+                out[r] = bi;
+                pd = bd; pi = bi;
+            }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp_u == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ---- exhaustive rows (worklist): one warp per row, canonical distances of all n candidates in shared memory, then k rounds of
+// lexicographic minimum.  NaN distances are never selected ahead of numbers (the oracle's `row[q] < row[best]` is false for them).
+constexpr int kKxWarps = 4;
+__global__ void __launch_bounds__(kKxWarps * 32) knn_rows_exact_kernel(int n, int c, int k, const float* __restrict__ x, const float* __restrict__ sq,
+                                                                      int npad, const int* __restrict__ rows, const unsigned* __restrict__ count,
+                                                                      int* __restrict__ nn_idx) {
+    extern __shared__ float sm_d[];                  // kKxWarps x n
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* dist = sm_d + (size_t)warp * n;
+    const unsigned total = *count;
+    for (unsigned w = blockIdx.x * kKxWarps + warp; w < total; w += gridDim.x * kKxWarps) {
+        const int row = rows[w];
+        const int cloud = row / n, p = row - cloud * n;
+        const float* xc = x + (size_t)cloud * n * c;
+        const float* sqc = sq + (size_t)cloud * npad;
+        const float sqp = __ldg(sqc + p);
+        for (int qd = lane; qd < n; qd += 32) dist[qd] = knn_canonical(xc + (size_t)p * c, xc + (size_t)qd * c, c, sqp, __ldg(sqc + qd));
+        __syncwarp();
+        int* out = nn_idx + (size_t)row * k;
+        // the oracle scans q ascending keeping the first strict minimum among the untaken: equal values -> lowest index; a NaN
+        // candidate is only ever chosen when it is the first untaken entry and nothing compares below it
+        unsigned long long taken_lo = 0ull;          // (the general "taken" set lives in the NaN-free ordering below)
+        (void)taken_lo;
+        float pd = -__int_as_float(0x7f800000);
+        int pi = -1;
+        for (int r = 0; r < k; ++r) {
+            float bd = __int_as_float(0x7f800000);
+            int bi = 0x7fffffff;
+            for (int qd = lane; qd < n; qd += 32) {
+                const float dd = dist[qd];
+                const bool after = dd > pd || (dd == pd && qd > pi);
+                const bool better = dd < bd || (dd == bd && qd < bi);
+                if (after && better) { bd = dd; bi = qd; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi == 0x7fffffff) {
+                // only +inf / NaN entries remain beyond (pd, pi): take the lowest untaken index (the oracle's scan order)
+                int cand = 0x7fffffff;
+                for (int qd = lane; qd < n; qd += 32) {
+                    const float dd = dist[qd];
+                    const bool fin_after = dd > pd || (dd == pd && qd > pi);
+                    bool used = false;
+                    for (int u = 0; u < r; ++u) used = used || (out[u] == qd);
+                    if (!used && !(fin_after && dd < __int_as_float(0x7f800000))) cand = min(cand, qd);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+                bi = cand;
+                bd = __int_as_float(0x7f800000);
+            }
+            if (lane == 0) out[r] = bi;
+            __syncwarp();
+            pd = bd; pi = bi;
+        }
+        __syncwarp();
+    }
+}
+
+static size_t knn_tc_smem_bytes(int npad) {
+    return 1024 + 3 * (size_t)kKtBlock + (size_t)npad * 4 + (size_t)kKtCap * 128 * 2 + (size_t)kKtCap * 128 * 4 + 64;
+}
+
+bool knn_tc_eligible(int n, int c, int k) { return n >= 128 && n <= kKtMaxN && c >= 1 && c <= 64 && k >= 1 && k <= 64 && k <= n; }
+
+}  // namespace psa
+
+using namespace psa;
+
+extern "C" size_t psa_knn_graph_workspace_bytes(int b, int n, int c, int k) {
+    if (!knn_tc_eligible(n, c, k)) return 0;
+    const int npad = (n + 127) / 128 * 128;
+    return (size_t)b * (npad / 128) * kKtBlock + (((size_t)b * npad * 4 + 255) & ~(size_t)255) + (((size_t)b * n * 4 + 255) & ~(size_t)255) + 256;
+}
+
+// fp32 kernel of graph.cu (no workspace)
+extern "C" int psa_knn_graph(int b, int n, int c, int k, const float* x, int* nn_idx, psa_stream_t stream);
+
+extern "C" int psa_knn_graph_ws(int b, int n, int c, int k, const float* x, int* nn_idx, void* workspace, size_t workspace_bytes,
+                                psa_stream_t stream) {
+    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0 && k >= 0, "knn_graph: negative dimension");
+    if (b == 0 || n == 0 || k == 0) return PSA_OK;
+    const size_t need = psa_knn_graph_workspace_bytes(b, n, c, k);
+    if (need == 0 || workspace == nullptr || workspace_bytes < need || b > 65535) return psa_knn_graph(b, n, c, k, x, nn_idx, stream);
+    PSA_REQUIRE(x && nn_idx, "knn_graph: null buffer");
+    cudaStream_t st = as_stream(stream);
+    const int npad = (n + 127) / 128 * 128, NT = npad / 128;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    uint8_t* image = ws;
+    ws += (size_t)b * NT * kKtBlock;
+    float* sq = reinterpret_cast<float*>(ws);
+    ws += ((size_t)b * npad * 4 + 255) & ~(size_t)255;
+    int* flag_rows = reinterpret_cast<int*>(ws);
+    ws += ((size_t)b * n * 4 + 255) & ~(size_t)255;
+    unsigned* flag_count = reinterpret_cast<unsigned*>(ws);
+    PSA_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(unsigned), st));
+    knn_prep_kernel<<<dim3(NT, b), 128, 0, st>>>(n, npad, c, x, image, sq);
+    int rc = check_launch("knn_prep_kernel");
+    if (rc != PSA_OK) return rc;
+    KnnTcArgs a;
+    a.n = n; a.npad = npad; a.c = c; a.k = k; a.x = x; a.image = image; a.sq = sq; a.nn_idx = nn_idx; a.flag_rows = flag_rows; a.flag_count = flag_count;
+    const size_t smem = knn_tc_smem_bytes(npad);
+    PSA_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_tc_kernel<<<dim3(NT, b), kKtThreads, smem, st>>>(a);
+    rc = check_launch("knn_tc_kernel");
+    if (rc != PSA_OK) return rc;
+    const size_t xsmem = (size_t)kKxWarps * n * sizeof(float);
+    PSA_CUDA(cudaFuncSetAttribute(knn_rows_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsmem));
+    knn_rows_exact_kernel<<<2 * kNumSMs, kKxWarps * 32, xsmem, st>>>(n, c, k, x, sq, npad, flag_rows, flag_count, nn_idx);
+    return check_launch("knn_rows_exact_kernel");
+}

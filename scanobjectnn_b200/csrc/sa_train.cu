@@ -202,7 +202,7 @@ __host__ __device__ inline int f1s_num_batches(long long nq) {
 
 // shared memory: cloud as float4 (x,y,z,bits(k)) | kF1Batch bitmaps of bw words | ring slots (idx rows | centred rows)
 __host__ __device__ inline int f1s_bitmap_words(int np, int pptp) { const int w = np * pptp; return w < 32 ? 32 : w; }
-__host__ __device__ inline size_t f1s_slot_bytes(int nsample) { return (size_t)kF1Batch * nsample * (sizeof(int) + sizeof(float4)); }
+__host__ __device__ inline size_t f1s_slot_bytes(int nsample) { return (size_t)kF1Batch * nsample * (sizeof(int) + sizeof(float4)) + kF1Batch * sizeof(float4); }
 __host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, int np, int pptp) {
     size_t ring = kF1Ring * f1s_slot_bytes(nsample);
     if (ring < 8192) ring = 8192;                   // the statistics epilogue reuses the ring: up to 8 KB of partials
@@ -226,11 +226,8 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
     if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 0] = gtime();
 #endif
 
-    const int sub = lane & 7, rsub = lane >> 3;
-    constexpr int NPK = 2 * NV;
-    float2 ssum[NPK], ssq[NPK];
-#pragma unroll
-    for (int p = 0; p < NPK; ++p) ssum[p] = ssq[p] = make_float2(0.f, 0.f);
+    float2 ssum[2], ssq[2];                                // this lane's four channels (consumers)
+    ssum[0] = ssum[1] = ssq[0] = ssq[1] = make_float2(0.f, 0.f);
 
     const long long T = (long long)a.b * a.m;
     const long long q_begin = T * blockIdx.x / gridDim.x, q_end = T * (blockIdx.x + 1) / gridDim.x;
@@ -278,21 +275,32 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                 int* sidx = reinterpret_cast<int*>(ring + slot * slot_bytes);
                 float4* sd = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
                 const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
+                float4* sctr = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * (sizeof(int) + sizeof(float4)));
+                // the batch's query centres: lane i of every producer warp loads query i ONCE (one global round trip per batch,
+                // not one per query), the search reads them through shuffles, the row builder through shared memory
+                float cqx = 0.f, cqy = 0.f, cqz = 0.f;
+                if (lane < nqb) {
+                    const float* p2 = a.new_xyz + (size_t)(gq0 + lane) * 3;
+                    cqx = __ldg(p2); cqy = __ldg(p2 + 1); cqz = __ldg(p2 + 2);
+                    if (warp == 0) sctr[lane] = make_float4(cqx, cqy, cqz, 0.f);
+                }
                 // ---- exhaustive test: one ballot per 32-point word = that word of the query's bitmap ----
                 if (!a.none) {
                     for (int qi = 0; qi < nqb; ++qi) {
-                        const float* p2 = a.new_xyz + (size_t)(gq0 + qi) * 3;
-                        const float qx = __ldg(p2), qy = __ldg(p2 + 1), qz = __ldg(p2 + 2);
+                        const float qx = __shfl_sync(0xffffffffu, cqx, qi), qy = __shfl_sync(0xffffffffu, cqy, qi), qz = __shfl_sync(0xffffffffu, cqz, qi);
                         const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
                         unsigned* bm = bitmaps + qi * BW;
+                        unsigned mine = 0u;                                  // lane i keeps word i of this warp's share, stored once
 #pragma unroll
                         for (int i = 0; i < PPTP; i += 2) {
                             const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
                             // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
                             const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr) && ((valid >> i) & 1u));
                             const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr) && ((valid >> (i + 1)) & 1u));
-                            if (lane == 0) { bm[warp + NP * i] = w0; bm[warp + NP * (i + 1)] = w1; }
+                            if (lane == i) mine = w0;
+                            if (lane == i + 1) mine = w1;
                         }
+                        if (lane < PPTP) bm[warp + NP * lane] = mine;         // one store instruction per query and warp
                     }
                 }
                 named_bar_sync(15, PT);                                                     // bitmaps complete
@@ -303,7 +311,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                 for (int q0 = warp * 4; q0 < kF1Batch; q0 += NP * 4) {
                     const int qi = q0 + (lane >> 3);
                     const bool act = qi < nqb;
-                    const int cnt = bq_extract_bitmap_sub8(bitmaps + qi * BW, BW, K, sidx + qi * K, lane, act);
+                    const int cnt = bq_extract_bitmap_sub8<BW / 8>(bitmaps + qi * BW, K, sidx + qi * K, lane, act);
                     if (act && a.pts_cnt != nullptr && (lane & 7) == 0) a.pts_cnt[gq0 + qi] = cnt;
                 }
                 named_bar_sync(15, PT);                                                     // idx rows complete
@@ -315,10 +323,10 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                 int* gidx = a.idx + (size_t)gq0 * K;
                 for (int r = tid; r < nrows; r += PT) {
                     const int j = sidx[r];
-                    const float* p2 = a.new_xyz + (size_t)(gq0 + r / K) * 3;
+                    const float4 ctr = sctr[r / K];
                     const float4 pt = cloud4[j];
                     gidx[r] = j;
-                    sd[r] = make_float4(pt.x - __ldg(p2), pt.y - __ldg(p2 + 1), pt.z - __ldg(p2 + 2), __int_as_float(j));
+                    sd[r] = make_float4(pt.x - ctr.x, pt.y - ctr.y, pt.z - ctr.z, __int_as_float(j));
                 }
                 __threadfence_block();
                 named_bar_arrive(1 + slot, kF1SThreads);                                    // FULL
@@ -334,51 +342,50 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
 #endif
     } else {
         // =========================================== CONSUMERS ===========================================
+        // lane mapping: LPR = C1/4 lanes cover one row (4 consecutive channels each), so a warp store instruction writes
+        // 32/LPR whole rows = 512 contiguous bytes; a lane's channels are fixed, its weights live in registers
         const int cw = warp - NP;
-        // first-layer weights of this lane's channels, resident in registers: lane-in-row `sub` owns channels [32 i + 4 sub, +4)
-        float2 wx[NPK], wy[NPK], wz[NPK], bs[NPK];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = 32 * i + 4 * sub;
-            const float4 x4 = __ldg(reinterpret_cast<const float4*>(a.w1 + c));
-            const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + c));
-            const float4 z4 = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * C1 + c));
-            const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            wx[2 * i] = make_float2(x4.x, x4.y); wx[2 * i + 1] = make_float2(x4.z, x4.w);
-            wy[2 * i] = make_float2(y4.x, y4.y); wy[2 * i + 1] = make_float2(y4.z, y4.w);
-            wz[2 * i] = make_float2(z4.x, z4.y); wz[2 * i + 1] = make_float2(z4.z, z4.w);
-            bs[2 * i] = make_float2(b4.x, b4.y); bs[2 * i + 1] = make_float2(b4.z, b4.w);
-        }
+        constexpr int LPR = NV * 8;                    // 16 (C1 = 64) or 32 (C1 = 128)
+        constexpr int RPI = 32 / LPR;                  // rows per store instruction: 2 or 1
+        const int lr = lane / LPR, lc = (lane % LPR) * 4;
+        const float4 wx4 = __ldg(reinterpret_cast<const float4*>(a.w1 + lc));
+        const float4 wy4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + lc));
+        const float4 wz4 = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * C1 + lc));
+        const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2 wxa = make_float2(wx4.x, wx4.y), wxb = make_float2(wx4.z, wx4.w), wya = make_float2(wy4.x, wy4.y), wyb = make_float2(wy4.z, wy4.w);
+        const float2 wza = make_float2(wz4.x, wz4.y), wzb = make_float2(wz4.z, wz4.w), ba = make_float2(b4.x, b4.y), bb = make_float2(b4.z, b4.w);
         int ring_pos = 0;
         for (long long q = q_begin; q < q_end;) {
             const long long cloud = q / a.m;
             const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-            const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + 4 * sub : nullptr;
+            const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + lc : nullptr;
             long long gq0 = q;
             for (int bi = 0; gq0 < seg_end; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
                 const float4* sd = reinterpret_cast<const float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
                 const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
                 const int nrows = nqb * K;
-                float* outl = a.pre + (size_t)gq0 * K * C1 + 4 * sub;
+                float* outl = a.pre + (size_t)gq0 * K * C1 + lc;
                 named_bar_sync(1 + slot, kF1SThreads);                                      // FULL
-                for (int r = 4 * cw + rsub; r < nrows; r += 4 * NC) {
-                    const float4 d = sd[r];
-                    const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
-                    float* orow = outl + (unsigned)r * (unsigned)C1;
-                    const float* urow = HAS_U ? ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1 : nullptr;
+                // four rows per lane and trip: independent chains, stores of a warp instruction contiguous
+                for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI) {
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        float2 s0 = bs[2 * i], s1 = bs[2 * i + 1];
-                        if (HAS_U) {
-                            const float4 u = __ldg(reinterpret_cast<const float4*>(urow + 32 * i));
-                            s0 = __fadd2_rn(s0, make_float2(u.x, u.y)); s1 = __fadd2_rn(s1, make_float2(u.z, u.w));
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = r0 + u * RPI + lr;
+                        if (r < nrows) {
+                            const float4 d = sd[r];
+                            const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+                            float2 s0 = ba, s1 = bb;
+                            if (HAS_U) {
+                                const float4 uu = __ldg(reinterpret_cast<const float4*>(ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1));
+                                s0 = __fadd2_rn(s0, make_float2(uu.x, uu.y)); s1 = __fadd2_rn(s1, make_float2(uu.z, uu.w));
+                            }
+                            const float2 v0 = __ffma2_rn(dz, wza, __ffma2_rn(dy, wya, __ffma2_rn(dx, wxa, s0)));
+                            const float2 v1 = __ffma2_rn(dz, wzb, __ffma2_rn(dy, wyb, __ffma2_rn(dx, wxb, s1)));
+                            __stcs(reinterpret_cast<float4*>(outl + (unsigned)r * (unsigned)C1), make_float4(v0.x, v0.y, v1.x, v1.y));
+                            ssum[0] = __fadd2_rn(ssum[0], v0); ssum[1] = __fadd2_rn(ssum[1], v1);
+                            ssq[0] = __ffma2_rn(v0, v0, ssq[0]); ssq[1] = __ffma2_rn(v1, v1, ssq[1]);
                         }
-                        const float2 v0 = __ffma2_rn(dz, wz[2 * i], __ffma2_rn(dy, wy[2 * i], __ffma2_rn(dx, wx[2 * i], s0)));
-                        const float2 v1 = __ffma2_rn(dz, wz[2 * i + 1], __ffma2_rn(dy, wy[2 * i + 1], __ffma2_rn(dx, wx[2 * i + 1], s1)));
-                        __stcs(reinterpret_cast<float4*>(orow + 32 * i), make_float4(v0.x, v0.y, v1.x, v1.y));
-                        ssum[2 * i] = __fadd2_rn(ssum[2 * i], v0); ssum[2 * i + 1] = __fadd2_rn(ssum[2 * i + 1], v1);
-                        ssq[2 * i] = __ffma2_rn(v0, v0, ssq[2 * i]); ssq[2 * i + 1] = __ffma2_rn(v1, v1, ssq[2 * i + 1]);
                     }
                 }
                 if (ring_pos + kF1Ring < total_batches) named_bar_arrive(1 + kF1Ring + slot, kF1SThreads);   // EMPTY
@@ -394,18 +401,22 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
     if (a.stats != nullptr) {
         __syncthreads();                                   // ring memory is free: reuse it for the per-warp partials
         float* sstat = reinterpret_cast<float*>(ring);     // NC x 2 x C1
+        {
+            constexpr int LPR = NV * 8;
+            // lanes lr = 0 .. 32/LPR-1 of a warp hold partials of the same four channels: fold them, lane row 0 publishes
 #pragma unroll
-        for (int p = 0; p < NPK; ++p) {
+            for (int p = 0; p < 2; ++p) {
 #pragma unroll
-            for (int o = 8; o < 32; o <<= 1) {
-                ssum[p].x += __shfl_xor_sync(0xffffffffu, ssum[p].x, o); ssum[p].y += __shfl_xor_sync(0xffffffffu, ssum[p].y, o);
-                ssq[p].x += __shfl_xor_sync(0xffffffffu, ssq[p].x, o); ssq[p].y += __shfl_xor_sync(0xffffffffu, ssq[p].y, o);
-            }
-            if (warp >= NP && rsub == 0) {
-                float* w = sstat + (size_t)(warp - NP) * 2 * C1;
-                const int c = 32 * (p >> 1) + 4 * sub + 2 * (p & 1);
-                *reinterpret_cast<float2*>(w + c) = ssum[p];
-                *reinterpret_cast<float2*>(w + C1 + c) = ssq[p];
+                for (int o = LPR; o < 32; o <<= 1) {
+                    ssum[p].x += __shfl_xor_sync(0xffffffffu, ssum[p].x, o); ssum[p].y += __shfl_xor_sync(0xffffffffu, ssum[p].y, o);
+                    ssq[p].x += __shfl_xor_sync(0xffffffffu, ssq[p].x, o); ssq[p].y += __shfl_xor_sync(0xffffffffu, ssq[p].y, o);
+                }
+                if (warp >= NP && lane < LPR) {
+                    float* w = sstat + (size_t)(warp - NP) * 2 * C1;
+                    const int c = lane * 4 + 2 * p;
+                    *reinterpret_cast<float2*>(w + c) = ssum[p];
+                    *reinterpret_cast<float2*>(w + C1 + c) = ssq[p];
+                }
             }
         }
         __syncthreads();

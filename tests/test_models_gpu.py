@@ -52,9 +52,8 @@ def test_fp_module_with_single_known_point_broadcasts():
     assert torch.equal(w, torch.tensor([1.0, 0.0, 0.0], device="cuda").expand(2, 128, 3))
 
 
-@pytest.mark.parametrize("bga", [False, True])
-def test_dgcnn_stagewise_matches_oracle(bga):
-    n = 512
+@pytest.mark.parametrize("bga,n", [(False, 512), (True, 512), (False, 2048)])      # 2048 = BASELINE.json configs[2]
+def test_dgcnn_stagewise_matches_oracle(bga, n):
     p = dgcnn.init_params(seed=5, randomize_bn=True, bga=bga)
     # a non-trivial input transform (the reference initialises it to identity)
     p["transform_net1/transform_XYZ/weights"] = 0.01 * torch.randn((256, 9), device="cuda")

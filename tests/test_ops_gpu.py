@@ -241,3 +241,40 @@ def test_dgcnn_graph_matches_oracle(n, c, k):
     nb = x[np.arange(2)[:, None, None], oi]
     ctr = np.broadcast_to(x[:, :, None, :], nb.shape)
     assert np.array_equal(G.npy(edge), np.concatenate([ctr, nb - ctr], -1))
+
+
+@pytest.mark.parametrize("kind,n,c,k", [("gauss", 2048, 64, 20), ("ball", 2048, 3, 20), ("dup", 1024, 3, 20), ("gauss", 300, 16, 8),
+                                        ("gauss", 256, 64, 32), ("scaled", 1024, 64, 20), ("nan", 512, 8, 10)])
+def test_knn_graph_tensor_core_path_is_index_exact(kind, n, c, k):
+    """csrc/knn_tc.cu: bf16 / bf16x3 tensor-core distances only PRUNE; the neighbours come from the canonical fp32 distances of the
+    survivors, so the result equals the oracle (and the fp32 kernel) bit for bit -- incl. the BASELINE configs[2] size n = 2048,
+    clouds with many exactly equidistant points (list overflow -> exhaustive rows) and a cloud holding a NaN."""
+    rng = np.random.default_rng(n + c + k)
+    if kind in ("ball", "dup"):
+        x = make_clouds(kind, 2, n, seed=n + 1)
+    else:
+        x = rng.standard_normal((2, n, c)).astype(np.float32)
+        if kind == "scaled":
+            x[1] *= 37.5                      # per-cloud scale: the error bounds are relative to the cloud's norms
+            x[0, : n // 2] *= 1e-3            # a dense cluster far below the cloud's largest distances
+    if kind == "nan":
+        x[1, 7, 2] = np.nan
+    xt = G.cu(x)
+    assert _lib_ws(2, n, c, k) > 0
+    got = G.npy(ops.knn_graph(xt, k))
+    if kind == "nan":
+        want0 = orc.dgcnn_knn(x[:1], k)
+        assert np.array_equal(got[0], want0[0])            # the finite cloud is exact; the NaN cloud only has to complete
+        assert got[1].min() >= 0 and got[1].max() < n
+        return
+    assert np.array_equal(got, orc.dgcnn_knn(x, k))
+    ops._KNN_FP32_ONLY = True
+    try:
+        assert np.array_equal(got, G.npy(ops.knn_graph(xt, k)))
+    finally:
+        ops._KNN_FP32_ONLY = False
+
+
+def _lib_ws(b, n, c, k):
+    from scanobjectnn_b200 import _lib
+    return _lib.load().psa_knn_graph_workspace_bytes(b, n, c, k)

@@ -208,6 +208,11 @@ def test_training_step_gradients_match_float64_restatement():
         if name.endswith("/biases") and f"{name[:-7]}/bn/gamma" in before:
             assert np.abs(got).max() == 0.0 and np.abs(gw).max() < 1e-9       # exact zero here, rounding noise there
             continue
+        if np.abs(gw).max() < 1e-9:
+            # analytically zero (e.g. the beta of the last BN in front of the max-pool + fc1 + batch norm: a constant shift of
+            # the global feature is removed by fc1's batch statistics): only rounding noise on either side
+            assert np.abs(got).max() < 1e-5, (name, np.abs(got).max())
+            continue
         worst[name] = _rel(got, gw)
     bad = {k: v for k, v in worst.items() if v > GTOL}
     print("max relative gradient error:", max(worst.values()), "over", len(worst), "tensors")
