@@ -34,28 +34,47 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- prep: thread = point row ----
+// ---- prep: block = 128 rows.  Phase A: thread = row, the canonical |x|^2 (sequential fma chain).  Phase B: warp = row,
+// lane = two consecutive channels: coalesced 256-byte reads, three packed bf16x2 words per lane into the swizzled rows ----
 __global__ void __launch_bounds__(128) knn_prep_kernel(int n, int npad, int c, const float* __restrict__ x, uint8_t* __restrict__ image,
                                                        float* __restrict__ sq) {
-    const int cloud = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x;
-    const int r = rb * 128 + tid;
+    const int cloud = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t* blk = image + ((size_t)cloud * (npad / 128) + rb) * kKtBlock;
-    float s = 0.f;
-    const float* xr = x + ((size_t)cloud * n + r) * c;
-    for (int l = 0; l < 64; ++l) {
-        float v = 0.f;
-        if (r < n && l < c) { v = __ldg(xr + l); s = fmaf(v, v, s); }
-        const __nv_bfloat16 c1 = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(c1);
-        const __nv_bfloat16 c2 = __float2bfloat16_rn(r1);
-        const float r2 = r1 - __bfloat162float(c2);
-        const __nv_bfloat16 c3 = __float2bfloat16_rn(r2);
-        const uint32_t off = swz_off_bf16((uint32_t)tid, (uint32_t)l, 128u);
-        *reinterpret_cast<__nv_bfloat16*>(blk + off) = c1;
-        *reinterpret_cast<__nv_bfloat16*>(blk + kKtPiece + off) = c2;
-        *reinterpret_cast<__nv_bfloat16*>(blk + 2u * kKtPiece + off) = c3;
+    {
+        const int r = rb * 128 + tid;
+        float s = __int_as_float(0x7f800000);
+        if (r < n) {
+            const float* xr = x + ((size_t)cloud * n + r) * c;
+            s = 0.f;
+            if ((c & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
+                for (int l = 0; l < c; l += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(xr + l));
+                    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+                }
+            } else {
+                for (int l = 0; l < c; ++l) { const float v = __ldg(xr + l); s = fmaf(v, v, s); }
+            }
+        }
+        sq[(size_t)cloud * npad + r] = s;
     }
-    sq[(size_t)cloud * npad + r] = r < n ? s : __int_as_float(0x7f800000);
+    for (int rr = warp * 32; rr < warp * 32 + 32; ++rr) {
+        const int r = rb * 128 + rr, k = 2 * lane;
+        float h0 = 0.f, h1 = 0.f;
+        if (r < n) {
+            const float* xr = x + ((size_t)cloud * n + r) * c;
+            if (k < c) h0 = __ldg(xr + k);
+            if (k + 1 < c) h1 = __ldg(xr + k + 1);
+        }
+        const uint32_t off = swz_off_bf16((uint32_t)rr, (uint32_t)k, 128u);
+        const uint32_t p1 = pack_bf16x2(h0, h1);
+        h0 -= __uint_as_float(p1 << 16); h1 -= __uint_as_float(p1 & 0xffff0000u);
+        const uint32_t p2 = pack_bf16x2(h0, h1);
+        h0 -= __uint_as_float(p2 << 16); h1 -= __uint_as_float(p2 & 0xffff0000u);
+        const uint32_t p3 = pack_bf16x2(h0, h1);
+        *reinterpret_cast<uint32_t*>(blk + off) = p1;
+        *reinterpret_cast<uint32_t*>(blk + kKtPiece + off) = p2;
+        *reinterpret_cast<uint32_t*>(blk + 2u * kKtPiece + off) = p3;
+    }
 }
 
 struct KnnTcArgs {
@@ -96,7 +115,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     uint8_t* cstage = base + kKtBlock;                           // 2 x 48 KB
     float* s_sq = reinterpret_cast<float*>(base + 3 * kKtBlock); // npad floats
     uint8_t* scratch = reinterpret_cast<uint8_t*>(s_sq + npad);  // pass 1: u16 hist[256][128]; pass 2: u16 idx[96][128] | float adj[96][128]
-    unsigned short* hist = reinterpret_cast<unsigned short*>(scratch);
+    unsigned* hist = reinterpret_cast<unsigned*>(scratch);      // [256 bins][64 words]: thread t counts in half (t >> 6) of word t & 63
     unsigned short* lidx = reinterpret_cast<unsigned short*>(scratch);
     float* ladj = reinterpret_cast<float*>(scratch + (size_t)kKtCap * 128 * 2);
     const uint8_t* img = a.image + (size_t)cloud * NT * kKtBlock;
@@ -181,7 +200,10 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         const float dmax = 2.0f * (sqq + sqmax);
         const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp_u * 32) << 16);
-        for (int b = 0; b < kKtBins; ++b) hist[b * 128 + tid] = 0;
+        for (int b = 0; b < kKtBins; ++b) if (tid < 64) hist[b * 64 + tid] = 0u;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const unsigned hinc = tid < 64 ? 1u : 65536u;
+        unsigned* hcol = hist + (tid & 63);
         // ---- pass 1: coarse distances -> histogram ----
         for (int t = 0; t < NT; ++t) {
             const int s = t & 1;
@@ -197,7 +219,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
                     const int key = (int)(__float_as_uint(fmaxf(dist, 1e-30f)) >> 19);      // NaN -> 1e-30: lands in the last bin
                     const int bin = min(max(keymax - key, 0), kKtBins - 1);
-                    hist[bin * 128 + tid] += 1;
+                    atomicAdd(hcol + bin * 64, hinc);            // fire-and-forget: no dependent chain through shared memory
                 }
             }
             fence_before_thread_sync();
@@ -208,7 +230,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         float T;
         {
             int cum = 0, b = kKtBins - 1;
-            for (; b >= 0; --b) { cum += hist[b * 128 + tid]; if (cum >= a.k) break; }
+            for (; b >= 0; --b) { const unsigned w = hcol[b * 64]; cum += (int)(tid < 64 ? (w & 0xffffu) : (w >> 16)); if (cum >= a.k) break; }
             const float tau = b < 0 ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(keymax - b + 1) << 19);
             // |coarse - exact| <= E1 (one bf16 term: 2^-8 relative on every product), |fine - exact| <= E2 (bf16x3 + fp32 sums)
             const float E1 = 0.01f * sgeo, E2 = 1e-4f * sgeo + 2e-6f * (sqq + sqmax);
@@ -249,9 +271,30 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             // ---- refine: canonical fp32 distances of the listed candidates ----
             const float* xc = a.x + (size_t)cloud * n * a.c;
             const float* xq = xc + (size_t)q * a.c;
-            for (int e = 0; e < cnt; ++e) {
-                const int col = lidx[e * 128 + tid];
-                ladj[e * 128 + tid] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
+            if (a.c == 64 && (reinterpret_cast<uintptr_t>(xc) & 15) == 0) {
+                // the usual DGCNN width: query row resident in registers, candidate row fetched with 16 independent loads
+                float4 qv[16];
+#pragma unroll
+                for (int l = 0; l < 16; ++l) qv[l] = __ldg(reinterpret_cast<const float4*>(xq) + l);
+                for (int e = 0; e < cnt; ++e) {
+                    const int col = lidx[e * 128 + tid];
+                    const float4* cp4 = reinterpret_cast<const float4*>(xc + (size_t)col * 64);
+                    float4 cv[16];
+#pragma unroll
+                    for (int l = 0; l < 16; ++l) cv[l] = __ldg(cp4 + l);
+                    float dot = 0.f;
+#pragma unroll
+                    for (int l = 0; l < 16; ++l) {
+                        dot = fmaf(qv[l].x, cv[l].x, dot); dot = fmaf(qv[l].y, cv[l].y, dot);
+                        dot = fmaf(qv[l].z, cv[l].z, dot); dot = fmaf(qv[l].w, cv[l].w, dot);
+                    }
+                    ladj[e * 128 + tid] = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
+                }
+            } else {
+                for (int e = 0; e < cnt; ++e) {
+                    const int col = lidx[e * 128 + tid];
+                    ladj[e * 128 + tid] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
+                }
             }
             // ---- k rounds of lexicographic (distance, index) minimum: ascending distance, lower index first on ties ----
             float pd = -__int_as_float(0x7f800000);

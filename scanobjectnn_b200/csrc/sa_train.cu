@@ -252,10 +252,11 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             named_bar_sync(15, PT);                                          // the previous cloud's float4 copy is no longer read
             float2 px[PPTP / 2], py[PPTP / 2], pz[PPTP / 2];
             unsigned valid = 0u;
+            const float pinf = __int_as_float(0x7f800000);
 #pragma unroll
             for (int i = 0; i < PPTP; ++i) {
                 const int k = 32 * (warp + NP * i) + lane;
-                float x = 0.f, y = 0.f, z = 0.f;
+                float x = pinf, y = pinf, z = pinf;         // slots past the cloud: +inf, out of reach of every finite query
                 if (k < n) {
                     x = __ldg(gx + 3 * k); y = __ldg(gx + 3 * k + 1); z = __ldg(gx + 3 * k + 2);
                     cloud4[k] = make_float4(x, y, z, __int_as_float(k));
@@ -291,14 +292,27 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                         const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
                         unsigned* bm = bitmaps + qi * BW;
                         unsigned mine = 0u;                                  // lane i keeps word i of this warp's share, stored once
+                        const bool qfinite = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;   // warp-uniform
+                        if (qfinite) {
 #pragma unroll
-                        for (int i = 0; i < PPTP; i += 2) {
-                            const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
-                            // !(d > thr): a NaN distance counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
-                            const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr) && ((valid >> i) & 1u));
-                            const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr) && ((valid >> (i + 1)) & 1u));
-                            if (lane == i) mine = w0;
-                            if (lane == i + 1) mine = w1;
+                            for (int i = 0; i < PPTP; i += 2) {
+                                const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
+                                // !(d > thr): a NaN distance (NaN point) counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
+                                const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr));
+                                const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr));
+                                if (lane == i) mine = w0;
+                                if (lane == i + 1) mine = w1;
+                            }
+                        } else {
+                            // non-finite query: every distance is NaN = inside; only the slots past the cloud must be masked out
+#pragma unroll
+                            for (int i = 0; i < PPTP; i += 2) {
+                                const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
+                                const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr) && ((valid >> i) & 1u));
+                                const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr) && ((valid >> (i + 1)) & 1u));
+                                if (lane == i) mine = w0;
+                                if (lane == i + 1) mine = w1;
+                            }
                         }
                         if (lane < PPTP) bm[warp + NP * lane] = mine;         // one store instruction per query and warp
                     }
@@ -442,15 +456,15 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             const int e4 = tid % E4, rl = tid / E4;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const float4* part4 = reinterpret_cast<const float4*>(a.partial);
-            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 16 * RL) {
-                float4 v[16];
+            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 20 * RL) {
+                float4 v[20];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < 20; ++u) {
                     const unsigned p = p0 + u * RL;
                     v[u] = p < gridDim.x ? __ldcg(part4 + (size_t)p * E4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int u = 0; u < 16; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+                for (int u = 0; u < 20; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
             }
             double* sred = reinterpret_cast<double*>(ring);                // RL x 2*C1 doubles <= 8 KB (the ring is >= 15 KB)
 #pragma unroll

@@ -990,6 +990,12 @@ struct TcDenseArgs {
     const float* xyz3;     // optional side input (rows, 3): out += xyz3 . w3 before scale/shift (the xyz rows of a
     const float* w3;       // (3, N)                          [xyz, features] . W product, kept off the K loop)
     float* out;
+    // training-mode forward (tc_dense3 only): the input is relu(x * in_scale + in_shift) per INPUT channel (the previous layer's
+    // batch norm, applied while the operand is staged) and per-tile column statistics of the stored values are written
+    const float* in_scale = nullptr;   // (K) or null
+    const float* in_shift = nullptr;
+    int in_relu = 0;
+    float* stat_partial = nullptr;     // (row tiles, 2, N) or null
 };
 
 template <bool NARROW>
@@ -1464,6 +1470,11 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
         // this warp's 8 rows x 64 k of block kb, raw: issued a block ahead, before the stage is known to be free
         auto load_x = [&](int kb) {
             const int k = kb * 64 + 2 * lane;
+            float2 isc = make_float2(1.f, 1.f), ish = make_float2(0.f, 0.f);
+            if (a.in_scale != nullptr) {
+                if (k < a.K) { isc.x = __ldg(a.in_scale + k); ish.x = __ldg(a.in_shift + k); }
+                if (k + 1 < a.K) { isc.y = __ldg(a.in_scale + k + 1); ish.y = __ldg(a.in_shift + k + 1); }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const long long r = row0 + warp_u * 8 + i;
@@ -1472,6 +1483,10 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
                     const float* xr = a.x + (size_t)r * a.K + k;
                     if (vec2 && k + 1 < a.K) v[i] = __ldg(reinterpret_cast<const float2*>(xr));
                     else { if (k < a.K) v[i].x = __ldg(xr); if (k + 1 < a.K) v[i].y = __ldg(xr + 1); }
+                    if (a.in_scale != nullptr) {       // previous layer's batch norm (+ relu) on the fly; padded rows / channels stay 0
+                        if (k < a.K) { v[i].x = fmaf(v[i].x, isc.x, ish.x); if (a.in_relu) v[i].x = fmaxf(v[i].x, 0.f); }
+                        if (k + 1 < a.K) { v[i].y = fmaf(v[i].y, isc.y, ish.y); if (a.in_relu) v[i].y = fmaxf(v[i].y, 0.f); }
+                    }
                 }
             }
         };
@@ -1552,6 +1567,26 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
                 if (rbase + q < a.rows) a.out[(size_t)(rbase + q) * a.N + ch] = acc[q];       // 32 lanes = 128 contiguous bytes
+            if (a.stat_partial != nullptr) {
+                // column statistics of the stored tile: lane = channel, so sum / sum of squares over this slot's 32 rows are
+                // in-thread; the four row slots of a channel quarter fold through shared memory in slot order (deterministic)
+                float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (rbase + q < a.rows) { ssum += acc[q]; ssq = fmaf(acc[q], acc[q], ssq); }
+                __shared__ float s_st[2][TcDense3::kPrepWarps][32];
+                s_st[0][warp_u][lane] = ssum;
+                s_st[1][warp_u][lane] = ssq;
+                named_bar_sync(1, TcDense3::kPrepWarps * 32);
+                if (slot == 0) {
+                    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) { t0 += s_st[0][quarter + 4 * o][lane]; t1 += s_st[1][quarter + 4 * o][lane]; }
+                    float* dst = a.stat_partial + (size_t)blockIdx.x * 2 * a.N;
+                    dst[ch] = t0;
+                    dst[a.N + ch] = t1;
+                }
+            }
         } else {
             float mx = -FLT_MAX;
 #pragma unroll
@@ -1658,6 +1693,26 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
     return check_launch("tc_dense_kernel");
 }
 
+
+// Training-mode forward of one layer on tc_dense3: y = relu(bn_prev(x)) . W + bias (pre-BN output), per-row-tile column
+// statistics.  The weights change every step, so the image is rebuilt into `image_ws` (tc_dense_image_bytes(K, N)) per call.
+bool tc_train_fwd_eligible(long long rows, int K, int N) {
+    return g_tc_dense_v3 && g_tc_dense_v2 && rows >= 128 && K >= 32 && K <= 512 && N >= 128 && (N % 128) == 0;
+}
+int launch_tc_dense_train(long long rows, int K, int N, const float* x, const float* in_scale, const float* in_shift, int in_relu,
+                          const float* W, const float* bias, float* y, float* stat_partial, uint8_t* image_ws, cudaStream_t st) {
+    const int Kp = (K + 63) & ~63;
+    build_image(K, Kp, N, 128 | kImageBf16x3, W, image_ws, st);
+    TcDenseArgs a;
+    a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = 1; a.relu = 0;
+    a.x = x; a.image = image_ws; a.scale = nullptr; a.shift = bias; a.out = y; a.xyz3 = nullptr; a.w3 = nullptr;
+    a.in_scale = in_scale; a.in_shift = in_shift; a.in_relu = in_relu; a.stat_partial = stat_partial;
+    dim3 grid((unsigned)((rows + 127) / 128), N / 128);
+    const size_t smem3 = 4 * (size_t)TcDense3::kBlock + 1024;
+    PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    tc_dense3_kernel<<<grid, TcDense3::kThreads, smem3, st>>>(a);
+    return check_launch("tc_dense3_kernel");
+}
 
 // A prebuilt image (psa_prepare_weight_image) is used when it matches; otherwise the image is (re)built into `ws`.
 // `Nt` may carry kImageBf16x3 (three-bf16-piece image for tc_sa_dual_kernel).

@@ -6,10 +6,21 @@
 // scatter) is a fixed-order sum -- per-CTA partials in a fixed thread order, partials added in index order in fp64.  The
 // reference's gradient kernels are float atomicAdd scatters (tf_grouping_g.cu:61-78, tf_sampling_g.cu:183-192).
 #include <math.h>
+#include <stdlib.h>
 
 #include "train_gemm.cuh"
 
 namespace psa {
+
+// tensor-core forward of a training layer (tc_mlp.cu): operands split into three bf16 pieces, fp32 accumulation
+bool tc_train_fwd_eligible(long long rows, int K, int N);
+size_t tc_dense_image_bytes(int K, int N);
+int launch_tc_dense_train(long long rows, int K, int N, const float* x, const float* in_scale, const float* in_shift, int in_relu,
+                          const float* W, const float* bias, float* y, float* stat_partial, uint8_t* image_ws, cudaStream_t st);
+static int train_tc_enabled() {
+    static const int v = [] { const char* e = getenv("PSA_TRAIN_FP32_ONLY"); return (e && atoi(e)) ? 0 : 1; }();
+    return v;
+}
 
 // out[e] = sum_p partial[p * len + e] in a FIXED tree: block = 32 outputs x 32 chunk lanes; lane c adds its contiguous range of
 // partials in ascending order (fp64, eight loads in flight), the 32 chunk sums are added in lane order.  Deterministic, and
@@ -457,6 +468,8 @@ extern "C" size_t psa_train_dense_workspace_bytes(long long rows, int K, int N) 
     const size_t small = rows <= kSmallM ? (size_t)16 * rows * (K > N ? K : N) * sizeof(float) : 0;
     size_t mx = fwd > bwd ? fwd : bwd;
     if (small > mx) mx = small;
+    // tensor-core forward: statistics partials + the per-step weight image behind them
+    if (tc_train_fwd_eligible(rows, K, N)) { const size_t tcw = ((fwd + 255) & ~(size_t)255) + tc_dense_image_bytes(K, N); if (tcw > mx) mx = tcw; }
     return mx + 256;
 }
 
@@ -472,6 +485,17 @@ extern "C" int psa_train_dense_fwd(long long rows, int K, int N, const psa_act_i
     if (stats != nullptr) {
         PSA_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)tiles_m * 2 * N * sizeof(float), "train_dense_fwd: workspace too small");
         o.stat_partial = reinterpret_cast<float*>(workspace);
+    }
+    // wide layers: tcgen05 path (bf16x3 operands, fp32 accumulate) when the input is a plain (rows, K) tensor without dropout
+    if (train_tc_enabled() && tc_train_fwd_eligible(rows, K, N) && in->ld == K && in->mask == nullptr) {
+        const size_t stat_bytes = ((size_t)tiles_m * 2 * N * sizeof(float) + 255) & ~(size_t)255;
+        PSA_REQUIRE(workspace != nullptr && workspace_bytes >= stat_bytes + tc_dense_image_bytes(K, N), "train_dense_fwd: workspace too small");
+        float* sp = stats ? reinterpret_cast<float*>(workspace) : nullptr;
+        int rc0 = launch_tc_dense_train(rows, K, N, in->x, in->scale, in->shift, in->relu, W, bias, y, sp,
+                                        reinterpret_cast<uint8_t*>(workspace) + stat_bytes, st);
+        if (rc0 != PSA_OK) return rc0;
+        if (stats != nullptr) return reduce_partials((int)tiles_m, 2 * N, sp, stats, st);
+        return PSA_OK;
     }
     const ActIn fa(*in);
     const MatIn fb{W, N};

@@ -61,7 +61,7 @@ def test_dense_forward_backward_products(rows, K, N):
         h = x.astype(np.float64)
     assert lib.psa_train_dense_fwd(rows, K, N, C.byref(a), _vp(Wd), _vp(bd), _vp(y), _vp(stats), _vp(ws), C.c_size_t(need), _st()) == 0
     want = h @ W.astype(np.float64) + b
-    assert _rel(G.npy(y), want) < 2e-6
+    assert _rel(G.npy(y), want) < 1e-5        # wide layers run on the tensor cores (bf16x3 operands): the 1e-5 contract
     np.testing.assert_allclose(G.npy(stats)[0], want.sum(0), rtol=1e-5, atol=1e-3 * np.sqrt(rows))
     np.testing.assert_allclose(G.npy(stats)[1], (want ** 2).sum(0), rtol=1e-5, atol=1e-3)
     # backward products with a plain incoming gradient
