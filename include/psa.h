@@ -232,17 +232,14 @@ PSA_API size_t psa_sa_group_all_workspace_bytes(int b, int n, int c, const psa_m
 PSA_API int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, const float* points, const psa_mlp* mlp,
                                    float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream);
 
-/* Arithmetic of the grouped MLP.  0 (default): layers after the first run on the tcgen05 tensor cores as a
- * three-term tf32/tf32/bf16 operand split with fp32 accumulation (within 1e-5 of fp64 on O(1) activations) whenever
- * the shapes allow (widths 64/128, last width 64 or a multiple of 128, nsample 32/64/128), fp32 FMA otherwise; levels
- * with a 128-wide layer use the dual-group kernel (three bf16 pieces per operand, six MMAs per product).
- * 1: always the fp32-FMA kernels.  2: like 0, but 128-wide levels use the older one-tile-per-CTA kernel (A/B runs). */
+/* Arithmetic of the grouped MLP.  0 (default): layers after the first run on the tcgen05 tensor cores with both operands
+ * split into three exactly representable bf16 pieces (a = a1+a2+a3, w = w1+w2+w3; six MMAs per product, small terms first,
+ * fp32 accumulation in tensor memory: within 1e-5 of fp64 on O(1) activations) whenever the shapes allow -- set-abstraction
+ * levels with widths 64/128 (last width 64 or a multiple of 128) and nsample 32/64/128 on tc_sa_dual_kernel, dense layers with
+ * N = 64 or a multiple of 128 on tc_dense2 / tc_dense3 -- and on the fp32-FMA kernels otherwise.  1: fp32-FMA kernels only.
+ * The switch is process-global and not synchronised: set it before launching work, not concurrently with it. */
 PSA_API int psa_set_mlp_mode(int mode);
 PSA_API int psa_get_mlp_mode(void);
-
-/* Diagnostic: one 128-row tile through one tensor-core layer, D[128,N] = A[128,Kd] . W[Kd,N] (Kd, N in {64,128}). */
-PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, void* scratch /* 6*Kd*N bytes */,
-                            psa_stream_t stream);
 
 /* Training-mode front of a set-abstraction level ("variant F1"): ball query + group + centre + first 1x1 conv + bias in
  * one launch, writing the PRE-batch-norm activations (which training-mode BN needs in HBM once: batch statistics come

@@ -78,7 +78,6 @@ SIGNATURES = {
     "psa_prepare_weight_image": [_i, _i, _i, _i, _p, _p, _p],
     "psa_set_mlp_mode": [_i],
     "psa_get_mlp_mode": [],
-    "psa_tc_selftest": [_i, _i, _p, _p, _p, _p, _p],
     "psa_edgeconv_infer": [_i, _i, _i, _i, _p, _p, C.POINTER(PsaMlp), _p, _p, C.c_size_t, _p],
     # training mode
     "psa_train_dense_fwd": [_ll, _i, _i, _ain, _p, _p, _p, _p, _p, _sz, _p],

@@ -23,7 +23,7 @@
 namespace psa {
 using namespace tc;
 
-constexpr int kKtThreads = 160;                   // 4 row warps + 1 issuer warp
+constexpr int kKtThreads = 288;                   // 8 row warps (two threads per query row) + 1 issuer warp
 constexpr uint32_t kKtPiece = 128u * 128u;        // one bf16 piece of a [128 rows][64 k] block: 16 KB
 constexpr uint32_t kKtBlock = 3u * kKtPiece;      // 48 KB
 constexpr int kKtBins = 256;
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_qfull, s_full[2], s_dfull[2], s_dfree[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_wmax[5];
+    __shared__ float s_wmax[kKtThreads / 32];
+    __shared__ float s_T[128];
+    __shared__ int s_cnt[128];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
     const int cloud = blockIdx.y;
@@ -121,10 +123,10 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     const uint8_t* img = a.image + (size_t)cloud * NT * kKtBlock;
     const float* sqc = a.sq + (size_t)cloud * npad;
 
-    if (warp_u == 4) tmem_alloc(&s_tmem, 256);
+    if (warp_u == 8) tmem_alloc(&s_tmem, 256);
     if (tid == 0) {
         mbar_init(&s_qfull, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_dfull[i], 1); mbar_init(&s_dfree[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_dfull[i], 1); mbar_init(&s_dfree[i], 8); }
         fence_mbar_init();
     }
     // candidate norms -> shared memory; the cloud's largest finite-or-not norm over the real points
@@ -141,13 +143,16 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = warp_uniform(s_tmem);
-    const int J = 2 * NT;                            // jobs: pass 0 tiles, then pass 1 tiles
+    // pass 1 looks at every second candidate tile only: the k-th smallest of a SUBSET is still an upper bound of the k-th smallest
+    // of the whole cloud, the histogram work halves and pass 2 lists ~2k candidates instead of ~k
+    const int NT1 = (NT + 1) / 2;
+    const int J = NT1 + NT;                          // jobs: pass 1 tiles (0, 2, 4, ..), then every pass 2 tile
 
-    if (warp_u == 4) {
+    if (warp_u == 8) {
         // ================= issuer / loader warp =================
         auto load = [&](int j) {
-            const int s = j & 1, t = j % NT;
-            const uint32_t bytes = j < NT ? kKtPiece : kKtBlock;                   // pass 0 needs the leading piece only
+            const int s = j & 1, t = j < NT1 ? 2 * j : j - NT1;
+            const uint32_t bytes = j < NT1 ? kKtPiece : kKtBlock;                  // pass 1 needs the leading piece only
             if (lane == 0) {
                 mbar_expect_tx(&s_full[s], bytes);
                 for (uint32_t o = 0; o < bytes; o += 16384u) bulk_g2s(cstage + (uint32_t)s * kKtBlock + o, img + (size_t)t * kKtBlock + o, 16384u, &s_full[s]);
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             fence_after_thread_sync();
             const uint32_t d = tmem_base + (uint32_t)s * 128u;
             const SmemDescBase cb = smem_desc_base(warp_uniform(smem_u32(cstage) + (uint32_t)s * kKtBlock));
-            if (j < NT) {
+            if (j < NT1) {
 #pragma unroll
                 for (int s4 = 0; s4 < 4; ++s4) mma_bf16_ss(d, smem_desc_at(qa, s4 * 32), smem_desc_at(cb, s4 * 32), idesc, s4 ? 1u : 0u);
             } else {
@@ -190,30 +195,37 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             }
         }
     } else {
-        // ================= row threads: thread = query row =================
-        const int q = blockIdx.x * 128 + tid;
+        // ================= row threads: TWO threads per query row =================
+        // thread (r, h): row r = tid & 127, half h = tid >> 7 owns columns [64 h, 64 h + 64) of every candidate tile (warps w and
+        // w + 4 read the same TMEM lanes).  Histogram counters and the candidate list of a row are shared by its two threads
+        // through shared-memory atomics; twice the warps hide twice the latency of the serial per-row work.
+        const int r = tid & 127, h = tid >> 7;
+        const int q = blockIdx.x * 128 + r;
         const bool valid = q < n;
-        const float sqmax = fmaxf(fmaxf(fmaxf(s_wmax[0], s_wmax[1]), fmaxf(s_wmax[2], s_wmax[3])), s_wmax[4]);
+        float sqmax = s_wmax[0];
+#pragma unroll
+        for (int w = 1; w < kKtThreads / 32; ++w) sqmax = fmaxf(sqmax, s_wmax[w]);
         const float sqq = s_sq[valid ? q : 0];
-        bool ok = valid && fabsf(sqq) <= FLT_MAX && fabsf(sqmax) <= FLT_MAX;
+        const bool ok = valid && fabsf(sqq) <= FLT_MAX && fabsf(sqmax) <= FLT_MAX;
         const float sgeo = sqrtf(sqq * sqmax);
         const float dmax = 2.0f * (sqq + sqmax);
         const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp_u * 32) << 16);
-        for (int b = 0; b < kKtBins; ++b) if (tid < 64) hist[b * 64 + tid] = 0u;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        const unsigned hinc = tid < 64 ? 1u : 65536u;
-        unsigned* hcol = hist + (tid & 63);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)h * 64u;
+        for (int b = tid; b < kKtBins * 64; b += 256) hist[b] = 0u;
+        if (h == 0) s_cnt[r] = 0;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const unsigned hinc = r < 64 ? 1u : 65536u;
+        unsigned* hcol = hist + (r & 63);
         // ---- pass 1: coarse distances -> histogram ----
-        for (int t = 0; t < NT; ++t) {
-            const int s = t & 1;
-            mbar_wait(&s_dfull[s], (uint32_t)((t >> 1) & 1));
+        for (int t1 = 0; t1 < NT1; ++t1) {
+            const int s = t1 & 1, t = 2 * t1;
+            mbar_wait(&s_dfull[s], (uint32_t)((t1 >> 1) & 1));
             fence_after_thread_sync();
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 uint32_t d[32];
                 tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
                 tmem_ld_wait();
-                const float* sc = s_sq + t * 128 + ch * 32;
+                const float* sc = s_sq + t * 128 + h * 64 + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
@@ -226,35 +238,35 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive1(&s_dfree[s]);
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");           // both halves of every row are in the histogram
         // ---- threshold: upper edge of the bin that holds the k-th smallest coarse distance, widened by the error bounds ----
-        float T;
-        {
+        if (h == 0) {
             int cum = 0, b = kKtBins - 1;
-            for (; b >= 0; --b) { const unsigned w = hcol[b * 64]; cum += (int)(tid < 64 ? (w & 0xffffu) : (w >> 16)); if (cum >= a.k) break; }
+            for (; b >= 0; --b) { const unsigned w = hcol[b * 64]; cum += (int)(r < 64 ? (w & 0xffffu) : (w >> 16)); if (cum >= a.k) break; }
             const float tau = b < 0 ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(keymax - b + 1) << 19);
             // |coarse - exact| <= E1 (one bf16 term: 2^-8 relative on every product), |fine - exact| <= E2 (bf16x3 + fp32 sums)
             const float E1 = 0.01f * sgeo, E2 = 1e-4f * sgeo + 2e-6f * (sqq + sqmax);
-            T = tau + E1 + E2 + 1e-6f * tau;
+            s_T[r] = tau + E1 + E2 + 1e-6f * tau;
         }
-        // every row thread is done with its histogram before anybody's candidate list / distances overwrite the scratch area
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        // ---- pass 2: fine distances -> candidate list ----
-        int cnt = 0;
+        // every row is done with its histogram before anybody's candidate list / distances overwrite the scratch area
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float T = s_T[r];
+        // ---- pass 2: fine distances -> the row's candidate list (slots handed out by a shared-memory counter) ----
         for (int t = 0; t < NT; ++t) {
-            const int j = NT + t, s = j & 1;
+            const int j = NT1 + t, s = j & 1;
             mbar_wait(&s_dfull[s], (uint32_t)((j >> 1) & 1));
             fence_after_thread_sync();
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 uint32_t d[32];
                 tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
                 tmem_ld_wait();
-                const float* sc = s_sq + t * 128 + ch * 32;
+                const float* sc = s_sq + t * 128 + h * 64 + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
                     if (dist < T) {
-                        if (cnt < kKtCap) lidx[cnt * 128 + tid] = (unsigned short)(t * 128 + ch * 32 + i);
-                        ++cnt;
+                        const int slot = atomicAdd(&s_cnt[r], 1);
+                        if (slot < kKtCap) lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * 64 + ch * 32 + i);
                     }
                 }
             }
@@ -262,22 +274,24 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive1(&s_dfree[s]);
         }
-        if (valid && (!ok || cnt > kKtCap || cnt < a.k)) {
-            // exhaustive kernel takes this row (overflow: many equidistant candidates; non-finite coordinates; or fewer than k real points below T)
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int cnt = s_cnt[r];
+        const bool refine = ok && cnt <= kKtCap && cnt >= a.k;
+        if (valid && !refine && h == 0) {
+            // exhaustive kernel takes this row (overflow: many equidistant candidates; non-finite coordinates; fewer than k below T)
             a.flag_rows[atomicAdd(a.flag_count, 1u)] = cloud * n + q;
-            ok = false;
         }
-        if (ok) {
-            // ---- refine: canonical fp32 distances of the listed candidates ----
-            const float* xc = a.x + (size_t)cloud * n * a.c;
+        const float* xc = a.x + (size_t)cloud * n * a.c;
+        if (refine) {
+            // ---- refine: canonical fp32 distances of the listed candidates, entries split between the row's two threads ----
             const float* xq = xc + (size_t)q * a.c;
             if (a.c == 64 && (reinterpret_cast<uintptr_t>(xc) & 15) == 0) {
                 // the usual DGCNN width: query row resident in registers, candidate row fetched with 16 independent loads
                 float4 qv[16];
 #pragma unroll
                 for (int l = 0; l < 16; ++l) qv[l] = __ldg(reinterpret_cast<const float4*>(xq) + l);
-                for (int e = 0; e < cnt; ++e) {
-                    const int col = lidx[e * 128 + tid];
+                for (int e = h; e < cnt; e += 2) {
+                    const int col = lidx[e * 128 + r];
                     const float4* cp4 = reinterpret_cast<const float4*>(xc + (size_t)col * 64);
                     float4 cv[16];
 #pragma unroll
@@ -288,36 +302,36 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
                         dot = fmaf(qv[l].x, cv[l].x, dot); dot = fmaf(qv[l].y, cv[l].y, dot);
                         dot = fmaf(qv[l].z, cv[l].z, dot); dot = fmaf(qv[l].w, cv[l].w, dot);
                     }
-                    ladj[e * 128 + tid] = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
+                    ladj[e * 128 + r] = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
                 }
             } else {
-                for (int e = 0; e < cnt; ++e) {
-                    const int col = lidx[e * 128 + tid];
-                    ladj[e * 128 + tid] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
+                for (int e = h; e < cnt; e += 2) {
+                    const int col = lidx[e * 128 + r];
+                    ladj[e * 128 + r] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
                 }
             }
-            // ---- k rounds of lexicographic (distance, index) minimum: ascending distance, lower index first on ties ----
-            float pd = -__int_as_float(0x7f800000);
-            int pi = -1;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (refine) {
+            // ---- rank of every entry in the lexicographic (distance, index) order = its output position; entries are distinct, so
+            // ranks are too: ascending distance, lower index first on ties.  No loop-carried dependence, split between the two threads
             int* out = a.nn_idx + ((size_t)cloud * n + q) * a.k;
-            for (int r = 0; r < a.k; ++r) {
-                float bd = __int_as_float(0x7f800000);
-                int bi = 0x7fffffff;
-                for (int e = 0; e < cnt; ++e) {
-                    const float dd = ladj[e * 128 + tid];
-                    const int ii = lidx[e * 128 + tid];
-                    const bool after = dd > pd || (dd == pd && ii > pi);
-                    const bool better = dd < bd || (dd == bd && ii < bi);
-                    if (after && better) { bd = dd; bi = ii; }
+            for (int e = h; e < cnt; e += 2) {
+                const float de = ladj[e * 128 + r];
+                const int ie = lidx[e * 128 + r];
+                int rank = 0;
+                for (int f = 0; f < cnt; ++f) {
+                    const float df = ladj[f * 128 + r];
+                    const int jf = lidx[f * 128 + r];
+                    rank += (df < de || (df == de && jf < ie)) ? 1 : 0;
                 }
-                out[r] = bi;
-                pd = bd; pi = bi;
+                if (rank < a.k) out[rank] = ie;
             }
         }
     }
     fence_before_thread_sync();
     __syncthreads();
-    if (warp_u == 4) tmem_dealloc(tmem_base, 256);
+    if (warp_u == 8) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- exhaustive rows (worklist): one warp per row, canonical distances of all n candidates in shared memory, then k rounds of
@@ -387,7 +401,7 @@ static size_t knn_tc_smem_bytes(int npad) {
     return 1024 + 3 * (size_t)kKtBlock + (size_t)npad * 4 + (size_t)kKtCap * 128 * 2 + (size_t)kKtCap * 128 * 4 + 64;
 }
 
-bool knn_tc_eligible(int n, int c, int k) { return n >= 128 && n <= kKtMaxN && c >= 1 && c <= 64 && k >= 1 && k <= 64 && k <= n; }
+bool knn_tc_eligible(int n, int c, int k) { return n >= 128 && n <= kKtMaxN && c >= 1 && c <= 64 && k >= 1 && k <= 32; }   // tile 0 (128 real points) is in the pass-1 subsample: it holds k candidates
 
 }  // namespace psa
 

@@ -48,6 +48,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
+#if defined(PSA_MBAR_SLEEP_NS) && PSA_MBAR_SLEEP_NS > 0
+        if (!done) __nanosleep(PSA_MBAR_SLEEP_NS);      // A/B builds (tools/build_variant.py): back off instead of re-polling at once
+#endif
     } while (!done);
 }
 // MMA ISSUE CONVENTION.  tcgen05.mma takes its operands from UNIFORM registers.  Issued from `if (tid == 0)` the

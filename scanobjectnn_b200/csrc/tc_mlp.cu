@@ -15,14 +15,14 @@
 //   max-pool  the last epilogue reduces each neighbourhood's rows with a transposing warp butterfly and writes
 //             (B,m,C_out) coalesced.
 //
-// Kernels (default path first):
+// Kernels:
 //   tc_sa_dual_kernel<DBUF>   SA level, two row groups per CTA, bf16x3 operands (three exact bf16 pieces per operand, six
 //                             MMAs per product), per-group streamed last layer, tensor-pipe token, two D slots (DBUF)
-//   tc_dense3_kernel          dense layer, transposed (lane = channel), both operands from shared memory
+//   tc_dense3_kernel          dense layer, transposed (lane = channel), both operands from shared memory; also the
+//                             training-mode forward (previous batch norm applied on load, statistics in the epilogue)
 //   tc_dense2_kernel          dense layer, A from TMEM, warp-specialised pipeline (N = 64 or K > 512)
-//   tc_sa_kernel<NARROW>, tc_dense_kernel<NARROW>   the round's first generation (tf32/tf32/bf16 three-term split:
-//                             trunc_tf32(a)*trunc_tf32(w) + tf32(a-trunc a)*trunc_tf32(w) + bf16(a)*bf16(w-trunc w)),
-//                             kept behind psa_set_mlp_mode(2) for A/B runs and as a second implementation in the tests
+// (Round 1's first generation -- tc_sa_kernel / tc_dense_kernel with a tf32/tf32/bf16 three-term split -- is gone: the
+//  kernels above cover its shapes; levels the dual kernel cannot hold run on the fp32-FMA fused kernel of mlp.cu.)
 // fp32 parity: operands are quantised by this code, so the tensor core only ever sees exactly representable values; fp32
 // accumulation in TMEM truncates, hence small terms first and K cut into <= 128-wide pieces (tests hold 1e-5 vs fp64).
 #include <float.h>
@@ -35,48 +35,17 @@ namespace psa {
 
 using namespace tc;
 
-// Two configurations of every tensor-core kernel:
-//   wide   512 threads (16 warps), all 512 TMEM columns, 128-wide output tiles, A operand up to K = 128: one CTA per SM;
-//   narrow 256 threads ( 8 warps), 256 TMEM columns,      64-wide output tiles, A operand up to K = 64: TWO CTAs per SM,
-//          which hide each other's gather / TMEM / barrier latencies (the kernels are latency- not tensor-bound).
-// Warp w works on TMEM lanes 32*(w%4).. (hardware rule) and on column chunks w/4, w/4 + kChunkWarps, ...
-template <bool NARROW>
-struct TcCfg {
-    static constexpr int kThreads = NARROW ? 256 : 512;
-    static constexpr int kChunkWarps = kThreads / 128;
-    static constexpr int kTmemCols = NARROW ? 256 : 512;
-    static constexpr uint32_t D = 0, AHI = NARROW ? 64 : 128, ALO = NARROW ? 128 : 256, ABF = NARROW ? 192 : 384;
-    static constexpr int kNtCap = NARROW ? 64 : 128;
-    static constexpr int kMinBlocks = NARROW ? 2 : 1;
-};
 constexpr int kMaxTcLayers = 2;
 
 // ------------------------------------------------------------------------------------------------------------------
-// Weight images.  A tensor layer W (K x N, row-major, fp32) is pre-arranged ONCE per call (tc_prep_weights_kernel) into
+// Weight images.  A tensor layer W (K x N, row-major, fp32) is pre-arranged once per weight set (tc_prep_weights3_kernel) into
 // blocks that can be dropped into shared memory by a single cp.async.bulk and fed to tcgen05.mma unchanged:
-//   block (nt, kc) covers output channels [nt*Nt, nt*Nt+Nt) x input channels [kc*64, kc*64+64),  Nt = min(N,128):
-//     hi : trunc_tf32(w)              [Nt][64] fp32, K-major SWIZZLE_128B (two 32-wide K blocks)   Nt*256 B
-//     lo : bf16(w - trunc_tf32(w))    [Nt][64] bf16, K-major SWIZZLE_128B (one 64-wide K block)    Nt*128 B
+//   block (nt, kc) covers output channels [nt*Nt, nt*Nt+Nt) x input channels [kc*64, kc*64+64): three bf16 pieces
+//   (w = w1 + w2 + w3, every piece exactly representable), each [Nt][64] K-major SWIZZLE_128B, Nt*128 B per piece;
 //   blocks stored in (nt major, kc minor) order.  6 bytes per weight.
 // ------------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline int tc_nt(int N, int cap) { return N >= cap ? cap : 64; }
 __host__ __device__ inline uint32_t tc_block_bytes(int Nt) { return (uint32_t)Nt * 64u * 6u; }
 __host__ __device__ inline size_t tc_image_bytes(int K, int N) { return (size_t)K * N * 6u; }     // independent of the tile width
-
-// K rows of W are zero-padded to Kp (multiple of 64)
-__global__ void tc_prep_weights_kernel(int K, int Kp, int N, int Nt, const float* __restrict__ W, uint8_t* __restrict__ image) {
-    const int KC = Kp / 64;
-    const uint32_t bb = tc_block_bytes(Nt);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Kp * N; e += gridDim.x * blockDim.x) {
-        const int n = e % N, k = e / N;                       // coalesced read of W rows
-        const float w = k < K ? __ldg(W + e) : 0.f;
-        const float hi = tf32_trunc(w);
-        uint8_t* blk = image + (size_t)((n / Nt) * KC + (k >> 6)) * bb;
-        const uint32_t nn = n % Nt, kk = k & 63;
-        *reinterpret_cast<float*>(blk + swz_off_f32(nn, kk, Nt)) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blk + (uint32_t)Nt * 256u + swz_off_bf16(nn, kk, Nt)) = __float2bfloat16_rn(w - hi);
-    }
-}
 
 struct TcArgs {
     long long groups;      // neighbourhoods = b*m
@@ -106,60 +75,6 @@ struct TcArgs {
                                   // share their SM with another stream's kernels simply take fewer)
 };
 
-// quantise one row-chunk of 32 activations into the three A operands and store them into TMEM
-template <class CFG>
-__device__ __forceinline__ void store_a_chunk(uint32_t row_taddr, int ch, const float (&h)[32]) {
-    constexpr uint32_t AHI_COL = CFG::AHI, ALO_COL = CFG::ALO, ABF_COL = CFG::ABF;
-    uint32_t v[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(tf32_trunc(h[q]));
-    tmem_st32(row_taddr + AHI_COL + ch * 32, v);
-#pragma unroll
-    for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(tf32_trunc(h[q] - tf32_trunc(h[q])));
-    tmem_st32(row_taddr + ALO_COL + ch * 32, v);
-    uint32_t p[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
-    tmem_st16(row_taddr + ABF_COL + ch * 16, p);
-}
-
-template <class CFG, int KC, int NT_>
-__device__ __forceinline__ void issue_tile_c(uint32_t tmem_base, uint32_t blocks_addr) {
-    constexpr uint32_t D_COL = CFG::D, AHI_COL = CFG::AHI, ALO_COL = CFG::ALO, ABF_COL = CFG::ABF;
-    // the bases go through a shuffle right here and every offset is a compile-time constant: the operands are provably
-    // warp-uniform and the per-MMA work is a couple of uniform adds
-    const uint32_t tb = warp_uniform(tmem_base);
-    const uint32_t d = tb + D_COL;
-    const uint32_t id_tf32 = make_idesc(kFmtTF32, 128, NT_);
-    const uint32_t id_bf16 = make_idesc(kFmtBF16, 128, NT_);
-    const SmemDescBase b0 = smem_desc_base(warp_uniform(blocks_addr));
-    constexpr uint32_t bb = NT_ * 64u * 6u, kblk = NT_ * 128u, lo_off = NT_ * 256u;
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc)
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-            mma_bf16_ts(d, tb + ABF_COL + kc * 32 + s * 8, smem_desc_at(b0, kc * bb + lo_off + s * 32), id_bf16, (kc | s) ? 1u : 0u);
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc)
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-            mma_tf32_ts(d, tb + ALO_COL + kc * 64 + s * 8, smem_desc_at(b0, kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
-#pragma unroll
-    for (int kc = 0; kc < KC; ++kc)
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-            mma_tf32_ts(d, tb + AHI_COL + kc * 64 + s * 8, smem_desc_at(b0, kc * bb + (s >> 2) * kblk + (s & 3) * 32), id_tf32, 1);
-}
-
-// issuer warp (converged): D[128 x Nt] = A[128 x 64*KC] . W_tile^T as the three-term split over KC resident blocks.
-// The tensor core truncates (rounds toward zero) every time it adds into D, so the error grows with the number of
-// accumulation steps taken while D is large: the two small correction terms go first, the main term last.
-template <class CFG>
-__device__ __forceinline__ void issue_tile(uint32_t tmem_base, uint32_t blocks_addr, int KC, int Nt) {
-    if (Nt == 64) { if (KC == 1) issue_tile_c<CFG, 1, 64>(tmem_base, blocks_addr); else issue_tile_c<CFG, 2, 64>(tmem_base, blocks_addr); }
-    else          { if (KC == 1) issue_tile_c<CFG, 1, 128>(tmem_base, blocks_addr); else issue_tile_c<CFG, 2, 128>(tmem_base, blocks_addr); }
-}
-
 // transposing butterfly: v[q] = column q of this lane's row; afterwards v[0] on lane l = max over the warp's 32 rows of column l
 __device__ __forceinline__ float warp_colmax_32x32(float (&v)[32], int lane) {
 #pragma unroll
@@ -176,292 +91,20 @@ __device__ __forceinline__ float warp_colmax_32x32(float (&v)[32], int lane) {
     return v[0];
 }
 
-// shared-memory plan: resident blocks of layers [0, nres) back to back, then (stream_last) a ring that holds ONE
-// 128-channel tile of the last layer (KC blocks), then the per-channel vectors
-struct TcSmemLayout {
-    uint32_t w[kMaxTcLayers];    // byte offset of layer l's blocks (the ring for a streamed last layer)
-    uint32_t vec;
-    uint32_t total;
-};
-
-__host__ __device__ inline TcSmemLayout tc_layout(const TcArgs& a) {
-    TcSmemLayout L;
-    uint32_t off = 0;
-    for (int l = 0; l < a.nl; ++l) {
-        L.w[l] = off;
-        const bool streamed = a.stream_last && l == a.nl - 1;
-        off += streamed ? (uint32_t)(a.Kd[l] / 64) * tc_block_bytes(tc_nt(a.Ntot[l], a.ntcap)) : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
-    }
-    L.vec = off;
-    off += 5u * a.C1 * 4u;
-    for (int l = 0; l < a.nl; ++l) off += 2u * a.Ntot[l] * 4u;
-    L.total = off;
-    return L;
-}
-
 #ifdef PSA_TC_TIMING
-// debug build only (tools/tc_timing.py): cycles thread 0 of every CTA spends in each phase of tc_sa_kernel
+// debug build only (tools/tc_timing.py): cycles thread 0 of every CTA spends in each phase of the tensor-core kernels
 __device__ unsigned long long g_tc_timing[8];
 #define TC_STAMP(i) do { if (tid == 0) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tprev); tprev = now_; } } while (0)
 #else
 #define TC_STAMP(i) do { } while (0)
 #endif
 
-template <bool NARROW>
-__global__ void __launch_bounds__(TcCfg<NARROW>::kThreads, TcCfg<NARROW>::kMinBlocks)
-tc_sa_kernel(const __grid_constant__ TcArgs a) {
-    using CFG = TcCfg<NARROW>;
-    constexpr int kTcThreads = CFG::kThreads, kTcChunkWarps = CFG::kChunkWarps, kTmemCols = CFG::kTmemCols;
-    constexpr uint32_t D_COL = CFG::D;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar;     // MMA completion
-    __shared__ __align__(8) uint64_t s_wbar;     // a tile of the streamed last layer landed in the ring
-    __shared__ __align__(8) uint64_t s_rbar;     // resident weights landed (once)
-    __shared__ uint32_t s_tmem;
-    __shared__ float s_red[kTcThreads / 32][32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int warp_u = (int)warp_uniform((uint32_t)warp);   // provably warp-uniform copy: warp 0 is the MMA issuer
-    const int quarter = warp_u & 3, cs = warp_u >> 2;  // rows 32*quarter.., column-chunk slot
-    const int row = quarter * 32 + lane;
-    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const TcSmemLayout L = tc_layout(a);
-    const int last = a.nl - 1;
-
-    // ---- one-time setup: TMEM, barriers, resident weights (bulk copies), per-channel vectors ----
-    if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar, 1); mbar_init(&s_rbar, 1); fence_mbar_init(); }
-    float* vec = reinterpret_cast<float*>(base + L.vec);
-    float* w1x = vec;                       // 3*C1
-    float* s1 = vec + 3 * a.C1;
-    float* t1 = s1 + a.C1;
-    float* sl[kMaxTcLayers];
-    float* tl[kMaxTcLayers];
-    {
-        float* p = t1 + a.C1;
-        for (int l = 0; l < a.nl; ++l) { sl[l] = p; tl[l] = p + a.Ntot[l]; p += 2 * a.Ntot[l]; }
-    }
-    for (int i = tid; i < 3 * a.C1; i += kTcThreads) w1x[i] = __ldg(a.w1x + i);
-    for (int i = tid; i < a.C1; i += kTcThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
-    for (int l = 0; l < a.nl; ++l)
-        for (int i = tid; i < a.Ntot[l]; i += kTcThreads) {
-            sl[l][i] = a.s[l] ? __ldg(a.s[l] + i) : 1.f;
-            tl[l][i] = __ldg(a.t[l] + i);
-        }
-    __syncthreads();                          // barrier inits visible before anybody arms / waits
-    // Ring protocol (streamed last layer): exactly one fill is outstanding or landed before every issue of that layer --
-    // the first one starts here, each later one right after the MMAs that read the ring have completed, and only if
-    // another issue follows (`more`), so nothing is in flight when the CTA exits.  No "pending" flag: the issuer warp's
-    // control flow stays trivially uniform (a loop-carried flag made the compiler clone the issue code onto a path it
-    // treats as divergent, which costs ~4 R2UR + ELECT per MMA).
-    uint32_t wphase = 0;
-    const uint32_t ring_bytes = (uint32_t)(a.Kd[last] / 64) * tc_block_bytes(tc_nt(a.Ntot[last], CFG::kNtCap));   // one n-tile of the last layer
-    if (tid == 0) {
-        uint32_t total = 0;
-        for (int l = 0; l < a.nl; ++l)
-            if (!(a.stream_last && l == last)) total += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
-        if (total) mbar_expect_tx(&s_rbar, total);
-        if (a.stream_last) mbar_expect_tx(&s_wbar, ring_bytes);
-        for (int l = 0; l < a.nl; ++l) {
-            const bool st_ = a.stream_last && l == last;
-            const uint32_t bytes = st_ ? ring_bytes : (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
-            for (uint32_t o = 0; o < bytes; o += 32768u)       // bulk copies of <= 32 KB
-                bulk_g2s(base + L.w[l] + o, a.image[l] + o, min(32768u, bytes - o), st_ ? &s_wbar : &s_rbar);
-        }
-        if (total) mbar_wait(&s_rbar, 0);
-    }
-    fence_before_thread_sync();
-    __syncthreads();
-    fence_after_thread_sync();
-    const uint32_t tmem_base = warp_uniform(s_tmem);
-    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t phase = 0;
-
-    const int G = 128 / a.K;
-    const long long ntiles = (a.groups + G - 1) / G;
-    __shared__ unsigned int s_tile[2];
-    if (tid == 0) s_tile[0] = atomicAdd(a.tile_counter, 1u);
-    __syncthreads();
-    int tpar = 0;
-#ifdef PSA_TC_TIMING
-    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-#endif
-    // (the tile index goes through a shuffle so that the compiler sees a warp-uniform loop: MMA issue stays on the uniform path)
-    for (long long tile = warp_uniform(s_tile[0]); tile < ntiles; tile = warp_uniform(s_tile[tpar])) {
-#ifdef PSA_TC_TIMING
-        if (tid == 0) tacc[7] += 1;
-#endif
-        // thread 0 claims the NEXT tile now; everybody reads it after this tile's barriers (s_tile is double-buffered)
-        long long next_tile = 0;
-        if (tid == 0) { const unsigned int t = atomicAdd(a.tile_counter, 1u); s_tile[tpar ^ 1] = t; next_tile = t; }
-        tpar ^= 1;
-        const long long g0 = tile * G;
-        const long long gid = g0 + row / a.K;
-        const bool valid = gid < a.groups;
-        // ---- layer 1 on the FMA pipe, straight into the A operand ----
-        {
-            float dx = 0.f, dy = 0.f, dz = 0.f;
-            const float* urow = nullptr;
-            if (valid) {
-                const long long bi = gid / a.m;
-                const int j = __ldg(a.idx + gid * a.K + (row % a.K));
-                const float* p = a.xyz + ((size_t)bi * a.n + j) * 3;
-                const float* c = a.new_xyz + (size_t)gid * 3;
-                dx = __ldg(p) - __ldg(c); dy = __ldg(p + 1) - __ldg(c + 1); dz = __ldg(p + 2) - __ldg(c + 2);
-                if (a.uf) urow = a.uf + ((size_t)bi * a.n + j) * a.C1;
-            }
-            for (int ch = cs; ch < a.C1 / 32; ch += kTcChunkWarps) {
-                float h[32];
-                if (urow) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 u = __ldg(reinterpret_cast<const float4*>(urow + ch * 32) + q);
-                        h[4 * q] = u.x; h[4 * q + 1] = u.y; h[4 * q + 2] = u.z; h[4 * q + 3] = u.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) h[q] = 0.f;
-                }
-                const float4* wx4 = reinterpret_cast<const float4*>(w1x + ch * 32);
-                const float4* wy4 = reinterpret_cast<const float4*>(w1x + a.C1 + ch * 32);
-                const float4* wz4 = reinterpret_cast<const float4*>(w1x + 2 * a.C1 + ch * 32);
-                const float4* s4 = reinterpret_cast<const float4*>(s1 + ch * 32);
-                const float4* t4 = reinterpret_cast<const float4*>(t1 + ch * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 wx = wx4[q], wy = wy4[q], wz = wz4[q], sc = s4[q], sh = t4[q];
-                    float v0 = fmaf(fmaf(dz, wz.x, fmaf(dy, wy.x, fmaf(dx, wx.x, h[4 * q + 0]))), sc.x, sh.x);
-                    float v1 = fmaf(fmaf(dz, wz.y, fmaf(dy, wy.y, fmaf(dx, wx.y, h[4 * q + 1]))), sc.y, sh.y);
-                    float v2 = fmaf(fmaf(dz, wz.z, fmaf(dy, wy.z, fmaf(dx, wx.z, h[4 * q + 2]))), sc.z, sh.z);
-                    float v3 = fmaf(fmaf(dz, wz.w, fmaf(dy, wy.w, fmaf(dx, wx.w, h[4 * q + 3]))), sc.w, sh.w);
-                    if (a.relu1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                    h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
-                    h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
-                }
-                store_a_chunk<CFG>(row_taddr, ch, h);
-            }
-        }
-        tmem_st_wait();
-        fence_before_thread_sync();
-        __syncthreads();
-        TC_STAMP(0);
-        for (int l = 0; l < a.nl; ++l) {
-            // (per-layer shapes are indexed dynamically out of the parameter struct: through a shuffle, so that the
-            //  branches on them -- and the MMA issue inside -- stay on the warp-uniform path)
-            const int Nt = (int)warp_uniform((uint32_t)tc_nt(a.Ntot[l], CFG::kNtCap));
-            const int NT = (int)warp_uniform((uint32_t)a.Ntot[l]) / Nt, KC = (int)warp_uniform((uint32_t)a.Kd[l]) / 64;
-            const bool streamed = a.stream_last && l == last;
-            for (int nt = 0; nt < NT; ++nt) {
-                if (warp_u == 0) {                  // converged warp, elected lane issues (tc_common.cuh)
-                    // this tile's weights are in the ring / resident (an UNCONDITIONAL wait -- on the long-completed
-                    // resident barrier when nothing is streamed -- keeps the compiler's view of this warp converged)
-                    mbar_wait(streamed ? &s_wbar : &s_rbar, streamed ? wphase : 0u);
-                    wphase ^= streamed ? 1u : 0u;
-                    __syncwarp();
-                    fence_after_thread_sync();
-                    const uint32_t blocks = smem_u32(base + L.w[l]) + (streamed ? 0u : (uint32_t)nt * KC * tc_block_bytes(Nt));
-                    issue_tile<CFG>(tmem_base, blocks, KC, Nt);
-                    mma_commit(&s_mbar);
-                }
-                TC_STAMP(l == last ? 4 : 1);
-                mbar_wait(&s_mbar, phase);
-                phase ^= 1u;
-                fence_after_thread_sync();
-                TC_STAMP(l == last ? 5 : 2);
-                if (warp_u == 0 && streamed) {
-                    // the ring is free again: fetch the next tile (wrapping to tile 0 for the next row tile) if one follows
-                    const bool more = (nt + 1 < NT) || (__shfl_sync(0xffffffffu, next_tile, 0) < ntiles);
-                    if (more && lane == 0) {
-                        const int ring_tile = (nt + 1) % NT;
-                        mbar_expect_tx(&s_wbar, ring_bytes);
-                        for (uint32_t o = 0; o < ring_bytes; o += 32768u)
-                            bulk_g2s(base + L.w[l] + o, a.image[l] + (size_t)ring_tile * ring_bytes + o, min(32768u, ring_bytes - o), &s_wbar);
-                    }
-                }
-                if (l != last) {
-                    for (int ch = cs; ch < Nt / 32; ch += kTcChunkWarps) {
-                        uint32_t d[32];
-                        tmem_ld32(row_taddr + D_COL + ch * 32, d);
-                        tmem_ld_wait();
-                        float h[32];
-                        const float4* s4 = reinterpret_cast<const float4*>(sl[l] + ch * 32);
-                        const float4* t4 = reinterpret_cast<const float4*>(tl[l] + ch * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 sc = s4[q], sh = t4[q];
-                            float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
-                            float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
-                            if (a.relu[l]) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                            h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
-                            h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
-                        }
-                        store_a_chunk<CFG>(row_taddr, ch, h);
-                    }
-                    tmem_st_wait();
-                    fence_before_thread_sync();
-                    __syncthreads();
-                    TC_STAMP(3);
-                } else {
-                    // rows of one neighbourhood span K/32 lane-quarters; warps sharing a chunk slot combine through s_red
-                    const int quarters_per_group = a.K / 32;        // 1, 2 or 4
-                    const long long wg = g0 + (quarter * 32) / a.K; // this warp's neighbourhood
-                    const int nch = Nt / 32;
-                    for (int ch0 = 0; ch0 < nch; ch0 += kTcChunkWarps) {      // uniform trip count: barriers inside
-                        const int ch = ch0 + cs;
-                        float mx = -FLT_MAX;
-                        if (ch < nch) {
-                            uint32_t d[32];
-                            tmem_ld32(row_taddr + D_COL + ch * 32, d);
-                            tmem_ld_wait();
-                            float v[32];
-                            const float4* s4 = reinterpret_cast<const float4*>(sl[l] + nt * Nt + ch * 32);
-                            const float4* t4 = reinterpret_cast<const float4*>(tl[l] + nt * Nt + ch * 32);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 sc = s4[q], sh = t4[q];
-                                float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
-                                float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
-                                if (a.relu[l]) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                                v[4 * q + 0] = valid ? v0 : -FLT_MAX; v[4 * q + 1] = valid ? v1 : -FLT_MAX;
-                                v[4 * q + 2] = valid ? v2 : -FLT_MAX; v[4 * q + 3] = valid ? v3 : -FLT_MAX;
-                            }
-                            mx = warp_colmax_32x32(v, lane);
-                        }
-                        if (quarters_per_group > 1) {
-                            s_red[warp][lane] = mx;
-                            __syncthreads();
-                            if ((quarter % quarters_per_group) == 0)
-                                for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
-                            __syncthreads();
-                        }
-                        if (ch < nch && (quarter % quarters_per_group) == 0 && wg < a.groups)
-                            a.out[(size_t)wg * a.Ntot[l] + nt * Nt + ch * 32 + lane] = mx;
-                    }
-                    // D fully read by every warp before thread 0 may issue the next MMAs into it
-                    fence_before_thread_sync();
-                    __syncthreads();
-                    TC_STAMP(6);
-                }
-            }
-        }
-    }
-#ifdef PSA_TC_TIMING
-    if (tid == 0)
-        for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_timing[i], tacc[i]);
-#endif
-    __syncthreads();                          // (no ring fill is in flight here: see the ring protocol above)
-    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // tc_sa_dual_kernel -- levels with 128-wide layers (PointNet++ SA2: 131 -> 128 -> 128 -> 256 over 64-point neighbourhoods).
 //
-// tc_sa_kernel serialises "row work" (gather, BN/ReLU, operand split, max-pool: ~56 % of a tile) and the MMAs (~44 %),
-// and hides one behind the other only by putting TWO CTAs on an SM -- which needs the level to fit twice: 256 TMEM
-// columns and half the shared memory per CTA.  A 128-wide layer does not (A operand = 320 columns, W2 = 96 KB), so
-// the wide configuration ran one CTA per SM with the tensor pipe idle during row work and vice versa.
-// This kernel gets the overlap back inside ONE CTA:
+// One tile at a time per CTA serialises "row work" (gather, BN/ReLU, operand split, max-pool: ~56 % of a tile) and the MMAs
+// (~44 %); two CTAs per SM would hide one behind the other, but a 128-wide level does not fit twice (TMEM columns, 96 KB of
+// weights).  This kernel gets the overlap inside ONE CTA:
 //   * two independent ROW GROUPS of 8 warps, each with its own 128-row tile, its own 256 TMEM columns, its own MMA
 //     issuer (thread 0 of the group), mbarriers, named barrier and tile claims; while one group gathers / pools, the
 //     other group's MMAs run;
@@ -691,7 +334,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
             mbar_wait(&s_rbar, 0);
         }
     }
-    // ring protocol as in tc_sa_kernel: one fill outstanding or landed before every issue of the streamed layer
+    // ring protocol: one fill outstanding or landed before every issue of the streamed layer
     uint32_t wphase = 0;
     if (issuer && a.stream_last && lane == 0) {
         mbar_expect_tx(&s_wbar[g], L.ring_bytes);
@@ -913,64 +556,6 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     if (warp == 0) tmem_dealloc(s_tmem, 512);
 }
 
-// ---- self-test of one tensor layer: D[128 x N] = A[128 x K] . W[K x N] through exactly the device code above ----
-__global__ void __launch_bounds__(TcCfg<false>::kThreads, 1)
-tc_selftest_kernel(int Kd, int N, const float* __restrict__ A, const uint8_t* __restrict__ image, float* __restrict__ D) {
-    using CFG = TcCfg<false>;
-    constexpr int kTcChunkWarps = CFG::kChunkWarps, kTmemCols = CFG::kTmemCols;
-    constexpr uint32_t D_COL = CFG::D;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ __align__(8) uint64_t s_wbar;
-    __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int warp_u = (int)warp_uniform((uint32_t)warp);
-    const int quarter = warp_u & 3, cs = warp_u >> 2;
-    const int row = quarter * 32 + lane;
-    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar, 1); fence_mbar_init(); }
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t bytes = (uint32_t)tc_image_bytes(Kd, N);
-        mbar_expect_tx(&s_wbar, bytes);
-        for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(base + o, image + o, min(32768u, bytes - o), &s_wbar);
-        mbar_wait(&s_wbar, 0);
-    }
-    fence_before_thread_sync();
-    __syncthreads();
-    fence_after_thread_sync();
-    const uint32_t tmem_base = warp_uniform(s_tmem);
-    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int ch = cs; ch < Kd / 32; ch += kTcChunkWarps) {
-        float h[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) h[q] = A[(size_t)row * Kd + ch * 32 + q];
-        store_a_chunk<CFG>(row_taddr, ch, h);
-    }
-    tmem_st_wait();
-    fence_before_thread_sync();
-    __syncthreads();
-    if (warp_u == 0) {
-        fence_after_thread_sync();
-        issue_tile<CFG>(tmem_base, smem_u32(base), Kd / 64, tc_nt(N, 128));
-        mma_commit(&s_mbar);
-    }
-    mbar_wait(&s_mbar, 0);
-    fence_after_thread_sync();
-    for (int ch = cs; ch < N / 32; ch += kTcChunkWarps) {
-        uint32_t d[32];
-        tmem_ld32(row_taddr + D_COL + ch * 32, d);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) D[(size_t)row * N + ch * 32 + q] = __uint_as_float(d[q]);
-    }
-    fence_before_thread_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
 // Dense layer on the tensor cores: out = relu?((x . W) * scale + shift), optional max over runs of pool_k rows.
 // CTA = 128 rows x Nt output channels.  K is walked in segments of 128: per segment the row warps quantise their x
@@ -998,156 +583,8 @@ struct TcDenseArgs {
     float* stat_partial = nullptr;     // (row tiles, 2, N) or null
 };
 
-template <bool NARROW>
-__global__ void __launch_bounds__(TcCfg<NARROW>::kThreads, TcCfg<NARROW>::kMinBlocks)
-tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
-    using CFG = TcCfg<NARROW>;
-    constexpr int kTcThreads = CFG::kThreads, kTmemCols = CFG::kTmemCols;
-    constexpr uint32_t D_COL = CFG::D;
-    constexpr int SEGB = NARROW ? 1 : 2;              // 64-K weight blocks per segment (A operand capacity)
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ __align__(8) uint64_t s_wbar[2];
-    __shared__ uint32_t s_tmem;
-    __shared__ float s_red[kTcThreads / 32][32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int warp_u = (int)warp_uniform((uint32_t)warp);
-    const int quarter = warp_u & 3, cs = warp_u >> 2;
-    const int row = quarter * 32 + lane;
-    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int Nt = tc_nt(a.N, CFG::kNtCap), KCtot = a.Kp / 64;
-    const uint32_t bb = tc_block_bytes(Nt);
-    const uint32_t slot_bytes = (uint32_t)SEGB * bb;
-    const int nt = blockIdx.y;
-    const long long row0 = (long long)blockIdx.x * 128;
-    const long long grow = row0 + row;
-    const bool valid = grow < a.rows;
-    const int nseg = (KCtot + SEGB - 1) / SEGB;
-    const uint8_t* img = a.image + (size_t)nt * KCtot * bb;
-
-    if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_wbar[0], 1); mbar_init(&s_wbar[1], 1); fence_mbar_init(); }
-    __syncthreads();
-    auto load_seg = [&](int sg) {       // thread 0 only
-        const int kcs = min(SEGB, KCtot - SEGB * sg);
-        const uint32_t bytes = (uint32_t)kcs * bb;
-        uint64_t* bar = &s_wbar[sg & 1];
-        mbar_expect_tx(bar, bytes);
-        for (uint32_t o = 0; o < bytes; o += 32768u)
-            bulk_g2s(base + (sg & 1) * slot_bytes + o, img + (size_t)sg * slot_bytes + o, min(32768u, bytes - o), bar);
-    };
-    if (tid == 0) load_seg(0);
-    fence_before_thread_sync();
-    __syncthreads();
-    fence_after_thread_sync();
-    const uint32_t tmem_base = warp_uniform(s_tmem);
-    const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t phase = 0;
-    const bool vec_ok = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
-    float acc[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) acc[q] = 0.f;
-    const bool has_out_chunk = cs < Nt / 32;
-
-    for (int sg = 0; sg < nseg; ++sg) {
-        const int kcs = min(SEGB, KCtot - SEGB * sg);
-        // ---- this warp's 32-wide chunk of the segment's x columns -> A operand ----
-        if (cs < kcs * 2) {
-            const int k0 = sg * (SEGB * 64) + cs * 32;
-            float h[32];
-            const float* xr = a.x + (size_t)(valid ? grow : 0) * a.K + k0;
-            if (valid && vec_ok && k0 + 32 <= a.K) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 u = __ldg(reinterpret_cast<const float4*>(xr) + q);
-                    h[4 * q] = u.x; h[4 * q + 1] = u.y; h[4 * q + 2] = u.z; h[4 * q + 3] = u.w;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) h[q] = (valid && k0 + q < a.K) ? __ldg(xr + q) : 0.f;
-            }
-            store_a_chunk<CFG>(row_taddr, cs, h);
-        }
-        tmem_st_wait();
-        fence_before_thread_sync();
-        __syncthreads();
-        if (warp_u == 0) {                      // converged warp, elected lane issues (tc_common.cuh)
-            mbar_wait(&s_wbar[sg & 1], (uint32_t)((sg >> 1) & 1));
-            fence_after_thread_sync();
-            issue_tile<CFG>(tmem_base, smem_u32(base + (sg & 1) * slot_bytes), kcs, Nt);
-            mma_commit(&s_mbar);
-            if (lane == 0 && sg + 1 < nseg) load_seg(sg + 1);    // the other slot's MMAs (segment sg-1) completed before this segment began
-        }
-        mbar_wait(&s_mbar, phase);
-        phase ^= 1u;
-        fence_after_thread_sync();
-        if (has_out_chunk) {
-            uint32_t d[32];
-            tmem_ld32(row_taddr + D_COL + cs * 32, d);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(d[q]);
-        }
-        fence_before_thread_sync();       // D read / A free before the next segment overwrites them (barrier at loop top)
-    }
-    // ---- epilogue ----
-    const int col0 = nt * Nt + cs * 32;
-    float v[32];
-    if (has_out_chunk) {
-        float sx3 = 0.f, sy3 = 0.f, sz3 = 0.f;
-        if (a.xyz3 != nullptr && valid) {
-            sx3 = __ldg(a.xyz3 + (size_t)grow * 3); sy3 = __ldg(a.xyz3 + (size_t)grow * 3 + 1); sz3 = __ldg(a.xyz3 + (size_t)grow * 3 + 2);
-        }
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            const float sc = a.scale ? __ldg(a.scale + col0 + q) : 1.f;
-            const float sh = a.shift ? __ldg(a.shift + col0 + q) : 0.f;
-            if (a.xyz3 != nullptr)
-                acc[q] = fmaf(sz3, __ldg(a.w3 + 2 * a.N + col0 + q), fmaf(sy3, __ldg(a.w3 + a.N + col0 + q), fmaf(sx3, __ldg(a.w3 + col0 + q), acc[q])));
-            float x = fmaf(acc[q], sc, sh);
-            if (a.relu) x = fmaxf(x, 0.f);
-            v[q] = x;
-        }
-    }
-    if (a.pool_k == 1) {
-        if (has_out_chunk && valid) {
-            float4* o = reinterpret_cast<float4*>(a.out + (size_t)grow * a.N + col0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-    } else {
-        const bool big = a.pool_k > 128;                         // the whole 128-row tile lies inside one group
-        const int quarters_per_group = big ? 4 : a.pool_k / 32;
-        const long long wg = (row0 + quarter * 32) / a.pool_k;
-        float mx = -FLT_MAX;
-        if (has_out_chunk) {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = valid ? v[q] : -FLT_MAX;
-            mx = warp_colmax_32x32(v, lane);
-        }
-        if (quarters_per_group > 1) {
-            s_red[warp][lane] = mx;
-            __syncthreads();
-            if ((quarter % quarters_per_group) == 0)
-                for (int o = 1; o < quarters_per_group; ++o) mx = fmaxf(mx, s_red[warp + o][lane]);
-        }
-        if (has_out_chunk && (quarter % quarters_per_group) == 0 && row0 + quarter * 32 < a.rows) {
-            if (!big) {
-                a.out[(size_t)wg * a.N + col0 + lane] = mx;
-            } else {
-                // out was pre-filled with the order-preserving int code of -inf; decoded after the kernel
-                int code = __float_as_int(mx);
-                code = code >= 0 ? code : code ^ 0x7fffffff;
-                atomicMax(reinterpret_cast<int*>(a.out) + (size_t)wg * a.N + col0 + lane, code);
-            }
-        }
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// tc_dense2_kernel -- the dense layer as a software pipeline (replaces tc_dense_kernel on the default path).
+// tc_dense2_kernel -- the dense layer as a software pipeline.
 //   CTA = 128 rows x Nt output channels (Nt = 128, or 64 for a 64-wide layer), 17 warps, one CTA per SM:
 //   * 16 ROW warps (quarter = w & 3 -> TMEM lanes, slot = w >> 2 -> 32-column chunk) quantise their chunk of the next
 //     K = 128 segment of x into bf16x3 pieces in one of TWO A-operand buffers in TMEM, while
@@ -1155,7 +592,7 @@ tc_dense_kernel(const __grid_constant__ TcDenseArgs a) {
 //     into a two-slot shared-memory ring, refilled as soon as the MMAs that read a slot have completed) and for D to
 //     be drained, then issues the segment's six-term MMAs and commits;
 //   * the row warps add each segment's D to fp32 register accumulators (the truncating TMEM accumulation never runs
-//     over more than 128 K), then run the epilogue of tc_dense_kernel (affine, ReLU, xyz side input, max-pool).
+//     over more than 128 K), then run the epilogue (affine, ReLU, xyz side input, max-pool).
 //   A-preparation of segment s+1 overlaps the MMAs of segment s; all hand-offs are mbarriers, no CTA-wide barrier
 //   inside the K loop.   TMEM: D 128 | A[0] 192 | A[1] 192 columns.
 // ------------------------------------------------------------------------------------------------------------------
@@ -1313,7 +750,7 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
             if (lane == 0) mbar_arrive(&s_dfree);
             TC_STAMP(4);
         }
-        // ---- epilogue (as tc_dense_kernel) ----
+        // ---- epilogue ----
         const int col0 = nt * NT_ + cs * 32;
         float v[32];
         if (has_out_chunk) {
@@ -1631,14 +1068,8 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
 }
 size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
 
-static int g_tc_dense_narrow = 1;
-static int g_tc_dense_v2 = 1;     // 1: pipelined tc_dense2_kernel (bf16x3 images); 0: tc_dense_kernel (psa_set_mlp_mode(2))
-static int g_tc_dense_v3 = 1;     // 1: 128-wide layers with K <= 512 use the transposed tc_dense3_kernel (off together with v2 in mode 2)
-static int g_tc_sa_dual = 1;      // 0: 128-wide levels fall back to the one-tile-per-CTA wide kernel (psa_set_mlp_mode(2), A/B runs)
-int tc_dense_nt(int N) {
-    if (g_tc_dense_v2) return ((N % 128) == 0 ? 128 : 64) | kImageBf16x3;
-    return tc_nt(N, g_tc_dense_narrow ? 64 : 128);
-}
+// tile width of a dense layer's weight image (the flag marks the three-bf16-piece format, the only one left)
+int tc_dense_nt(int N) { return ((N % 128) == 0 ? 128 : 64) | kImageBf16x3; }
 
 static void build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st);
 
@@ -1647,57 +1078,41 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
                     const float* shift, float* out, const uint8_t* image, cudaStream_t st, const float* xyz3 = nullptr,
                     const float* w3 = nullptr, bool prebuilt = false) {
     const int Kp = (K + 63) & ~63;
-    const bool narrow = g_tc_dense_narrow != 0;
     const int nt_img = tc_dense_nt(N);
     const int Nt = nt_img & ~kImageBf16x3;
     if (!prebuilt) build_image(K, Kp, N, nt_img, W, const_cast<uint8_t*>(image), st);
     TcDenseArgs a;
     a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
     a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out; a.xyz3 = xyz3; a.w3 = w3;
-    if (g_tc_dense_v2) {
-        dim3 grid2((unsigned)((rows + 127) / 128), N / Nt);
-        if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
-        if (Nt == 128 && Kp <= 512 && g_tc_dense_v3) {
-            const size_t smem3 = 4 * (size_t)TcDense3::kBlock + 1024;
-            PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            tc_dense3_kernel<<<grid2, TcDense3::kThreads, smem3, st>>>(a);
-            if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
-            return check_launch("tc_dense3_kernel");
-        }
-        const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt) + 1024;      // two slots of two 64-K blocks
-        if (Nt == 128) {
-            PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            tc_dense2_kernel<128><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
-        } else {
-            PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            tc_dense2_kernel<64><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
-        }
-        if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
-        return check_launch("tc_dense2_kernel");
-    }
-    dim3 grid((unsigned)((rows + 127) / 128), N / Nt);
+    dim3 grid2((unsigned)((rows + 127) / 128), N / Nt);
     if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
-    if (narrow) {
-        // two slots of one block; two CTAs (256 TMEM columns each) per SM
-        const size_t smem = 2 * (size_t)tc_block_bytes(Nt) + 1024;
-        PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_dense_kernel<true><<<grid, TcCfg<true>::kThreads, smem, st>>>(a);
+    if (Nt == 128 && Kp <= 512) {
+        // transposed kernel, both operands from shared memory
+        const size_t smem3 = 4 * (size_t)TcDense3::kBlock + 1024;
+        PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        tc_dense3_kernel<<<grid2, TcDense3::kThreads, smem3, st>>>(a);
+        if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
+        return check_launch("tc_dense3_kernel");
+    }
+    const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt) + 1024;      // two slots of two 64-K blocks
+    if (Nt == 128) {
+        PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        tc_dense2_kernel<128><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
     } else {
-        // two slots of two blocks; >= 120 KB requested so that only one CTA (all 512 TMEM columns) lands on an SM
-        size_t smem = 4 * (size_t)tc_block_bytes(Nt) + 1024;
-        if (smem < 120 * 1024) smem = 120 * 1024;
-        PSA_CUDA(cudaFuncSetAttribute(tc_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_dense_kernel<false><<<grid, TcCfg<false>::kThreads, smem, st>>>(a);
+        PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        tc_dense2_kernel<64><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
     }
     if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
-    return check_launch("tc_dense_kernel");
+    return check_launch("tc_dense2_kernel");
 }
 
 
 // Training-mode forward of one layer on tc_dense3: y = relu(bn_prev(x)) . W + bias (pre-BN output), per-row-tile column
 // statistics.  The weights change every step, so the image is rebuilt into `image_ws` (tc_dense_image_bytes(K, N)) per call.
 bool tc_train_fwd_eligible(long long rows, int K, int N) {
-    return g_tc_dense_v3 && g_tc_dense_v2 && rows >= 128 && K >= 32 && K <= 512 && N >= 128 && (N % 128) == 0;
+    // one CTA per 128-row tile with ~14 k cycles of fixed prologue / epilogue: pays off from two K blocks up (K = 64 layers over
+    // 500 k rows run faster on the fp32 FMA kernel: 268 vs 302 us measured at SA1's 64 -> 128 layer)
+    return rows >= 128 && K >= 128 && K <= 512 && N >= 128 && (N % 128) == 0;
 }
 int launch_tc_dense_train(long long rows, int K, int N, const float* x, const float* in_scale, const float* in_shift, int in_relu,
                           const float* W, const float* bias, float* y, float* stat_partial, uint8_t* image_ws, cudaStream_t st) {
@@ -1717,8 +1132,7 @@ int launch_tc_dense_train(long long rows, int K, int N, const float* x, const fl
 // A prebuilt image (psa_prepare_weight_image) is used when it matches; otherwise the image is (re)built into `ws`.
 // `Nt` may carry kImageBf16x3 (three-bf16-piece image for tc_sa_dual_kernel).
 static void build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st) {
-    if (Nt & kImageBf16x3) tc_prep_weights3_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt & ~kImageBf16x3, W, image);
-    else tc_prep_weights_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt, W, image);
+    tc_prep_weights3_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt & ~kImageBf16x3, W, image);
 }
 static const uint8_t* use_or_build_image(const psa_mlp* mlp, int l, int row0, int N, int Nt, uint8_t* ws, cudaStream_t st) {
     if (mlp->image[l] != nullptr && mlp->image_nt[l] == Nt && mlp->image_row0[l] == row0) return reinterpret_cast<const uint8_t*>(mlp->image[l]);
@@ -1747,22 +1161,11 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
         if (is_last && !(a.Ntot[l] == 64 || a.Ntot[l] % 128 == 0)) return false;
         all += tc_image_bytes(a.Kd[l], a.Ntot[l]);
     }
-    bool all64 = (C1 == 64);
-    for (int l = 0; l < a.nl; ++l) all64 = all64 && a.Kd[l] == 64;
-    if (g_tc_sa_dual) {
-        // two row groups per CTA, bf16x3 operands, 64-wide tiles; the last layer is streamed per group if it does not fit
-        a.dual = 1; a.ntcap = 64; a.stream_last = 0;
-        if (tc_dual_layout(a).total + 1024 > 226u * 1024u) a.stream_last = 1;
-        if (tc_dual_layout(a).total + 1024 <= 226u * 1024u) { *out = a; return true; }
-        a.dual = 0;
-    }
-    a.ntcap = all64 ? 64 : 128;
-    const uint32_t budget = all64 ? 100 * 1024 : 200 * 1024;      // narrow: two CTAs share the SM
-    a.stream_last = 0;
-    if (tc_layout(a).total + 1024 > budget) {
-        a.stream_last = 1;
-        if (tc_layout(a).total + 1024 > budget) return false;
-    }
+    // two row groups per CTA, bf16x3 operands, 64-wide tiles; the last layer is streamed per group if it does not fit; a level
+    // that does not fit even then runs on the fp32-FMA fused kernel
+    a.dual = 1; a.ntcap = 64; a.stream_last = 0;
+    if (tc_dual_layout(a).total + 1024 > 226u * 1024u) a.stream_last = 1;
+    if (tc_dual_layout(a).total + 1024 > 226u * 1024u) return false;
     (void)all;
     *out = a;
     return true;
@@ -1776,7 +1179,7 @@ size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
 }
 
 // tile width (with the image-format flag) of the tensor layers of a level
-static int tc_sa_image_nt(const TcArgs& a, int N) { return a.dual ? (TcDual::kNt | kImageBf16x3) : tc_nt(N, a.ntcap); }
+static int tc_sa_image_nt(const TcArgs&, int) { return TcDual::kNt | kImageBf16x3; }
 
 int launch_tc_sa(TcArgs& a, cudaStream_t st) {
     const int G = 128 / a.K;
@@ -1797,52 +1200,21 @@ int launch_tc_sa(TcArgs& a, cudaStream_t st) {
         }
         return check_launch("tc_sa_dual_kernel");
     }
-    const TcSmemLayout L = tc_layout(a);
-    size_t smem = (size_t)L.total + 1024;
-    const bool narrow = a.ntcap == 64;
-    long long ctas = narrow ? 2 * kNumSMs : kNumSMs;
-    if (ctas > ntiles) ctas = ntiles;
-    if (ctas < 1) ctas = 1;
-    if (narrow) {
-        PSA_CUDA(cudaFuncSetAttribute(tc_sa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_sa_kernel<true><<<(int)ctas, TcCfg<true>::kThreads, smem, st>>>(a);
-    } else {
-        if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
-        PSA_CUDA(cudaFuncSetAttribute(tc_sa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_sa_kernel<false><<<(int)ctas, TcCfg<false>::kThreads, smem, st>>>(a);
-    }
-    return check_launch("tc_sa_kernel");
+    set_error("tc_sa: level not eligible for the dual-group kernel");
+    return PSA_ERR_UNSUPPORTED;
 }
 
 }  // namespace psa
 
 using namespace psa;
 
-// Diagnostic entry point (not part of the reference's op surface): one 128-row tile through one tensor-core layer.
-// `scratch` must hold 6*Kd*N bytes (the weight image).
-extern "C" PSA_API int psa_tc_selftest(int Kd, int N, const float* A, const float* W, float* D, void* scratch, psa_stream_t stream) {
-    PSA_REQUIRE((Kd == 64 || Kd == 128) && (N == 64 || N == 128), "tc_selftest: Kd, N must be 64 or 128");
-    PSA_REQUIRE(A && W && D && scratch, "tc_selftest: null buffer");
-    cudaStream_t st = as_stream(stream);
-    tc_prep_weights_kernel<<<(Kd * N + 255) / 256, 256, 0, st>>>(Kd, Kd, N, tc_nt(N, 128), W, reinterpret_cast<uint8_t*>(scratch));
-    size_t smem = tc_image_bytes(Kd, N) + 1024;
-    if (smem < 120 * 1024) smem = 120 * 1024;
-    PSA_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, TcCfg<false>::kThreads, smem, st>>>(Kd, N, A, reinterpret_cast<const uint8_t*>(scratch), D);
-    return check_launch("tc_selftest_kernel");
-}
-
-// 0 = auto (tensor cores where the shapes allow, fp32 FMA otherwise); 1 = always the fp32-FMA kernels
-// 2 = like 0, but 128-wide levels use the one-tile-per-CTA wide kernel instead of the dual-group kernel (A/B measurements)
 static int g_mlp_mode = 0;
 extern "C" PSA_API int psa_set_mlp_mode(int mode) {
-    PSA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_mlp_mode: mode must be 0 (auto), 1 (fp32 FMA) or 2 (auto, legacy wide kernel)");
-    g_mlp_mode = (mode == 1) ? 1 : 0;
-    g_tc_sa_dual = (mode == 2) ? 0 : 1;
-    g_tc_dense_v2 = (mode == 2) ? 0 : 1;
+    PSA_REQUIRE(mode == 0 || mode == 1, "set_mlp_mode: mode must be 0 (tensor cores where the shapes allow) or 1 (fp32 FMA kernels only)");
+    g_mlp_mode = mode;
     return PSA_OK;
 }
-extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode ? 1 : (g_tc_sa_dual ? 0 : 2); }
+extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode; }
 
 extern "C" size_t psa_sa_module_workspace_bytes(int b, int n, int m, int c, int nsample, const psa_mlp* mlp) {
     (void)m;
@@ -1888,7 +1260,7 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
             a.image[l] = use_or_build_image(mlp, 1 + l, 0, N, tc_sa_image_nt(a, N), ws, st);
             ws += (tc_image_bytes(K, N) + 255) & ~(size_t)255;
         }
-        rc = check_launch("tc_prep_weights_kernel");
+        rc = check_launch("tc_prep_weights3_kernel");
         if (rc != PSA_OK) return rc;
         if (c > 0) {
             // U = points . W1[3:,:]  once per source point (rows b*n), raw (affine + ReLU are applied after the xyz part)
@@ -2140,7 +1512,7 @@ extern "C" int psa_prepare_weight_image(int K, int N, int row0, int nt, const fl
     PSA_REQUIRE(W && image, "prepare_weight_image: null buffer");
     const int Ki = K - row0, Kp = (Ki + 63) & ~63;
     build_image(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image), as_stream(stream));
-    return check_launch("tc_prep_weights_kernel");
+    return check_launch("tc_prep_weights3_kernel");
 }
 
 extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, int nsample, const psa_mlp* mlp,

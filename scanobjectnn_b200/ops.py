@@ -19,7 +19,7 @@ __all__ = [
     "farthest_point_sample", "gather_point", "query_ball_point", "group_point", "select_top_k", "knn_point",
     "three_nn", "three_interpolate", "three_nn_interpolate", "pairwise_distance", "knn", "knn_graph",
     "get_edge_feature", "farthest_point_sample_and_gather", "MlpParams", "shared_mlp", "sa_module_infer",
-    "edgeconv_infer", "sa_conv1_prebn", "pool_rows", "sa_group_all_infer", "set_mlp_mode", "get_mlp_mode", "tc_selftest",
+    "edgeconv_infer", "sa_conv1_prebn", "pool_rows", "sa_group_all_infer", "set_mlp_mode", "get_mlp_mode",
 ]
 
 
@@ -603,13 +603,3 @@ def get_mlp_mode() -> int:
     return int(_lib.load().psa_get_mlp_mode())
 
 
-def tc_selftest(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """Diagnostic: a (128,Kd) . w (Kd,N) through one tensor-core layer (three-term split) -> (128,N)."""
-    a = _dev(a, torch.float32, "a", 2)
-    w = _dev(w, torch.float32, "w", 2)
-    if a.shape[0] != 128 or a.shape[1] != w.shape[0]:
-        raise ValueError("tc_selftest expects a (128,Kd) and w (Kd,N)")
-    d = torch.empty((128, w.shape[1]), dtype=torch.float32, device=a.device)
-    scratch = torch.empty(6 * w.numel(), dtype=torch.uint8, device=a.device)
-    check(_lib.load().psa_tc_selftest(a.shape[1], w.shape[1], _ptr(a), _ptr(w), _ptr(d), _ptr(scratch), _stream()), "tc_selftest")
-    return d

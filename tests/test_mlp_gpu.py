@@ -23,11 +23,10 @@ def _store(seed=0):
     return VariableStore(device="cuda", seed=seed)
 
 
-@pytest.fixture(params=["tensor", "fma", "tensor_wide"])
+@pytest.fixture(params=["tensor", "fma"])
 def mlp_mode(request):
-    """0 = auto (tcgen05 operand-split kernels where the shapes allow), 1 = fp32 FMA kernels, 2 = auto with the legacy
-    one-tile-per-CTA kernel for 128-wide levels instead of the dual-group one"""
-    ops.set_mlp_mode({"tensor": 0, "fma": 1, "tensor_wide": 2}[request.param])
+    """0 = auto (tcgen05 operand-split kernels where the shapes allow), 1 = fp32 FMA kernels"""
+    ops.set_mlp_mode({"tensor": 0, "fma": 1}[request.param])
     yield request.param
     ops.set_mlp_mode(0)
 
