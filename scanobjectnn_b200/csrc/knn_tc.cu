@@ -143,15 +143,17 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = warp_uniform(s_tmem);
-    // pass 1 looks at every second candidate tile only: the k-th smallest of a SUBSET is still an upper bound of the k-th smallest
-    // of the whole cloud, the histogram work halves and pass 2 lists ~2k candidates instead of ~k
-    const int NT1 = (NT + 1) / 2;
+    // pass 1 could look at a subset of the tiles (the k-th smallest of a SUBSET is still an upper bound of the k-th smallest of the
+    // cloud): measured, every second tile halves the histogram work but doubles the lists -- 1-3 % of the rows of a feature cloud then
+    // overflow kKtCap and the exhaustive kernel costs more than was saved (716 -> 1218 us at C = 64).  So: every tile.
+    constexpr int kStride1 = 1;
+    const int NT1 = (NT + kStride1 - 1) / kStride1;
     const int J = NT1 + NT;                          // jobs: pass 1 tiles (0, 2, 4, ..), then every pass 2 tile
 
     if (warp_u == 8) {
         // ================= issuer / loader warp =================
         auto load = [&](int j) {
-            const int s = j & 1, t = j < NT1 ? 2 * j : j - NT1;
+            const int s = j & 1, t = j < NT1 ? kStride1 * j : j - NT1;
             const uint32_t bytes = j < NT1 ? kKtPiece : kKtBlock;                  // pass 1 needs the leading piece only
             if (lane == 0) {
                 mbar_expect_tx(&s_full[s], bytes);
@@ -217,8 +219,13 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         const unsigned hinc = r < 64 ? 1u : 65536u;
         unsigned* hcol = hist + (r & 63);
         // ---- pass 1: coarse distances -> histogram ----
+        // Running cut: once the bins at or above `bmin` already hold k candidates, the k-th smallest can only move towards
+        // smaller distances, so farther candidates (bin < bmin) no longer matter and their shared-memory atomics are skipped --
+        // after the first tiles ~99 % of them.  (Counts of the bins >= bmin stay exact; the final scan never goes below bmin.)
+        int bmin = 0;
+        const bool is_r_lo = r < 64;
         for (int t1 = 0; t1 < NT1; ++t1) {
-            const int s = t1 & 1, t = 2 * t1;
+            const int s = t1 & 1, t = kStride1 * t1;
             mbar_wait(&s_dfull[s], (uint32_t)((t1 >> 1) & 1));
             fence_after_thread_sync();
             for (int ch = 0; ch < 2; ++ch) {
@@ -231,12 +238,17 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
                     const int key = (int)(__float_as_uint(fmaxf(dist, 1e-30f)) >> 19);      // NaN -> 1e-30: lands in the last bin
                     const int bin = min(max(keymax - key, 0), kKtBins - 1);
-                    atomicAdd(hcol + bin * 64, hinc);            // fire-and-forget: no dependent chain through shared memory
+                    if (bin >= bmin) atomicAdd(hcol + bin * 64, hinc);   // fire-and-forget: no dependent chain through shared memory
                 }
             }
             fence_before_thread_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive1(&s_dfree[s]);
+            if ((t1 & (t1 + 1)) == 0 && t1 + 1 < NT1) {          // after tiles 0, 1, 3, 7, ..: tighten the cut
+                int cum = 0, b = kKtBins - 1;
+                for (; b > bmin; --b) { const unsigned w = hcol[b * 64]; cum += (int)(is_r_lo ? (w & 0xffffu) : (w >> 16)); if (cum >= a.k) break; }
+                bmin = max(bmin, b);
+            }
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");           // both halves of every row are in the histogram
         // ---- threshold: upper edge of the bin that holds the k-th smallest coarse distance, widened by the error bounds ----

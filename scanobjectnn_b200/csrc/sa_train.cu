@@ -483,6 +483,253 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Synchronous streaming F1 kernel: no warp specialisation.  In the producer / consumer kernel above the four consumer warps sit
+// at the FULL barrier ~80 % of the time (the exhaustive search is the long pole, the stores are fire-and-forget), so here ALL
+// eight warps do every phase of a batch in turn:
+//   search    each warp holds PPT points per lane in registers (point k = 32 (warp + 8 i) + lane) and tests them against the
+//             batch's queries; one ballot per 32-point word IS that word of the query's hit bitmap;
+//   extract   8 lanes per query read the nsample lowest set bits out in order (idx rows, pts_cnt);
+//   rows      centred coordinates (dx,dy,dz,j) of the batch's rows into shared memory, idx to global memory;
+//   conv      LPR lanes per row x 4 channels, weights in registers, whole rows per store instruction (512 contiguous bytes),
+//             streaming stores, BN statistics in registers.
+// The stores of batch t drain while batch t+1 is searched; 2-3 CTAs per SM interleave their phases.  Batches ramp 2, 4, 8, 16
+// queries so the first stores leave ~3 us after launch.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kF1YBatch = 16;
+__host__ __device__ inline int f1y_batch_size(int t) { return t == 0 ? 2 : (t == 1 ? 4 : (t == 2 ? 8 : kF1YBatch)); }
+__host__ __device__ inline size_t f1y_smem_bytes(int n, int nsample, int ppt) {
+    const int bw = 8 * ppt < 32 ? 32 : 8 * ppt;
+    size_t rest = (size_t)kF1YBatch * bw * 4 + (size_t)kF1YBatch * nsample * (sizeof(int) + sizeof(float4)) + kF1YBatch * sizeof(float4);
+    if (rest < 8192 + 2048) rest = 8192 + 2048;              // the statistics epilogue reuses this area (up to 8 KB + 2 KB)
+    return (size_t)n * 16 + rest;
+}
+
+template <int NV, bool HAS_U, int PPT>
+__global__ void __launch_bounds__(kF1SThreads, PPT <= 8 ? 3 : 2)
+sa_conv1_sync_kernel(const __grid_constant__ F1SArgs a) {
+    constexpr int BW = 8 * PPT < 32 ? 32 : 8 * PPT;        // bitmap words per query
+    constexpr int LPR = NV * 8;                            // lanes per row (4 channels each): 16 (C1 = 64) or 32 (C1 = 128)
+    constexpr int RPI = 32 / LPR;                          // rows per store instruction
+    extern __shared__ __align__(16) float smem_f[];
+    const int n = a.n, K = a.nsample, C1 = a.C1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* cloud4 = reinterpret_cast<float4*>(smem_f);
+    unsigned* bitmaps = reinterpret_cast<unsigned*>(cloud4 + n);                                  // kF1YBatch x BW
+    int* sidx = reinterpret_cast<int*>(bitmaps + kF1YBatch * BW);                                 // kF1YBatch x K
+    float4* sd = reinterpret_cast<float4*>(sidx + kF1YBatch * K);                                 // kF1YBatch x K
+    float4* sctr = sd + kF1YBatch * K;                                                            // kF1YBatch
+    float* scratch = reinterpret_cast<float*>(bitmaps);                                           // epilogue reuse
+#ifdef PSA_F1_TIMING
+    if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 0] = gtime();
+#endif
+    for (int i = tid; i < kF1YBatch * BW; i += kF1SThreads) bitmaps[i] = 0u;     // words no warp owns (BW > 8 PPT) stay zero
+
+    // conv: this lane's four channels
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    const float4 wx4 = __ldg(reinterpret_cast<const float4*>(a.w1 + lc));
+    const float4 wy4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + lc));
+    const float4 wz4 = __ldg(reinterpret_cast<const float4*>(a.w1 + 2 * C1 + lc));
+    const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2 wxa = make_float2(wx4.x, wx4.y), wxb = make_float2(wx4.z, wx4.w), wya = make_float2(wy4.x, wy4.y), wyb = make_float2(wy4.z, wy4.w);
+    const float2 wza = make_float2(wz4.x, wz4.y), wzb = make_float2(wz4.z, wz4.w), ba = make_float2(b4.x, b4.y), bb = make_float2(b4.z, b4.w);
+    float2 ssum[2], ssq[2];
+    ssum[0] = ssum[1] = ssq[0] = ssq[1] = make_float2(0.f, 0.f);
+
+    const long long T = (long long)a.b * a.m;
+    const long long q_begin = T * blockIdx.x / gridDim.x, q_end = T * (blockIdx.x + 1) / gridDim.x;
+    bool first = true;
+    for (long long q = q_begin; q < q_end;) {
+        const long long cloud = q / a.m;
+        const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
+        const float* gx = a.xyz + (size_t)cloud * n * 3;
+        const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + lc : nullptr;
+        // ---- this cloud: PPT points per thread in registers, float4 copy in shared memory ----
+        __syncthreads();                                       // the previous cloud's copy / batch buffers are no longer read
+        float2 px[PPT / 2], py[PPT / 2], pz[PPT / 2];
+        unsigned valid = 0u;
+        const float pinf = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int k = 32 * (warp + 8 * i) + lane;
+            float x = pinf, y = pinf, z = pinf;                // slots past the cloud: out of reach of every finite query
+            if (k < n) {
+                x = __ldg(gx + 3 * k); y = __ldg(gx + 3 * k + 1); z = __ldg(gx + 3 * k + 2);
+                cloud4[k] = make_float4(x, y, z, __int_as_float(k));
+                valid |= 1u << i;
+            }
+            if (i & 1) { px[i >> 1].y = x; py[i >> 1].y = y; pz[i >> 1].y = z; }
+            else { px[i >> 1].x = x; py[i >> 1].x = y; pz[i >> 1].x = z; }
+        }
+        __syncthreads();
+#ifdef PSA_F1_TIMING
+        if (tid == 0 && a.tlog && first) a.tlog[blockIdx.x * 8 + 1] = gtime();
+#endif
+        long long gq0 = q;
+        for (int bi = 0; gq0 < seg_end; ++bi) {
+            const int nqb = min(f1y_batch_size(bi), (int)(seg_end - gq0));
+            // ---- search ----
+            float cqx = 0.f, cqy = 0.f, cqz = 0.f;
+            if (lane < nqb) {
+                const float* p2 = a.new_xyz + (size_t)(gq0 + lane) * 3;
+                cqx = __ldg(p2); cqy = __ldg(p2 + 1); cqz = __ldg(p2 + 2);
+                if (warp == 0) sctr[lane] = make_float4(cqx, cqy, cqz, 0.f);
+            }
+            if (!a.none) {
+                for (int qi = 0; qi < nqb; ++qi) {
+                    const float qx = __shfl_sync(0xffffffffu, cqx, qi), qy = __shfl_sync(0xffffffffu, cqy, qi), qz = __shfl_sync(0xffffffffu, cqz, qi);
+                    const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+                    unsigned mine = 0u;                        // lane i keeps word i of this warp's share, stored once
+                    const bool qfinite = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;   // warp-uniform
+                    if (qfinite) {
+#pragma unroll
+                        for (int i = 0; i < PPT; i += 2) {
+                            const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
+                            // !(d > thr): a NaN distance (NaN point) counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
+                            const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr));
+                            const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr));
+                            if (lane == i) mine = w0;
+                            if (lane == i + 1) mine = w1;
+                        }
+                    } else {
+                        // non-finite query: every distance is NaN = inside; only the slots past the cloud are masked out
+#pragma unroll
+                        for (int i = 0; i < PPT; i += 2) {
+                            const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
+                            const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr) && ((valid >> i) & 1u));
+                            const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr) && ((valid >> (i + 1)) & 1u));
+                            if (lane == i) mine = w0;
+                            if (lane == i + 1) mine = w1;
+                        }
+                    }
+                    if (lane < PPT) bitmaps[qi * BW + warp + 8 * lane] = mine;
+                }
+            }
+            __syncthreads();                                   // bitmaps complete
+#ifdef PSA_F1_TIMING
+            if (tid == 0 && a.tlog && first && bi == 0) a.tlog[blockIdx.x * 8 + 4] = gtime();
+#endif
+            // ---- bitmaps -> ordered idx rows: 8 lanes per query, 4 queries per warp pass ----
+            for (int q0 = warp * 4; q0 < nqb; q0 += 32) {
+                const int qi = q0 + (lane >> 3);
+                const bool act = qi < nqb;
+                const int cnt = bq_extract_bitmap_sub8<BW / 8>(bitmaps + qi * BW, K, sidx + qi * K, lane, act);
+                if (act && a.pts_cnt != nullptr && (lane & 7) == 0) a.pts_cnt[gq0 + qi] = cnt;
+            }
+            __syncthreads();                                   // idx rows complete
+            // ---- centred rows + idx to global memory ----
+            const int nrows = nqb * K;
+            int* gidx = a.idx + (size_t)gq0 * K;
+            for (int r = tid; r < nrows; r += kF1SThreads) {
+                const int j = sidx[r];
+                const float4 ctr = sctr[r / K];
+                const float4 pt = cloud4[j];
+                gidx[r] = j;
+                sd[r] = make_float4(pt.x - ctr.x, pt.y - ctr.y, pt.z - ctr.z, __int_as_float(j));
+            }
+            __syncthreads();
+#ifdef PSA_F1_TIMING
+            if (tid == 0 && a.tlog && first && bi == 0) a.tlog[blockIdx.x * 8 + 2] = gtime();
+#endif
+            // ---- conv + streaming stores: four rows per lane and trip, whole rows per store instruction ----
+            float* outl = a.pre + (size_t)gq0 * K * C1 + lc;
+            for (int r0 = warp * 4 * RPI; r0 < nrows; r0 += 8 * 4 * RPI) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u * RPI + lr;
+                    if (r < nrows) {
+                        const float4 d = sd[r];
+                        const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+                        float2 s0 = ba, s1 = bb;
+                        if (HAS_U) {
+                            const float4 uu = __ldg(reinterpret_cast<const float4*>(ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1));
+                            s0 = __fadd2_rn(s0, make_float2(uu.x, uu.y)); s1 = __fadd2_rn(s1, make_float2(uu.z, uu.w));
+                        }
+                        const float2 v0 = __ffma2_rn(dz, wza, __ffma2_rn(dy, wya, __ffma2_rn(dx, wxa, s0)));
+                        const float2 v1 = __ffma2_rn(dz, wzb, __ffma2_rn(dy, wyb, __ffma2_rn(dx, wxb, s1)));
+                        __stcs(reinterpret_cast<float4*>(outl + (unsigned)r * (unsigned)C1), make_float4(v0.x, v0.y, v1.x, v1.y));
+                        ssum[0] = __fadd2_rn(ssum[0], v0); ssum[1] = __fadd2_rn(ssum[1], v1);
+                        ssq[0] = __ffma2_rn(v0, v0, ssq[0]); ssq[1] = __ffma2_rn(v1, v1, ssq[1]);
+                    }
+                }
+            }
+            gq0 += nqb;
+            // (the next batch's search only writes the bitmaps; the batch buffers are rewritten after its first barrier, which every
+            //  warp reaches only after finishing this conv phase)
+        }
+        first = false;
+        q = seg_end;
+    }
+#ifdef PSA_F1_TIMING
+    if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 5] = gtime();
+#endif
+
+    if (a.stats != nullptr) {
+        __syncthreads();
+        float* sstat = scratch;                            // 8 warps x 2 x C1 floats = up to 8 KB
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                ssum[p].x += __shfl_xor_sync(0xffffffffu, ssum[p].x, o); ssum[p].y += __shfl_xor_sync(0xffffffffu, ssum[p].y, o);
+                ssq[p].x += __shfl_xor_sync(0xffffffffu, ssq[p].x, o); ssq[p].y += __shfl_xor_sync(0xffffffffu, ssq[p].y, o);
+            }
+            if (lane < LPR) {
+                float* w = sstat + (size_t)warp * 2 * C1;
+                const int c = lane * 4 + 2 * p;
+                *reinterpret_cast<float2*>(w + c) = ssum[p];
+                *reinterpret_cast<float2*>(w + C1 + c) = ssq[p];
+            }
+        }
+        __syncthreads();
+        float* dst = a.partial + (size_t)blockIdx.x * 2 * C1;
+        for (int e = tid; e < 2 * C1; e += kF1SThreads) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += sstat[(size_t)w * 2 * C1 + e];      // fixed order
+            dst[e] = t;
+        }
+        // last CTA to arrive adds the CTA partials (fp64) in a fixed tree: deterministic whatever the finishing order
+        __shared__ unsigned s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&g_f1_tickets[a.ticket], 1u) == gridDim.x - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int E4 = 2 * C1 / 4;                                     // 32 (C1 = 64) or 64 (C1 = 128)
+            const int RL = kF1SThreads / E4;                               // 8 or 4
+            const int e4 = tid % E4, rl = tid / E4;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const float4* part4 = reinterpret_cast<const float4*>(a.partial);
+            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 10 * RL) {
+                float4 v[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) {
+                    const unsigned p = p0 + u * RL;
+                    v[u] = p < gridDim.x ? __ldcg(part4 + (size_t)p * E4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 10; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+            }
+            double* sred = reinterpret_cast<double*>(scratch);             // RL x 2*C1 doubles = 8 KB
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sred[(size_t)rl * 2 * C1 + e4 * 4 + c] = acc[c];
+            __syncthreads();
+            for (int e = tid; e < 2 * C1; e += kF1SThreads) {
+                double t = 0.0;
+                for (int r = 0; r < RL; ++r) t += sred[(size_t)r * 2 * C1 + e];
+                a.stats[e] = (float)t;
+            }
+            if (tid == 0) g_f1_tickets[a.ticket] = 0u;
+        }
+    }
+#ifdef PSA_F1_TIMING
+    if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 6] = gtime();
+#endif
+}
+
 // stats[0..C1) = sum, stats[C1..2C1) = sum of squares, over all rows; CTA partials added in index order in fp64
 __global__ void f1_stats_reduce_kernel(int nparts, int twoC, const float* __restrict__ partial, float* __restrict__ stats) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,7 +752,8 @@ int launch_dense_raw(long long rows, int K, int N, const float* x, const float* 
     d.x = x; d.W = W; d.scale = nullptr; d.shift = nullptr; d.out = out;
     return launch_dense(d, st);
 }
-// 0 = streaming kernel where it applies, 1 = round-1 kernel; PSA_F1_VARIANT in the environment (A/B runs of tools/ only)
+// 0 = producer / consumer streaming kernel where it applies, 1 = round-1 kernel, 3 = synchronous streaming kernel;
+// PSA_F1_VARIANT in the environment (A/B runs of tools/ only)
 static int f1_variant() {
     static const int v = [] { const char* e = getenv("PSA_F1_VARIANT"); return e ? atoi(e) : 0; }();
     return v;
@@ -544,8 +792,8 @@ extern "C" size_t psa_sa_conv1_prebn_workspace_bytes(int b, int n, int m, int c,
         int q; dim3 g;
         f1_grid(b, m, &q, &g);
         size_t parts = (size_t)g.x * g.y;
-        if (parts < 2 * (size_t)kNumSMs) parts = 2 * (size_t)kNumSMs;
-        bytes += parts * 2 * C1 * sizeof(float) + 256 + 2 * (size_t)kNumSMs * 8 * sizeof(unsigned long long);   // CTA partials (+ timing stamps of debug builds)
+        if (parts < 3 * (size_t)kNumSMs) parts = 3 * (size_t)kNumSMs;      // the streaming kernels run up to 3 CTAs per SM
+        bytes += parts * 2 * C1 * sizeof(float) + 256 + 3 * (size_t)kNumSMs * 8 * sizeof(unsigned long long);   // CTA partials (+ timing stamps of debug builds)
     }
     return bytes;
 }
@@ -590,8 +838,29 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
                 s.ticket = (int)(call_no.fetch_add(1u) % kF1Tickets);
                 s.partial = reinterpret_cast<float*>(ws + 256);
 #ifdef PSA_F1_TIMING
-                s.tlog = reinterpret_cast<unsigned long long*>(ws + 256 + (size_t)2 * kNumSMs * 2 * C1 * sizeof(float));
+                s.tlog = reinterpret_cast<unsigned long long*>(ws + 256 + (size_t)3 * kNumSMs * 2 * C1 * sizeof(float));
 #endif
+            }
+            if (f1_variant() == 3) {
+                // synchronous kernel (all warps do every phase; A/B runs: 61 us vs 57 us for the producer / consumer kernel at SA1): points per thread 4 / 8 / 16 for n <= 1024 / 2048 / 4096
+                const int ppt = n <= 1024 ? 4 : (n <= 2048 ? 8 : 16);
+                const size_t ysm = f1y_smem_bytes(n, nsample, ppt);
+                const long long T = (long long)b * m;
+                const long long units = (T + 7) / 8;
+                const int per_sm = (ppt <= 8 && ysm <= 72 * 1024) ? 3 : 2;      // matches the kernel's __launch_bounds__
+                const int yctas = (int)(units < (long long)per_sm * kNumSMs ? units : (long long)per_sm * kNumSMs);
+#define PSA_F1Y_LAUNCH(NV_, U_, PPT_)                                                                                         \
+    do {                                                                                                                     \
+        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_sync_kernel<NV_, U_, PPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm)); \
+        sa_conv1_sync_kernel<NV_, U_, PPT_><<<yctas, kF1SThreads, ysm, st>>>(s);                                             \
+    } while (0)
+#define PSA_F1Y_U(NV_, PPT_) do { if (s.uf) PSA_F1Y_LAUNCH(NV_, true, PPT_); else PSA_F1Y_LAUNCH(NV_, false, PPT_); } while (0)
+#define PSA_F1Y_P(NV_) do { if (ppt == 4) PSA_F1Y_U(NV_, 4); else if (ppt == 8) PSA_F1Y_U(NV_, 8); else PSA_F1Y_U(NV_, 16); } while (0)
+                if (C1 == 64) PSA_F1Y_P(2); else PSA_F1Y_P(4);
+#undef PSA_F1Y_P
+#undef PSA_F1Y_U
+#undef PSA_F1Y_LAUNCH
+                return check_launch("sa_conv1_sync_kernel");
             }
 #define PSA_F1S_LAUNCH(NV_, U_, NP_, PP_)                                                                                     \
     do {                                                                                                                     \

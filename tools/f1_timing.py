@@ -68,14 +68,14 @@ if os.environ.get("PSA_F1_TLOG"):
     torch.cuda.synchronize()
     launch()
     torch.cuda.synchronize()
-    off = (256 + 2 * 148 * 2 * C1 * 4) // 4
-    raw = ws[off:off + 296 * 8 * 2].view(torch.int64).view(-1, 8).cpu().numpy()
+    off = (256 + 3 * 148 * 2 * C1 * 4) // 4
+    raw = ws[off:off + 444 * 8 * 2].view(torch.int64).view(-1, 8).cpu().numpy()
     raw = raw[raw[:, 0] > 0]
     t0 = raw[:, 0].min()
     med = lambda c: float(sorted(raw[:, c] - t0)[len(raw) // 2]) / 1e3   # noqa: E731
     mx = lambda c: float((raw[:, c] - t0).max()) / 1e3                   # noqa: E731
     tl = {"ctas": int(len(raw)), "us_from_first_cta_start": {"cta_start_max": mx(0), "cloud_loaded_median": med(1), "cloud_loaded_max": mx(1),
-          "first_search_done_median": med(4), "first_idx_rows_done_median": med(7), "first_batch_full_median": med(2), "first_batch_full_max": mx(2), "producers_done_median": med(3), "producers_done_max": mx(3),
+          "first_search_done_median": med(4), "first_rows_ready_median": med(2), "first_rows_ready_max": mx(2),
           "consumers_done_median": med(5), "consumers_done_max": mx(5), "cta_end_max": mx(6)}}
 nbytes = B * (12 * N + 12 * M) + 4 * B * M * K * C1 + 4 * B * M * K + 4 * B * M + (4 * B * N * C1 if c else 0)
 print(json.dumps({"variant": os.environ.get("PSA_F1_VARIANT", "0"), "shape": [B, N, M, K, C1, c], "alg_bytes": nbytes,
