@@ -23,7 +23,8 @@
 namespace psa {
 using namespace tc;
 
-constexpr int kKtThreads = 288;                   // 8 row warps (two threads per query row) + 1 issuer warp
+constexpr int kKtRowT = 4;                        // threads per query row (each owns 128 / kKtRowT columns of every tile)
+constexpr int kKtThreads = 128 * kKtRowT + 32;    // row warps + 1 issuer warp
 constexpr uint32_t kKtPiece = 128u * 128u;        // one bf16 piece of a [128 rows][64 k] block: 16 KB
 constexpr uint32_t kKtBlock = 3u * kKtPiece;      // 48 KB
 constexpr int kKtBins = 256;
@@ -123,10 +124,10 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     const uint8_t* img = a.image + (size_t)cloud * NT * kKtBlock;
     const float* sqc = a.sq + (size_t)cloud * npad;
 
-    if (warp_u == 8) tmem_alloc(&s_tmem, 256);
+    if (warp_u == 4 * kKtRowT) tmem_alloc(&s_tmem, 256);
     if (tid == 0) {
         mbar_init(&s_qfull, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_dfull[i], 1); mbar_init(&s_dfree[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_dfull[i], 1); mbar_init(&s_dfree[i], 4 * kKtRowT); }
         fence_mbar_init();
     }
     // candidate norms -> shared memory; the cloud's largest finite-or-not norm over the real points
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     const int NT1 = (NT + kStride1 - 1) / kStride1;
     const int J = NT1 + NT;                          // jobs: pass 1 tiles (0, 2, 4, ..), then every pass 2 tile
 
-    if (warp_u == 8) {
+    if (warp_u == 4 * kKtRowT) {
         // ================= issuer / loader warp =================
         auto load = [&](int j) {
             const int s = j & 1, t = j < NT1 ? kStride1 * j : j - NT1;
@@ -197,9 +198,9 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             }
         }
     } else {
-        // ================= row threads: TWO threads per query row =================
-        // thread (r, h): row r = tid & 127, half h = tid >> 7 owns columns [64 h, 64 h + 64) of every candidate tile (warps w and
-        // w + 4 read the same TMEM lanes).  Histogram counters and the candidate list of a row are shared by its two threads
+        // ================= row threads: kKtRowT threads per query row =================
+        // thread (r, h): row r = tid & 127, part h = tid >> 7 owns columns [CW h, CW h + CW) of every candidate tile, CW = 128 / kKtRowT
+        // (warps w, w + 4, w + 8, .. read the same TMEM lanes).  Histogram counters and the candidate list of a row are shared by its two threads
         // through shared-memory atomics; twice the warps hide twice the latency of the serial per-row work.
         const int r = tid & 127, h = tid >> 7;
         const int q = blockIdx.x * 128 + r;
@@ -212,45 +213,39 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         const float sgeo = sqrtf(sqq * sqmax);
         const float dmax = 2.0f * (sqq + sqmax);
         const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)h * 64u;
-        for (int b = tid; b < kKtBins * 64; b += 256) hist[b] = 0u;
+        constexpr int CW = 128 / kKtRowT, NCH = CW / 32;
+        constexpr int kRowThreads = 128 * kKtRowT;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(h * CW);
+        for (int b = tid; b < kKtBins * 64; b += kRowThreads) hist[b] = 0u;
         if (h == 0) s_cnt[r] = 0;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
         const unsigned hinc = r < 64 ? 1u : 65536u;
         unsigned* hcol = hist + (r & 63);
         // ---- pass 1: coarse distances -> histogram ----
-        // Running cut: once the bins at or above `bmin` already hold k candidates, the k-th smallest can only move towards
-        // smaller distances, so farther candidates (bin < bmin) no longer matter and their shared-memory atomics are skipped --
-        // after the first tiles ~99 % of them.  (Counts of the bins >= bmin stay exact; the final scan never goes below bmin.)
-        int bmin = 0;
-        const bool is_r_lo = r < 64;
+        // (A running cut -- skipping the atomics of candidates farther than the bins that already hold k -- was measured slower:
+        //  987 vs 716 us at C = 64; the predicated atomics and the periodic histogram scans cost more than the atomics they save.)
         for (int t1 = 0; t1 < NT1; ++t1) {
             const int s = t1 & 1, t = kStride1 * t1;
             mbar_wait(&s_dfull[s], (uint32_t)((t1 >> 1) & 1));
             fence_after_thread_sync();
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NCH; ++ch) {
                 uint32_t d[32];
                 tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
                 tmem_ld_wait();
-                const float* sc = s_sq + t * 128 + h * 64 + ch * 32;
+                const float* sc = s_sq + t * 128 + h * CW + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
                     const int key = (int)(__float_as_uint(fmaxf(dist, 1e-30f)) >> 19);      // NaN -> 1e-30: lands in the last bin
                     const int bin = min(max(keymax - key, 0), kKtBins - 1);
-                    if (bin >= bmin) atomicAdd(hcol + bin * 64, hinc);   // fire-and-forget: no dependent chain through shared memory
+                    atomicAdd(hcol + bin * 64, hinc);            // fire-and-forget: no dependent chain through shared memory
                 }
             }
             fence_before_thread_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive1(&s_dfree[s]);
-            if ((t1 & (t1 + 1)) == 0 && t1 + 1 < NT1) {          // after tiles 0, 1, 3, 7, ..: tighten the cut
-                int cum = 0, b = kKtBins - 1;
-                for (; b > bmin; --b) { const unsigned w = hcol[b * 64]; cum += (int)(is_r_lo ? (w & 0xffffu) : (w >> 16)); if (cum >= a.k) break; }
-                bmin = max(bmin, b);
-            }
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");           // both halves of every row are in the histogram
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");           // both halves of every row are in the histogram
         // ---- threshold: upper edge of the bin that holds the k-th smallest coarse distance, widened by the error bounds ----
         if (h == 0) {
             int cum = 0, b = kKtBins - 1;
@@ -261,24 +256,24 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             s_T[r] = tau + E1 + E2 + 1e-6f * tau;
         }
         // every row is done with its histogram before anybody's candidate list / distances overwrite the scratch area
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
         const float T = s_T[r];
         // ---- pass 2: fine distances -> the row's candidate list (slots handed out by a shared-memory counter) ----
         for (int t = 0; t < NT; ++t) {
             const int j = NT1 + t, s = j & 1;
             mbar_wait(&s_dfull[s], (uint32_t)((j >> 1) & 1));
             fence_after_thread_sync();
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NCH; ++ch) {
                 uint32_t d[32];
                 tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
                 tmem_ld_wait();
-                const float* sc = s_sq + t * 128 + h * 64 + ch * 32;
+                const float* sc = s_sq + t * 128 + h * CW + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
                     if (dist < T) {
                         const int slot = atomicAdd(&s_cnt[r], 1);
-                        if (slot < kKtCap) lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * 64 + ch * 32 + i);
+                        if (slot < kKtCap) lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * CW + ch * 32 + i);
                     }
                 }
             }
@@ -286,7 +281,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive1(&s_dfree[s]);
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
         const int cnt = s_cnt[r];
         const bool refine = ok && cnt <= kKtCap && cnt >= a.k;
         if (valid && !refine && h == 0) {
@@ -299,36 +294,37 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             const float* xq = xc + (size_t)q * a.c;
             if (a.c == 64 && (reinterpret_cast<uintptr_t>(xc) & 15) == 0) {
                 // the usual DGCNN width: query row resident in registers, candidate row fetched with 16 independent loads
-                float4 qv[16];
-#pragma unroll
-                for (int l = 0; l < 16; ++l) qv[l] = __ldg(reinterpret_cast<const float4*>(xq) + l);
-                for (int e = h; e < cnt; e += 2) {
+                for (int e = h; e < cnt; e += kKtRowT) {
                     const int col = lidx[e * 128 + r];
                     const float4* cp4 = reinterpret_cast<const float4*>(xc + (size_t)col * 64);
-                    float4 cv[16];
-#pragma unroll
-                    for (int l = 0; l < 16; ++l) cv[l] = __ldg(cp4 + l);
+                    const float4* qp4 = reinterpret_cast<const float4*>(xq);
                     float dot = 0.f;
 #pragma unroll
-                    for (int l = 0; l < 16; ++l) {
-                        dot = fmaf(qv[l].x, cv[l].x, dot); dot = fmaf(qv[l].y, cv[l].y, dot);
-                        dot = fmaf(qv[l].z, cv[l].z, dot); dot = fmaf(qv[l].w, cv[l].w, dot);
+                    for (int hf = 0; hf < 2; ++hf) {                 // 2 x 8 independent 16-byte loads per operand, one fma chain
+                        float4 qv[8], cv[8];
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) { qv[l] = __ldg(qp4 + hf * 8 + l); cv[l] = __ldg(cp4 + hf * 8 + l); }
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            dot = fmaf(qv[l].x, cv[l].x, dot); dot = fmaf(qv[l].y, cv[l].y, dot);
+                            dot = fmaf(qv[l].z, cv[l].z, dot); dot = fmaf(qv[l].w, cv[l].w, dot);
+                        }
                     }
                     ladj[e * 128 + r] = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
                 }
             } else {
-                for (int e = h; e < cnt; e += 2) {
+                for (int e = h; e < cnt; e += kKtRowT) {
                     const int col = lidx[e * 128 + r];
                     ladj[e * 128 + r] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
                 }
             }
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
         if (refine) {
             // ---- rank of every entry in the lexicographic (distance, index) order = its output position; entries are distinct, so
             // ranks are too: ascending distance, lower index first on ties.  No loop-carried dependence, split between the two threads
             int* out = a.nn_idx + ((size_t)cloud * n + q) * a.k;
-            for (int e = h; e < cnt; e += 2) {
+            for (int e = h; e < cnt; e += kKtRowT) {
                 const float de = ladj[e * 128 + r];
                 const int ie = lidx[e * 128 + r];
                 int rank = 0;
@@ -343,7 +339,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     }
     fence_before_thread_sync();
     __syncthreads();
-    if (warp_u == 8) tmem_dealloc(tmem_base, 256);
+    if (warp_u == 4 * kKtRowT) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- exhaustive rows (worklist): one warp per row, canonical distances of all n candidates in shared memory, then k rounds of

@@ -210,7 +210,7 @@ __host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, int np, int
 }
 
 template <int NV, bool HAS_U, int NP, int PPTP>
-__global__ void __launch_bounds__(kF1SThreads, 2)
+__global__ void __launch_bounds__(kF1SThreads, 2)       // (3 CTAs per SM at 80 registers spills the point registers: 63 vs 57 us)
 sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
     constexpr int NC = kF1SThreads / 32 - NP;              // consumer warps
     constexpr int PT = NP * 32;                            // producer threads
@@ -456,15 +456,15 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             const int e4 = tid % E4, rl = tid / E4;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const float4* part4 = reinterpret_cast<const float4*>(a.partial);
-            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 20 * RL) {
-                float4 v[20];
+            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 8 * RL) {
+                float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 20; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const unsigned p = p0 + u * RL;
                     v[u] = p < gridDim.x ? __ldcg(part4 + (size_t)p * E4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int u = 0; u < 20; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+                for (int u = 0; u < 8; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
             }
             double* sred = reinterpret_cast<double*>(ring);                // RL x 2*C1 doubles <= 8 KB (the ring is >= 15 KB)
 #pragma unroll
@@ -780,7 +780,8 @@ static bool f1s_plan(int b, int n, int m, int nsample, int* np, int* pptp, int* 
     if (*smem > 110 * 1024) return false;
     const long long T = (long long)b * m;
     const long long batches = (T + kF1Batch - 1) / kF1Batch;
-    *ctas = (int)(batches < 2LL * kNumSMs ? batches : 2LL * kNumSMs);
+    const long long per_sm = 2;                                                   // matches the kernel's __launch_bounds__
+    *ctas = (int)(batches < per_sm * kNumSMs ? batches : per_sm * kNumSMs);
     return true;
 }
 static bool f1_want_grid(int n, int m) { return bq_grid_fits(n) && n >= 256 && m >= 32; }
