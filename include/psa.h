@@ -63,9 +63,17 @@ PSA_API int psa_farthest_point_sample(int b, int n, int m, const float* xyz, int
 PSA_API int psa_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, psa_stream_t stream);
 
 /* Replaces cudaMemset + scatteraddpointLauncher (sampling/tf_sampling.cpp:150,174; tf_sampling_g.cu:183-192).
- * out_g (b,m,3), idx (b,m) -> inp_g (b,n,3); inp_g is zeroed by this call, then scatter-added. */
-PSA_API int psa_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g,
-                          psa_stream_t stream);
+ * out_g (b,m,3), idx (b,m) -> inp_g (b,n,3), every element written.  Ordered (no float atomics): see
+ * psa_scatter_workspace_bytes(b, n, m). */
+PSA_API int psa_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g, void* workspace,
+                          size_t workspace_bytes, psa_stream_t stream);
+
+/* The three scatter-add gradients (GatherPointGrad, GroupPointGrad, ThreeInterpolateGrad) add the contributions of one
+ * destination in ascending entry order -- the order of the reference's sequential CPU loops (test/*_cpu, tf_interpolate.cpp)
+ * -- instead of the float atomicAdd of its CUDA kernels: results are bit-reproducible.  They need a device scratch buffer of
+ * this many bytes for the per-cloud (destination -> entries) lists: b clouds, n_dst destination points and `entries`
+ * scattered rows per cloud (m; m*nsample; 3*n).  Out-of-range indices are dropped.  n_dst <= 51200. */
+PSA_API size_t psa_scatter_workspace_bytes(int b, int n_dst, long long entries);
 
 /* ---------------------------------------------------------------------------------------------
  * grouping/  (tf_grouping.cpp, tf_grouping_g.cu)
@@ -85,9 +93,10 @@ PSA_API int psa_group_point(int b, int n, int c, int m, int nsample, const float
                     psa_stream_t stream);
 
 /* Replaces cudaMemset + groupPointGradLauncher (grouping/tf_grouping.cpp:173,204; tf_grouping_g.cu:61-78).
- * grad_out (b,m,nsample,c), idx -> grad_points (b,n,c), zeroed by this call first. */
+ * grad_out (b,m,nsample,c), idx -> grad_points (b,n,c), every element written.
+ * workspace: psa_scatter_workspace_bytes(b, n, m*nsample). */
 PSA_API int psa_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
-                         float* grad_points, psa_stream_t stream);
+                         float* grad_points, void* workspace, size_t workspace_bytes, psa_stream_t stream);
 
 /* Replaces selectionSortLauncher (grouping/tf_grouping.cpp:108, tf_grouping_g.cu:83-123; op SelectionSort).
  * dist (b,m,n) -> outi (b,m,n) int32, out (b,m,n): full copies whose first k slots per row hold the k
@@ -116,9 +125,11 @@ PSA_API int psa_three_interpolate(int b, int m, int c, int n, const float* point
                           float* out, psa_stream_t stream);
 
 /* Replaces memset + threeinterpolate_grad_cpu (tf_interpolate.cpp:131-153,258).
- * grad_out (b,n,c), idx, weight -> grad_points (b,m,c), zeroed by this call first. */
+ * grad_out (b,n,c), idx, weight -> grad_points (b,m,c), every element written; bit-identical to the reference's CPU loop
+ * (same order, product rounded before the add).  workspace: psa_scatter_workspace_bytes(b, m, 3*n). */
 PSA_API int psa_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx,
-                               const float* weight, float* grad_points, psa_stream_t stream);
+                               const float* weight, float* grad_points, void* workspace, size_t workspace_bytes,
+                               psa_stream_t stream);
 
 /* The interpolation half of pointnet_fp_module (pointnet2/utils/pointnet_util.py:211-216) in one launch:
  * three_nn -> dist=max(dist,1e-10) -> w=(1/dist)/sum(1/dist) -> three_interpolate.

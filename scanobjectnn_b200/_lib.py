@@ -54,15 +54,15 @@ _ain, _gin = C.POINTER(PsaActIn), C.POINTER(PsaGradIn)
 SIGNATURES = {
     "psa_farthest_point_sample": [_i, _i, _i, _p, _p, _p, _p],
     "psa_gather_point": [_i, _i, _i, _p, _p, _p, _p],
-    "psa_gather_point_grad": [_i, _i, _i, _p, _p, _p, _p],
+    "psa_gather_point_grad": [_i, _i, _i, _p, _p, _p, _p, _sz, _p],
     "psa_query_ball_point": [_i, _i, _i, _f, _i, _p, _p, _p, _p, _p],
     "psa_group_point": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
-    "psa_group_point_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "psa_group_point_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p],
     "psa_selection_sort": [_i, _i, _i, _i, _p, _p, _p, _p],
     "psa_knn_point": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "psa_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
     "psa_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
-    "psa_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "psa_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p],
     "psa_three_nn_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "psa_augment_batch": [_i, _i, _i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, _p, _i, _i, _p, _p],
     "psa_pairwise_distance": [_i, _i, _i, _p, _p, _p],
@@ -94,7 +94,8 @@ SIGNATURES = {
 }
 INFO_SYMBOLS = ("psa_version", "psa_last_error", "psa_sm_arch", "psa_shared_mlp_workspace_bytes",
                 "psa_sa_module_workspace_bytes", "psa_sa_conv1_prebn_workspace_bytes", "psa_sa_group_all_workspace_bytes", "psa_edgeconv_workspace_bytes",
-                "psa_train_dense_workspace_bytes", "psa_bn_bwd_workspace_bytes", "psa_sa_conv1_bwd_workspace_bytes", "psa_knn_graph_workspace_bytes")
+                "psa_train_dense_workspace_bytes", "psa_bn_bwd_workspace_bytes", "psa_sa_conv1_bwd_workspace_bytes", "psa_knn_graph_workspace_bytes",
+                "psa_scatter_workspace_bytes")
 
 _lib = None
 
@@ -131,6 +132,8 @@ def load() -> C.CDLL:
     lib.psa_sa_conv1_bwd_workspace_bytes.restype = C.c_size_t
     lib.psa_knn_graph_workspace_bytes.argtypes = [_i, _i, _i, _i]
     lib.psa_knn_graph_workspace_bytes.restype = C.c_size_t
+    lib.psa_scatter_workspace_bytes.argtypes = [_i, _i, _ll]
+    lib.psa_scatter_workspace_bytes.restype = C.c_size_t
     lib.psa_version.restype = C.c_int
     lib.psa_sm_arch.restype = C.c_int
     lib.psa_last_error.restype = C.c_char_p

@@ -16,6 +16,9 @@ constexpr int kNumSMs = 148;  // B200
 
 void set_error(const char* fmt, ...);
 
+// scatter.cu: stable counting sort of a cloud's (entry -> destination) pairs; offsets (b, n+1), list (b, mk)
+int launch_group_csr(int b, int n, int mk, const int* idx, int* offsets, int* list, cudaStream_t st);
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -99,19 +99,6 @@ __global__ void group_point_kernel(int n, int cv, long long rows_per_b, long lon
     }
 }
 
-__global__ void group_point_grad_kernel(int n, int c, long long rows_per_b, long long total,
-                                        const float* __restrict__ grad_out, const int* __restrict__ idx,
-                                        float* __restrict__ grad_points) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        long long row = e / c;
-        int l = (int)(e - row * c);
-        long long bi = row / rows_per_b;
-        int ii = __ldg(idx + row);
-        atomicAdd(&grad_points[(bi * n + ii) * c + l], grad_out[e]);
-    }
-}
-
 // ---- SelectionSort (tf_grouping_g.cu:83-123): one warp per (b,j) row, row resident in shared memory ----
 // Round s: position of the FIRST strict minimum in [s,n) (the reference starts min=s and scans t>s with '<',
 // so the earliest position among equal minima wins), swap with slot s carrying indices.
@@ -353,21 +340,6 @@ extern "C" int psa_group_point(int b, int n, int c, int m, int nsample, const fl
         group_point_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(n, c, rows_per_b, total, points, idx, out);
     }
     return check_launch("group_point_kernel");
-}
-
-extern "C" int psa_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
-                                    float* grad_points, psa_stream_t stream) {
-    PSA_REQUIRE(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0, "GroupPointGrad: negative dimension");
-    if ((long long)b * n * c == 0) return PSA_OK;
-    PSA_REQUIRE(grad_points != nullptr, "GroupPointGrad: null buffer");
-    cudaStream_t st = as_stream(stream);
-    PSA_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, st));
-    long long rows_per_b = (long long)m * nsample;
-    long long total = (long long)b * rows_per_b * c;
-    if (total == 0) return PSA_OK;
-    PSA_REQUIRE(grad_out && idx, "GroupPointGrad: null buffer");
-    group_point_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(n, c, rows_per_b, total, grad_out, idx, grad_points);
-    return check_launch("group_point_grad_kernel");
 }
 
 extern "C" int psa_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out,

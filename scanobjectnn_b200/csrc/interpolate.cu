@@ -101,23 +101,6 @@ __global__ void three_interpolate_kernel(int m, int c, int n, long long total, c
     }
 }
 
-__global__ void three_interpolate_grad_kernel(int m, int c, int n, long long total,
-                                              const float* __restrict__ grad_out, const int* __restrict__ idx,
-                                              const float* __restrict__ weight, float* __restrict__ grad_points) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        long long row = e / c;
-        int l = (int)(e - row * c);
-        long long bi = row / n;
-        const int* id = idx + row * 3;
-        const float* w = weight + row * 3;
-        float g = grad_out[e];
-        float* gb = grad_points + bi * m * (long long)c + l;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) atomicAdd(gb + (long long)__ldg(id + t) * c, __fmul_rn(g, __ldg(w + t)));
-    }
-}
-
 // pointnet_fp_module's interpolation half in one launch (pointnet_util.py:211-216).
 // CTA = kNnThreads unknown points of one cloud: phase 1 thread-per-point 3-NN + weights into shared memory,
 // phase 2 the CTA sweeps (point, channel) with channels fastest so the gathers/writes are coalesced.
@@ -196,20 +179,6 @@ extern "C" int psa_three_interpolate(int b, int m, int c, int n, const float* po
     PSA_REQUIRE(points && idx && weight && out, "ThreeInterpolate: null buffer");
     three_interpolate_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(m, c, n, total, points, idx, weight, out);
     return check_launch("three_interpolate_kernel");
-}
-
-extern "C" int psa_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx,
-                                          const float* weight, float* grad_points, psa_stream_t stream) {
-    PSA_REQUIRE(b >= 0 && n >= 0 && m >= 0 && c >= 0, "ThreeInterpolateGrad: negative dimension");
-    if ((long long)b * m * c == 0) return PSA_OK;
-    PSA_REQUIRE(grad_points != nullptr, "ThreeInterpolateGrad: null buffer");
-    cudaStream_t st = as_stream(stream);
-    PSA_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, st));
-    long long total = (long long)b * n * c;
-    if (total == 0) return PSA_OK;
-    PSA_REQUIRE(grad_out && idx && weight, "ThreeInterpolateGrad: null buffer");
-    three_interpolate_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(m, c, n, total, grad_out, idx, weight, grad_points);
-    return check_launch("three_interpolate_grad_kernel");
 }
 
 extern "C" int psa_three_nn_interpolate(int b, int n, int m, int c, const float* xyz1, const float* xyz2,

@@ -111,18 +111,6 @@ __global__ void gather_point_kernel(int n, int m, long long total, const float* 
     }
 }
 
-__global__ void gather_point_grad_kernel(int n, int m, long long total, const float* __restrict__ out_g,
-                                         const int* __restrict__ idx, float* __restrict__ inp_g) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        long long row = e / 3;
-        int c = (int)(e - row * 3);
-        long long bi = row / m;
-        int a = idx[row];
-        atomicAdd(&inp_g[(bi * n + a) * 3 + c], out_g[e]);
-    }
-}
-
 template <int T, int R>
 static int launch_fps(int b, int n, int m, const float* xyz, int* idx, float* new_xyz, cudaStream_t st) {
     size_t smem = (size_t)n * 3 * sizeof(float) + (size_t)m * sizeof(int);
@@ -168,15 +156,3 @@ extern "C" int psa_gather_point(int b, int n, int m, const float* inp, const int
     return check_launch("gather_point_kernel");
 }
 
-extern "C" int psa_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g,
-                                     psa_stream_t stream) {
-    PSA_REQUIRE(b >= 0 && n >= 0 && m >= 0, "GatherPointGrad: negative dimension");
-    if ((long long)b * n == 0) return PSA_OK;
-    PSA_REQUIRE(inp_g != nullptr, "GatherPointGrad: null buffer");
-    PSA_CUDA(cudaMemsetAsync(inp_g, 0, sizeof(float) * (size_t)b * n * 3, as_stream(stream)));
-    long long total = (long long)b * m * 3;
-    if (total == 0) return PSA_OK;
-    PSA_REQUIRE(out_g && idx, "GatherPointGrad: null buffer");
-    gather_point_grad_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(n, m, total, out_g, idx, inp_g);
-    return check_launch("gather_point_grad_kernel");
-}

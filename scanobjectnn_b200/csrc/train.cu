@@ -298,59 +298,8 @@ conv1_dwxyz_partial_kernel(const GradIn g, long long rows, int nsample, long lon
     }
 }
 
-// GroupPointGrad (tf_grouping_g.cu:61-78) without atomics, in two kernels:
-//  1. group_csr_kernel (one CTA per cloud): a STABLE counting sort of the cloud's m*nsample (row -> source point) entries:
-//     counts (shared-memory integer atomics: order-free), exclusive scan, then one warp walks the entries in row order, 32 at
-//     a time -- __match_any_sync groups the lanes that reference the same point, the rank inside the group is a popcount of
-//     the lower lanes, the group leader advances that point's cursor -- so list[] holds, per source point, its rows in
-//     ascending order;
-//  2. group_grad_csr_kernel (one warp per source point, lane = 4 channels): adds the rows of the point in list order.
-// Fixed order => bit-reproducible, unlike the reference's float atomicAdd.
-__global__ void __launch_bounds__(256) group_csr_kernel(int n, int mk, const int* __restrict__ idx, int* __restrict__ offsets, int* __restrict__ list) {
-    extern __shared__ int sm_i[];                 // n counters / cursors
-    const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int* ic = idx + (size_t)cloud * mk;
-    int* off = offsets + (size_t)cloud * (n + 1);
-    int* lst = list + (size_t)cloud * mk;
-    for (int j = tid; j < n; j += 256) sm_i[j] = 0;
-    __syncthreads();
-    for (int e = tid; e < mk; e += 256) atomicAdd(&sm_i[__ldg(ic + e)], 1);
-    __syncthreads();
-    // exclusive scan by one warp (n <= a few thousand): lane owns a contiguous run of counters
-    if (tid < 32) {
-        const int per = (n + 31) / 32;
-        const int j0 = lane * per, j1 = min(n, j0 + per);
-        int local = 0;
-        for (int j = j0; j < j1; ++j) local += sm_i[j];
-        int incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        int run = incl - local;
-        for (int j = j0; j < j1; ++j) { const int c = sm_i[j]; sm_i[j] = run; off[j] = run; run += c; }
-        if (lane == 31) off[n] = incl;
-        __syncwarp();
-        // stable placement: entries in row order, 32 per step
-        for (int base = 0; base < mk; base += 32) {
-            const int e = base + lane;
-            const bool act = e < mk;
-            const int v = act ? __ldg(ic + e) : -1 - lane;             // inactive lanes: distinct dummies
-            const unsigned grp = __match_any_sync(0xffffffffu, v);
-            const int rank = __popc(grp & lanemask_lt());
-            int cur = 0;
-            if (act) cur = sm_i[v];
-            __syncwarp();
-            if (act) {
-                lst[cur + rank] = e;
-                if (rank == 0) sm_i[v] = cur + __popc(grp);             // the group's lowest lane advances the cursor
-            }
-            __syncwarp();
-        }
-    }
-}
-
+// GroupPointGrad of the training path: CSR built by scatter.cu's stable counting sort (launch_group_csr), then one warp per
+// source point (lane = 4 channels) adds the rows of the point in list order.  Fixed order => bit-reproducible.
 __global__ void __launch_bounds__(256)
 group_grad_csr_kernel(const GradIn g, int n, int mk, int C1, long long total_points, const int* __restrict__ offsets, const int* __restrict__ list,
                       float* __restrict__ dU) {
@@ -675,13 +624,9 @@ extern "C" int psa_sa_conv1_bwd(int b, int n, int m, int nsample, int C1, const 
     if (dU != nullptr) {
         // CSR scratch behind the dW partials: offsets (b, n+1) + list (b, m*nsample)
         uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace) + conv1_bwd_partial_bytes(C1);
-        PSA_SUPPORTED((size_t)n * sizeof(int) <= 160 * 1024, "sa_conv1_bwd: n=%d too large for the per-cloud counters", n);
         int* offsets = reinterpret_cast<int*>(wsb);
         int* list = offsets + (size_t)b * (n + 1);
-        const size_t smem = (size_t)n * sizeof(int);
-        PSA_CUDA(cudaFuncSetAttribute(group_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        group_csr_kernel<<<b, 256, smem, st>>>(n, m * nsample, idx, offsets, list);
-        rc = check_launch("group_csr_kernel");
+        rc = launch_group_csr(b, n, m * nsample, idx, offsets, list, st);
         if (rc != PSA_OK) return rc;
         const long long pts = (long long)b * n;
         group_grad_csr_kernel<<<(unsigned)((pts + 7) / 8), 256, 0, st>>>(gi, n, m * nsample, C1, pts, offsets, list, dU);

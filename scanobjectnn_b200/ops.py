@@ -43,6 +43,12 @@ def _ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _scatter_ws(b: int, n_dst: int, entries: int, device) -> tuple[torch.Tensor, C.c_size_t]:
+    """Scratch for the ordered scatter-add gradients (psa_scatter_workspace_bytes)."""
+    need = int(_lib.load().psa_scatter_workspace_bytes(b, n_dst, entries))
+    return torch.empty((need,), dtype=torch.uint8, device=device), C.c_size_t(need)
+
+
 # ------------------------------------------------------------------------------------------------
 # sampling
 # ------------------------------------------------------------------------------------------------
@@ -88,7 +94,8 @@ class _GatherPoint(torch.autograd.Function):
         out_g = out_g.contiguous()
         b, m, _ = out_g.shape
         inp_g = torch.empty((b, ctx.n, 3), dtype=torch.float32, device=out_g.device)
-        check(_lib.load().psa_gather_point_grad(b, ctx.n, m, _ptr(out_g), _ptr(idx), _ptr(inp_g), _stream()),
+        ws, nbytes = _scatter_ws(b, ctx.n, m, out_g.device)
+        check(_lib.load().psa_gather_point_grad(b, ctx.n, m, _ptr(out_g), _ptr(idx), _ptr(inp_g), _ptr(ws), nbytes, _stream()),
               "gather_point_grad")
         return inp_g, None
 
@@ -148,7 +155,8 @@ class _GroupPoint(torch.autograd.Function):
         _, m, k = idx.shape
         grad_out = grad_out.contiguous()
         g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
-        check(_lib.load().psa_group_point_grad(b, n, c, m, k, _ptr(grad_out), _ptr(idx), _ptr(g), _stream()),
+        ws, nbytes = _scatter_ws(b, n, m * k, grad_out.device)
+        check(_lib.load().psa_group_point_grad(b, n, c, m, k, _ptr(grad_out), _ptr(idx), _ptr(g), _ptr(ws), nbytes, _stream()),
               "group_point_grad")
         return g, None
 
@@ -288,7 +296,8 @@ class _ThreeInterpolate(torch.autograd.Function):
         n = idx.shape[1]
         grad_out = grad_out.contiguous()
         g = torch.empty((b, m, c), dtype=torch.float32, device=grad_out.device)
-        check(_lib.load().psa_three_interpolate_grad(b, n, c, m, _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(g),
+        ws, nbytes = _scatter_ws(b, m, 3 * n, grad_out.device)
+        check(_lib.load().psa_three_interpolate_grad(b, n, c, m, _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(g), _ptr(ws), nbytes,
                                                      _stream()), "three_interpolate_grad")
         return g, None, None
 

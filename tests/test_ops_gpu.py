@@ -80,7 +80,8 @@ def test_gather_point_and_grad():
     assert np.array_equal(G.npy(out), orc.gather_point(inp, idx))
     go = rng.standard_normal((3, 20, 3)).astype(np.float32)
     out.backward(G.cu(go))
-    np.testing.assert_allclose(G.npy(t.grad), orc.gather_point_grad(inp.shape, idx, go), rtol=1e-6, atol=1e-6)
+    # ordered scatter-add: the sum order of the reference's sequential CPU loop -> bit-identical, not just close
+    assert np.array_equal(G.npy(t.grad), orc.gather_point_grad(inp.shape, idx, go))
 
 
 # ----------------------------------------------------------------------------------------------- ball query
@@ -157,7 +158,7 @@ def test_group_point_and_grad(c):
         assert torch.equal(out.detach(), G.ref_group_point(t.detach(), G.cu(idx)))
     go = rng.standard_normal(out.shape).astype(np.float32)
     out.backward(G.cu(go))
-    np.testing.assert_allclose(G.npy(t.grad), orc.group_point_grad(pts.shape, idx, go), rtol=1e-5, atol=1e-5)
+    assert np.array_equal(G.npy(t.grad), orc.group_point_grad(pts.shape, idx, go))
 
 
 # ----------------------------------------------------------------------------------------------- selection sort / knn_point
@@ -209,7 +210,56 @@ def test_three_interpolate_and_grad(c):
     assert np.array_equal(G.npy(out), orc.three_interpolate(pts, idx, w))
     go = rng.standard_normal(out.shape).astype(np.float32)
     out.backward(G.cu(go))
-    np.testing.assert_allclose(G.npy(t.grad), orc.three_interpolate_grad(pts.shape, idx, w, go), rtol=1e-5, atol=1e-5)
+    assert np.array_equal(G.npy(t.grad), orc.three_interpolate_grad(pts.shape, idx, w, go))
+
+
+def test_scatter_gradients_are_ordered_at_model_shapes():
+    """SA-1 shapes (B=8, N=2048 -> 512 x 32 rows, hot destinations hit hundreds of times): the three gradients equal the
+    reference's sequential CPU sums bit for bit, twice in a row, and unreferenced destinations are exact zeros."""
+    rng = np.random.default_rng(77)
+    b, n, m, k, c = 8, 2048, 512, 32, 64
+    idx = (rng.integers(0, n // 4, size=(b, m, k)) * rng.integers(1, 5, size=(b, m, 1))).astype(np.int32) % n
+    idx[:, :, :4] = 5                                                     # one very hot destination
+    go = rng.standard_normal((b, m, k, c)).astype(np.float32)
+    pts = torch.zeros((b, n, c), device="cuda", requires_grad=True)
+    want = orc.group_point_grad((b, n, c), idx, go)
+    for _ in range(2):
+        pts.grad = None
+        ops.group_point(pts, G.cu(idx)).backward(G.cu(go))
+        assert np.array_equal(G.npy(pts.grad), want)
+    untouched = np.ones((b, n), bool)
+    for i in range(b):
+        untouched[i, np.unique(idx[i])] = False
+    assert untouched.any() and not G.npy(pts.grad)[untouched].any()
+    # FP-module shapes: 2048 unknown points interpolate from 128 known ones
+    idx3 = rng.integers(0, 128, size=(b, n, 3), dtype=np.int32)
+    w3 = rng.random((b, n, 3), dtype=np.float32)
+    g3 = rng.standard_normal((b, n, 256)).astype(np.float32)
+    known = torch.zeros((b, 128, 256), device="cuda", requires_grad=True)
+    ops.three_interpolate(known, G.cu(idx3), G.cu(w3)).backward(G.cu(g3))
+    assert np.array_equal(G.npy(known.grad), orc.three_interpolate_grad((b, 128, 256), idx3, w3, g3))
+    # FPS gather: every centre index once, most inputs untouched
+    fidx = np.stack([rng.permutation(n)[:m] for _ in range(b)]).astype(np.int32)
+    gg = rng.standard_normal((b, m, 3)).astype(np.float32)
+    xyz = torch.zeros((b, n, 3), device="cuda", requires_grad=True)
+    ops.gather_point(xyz, G.cu(fidx)).backward(G.cu(gg))
+    assert np.array_equal(G.npy(xyz.grad), orc.gather_point_grad((b, n, 3), fidx, gg))
+
+
+def test_scatter_gradient_workspace_is_checked():
+    import ctypes as C
+
+    from scanobjectnn_b200 import _lib
+    lib = _lib.load()
+    need = lib.psa_scatter_workspace_bytes(2, 16, 8)
+    assert need >= (2 * 17 + 2 * 8) * 4
+    g = torch.zeros((2, 16, 3), device="cuda")
+    og = torch.zeros((2, 8, 3), device="cuda")
+    ix = torch.zeros((2, 8), dtype=torch.int32, device="cuda")
+    small = torch.empty((16,), dtype=torch.uint8, device="cuda")
+    rc = lib.psa_gather_point_grad(2, 16, 8, C.c_void_p(og.data_ptr()), C.c_void_p(ix.data_ptr()), C.c_void_p(g.data_ptr()),
+                                   C.c_void_p(small.data_ptr()), C.c_size_t(16), None)
+    assert rc == -1 and b"workspace" in lib.psa_last_error()
 
 
 @pytest.mark.parametrize("n,m,c", [(128, 1, 16), (512, 128, 256), (2048, 512, 128), (333, 50, 7)])
