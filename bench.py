@@ -26,6 +26,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv and os.environ.get("RANK", "0") == "0" and "TORCHELASTIC_RUN_ID" in os.environ:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and is meant to use every host core
+    # (set before numpy / the OpenMP runtime load)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 B, N, NUM_CLASS = 32, 2048, 15
 WORKLOAD = "pointnet2_cls_ssg inference forward, B=32 N=2048 K=32/64, 15 classes (BASELINE.json configs[1])"
 METRIC = "point-clouds/sec (B=32, N=2048, 15-class)"

@@ -12,7 +12,9 @@
 //             (float exponent + 4 mantissa bits) in shared memory -> tau = upper edge of the bin that holds the k-th smallest;
 //     pass 2  six MMA terms (bf16x3, error <= E2): every candidate with d < tau + E1 + E2 -- a superset of the true top-k --
 //             is appended to the row's list (typically k + 10..30 entries);
-//     refine  canonical fp32 distances of the listed candidates only, then k rounds of lexicographic (d, index) minimum.
+//     order   rank of every listed candidate = its output position.  Fine distances decide wherever two entries are more than
+//             2 E2 apart; entries with a neighbour inside 2 E2 (near-ties, duplicates) get their canonical fp32 distance and are
+//             compared canonically (distance, then index) -- every comparison agrees with the canonical order.
 //   fallback  rows whose list overflows (many equidistant points) or whose cloud holds non-finite values are written to a
 //             worklist and done exhaustively in fp32 by knn_rows_exact_kernel (same canonical arithmetic).
 #include <float.h>
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     __shared__ uint32_t s_tmem;
     __shared__ float s_wmax[kKtThreads / 32];
     __shared__ float s_T[128];
-    __shared__ int s_cnt[128];
+    __shared__ int s_cnt[128], s_namb[128];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
     const int cloud = blockIdx.y;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         constexpr int kRowThreads = 128 * kKtRowT;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(h * CW);
         for (int b = tid; b < kKtBins * 64; b += kRowThreads) hist[b] = 0u;
-        if (h == 0) s_cnt[r] = 0;
+        if (h == 0) { s_cnt[r] = 0; s_namb[r] = 0; }
         asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
         const unsigned hinc = r < 64 ? 1u : 65536u;
         unsigned* hcol = hist + (r & 63);
@@ -273,7 +275,10 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
                     const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
                     if (dist < T) {
                         const int slot = atomicAdd(&s_cnt[r], 1);
-                        if (slot < kKtCap) lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * CW + ch * 32 + i);
+                        if (slot < kKtCap) {
+                            lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * CW + ch * 32 + i);
+                            ladj[slot * 128 + r] = dist;
+                        }
                     }
                 }
             }
@@ -288,19 +293,54 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             // exhaustive kernel takes this row (overflow: many equidistant candidates; non-finite coordinates; fewer than k below T)
             a.flag_rows[atomicAdd(a.flag_count, 1u)] = cloud * n + q;
         }
+        // ---- order of the listed candidates.  The fine distances are within E2 of the canonical fp32 values, so two entries more
+        // than delta = 2 E2 apart are ordered canonically the way their fine distances are; only entries with a neighbour inside
+        // delta ("ambiguous": near-ties, duplicates) get their canonical distance evaluated, and only those pairs are compared
+        // canonically (distance, then index).  Every pairwise comparison therefore agrees with the canonical order and
+        // rank = number of entries that precede = output position.  Typical feature clouds: 1-3 ambiguous entries per row instead of
+        // 30-40 canonical evaluations (each a 256-byte gather).  The operand buffers are dead after pass 2 and hold the scratch:
+        float* lcan = reinterpret_cast<float*>(qblk);                       // [kKtCap][128] canonical distance of ambiguous entries
+        unsigned short* lrank = reinterpret_cast<unsigned short*>(cstage);   // [kKtCap][128] number of entries surely before
+        unsigned char* lamb = cstage + (size_t)kKtCap * 128 * 2;             // [kKtCap][128] compact list of the row's ambiguous entries
         const float* xc = a.x + (size_t)cloud * n * a.c;
+        const float delta = 2.0f * (1e-4f * sgeo + 2e-6f * (sqq + sqmax));   // 2 E2, E2 as in the threshold above
+        int* out = a.nn_idx + ((size_t)cloud * n + q) * a.k;
+        // phase 1: fine-distance counts of every entry (entries split between the row's threads); unambiguous ones are final
         if (refine) {
-            // ---- refine: canonical fp32 distances of the listed candidates, entries split between the row's two threads ----
+            for (int e = h; e < cnt; e += kKtRowT) {
+                const float fe = ladj[e * 128 + r];
+                int lo = 0, amb = 0;
+#pragma unroll 4
+                for (int f = 0; f < cnt; ++f) {
+                    const float d = ladj[f * 128 + r] - fe;
+                    lo += d < -delta ? 1 : 0;
+                    amb += fabsf(d) <= delta ? 1 : 0;                        // counts e itself
+                }
+                if (amb == 1) {
+                    if (lo < a.k) out[lo] = lidx[e * 128 + r];
+                } else {
+                    lrank[e * 128 + r] = (unsigned short)lo;
+                    lamb[atomicAdd(&s_namb[r], 1) * 128 + r] = (unsigned char)e;
+                }
+            }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
+        // phase 2: canonical distances of the ambiguous entries, dealt round-robin to the row's threads
+        const int namb = refine ? s_namb[r] : 0;
+        if (namb > 0) {
             const float* xq = xc + (size_t)q * a.c;
-            if (a.c == 64 && (reinterpret_cast<uintptr_t>(xc) & 15) == 0) {
-                // the usual DGCNN width: query row resident in registers, candidate row fetched with 16 independent loads
-                for (int e = h; e < cnt; e += kKtRowT) {
-                    const int col = lidx[e * 128 + r];
+            const bool wide = a.c == 64 && (reinterpret_cast<uintptr_t>(xc) & 15) == 0;
+            for (int i = h; i < namb; i += kKtRowT) {
+                const int e = lamb[i * 128 + r];
+                const int col = lidx[e * 128 + r];
+                float can;
+                if (wide) {
+                    // the usual DGCNN width: 2 x 8 independent 16-byte loads per operand, one ascending fma chain
                     const float4* cp4 = reinterpret_cast<const float4*>(xc + (size_t)col * 64);
                     const float4* qp4 = reinterpret_cast<const float4*>(xq);
                     float dot = 0.f;
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {                 // 2 x 8 independent 16-byte loads per operand, one fma chain
+                    for (int hf = 0; hf < 2; ++hf) {
                         float4 qv[8], cv[8];
 #pragma unroll
                         for (int l = 0; l < 8; ++l) { qv[l] = __ldg(qp4 + hf * 8 + l); cv[l] = __ldg(cp4 + hf * 8 + l); }
@@ -310,31 +350,33 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
                             dot = fmaf(qv[l].z, cv[l].z, dot); dot = fmaf(qv[l].w, cv[l].w, dot);
                         }
                     }
-                    ladj[e * 128 + r] = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
+                    can = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
+                } else {
+                    can = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
                 }
-            } else {
-                for (int e = h; e < cnt; e += kKtRowT) {
-                    const int col = lidx[e * 128 + r];
-                    ladj[e * 128 + r] = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
-                }
+                lcan[e * 128 + r] = can;
+#ifdef PSA_KNN_ERRSTAT
+                // diagnostic build (tools/knn_tc_timing.py): largest observed |fine - canonical| / E2 over the ambiguous entries
+                atomicMax(a.flag_count + 1, __float_as_uint(fabsf(ladj[e * 128 + r] - can) / (0.5f * delta)));
+                atomicAdd(a.flag_count + 2, 1u);
+#endif
             }
         }
         asm volatile("bar.sync 2, %0;" ::"n"(128 * kKtRowT) : "memory");
-        if (refine) {
-            // ---- rank of every entry in the lexicographic (distance, index) order = its output position; entries are distinct, so
-            // ranks are too: ascending distance, lower index first on ties.  No loop-carried dependence, split between the two threads
-            int* out = a.nn_idx + ((size_t)cloud * n + q) * a.k;
-            for (int e = h; e < cnt; e += kKtRowT) {
-                const float de = ladj[e * 128 + r];
-                const int ie = lidx[e * 128 + r];
-                int rank = 0;
-                for (int f = 0; f < cnt; ++f) {
-                    const float df = ladj[f * 128 + r];
-                    const int jf = lidx[f * 128 + r];
-                    rank += (df < de || (df == de && jf < ie)) ? 1 : 0;
-                }
-                if (rank < a.k) out[rank] = ie;
+        // phase 3: an ambiguous entry is preceded by the entries surely before it plus the ambiguous neighbours that precede canonically
+        for (int i = h; i < namb; i += kKtRowT) {
+            const int e = lamb[i * 128 + r];
+            const float fe = ladj[e * 128 + r], ce = lcan[e * 128 + r];
+            const int ie = lidx[e * 128 + r];
+            int rank = lrank[e * 128 + r];
+            for (int j = 0; j < namb; ++j) {
+                const int f = lamb[j * 128 + r];
+                if (f == e || fabsf(ladj[f * 128 + r] - fe) > delta) continue;
+                const float cf = lcan[f * 128 + r];
+                const int jf = lidx[f * 128 + r];
+                rank += (cf < ce || (cf == ce && jf < ie)) ? 1 : 0;
             }
+            if (rank < a.k) out[rank] = ie;
         }
     }
     fence_before_thread_sync();
@@ -441,7 +483,7 @@ extern "C" int psa_knn_graph_ws(int b, int n, int c, int k, const float* x, int*
     int* flag_rows = reinterpret_cast<int*>(ws);
     ws += ((size_t)b * n * 4 + 255) & ~(size_t)255;
     unsigned* flag_count = reinterpret_cast<unsigned*>(ws);
-    PSA_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(unsigned), st));
+    PSA_CUDA(cudaMemsetAsync(flag_count, 0, 4 * sizeof(unsigned), st));       // [0] worklist length (+ [1..2] PSA_KNN_ERRSTAT diagnostics)
     knn_prep_kernel<<<dim3(NT, b), 128, 0, st>>>(n, npad, c, x, image, sq);
     int rc = check_launch("knn_prep_kernel");
     if (rc != PSA_OK) return rc;

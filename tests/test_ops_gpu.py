@@ -294,7 +294,9 @@ def test_dgcnn_graph_matches_oracle(n, c, k):
 
 
 @pytest.mark.parametrize("kind,n,c,k", [("gauss", 2048, 64, 20), ("ball", 2048, 3, 20), ("dup", 1024, 3, 20), ("gauss", 300, 16, 8),
-                                        ("gauss", 256, 64, 32), ("scaled", 1024, 64, 20), ("nan", 512, 8, 10)])
+                                        ("gauss", 256, 64, 32), ("scaled", 1024, 64, 20), ("nan", 512, 8, 10),
+                                        ("lattice", 1024, 3, 20), ("jitter", 1024, 64, 20), ("offset", 2048, 64, 20), ("relu", 2048, 64, 20),
+                                        ("jitter", 640, 12, 16)])
 def test_knn_graph_tensor_core_path_is_index_exact(kind, n, c, k):
     """csrc/knn_tc.cu: bf16 / bf16x3 tensor-core distances only PRUNE; the neighbours come from the canonical fp32 distances of the
     survivors, so the result equals the oracle (and the fp32 kernel) bit for bit -- incl. the BASELINE configs[2] size n = 2048,
@@ -304,6 +306,17 @@ def test_knn_graph_tensor_core_path_is_index_exact(kind, n, c, k):
         x = make_clouds(kind, 2, n, seed=n + 1)
     else:
         x = rng.standard_normal((2, n, c)).astype(np.float32)
+        if kind == "lattice":                 # integer grid: most distances tie exactly -> everything is decided canonically / by index
+            x = rng.integers(0, 7, size=(2, n, c)).astype(np.float32)
+        if kind == "jitter":                  # a few hundred distinct sites + noise from 1e-7 to 1e-2: near-ties on every scale around
+            sites = rng.standard_normal((2, 40, c)).astype(np.float32)          # the fine/canonical decision boundary
+            pick = rng.integers(0, 40, size=(2, n))
+            amp = (10.0 ** rng.uniform(-7, -2, size=(2, n, 1))).astype(np.float32)
+            x = np.take_along_axis(sites, pick[:, :, None].repeat(c, 2), 1) + amp * rng.standard_normal((2, n, c)).astype(np.float32)
+        if kind == "offset":                  # large common offset: |x|^2 terms dwarf the distances (cancellation in adj)
+            x = (x * 0.05 + 3.0).astype(np.float32)
+        if kind == "relu":
+            x = np.maximum(x, 0)
         if kind == "scaled":
             x[1] *= 37.5                      # per-cloud scale: the error bounds are relative to the cloud's norms
             x[0, : n // 2] *= 1e-3            # a dense cluster far below the cloud's largest distances

@@ -31,6 +31,10 @@ for name, x in (("c64_gauss", torch.randn((B, N, 64), device="cuda")), ("c3_ball
     npad = (N + 127) // 128 * 128
     off = (B * (npad // 128) * 49152 + ((B * npad * 4 + 255) & ~255) + ((B * N * 4 + 255) & ~255)) // 4
     flagged = int(ws[off:off + 1].view(torch.int32).item())
+    # PSA_KNN_ERRSTAT build only (python tools/build_variant.py errstat -DPSA_KNN_ERRSTAT; PSA_LIB_PATH=...): the largest observed
+    # |fine - canonical| in units of the bound E2 and the number of canonically evaluated (ambiguous) entries; zeros otherwise
+    err_over_e2 = float(ws[off + 1:off + 2].view(torch.float32).item())
+    ambiguous = int(ws[off + 2:off + 3].view(torch.int32).item())
     ts = []
     for _ in range(7):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,6 +51,6 @@ for name, x in (("c64_gauss", torch.randn((B, N, 64), device="cuda")), ("c3_ball
         t2.append(e0.elapsed_time(e1) * 1e3)
     t2.sort()
     ops._KNN_FP32_ONLY = False
-    out[name] = {"tc_us": ts[len(ts) // 2], "fp32_us": t2[len(t2) // 2], "rows_to_exhaustive_kernel": flagged, "rows": B * N,
+    out[name] = {"max_err_over_E2": err_over_e2, "ambiguous_entries_per_row": ambiguous / (B * N), "tc_us": ts[len(ts) // 2], "fp32_us": t2[len(t2) // 2], "rows_to_exhaustive_kernel": flagged, "rows": B * N,
                  "equal": bool(torch.equal(idx, ref))}
 print(json.dumps(out))
