@@ -10,7 +10,8 @@
 //             Thread q owns row q and reads ITS distances with tcgen05.ld -- selection needs no cross-lane traffic:
 //     pass 1  one bf16 MMA term (4 MMAs per tile): coarse distances (error <= E1) -> per-row histogram over logarithmic bins
 //             (float exponent + 4 mantissa bits) in shared memory -> tau = upper edge of the bin that holds the k-th smallest;
-//     pass 2  six MMA terms (bf16x3, error <= E2): every candidate with d < tau + E1 + E2 -- a superset of the true top-k --
+//     pass 2  three MMA terms (two bf16 pieces per operand, error <= E2): every candidate with d < tau + E1 + E2 -- a superset of the
+//             true top-k --
 //             is appended to the row's list (typically k + 10..30 entries);
 //     order   rank of every listed candidate = its output position.  Fine distances decide wherever two entries are more than
 //             2 E2 apart; entries with a neighbour inside 2 E2 (near-ties, duplicates) get their canonical fp32 distance and are
@@ -21,6 +22,13 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+
+// pass 2 precision: 3 = two bf16 pieces per operand (a1 b1 + a1 b2 + a2 b1), 6 = three pieces (bf16x3).  Both stay inside the
+// bound E2 used below (3 terms: <= 3 * 2^-18 per product + 192 truncating adds + the canonical chain's own 64 * 2^-24, together
+// 3.8e-5 of |q||c| against E2 = 1e-4 |q||c|); 3 terms: 352 us, 6 terms: 374 us at B=32 N=2048 C=64.
+#ifndef PSA_KNN_TERMS
+#define PSA_KNN_TERMS 3
+#endif
 
 namespace psa {
 using namespace tc;
@@ -153,11 +161,12 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     const int NT1 = (NT + kStride1 - 1) / kStride1;
     const int J = NT1 + NT;                          // jobs: pass 1 tiles (0, 2, 4, ..), then every pass 2 tile
 
+    constexpr uint32_t kTermPieces = PSA_KNN_TERMS == 6 ? 3u : 2u;
     if (warp_u == 4 * kKtRowT) {
         // ================= issuer / loader warp =================
         auto load = [&](int j) {
             const int s = j & 1, t = j < NT1 ? kStride1 * j : j - NT1;
-            const uint32_t bytes = j < NT1 ? kKtPiece : kKtBlock;                  // pass 1 needs the leading piece only
+            const uint32_t bytes = j < NT1 ? kKtPiece : (kTermPieces * kKtPiece);   // pass 1 needs the leading piece only
             if (lane == 0) {
                 mbar_expect_tx(&s_full[s], bytes);
                 for (uint32_t o = 0; o < bytes; o += 16384u) bulk_g2s(cstage + (uint32_t)s * kKtBlock + o, img + (size_t)t * kKtBlock + o, 16384u, &s_full[s]);
@@ -171,8 +180,15 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         if (J > 1) load(1);
         mbar_wait(&s_qfull, 0);
         const uint32_t idesc = make_idesc(kFmtBF16, 128, 128);
-        constexpr uint32_t qp[6] = {0, 1, 2, 0, 1, 0};       // query piece / candidate piece of the six terms, small products first
+        constexpr int kTerms = PSA_KNN_TERMS;                // 6: bf16x3 (all products down to 2^-24); 3: bf16x2 (2^-16), same error bound E2
+#if PSA_KNN_TERMS == 6
+        constexpr uint32_t qp[6] = {0, 1, 2, 0, 1, 0};       // query piece / candidate piece of the terms, small products first
         constexpr uint32_t cp[6] = {2, 1, 0, 1, 0, 0};
+#else
+        constexpr uint32_t qp[3] = {0, 1, 0};
+        constexpr uint32_t cp[3] = {1, 0, 0};
+#endif
+        const int ks = (a.c + 15) / 16;                      // k-steps of 16 channels that hold data (the image is zero beyond c)
         const SmemDescBase qa = smem_desc_base(warp_uniform(smem_u32(qblk)));
         for (int j = 0; j < J; ++j) {
             const int s = j & 1;
@@ -184,13 +200,11 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             const uint32_t d = tmem_base + (uint32_t)s * 128u;
             const SmemDescBase cb = smem_desc_base(warp_uniform(smem_u32(cstage) + (uint32_t)s * kKtBlock));
             if (j < NT1) {
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) mma_bf16_ss(d, smem_desc_at(qa, s4 * 32), smem_desc_at(cb, s4 * 32), idesc, s4 ? 1u : 0u);
+                for (int s4 = 0; s4 < ks; ++s4) mma_bf16_ss(d, smem_desc_at(qa, s4 * 32), smem_desc_at(cb, s4 * 32), idesc, s4 ? 1u : 0u);
             } else {
 #pragma unroll
-                for (int t6 = 0; t6 < 6; ++t6)
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4)
+                for (int t6 = 0; t6 < kTerms; ++t6)
+                    for (int s4 = 0; s4 < ks; ++s4)
                         mma_bf16_ss(d, smem_desc_at(qa, qp[t6] * kKtPiece + s4 * 32), smem_desc_at(cb, cp[t6] * kKtPiece + s4 * 32), idesc, (t6 | s4) ? 1u : 0u);
             }
             mma_commit(&s_dfull[s]);
@@ -215,7 +229,16 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         const float sgeo = sqrtf(sqq * sqmax);
         const float dmax = 2.0f * (sqq + sqmax);
         const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
-        constexpr int CW = 128 / kKtRowT, NCH = CW / 32;
+        constexpr int CW = 128 / kKtRowT;
+        static_assert(CW == 32, "one 32-column tcgen05.ld per thread and tile");
+        auto load_base = [&](float (&base)[32], int t) {
+            const float4* sc4 = reinterpret_cast<const float4*>(s_sq + t * 128 + h * CW);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                const float4 v = sc4[l];
+                base[4 * l] = sqq + v.x; base[4 * l + 1] = sqq + v.y; base[4 * l + 2] = sqq + v.z; base[4 * l + 3] = sqq + v.w;
+            }
+        };
         constexpr int kRowThreads = 128 * kKtRowT;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp_u & 3) * 32) << 16) + (uint32_t)(h * CW);
         for (int b = tid; b < kKtBins * 64; b += kRowThreads) hist[b] = 0u;
@@ -228,17 +251,18 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         //  987 vs 716 us at C = 64; the predicated atomics and the periodic histogram scans cost more than the atomics they save.)
         for (int t1 = 0; t1 < NT1; ++t1) {
             const int s = t1 & 1, t = kStride1 * t1;
+            float base[32];                                      // |q|^2 + |c|^2 of this thread's 32 columns, fetched while the MMAs run
+            load_base(base, t);
             mbar_wait(&s_dfull[s], (uint32_t)((t1 >> 1) & 1));
             fence_after_thread_sync();
-            for (int ch = 0; ch < NCH; ++ch) {
+            {
                 uint32_t d[32];
-                tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
+                tmem_ld32(taddr + (uint32_t)s * 128u, d);
                 tmem_ld_wait();
-                const float* sc = s_sq + t * 128 + h * CW + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
-                    const int key = (int)(__float_as_uint(fmaxf(dist, 1e-30f)) >> 19);      // NaN -> 1e-30: lands in the last bin
+                    const float dist = fmaf(-2.0f, __uint_as_float(d[i]), base[i]);
+                    const int key = __float_as_int(dist) >> 19;      // arithmetic shift: zero / negative distances land in the last (nearest) bin
                     const int bin = min(max(keymax - key, 0), kKtBins - 1);
                     atomicAdd(hcol + bin * 64, hinc);            // fire-and-forget: no dependent chain through shared memory
                 }
@@ -263,20 +287,21 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         // ---- pass 2: fine distances -> the row's candidate list (slots handed out by a shared-memory counter) ----
         for (int t = 0; t < NT; ++t) {
             const int j = NT1 + t, s = j & 1;
+            float base[32];
+            load_base(base, t);
             mbar_wait(&s_dfull[s], (uint32_t)((j >> 1) & 1));
             fence_after_thread_sync();
-            for (int ch = 0; ch < NCH; ++ch) {
+            {
                 uint32_t d[32];
-                tmem_ld32(taddr + (uint32_t)s * 128u + (uint32_t)ch * 32u, d);
+                tmem_ld32(taddr + (uint32_t)s * 128u, d);
                 tmem_ld_wait();
-                const float* sc = s_sq + t * 128 + h * CW + ch * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float dist = fmaf(-2.0f, __uint_as_float(d[i]), sqq + sc[i]);
+                    const float dist = fmaf(-2.0f, __uint_as_float(d[i]), base[i]);
                     if (dist < T) {
                         const int slot = atomicAdd(&s_cnt[r], 1);
                         if (slot < kKtCap) {
-                            lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * CW + ch * 32 + i);
+                            lidx[slot * 128 + r] = (unsigned short)(t * 128 + h * CW + i);
                             ladj[slot * 128 + r] = dist;
                         }
                     }
