@@ -243,12 +243,19 @@ PSA_API size_t psa_sa_group_all_workspace_bytes(int b, int n, int c, const psa_m
 PSA_API int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, const float* points, const psa_mlp* mlp,
                                    float* out, void* workspace, size_t workspace_bytes, psa_stream_t stream);
 
-/* Arithmetic of the grouped MLP.  0 (default): layers after the first run on the tcgen05 tensor cores with both operands
- * split into three exactly representable bf16 pieces (a = a1+a2+a3, w = w1+w2+w3; six MMAs per product, small terms first,
- * fp32 accumulation in tensor memory: within 1e-5 of fp64 on O(1) activations) whenever the shapes allow -- set-abstraction
- * levels with widths 64/128 (last width 64 or a multiple of 128) and nsample 32/64/128 on tc_sa_dual_kernel, dense layers with
- * N = 64 or a multiple of 128 on tc_dense2 / tc_dense3 -- and on the fp32-FMA kernels otherwise.  1: fp32-FMA kernels only.
- * The switch is process-global and not synchronised: set it before launching work, not concurrently with it. */
+/* Arithmetic of the grouped MLP.  Whenever the shapes allow -- set-abstraction levels with widths 64/128 (last width 64 or a
+ * multiple of 128) and nsample 32/64/128 on tc_sa_dual_kernel, dense layers with N = 64 or a multiple of 128 on tc_dense2 /
+ * tc_dense3 -- the layers after the first run on the tcgen05 tensor cores with fp32 accumulation in tensor memory; other shapes
+ * run on the fp32-FMA kernels.  The fp32 operands are split into exactly representable 16-bit pieces:
+ *   0 (default): two fp16 pieces per operand (22 mantissa bits), three MMAs per product  a1w2 + a2w1 + a1w1  -- the same error
+ *      against fp64 as an fp32 FMA chain (1e-5 contract of the tests).  fp16 covers |v| < 65504: every kernel tracks the pieces
+ *      it stores (weights too) and raises a device-side flag when a value leaves that range; the call then reruns the op with
+ *      bf16x3 operands (launched unconditionally, a no-op unless the flag is set), so results are valid for any fp32 input.
+ *   2: three bf16 pieces per operand, six MMAs per product (small terms first) -- any magnitude, twice the tensor work.
+ *   1: fp32-FMA kernels only.
+ * Weight images (psa_prepare_weight_image) are format-specific: psa_mlp_image_plan returns the format of the current mode in its
+ * nt values; images of the other format are ignored (rebuilt per call).  The switch is process-global and not synchronised:
+ * set it before launching work, not concurrently with it. */
 PSA_API int psa_set_mlp_mode(int mode);
 PSA_API int psa_get_mlp_mode(void);
 

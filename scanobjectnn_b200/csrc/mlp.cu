@@ -583,12 +583,14 @@ int launch_fc_small(const DenseArgs& d, float* partial, cudaStream_t st) {
     return check_launch("fc_small");
 }
 
-__global__ void fill_ord_neg_inf_kernel(long long total, int* out) {
+__global__ void fill_ord_neg_inf_kernel(long long total, int* out, const unsigned int* run_if = nullptr) {
+    if (run_if != nullptr && *run_if == 0u) return;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x)
         out[e] = f2ord(__int_as_float(0xff800000));
 }
-__global__ void decode_ord_kernel(long long total, int* out) {
+__global__ void decode_ord_kernel(long long total, int* out, const unsigned int* run_if = nullptr) {
+    if (run_if != nullptr && *run_if == 0u) return;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x)
         out[e] = __float_as_int(ord2f(out[e]));
@@ -679,12 +681,12 @@ int edgeconv_simt(int b, int n, int c, int k, const float* x, const int* nn_idx,
     a.xyz = nullptr; a.new_xyz = nullptr; a.feat = x; a.idx = nn_idx; a.out = out;
     return launch_fused<kGatherEdge>(a, st, "edgeconv");
 }
-int launch_fill_ord_neg_inf(long long total, float* out, cudaStream_t st) {
-    fill_ord_neg_inf_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, reinterpret_cast<int*>(out));
+int launch_fill_ord_neg_inf(long long total, float* out, cudaStream_t st, const unsigned int* run_if) {
+    fill_ord_neg_inf_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, reinterpret_cast<int*>(out), run_if);
     return check_launch("fill_ord_neg_inf_kernel");
 }
-int launch_decode_ord(long long total, float* out, cudaStream_t st) {
-    decode_ord_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, reinterpret_cast<int*>(out));
+int launch_decode_ord(long long total, float* out, cudaStream_t st, const unsigned int* run_if) {
+    decode_ord_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(total, reinterpret_cast<int*>(out), run_if);
     return check_launch("decode_ord_kernel");
 }
 }  // namespace psa

@@ -24,7 +24,8 @@ int sa_module_simt(int b, int n, int m, int c, int nsample, const float* xyz, co
                    const int* idx, const psa_mlp* mlp, float* out, cudaStream_t st);
 int validate_mlp_public(const psa_mlp* mlp, const char* who);
 int edgeconv_simt(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp, float* out, cudaStream_t st);
-int launch_fill_ord_neg_inf(long long total, float* out, cudaStream_t st);   // out := order-preserving int code of -inf
-int launch_decode_ord(long long total, float* out, cudaStream_t st);         // int codes -> floats, in place
+// `run_if` non-null: no-op unless *run_if != 0 (device-side condition, see tc_mlp.cu)
+int launch_fill_ord_neg_inf(long long total, float* out, cudaStream_t st, const unsigned int* run_if = nullptr);   // out := order-preserving int code of -inf
+int launch_decode_ord(long long total, float* out, cudaStream_t st, const unsigned int* run_if = nullptr);         // int codes -> floats, in place
 
 }  // namespace psa

@@ -10,6 +10,7 @@
 //     ISSUE CONVENTION below); everybody else waits on the barrier's parity.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace psa {
@@ -105,7 +106,7 @@ __device__ __forceinline__ uint64_t smem_desc_at(SmemDescBase b, uint32_t off) {
 __device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t M, uint32_t N) {
     return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t kFmtBF16 = 1, kFmtTF32 = 2;
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2;     // kind::f16 takes F16 or BF16 operands; kind::tf32 takes TF32
 
 // D[tmem] (+)= A[tmem] * B[smem desc]; accumulate = 0 overwrites D.  Call from a CONVERGED warp (see above).
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -179,6 +180,56 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo_elem, hi_elem);   // .x = lo_elem (low 16 bits), .y = hi_elem
     return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// fp16 pieces (two per operand: 22 mantissa bits, three MMAs per product).  pack: .x = lo_elem in the low 16 bits.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+    __half2 p = __floats2half2_rn(lo_elem, hi_elem);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t p) { return __half22float2(*reinterpret_cast<__half2*>(&p)); }
+// running |max| of every leading piece a kernel stores (packed halves): an infinity here means a value left the fp16 range
+__device__ __forceinline__ void track_f16x2(uint32_t& m, uint32_t p) {
+    const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&m), __habs2(*reinterpret_cast<__half2*>(&p)));
+    m = *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ bool f16x2_overflowed(uint32_t m) { return (m & 0x7c00u) == 0x7c00u || (m & 0x7c000000u) == 0x7c000000u; }
+
+// Operand split of the tensor-core kernels, NP pieces per operand:
+//   NP = 3: three bf16 pieces (a = a1 + a2 + a3 exactly), six MMAs  a1w3 + a2w2 + a3w1 + a1w2 + a2w1 + a1w1  (small products first: the
+//           accumulator add truncates) -- any fp32 magnitude;
+//   NP = 2: two fp16 pieces (22 mantissa bits; the tail below 2^-24 absolute is dropped), three MMAs  a1w2 + a2w1 + a1w1 -- half
+//           the tensor work, same accuracy against fp64 as the fp32 FMA kernels, valid while |a| < 65504 (the kernels track the
+//           stored pieces and raise a flag otherwise; the launcher then reruns the op on the NP = 3 instantiation).
+template <int NP> struct Split;
+template <> struct Split<3> {
+    static constexpr uint32_t kFmt = kFmtBF16;
+    static constexpr int kTerms = 6;
+    __host__ __device__ static constexpr uint32_t a(int t) { return t == 0 ? 0u : t == 1 ? 1u : t == 2 ? 2u : t == 3 ? 0u : t == 4 ? 1u : 0u; }
+    __host__ __device__ static constexpr uint32_t w(int t) { return t == 0 ? 2u : t == 1 ? 1u : t == 2 ? 0u : t == 3 ? 1u : 0u; }
+};
+template <> struct Split<2> {
+    static constexpr uint32_t kFmt = kFmtF16;
+    static constexpr int kTerms = 3;
+    __host__ __device__ static constexpr uint32_t a(int t) { return t == 1 ? 1u : 0u; }
+    __host__ __device__ static constexpr uint32_t w(int t) { return t == 0 ? 1u : 0u; }
+};
+// split two consecutive elements into NP packed pieces p[0..NP) (h0, h1 are clobbered); NP = 2 also tracks the leading piece
+template <int NP>
+__device__ __forceinline__ void split_pair(float h0, float h1, uint32_t (&p)[NP], uint32_t& ovf) {
+    if constexpr (NP == 3) {
+        (void)ovf;
+        p[0] = pack_bf16x2(h0, h1);
+        h0 -= __uint_as_float(p[0] << 16); h1 -= __uint_as_float(p[0] & 0xffff0000u);
+        p[1] = pack_bf16x2(h0, h1);
+        h0 -= __uint_as_float(p[1] << 16); h1 -= __uint_as_float(p[1] & 0xffff0000u);
+        p[2] = pack_bf16x2(h0, h1);
+    } else {
+        p[0] = pack_f16x2(h0, h1);
+        track_f16x2(ovf, p[0]);
+        const float2 f = unpack_f16x2(p[0]);
+        p[1] = pack_f16x2(h0 - f.x, h1 - f.y);
+    }
 }
 
 // byte offset of element (n, k) of a [N][K] K-major SWIZZLE_128B tile

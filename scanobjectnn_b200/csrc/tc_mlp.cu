@@ -44,8 +44,11 @@ constexpr int kMaxTcLayers = 2;
 //   (w = w1 + w2 + w3, every piece exactly representable), each [Nt][64] K-major SWIZZLE_128B, Nt*128 B per piece;
 //   blocks stored in (nt major, kc minor) order.  6 bytes per weight.
 // ------------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t tc_block_bytes(int Nt) { return (uint32_t)Nt * 64u * 6u; }
-__host__ __device__ inline size_t tc_image_bytes(int K, int N) { return (size_t)K * N * 6u; }     // independent of the tile width
+// np = pieces per weight: 3 (bf16x3, 6 bytes per weight) or 2 (fp16x2, 4 bytes); see Split<NP> in tc_common.cuh
+__host__ __device__ inline uint32_t tc_block_bytes(int Nt, int np) { return (uint32_t)Nt * 128u * (uint32_t)np; }
+__host__ __device__ inline size_t tc_image_bytes(int K, int N, int np) { return (size_t)K * N * 2u * (size_t)np; }     // independent of the tile width
+// an image allocation = the blocks + a 256-byte trailer whose first word is set when a weight left the fp16 range (np = 2)
+__host__ __device__ inline size_t tc_image_alloc_bytes(int K, int N, int np) { return ((tc_image_bytes(K, N, np) + 255) & ~(size_t)255) + 256; }
 
 struct TcArgs {
     long long groups;      // neighbourhoods = b*m
@@ -73,6 +76,10 @@ struct TcArgs {
     int dual;              // 1: tc_sa_dual_kernel (two row groups per CTA, bf16x3 operands, 64-wide output tiles)
     unsigned int* tile_counter;   // zeroed before the launch: tiles are handed out dynamically (CTAs that start late or
                                   // share their SM with another stream's kernels simply take fewer)
+    int np;                       // operand pieces: 2 (fp16x2) or 3 (bf16x3)
+    unsigned int* ovf;            // np = 2: set to 1 when an activation or weight left the fp16 range (the result is then invalid)
+    const unsigned int* run_if;   // non-null: the launch is a no-op unless *run_if != 0 (the np = 3 rerun of a flagged launch)
+    const unsigned int* wflag[kMaxTcLayers];   // np = 2: trailer word of each weight image
 };
 
 // transposing butterfly: v[q] = column q of this lane's row; afterwards v[0] on lane l = max over the warp's 32 rows of column l
@@ -115,25 +122,29 @@ __device__ unsigned long long g_tc_timing[8];
 //     Six bf16 MMAs  a1w3 + a2w2 + a3w1 + a1w2 + a2w1 + a1w1  (small terms first: the accumulator add truncates)
 //     reproduce the fp32 product to ~2^-25; weights stay at 6 bytes per element.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kImageBf16x3 = 0x100;      // flag in psa_mlp.image_nt / psa_mlp_image_plan: image holds three bf16 pieces
+constexpr int kImageBf16x3 = 0x100;      // flags in psa_mlp.image_nt / psa_mlp_image_plan: image holds three bf16 pieces ..
+constexpr int kImageF16x2 = 0x200;       // .. or two fp16 pieces
+constexpr int kImageFlags = kImageBf16x3 | kImageF16x2;
+__host__ __device__ inline int image_flag(int np) { return np == 2 ? kImageF16x2 : kImageBf16x3; }
 
-__global__ void tc_prep_weights3_kernel(int K, int Kp, int N, int Nt, const float* __restrict__ W, uint8_t* __restrict__ image) {
+template <int NP>
+__global__ void tc_prep_weights_kernel(int K, int Kp, int N, int Nt, const float* __restrict__ W, uint8_t* __restrict__ image,
+                                       unsigned int* __restrict__ trailer, const unsigned int* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0u) return;
     const int KC = Kp / 64;
-    const uint32_t bb = tc_block_bytes(Nt), piece = (uint32_t)Nt * 128u;
+    const uint32_t bb = tc_block_bytes(Nt, NP), piece = (uint32_t)Nt * 128u;
+    uint32_t ovf = 0u;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Kp * N; e += gridDim.x * blockDim.x) {
         const int n = e % N, k = e / N;
         const float w = k < K ? __ldg(W + e) : 0.f;
-        const __nv_bfloat16 c1 = __float2bfloat16_rn(w);
-        const float r1 = w - __bfloat162float(c1);
-        const __nv_bfloat16 c2 = __float2bfloat16_rn(r1);
-        const float r2 = r1 - __bfloat162float(c2);
-        const __nv_bfloat16 c3 = __float2bfloat16_rn(r2);
+        uint32_t pc[NP];
+        split_pair<NP>(w, 0.f, pc, ovf);
         uint8_t* blk = image + (size_t)((n / Nt) * KC + (k >> 6)) * bb;
         const uint32_t off = swz_off_bf16(n % Nt, k & 63, Nt);
-        *reinterpret_cast<__nv_bfloat16*>(blk + off) = c1;
-        *reinterpret_cast<__nv_bfloat16*>(blk + piece + off) = c2;
-        *reinterpret_cast<__nv_bfloat16*>(blk + 2u * piece + off) = c3;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) *reinterpret_cast<uint16_t*>(blk + i * piece + off) = (uint16_t)(pc[i] & 0xffffu);
     }
+    if (NP == 2 && f16x2_overflowed(ovf)) atomicOr(trailer, 1u);
 }
 
 struct TcDual {
@@ -143,55 +154,72 @@ struct TcDual {
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;\n" ::"r"(g + 1) : "memory"); }
 
-// split 32 activations into three bf16 pieces and store them as 16 columns each at a1, a1 + ps, a1 + 2 ps (h is clobbered)
-__device__ __forceinline__ void store_a3_at(uint32_t a1, float (&h)[32], uint32_t ps = 64) {
+// split 32 activations into NP pieces and store them as 16 columns each at a1, a1 + ps, .. (h is clobbered)
+template <int NP>
+__device__ __forceinline__ void store_a_at(uint32_t a1, float (&h)[32], uint32_t ps, uint32_t& ovf) {
     uint32_t p[16];
+    if constexpr (NP == 3) {
+        (void)ovf;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
-        h[2 * q] -= __uint_as_float(p[q] << 16);
-        h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
+        for (int q = 0; q < 16; ++q) {
+            p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+            h[2 * q] -= __uint_as_float(p[q] << 16);
+            h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
+        }
+        tmem_st16(a1, p);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+            h[2 * q] -= __uint_as_float(p[q] << 16);
+            h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
+        }
+        tmem_st16(a1 + ps, p);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
+        tmem_st16(a1 + 2 * ps, p);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            p[q] = pack_f16x2(h[2 * q], h[2 * q + 1]);
+            track_f16x2(ovf, p[q]);
+            const float2 f = unpack_f16x2(p[q]);
+            h[2 * q] -= f.x;
+            h[2 * q + 1] -= f.y;
+        }
+        tmem_st16(a1, p);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p[q] = pack_f16x2(h[2 * q], h[2 * q + 1]);
+        tmem_st16(a1 + ps, p);
     }
-    tmem_st16(a1, p);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
-        h[2 * q] -= __uint_as_float(p[q] << 16);
-        h[2 * q + 1] -= __uint_as_float(p[q] & 0xffff0000u);
-    }
-    tmem_st16(a1 + ps, p);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[2 * q], h[2 * q + 1]);
-    tmem_st16(a1 + 2 * ps, p);
 }
 
-// issuer warp (converged): D[128 x NT_] (+)= sum over the six piece pairs, KC blocks of 64 input channels.
-// a1_col: TMEM column of piece 1 of the A operand (pieces 64 columns apart); d_col: accumulator; `first`: overwrite D.
-template <int KC, int NT_, int PS = 64>
-__device__ __forceinline__ void issue_tile3_c(uint32_t tmem_base, uint32_t d_col, uint32_t a1_col, uint32_t blocks_addr) {
-    constexpr uint32_t bb = NT_ * 384u, piece = NT_ * 128u;
+// issuer warp (converged): D[128 x NT_] (+)= sum over the piece pairs of Split<NP>, KC blocks of 64 input channels.
+// a1_col: TMEM column of piece 1 of the A operand (pieces PS columns apart); d_col: accumulator (overwritten by the first MMA).
+template <int KC, int NT_, int PS, int NP>
+__device__ __forceinline__ void issue_tile_c(uint32_t tmem_base, uint32_t d_col, uint32_t a1_col, uint32_t blocks_addr) {
+    constexpr uint32_t bb = NT_ * 128u * NP, piece = NT_ * 128u;
     const uint32_t tb = warp_uniform(tmem_base);
     const uint32_t d = tb + d_col;
     const uint32_t a1 = tb + a1_col;
-    const uint32_t idesc = make_idesc(kFmtBF16, 128, NT_);
+    const uint32_t idesc = make_idesc(Split<NP>::kFmt, 128, NT_);
     const SmemDescBase b0 = smem_desc_base(warp_uniform(blocks_addr));
-    constexpr uint32_t ap[6] = {0, 1, 2, 0, 1, 0};     // A piece / W piece of the six terms, small products first
-    constexpr uint32_t wp[6] = {2, 1, 0, 1, 0, 0};
 #pragma unroll
-    for (int t = 0; t < 6; ++t)
+    for (int t = 0; t < Split<NP>::kTerms; ++t)
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4)
-                mma_bf16_ts(d, a1 + ap[t] * PS + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + wp[t] * piece + s4 * 32), idesc, (t | kc | s4) ? 1u : 0u);
+                mma_bf16_ts(d, a1 + Split<NP>::a(t) * PS + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + Split<NP>::w(t) * piece + s4 * 32), idesc,
+                            (t | kc | s4) ? 1u : 0u);
 }
 // dbuf (levels whose layers are all <= 64 wide): A pieces 32 columns apart at 128.., two D slots at 0 and 64
-__device__ __forceinline__ void issue_tile3(uint32_t gbase, uint32_t blocks_addr, int KC, bool dbuf, int dslot) {
+template <int NP>
+__device__ __forceinline__ void issue_tile(uint32_t gbase, uint32_t blocks_addr, int KC, bool dbuf, int dslot) {
     if (dbuf) {
-        if (dslot == 0) issue_tile3_c<1, TcDual::kNt, 32>(gbase, 0, 128, blocks_addr);
-        else issue_tile3_c<1, TcDual::kNt, 32>(gbase, 64, 128, blocks_addr);
-    } else if (KC == 1) issue_tile3_c<1, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
-    else issue_tile3_c<2, TcDual::kNt>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+        if (dslot == 0) issue_tile_c<1, TcDual::kNt, 32, NP>(gbase, 0, 128, blocks_addr);
+        else issue_tile_c<1, TcDual::kNt, 32, NP>(gbase, 64, 128, blocks_addr);
+    } else if (KC == 1) issue_tile_c<1, TcDual::kNt, 64, NP>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+    else issue_tile_c<2, TcDual::kNt, 64, NP>(gbase, TcDual::D, TcDual::A1, blocks_addr);
 }
 
 struct TcDualLayout {
@@ -206,9 +234,9 @@ __host__ __device__ inline TcDualLayout tc_dual_layout(const TcArgs& a) {
     uint32_t off = 0;
     for (int l = 0; l < a.nl; ++l) {
         L.w[l] = off;
-        if (!(a.stream_last && l == a.nl - 1)) off += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+        if (!(a.stream_last && l == a.nl - 1)) off += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l], a.np);
     }
-    L.ring_bytes = a.stream_last ? (uint32_t)(a.Kd[a.nl - 1] / 64) * tc_block_bytes(TcDual::kNt) : 0u;
+    L.ring_bytes = a.stream_last ? (uint32_t)(a.Kd[a.nl - 1] / 64) * tc_block_bytes(TcDual::kNt, a.np) : 0u;
     L.ring[0] = off; off += L.ring_bytes;
     L.ring[1] = off; off += L.ring_bytes;
     L.vec = off;
@@ -268,10 +296,12 @@ __device__ __forceinline__ void pipe_release(int* token, int lane) {
         : "memory");
 }
 
-template <bool DBUF>
+template <bool DBUF, int NP>
 __global__ void __launch_bounds__(TcDual::kThreads, 1)
 tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
+    if (a.run_if != nullptr && *a.run_if == 0u) return;      // np = 3 rerun of a launch that stayed inside the fp16 range: nothing to do
     constexpr int kNt = TcDual::kNt;
+    uint32_t ovf = 0u;                                        // np = 2: packed |max| of every leading piece this thread stores
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[2];  // MMA completion, per group
     __shared__ __align__(8) uint64_t s_mbar2[2]; // MMA completion of the second D slot (dbuf levels), per group
@@ -323,12 +353,12 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     if (tid == 0) {
         uint32_t total = 0;
         for (int l = 0; l < a.nl; ++l)
-            if (!(a.stream_last && l == last)) total += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+            if (!(a.stream_last && l == last)) total += (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l], NP);
         if (total) {
             mbar_expect_tx(&s_rbar, total);
             for (int l = 0; l < a.nl; ++l) {
                 if (a.stream_last && l == last) continue;
-                const uint32_t bytes = (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l]);
+                const uint32_t bytes = (uint32_t)tc_image_bytes(a.Kd[l], a.Ntot[l], NP);
                 for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(base + L.w[l] + o, a.image[l] + o, min(32768u, bytes - o), &s_rbar);
             }
             mbar_wait(&s_rbar, 0);
@@ -415,7 +445,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
                     h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
                 }
-                store_a3_at(row_taddr + a1_col + ch * 16, h, a_ps);
+                store_a_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
             }
         }
         tmem_st_wait();
@@ -432,7 +462,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     if (issuer) {
                         pipe_acquire(&s_token, lane);
                         fence_after_thread_sync();
-                        issue_tile3(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt), KC, dbuf, 0);
+                        issue_tile<NP>(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt, NP), KC, dbuf, 0);
                         mma_commit(&s_mbar[g]);
                         pipe_release(&s_token, lane);
                     }
@@ -448,8 +478,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], valid, 0.f, h1);
                     if (nt + 1 < NT) { fence_before_thread_sync(); group_bar(g); }       // D drained before the next tile lands in it
                 }
-                store_a3_at(row_taddr + a1_col + cs * 16, h0, a_ps);
-                if (NT == 2) store_a3_at(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps);
+                store_a_at<NP>(row_taddr + a1_col + cs * 16, h0, a_ps, ovf);
+                if (NT == 2) store_a_at<NP>(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps, ovf);
                 tmem_st_wait();
                 fence_before_thread_sync();
                 group_bar(g);
@@ -490,11 +520,11 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                         if (streamed) { mbar_wait(&s_wbar[g], wphase); wphase ^= 1u; }
                         pipe_acquire(&s_token, lane);   // (ends in __syncwarp: the issue below must be warp-uniform)
                         fence_after_thread_sync();
-                        const uint32_t blocks = streamed ? smem_u32(base + L.ring[g]) : smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt);
-                        issue_tile3(tmem_base, blocks, KC, dbuf, 0);
+                        const uint32_t blocks = streamed ? smem_u32(base + L.ring[g]) : smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt, NP);
+                        issue_tile<NP>(tmem_base, blocks, KC, dbuf, 0);
                         mma_commit(&s_mbar[g]);
                         if (DBUF) {                 // the pair's second tile goes to the other D slot right away (NT is even)
-                            issue_tile3(tmem_base, blocks + (uint32_t)KC * tc_block_bytes(kNt), KC, true, 1);
+                            issue_tile<NP>(tmem_base, blocks + (uint32_t)KC * tc_block_bytes(kNt, NP), KC, true, 1);
                             mma_commit(&s_mbar2[g]);
                         }
                         pipe_release(&s_token, lane);
@@ -552,6 +582,12 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     if (tid == 0)
         for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_timing[i], tacc[i]);
 #endif
+    if constexpr (NP == 2) {
+        if (f16x2_overflowed(ovf)) atomicOr(a.ovf, 1u);
+        if (tid == 0)
+            for (int l = 0; l < a.nl; ++l)
+                if (a.wflag[l] != nullptr && *a.wflag[l] != 0u) atomicOr(a.ovf, 1u);
+    }
     __syncthreads();
     if (warp == 0) tmem_dealloc(s_tmem, 512);
 }
@@ -581,6 +617,10 @@ struct TcDenseArgs {
     const float* in_shift = nullptr;
     int in_relu = 0;
     float* stat_partial = nullptr;     // (row tiles, 2, N) or null
+    // operand split (see TcArgs): np = 2 launches raise *ovf, the np = 3 rerun is skipped unless *run_if != 0
+    unsigned int* ovf = nullptr;
+    const unsigned int* run_if = nullptr;
+    const unsigned int* wflag = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -606,9 +646,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int NT_>
+template <int NT_, int NP>
 __global__ void __launch_bounds__(TcDense2::kThreads, 1)
 tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
+    if (a.run_if != nullptr && *a.run_if == 0u) return;
+    uint32_t ovf = 0u;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_wfull[2];     // weight slot landed (tx)
     __shared__ __align__(8) uint64_t s_afull[2];     // A buffer written by all 16 row warps
@@ -621,7 +663,7 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
     const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int KCtot = a.Kp / 64;
-    constexpr uint32_t bb = NT_ * 384u, slot_bytes = 2u * bb;
+    constexpr uint32_t bb = NT_ * 128u * NP, slot_bytes = 2u * bb;
     const int nt = blockIdx.y;
     for (int i = tid; i < NT_; i += TcDense2::kThreads) {
         const int c = nt * NT_ + i;
@@ -676,8 +718,8 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
             fence_after_thread_sync();
             const uint32_t blocks = smem_u32(base) + (uint32_t)b * slot_bytes;
             const uint32_t a1 = TcDense2::A0 + (uint32_t)b * TcDense2::ABUF;
-            if (KCtot - 2 * sg >= 2) issue_tile3_c<2, NT_>(tmem_base, TcDense2::D, a1, blocks);
-            else issue_tile3_c<1, NT_>(tmem_base, TcDense2::D, a1, blocks);
+            if (KCtot - 2 * sg >= 2) issue_tile_c<2, NT_, 64, NP>(tmem_base, TcDense2::D, a1, blocks);
+            else issue_tile_c<1, NT_, 64, NP>(tmem_base, TcDense2::D, a1, blocks);
             mma_commit(&s_mma);
         }
     } else {
@@ -715,7 +757,7 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
         auto store_x = [&](int sg, float (&h)[32]) {
             const int kcs = min(2, KCtot - 2 * sg);
             if (cs < kcs * 2) {
-                store_a3_at(row_taddr + TcDense2::A0 + (uint32_t)(sg & 1) * TcDense2::ABUF + cs * 16, h);
+                store_a_at<NP>(row_taddr + TcDense2::A0 + (uint32_t)(sg & 1) * TcDense2::ABUF + cs * 16, h, 64, ovf);
                 tmem_st_wait();
             }
             fence_before_thread_sync();
@@ -805,6 +847,9 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
         }
     }
     TC_STAMP(5);
+    if constexpr (NP == 2) {
+        if (f16x2_overflowed(ovf) || (tid == 0 && a.wflag != nullptr && *a.wflag != 0u)) atomicOr(a.ovf, 1u);
+    }
     fence_before_thread_sync();
     __syncthreads();
     TC_STAMP(6);
@@ -832,12 +877,15 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
 // ------------------------------------------------------------------------------------------------------------------
 struct TcDense3 {
     static constexpr int kPrepWarps = 16, kThreads = 17 * 32;
-    static constexpr uint32_t kPiece = 128u * 128u;          // one bf16 piece of a 128 x 64 block: 16 KB
-    static constexpr uint32_t kBlock = 3u * kPiece;          // 48 KB
+    static constexpr uint32_t kPiece = 128u * 128u;          // one 16-bit piece of a 128 x 64 block: 16 KB
 };
 
+template <int NP>
 __global__ void __launch_bounds__(TcDense3::kThreads, 1)
 tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
+    if (a.run_if != nullptr && *a.run_if == 0u) return;
+    constexpr uint32_t kBlock = NP * TcDense3::kPiece;       // 48 KB (bf16x3) or 32 KB (fp16x2)
+    uint32_t ovf = 0u;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_wfull[2];     // weight block landed (tx)
     __shared__ __align__(8) uint64_t s_xfull[2];     // x block written by the 16 prep warps
@@ -849,11 +897,11 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
     const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* wslot = base;                                   // 2 x 48 KB
-    uint8_t* xslot = base + 2 * TcDense3::kBlock;            // 2 x 48 KB
+    uint8_t* xslot = base + 2 * kBlock;            // 2 x 48 KB
     const int KB = a.Kp / 64;
     const int nt = blockIdx.y;
     const long long row0 = (long long)blockIdx.x * 128;
-    const uint8_t* img = a.image + (size_t)nt * KB * TcDense3::kBlock;
+    const uint8_t* img = a.image + (size_t)nt * KB * kBlock;
 
     if (warp_u == 0) tmem_alloc(&s_tmem, 512);
     if (tid == 0) {
@@ -878,9 +926,7 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
 
     if (warp_u == TcDense3::kPrepWarps) {
         // ================= issuer warp =================
-        const uint32_t idesc = make_idesc(kFmtBF16, 128, 128);
-        constexpr uint32_t xp[6] = {0, 1, 2, 0, 1, 0};     // x piece / W piece of the six terms, small products first
-        constexpr uint32_t wp[6] = {2, 1, 0, 1, 0, 0};
+        const uint32_t idesc = make_idesc(Split<NP>::kFmt, 128, 128);
         for (int kb = 0; kb < KB; ++kb) {
             const int st = kb & 1;
             const uint32_t par = (uint32_t)((kb >> 1) & 1);
@@ -889,15 +935,15 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
             __syncwarp();
             fence_after_thread_sync();
             const uint32_t d = tmem_base + (uint32_t)(kb & 3) * 128u;
-            const SmemDescBase wa = smem_desc_base(warp_uniform(smem_u32(wslot) + (uint32_t)st * TcDense3::kBlock));
-            const SmemDescBase xb = smem_desc_base(warp_uniform(smem_u32(xslot) + (uint32_t)st * TcDense3::kBlock));
+            const SmemDescBase wa = smem_desc_base(warp_uniform(smem_u32(wslot) + (uint32_t)st * kBlock));
+            const SmemDescBase xb = smem_desc_base(warp_uniform(smem_u32(xslot) + (uint32_t)st * kBlock));
             const uint32_t first = kb < 4 ? 0u : 1u;         // an accumulator's first block overwrites it
 #pragma unroll
-            for (int t = 0; t < 6; ++t)
+            for (int t = 0; t < Split<NP>::kTerms; ++t)
 #pragma unroll
                 for (int s4 = 0; s4 < 4; ++s4)
-                    mma_bf16_ss(d, smem_desc_at(wa, wp[t] * TcDense3::kPiece + s4 * 32), smem_desc_at(xb, xp[t] * TcDense3::kPiece + s4 * 32), idesc,
-                                (t | s4) ? 1u : first);
+                    mma_bf16_ss(d, smem_desc_at(wa, Split<NP>::w(t) * TcDense3::kPiece + s4 * 32), smem_desc_at(xb, Split<NP>::a(t) * TcDense3::kPiece + s4 * 32),
+                                idesc, (t | s4) ? 1u : first);
             mma_commit(&s_free[st]);
         }
     } else {
@@ -934,24 +980,19 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
             if (kb >= 2) mbar_wait(&s_free[st], (uint32_t)(((kb - 2) >> 1) & 1));      // stage released by block kb-2's MMAs
             TC_STAMP(1);
             if (warp_u == 0 && lane == 0) {                                             // its weight slot is free too
-                mbar_expect_tx(&s_wfull[st], TcDense3::kBlock);
-                for (uint32_t o = 0; o < TcDense3::kBlock; o += 16384u)
-                    bulk_g2s(wslot + (uint32_t)st * TcDense3::kBlock + o, img + (size_t)kb * TcDense3::kBlock + o, 16384u, &s_wfull[st]);
+                mbar_expect_tx(&s_wfull[st], kBlock);
+                for (uint32_t o = 0; o < kBlock; o += 16384u)
+                    bulk_g2s(wslot + (uint32_t)st * kBlock + o, img + (size_t)kb * kBlock + o, 16384u, &s_wfull[st]);
             }
-            uint8_t* xs = xslot + (uint32_t)st * TcDense3::kBlock;
+            uint8_t* xs = xslot + (uint32_t)st * kBlock;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t rr = (uint32_t)(warp_u * 8 + i);
                 const uint32_t off = swz_off_bf16(rr, 2u * (uint32_t)lane, 128u);
-                float h0 = v[i].x, h1 = v[i].y;
-                uint32_t p1 = pack_bf16x2(h0, h1);
-                h0 -= __uint_as_float(p1 << 16); h1 -= __uint_as_float(p1 & 0xffff0000u);
-                uint32_t p2 = pack_bf16x2(h0, h1);
-                h0 -= __uint_as_float(p2 << 16); h1 -= __uint_as_float(p2 & 0xffff0000u);
-                uint32_t p3 = pack_bf16x2(h0, h1);
-                *reinterpret_cast<uint32_t*>(xs + off) = p1;
-                *reinterpret_cast<uint32_t*>(xs + TcDense3::kPiece + off) = p2;
-                *reinterpret_cast<uint32_t*>(xs + 2u * TcDense3::kPiece + off) = p3;
+                uint32_t pc[NP];
+                split_pair<NP>(v[i].x, v[i].y, pc, ovf);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) *reinterpret_cast<uint32_t*>(xs + (uint32_t)j * TcDense3::kPiece + off) = pc[j];
             }
             fence_proxy_async_smem();            // generic-proxy writes -> visible to the MMA's async-proxy reads
             __syncwarp();
@@ -1049,6 +1090,9 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
         }
     }
     TC_STAMP(4);
+    if constexpr (NP == 2) {
+        if (f16x2_overflowed(ovf) || (tid == 0 && a.wflag != nullptr && *a.wflag != 0u)) atomicOr(a.ovf, 1u);
+    }
     fence_before_thread_sync();
     __syncthreads();
     TC_STAMP(5);
@@ -1066,49 +1110,96 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
     if (pool_k > 1 && rows % pool_k != 0) return false;
     return true;
 }
-size_t tc_dense_image_bytes(int K, int N) { return (tc_image_bytes((K + 63) & ~63, N) + 255) & ~(size_t)255; }
 
-// tile width of a dense layer's weight image (the flag marks the three-bf16-piece format, the only one left)
-int tc_dense_nt(int N) { return ((N % 128) == 0 ? 128 : 64) | kImageBf16x3; }
+// Operand split of the inference launches: 2 = fp16x2 with the np = 3 rerun guard (default), 3 = bf16x3 only (psa_set_mlp_mode(2)).
+static int g_tc_np = 2;
+int tc_np() { return g_tc_np; }
 
-static void build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st);
+// Workspace reservation for one dense layer's images: an fp16x2 image (used when the caller brought no prebuilt one) followed by
+// the bf16x3 image of the guarded rerun / of mode 2 / of the training forward.
+static size_t tc_dense_image_off3(int K, int N) { return tc_image_alloc_bytes((K + 63) & ~63, N, 2); }
+size_t tc_dense_image_bytes(int K, int N) { return tc_dense_image_off3(K, N) + tc_image_alloc_bytes((K + 63) & ~63, N, 3); }
 
-// `image`: workspace to build the weight image in, or -- when `prebuilt` -- an image that already holds it
-int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
-                    const float* shift, float* out, const uint8_t* image, cudaStream_t st, const float* xyz3 = nullptr,
-                    const float* w3 = nullptr, bool prebuilt = false) {
-    const int Kp = (K + 63) & ~63;
-    const int nt_img = tc_dense_nt(N);
-    const int Nt = nt_img & ~kImageBf16x3;
-    if (!prebuilt) build_image(K, Kp, N, nt_img, W, const_cast<uint8_t*>(image), st);
-    TcDenseArgs a;
-    a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
-    a.x = x; a.image = image; a.scale = scale; a.shift = shift; a.out = out; a.xyz3 = xyz3; a.w3 = w3;
-    dim3 grid2((unsigned)((rows + 127) / 128), N / Nt);
-    if (pool_k > 128) { int rc0 = launch_fill_ord_neg_inf(rows / pool_k * N, out, st); if (rc0 != PSA_OK) return rc0; }
-    if (Nt == 128 && Kp <= 512) {
-        // transposed kernel, both operands from shared memory
-        const size_t smem3 = 4 * (size_t)TcDense3::kBlock + 1024;
-        PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        tc_dense3_kernel<<<grid2, TcDense3::kThreads, smem3, st>>>(a);
-        if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
-        return check_launch("tc_dense3_kernel");
-    }
-    const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt) + 1024;      // two slots of two 64-K blocks
-    if (Nt == 128) {
-        PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        tc_dense2_kernel<128><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
+// tile width of a dense layer's weight image, with the format flag of the current split
+int tc_dense_nt(int N) { return ((N % 128) == 0 ? 128 : 64) | image_flag(g_tc_np); }
+
+// builds the image of W (K x N, rows K..Kp zero) in the format `Nt` carries (width | format flag); zeroes the trailer first
+static int build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st, const unsigned int* run_if = nullptr) {
+    const int np = (Nt & kImageF16x2) ? 2 : 3;
+    unsigned int* trailer = reinterpret_cast<unsigned int*>(image + ((tc_image_bytes(Kp, N, np) + 255) & ~(size_t)255));
+    if (np == 2) {
+        PSA_CUDA(cudaMemsetAsync(trailer, 0, 256, st));
+        tc_prep_weights_kernel<2><<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt & ~kImageFlags, W, image, trailer, run_if);
     } else {
-        PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        tc_dense2_kernel<64><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
+        tc_prep_weights_kernel<3><<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt & ~kImageFlags, W, image, trailer, run_if);
     }
-    if (pool_k > 128) { int rc1 = launch_decode_ord(rows / pool_k * N, out, st); if (rc1 != PSA_OK) return rc1; }
-    return check_launch("tc_dense2_kernel");
+    return check_launch("tc_prep_weights_kernel");
+}
+static const unsigned int* image_trailer(const uint8_t* image, int Kp, int N, int np) {
+    return reinterpret_cast<const unsigned int*>(image + ((tc_image_bytes(Kp, N, np) + 255) & ~(size_t)255));
 }
 
+// one launch of a dense layer with NP pieces; `image` holds the weights in that format
+template <int NP>
+static int launch_tc_dense_np(TcDenseArgs& a, int Nt, cudaStream_t st) {
+    dim3 grid2((unsigned)((a.rows + 127) / 128), a.N / Nt);
+    const bool big = a.pool_k > 128;
+    if (big) { int rc0 = launch_fill_ord_neg_inf(a.rows / a.pool_k * a.N, a.out, st, a.run_if); if (rc0 != PSA_OK) return rc0; }
+    if (Nt == 128 && a.Kp <= 512) {
+        // transposed kernel, both operands from shared memory
+        const size_t smem3 = 4 * (size_t)NP * TcDense3::kPiece + 1024;
+        PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        tc_dense3_kernel<NP><<<grid2, TcDense3::kThreads, smem3, st>>>(a);
+    } else {
+        const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt, NP) + 1024;      // two slots of two 64-K blocks
+        if (Nt == 128) {
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<128, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc_dense2_kernel<128, NP><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
+        } else {
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense2_kernel<64, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc_dense2_kernel<64, NP><<<grid2, TcDense2::kThreads, smem2, st>>>(a);
+        }
+    }
+    int rc = check_launch("tc_dense_kernel");
+    if (rc != PSA_OK) return rc;
+    if (big) return launch_decode_ord(a.rows / a.pool_k * a.N, a.out, st, a.run_if);
+    return PSA_OK;
+}
+
+// out = relu?((x . W [+ xyz3 . w3]) * scale + shift) on the tensor cores, optional max over runs of pool_k rows.
+//   prebuilt : image of W in the CURRENT split's format (psa_prepare_weight_image), or null
+//   ws_img   : tc_dense_image_bytes(K, N) of scratch (missing images are built here)
+//   flag     : one zeroed device word (np = 2: raised when a value left the fp16 range; the bf16x3 rerun is conditional on it)
+int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const float* x, const float* W, const float* scale,
+                    const float* shift, float* out, const uint8_t* prebuilt, uint8_t* ws_img, unsigned int* flag, cudaStream_t st,
+                    const float* xyz3 = nullptr, const float* w3 = nullptr) {
+    const int Kp = (K + 63) & ~63;
+    const int Nt = (N % 128) == 0 ? 128 : 64;
+    TcDenseArgs a;
+    a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = pool_k; a.relu = relu;
+    a.x = x; a.scale = scale; a.shift = shift; a.out = out; a.xyz3 = xyz3; a.w3 = w3;
+    uint8_t* img3 = ws_img + tc_dense_image_off3(K, N);
+    int rc;
+    if (g_tc_np == 3) {
+        if (prebuilt == nullptr) { rc = build_image(K, Kp, N, Nt | kImageBf16x3, W, img3, st); if (rc != PSA_OK) return rc; }
+        a.image = prebuilt ? prebuilt : img3;
+        return launch_tc_dense_np<3>(a, Nt, st);
+    }
+    if (prebuilt == nullptr) { rc = build_image(K, Kp, N, Nt | kImageF16x2, W, ws_img, st); if (rc != PSA_OK) return rc; }
+    a.image = prebuilt ? prebuilt : ws_img;
+    a.ovf = flag; a.wflag = image_trailer(a.image, Kp, N, 2);
+    rc = launch_tc_dense_np<2>(a, Nt, st);
+    if (rc != PSA_OK) return rc;
+    // guarded rerun: both launches are no-ops unless the fp16x2 pass raised the flag
+    rc = build_image(K, Kp, N, Nt | kImageBf16x3, W, img3, st, flag);
+    if (rc != PSA_OK) return rc;
+    a.image = img3; a.ovf = nullptr; a.wflag = nullptr; a.run_if = flag;
+    return launch_tc_dense_np<3>(a, Nt, st);
+}
 
 // Training-mode forward of one layer on tc_dense3: y = relu(bn_prev(x)) . W + bias (pre-BN output), per-row-tile column
 // statistics.  The weights change every step, so the image is rebuilt into `image_ws` (tc_dense_image_bytes(K, N)) per call.
+// bf16x3 only: batch-statistics activations are not range-checked.
 bool tc_train_fwd_eligible(long long rows, int K, int N) {
     // one CTA per 128-row tile with ~14 k cycles of fixed prologue / epilogue: pays off from two K blocks up (K = 64 layers over
     // 500 k rows run faster on the fp32 FMA kernel: 268 vs 302 us measured at SA1's 64 -> 128 layer)
@@ -1117,32 +1208,25 @@ bool tc_train_fwd_eligible(long long rows, int K, int N) {
 int launch_tc_dense_train(long long rows, int K, int N, const float* x, const float* in_scale, const float* in_shift, int in_relu,
                           const float* W, const float* bias, float* y, float* stat_partial, uint8_t* image_ws, cudaStream_t st) {
     const int Kp = (K + 63) & ~63;
-    build_image(K, Kp, N, 128 | kImageBf16x3, W, image_ws, st);
+    int rc = build_image(K, Kp, N, 128 | kImageBf16x3, W, image_ws, st);
+    if (rc != PSA_OK) return rc;
     TcDenseArgs a;
     a.rows = rows; a.K = K; a.Kp = Kp; a.N = N; a.pool_k = 1; a.relu = 0;
     a.x = x; a.image = image_ws; a.scale = nullptr; a.shift = bias; a.out = y; a.xyz3 = nullptr; a.w3 = nullptr;
     a.in_scale = in_scale; a.in_shift = in_shift; a.in_relu = in_relu; a.stat_partial = stat_partial;
-    dim3 grid((unsigned)((rows + 127) / 128), N / 128);
-    const size_t smem3 = 4 * (size_t)TcDense3::kBlock + 1024;
-    PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    tc_dense3_kernel<<<grid, TcDense3::kThreads, smem3, st>>>(a);
-    return check_launch("tc_dense3_kernel");
+    return launch_tc_dense_np<3>(a, 128, st);
 }
 
-// A prebuilt image (psa_prepare_weight_image) is used when it matches; otherwise the image is (re)built into `ws`.
-// `Nt` may carry kImageBf16x3 (three-bf16-piece image for tc_sa_dual_kernel).
-static void build_image(int K, int Kp, int N, int Nt, const float* W, uint8_t* image, cudaStream_t st) {
-    tc_prep_weights3_kernel<<<(Kp * N + 255) / 256, 256, 0, st>>>(K, Kp, N, Nt & ~kImageBf16x3, W, image);
-}
-static const uint8_t* use_or_build_image(const psa_mlp* mlp, int l, int row0, int N, int Nt, uint8_t* ws, cudaStream_t st) {
+// A prebuilt image (psa_prepare_weight_image) is used when its format, tile width and first row match; otherwise null (the
+// launchers then build what they need in their workspace).  `Nt` carries the format flag.
+static const uint8_t* prebuilt_image(const psa_mlp* mlp, int l, int row0, int Nt) {
     if (mlp->image[l] != nullptr && mlp->image_nt[l] == Nt && mlp->image_row0[l] == row0) return reinterpret_cast<const uint8_t*>(mlp->image[l]);
-    const int K = mlp->channels[l] - row0, Kp = (K + 63) & ~63;
-    build_image(K, Kp, N, Nt, mlp->weight[l] + (size_t)row0 * N, ws, st);
-    return ws;
+    return nullptr;
 }
 
-// Can this MLP / geometry run on the tensor-core kernel?  (otherwise the fp32-FMA fused kernel in mlp.cu is used)
-bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
+// Can this MLP / geometry run on the tensor-core kernel with `np` pieces per operand?  (otherwise the fp32-FMA fused kernel
+// in mlp.cu is used).  Whatever fits with three pieces fits with two; the guarded default needs both.
+bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out, int np) {
     if (mlp->n_layers < 2 || mlp->n_layers > 1 + kMaxTcLayers) return false;
     if (!(nsample == 32 || nsample == 64 || nsample == 128)) return false;
     if (mlp->channels[0] != 3 + c) return false;
@@ -1151,7 +1235,7 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
     TcArgs a{};
     a.C1 = C1;
     a.nl = mlp->n_layers - 1;
-    size_t all = 0;
+    a.np = np;
     for (int l = 0; l < a.nl; ++l) {
         a.Kd[l] = mlp->channels[1 + l];
         a.Ntot[l] = mlp->channels[2 + l];
@@ -1159,49 +1243,51 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
         const bool is_last = (l == a.nl - 1);
         if (!is_last && !(a.Ntot[l] == 64 || a.Ntot[l] == 128)) return false;       // D and the next A operand are one tile wide
         if (is_last && !(a.Ntot[l] == 64 || a.Ntot[l] % 128 == 0)) return false;
-        all += tc_image_bytes(a.Kd[l], a.Ntot[l]);
     }
-    // two row groups per CTA, bf16x3 operands, 64-wide tiles; the last layer is streamed per group if it does not fit; a level
-    // that does not fit even then runs on the fp32-FMA fused kernel
+    // two row groups per CTA, 64-wide tiles; the last layer is streamed per group if it does not fit; a level that does not fit
+    // even then runs on the fp32-FMA fused kernel
     a.dual = 1; a.ntcap = 64; a.stream_last = 0;
     if (tc_dual_layout(a).total + 1024 > 226u * 1024u) a.stream_last = 1;
     if (tc_dual_layout(a).total + 1024 > 226u * 1024u) return false;
-    (void)all;
     *out = a;
     return true;
 }
+bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out) {
+    TcArgs a3;
+    if (!tc_sa_eligible(mlp, c, nsample, &a3, 3)) return false;
+    if (g_tc_np == 3) { *out = a3; return true; }
+    return tc_sa_eligible(mlp, c, nsample, out, 2);
+}
 
+// per tensor layer: an fp16x2 image (when the caller brought none) + the bf16x3 image of the guarded rerun / of mode 2
 size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
-    size_t bytes = 256;       // dynamic tile counter
-    for (int l = 0; l < a.nl; ++l) bytes += (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255;
+    size_t bytes = 256;       // tile counters + range flags
+    for (int l = 0; l < a.nl; ++l) bytes += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 2) + tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 3);
     if (c > 0) bytes += (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255) + tc_dense_image_bytes(c, a.C1);
     return bytes;
 }
 
-// tile width (with the image-format flag) of the tensor layers of a level
-static int tc_sa_image_nt(const TcArgs&, int) { return TcDual::kNt | kImageBf16x3; }
+// tile width (with the image-format flag of the current split) of the tensor layers of a level
+static int tc_sa_image_nt() { return TcDual::kNt | image_flag(g_tc_np); }
 
-int launch_tc_sa(TcArgs& a, cudaStream_t st) {
+template <int NP>
+static int launch_tc_sa_np(TcArgs& a, cudaStream_t st) {
     const int G = 128 / a.K;
     const long long ntiles = (a.groups + G - 1) / G;
-    if (a.dual) {
-        const size_t smem = (size_t)tc_dual_layout(a).total + 1024;
-        long long ctas = (ntiles + 1) / 2;
-        if (ctas > kNumSMs) ctas = kNumSMs;
-        if (ctas < 1) ctas = 1;
-        bool dbuf = a.C1 <= 64 && !a.stream_last && (a.Ntot[a.nl - 1] % 128) == 0;     // tile pairs: an even number of 64-wide tiles
-        for (int l = 0; l < a.nl; ++l) dbuf = dbuf && a.Kd[l] <= 64;
-        if (dbuf) {
-            PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_sa_dual_kernel<true><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
-        } else {
-            PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_sa_dual_kernel<false><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
-        }
-        return check_launch("tc_sa_dual_kernel");
+    const size_t smem = (size_t)tc_dual_layout(a).total + 1024;
+    long long ctas = (ntiles + 1) / 2;
+    if (ctas > kNumSMs) ctas = kNumSMs;
+    if (ctas < 1) ctas = 1;
+    bool dbuf = a.C1 <= 64 && !a.stream_last && (a.Ntot[a.nl - 1] % 128) == 0;     // tile pairs: an even number of 64-wide tiles
+    for (int l = 0; l < a.nl; ++l) dbuf = dbuf && a.Kd[l] <= 64;
+    if (dbuf) {
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<true, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_dual_kernel<true, NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+    } else {
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<false, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_dual_kernel<false, NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
     }
-    set_error("tc_sa: level not eligible for the dual-group kernel");
-    return PSA_ERR_UNSUPPORTED;
+    return check_launch("tc_sa_dual_kernel");
 }
 
 }  // namespace psa
@@ -1210,8 +1296,10 @@ using namespace psa;
 
 static int g_mlp_mode = 0;
 extern "C" PSA_API int psa_set_mlp_mode(int mode) {
-    PSA_REQUIRE(mode == 0 || mode == 1, "set_mlp_mode: mode must be 0 (tensor cores where the shapes allow) or 1 (fp32 FMA kernels only)");
+    PSA_REQUIRE(mode == 0 || mode == 1 || mode == 2,
+                "set_mlp_mode: mode must be 0 (tensor cores, fp16x2 operands with the range guard), 1 (fp32 FMA kernels only) or 2 (tensor cores, bf16x3)");
     g_mlp_mode = mode;
+    g_tc_np = mode == 2 ? 3 : 2;
     return PSA_OK;
 }
 extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode; }
@@ -1219,7 +1307,7 @@ extern "C" PSA_API int psa_get_mlp_mode(void) { return g_mlp_mode; }
 extern "C" size_t psa_sa_module_workspace_bytes(int b, int n, int m, int c, int nsample, const psa_mlp* mlp) {
     (void)m;
     TcArgs a;
-    if (g_mlp_mode == 0 && mlp != nullptr && tc_sa_eligible(mlp, c, nsample, &a)) return tc_sa_workspace_bytes(a, b, n, c);
+    if (g_mlp_mode != 1 && mlp != nullptr && tc_sa_eligible(mlp, c, nsample, &a)) return tc_sa_workspace_bytes(a, b, n, c);
     return 0;
 }
 
@@ -1242,44 +1330,72 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
     }
     cudaStream_t st = as_stream(stream);
     TcArgs a;
-    if (g_mlp_mode == 0 && tc_sa_eligible(mlp, c, nsample, &a)) {
+    if (g_mlp_mode != 1 && tc_sa_eligible(mlp, c, nsample, &a)) {
         const size_t need = tc_sa_workspace_bytes(a, b, n, c);
         PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need,
                     "sa_module: workspace of %zu bytes required (psa_sa_module_workspace_bytes), got %zu", need, workspace_bytes);
         PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sa_module: workspace must be 256-byte aligned");
-        a.groups = (long long)b * m; a.K = nsample; a.n = n; a.m = m;
-        a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.out = out; a.uf = nullptr;
-        a.w1x = mlp->weight[0]; a.s1 = mlp->scale[0]; a.t1 = mlp->shift[0]; a.relu1 = mlp->relu[0];
         uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-        a.tile_counter = reinterpret_cast<unsigned int*>(ws);
-        PSA_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+        unsigned int* words = reinterpret_cast<unsigned int*>(ws);     // [0] tile counter, [1] tile counter of the rerun, [2] range flag of
+        PSA_CUDA(cudaMemsetAsync(ws, 0, 256, st));                     // the level, [3] range flag of the U GEMM
         ws += 256;
+        uint8_t* img2[kMaxTcLayers];
+        uint8_t* img3[kMaxTcLayers];
         for (int l = 0; l < a.nl; ++l) {
-            a.s[l] = mlp->scale[1 + l]; a.t[l] = mlp->shift[1 + l]; a.relu[l] = mlp->relu[1 + l];
-            const int K = a.Kd[l], N = a.Ntot[l];
-            a.image[l] = use_or_build_image(mlp, 1 + l, 0, N, tc_sa_image_nt(a, N), ws, st);
-            ws += (tc_image_bytes(K, N) + 255) & ~(size_t)255;
+            img2[l] = ws; ws += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 2);
+            img3[l] = ws; ws += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 3);
         }
-        rc = check_launch("tc_prep_weights3_kernel");
-        if (rc != PSA_OK) return rc;
+        const float* uf = nullptr;
         if (c > 0) {
             // U = points . W1[3:,:]  once per source point (rows b*n), raw (affine + ReLU are applied after the xyz part)
-            float* uf = reinterpret_cast<float*>(ws);
+            float* ufw = reinterpret_cast<float*>(ws);
             uint8_t* uimg = ws + (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255);
             const float* w1f = mlp->weight[0] + (size_t)3 * a.C1;
             if (tc_dense_eligible((long long)b * n, c, a.C1, 1)) {
-                const uint8_t* im = use_or_build_image(mlp, 0, 3, a.C1, tc_dense_nt(a.C1), uimg, st);
-                rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, uf, im, st, nullptr, nullptr, true);
+                rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, ufw, prebuilt_image(mlp, 0, 3, tc_dense_nt(a.C1)), uimg,
+                                     words + 3, st);
             } else {
                 DenseArgs d;
                 d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
-                d.x = points; d.W = w1f; d.scale = nullptr; d.shift = nullptr; d.out = uf;
+                d.x = points; d.W = w1f; d.scale = nullptr; d.shift = nullptr; d.out = ufw;
                 rc = launch_dense(d, st);
             }
             if (rc != PSA_OK) return rc;
-            a.uf = uf;
+            uf = ufw;
         }
-        return launch_tc_sa(a, st);
+        auto fill = [&](TcArgs& t) {
+            t.groups = (long long)b * m; t.K = nsample; t.n = n; t.m = m;
+            t.xyz = xyz; t.new_xyz = new_xyz; t.idx = idx; t.out = out; t.uf = uf;
+            t.w1x = mlp->weight[0]; t.s1 = mlp->scale[0]; t.t1 = mlp->shift[0]; t.relu1 = mlp->relu[0];
+            t.ovf = nullptr; t.run_if = nullptr;
+            for (int l = 0; l < t.nl; ++l) { t.s[l] = mlp->scale[1 + l]; t.t[l] = mlp->shift[1 + l]; t.relu[l] = mlp->relu[1 + l]; t.wflag[l] = nullptr; }
+        };
+        fill(a);
+        const int nt_img = tc_sa_image_nt();
+        for (int l = 0; l < a.nl; ++l) {
+            const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, nt_img);
+            uint8_t* own = a.np == 2 ? img2[l] : img3[l];
+            if (pre == nullptr) { rc = build_image(a.Kd[l], a.Kd[l], a.Ntot[l], nt_img, mlp->weight[1 + l], own, st); if (rc != PSA_OK) return rc; }
+            a.image[l] = pre ? pre : own;
+            if (a.np == 2) a.wflag[l] = image_trailer(a.image[l], a.Kd[l], a.Ntot[l], 2);
+        }
+        a.tile_counter = words;
+        if (a.np == 3) return launch_tc_sa_np<3>(a, st);
+        a.ovf = words + 2;
+        rc = launch_tc_sa_np<2>(a, st);
+        if (rc != PSA_OK) return rc;
+        // guarded rerun with bf16x3 operands: image builds and the level itself are no-ops unless the fp16x2 pass raised the flag
+        TcArgs a3;
+        PSA_REQUIRE(tc_sa_eligible(mlp, c, nsample, &a3, 3), "sa_module: internal error (bf16x3 eligibility)");
+        fill(a3);
+        for (int l = 0; l < a3.nl; ++l) {
+            rc = build_image(a3.Kd[l], a3.Kd[l], a3.Ntot[l], TcDual::kNt | kImageBf16x3, mlp->weight[1 + l], img3[l], st, words + 2);
+            if (rc != PSA_OK) return rc;
+            a3.image[l] = img3[l];
+        }
+        a3.tile_counter = words + 1;
+        a3.run_if = words + 2;
+        return launch_tc_sa_np<3>(a3, st);
     }
     return sa_module_simt(b, n, m, c, nsample, xyz, new_xyz, points, idx, mlp, out, st);
 }
@@ -1296,7 +1412,7 @@ extern "C" size_t psa_shared_mlp_workspace_bytes(long long rows, const psa_mlp* 
         for (int l = 0; l < mlp->n_layers; ++l) { size_t f = fc_small_workspace_bytes(mlp->channels[l], mlp->channels[l + 1]); fc = f > fc ? f : fc; }
         bytes += (fc + 255) & ~(size_t)255;
     }
-    return bytes;
+    return bytes + 256;       // range flags of the tensor-core layers (one word per layer), last
 }
 
 extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const psa_mlp* mlp, float* out,
@@ -1326,13 +1442,15 @@ extern "C" int psa_shared_mlp(long long rows, int pool_k, const float* x, const 
     }
     const float* cur = x;
     cudaStream_t st = as_stream(stream);
+    unsigned int* flags = reinterpret_cast<unsigned int*>(wsb + need - 256);
+    PSA_CUDA(cudaMemsetAsync(flags, 0, 256, st));
     for (int l = 0; l < L; ++l) {
         const int K = mlp->channels[l], N = mlp->channels[l + 1];
         const int pk = (l == L - 1) ? pool_k : 1;
         float* dst = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
-        if (g_mlp_mode == 0 && tc_dense_eligible(rows, K, N, pk)) {
-            const uint8_t* im = use_or_build_image(mlp, l, 0, N, tc_dense_nt(N), img, st);
-            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, mlp->weight[l], mlp->scale[l], mlp->shift[l], dst, im, st, nullptr, nullptr, true);
+        if (g_mlp_mode != 1 && tc_dense_eligible(rows, K, N, pk)) {
+            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, mlp->weight[l], mlp->scale[l], mlp->shift[l], dst, prebuilt_image(mlp, l, 0, tc_dense_nt(N)),
+                                 img, flags + l, st);
         } else {
             DenseArgs d;
             d.rows = rows; d.K = K; d.N = N; d.pool_k = pk; d.relu = mlp->relu[l];
@@ -1368,7 +1486,7 @@ extern "C" int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, con
     const int L = mlp->n_layers;
     const int N0 = mlp->channels[1];
     const int pk0 = (L == 1) ? n : 1;
-    PSA_SUPPORTED(g_mlp_mode == 0 && tc_dense_eligible(rows, c, N0, pk0),
+    PSA_SUPPORTED(g_mlp_mode != 1 && tc_dense_eligible(rows, c, N0, pk0),
                   "sa_group_all: first layer (%d -> %d over %lld rows) is not eligible for the tensor-core path; concatenate and use shared_mlp", c, N0, rows);
     const size_t need = psa_sa_group_all_workspace_bytes(b, n, c, mlp);
     PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, "sa_group_all: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
@@ -1381,6 +1499,8 @@ extern "C" int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, con
     float* ws1 = reinterpret_cast<float*>(wsb + half);
     uint8_t* img = wsb + 2 * half;
     cudaStream_t st = as_stream(stream);
+    unsigned int* flags = reinterpret_cast<unsigned int*>(wsb + need - 256);
+    PSA_CUDA(cudaMemsetAsync(flags, 0, 256, st));
     const float* cur = points;
     for (int l = 0; l < L; ++l) {
         const int K = (l == 0) ? c : mlp->channels[l], N = mlp->channels[l + 1];
@@ -1388,9 +1508,8 @@ extern "C" int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, con
         float* dst = (l == L - 1) ? out : ((l & 1) ? ws1 : ws0);
         const float* W = (l == 0) ? mlp->weight[0] + (size_t)3 * N : mlp->weight[l];
         if (tc_dense_eligible(rows, K, N, pk)) {
-            const uint8_t* im = use_or_build_image(mlp, l, l == 0 ? 3 : 0, N, tc_dense_nt(N), img, st);
-            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, W, mlp->scale[l], mlp->shift[l], dst, im, st,
-                                 l == 0 ? xyz : nullptr, l == 0 ? mlp->weight[0] : nullptr, true);
+            rc = launch_tc_dense(rows, K, N, pk, mlp->relu[l], cur, W, mlp->scale[l], mlp->shift[l], dst, prebuilt_image(mlp, l, l == 0 ? 3 : 0, tc_dense_nt(N)),
+                                 img, flags + l, st, l == 0 ? xyz : nullptr, l == 0 ? mlp->weight[0] : nullptr);
         } else {
             PSA_SUPPORTED(l > 0, "sa_group_all: layer 0 must run on the tensor-core path");
             DenseArgs d;
@@ -1456,7 +1575,7 @@ edge_gather_max_kernel(long long points, int n, int k, int N, const float* __res
 
 static bool edgeconv_algebra_ok(long long rows, int c, int k, const psa_mlp* mlp) {
     const int N = mlp->channels[1];
-    return g_mlp_mode == 0 && mlp->n_layers == 1 && rows >= 128 && k <= 32 && (N == 32 || N == 64 || N == 128 || N == 256) && c >= 1;
+    return g_mlp_mode != 1 && mlp->n_layers == 1 && rows >= 128 && k <= 32 && (N == 32 || N == 64 || N == 128 || N == 256) && c >= 1;
 }
 
 extern "C" size_t psa_edgeconv_workspace_bytes(int b, int n, int c, int k, const psa_mlp* mlp) {
@@ -1464,7 +1583,7 @@ extern "C" size_t psa_edgeconv_workspace_bytes(int b, int n, int c, int k, const
     const long long rows = (long long)b * n;
     if (!edgeconv_algebra_ok(rows, c, k, mlp)) return 0;
     const int N = mlp->channels[1];
-    return (((size_t)c * 2 * N * 4 + 255) & ~(size_t)255) + (((size_t)rows * 2 * N * 4 + 255) & ~(size_t)255) + tc_dense_image_bytes(c, 2 * N);
+    return (((size_t)c * 2 * N * 4 + 255) & ~(size_t)255) + (((size_t)rows * 2 * N * 4 + 255) & ~(size_t)255) + tc_dense_image_bytes(c, 2 * N) + 256;
 }
 
 extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, const int* nn_idx, const psa_mlp* mlp,
@@ -1489,7 +1608,9 @@ extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, co
     ws += ((size_t)rows * 2 * N * 4 + 255) & ~(size_t)255;
     edge_wc_kernel<<<(c * 2 * N + 255) / 256, 256, 0, st>>>(c, N, mlp->weight[0], Wc);
     if (tc_dense_eligible(rows, c, 2 * N, 1)) {
-        rc = launch_tc_dense(rows, c, 2 * N, 1, 0, x, Wc, nullptr, nullptr, AB, ws, st);
+        unsigned int* flag = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + need - 256);
+        PSA_CUDA(cudaMemsetAsync(flag, 0, 256, st));
+        rc = launch_tc_dense(rows, c, 2 * N, 1, 0, x, Wc, nullptr, nullptr, AB, nullptr, ws, flag, st);
     } else {
         DenseArgs d;
         d.rows = rows; d.K = c; d.N = 2 * N; d.pool_k = 1; d.relu = 0;
@@ -1506,13 +1627,13 @@ extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, co
 }
 
 extern "C" int psa_prepare_weight_image(int K, int N, int row0, int nt, const float* W, void* image, psa_stream_t stream) {
-    const int ntw = nt & ~kImageBf16x3;       // nt as returned by psa_mlp_image_plan (may carry the bf16x3 format flag)
+    const int ntw = nt & ~kImageFlags;        // nt as returned by psa_mlp_image_plan: tile width | format flag
+    PSA_REQUIRE((nt & kImageFlags) == kImageBf16x3 || (nt & kImageFlags) == kImageF16x2, "prepare_weight_image: nt=%d carries no image format flag", nt);
     PSA_REQUIRE(K >= 1 && N >= 64 && N % 64 == 0 && row0 >= 0 && row0 < K && (ntw == 64 || ntw == 128) && N % ntw == 0,
                 "prepare_weight_image: bad arguments K=%d N=%d row0=%d nt=%d", K, N, row0, nt);
     PSA_REQUIRE(W && image, "prepare_weight_image: null buffer");
     const int Ki = K - row0, Kp = (Ki + 63) & ~63;
-    build_image(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image), as_stream(stream));
-    return check_launch("tc_prep_weights3_kernel");
+    return build_image(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image), as_stream(stream));
 }
 
 extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, int nsample, const psa_mlp* mlp,
@@ -1520,22 +1641,22 @@ extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, 
     int rc = validate_mlp_public(mlp, "mlp_image_plan");
     if (rc != PSA_OK) return rc;
     for (int l = 0; l < PSA_MAX_MLP_LAYERS; ++l) { nt[l] = 0; row0[l] = 0; bytes[l] = 0; }
-    if (g_mlp_mode != 0) return PSA_OK;
+    if (g_mlp_mode == 1) return PSA_OK;
     const int L = mlp->n_layers;
     if (usage == PSA_USAGE_SHARED_MLP || usage == PSA_USAGE_SA_GROUP_ALL) {
         for (int l = 0; l < L; ++l) {
             const int r0 = (usage == PSA_USAGE_SA_GROUP_ALL && l == 0) ? 3 : 0;
             const int K = mlp->channels[l] - r0, N = mlp->channels[l + 1];
             const int pk = (l == L - 1) ? pool_k : 1;
-            if (K >= 1 && tc_dense_eligible(rows, K, N, pk)) { nt[l] = tc_dense_nt(N); row0[l] = r0; bytes[l] = tc_dense_image_bytes(K, N); }
+            if (K >= 1 && tc_dense_eligible(rows, K, N, pk)) { nt[l] = tc_dense_nt(N); row0[l] = r0; bytes[l] = tc_image_alloc_bytes((K + 63) & ~63, N, g_tc_np); }
         }
         return PSA_OK;
     }
     PSA_REQUIRE(usage == PSA_USAGE_SA_MODULE, "mlp_image_plan: unknown usage %d", usage);
     TcArgs a;
     if (!tc_sa_eligible(mlp, c, nsample, &a)) return PSA_OK;
-    if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_dense_image_bytes(c, a.C1); }
-    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(a, a.Ntot[l]); row0[1 + l] = 0; bytes[1 + l] = (tc_image_bytes(a.Kd[l], a.Ntot[l]) + 255) & ~(size_t)255; }
+    if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_image_alloc_bytes((c + 63) & ~63, a.C1, g_tc_np); }
+    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(); row0[1 + l] = 0; bytes[1 + l] = tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], g_tc_np); }
     return PSA_OK;
 }
 

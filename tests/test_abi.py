@@ -53,7 +53,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert lib.psa_farthest_point_sample(-1, 8, 4, null, null, null, null) == -1
     assert lib.psa_query_ball_point(1, 8, 4, C.c_float(0.2), -3, null, null, null, null, null) == -1
     assert lib.psa_farthest_point_sample(0, 8, 4, null, null, null, null) == 0         # b = 0: no-op
-    assert lib.psa_set_mlp_mode(5) == -1 and lib.psa_set_mlp_mode(2) == -1
+    assert lib.psa_set_mlp_mode(5) == -1 and lib.psa_set_mlp_mode(-1) == -1
 
 
 def test_ops_refuse_cpu_tensors():

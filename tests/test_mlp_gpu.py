@@ -23,10 +23,11 @@ def _store(seed=0):
     return VariableStore(device="cuda", seed=seed)
 
 
-@pytest.fixture(params=["tensor", "fma"])
+@pytest.fixture(params=["tensor", "fma", "tensor_bf16x3"])
 def mlp_mode(request):
-    """0 = auto (tcgen05 operand-split kernels where the shapes allow), 1 = fp32 FMA kernels"""
-    ops.set_mlp_mode({"tensor": 0, "fma": 1}[request.param])
+    """0 = auto (tcgen05 kernels where the shapes allow: fp16x2 operands + range guard), 1 = fp32 FMA kernels,
+    2 = tcgen05 kernels with bf16x3 operands (also what the range guard reruns on)"""
+    ops.set_mlp_mode({"tensor": 0, "fma": 1, "tensor_bf16x3": 2}[request.param])
     yield request.param
     ops.set_mlp_mode(0)
 
@@ -38,7 +39,7 @@ def mlp_mode(request):
                                                # pool 32 / 64 / 256 (atomicMax path); K > 512 and N = 64 (TMEM-A kernel); 8 K-blocks x 3 n-tiles
                                                (1000, 1, [100, 128]), (1000, 1, [99, 256]), (1024, 32, [64, 128, 256]), (1024, 64, [128, 128]),
                                                (512, 256, [200, 128]), (384, 1, [576, 128]), (384, 1, [64, 64]), (130, 1, [512, 384])])
-def test_shared_mlp_matches_fp64(rows, pool_k, chans):
+def test_shared_mlp_matches_fp64(rows, pool_k, chans, mlp_mode):
     p = _store(rows)
     scopes = []
     for i in range(len(chans) - 1):
@@ -245,3 +246,41 @@ def test_sa_conv1_prebn_nonfinite_inputs_keep_reference_indices():
     ok = np.isfinite(want)
     assert ok[0].mean() > 0.9
     G.contract_close(G.npy(pre)[ok], want[ok], "pre-BN rows")
+
+
+@pytest.mark.parametrize("where", ["features", "weights", "inner"])
+def test_fp16_range_guard_reruns_on_bf16x3(where):
+    """mode 0 splits operands into two fp16 pieces (|value| < 65504).  Features, weights or an inner activation beyond that range
+    raise the device-side flag and the op is rerun with bf16x3 operands inside the same call: the result still meets the contract
+    (relative to its own magnitude); nothing is clamped, nothing becomes inf."""
+    p = _store(91)
+    mlp = [128, 128, 256]
+    add_sa_module_params(p, "sa", 3 + 64, mlp, randomize_bn=True)
+    rng = np.random.default_rng(5)
+    xyz = make_clouds("ball", 2, 512, seed=12)
+    pts = rng.standard_normal((2, 512, 64)).astype(np.float32)
+    if where == "features":
+        pts *= 3.0e5
+    elif where == "weights":
+        p["sa/conv1/weights"] = p["sa/conv1/weights"] * 1.0e6
+    else:
+        p["sa/conv0/bn/gamma"] = p["sa/conv0/bn/gamma"] * 2.0e5        # layer-1 activations ~1e5..1e6, inputs and weights ordinary
+    assert ops.get_mlp_mode() == 0
+    _, got, _ = pointnet_sa_module(G.cu(xyz), G.cu(pts), 128, 0.4, 64, mlp, None, False, False, None, "sa", params=p)
+    want = mo.sa_module(xyz, pts, 128, 0.4, 64, mlp, False, "sa", p)[1]
+    got = G.npy(got)
+    assert np.isfinite(got).all() and np.abs(want).max() > 7e4
+    G.contract_close(got, want, f"range guard ({where})")
+    # dense chain (SA3 / PointNet shape): same guard, per layer
+    q = _store(92)
+    q.add_conv2d("m/conv0", 256, 256, bn=True, randomize_bn=True)
+    q.add_conv2d("m/conv1", 256, 128, bn=True, randomize_bn=True)
+    x = (rng.standard_normal((512, 256)) * (4.0e5 if where == "features" else 1.0)).astype(np.float32)
+    if where == "weights":
+        q["m/conv1/weights"] = q["m/conv1/weights"] * 1.0e6
+    if where == "inner":
+        q["m/conv0/bn/gamma"] = q["m/conv0/bn/gamma"] * 2.0e5
+    d = G.npy(ops.shared_mlp(G.cu(x), q.mlp(["m/conv0", "m/conv1"], [True, False])))
+    dw = mo.mlp_chain(x, q, ["m/conv0", "m/conv1"], [True, False])
+    assert np.isfinite(d).all() and np.abs(dw).max() > 7e4
+    G.contract_close(d, dw, f"range guard dense ({where})")

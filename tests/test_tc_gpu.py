@@ -29,7 +29,7 @@ def test_tc_identity_weight_is_exact_passthrough():
     a = np.random.default_rng(0).standard_normal((128, 128)).astype(np.float32)
     mlp = ops.MlpParams([(torch.eye(128, device="cuda"), None, torch.zeros(128, device="cuda"), False)])
     d = G.npy(ops.shared_mlp(G.cu(a), mlp))
-    # w = 1 is one exact bf16 piece, a = a1 + a2 + a3 is an exact split: the product reproduces a to the accumulator's rounding
+    # w = 1 is one exact piece; a = a1 + a2 drops what lies below 2^-22 |a| (fp16x2): the product reproduces a to that rounding
     assert np.abs(d - a).max() <= np.abs(a).max() * 2.0 ** -22
 
 
@@ -37,6 +37,8 @@ def test_mlp_mode_switch():
     assert ops.get_mlp_mode() == 0
     ops.set_mlp_mode(1)
     assert ops.get_mlp_mode() == 1
+    ops.set_mlp_mode(2)              # tensor cores with bf16x3 operands (what the fp16 range guard reruns on)
+    assert ops.get_mlp_mode() == 2
     ops.set_mlp_mode(0)
     with pytest.raises(ValueError):
-        ops.set_mlp_mode(2)          # the round-1 legacy mode is gone
+        ops.set_mlp_mode(3)
