@@ -571,7 +571,7 @@ def main():
         flops = {"sa1_mlp": SA_FLOPS["sa1"], "sa2_mlp": SA_FLOPS["sa2"], "sa3_mlp": SA_FLOPS["sa3"]}.get(dom)
         if flops:
             ach = flops / (stages[dom] * 1e-6) / 1e12
-            # share of the level's flops that runs on the tensor cores (layers after the first); each fp32 product is six bf16 MMAs
+            # share of the level's flops that runs on the tensor cores (layers after the first); each fp32 product is three f16 MMAs
             tc_flops = {"sa1_mlp": 2 * 524288 * (64 * 64 + 64 * 128), "sa2_mlp": 2 * 262144 * (128 * 128 + 128 * 256) + 2 * 16384 * 128 * 128,
                         "sa3_mlp": 2 * 4096 * (256 * 256 + 256 * 512 + 512 * 1024)}[dom]
             traffic, tsrc = _traffic(dom)
@@ -580,9 +580,9 @@ def main():
                         "frac": ach / peaks["tf"], "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["src"] + " bf16 burst",
                         "algorithmic_flops": flops,
                         "note": "achieved = SURVEY 8d fp32 MLP flops of the level / measured stage time. fp32 parity (1e-5) is kept by splitting "
-                                "both operands into three bf16 pieces: six bf16 MMAs per product, so the tensor pipe executes 6x the "
-                                "tensor-core share of these flops (tensor_pipe_frac).",
-                        "tensor_pipe_frac": 6.0 * tc_flops / (stages[dom] * 1e-6) / 1e12 / peaks["tf"]}
+                                "both operands into two fp16 pieces: three f16 MMAs per product (fp32 accumulate), so the tensor pipe executes "
+                                "3x the tensor-core share of these flops (tensor_pipe_frac; the bf16x3 mode of round 1 executed 6x).",
+                        "tensor_pipe_frac": 3.0 * tc_flops / (stages[dom] * 1e-6) / 1e12 / peaks["tf"]}
         else:
             fps_bytes = B * (12 * N + 4 * 512)
             ach = fps_bytes / (stages[dom] * 1e-6) / 1e9
@@ -640,7 +640,9 @@ def main():
                                                              "note": "same engine with ONE slot: a step starts when the previous one has finished"},
         "e2e": {"value": e2e_v, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * N * 3 * 4,
                 "d2h_bytes_per_step": B * NUM_CLASS * 4},
-        "gpu_launches": 16 * args.steps,
+        # kernels of libpsa.so per step: 2 FPS (+ fused gather), 2 ball queries, SA1 level + its guarded rerun, SA2 per-point GEMM + level +
+        # their reruns, SA3 3 x (layer + rerun), head 3 x (K-split partial + reduce); reruns are no-ops unless a value left the fp16 range
+        "gpu_launches": 22 * args.steps,
         "roofline": roofline,
         "roofline_f1": roofline_f1,
         "kernels": kern,

@@ -194,7 +194,7 @@ typedef struct psa_mlp {
      * (~45 us per PointNet++ forward).  An image is only used if its tile width / first row match what the entry point
      * needs (psa_mlp_image_plan() tells); otherwise it is ignored and rebuilt. */
     const void* image[PSA_MAX_MLP_LAYERS];
-    int image_nt[PSA_MAX_MLP_LAYERS];      /* tile width the image was built for, as returned by psa_mlp_image_plan (64 or 128, | 0x100 = bf16x3 format) */
+    int image_nt[PSA_MAX_MLP_LAYERS];      /* tile width the image was built for, as returned by psa_mlp_image_plan (64 or 128, | 0x200 = fp16x2 blocks followed by their bf16x3 twin, | 0x100 = bf16x3 only) */
     int image_row0[PSA_MAX_MLP_LAYERS];    /* first row of weight[l] covered by the image (3 when the xyz rows are split off) */
 } psa_mlp;
 
@@ -206,7 +206,8 @@ typedef struct psa_mlp {
 #define PSA_USAGE_SA_MODULE 2
 PSA_API int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, int nsample, const psa_mlp* mlp,
                                int nt[PSA_MAX_MLP_LAYERS], int row0[PSA_MAX_MLP_LAYERS], size_t bytes[PSA_MAX_MLP_LAYERS]);
-/* Build the image of rows [row0, K) of W (K, N) for tile width nt into `image` (bytes from psa_mlp_image_plan). */
+/* Build the image of rows [row0, K) of W (K, N) for tile width | format `nt` into `image` (bytes from psa_mlp_image_plan).
+ * An fp16x2 image is followed, in the same buffer, by the bf16x3 image the range guard reruns on. */
 PSA_API int psa_prepare_weight_image(int K, int N, int row0, int nt, const float* W, void* image, psa_stream_t stream);
 
 /* Dense rows: x (rows, C_0) -> out.  pool_k == 1: out (rows, C_L).  pool_k > 1: rows must be a multiple

@@ -45,36 +45,67 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- prep: block = 128 rows.  Phase A: thread = row, the canonical |x|^2 (sequential fma chain).  Phase B: warp = row,
-// lane = two consecutive channels: coalesced 256-byte reads, three packed bf16x2 words per lane into the swizzled rows ----
-__global__ void __launch_bounds__(128) knn_prep_kernel(int n, int npad, int c, const float* __restrict__ x, uint8_t* __restrict__ image,
-                                                       float* __restrict__ sq) {
+// ---- centre: a translation vector per cloud (mean of every 8th point, fixed order).  Distances do not depend on it mathematically;
+// the tensor-core passes run on x - mu so that their error bounds scale with the cloud's EXTENT, not with its offset from the origin
+// (post-ReLU feature clouds sit far from it: |x|^2 ~ 100 x the neighbour distances, and bounds relative to |x|^2 would admit
+// hundreds of candidates per row).  Any vector works -- the canonical refine always uses the original coordinates. ----
+constexpr int kKtMeanLanes = 16;
+__global__ void __launch_bounds__(64 * kKtMeanLanes) knn_centre_kernel(int n, int c, const float* __restrict__ x, float* __restrict__ mu) {
+    __shared__ float s_part[kKtMeanLanes][64];
+    const int cloud = blockIdx.x, ch = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    float s = 0.f;
+    int cnt = 0;
+    if (ch < c)
+        for (int r = rl * 8; r < n; r += 8 * kKtMeanLanes) { s += __ldg(x + ((size_t)cloud * n + r) * c + ch); ++cnt; }
+    s_part[rl][ch] = s;
+    __shared__ int s_cnt[kKtMeanLanes];
+    if (ch == 0) s_cnt[rl] = cnt;
+    __syncthreads();
+    if (rl == 0) {
+        float t = 0.f;
+        int m = 0;
+        for (int i = 0; i < kKtMeanLanes; ++i) { t += s_part[i][ch]; m += s_cnt[i]; }
+        mu[cloud * 64 + ch] = ch < c ? t / (float)max(m, 1) : 0.f;
+    }
+}
+
+// ---- prep: block = 128 rows.  Phase A: thread = row, the canonical |x|^2 (sequential fma chain) and the centred |x - mu|^2.
+// Phase B: warp = row, lane = two consecutive channels: coalesced 256-byte reads, three packed bf16x2 words of x - mu per lane into
+// the swizzled rows ----
+__global__ void __launch_bounds__(128) knn_prep_kernel(int n, int npad, int c, const float* __restrict__ x, const float* __restrict__ mu,
+                                                       uint8_t* __restrict__ image, float* __restrict__ sq, float* __restrict__ sqc) {
     const int cloud = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t* blk = image + ((size_t)cloud * (npad / 128) + rb) * kKtBlock;
+    __shared__ float s_mu[64];
+    if (tid < 64) s_mu[tid] = mu[cloud * 64 + tid];
+    __syncthreads();
     {
         const int r = rb * 128 + tid;
-        float s = __int_as_float(0x7f800000);
+        float s = __int_as_float(0x7f800000), sc = __int_as_float(0x7f800000);
         if (r < n) {
             const float* xr = x + ((size_t)cloud * n + r) * c;
-            s = 0.f;
+            s = 0.f; sc = 0.f;
             if ((c & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
                 for (int l = 0; l < c; l += 4) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(xr + l));
                     s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+                    const float d0 = v.x - s_mu[l], d1 = v.y - s_mu[l + 1], d2 = v.z - s_mu[l + 2], d3 = v.w - s_mu[l + 3];
+                    sc = fmaf(d0, d0, sc); sc = fmaf(d1, d1, sc); sc = fmaf(d2, d2, sc); sc = fmaf(d3, d3, sc);
                 }
             } else {
-                for (int l = 0; l < c; ++l) { const float v = __ldg(xr + l); s = fmaf(v, v, s); }
+                for (int l = 0; l < c; ++l) { const float v = __ldg(xr + l); s = fmaf(v, v, s); const float d = v - s_mu[l]; sc = fmaf(d, d, sc); }
             }
         }
         sq[(size_t)cloud * npad + r] = s;
+        sqc[(size_t)cloud * npad + r] = sc;
     }
     for (int rr = warp * 32; rr < warp * 32 + 32; ++rr) {
         const int r = rb * 128 + rr, k = 2 * lane;
         float h0 = 0.f, h1 = 0.f;
         if (r < n) {
             const float* xr = x + ((size_t)cloud * n + r) * c;
-            if (k < c) h0 = __ldg(xr + k);
-            if (k + 1 < c) h1 = __ldg(xr + k + 1);
+            if (k < c) h0 = __ldg(xr + k) - s_mu[k];
+            if (k + 1 < c) h1 = __ldg(xr + k + 1) - s_mu[k + 1];
         }
         const uint32_t off = swz_off_bf16((uint32_t)rr, (uint32_t)k, 128u);
         const uint32_t p1 = pack_bf16x2(h0, h1);
@@ -92,7 +123,8 @@ struct KnnTcArgs {
     int n, npad, c, k;
     const float* x;
     const uint8_t* image;
-    const float* sq;
+    const float* sq;           // (b, npad) canonical |x|^2 (the refine and the exhaustive kernel)
+    const float* sqc;          // (b, npad) |x - mu|^2 (the tensor-core passes)
     int* nn_idx;
     int* flag_rows;            // (b * n) worklist of global row ids for the exhaustive kernel
     unsigned* flag_count;
@@ -116,7 +148,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_qfull, s_full[2], s_dfull[2], s_dfree[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_wmax[kKtThreads / 32];
+    __shared__ float s_wmax[kKtThreads / 32], s_wmaxo[kKtThreads / 32];
     __shared__ float s_T[128];
     __shared__ int s_cnt[128], s_namb[128];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -132,7 +164,8 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
     unsigned short* lidx = reinterpret_cast<unsigned short*>(scratch);
     float* ladj = reinterpret_cast<float*>(scratch + (size_t)kKtCap * 128 * 2);
     const uint8_t* img = a.image + (size_t)cloud * NT * kKtBlock;
-    const float* sqc = a.sq + (size_t)cloud * npad;
+    const float* sqc = a.sqc + (size_t)cloud * npad;      // centred norms: what the tensor-core distances are assembled from
+    const float* sqo = a.sq + (size_t)cloud * npad;       // original norms: the canonical formula and its rounding bound
 
     if (warp_u == 4 * kKtRowT) tmem_alloc(&s_tmem, 256);
     if (tid == 0) {
@@ -141,15 +174,18 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         fence_mbar_init();
     }
     // candidate norms -> shared memory; the cloud's largest finite-or-not norm over the real points
-    float mx = 0.f;
+    float mx = 0.f, mxo = 0.f;
     for (int i = tid; i < npad; i += kKtThreads) {
-        const float v = __ldg(sqc + i);
+        const float v = __ldg(sqc + i), vo = __ldg(sqo + i);
         s_sq[i] = v;
-        if (i < n) mx = fmaxf(mx, fabsf(v) <= FLT_MAX ? v : __int_as_float(0x7f800000));     // NaN -> +inf: the cloud is flagged
+        if (i < n) {
+            mx = fmaxf(mx, fabsf(v) <= FLT_MAX ? v : __int_as_float(0x7f800000));            // NaN -> +inf: the cloud is flagged
+            mxo = fmaxf(mxo, fabsf(vo) <= FLT_MAX ? vo : __int_as_float(0x7f800000));
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) s_wmax[warp_u] = mx;
+    for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mxo = fmaxf(mxo, __shfl_xor_sync(0xffffffffu, mxo, o)); }
+    if (lane == 0) { s_wmax[warp_u] = mx; s_wmaxo[warp_u] = mxo; }
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
@@ -221,12 +257,16 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         const int r = tid & 127, h = tid >> 7;
         const int q = blockIdx.x * 128 + r;
         const bool valid = q < n;
-        float sqmax = s_wmax[0];
+        float sqmax = s_wmax[0], sqmaxo = s_wmaxo[0];
 #pragma unroll
-        for (int w = 1; w < kKtThreads / 32; ++w) sqmax = fmaxf(sqmax, s_wmax[w]);
-        const float sqq = s_sq[valid ? q : 0];
-        const bool ok = valid && fabsf(sqq) <= FLT_MAX && fabsf(sqmax) <= FLT_MAX;
+        for (int w = 1; w < kKtThreads / 32; ++w) { sqmax = fmaxf(sqmax, s_wmax[w]); sqmaxo = fmaxf(sqmaxo, s_wmaxo[w]); }
+        const float sqq = s_sq[valid ? q : 0];                 // centred
+        const float sqqo = __ldg(sqo + (valid ? q : 0));       // original
+        const bool ok = valid && fabsf(sqq) <= FLT_MAX && fabsf(sqmax) <= FLT_MAX && fabsf(sqqo) <= FLT_MAX && fabsf(sqmaxo) <= FLT_MAX;
         const float sgeo = sqrtf(sqq * sqmax);
+        // |fine - canonical| <= E2: the bf16 products and fp32 sums of the centred Gram entry (relative to the centred norms) + what the
+        // canonical fp32 formula itself loses on the ORIGINAL coordinates (its 64-term dot chain and two adds; centring rounds too)
+        const float E2 = 1e-4f * sgeo + 8e-6f * sqrtf(sqqo * sqmaxo) + 2e-6f * (sqqo + sqmaxo);
         const float dmax = 2.0f * (sqq + sqmax);
         const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
         constexpr int CW = 128 / kKtRowT;
@@ -278,7 +318,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
             for (; b >= 0; --b) { const unsigned w = hcol[b * 64]; cum += (int)(r < 64 ? (w & 0xffffu) : (w >> 16)); if (cum >= a.k) break; }
             const float tau = b < 0 ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(keymax - b + 1) << 19);
             // |coarse - exact| <= E1 (one bf16 term: 2^-8 relative on every product), |fine - exact| <= E2 (bf16x3 + fp32 sums)
-            const float E1 = 0.01f * sgeo, E2 = 1e-4f * sgeo + 2e-6f * (sqq + sqmax);
+            const float E1 = 0.01f * sgeo;
             s_T[r] = tau + E1 + E2 + 1e-6f * tau;
         }
         // every row is done with its histogram before anybody's candidate list / distances overwrite the scratch area
@@ -328,7 +368,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         unsigned short* lrank = reinterpret_cast<unsigned short*>(cstage);   // [kKtCap][128] number of entries surely before
         unsigned char* lamb = cstage + (size_t)kKtCap * 128 * 2;             // [kKtCap][128] compact list of the row's ambiguous entries
         const float* xc = a.x + (size_t)cloud * n * a.c;
-        const float delta = 2.0f * (1e-4f * sgeo + 2e-6f * (sqq + sqmax));   // 2 E2, E2 as in the threshold above
+        const float delta = 2.0f * E2;
         int* out = a.nn_idx + ((size_t)cloud * n + q) * a.k;
         // phase 1: fine-distance counts of every entry (entries split between the row's threads); unambiguous ones are final
         if (refine) {
@@ -375,9 +415,9 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
                             dot = fmaf(qv[l].z, cv[l].z, dot); dot = fmaf(qv[l].w, cv[l].w, dot);
                         }
                     }
-                    can = __fadd_rn(__fadd_rn(sqq, __fmul_rn(-2.0f, dot)), s_sq[col]);
+                    can = __fadd_rn(__fadd_rn(sqqo, __fmul_rn(-2.0f, dot)), __ldg(sqo + col));
                 } else {
-                    can = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqq, s_sq[col]);
+                    can = knn_canonical(xq, xc + (size_t)col * a.c, a.c, sqqo, __ldg(sqo + col));
                 }
                 lcan[e * 128 + r] = can;
 #ifdef PSA_KNN_ERRSTAT
@@ -485,7 +525,8 @@ using namespace psa;
 extern "C" size_t psa_knn_graph_workspace_bytes(int b, int n, int c, int k) {
     if (!knn_tc_eligible(n, c, k)) return 0;
     const int npad = (n + 127) / 128 * 128;
-    return (size_t)b * (npad / 128) * kKtBlock + (((size_t)b * npad * 4 + 255) & ~(size_t)255) + (((size_t)b * n * 4 + 255) & ~(size_t)255) + 256;
+    return (size_t)b * (npad / 128) * kKtBlock + 2 * (((size_t)b * npad * 4 + 255) & ~(size_t)255) + (((size_t)b * n * 4 + 255) & ~(size_t)255) + 256 +
+           (((size_t)b * 64 * 4 + 255) & ~(size_t)255);
 }
 
 // fp32 kernel of graph.cu (no workspace)
@@ -508,12 +549,17 @@ extern "C" int psa_knn_graph_ws(int b, int n, int c, int k, const float* x, int*
     int* flag_rows = reinterpret_cast<int*>(ws);
     ws += ((size_t)b * n * 4 + 255) & ~(size_t)255;
     unsigned* flag_count = reinterpret_cast<unsigned*>(ws);
+    ws += 256;
+    float* sqc = reinterpret_cast<float*>(ws);
+    ws += ((size_t)b * npad * 4 + 255) & ~(size_t)255;
+    float* mu = reinterpret_cast<float*>(ws);
     PSA_CUDA(cudaMemsetAsync(flag_count, 0, 4 * sizeof(unsigned), st));       // [0] worklist length (+ [1..2] PSA_KNN_ERRSTAT diagnostics)
-    knn_prep_kernel<<<dim3(NT, b), 128, 0, st>>>(n, npad, c, x, image, sq);
+    knn_centre_kernel<<<b, 64 * kKtMeanLanes, 0, st>>>(n, c, x, mu);
+    knn_prep_kernel<<<dim3(NT, b), 128, 0, st>>>(n, npad, c, x, mu, image, sq, sqc);
     int rc = check_launch("knn_prep_kernel");
     if (rc != PSA_OK) return rc;
     KnnTcArgs a;
-    a.n = n; a.npad = npad; a.c = c; a.k = k; a.x = x; a.image = image; a.sq = sq; a.nn_idx = nn_idx; a.flag_rows = flag_rows; a.flag_count = flag_count;
+    a.n = n; a.npad = npad; a.c = c; a.k = k; a.x = x; a.image = image; a.sq = sq; a.sqc = sqc; a.nn_idx = nn_idx; a.flag_rows = flag_rows; a.flag_count = flag_count;
     const size_t smem = knn_tc_smem_bytes(npad);
     PSA_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_tc_kernel<<<dim3(NT, b), kKtThreads, smem, st>>>(a);

@@ -60,6 +60,7 @@ struct TcArgs {
     const int* idx;        // (groups, K)
     float* out;            // (groups, Ntot[last])
     // layer 1 (FMA path)
+    const float* w1c;      // optional (3, C1): weights applied to the CENTRE coordinates new_xyz (EdgeConv's x_i part), or null
     const float* w1x;      // (3, C1): rows 0..2 of W1
     const float* s1;       // scale or null
     const float* t1;       // shift
@@ -212,14 +213,28 @@ __device__ __forceinline__ void issue_tile_c(uint32_t tmem_base, uint32_t d_col,
                 mma_bf16_ts(d, a1 + Split<NP>::a(t) * PS + kc * 32 + s4 * 8, smem_desc_at(b0, kc * bb + Split<NP>::w(t) * piece + s4 * 32), idesc,
                             (t | kc | s4) ? 1u : 0u);
 }
-// dbuf (levels whose layers are all <= 64 wide): A pieces 32 columns apart at 128.., two D slots at 0 and 64
-template <int NP>
-__device__ __forceinline__ void issue_tile(uint32_t gbase, uint32_t blocks_addr, int KC, bool dbuf, int dslot) {
-    if (dbuf) {
+// TMEM columns of a row group (256), by D-buffering mode DB:
+//   0  one D slot:            D 0..63 | A pieces 64 columns apart from 64
+//   1  levels whose layers are all <= 64 wide: D slots 0 and 64 | A pieces 32 columns apart from 128
+//   2  two-piece operands (NP = 2) of 128-wide layers leave 192..255 free: D slots 0 and 192 | A pieces at 64 and 128
+template <int DB> __device__ __forceinline__ constexpr uint32_t dual_dcol(int dslot) { return dslot == 0 ? 0u : (DB == 2 ? 192u : 64u); }
+template <int NP, int DB>
+__device__ __forceinline__ void issue_tile(uint32_t gbase, uint32_t blocks_addr, int KC, int dslot) {
+    if constexpr (DB == 1) {
         if (dslot == 0) issue_tile_c<1, TcDual::kNt, 32, NP>(gbase, 0, 128, blocks_addr);
         else issue_tile_c<1, TcDual::kNt, 32, NP>(gbase, 64, 128, blocks_addr);
-    } else if (KC == 1) issue_tile_c<1, TcDual::kNt, 64, NP>(gbase, TcDual::D, TcDual::A1, blocks_addr);
-    else issue_tile_c<2, TcDual::kNt, 64, NP>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+    } else if constexpr (DB == 2) {
+        if (KC == 1) {
+            if (dslot == 0) issue_tile_c<1, TcDual::kNt, 64, NP>(gbase, 0, TcDual::A1, blocks_addr);
+            else issue_tile_c<1, TcDual::kNt, 64, NP>(gbase, 192, TcDual::A1, blocks_addr);
+        } else {
+            if (dslot == 0) issue_tile_c<2, TcDual::kNt, 64, NP>(gbase, 0, TcDual::A1, blocks_addr);
+            else issue_tile_c<2, TcDual::kNt, 64, NP>(gbase, 192, TcDual::A1, blocks_addr);
+        }
+    } else {
+        if (KC == 1) issue_tile_c<1, TcDual::kNt, 64, NP>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+        else issue_tile_c<2, TcDual::kNt, 64, NP>(gbase, TcDual::D, TcDual::A1, blocks_addr);
+    }
 }
 
 struct TcDualLayout {
@@ -240,7 +255,7 @@ __host__ __device__ inline TcDualLayout tc_dual_layout(const TcArgs& a) {
     L.ring[0] = off; off += L.ring_bytes;
     L.ring[1] = off; off += L.ring_bytes;
     L.vec = off;
-    off += 5u * a.C1 * 4u;
+    off += 8u * a.C1 * 4u;       // w1x (3 C1), s1, t1, w1c (3 C1)
     for (int l = 0; l < a.nl; ++l) off += 2u * a.Ntot[l] * 4u;
     L.total = off;
     return L;
@@ -296,9 +311,10 @@ __device__ __forceinline__ void pipe_release(int* token, int lane) {
         : "memory");
 }
 
-template <bool DBUF, int NP>
+template <int DB, int NP>
 __global__ void __launch_bounds__(TcDual::kThreads, 1)
 tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
+    constexpr bool DBUF = DB != 0;
     if (a.run_if != nullptr && *a.run_if == 0u) return;      // np = 3 rerun of a launch that stayed inside the fp16 range: nothing to do
     constexpr int kNt = TcDual::kNt;
     uint32_t ovf = 0u;                                        // np = 2: packed |max| of every leading piece this thread stores
@@ -336,10 +352,11 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     float* sl[kMaxTcLayers];
     float* tl[kMaxTcLayers];
     {
-        float* p = t1 + a.C1;
+        float* p = t1 + 4 * a.C1;
         for (int l = 0; l < a.nl; ++l) { sl[l] = p; tl[l] = p + a.Ntot[l]; p += 2 * a.Ntot[l]; }
     }
-    for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) w1x[i] = __ldg(a.w1x + i);
+    float* w1c = t1 + a.C1;
+    for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) { w1x[i] = __ldg(a.w1x + i); w1c[i] = a.w1c ? __ldg(a.w1c + i) : 0.f; }
     for (int i = tid; i < a.C1; i += TcDual::kThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
     if (tid == 0) { s_nonneg = 1; s_token = 0; }
     __syncthreads();
@@ -376,8 +393,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     const uint32_t tmem_base = warp_uniform(s_tmem) + (uint32_t)g * TcDual::kGroupCols;
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0, phase2 = 0;
-    constexpr bool dbuf = DBUF;
-    constexpr uint32_t a1_col = DBUF ? 128u : TcDual::A1, a_ps = DBUF ? 32u : 64u;
+    constexpr uint32_t a1_col = DB == 1 ? 128u : TcDual::A1, a_ps = DB == 1 ? 32u : 64u;
     const bool pool_first = s_nonneg != 0;    // relu(s*d + t) is non-decreasing in d when s >= 0: max over rows commutes with it
     bool have_geo = false;                    // s_geo[g] holds this tile's geometry (written during the previous tile)
 
@@ -404,7 +420,12 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
         // ---- layer 1 on the FMA pipe, straight into the A operand ----
         {
             float dx = 0.f, dy = 0.f, dz = 0.f;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
             const float* urow = nullptr;
+            if (a.w1c != nullptr && valid) {
+                const float* c = a.new_xyz + (size_t)gid * 3;
+                cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+            }
             if (have_geo) {
                 const float4 gq = s_geo[g][row];
                 dx = gq.x; dy = gq.y; dz = gq.z;
@@ -428,6 +449,19 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 } else {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) h[q] = 0.f;
+                }
+                if (a.w1c != nullptr) {       // EdgeConv: the part of the first layer that acts on the centre x_i
+                    const float4* cx4 = reinterpret_cast<const float4*>(w1c + ch * 32);
+                    const float4* cy4 = reinterpret_cast<const float4*>(w1c + a.C1 + ch * 32);
+                    const float4* cz4 = reinterpret_cast<const float4*>(w1c + 2 * a.C1 + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 wx = cx4[q], wy = cy4[q], wz = cz4[q];
+                        h[4 * q + 0] = fmaf(cz, wz.x, fmaf(cy, wy.x, fmaf(cx, wx.x, h[4 * q + 0])));
+                        h[4 * q + 1] = fmaf(cz, wz.y, fmaf(cy, wy.y, fmaf(cx, wx.y, h[4 * q + 1])));
+                        h[4 * q + 2] = fmaf(cz, wz.z, fmaf(cy, wy.z, fmaf(cx, wx.z, h[4 * q + 2])));
+                        h[4 * q + 3] = fmaf(cz, wz.w, fmaf(cy, wy.w, fmaf(cx, wx.w, h[4 * q + 3])));
+                    }
                 }
                 const float4* wx4 = reinterpret_cast<const float4*>(w1x + ch * 32);
                 const float4* wy4 = reinterpret_cast<const float4*>(w1x + a.C1 + ch * 32);
@@ -462,7 +496,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     if (issuer) {
                         pipe_acquire(&s_token, lane);
                         fence_after_thread_sync();
-                        issue_tile<NP>(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt, NP), KC, dbuf, 0);
+                        issue_tile<NP, DB>(tmem_base, smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt, NP), KC, 0);
                         mma_commit(&s_mbar[g]);
                         pipe_release(&s_token, lane);
                     }
@@ -491,7 +525,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 // pooled epilogue of output tile `nt` out of D slot `dslot`
                 auto pooled_epilogue = [&](int nt, int dslot) {
                     uint32_t d[32];
-                    tmem_ld32(row_taddr + TcDual::D + dslot * 64 + cs * 32, d);
+                    tmem_ld32(row_taddr + (dslot == 0 ? dual_dcol<DB>(0) : dual_dcol<DB>(1)) + cs * 32, d);
                     tmem_ld_wait();
                     float v[32];
                     if (pool_first) {
@@ -521,10 +555,10 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                         pipe_acquire(&s_token, lane);   // (ends in __syncwarp: the issue below must be warp-uniform)
                         fence_after_thread_sync();
                         const uint32_t blocks = streamed ? smem_u32(base + L.ring[g]) : smem_u32(base + L.w[l]) + (uint32_t)nt * KC * tc_block_bytes(kNt, NP);
-                        issue_tile<NP>(tmem_base, blocks, KC, dbuf, 0);
+                        issue_tile<NP, DB>(tmem_base, blocks, KC, 0);
                         mma_commit(&s_mbar[g]);
                         if (DBUF) {                 // the pair's second tile goes to the other D slot right away (NT is even)
-                            issue_tile<NP>(tmem_base, blocks + (uint32_t)KC * tc_block_bytes(kNt, NP), KC, true, 1);
+                            issue_tile<NP, DB>(tmem_base, blocks + (uint32_t)KC * tc_block_bytes(kNt, NP), KC, 1);
                             mma_commit(&s_mbar2[g]);
                         }
                         pipe_release(&s_token, lane);
@@ -1120,6 +1154,9 @@ int tc_np() { return g_tc_np; }
 static size_t tc_dense_image_off3(int K, int N) { return tc_image_alloc_bytes((K + 63) & ~63, N, 2); }
 size_t tc_dense_image_bytes(int K, int N) { return tc_dense_image_off3(K, N) + tc_image_alloc_bytes((K + 63) & ~63, N, 3); }
 
+// bytes of a prebuilt image of the current split: mode 0 = fp16x2 blocks + their bf16x3 twin, mode 2 = bf16x3 blocks
+static size_t tc_plan_image_bytes(int Kp, int N) { return g_tc_np == 2 ? tc_image_alloc_bytes(Kp, N, 2) + tc_image_alloc_bytes(Kp, N, 3) : tc_image_alloc_bytes(Kp, N, 3); }
+
 // tile width of a dense layer's weight image, with the format flag of the current split
 int tc_dense_nt(int N) { return ((N % 128) == 0 ? 128 : 64) | image_flag(g_tc_np); }
 
@@ -1190,9 +1227,14 @@ int launch_tc_dense(long long rows, int K, int N, int pool_k, int relu, const fl
     a.ovf = flag; a.wflag = image_trailer(a.image, Kp, N, 2);
     rc = launch_tc_dense_np<2>(a, Nt, st);
     if (rc != PSA_OK) return rc;
-    // guarded rerun: both launches are no-ops unless the fp16x2 pass raised the flag
-    rc = build_image(K, Kp, N, Nt | kImageBf16x3, W, img3, st, flag);
-    if (rc != PSA_OK) return rc;
+    // guarded rerun, a no-op unless the fp16x2 pass raised the flag.  A prebuilt image carries its bf16x3 twin behind the fp16x2
+    // blocks (psa_prepare_weight_image); otherwise the twin is built here, conditionally too.
+    if (prebuilt != nullptr) {
+        img3 = const_cast<uint8_t*>(prebuilt) + tc_image_alloc_bytes(Kp, N, 2);
+    } else {
+        rc = build_image(K, Kp, N, Nt | kImageBf16x3, W, img3, st, flag);
+        if (rc != PSA_OK) return rc;
+    }
     a.image = img3; a.ovf = nullptr; a.wflag = nullptr; a.run_if = flag;
     return launch_tc_dense_np<3>(a, Nt, st);
 }
@@ -1278,16 +1320,93 @@ static int launch_tc_sa_np(TcArgs& a, cudaStream_t st) {
     long long ctas = (ntiles + 1) / 2;
     if (ctas > kNumSMs) ctas = kNumSMs;
     if (ctas < 1) ctas = 1;
-    bool dbuf = a.C1 <= 64 && !a.stream_last && (a.Ntot[a.nl - 1] % 128) == 0;     // tile pairs: an even number of 64-wide tiles
-    for (int l = 0; l < a.nl; ++l) dbuf = dbuf && a.Kd[l] <= 64;
-    if (dbuf) {
-        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<true, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_sa_dual_kernel<true, NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+    const bool pairs = !a.stream_last && (a.Ntot[a.nl - 1] % 128) == 0;            // tile pairs: an even number of resident 64-wide tiles
+    bool narrow = a.C1 <= 64;
+    for (int l = 0; l < a.nl; ++l) narrow = narrow && a.Kd[l] <= 64;
+    if (pairs && narrow) {
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<1, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_dual_kernel<1, NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+    } else if (pairs && NP == 2) {
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<(NP == 2 ? 2 : 0), NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_dual_kernel<(NP == 2 ? 2 : 0), NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
     } else {
-        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<false, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_sa_dual_kernel<false, NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+        PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<0, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_sa_dual_kernel<0, NP><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
     }
     return check_launch("tc_sa_dual_kernel");
+}
+
+// One set-abstraction level on the dual-group kernel (`a` = eligibility result for the current split): weight images, the U GEMM
+// of the feature part of layer 1, the level, and -- fp16x2 -- its guarded bf16x3 rerun.  w1c: optional centre weights (EdgeConv).
+static int tc_sa_run(TcArgs& a, int b, int n, int m, int c, int nsample, const float* xyz, const float* new_xyz, const float* points,
+                     const int* idx, const psa_mlp* mlp, const float* w1c, float* out, void* workspace, cudaStream_t st) {
+    int rc = PSA_OK;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    unsigned int* words = reinterpret_cast<unsigned int*>(ws);     // [0] tile counter, [1] tile counter of the rerun, [2] range flag of
+    PSA_CUDA(cudaMemsetAsync(ws, 0, 256, st));                     // the level, [3] range flag of the U GEMM
+    ws += 256;
+    uint8_t* img2[kMaxTcLayers];
+    uint8_t* img3[kMaxTcLayers];
+    for (int l = 0; l < a.nl; ++l) {
+        img2[l] = ws; ws += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 2);
+        img3[l] = ws; ws += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 3);
+    }
+    const float* uf = nullptr;
+    if (c > 0) {
+        // U = points . W1[3:,:]  once per source point (rows b*n), raw (affine + ReLU are applied after the xyz part)
+        float* ufw = reinterpret_cast<float*>(ws);
+        uint8_t* uimg = ws + (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255);
+        const float* w1f = mlp->weight[0] + (size_t)3 * a.C1;
+        if (tc_dense_eligible((long long)b * n, c, a.C1, 1)) {
+            rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, ufw, prebuilt_image(mlp, 0, 3, tc_dense_nt(a.C1)), uimg,
+                                 words + 3, st);
+        } else {
+            DenseArgs d;
+            d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
+            d.x = points; d.W = w1f; d.scale = nullptr; d.shift = nullptr; d.out = ufw;
+            rc = launch_dense(d, st);
+        }
+        if (rc != PSA_OK) return rc;
+        uf = ufw;
+    }
+    auto fill = [&](TcArgs& t) {
+        t.groups = (long long)b * m; t.K = nsample; t.n = n; t.m = m;
+        t.xyz = xyz; t.new_xyz = new_xyz; t.idx = idx; t.out = out; t.uf = uf;
+        t.w1x = mlp->weight[0]; t.s1 = mlp->scale[0]; t.t1 = mlp->shift[0]; t.relu1 = mlp->relu[0];
+        t.ovf = nullptr; t.run_if = nullptr; t.w1c = w1c;
+        for (int l = 0; l < t.nl; ++l) { t.s[l] = mlp->scale[1 + l]; t.t[l] = mlp->shift[1 + l]; t.relu[l] = mlp->relu[1 + l]; t.wflag[l] = nullptr; }
+    };
+    fill(a);
+    const int nt_img = tc_sa_image_nt();
+    for (int l = 0; l < a.nl; ++l) {
+        const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, nt_img);
+        uint8_t* own = a.np == 2 ? img2[l] : img3[l];
+        if (pre == nullptr) { rc = build_image(a.Kd[l], a.Kd[l], a.Ntot[l], nt_img, mlp->weight[1 + l], own, st); if (rc != PSA_OK) return rc; }
+        a.image[l] = pre ? pre : own;
+        if (a.np == 2) a.wflag[l] = image_trailer(a.image[l], a.Kd[l], a.Ntot[l], 2);
+    }
+    a.tile_counter = words;
+    if (a.np == 3) return launch_tc_sa_np<3>(a, st);
+    a.ovf = words + 2;
+    rc = launch_tc_sa_np<2>(a, st);
+    if (rc != PSA_OK) return rc;
+    // guarded rerun with bf16x3 operands: image builds and the level itself are no-ops unless the fp16x2 pass raised the flag
+    TcArgs a3;
+    PSA_REQUIRE(tc_sa_eligible(mlp, c, nsample, &a3, 3), "sa_module: internal error (bf16x3 eligibility)");
+    fill(a3);
+    for (int l = 0; l < a3.nl; ++l) {
+        const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, nt_img);       // carries its bf16x3 twin behind the fp16x2 blocks
+        if (pre != nullptr) {
+            a3.image[l] = pre + tc_image_alloc_bytes(a3.Kd[l], a3.Ntot[l], 2);
+        } else {
+            rc = build_image(a3.Kd[l], a3.Kd[l], a3.Ntot[l], TcDual::kNt | kImageBf16x3, mlp->weight[1 + l], img3[l], st, words + 2);
+            if (rc != PSA_OK) return rc;
+            a3.image[l] = img3[l];
+        }
+    }
+    a3.tile_counter = words + 1;
+    a3.run_if = words + 2;
+    return launch_tc_sa_np<3>(a3, st);
 }
 
 }  // namespace psa
@@ -1335,67 +1454,7 @@ extern "C" int psa_sa_module_infer(int b, int n, int m, int c, float radius, int
         PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need,
                     "sa_module: workspace of %zu bytes required (psa_sa_module_workspace_bytes), got %zu", need, workspace_bytes);
         PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sa_module: workspace must be 256-byte aligned");
-        uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-        unsigned int* words = reinterpret_cast<unsigned int*>(ws);     // [0] tile counter, [1] tile counter of the rerun, [2] range flag of
-        PSA_CUDA(cudaMemsetAsync(ws, 0, 256, st));                     // the level, [3] range flag of the U GEMM
-        ws += 256;
-        uint8_t* img2[kMaxTcLayers];
-        uint8_t* img3[kMaxTcLayers];
-        for (int l = 0; l < a.nl; ++l) {
-            img2[l] = ws; ws += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 2);
-            img3[l] = ws; ws += tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], 3);
-        }
-        const float* uf = nullptr;
-        if (c > 0) {
-            // U = points . W1[3:,:]  once per source point (rows b*n), raw (affine + ReLU are applied after the xyz part)
-            float* ufw = reinterpret_cast<float*>(ws);
-            uint8_t* uimg = ws + (((size_t)b * n * a.C1 * sizeof(float) + 255) & ~(size_t)255);
-            const float* w1f = mlp->weight[0] + (size_t)3 * a.C1;
-            if (tc_dense_eligible((long long)b * n, c, a.C1, 1)) {
-                rc = launch_tc_dense((long long)b * n, c, a.C1, 1, 0, points, w1f, nullptr, nullptr, ufw, prebuilt_image(mlp, 0, 3, tc_dense_nt(a.C1)), uimg,
-                                     words + 3, st);
-            } else {
-                DenseArgs d;
-                d.rows = (long long)b * n; d.K = c; d.N = a.C1; d.pool_k = 1; d.relu = 0;
-                d.x = points; d.W = w1f; d.scale = nullptr; d.shift = nullptr; d.out = ufw;
-                rc = launch_dense(d, st);
-            }
-            if (rc != PSA_OK) return rc;
-            uf = ufw;
-        }
-        auto fill = [&](TcArgs& t) {
-            t.groups = (long long)b * m; t.K = nsample; t.n = n; t.m = m;
-            t.xyz = xyz; t.new_xyz = new_xyz; t.idx = idx; t.out = out; t.uf = uf;
-            t.w1x = mlp->weight[0]; t.s1 = mlp->scale[0]; t.t1 = mlp->shift[0]; t.relu1 = mlp->relu[0];
-            t.ovf = nullptr; t.run_if = nullptr;
-            for (int l = 0; l < t.nl; ++l) { t.s[l] = mlp->scale[1 + l]; t.t[l] = mlp->shift[1 + l]; t.relu[l] = mlp->relu[1 + l]; t.wflag[l] = nullptr; }
-        };
-        fill(a);
-        const int nt_img = tc_sa_image_nt();
-        for (int l = 0; l < a.nl; ++l) {
-            const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, nt_img);
-            uint8_t* own = a.np == 2 ? img2[l] : img3[l];
-            if (pre == nullptr) { rc = build_image(a.Kd[l], a.Kd[l], a.Ntot[l], nt_img, mlp->weight[1 + l], own, st); if (rc != PSA_OK) return rc; }
-            a.image[l] = pre ? pre : own;
-            if (a.np == 2) a.wflag[l] = image_trailer(a.image[l], a.Kd[l], a.Ntot[l], 2);
-        }
-        a.tile_counter = words;
-        if (a.np == 3) return launch_tc_sa_np<3>(a, st);
-        a.ovf = words + 2;
-        rc = launch_tc_sa_np<2>(a, st);
-        if (rc != PSA_OK) return rc;
-        // guarded rerun with bf16x3 operands: image builds and the level itself are no-ops unless the fp16x2 pass raised the flag
-        TcArgs a3;
-        PSA_REQUIRE(tc_sa_eligible(mlp, c, nsample, &a3, 3), "sa_module: internal error (bf16x3 eligibility)");
-        fill(a3);
-        for (int l = 0; l < a3.nl; ++l) {
-            rc = build_image(a3.Kd[l], a3.Kd[l], a3.Ntot[l], TcDual::kNt | kImageBf16x3, mlp->weight[1 + l], img3[l], st, words + 2);
-            if (rc != PSA_OK) return rc;
-            a3.image[l] = img3[l];
-        }
-        a3.tile_counter = words + 1;
-        a3.run_if = words + 2;
-        return launch_tc_sa_np<3>(a3, st);
+        return tc_sa_run(a, b, n, m, c, nsample, xyz, new_xyz, points, idx, mlp, nullptr, out, workspace, st);
     }
     return sa_module_simt(b, n, m, c, nsample, xyz, new_xyz, points, idx, mlp, out, st);
 }
@@ -1578,9 +1637,34 @@ static bool edgeconv_algebra_ok(long long rows, int c, int k, const psa_mlp* mlp
     return g_mlp_mode != 1 && mlp->n_layers == 1 && rows >= 128 && k <= 32 && (N == 32 || N == 64 || N == 128 || N == 256) && c >= 1;
 }
 
+// Multi-layer EdgeConv over 3-D points (DGCNN's input transform net, dgcnn/models/transform_nets.py:13-27: [x_i, x_j - x_i] ->
+// 64 -> 128 -> max over k) on the set-abstraction kernel: W1 . [x_i ; x_j - x_i] = W1[0:3] . x_i + W1[3:6] . (x_j - x_i) is exactly
+// a level whose centres are the points themselves, with W1[3:6] as the xyz weights and W1[0:3] as centre weights (TcArgs::w1c); the
+// k <= 32 neighbours are padded to the kernel's 32-row neighbourhoods by repeating the first one (a max-pool ignores duplicates).
+__global__ void edge_pad_idx_kernel(long long rows, int k, const int* __restrict__ idx, int* __restrict__ idx32) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < rows * 32; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e >> 5;
+        const int j = (int)(e & 31);
+        idx32[e] = __ldg(idx + r * k + (j < k ? j : 0));
+    }
+}
+static bool edgeconv_dual_ok(int c, int k, const psa_mlp* mlp, psa_mlp* m2, TcArgs* a) {
+    if (g_mlp_mode == 1 || c != 3 || k < 1 || k > 32 || mlp->n_layers < 2) return false;
+    *m2 = *mlp;
+    m2->channels[0] = 3;
+    m2->weight[0] = mlp->weight[0] + (size_t)3 * mlp->channels[1];
+    for (int l = 0; l < PSA_MAX_MLP_LAYERS; ++l) { m2->image[l] = nullptr; m2->image_nt[l] = 0; m2->image_row0[l] = 0; }
+    return tc_sa_eligible(m2, 0, 32, a);
+}
+
 extern "C" size_t psa_edgeconv_workspace_bytes(int b, int n, int c, int k, const psa_mlp* mlp) {
     if (mlp == nullptr) return 0;
     const long long rows = (long long)b * n;
+    {
+        psa_mlp m2;
+        TcArgs a;
+        if (edgeconv_dual_ok(c, k, mlp, &m2, &a)) return (((size_t)rows * 32 * 4 + 255) & ~(size_t)255) + tc_sa_workspace_bytes(a, b, n, 0);
+    }
     if (!edgeconv_algebra_ok(rows, c, k, mlp)) return 0;
     const int N = mlp->channels[1];
     return (((size_t)c * 2 * N * 4 + 255) & ~(size_t)255) + (((size_t)rows * 2 * N * 4 + 255) & ~(size_t)255) + tc_dense_image_bytes(c, 2 * N) + 256;
@@ -1596,6 +1680,21 @@ extern "C" int psa_edgeconv_infer(int b, int n, int c, int k, const float* x, co
     PSA_REQUIRE(x && nn_idx && out, "edgeconv: null buffer");
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)b * n;
+    {
+        psa_mlp m2;
+        TcArgs a;
+        if (edgeconv_dual_ok(c, k, mlp, &m2, &a)) {
+            const size_t need = psa_edgeconv_workspace_bytes(b, n, c, k, mlp);
+            PSA_REQUIRE(workspace != nullptr && workspace_bytes >= need, "edgeconv: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+            PSA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "edgeconv: workspace must be 256-byte aligned");
+            int* idx32 = reinterpret_cast<int*>(workspace);
+            edge_pad_idx_kernel<<<(unsigned)((rows * 32 + 255) / 256 < 65535 * 4 ? (rows * 32 + 255) / 256 : 65535 * 4), 256, 0, st>>>(rows, k, nn_idx, idx32);
+            rc = check_launch("edge_pad_idx_kernel");
+            if (rc != PSA_OK) return rc;
+            return tc_sa_run(a, b, n, n, 0, 32, x, x, nullptr, idx32, &m2, mlp->weight[0], out,
+                             reinterpret_cast<uint8_t*>(workspace) + (((size_t)rows * 32 * 4 + 255) & ~(size_t)255), st);
+        }
+    }
     if (!edgeconv_algebra_ok(rows, c, k, mlp)) return edgeconv_simt(b, n, c, k, x, nn_idx, mlp, out, st);
     const int N = mlp->channels[1];
     const size_t need = psa_edgeconv_workspace_bytes(b, n, c, k, mlp);
@@ -1633,7 +1732,10 @@ extern "C" int psa_prepare_weight_image(int K, int N, int row0, int nt, const fl
                 "prepare_weight_image: bad arguments K=%d N=%d row0=%d nt=%d", K, N, row0, nt);
     PSA_REQUIRE(W && image, "prepare_weight_image: null buffer");
     const int Ki = K - row0, Kp = (Ki + 63) & ~63;
-    return build_image(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image), as_stream(stream));
+    int rc = build_image(Ki, Kp, N, nt, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image), as_stream(stream));
+    if (rc != PSA_OK || (nt & kImageF16x2) == 0) return rc;
+    // fp16x2 images carry the bf16x3 image of the range guard's rerun right behind them
+    return build_image(Ki, Kp, N, ntw | kImageBf16x3, W + (size_t)row0 * N, reinterpret_cast<uint8_t*>(image) + tc_image_alloc_bytes(Kp, N, 2), as_stream(stream));
 }
 
 extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, int nsample, const psa_mlp* mlp,
@@ -1648,15 +1750,15 @@ extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, 
             const int r0 = (usage == PSA_USAGE_SA_GROUP_ALL && l == 0) ? 3 : 0;
             const int K = mlp->channels[l] - r0, N = mlp->channels[l + 1];
             const int pk = (l == L - 1) ? pool_k : 1;
-            if (K >= 1 && tc_dense_eligible(rows, K, N, pk)) { nt[l] = tc_dense_nt(N); row0[l] = r0; bytes[l] = tc_image_alloc_bytes((K + 63) & ~63, N, g_tc_np); }
+            if (K >= 1 && tc_dense_eligible(rows, K, N, pk)) { nt[l] = tc_dense_nt(N); row0[l] = r0; bytes[l] = tc_plan_image_bytes((K + 63) & ~63, N); }
         }
         return PSA_OK;
     }
     PSA_REQUIRE(usage == PSA_USAGE_SA_MODULE, "mlp_image_plan: unknown usage %d", usage);
     TcArgs a;
     if (!tc_sa_eligible(mlp, c, nsample, &a)) return PSA_OK;
-    if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_image_alloc_bytes((c + 63) & ~63, a.C1, g_tc_np); }
-    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(); row0[1 + l] = 0; bytes[1 + l] = tc_image_alloc_bytes(a.Kd[l], a.Ntot[l], g_tc_np); }
+    if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_plan_image_bytes((c + 63) & ~63, a.C1); }
+    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(); row0[1 + l] = 0; bytes[1 + l] = tc_plan_image_bytes(a.Kd[l], a.Ntot[l]); }
     return PSA_OK;
 }
 

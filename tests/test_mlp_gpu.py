@@ -147,7 +147,7 @@ def test_sa_module_unfused_paths_agree():
 
 
 @pytest.mark.parametrize("n,c,k,mlp", [(1024, 3, 20, [64]), (512, 64, 20, [64]), (256, 64, 20, [128]), (200, 3, 20, [64, 128]),
-                                       (128, 8, 16, [32])])
+                                       (128, 8, 16, [32]), (2048, 3, 20, [64, 128]), (300, 3, 32, [64, 64, 128]), (256, 3, 7, [128, 128])])
 def test_edgeconv_infer_matches_fp64(n, c, k, mlp):
     p = _store(n)
     scopes = []

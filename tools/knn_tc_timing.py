@@ -17,7 +17,9 @@ lib = _lib.load()
 B, N, K = 32, 2048, 20
 out = {}
 for name, x in (("c64_gauss", torch.randn((B, N, 64), device="cuda")), ("c3_ball", torch.from_numpy(make_clouds("ball", B, N, seed=5)).cuda()),
-                ("c64_relu", torch.relu(torch.randn((B, N, 64), device="cuda")))):
+                ("c64_relu", torch.relu(torch.randn((B, N, 64), device="cuda"))),
+                # a feature cloud far from the origin (|x|^2 ~ 50 x the neighbour distances), like DGCNN's post-ReLU EdgeConv outputs
+                ("c64_offset", torch.relu(torch.randn((B, N, 64), device="cuda") * 0.3 + 2.0))):
     c = x.shape[2]
     need = lib.psa_knn_graph_workspace_bytes(B, N, c, K)
     ws = torch.zeros(need // 4 + 1, dtype=torch.float32, device="cuda")
