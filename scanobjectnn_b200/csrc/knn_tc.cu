@@ -3,16 +3,16 @@
 // (oracle/psa_oracle.c orc_dgcnn_knn: dot as an fma chain over the channels, adj = (|p|^2 + (-2 dot)) + |q|^2, k smallest,
 // lower index first on ties).
 //
-//   prep      every point row is split once into three bf16 pieces and laid out as [128 rows][64 k] K-major SWIZZLE_128B
-//             blocks (the weight-image layout of tc_mlp.cu), + the canonical |x|^2 per row;
+//   prep      a translation vector per cloud (knn_centre_kernel); every point row minus that vector is split once into bf16 pieces
+//             and laid out as [128 rows][64 k] K-major SWIZZLE_128B blocks (the weight-image layout of tc_mlp.cu), + the
+//             canonical |x|^2 and the centred |x - mu|^2 per row;
 //   main      CTA = 128 query rows of one cloud (TMEM lane = query row).  The query block is the A operand, candidate blocks
 //             stream through a two-stage ring (cp.async.bulk) as the B operand, D[128 x 128] = G tile in TMEM, two D slots.
-//             Thread q owns row q and reads ITS distances with tcgen05.ld -- selection needs no cross-lane traffic:
+//             Four threads share a row, each reads ITS 32 columns of every tile with one tcgen05.ld -- no cross-lane traffic:
 //     pass 1  one bf16 MMA term (4 MMAs per tile): coarse distances (error <= E1) -> per-row histogram over logarithmic bins
 //             (float exponent + 4 mantissa bits) in shared memory -> tau = upper edge of the bin that holds the k-th smallest;
-//     pass 2  three MMA terms (two bf16 pieces per operand, error <= E2): every candidate with d < tau + E1 + E2 -- a superset of the
-//             true top-k --
-//             is appended to the row's list (typically k + 10..30 entries);
+//     pass 2  six MMA terms (bf16x3, error <= E2): every candidate with d < tau + E1 + E2 -- a superset of the true top-k -- is
+//             appended to the row's list (typically k + 10..30 entries);
 //     order   rank of every listed candidate = its output position.  Fine distances decide wherever two entries are more than
 //             2 E2 apart; entries with a neighbour inside 2 E2 (near-ties, duplicates) get their canonical fp32 distance and are
 //             compared canonically (distance, then index) -- every comparison agrees with the canonical order.
@@ -23,11 +23,14 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-// pass 2 precision: 3 = two bf16 pieces per operand (a1 b1 + a1 b2 + a2 b1), 6 = three pieces (bf16x3).  Both stay inside the
-// bound E2 used below (3 terms: <= 3 * 2^-18 per product + 192 truncating adds + the canonical chain's own 64 * 2^-24, together
-// 3.8e-5 of |q||c| against E2 = 1e-4 |q||c|); 3 terms: 352 us, 6 terms: 374 us at B=32 N=2048 C=64.
+// pass 2 precision: 6 = three bf16 pieces per operand (bf16x3, default), 3 = two pieces (a1 b1 + a1 b2 + a2 b1).
+// The ordering step relies on |fine - canonical| <= E2 with E2 = 1e-4 |q||c| (+ the canonical formula's own rounding), so the bound has
+// to be rigorous.  Per distance (= -2 x the Gram entry): six terms drop <= 2 * 4 * 2^-24 |q||c| of products and add <= 2 * 24 MMAs *
+// 17 * 2^-23 |q||c| of truncating accumulation = 9.3e-5 in the worst case (measured: 0.005 E2).  Three terms drop 2 * 3 * 2^-16 = 9.2e-5
+// of products ALONE (bf16 rounds to 2^-8) -- 1.4e-4 with the accumulation, above the bound (measured up to 0.33 E2 on 3-D clouds) -- and
+// run only 5 % faster (352 vs 374 us at B=32 N=2048 C=64): a build with PSA_KNN_TERMS=3 must also raise E2 to 1.5e-4.
 #ifndef PSA_KNN_TERMS
-#define PSA_KNN_TERMS 3
+#define PSA_KNN_TERMS 6
 #endif
 
 namespace psa {
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         if (J > 1) load(1);
         mbar_wait(&s_qfull, 0);
         const uint32_t idesc = make_idesc(kFmtBF16, 128, 128);
-        constexpr int kTerms = PSA_KNN_TERMS;                // 6: bf16x3 (all products down to 2^-24); 3: bf16x2 (2^-16), same error bound E2
+        constexpr int kTerms = PSA_KNN_TERMS;                // 6: bf16x3 (all products down to 2^-24); 3: bf16x2 (2^-16)
 #if PSA_KNN_TERMS == 6
         constexpr uint32_t qp[6] = {0, 1, 2, 0, 1, 0};       // query piece / candidate piece of the terms, small products first
         constexpr uint32_t cp[6] = {2, 1, 0, 1, 0, 0};
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(kKtThreads, 1) knn_tc_kernel(const __grid_cons
         const float sgeo = sqrtf(sqq * sqmax);
         // |fine - canonical| <= E2: the bf16 products and fp32 sums of the centred Gram entry (relative to the centred norms) + what the
         // canonical fp32 formula itself loses on the ORIGINAL coordinates (its 64-term dot chain and two adds; centring rounds too)
-        const float E2 = 1e-4f * sgeo + 8e-6f * sqrtf(sqqo * sqmaxo) + 2e-6f * (sqqo + sqmaxo);
+        const float E2 = (PSA_KNN_TERMS == 6 ? 1e-4f : 1.5e-4f) * sgeo + 8e-6f * sqrtf(sqqo * sqmaxo) + 2e-6f * (sqqo + sqmaxo);
         const float dmax = 2.0f * (sqq + sqmax);
         const int keymax = (int)(__float_as_uint(fmaxf(dmax, 1e-30f)) >> 19) + 1;
         constexpr int CW = 128 / kKtRowT;

@@ -15,16 +15,19 @@
 //   max-pool  the last epilogue reduces each neighbourhood's rows with a transposing warp butterfly and writes
 //             (B,m,C_out) coalesced.
 //
-// Kernels:
-//   tc_sa_dual_kernel<DBUF>   SA level, two row groups per CTA, bf16x3 operands (three exact bf16 pieces per operand, six
-//                             MMAs per product), per-group streamed last layer, tensor-pipe token, two D slots (DBUF)
-//   tc_dense3_kernel          dense layer, transposed (lane = channel), both operands from shared memory; also the
+// Kernels (all templated on NP, the pieces per operand -- Split<NP> in tc_common.cuh):
+//   tc_sa_dual_kernel<DB,NP>  SA level, two row groups per CTA, per-group streamed last layer, tensor-pipe token, one or two D
+//                             slots (DB); optional centre weights = multi-layer EdgeConv over 3-D points
+//   tc_dense3_kernel<NP>      dense layer, transposed (lane = channel), both operands from shared memory; also the
 //                             training-mode forward (previous batch norm applied on load, statistics in the epilogue)
-//   tc_dense2_kernel          dense layer, A from TMEM, warp-specialised pipeline (N = 64 or K > 512)
-// (Round 1's first generation -- tc_sa_kernel / tc_dense_kernel with a tf32/tf32/bf16 three-term split -- is gone: the
-//  kernels above cover its shapes; levels the dual kernel cannot hold run on the fp32-FMA fused kernel of mlp.cu.)
+//   tc_dense2_kernel<NT,NP>   dense layer, A from TMEM, warp-specialised pipeline (N = 64 or K > 512)
 // fp32 parity: operands are quantised by this code, so the tensor core only ever sees exactly representable values; fp32
 // accumulation in TMEM truncates, hence small terms first and K cut into <= 128-wide pieces (tests hold 1e-5 vs fp64).
+//   NP = 2 (inference default): two fp16 pieces, three MMAs per product; every kernel tracks the leading pieces it stores and raises
+//           a device-side flag when a value leaves the fp16 range -- the launchers then rerun the op on the NP = 3 instantiation
+//           (enqueued unconditionally, a no-op unless the flag is set: `run_if`);
+//   NP = 3 (psa_set_mlp_mode(2), the guarded rerun, the training forward): three bf16 pieces, six MMAs per product.
+// Levels the dual kernel cannot hold run on the fp32-FMA fused kernel of mlp.cu.
 #include <float.h>
 
 #include "common.cuh"
@@ -38,11 +41,11 @@ using namespace tc;
 constexpr int kMaxTcLayers = 2;
 
 // ------------------------------------------------------------------------------------------------------------------
-// Weight images.  A tensor layer W (K x N, row-major, fp32) is pre-arranged once per weight set (tc_prep_weights3_kernel) into
+// Weight images.  A tensor layer W (K x N, row-major, fp32) is pre-arranged once per weight set (tc_prep_weights_kernel) into
 // blocks that can be dropped into shared memory by a single cp.async.bulk and fed to tcgen05.mma unchanged:
-//   block (nt, kc) covers output channels [nt*Nt, nt*Nt+Nt) x input channels [kc*64, kc*64+64): three bf16 pieces
-//   (w = w1 + w2 + w3, every piece exactly representable), each [Nt][64] K-major SWIZZLE_128B, Nt*128 B per piece;
-//   blocks stored in (nt major, kc minor) order.  6 bytes per weight.
+//   block (nt, kc) covers output channels [nt*Nt, nt*Nt+Nt) x input channels [kc*64, kc*64+64): NP 16-bit pieces
+//   (every piece exactly representable), each [Nt][64] K-major SWIZZLE_128B, Nt*128 B per piece; blocks stored in (nt major,
+//   kc minor) order.  2 NP bytes per weight.
 // ------------------------------------------------------------------------------------------------------------------
 // np = pieces per weight: 3 (bf16x3, 6 bytes per weight) or 2 (fp16x2, 4 bytes); see Split<NP> in tc_common.cuh
 __host__ __device__ inline uint32_t tc_block_bytes(int Nt, int np) { return (uint32_t)Nt * 128u * (uint32_t)np; }
@@ -74,7 +77,7 @@ struct TcArgs {
     int Kd[kMaxTcLayers], Ntot[kMaxTcLayers];
     int stream_last;       // 1: the last layer's weights do not fit next to the others -> one 128-channel tile at a time
     int ntcap;             // 64 (narrow configuration) or 128 (wide)
-    int dual;              // 1: tc_sa_dual_kernel (two row groups per CTA, bf16x3 operands, 64-wide output tiles)
+    int dual;              // 1: tc_sa_dual_kernel (two row groups per CTA, 64-wide output tiles)
     unsigned int* tile_counter;   // zeroed before the launch: tiles are handed out dynamically (CTAs that start late or
                                   // share their SM with another stream's kernels simply take fewer)
     int np;                       // operand pieces: 2 (fp16x2) or 3 (bf16x3)
@@ -118,10 +121,8 @@ __device__ unsigned long long g_tc_timing[8];
 //     other group's MMAs run;
 //   * the weights of the inner layer are resident ONCE and shared by both groups; a last layer that does not fit is
 //     streamed per group, one 64-channel tile (48 KB) at a time, L2 -> shared memory during the previous epilogue;
-//   * operands are split into three bf16 pieces each (a = a1 + a2 + a3, w = w1 + w2 + w3, every piece exact): the A
-//     operand of a K = 128 layer is 192 TMEM columns instead of 320, so that A + a 64-column D fit in a group's 256.
-//     Six bf16 MMAs  a1w3 + a2w2 + a3w1 + a1w2 + a2w1 + a1w1  (small terms first: the accumulator add truncates)
-//     reproduce the fp32 product to ~2^-25; weights stay at 6 bytes per element.
+//   * operands are split into NP 16-bit pieces each (Split<NP>): the A operand of a K = 128 layer is 64 NP TMEM columns, so that
+//     A + a 64-column D (two of them with NP = 2) fit in a group's 256; weights are 2 NP bytes per element.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kImageBf16x3 = 0x100;      // flags in psa_mlp.image_nt / psa_mlp_image_plan: image holds three bf16 pieces ..
 constexpr int kImageF16x2 = 0x200;       // .. or two fp16 pieces
@@ -261,9 +262,11 @@ __host__ __device__ inline TcDualLayout tc_dual_layout(const TcArgs& a) {
     return L;
 }
 
-// D chunk (32 columns of this lane's row) -> relu?(d * scale + shift), `fill` for rows past the end
+// D chunk (32 columns of this lane's row) -> relu?(d * scale + shift).  Rows past the end of the problem need no masking: a row of D
+// depends on the same row of A only, validity is per NEIGHBOURHOOD (K divides the tile), and outputs of neighbourhoods past the end are
+// never stored; their layer-1 inputs are zeros, so they carry finite values (no spurious range flag either).
 __device__ __forceinline__ void affine_chunk(const uint32_t (&d)[32], const float* __restrict__ sc_, const float* __restrict__ sh_, int relu,
-                                             bool valid, float fill, float (&h)[32]) {
+                                             float (&h)[32]) {
     const float4* s4 = reinterpret_cast<const float4*>(sc_);
     const float4* t4 = reinterpret_cast<const float4*>(sh_);
 #pragma unroll
@@ -272,8 +275,7 @@ __device__ __forceinline__ void affine_chunk(const uint32_t (&d)[32], const floa
         float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
         float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
         if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-        h[4 * q + 0] = valid ? v0 : fill; h[4 * q + 1] = valid ? v1 : fill;
-        h[4 * q + 2] = valid ? v2 : fill; h[4 * q + 3] = valid ? v3 : fill;
+        h[4 * q + 0] = v0; h[4 * q + 1] = v1; h[4 * q + 2] = v2; h[4 * q + 3] = v3;
     }
 }
 
@@ -416,7 +418,6 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
         const long long g0 = tile * G;
         const long long gid = g0 + row / a.K;
         const bool valid = gid < a.groups;
-        const bool tile_full = g0 + G <= a.groups;
         // ---- layer 1 on the FMA pipe, straight into the A operand ----
         {
             float dx = 0.f, dy = 0.f, dz = 0.f;
@@ -476,8 +477,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     float v2 = fmaf(fmaf(dz, wz.z, fmaf(dy, wy.z, fmaf(dx, wx.z, h[4 * q + 2]))), sc.z, sh.z);
                     float v3 = fmaf(fmaf(dz, wz.w, fmaf(dy, wy.w, fmaf(dx, wx.w, h[4 * q + 3]))), sc.w, sh.w);
                     if (a.relu1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                    h[4 * q + 0] = valid ? v0 : 0.f; h[4 * q + 1] = valid ? v1 : 0.f;
-                    h[4 * q + 2] = valid ? v2 : 0.f; h[4 * q + 3] = valid ? v3 : 0.f;
+                    h[4 * q + 0] = v0; h[4 * q + 1] = v1; h[4 * q + 2] = v2; h[4 * q + 3] = v3;      // rows past the end: see affine_chunk
                 }
                 store_a_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
             }
@@ -508,8 +508,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     uint32_t d[32];
                     tmem_ld32(row_taddr + TcDual::D + cs * 32, d);
                     tmem_ld_wait();
-                    if (nt == 0) affine_chunk(d, sl[l] + cs * 32, tl[l] + cs * 32, a.relu[l], valid, 0.f, h0);
-                    else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], valid, 0.f, h1);
+                    if (nt == 0) affine_chunk(d, sl[l] + cs * 32, tl[l] + cs * 32, a.relu[l], h0);
+                    else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], h1);
                     if (nt + 1 < NT) { fence_before_thread_sync(); group_bar(g); }       // D drained before the next tile lands in it
                 }
                 store_a_at<NP>(row_taddr + a1_col + cs * 16, h0, a_ps, ovf);
@@ -530,9 +530,9 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     float v[32];
                     if (pool_first) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = (tile_full || valid) ? __uint_as_float(d[q]) : -FLT_MAX;
+                        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(d[q]);
                     } else {
-                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], valid, -FLT_MAX, v);
+                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], v);
                     }
                     float mx = warp_colmax_32x32(v, lane);
                     if (quarters_per_group > 1) {
@@ -661,10 +661,10 @@ struct TcDenseArgs {
 // tc_dense2_kernel -- the dense layer as a software pipeline.
 //   CTA = 128 rows x Nt output channels (Nt = 128, or 64 for a 64-wide layer), 17 warps, one CTA per SM:
 //   * 16 ROW warps (quarter = w & 3 -> TMEM lanes, slot = w >> 2 -> 32-column chunk) quantise their chunk of the next
-//     K = 128 segment of x into bf16x3 pieces in one of TWO A-operand buffers in TMEM, while
+//     K = 128 segment of x into NP pieces in one of TWO A-operand buffers in TMEM, while
 //   * the ISSUER warp (converged, tc_common.cuh) waits for that buffer, the segment's weight blocks (cp.async.bulk
 //     into a two-slot shared-memory ring, refilled as soon as the MMAs that read a slot have completed) and for D to
-//     be drained, then issues the segment's six-term MMAs and commits;
+//     be drained, then issues the segment's MMAs (three or six terms) and commits;
 //   * the row warps add each segment's D to fp32 register accumulators (the truncating TMEM accumulation never runs
 //     over more than 128 K), then run the epilogue (affine, ReLU, xyz side input, max-pool).
 //   A-preparation of segment s+1 overlaps the MMAs of segment s; all hand-offs are mbarriers, no CTA-wide barrier
@@ -787,7 +787,7 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
                 }
             }
         };
-        // split into bf16x3 pieces -> A buffer sg & 1, then tell the issuer
+        // split into NP pieces -> A buffer sg & 1, then tell the issuer
         auto store_x = [&](int sg, float (&h)[32]) {
             const int kcs = min(2, KCtot - 2 * sg);
             if (cs < kcs * 2) {
@@ -901,7 +901,7 @@ tc_dense2_kernel(const __grid_constant__ TcDenseArgs a) {
 //   * A operand = the weight image block exactly as tc_dense2 uses it as B ([128 ch][64 k] K-major SWIZZLE_128B, three
 //     bf16 pieces, 48 KB, one cp.async.bulk);
 //   * B operand = x quantised into the same layout by 16 prep warps: each warp reads 8 rows x 256 B fully COALESCED
-//     (lane = two consecutive k), splits into bf16x3 and writes 4-byte words into the swizzled rows -- conflict-free.
+//     (lane = two consecutive k), splits into NP pieces and writes 4-byte words into the swizzled rows -- conflict-free.
 //     (tc_dense2's lane = row loads cost 4096 L1 wavefronts per K = 128 segment; here 256 per 64-K block.)
 //   * the issuer warp waits for a stage's two operands and issues its 24 MMAs; the commit frees the stage;
 //   * accumulation: K-block kb goes to accumulator kb & 3 (4 x 128 TMEM columns), so no accumulator takes more than 48
