@@ -187,7 +187,7 @@ class PointNet2ClsTrainer:
     """Training engine of pointnet2_cls_ssg (or any stack of LevelSpec + FC head with the same structure)."""
 
     def __init__(self, params: VariableStore, batch: int, npoints: int, num_class: int = 15, levels=None, head=None,
-                 device=None, process_group=None):
+                 device=None, process_group=None, in_channels: int = 0):
         self.lib = _lib.load()
         self.params = params
         self.dev = torch.device(device) if device is not None else params.device
@@ -201,7 +201,8 @@ class PointNet2ClsTrainer:
         f32 = dict(dtype=torch.float32, device=dev)
         specs = levels if levels is not None else SSG_LEVELS
         self.levels: list[_Level] = []
-        n, c = npoints, 0
+        n, c = npoints, in_channels          # in_channels > 0: the first level takes per-point features (a level used on its own)
+        self.in_channels = in_channels
         ws_bytes = 0
         lib = self.lib
         for sp in specs:
@@ -251,7 +252,7 @@ class PointNet2ClsTrainer:
             ws_bytes = max(ws_bytes, lib.psa_train_dense_workspace_bytes(batch, cin, width), lib.psa_bn_bwd_workspace_bytes(width))
             cin = width
         self.head_dh = [torch.empty((batch, ly.N), **f32) for ly in self.head[:-1]]
-        self.d_feat = torch.empty((batch, self.levels[-1].spec.mlp[-1]), **f32)
+        self.d_feat = torch.empty_like(self.levels[-1].pooled)          # (B, C) under a head; (B*m, C) for a bare level stack
         self.dlogits = torch.empty((batch, num_class), **f32)
         self.loss = torch.zeros(1, **f32)
         self.ws = torch.empty(ws_bytes // 4 + 64, **f32)
@@ -279,12 +280,17 @@ class PointNet2ClsTrainer:
                 ly.mask.copy_((r < keep).to(torch.float32) / keep)
 
     # ------------------------------------------------------------------------------------------------
-    def forward(self, xyz: torch.Tensor, bn_decay: float = 0.5) -> torch.Tensor:
-        """Training-mode forward (batch statistics, moving averages updated with `bn_decay`) -> logits (B, num_class)."""
+    def forward(self, xyz: torch.Tensor, bn_decay: float = 0.5, points: torch.Tensor | None = None) -> torch.Tensor:
+        """Training-mode forward (batch statistics, moving averages updated with `bn_decay`) -> logits (B, num_class); without a head
+        -> the last level's pooled features (B*m, C).  `points` (B, N, in_channels): input features of the first level."""
         lib = self.lib
         B = self.B
         assert xyz.shape == (B, self.N0, 3) and xyz.is_cuda and xyz.dtype == torch.float32
+        assert (points is None) == (self.in_channels == 0), "points must be given exactly when the trainer was built with in_channels > 0"
         cur_xyz, cur_pts = xyz.contiguous(), None
+        if points is not None:
+            assert points.shape == (B, self.N0, self.in_channels) and points.dtype == torch.float32
+            cur_pts = points.contiguous()
         self.in_xyz = []
         for lv in self.levels:
             sp = lv.spec
@@ -312,6 +318,8 @@ class PointNet2ClsTrainer:
                                            _stream()), "train_pool_fwd")
             cur_xyz, cur_pts = lv.new_xyz, lv.pooled.view(B, lv.m, -1)
         feat = self.levels[-1].pooled                                   # (B, C)
+        if not self.head:
+            return feat
         a = _raw_in(feat)
         for ly in self.head:
             self._dense_fwd(ly, a)
@@ -341,8 +349,10 @@ class PointNet2ClsTrainer:
         """Gradients of every trainable variable for d(loss)/d(logits) = dlogits, into the flat gradient bucket."""
         lib = self.lib
         B = self.B
-        # ---- head ----
+        # ---- head ----  (a bare level stack: dlogits is the gradient of the last level's pooled features)
         dh = dlogits.contiguous()
+        if not self.head:
+            self.d_feat.copy_(dh.reshape(self.d_feat.shape))
         feat = self.levels[-1].pooled
         for i in range(len(self.head) - 1, -1, -1):
             ly = self.head[i]
@@ -434,6 +444,53 @@ class _TrainFn(torch.autograd.Function):
         tr = ctx.trainer
         tr.backward(dlogits.contiguous())
         return tr.fp.grad.clone(), None, None, None
+
+
+class _LevelFn(torch.autograd.Function):
+    """One pointnet_sa_module(is_training=True): pooled features whose backward returns the gradient of the input features and
+    of this level's variables (a flat bucket that is zero outside the level -- several levels may share one store)."""
+
+    @staticmethod
+    def forward(ctx, flat, points, trainer, xyz, bn_decay):
+        ctx.trainer = trainer
+        ctx.has_points = points is not None
+        out = trainer.forward(xyz, bn_decay, points)
+        lv = trainer.levels[-1]
+        return out.clone().view(trainer.B, lv.m, -1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        tr = ctx.trainer
+        tr.backward(dout.contiguous())
+        g = torch.zeros_like(tr.fp.grad)
+        base = tr.fp.grad.data_ptr()
+        for lv in tr.levels:
+            for ly in lv.layers:
+                for t in ([ly.dW, ly.db] + ([ly.dgamma, ly.dbeta] if ly.bn else [])):
+                    off = (t.data_ptr() - base) // 4
+                    g[off:off + t.numel()].copy_(t.reshape(-1))
+        dp = tr.levels[0].d_in.view(tr.B, tr.N0, tr.in_channels).clone() if ctx.has_points else None
+        return g, dp, None, None, None
+
+
+def sa_module_training(xyz, points, spec: LevelSpec, bn_decay, params: VariableStore):
+    """Training-mode pointnet_sa_module (max pooling, use_xyz): -> (new_xyz, new_points (B,m,C) with a grad_fn, idx).  The level's
+    buffers are cached on `params` per (scope, shape); gradients of its variables arrive in `params._flat.grad_of(name)` /
+    through autograd on `params._flat.flat`, the gradient of `points` through autograd."""
+    b, n, _ = xyz.shape
+    c = 0 if points is None else points.shape[-1]
+    key = ("level", spec.scope, b, n, c, spec.npoint, spec.radius, spec.nsample, tuple(spec.mlp), spec.group_all)
+    cache = params.__dict__.setdefault("_trainers", {})
+    if key not in cache:
+        cache[key] = PointNet2ClsTrainer(params, b, n, levels=[spec], head=[], device=xyz.device, in_channels=c)
+    tr = cache[key]
+    tr.fp.flat.requires_grad_(True)
+    out = _LevelFn.apply(tr.fp.flat, points, tr, xyz, 0.5 if bn_decay is None else float(bn_decay))
+    lv = tr.levels[0]
+    idx = lv.idx
+    if spec.group_all:            # sample_and_group_all: one group holding every point in order (pointnet_util.py:75-77)
+        idx = torch.arange(n, dtype=torch.int32, device=xyz.device).view(1, 1, n).repeat(b, 1, 1)
+    return lv.new_xyz, out, idx
 
 
 def get_model_training(point_cloud, bn_decay, num_class, params: VariableStore, levels=None, head=None):

@@ -260,3 +260,59 @@ def test_get_model_is_training_autograd_path():
     flat = p._flat
     assert flat.flat.grad is not None and torch.isfinite(flat.flat.grad).all() and float(flat.flat.grad.abs().max()) > 0
     assert end_points["l1_indices"].shape == (B, 512, 32)
+
+
+@pytest.mark.parametrize("c,group_all", [(16, False), (0, False), (24, True)])
+def test_pointnet_sa_module_is_training_level_autograd(c, group_all):
+    """pointnet_sa_module(is_training=True) on its own: batch-statistics forward, autograd into the input features and the level's
+    variables, against the float64 level restatement (oracle/train_oracle.py) on the SAME sampling / grouping indices; two levels
+    chained through autograd share one variable store without double-counting each other's gradients."""
+    from scanobjectnn_b200.pointnet_util import pointnet_sa_module
+    B, N, m, k, r = 3, 256, 64, 16, 0.35
+    mlp = [64, 32, 64]                                      # the fused level front takes a first width of 64 or 128
+    p = VariableStore(device="cuda", seed=5)
+    add_sa_module_params(p, "lv", 3 + c, mlp)
+    add_sa_module_params(p, "other", 3 + 8, [16])          # a second level in the same store: its gradients must stay zero here
+    rng = np.random.default_rng(c + 1)
+    xyz = make_clouds("ball", B, N, seed=31)
+    pts = rng.standard_normal((B, N, c)).astype(np.float32) if c else None
+    xt = G.cu(xyz)
+    pt = G.cu(pts).requires_grad_(True) if c else None
+    new_xyz, out, idx = pointnet_sa_module(xt, pt, None if group_all else m, None if group_all else r, None if group_all else k, mlp, None,
+                                            group_all, True, 0.5, "lv", params=p)
+    mm = 1 if group_all else m
+    assert out.shape == (B, mm, mlp[-1]) and out.requires_grad
+    R = rng.standard_normal(out.shape).astype(np.float32)
+    (out * G.cu(R)).sum().backward()
+    # oracle on the same indices
+    fps_idx = np.zeros((B, 1), np.int64) if group_all else orc.fps(xyz, m).astype(np.int64)
+    idx_np = G.npy(idx).astype(np.int64)
+    layers = []
+    for i in range(len(mlp)):
+        w = G.npy(p[f"lv/conv{i}/weights"]).astype(np.float64)
+        layers.append((w.reshape(-1, w.shape[-1]), G.npy(p[f"lv/conv{i}/biases"]).astype(np.float64), G.npy(p[f"lv/conv{i}/bn/gamma"]).astype(np.float64),
+                       G.npy(p[f"lv/conv{i}/bn/beta"]).astype(np.float64)))
+    x64 = xyz.astype(np.float64)
+    if group_all:
+        # sample_and_group_all: new_xyz = 0, grouped_xyz = xyz (no centring): same as a centre at the origin
+        x_aug = np.concatenate([x64, np.zeros((B, 1, 3))], axis=1)
+        fps_idx = np.full((B, 1), N, np.int64)
+        pooled, cache, _ = T.sa_level_train_fwd(x_aug, None if pts is None else np.concatenate([pts.astype(np.float64), np.zeros((B, 1, c))], axis=1),
+                                                fps_idx, idx_np, layers)
+    else:
+        pooled, cache, _ = T.sa_level_train_fwd(x64, None if pts is None else pts.astype(np.float64), fps_idx, idx_np, layers)
+    assert _rel(G.npy(out), pooled) < 1e-5
+    _, dpts, grads = T.sa_level_train_bwd(R.astype(np.float64), cache)
+    fp = p._flat
+    for i, (dw, db, dgamma, dbeta) in enumerate(grads):
+        assert _rel(G.npy(fp.grad_of(f"lv/conv{i}/weights")).reshape(dw.shape), dw) < GTOL, f"dW{i}"
+        assert _rel(G.npy(fp.grad_of(f"lv/conv{i}/bn/gamma")), dgamma) < GTOL and _rel(G.npy(fp.grad_of(f"lv/conv{i}/bn/beta")), dbeta) < GTOL
+        assert float(np.abs(G.npy(fp.grad_of(f"lv/conv{i}/biases"))).max()) < 1e-5       # a bias under batch norm has no gradient
+    if c:
+        want = dpts[:, :N] if group_all else dpts
+        assert _rel(G.npy(pt.grad), want) < GTOL
+    # autograd on the flat bucket: this level's entries, zeros elsewhere
+    g = fp.flat.grad
+    assert g is not None and float(g.abs().max()) > 0
+    off = (fp.views["other/conv0/weights"].data_ptr() - fp.flat.data_ptr()) // 4
+    assert float(g[off:off + fp.views["other/conv0/weights"].numel()].abs().max()) == 0.0
