@@ -172,8 +172,18 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
                        params: VariableStore):
     """pointnet_util.pointnet_fp_module (pointnet_util.py:199-229): three_nn + inverse-distance weights +
     three_interpolate in ONE launch (the reference runs them on the CPU), concat skip features, 1x1 convs."""
-    _require_inference(is_training)
+    scopes = [f"{scope}/conv_{i}" for i in range(len(mlp))]
+    if is_training:
+        # three_nn and the inverse-distance weights carry no gradient (they depend on coordinates only); three_interpolate is
+        # differentiable in points2 (ThreeInterpolateGrad), the concat is autograd's, the MLP runs with batch-statistics batch norm
+        if not bn:
+            raise NotImplementedError("pointnet_fp_module(is_training=True) needs bn=True (what the in-scope models use)")
+        from .training import mlp_training
+        with torch.no_grad():
+            _, _, idx, weight = ops.three_nn_interpolate(xyz1, xyz2, points2.detach(), return_aux=True)
+        interpolated = ops.three_interpolate(points2, idx, weight)
+        new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
+        return mlp_training(new_points1, [(sc, True) for sc in scopes], bn_decay, params)
     interpolated = ops.three_nn_interpolate(xyz1, xyz2, points2)
     new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
-    scopes = [f"{scope}/conv_{i}" for i in range(len(mlp))]
     return ops.shared_mlp(new_points1, params.mlp(scopes))

@@ -183,7 +183,137 @@ class _Level:
     d_in: torch.Tensor = None                   # gradient w.r.t. the level's input features (B*n, c_in)
 
 
-class PointNet2ClsTrainer:
+class _TrainOps:
+    """Per-layer training operations shared by the trainers below (they provide self.lib, self.ws, self.ws_bytes)."""
+
+    def _c(self, rc, what):
+        check(rc, what)
+
+    def _bn_finalize(self, ly: _Layer, count: int, decay: float):
+        self._c(self.lib.psa_bn_finalize(ly.N, count, _p(ly.stats), _p(ly.gamma), _p(ly.beta), C.c_float(decay), _p(ly.mov_mean),
+                                         _p(ly.mov_var), _p(ly.scale), _p(ly.shift), _p(ly.mean_inv), _stream()), "bn_finalize")
+
+    def _dense_fwd(self, ly: _Layer, a: PsaActIn):
+        self._c(self.lib.psa_train_dense_fwd(ly.rows, ly.K, ly.N, C.byref(a), _p(ly.W), _p(ly.b), _p(ly.y),
+                                             _p(ly.stats) if ly.bn else None, _p(self.ws), C.c_size_t(self.ws_bytes), _stream()), "train_dense_fwd")
+
+    def _layer_bwd(self, ly: _Layer, g_nocoef: PsaGradIn, g: PsaGradIn, a_in: PsaActIn, dx: torch.Tensor | None, col_skip: int = 0):
+        """gradients of one conv/fc(+BN+relu) layer: BN sums/coefficients, dW, (db), dx."""
+        lib = self.lib
+        if ly.bn:
+            self._c(lib.psa_bn_bwd_coeffs(ly.rows, ly.N, C.byref(g_nocoef), _p(ly.gamma), _p(ly.mean_inv), _p(ly.dgamma), _p(ly.dbeta),
+                                          _p(ly.ca), _p(ly.cb), _p(ly.cc), _p(self.ws), C.c_size_t(self.ws_bytes), _stream()), "bn_bwd_coeffs")
+            ly.db.zero_()          # sum_r dy = 0 under batch norm
+        else:
+            self._c(lib.psa_train_bias_grad(ly.rows, ly.N, C.byref(g), _p(ly.db), _stream()), "train_bias_grad")
+        if a_in is not None:
+            self._c(lib.psa_train_dense_bwd_weight(ly.rows, ly.K, ly.N, C.byref(a_in), C.byref(g), _p(ly.dW), _p(self.ws), C.c_size_t(self.ws_bytes),
+                                                   _stream()), "train_dense_bwd_weight")
+        if dx is not None:
+            self._c(lib.psa_train_dense_bwd_input(ly.rows, ly.K, ly.N, C.byref(g), _p(ly.W), _p(dx), dx.shape[-1], col_skip, _p(self.ws),
+                                                  C.c_size_t(self.ws_bytes), _stream()), "train_dense_bwd_input")
+
+
+def _flat_grad_of_layers(fp: FlatParams, layers) -> torch.Tensor:
+    """a gradient bucket that holds the given layers' gradients and zeros elsewhere (several autograd nodes share one bucket)"""
+    g = torch.zeros_like(fp.grad)
+    base = fp.grad.data_ptr()
+    for ly in layers:
+        for t in ([ly.dW, ly.db] + ([ly.dgamma, ly.dbeta] if ly.bn else [])):
+            off = (t.data_ptr() - base) // 4
+            g[off:off + t.numel()].copy_(t.reshape(-1))
+    return g
+
+
+class MlpTrainer(_TrainOps):
+    """Training-mode shared MLP on dense rows -- tf_util.conv1d / conv2d(1x1) / fully_connected chains with batch-statistics batch
+    norm + ReLU (tf_util.py:120-185,512-531): the FP modules' MLPs, FC heads, per-point heads.  layers = [(scope, bn), ...];
+    a layer with bn=False has no activation (the reference's logits layers)."""
+
+    def __init__(self, params: VariableStore, rows: int, in_channels: int, layers, device=None):
+        self.lib = _lib.load()
+        self.params = params
+        self.dev = torch.device(device) if device is not None else params.device
+        self.fp = params._flat if getattr(params, "_flat", None) is not None else FlatParams(params)
+        params._flat = self.fp
+        self.rows, self.in_channels = rows, in_channels
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.layers: list[_Layer] = []
+        cin, ws_bytes = in_channels, 0
+        for scope, bn in layers:
+            ly = _Layer(self.fp, scope, rows, bn, self.dev)
+            assert ly.K == cin, (scope, ly.W.shape, cin)
+            ws_bytes = max(ws_bytes, self.lib.psa_train_dense_workspace_bytes(rows, ly.K, ly.N), self.lib.psa_bn_bwd_workspace_bytes(ly.N))
+            self.layers.append(ly)
+            cin = ly.N
+        self.dh = [torch.empty((rows, ly.N), **f32) for ly in self.layers[:-1]]
+        self.d_in = torch.empty((rows, in_channels), **f32)
+        last = self.layers[-1]
+        if last.bn:
+            assert last.N % 4 == 0, "an activated last layer needs a width that is a multiple of 4"
+            self.out = torch.empty((rows, last.N), **f32)
+            self.argk = torch.empty((rows, last.N), dtype=torch.int32, device=self.dev)
+        self.ws = torch.empty(ws_bytes // 4 + 64, **f32)
+        self.ws_bytes = ws_bytes
+
+    def forward(self, x: torch.Tensor, bn_decay: float = 0.5) -> torch.Tensor:
+        assert x.shape == (self.rows, self.in_channels) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        self.x = x
+        a = _raw_in(x)
+        for ly in self.layers:
+            self._dense_fwd(ly, a)
+            if ly.bn:
+                self._bn_finalize(ly, ly.rows, bn_decay)
+            a = ly.act_in()
+        last = self.layers[-1]
+        if not last.bn:
+            return last.y
+        # the stack's output is the activated tensor: relu(BN(y)) through the pooling kernel with runs of one row
+        self._c(self.lib.psa_train_pool_fwd(self.rows, 1, last.N, _p(last.y), _p(last.scale), _p(last.shift), _p(self.out), _p(self.argk),
+                                            _stream()), "train_pool_fwd")
+        return self.out
+
+    def backward(self, dout: torch.Tensor) -> torch.Tensor:
+        """dout = gradient w.r.t. forward()'s return value -> gradient w.r.t. x; the layers' gradients go to the flat bucket"""
+        dh = dout.contiguous()
+        for i in range(len(self.layers) - 1, -1, -1):
+            ly = self.layers[i]
+            a_in = self.layers[i - 1].act_in() if i > 0 else _raw_in(self.x)
+            dx = self.dh[i - 1] if i > 0 else self.d_in
+            self._layer_bwd(ly, _grad_dense(ly, dh, False), _grad_dense(ly, dh, True), a_in, dx)
+            dh = dx
+        return self.d_in
+
+
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flat, x, trainer, bn_decay):
+        ctx.trainer = trainer
+        return trainer.forward(x, bn_decay).clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        tr = ctx.trainer
+        dx = tr.backward(dout)
+        return _flat_grad_of_layers(tr.fp, tr.layers), dx.clone(), None, None
+
+
+def mlp_training(x: torch.Tensor, layers, bn_decay, params: VariableStore) -> torch.Tensor:
+    """Training-mode shared MLP with autograd: x (..., C_in) -> (..., C_out); layers = [(scope, bn), ...].  Buffers are cached on
+    `params` per (scopes, shape)."""
+    shape = x.shape
+    rows = x.numel() // shape[-1]
+    key = ("mlp", tuple(layers), rows, shape[-1])
+    cache = params.__dict__.setdefault("_trainers", {})
+    if key not in cache:
+        cache[key] = MlpTrainer(params, rows, shape[-1], list(layers), device=x.device)
+    tr = cache[key]
+    tr.fp.flat.requires_grad_(True)
+    out = _MlpFn.apply(tr.fp.flat, x.reshape(rows, shape[-1]).contiguous(), tr, 0.5 if bn_decay is None else float(bn_decay))
+    return out.view(*shape[:-1], out.shape[-1])
+
+
+class PointNet2ClsTrainer(_TrainOps):
     """Training engine of pointnet2_cls_ssg (or any stack of LevelSpec + FC head with the same structure)."""
 
     def __init__(self, params: VariableStore, batch: int, npoints: int, num_class: int = 15, levels=None, head=None,
@@ -261,17 +391,6 @@ class PointNet2ClsTrainer:
         self._gen.manual_seed(1234)
 
     # ------------------------------------------------------------------------------------------------
-    def _c(self, rc, what):
-        check(rc, what)
-
-    def _bn_finalize(self, ly: _Layer, count: int, decay: float):
-        self._c(self.lib.psa_bn_finalize(ly.N, count, _p(ly.stats), _p(ly.gamma), _p(ly.beta), C.c_float(decay), _p(ly.mov_mean),
-                                         _p(ly.mov_var), _p(ly.scale), _p(ly.shift), _p(ly.mean_inv), _stream()), "bn_finalize")
-
-    def _dense_fwd(self, ly: _Layer, a: PsaActIn):
-        self._c(self.lib.psa_train_dense_fwd(ly.rows, ly.K, ly.N, C.byref(a), _p(ly.W), _p(ly.b), _p(ly.y),
-                                             _p(ly.stats) if ly.bn else None, _p(self.ws), C.c_size_t(self.ws_bytes), _stream()), "train_dense_fwd")
-
     def draw_dropout(self):
         """tf.nn.dropout masks of the head (0 or 1/keep_prob), drawn on the device before the step."""
         for ly, keep in zip(self.head, self.keep):
@@ -329,22 +448,6 @@ class PointNet2ClsTrainer:
         return self.head[-1].y
 
     # ------------------------------------------------------------------------------------------------
-    def _layer_bwd(self, ly: _Layer, g_nocoef: PsaGradIn, g: PsaGradIn, a_in: PsaActIn, dx: torch.Tensor | None, col_skip: int = 0):
-        """gradients of one conv/fc(+BN+relu) layer: BN sums/coefficients, dW, (db), dx."""
-        lib = self.lib
-        if ly.bn:
-            self._c(lib.psa_bn_bwd_coeffs(ly.rows, ly.N, C.byref(g_nocoef), _p(ly.gamma), _p(ly.mean_inv), _p(ly.dgamma), _p(ly.dbeta),
-                                          _p(ly.ca), _p(ly.cb), _p(ly.cc), _p(self.ws), C.c_size_t(self.ws_bytes), _stream()), "bn_bwd_coeffs")
-            ly.db.zero_()          # sum_r dy = 0 under batch norm
-        else:
-            self._c(lib.psa_train_bias_grad(ly.rows, ly.N, C.byref(g), _p(ly.db), _stream()), "train_bias_grad")
-        if a_in is not None:
-            self._c(lib.psa_train_dense_bwd_weight(ly.rows, ly.K, ly.N, C.byref(a_in), C.byref(g), _p(ly.dW), _p(self.ws), C.c_size_t(self.ws_bytes),
-                                                   _stream()), "train_dense_bwd_weight")
-        if dx is not None:
-            self._c(lib.psa_train_dense_bwd_input(ly.rows, ly.K, ly.N, C.byref(g), _p(ly.W), _p(dx), dx.shape[-1], col_skip, _p(self.ws),
-                                                  C.c_size_t(self.ws_bytes), _stream()), "train_dense_bwd_input")
-
     def backward(self, dlogits: torch.Tensor):
         """Gradients of every trainable variable for d(loss)/d(logits) = dlogits, into the flat gradient bucket."""
         lib = self.lib
@@ -462,13 +565,7 @@ class _LevelFn(torch.autograd.Function):
     def backward(ctx, dout):
         tr = ctx.trainer
         tr.backward(dout.contiguous())
-        g = torch.zeros_like(tr.fp.grad)
-        base = tr.fp.grad.data_ptr()
-        for lv in tr.levels:
-            for ly in lv.layers:
-                for t in ([ly.dW, ly.db] + ([ly.dgamma, ly.dbeta] if ly.bn else [])):
-                    off = (t.data_ptr() - base) // 4
-                    g[off:off + t.numel()].copy_(t.reshape(-1))
+        g = _flat_grad_of_layers(tr.fp, [ly for lv in tr.levels for ly in lv.layers])
         dp = tr.levels[0].d_in.view(tr.B, tr.N0, tr.in_channels).clone() if ctx.has_points else None
         return g, dp, None, None, None
 

@@ -316,3 +316,82 @@ def test_pointnet_sa_module_is_training_level_autograd(c, group_all):
     assert g is not None and float(g.abs().max()) > 0
     off = (fp.views["other/conv0/weights"].data_ptr() - fp.flat.data_ptr()) // 4
     assert float(g[off:off + fp.views["other/conv0/weights"].numel()].abs().max()) == 0.0
+
+
+def _torch_bn_relu(x, w, b, gamma, beta):
+    y = x @ w + b
+    mean = y.mean(0)
+    var = y.var(0, unbiased=False)
+    return torch.relu((y - mean) / torch.sqrt(var + 1e-3) * gamma + beta)
+
+
+def test_mlp_training_autograd_matches_float64_torch():
+    """training.mlp_training (conv / fc chains with batch-statistics batch norm): outputs, input gradient and variable gradients
+    against the same chain written in float64 torch ops with torch's autograd."""
+    from scanobjectnn_b200.training import mlp_training
+    p = VariableStore(device="cuda", seed=9)
+    p.add_conv2d("s/c0", 96, 128, bn=True)
+    p.add_conv2d("s/c1", 128, 64, bn=True)
+    p.add_conv2d("s/c2", 64, 10, bn=False)
+    rng = np.random.default_rng(2)
+    x = torch.tensor(rng.standard_normal((2, 300, 96)).astype(np.float32), device="cuda", requires_grad=True)
+    hid = mlp_training(x, [("s/c0", True), ("s/c1", True)], 0.5, p)                 # activated output (B, N, 64)
+    out = mlp_training(hid, [("s/c2", False)], 0.5, p)                               # logits layer, a second autograd node
+    R = torch.tensor(rng.standard_normal(tuple(out.shape)).astype(np.float32), device="cuda")
+    R2 = torch.tensor(rng.standard_normal(tuple(hid.shape)).astype(np.float32), device="cuda")
+    ((out * R).sum() + (hid * R2).sum()).backward()
+    fp = p._flat
+    # float64 reference
+    ws = {k: p[k].detach().double().clone().requires_grad_(True) for k in p.keys() if k.startswith("s/") and "moving" not in k}
+    x64 = x.detach().double().reshape(-1, 96).requires_grad_(True)
+    h = _torch_bn_relu(x64, ws["s/c0/weights"].reshape(96, 128), ws["s/c0/biases"], ws["s/c0/bn/gamma"], ws["s/c0/bn/beta"])
+    h = _torch_bn_relu(h, ws["s/c1/weights"].reshape(128, 64), ws["s/c1/biases"], ws["s/c1/bn/gamma"], ws["s/c1/bn/beta"])
+    o = h @ ws["s/c2/weights"].reshape(64, 10) + ws["s/c2/biases"]
+    ((o * R.double().reshape(-1, 10)).sum() + (h * R2.double().reshape(-1, 64)).sum()).backward()
+    assert _rel(G.npy(hid).reshape(-1, 64), h.detach().cpu().numpy()) < 1e-5 and _rel(G.npy(out).reshape(-1, 10), o.detach().cpu().numpy()) < 1e-5
+    assert _rel(G.npy(x.grad).reshape(-1, 96), x64.grad.cpu().numpy()) < GTOL
+    for k, w in ws.items():
+        want = w.grad.cpu().numpy()
+        got = G.npy(fp.grad_of(k)).reshape(want.shape)
+        if np.abs(want).max() < 1e-9:
+            assert np.abs(got).max() < 1e-5, k          # conv bias under batch norm
+        else:
+            assert _rel(got, want) < GTOL, k
+    # the bucket autograd accumulated on the flat parameter vector is the sum of the two nodes' buckets = the per-name views
+    assert torch.equal(fp.flat.grad, fp.grad) or _rel(G.npy(fp.flat.grad), G.npy(fp.grad)) < 1e-6
+
+
+def test_pointnet2_cls_bga_is_training_backward_runs_and_matches_finite_difference():
+    """pointnet2_cls_bga.get_model(is_training=True): both heads carry a grad_fn; a directional finite difference of the joint loss along
+    a random direction in parameter space agrees with the autograd gradient (dropout off for the check)."""
+    from scanobjectnn_b200 import pointnet2_cls_bga as bga
+    B, N = 4, 1024
+    p = bga.init_params(seed=3)
+    xyz = G.cu(make_clouds("ball", B, N, seed=8))
+    labels = G.cu(np.array([1, 4, 7, 11], dtype=np.int64))
+    mask = G.cu((np.random.default_rng(0).random((B, N)) > 0.5).astype(np.int64))
+    cp, sp = bga.get_model(xyz, True, bn_decay=0.5, params=p)
+    assert cp.shape == (B, 15) and sp.shape == (B, N, 2) and cp.requires_grad and sp.requires_grad
+    loss, _, _ = bga.get_loss(cp, sp, labels, mask)
+    loss.backward()
+    g = p._flat.flat.grad.clone()
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+    def loss_at(flat_values):
+        with torch.no_grad():
+            p._flat.flat.copy_(flat_values)
+        p.invalidate()
+        c2, s2 = bga._get_model_training(xyz, 0.5, 15, p, False, dropout=False)
+        return float(bga.get_loss(c2, s2, labels, mask)[0].item())
+
+    base = p._flat.flat.detach().clone()
+    c2, s2 = bga._get_model_training(xyz, 0.5, 15, p, False, dropout=False)
+    p._flat.flat.grad = None
+    bga.get_loss(c2, s2, labels, mask)[0].backward()
+    g = p._flat.flat.grad.clone()
+    d = g / g.norm()                                 # steepest direction: the directional derivative is |g|
+    eps = 3e-3 / float(g.norm())                     # a +-3e-3 change of the loss: well above float32 resolution, well inside the linear range
+    fd = (loss_at(base + eps * d) - loss_at(base - eps * d)) / (2 * eps)
+    an = float((g * d).sum().item())
+    loss_at(base)
+    assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd)) + 1e-4, (fd, an)
