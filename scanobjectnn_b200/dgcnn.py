@@ -1,4 +1,4 @@
-"""dgcnn/models/dgcnn.py and dgcnn_bga.py on the B200 kernels (inference mode).
+"""dgcnn/models/dgcnn.py and dgcnn_bga.py on the B200 kernels (inference; dgcnn.get_model also with is_training=True).
 
 Every `pairwise_distance -> knn -> get_edge_feature -> conv2d -> reduce_max` group of the reference
 (dgcnn.py:31-80) is two launches here: the fused kNN graph (no (B,N,N) matrix) and the fused EdgeConv
@@ -73,9 +73,61 @@ def _backbone(point_cloud, params, end_points, k=K_NEIGHBORS):
     return nets, glob
 
 
+def _edge_conv_training(x, k, layers, bn_decay, params, idx=None):
+    """pairwise_distance -> knn -> get_edge_feature -> conv2d(+BN+ReLU)... -> reduce_max over k (dgcnn.py:31-44) in training mode.
+    The neighbour graph carries no gradient; the edge tensor [x_i, x_j - x_i] is built from the differentiable group_point
+    (GroupPointGrad) and torch glue, the convolutions run as mlp_training (batch statistics over all B*N*k edges)."""
+    from .training import mlp_training
+    b, n, c = x.shape
+    if idx is None:
+        with torch.no_grad():
+            idx = ops.knn_graph(x.detach().contiguous(), k)
+    neigh = ops.group_point(x.contiguous(), idx)                               # (B,N,k,C), differentiable in x
+    centre = x.unsqueeze(2).expand(b, n, k, c)
+    edge = torch.cat([centre, neigh - centre], dim=-1)                         # get_edge_feature, dgcnn/utils/tf_util.py:674-706
+    y = mlp_training(edge.reshape(b * n * k, 2 * c), layers, bn_decay, params)
+    return y.view(b, n, k, -1).amax(dim=2), idx                                # tf.reduce_max(axis=-2)
+
+
+def _get_model_training(point_cloud, bn_decay, num_class, params: VariableStore, dropout: bool = True, k=K_NEIGHBORS, graphs=None):
+    """dgcnn.get_model with is_training=True (dgcnn.py:24-102, transform_nets.py:10-55): batch-statistics batch norm everywhere,
+    dropout (keep 0.5) after fc1 and fc2, PyTorch autograd over the hand-written kernels.  `graphs` (tests): the five neighbour
+    graphs to use instead of recomputing them -- the graphs are piecewise-constant functions of the parameters, which a finite
+    difference must not cross."""
+    from .training import mlp_training
+    f = torch.nn.functional
+    b, n, _ = point_cloud.shape
+    end_points = {}
+    drop = (lambda t: f.dropout(t, 0.5, training=True)) if dropout else (lambda t: t)
+    # input transform net on the raw cloud
+    sc = "transform_net1"
+    net, idx0 = _edge_conv_training(point_cloud, k, [(f"{sc}/tconv1", True), (f"{sc}/tconv2", True)], bn_decay, params,
+                                    None if graphs is None else graphs[0])                                                # (B,N,128)
+    end_points["nn_idx0"] = idx0
+    net = mlp_training(net, [(f"{sc}/tconv3", True)], bn_decay, params).amax(dim=1)                                       # (B,1024)
+    net = mlp_training(net, [(f"{sc}/tfc1", True), (f"{sc}/tfc2", True)], bn_decay, params)                               # (B,256)
+    fp = params._flat
+    w, bias = fp.live(f"{sc}/transform_XYZ/weights"), fp.live(f"{sc}/transform_XYZ/biases")
+    transform = (net @ w + bias + torch.eye(3, device=w.device).flatten()).reshape(b, 3, 3)
+    x = torch.bmm(point_cloud, transform)
+    end_points.update(transform=transform, point_cloud_transformed=x)
+    nets = []
+    for i, scope in enumerate(["dgcnn1", "dgcnn2", "dgcnn3", "dgcnn4"]):
+        x, idx = _edge_conv_training(x, k, [(scope, True)], bn_decay, params, None if graphs is None else graphs[i + 1])
+        end_points[f"nn_idx{i + 1}"] = idx
+        end_points[f"net{i + 1}"] = x
+        nets.append(x)
+    net = mlp_training(torch.cat(nets, dim=-1), [("agg", True)], bn_decay, params).amax(dim=1)                            # (B,1024)
+    end_points["global"] = net
+    net = drop(mlp_training(net, [("fc1", True)], bn_decay, params))
+    net = drop(mlp_training(net, [("fc2", True)], bn_decay, params))
+    return mlp_training(net, [("fc3", False)], bn_decay, params), end_points
+
+
 def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore):
     """dgcnn.get_model (dgcnn.py:24-102): (B,N,3) -> (logits (B,num_class), end_points)."""
-    _require_inference(is_training)
+    if is_training:
+        return _get_model_training(point_cloud, bn_decay, num_class, params)
     end_points = {}
     _, net = _backbone(point_cloud, params, end_points)                      # tf.reduce_max over N already applied
     end_points["global"] = net

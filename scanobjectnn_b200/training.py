@@ -84,6 +84,13 @@ class FlatParams:
     def grad_of(self, name):
         return self.gviews[name]
 
+    def live(self, name) -> torch.Tensor:
+        """a view of the flat parameter vector taken NOW (autograd-tracked when flat.requires_grad): for variables used directly in
+        torch ops (e.g. the T-net's transform_XYZ matrix) rather than through the hand-written layers"""
+        v = self.views[name]
+        off = (v.data_ptr() - self.flat.data_ptr()) // 4
+        return self.flat[off:off + v.numel()].view(v.shape)
+
 
 class _Layer:
     """conv1x1 / fully_connected (+ batch norm + relu): parameter views, gradient views and per-step buffers."""

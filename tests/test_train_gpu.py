@@ -395,3 +395,49 @@ def test_pointnet2_cls_bga_is_training_backward_runs_and_matches_finite_differen
     an = float((g * d).sum().item())
     loss_at(base)
     assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd)) + 1e-4, (fd, an)
+
+
+def test_dgcnn_is_training_backward_matches_finite_difference():
+    """dgcnn.get_model(is_training=True): EdgeConv layers with batch-statistics batch norm over all edges, the T-net (its 3x3 output is a
+    plain torch op on a live view of the flat parameter vector), autograd over group_point / mlp_training; a directional finite difference
+    of the loss along the gradient agrees with the autograd gradient (dropout off, neighbour graphs held fixed)."""
+    from scanobjectnn_b200 import dgcnn
+    B, N = 8, 160                                       # 8 rows in the head's batch norm: two would make it a sign function
+    p = dgcnn.init_params(seed=5)
+    with torch.no_grad():
+        p["transform_net1/transform_XYZ/weights"].normal_(0, 0.01)          # the reference initialises it to zero: give it a gradient path
+    xyz = G.cu(make_clouds("ball", B, N, seed=6))
+    labels = G.cu(np.array([2, 9, 0, 14, 5, 5, 7, 1], dtype=np.int64))
+    logits, end_points = dgcnn.get_model(xyz, True, bn_decay=0.5, params=p)
+    assert logits.shape == (B, 15) and logits.requires_grad and end_points["nn_idx4"].shape == (B, N, 20)
+    fp = p._flat
+
+    graphs = [end_points[f"nn_idx{i}"] for i in range(5)]     # the graphs depend on the parameters piecewise-constantly: hold them
+
+    def run():
+        lg, _ = dgcnn._get_model_training(xyz, 0.5, 15, p, dropout=False, graphs=graphs)
+        return torch.nn.functional.cross_entropy(lg, labels)
+
+    fp.flat.grad = None
+    run().backward()
+    g = fp.flat.grad.clone()
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+    for name in ("transform_net1/tconv1/weights", "transform_net1/transform_XYZ/weights", "dgcnn1/weights", "dgcnn4/bn/gamma", "agg/weights", "fc3/biases"):
+        v = fp.views[name]
+        off = (v.data_ptr() - fp.flat.data_ptr()) // 4
+        assert float(g[off:off + v.numel()].abs().max()) > 0, f"no gradient reached {name}"
+    base = fp.flat.detach().clone()
+    d = g / g.norm()
+    eps = 3e-3 / float(g.norm())
+
+    def loss_at(values):
+        with torch.no_grad():
+            fp.flat.copy_(values)
+        p.invalidate()
+        with torch.no_grad():
+            return float(run().item())
+
+    fd = (loss_at(base + eps * d) - loss_at(base - eps * d)) / (2 * eps)
+    an = float((g * d).sum().item())
+    loss_at(base)
+    assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd)) + 1e-4, (fd, an)
