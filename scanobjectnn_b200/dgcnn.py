@@ -1,4 +1,4 @@
-"""dgcnn/models/dgcnn.py and dgcnn_bga.py on the B200 kernels (inference; dgcnn.get_model also with is_training=True).
+"""dgcnn/models/dgcnn.py and dgcnn_bga.py on the B200 kernels (inference, and training through autograd over the same kernels: is_training=True).
 
 Every `pairwise_distance -> knn -> get_edge_feature -> conv2d -> reduce_max` group of the reference
 (dgcnn.py:31-80) is two launches here: the fused kNN graph (no (B,N,N) matrix) and the fused EdgeConv
@@ -8,7 +8,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .tf_util import VariableStore, _require_inference
+from .tf_util import VariableStore
 
 NUM_CLASSES = 15
 K_NEIGHBORS = 20
@@ -89,7 +89,7 @@ def _edge_conv_training(x, k, layers, bn_decay, params, idx=None):
     return y.view(b, n, k, -1).amax(dim=2), idx                                # tf.reduce_max(axis=-2)
 
 
-def _get_model_training(point_cloud, bn_decay, num_class, params: VariableStore, dropout: bool = True, k=K_NEIGHBORS, graphs=None):
+def _get_model_training(point_cloud, bn_decay, num_class, params: VariableStore, dropout: bool = True, k=K_NEIGHBORS, graphs=None, bga: bool = False):
     """dgcnn.get_model with is_training=True (dgcnn.py:24-102, transform_nets.py:10-55): batch-statistics batch norm everywhere,
     dropout (keep 0.5) after fc1 and fc2, PyTorch autograd over the hand-written kernels.  `graphs` (tests): the five neighbour
     graphs to use instead of recomputing them -- the graphs are piecewise-constant functions of the parameters, which a finite
@@ -119,6 +119,17 @@ def _get_model_training(point_cloud, bn_decay, num_class, params: VariableStore,
         nets.append(x)
     net = mlp_training(torch.cat(nets, dim=-1), [("agg", True)], bn_decay, params).amax(dim=1)                            # (B,1024)
     end_points["global"] = net
+    if bga:
+        # dgcnn_bga.py:95-134: class vector taken after fc2 (before dp2); per-point head on [class vector, global max, net1..net4]
+        out_max = net
+        net = drop(mlp_training(net, [("fc1", True)], bn_decay, params))
+        net = mlp_training(net, [("fc2", True)], bn_decay, params)
+        class_pred = mlp_training(drop(net), [("fc3", False)], bn_decay, params)
+        concat = torch.cat([net.unsqueeze(1).expand(b, n, 256), out_max.unsqueeze(1).expand(b, n, 1024), *nets], dim=-1)
+        seg = mlp_training(concat, [("seg/conv1", True), ("seg/conv2", True)], bn_decay, params)
+        if dropout:
+            seg = f.dropout(seg, 0.3, training=True)                                                                      # keep_prob 0.7
+        return class_pred, mlp_training(seg, [("seg/conv3", False)], bn_decay, params), end_points
     net = drop(mlp_training(net, [("fc1", True)], bn_decay, params))
     net = drop(mlp_training(net, [("fc2", True)], bn_decay, params))
     return mlp_training(net, [("fc3", False)], bn_decay, params), end_points
@@ -137,7 +148,9 @@ def get_model(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *,
 
 def get_model_bga(point_cloud, is_training, bn_decay=None, num_class=NUM_CLASSES, *, params: VariableStore, return_end_points: bool = False):
     """dgcnn_bga.get_model (dgcnn_bga.py:27-134): -> (class_pred (B,num_class), seg_pred (B,N,2), end_points)."""
-    _require_inference(is_training)
+    if is_training:
+        cp, sp, ep = _get_model_training(point_cloud, bn_decay, num_class, params, bga=True)
+        return (cp, sp, ep) if return_end_points else (cp, sp)
     end_points = {}
     b, n, _ = point_cloud.shape
     nets, out_max = _backbone(point_cloud, params, end_points)               # (B,1024)

@@ -115,16 +115,29 @@ class VariableStore(dict):
 def _require_inference(is_training):
     if is_training:
         raise NotImplementedError(
-            "is_training=True (batch-statistics BN + backward) is a later row of the scope table; "
-            "this build runs the inference path (moving-average BN folded into the fused kernels)")
+            "is_training=True is not available for this configuration; training mode covers the models' own layer configurations "
+            "(training.py: sa_module_training, mlp_training, PointNet2ClsTrainer) -- see INTEGRATION.md")
+
+
+def _layer_training(inputs, scope, activation_fn, bn, bn_decay, params):
+    """one conv / fully-connected layer in training mode (training.mlp_training): conv+BN+ReLU or a plain linear layer"""
+    if bn and activation_fn is not None:
+        kind = True
+    elif not bn and activation_fn is None:
+        kind = False
+    else:
+        raise NotImplementedError("training mode covers conv/fc + batch norm + ReLU and plain linear layers (what the models use)")
+    from .training import mlp_training
+    return mlp_training(inputs, [(scope, kind)], bn_decay, params)
 
 
 def conv2d(inputs, num_output_channels, kernel_size, scope, stride=(1, 1), padding="SAME", data_format="NHWC",
            activation_fn="relu", bn=False, bn_decay=None, is_training=False, *, params: VariableStore):
     """tf_util.conv2d restricted to what the hot path uses: 1x1 kernels, stride 1, NHWC, ReLU or None."""
-    _require_inference(is_training)
     if tuple(kernel_size) != (1, 1) or tuple(stride) != (1, 1) or data_format != "NHWC":
         raise NotImplementedError("only 1x1 / stride-1 / NHWC convolutions are on the point-set-abstraction path")
+    if is_training:
+        return _layer_training(inputs, scope, activation_fn, bn, bn_decay, params)
     relu = activation_fn is not None
     mlp = params.mlp([scope], [relu])
     if mlp.channels[-1] != num_output_channels:
@@ -134,7 +147,8 @@ def conv2d(inputs, num_output_channels, kernel_size, scope, stride=(1, 1), paddi
 
 def fully_connected(inputs, num_outputs, scope, activation_fn="relu", bn=False, bn_decay=None, is_training=False, *,
                     params: VariableStore):
-    _require_inference(is_training)
+    if is_training:
+        return _layer_training(inputs, scope, activation_fn, bn, bn_decay, params)
     relu = activation_fn is not None
     mlp = params.mlp([scope], [relu])
     if mlp.channels[-1] != num_outputs:
@@ -143,5 +157,9 @@ def fully_connected(inputs, num_outputs, scope, activation_fn="relu", bn=False, 
 
 
 def dropout(inputs, is_training, scope, keep_prob=0.5, noise_shape=None):
-    _require_inference(is_training)
+    """tf_util.dropout (tf_util.py:560-580): identity at inference, tf.nn.dropout(keep_prob) in training"""
+    if is_training:
+        if noise_shape is not None:
+            raise NotImplementedError("dropout: noise_shape is not used by the in-scope models")
+        return torch.nn.functional.dropout(inputs, 1.0 - keep_prob, training=True)
     return inputs

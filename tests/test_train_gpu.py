@@ -441,3 +441,62 @@ def test_dgcnn_is_training_backward_matches_finite_difference():
     an = float((g * d).sum().item())
     loss_at(base)
     assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd)) + 1e-4, (fd, an)
+
+
+def _directional_check(fp, p, run, tol=0.05):
+    fp.flat.grad = None
+    run().backward()
+    g = fp.flat.grad.clone()
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+    base = fp.flat.detach().clone()
+    d = g / g.norm()
+    eps = 3e-3 / float(g.norm())
+
+    def loss_at(values):
+        with torch.no_grad():
+            fp.flat.copy_(values)
+            p.invalidate()
+            return float(run().item())
+
+    fd = (loss_at(base + eps * d) - loss_at(base - eps * d)) / (2 * eps)
+    an = float((g * d).sum().item())
+    loss_at(base)
+    assert abs(fd - an) <= tol * max(abs(an), abs(fd)) + 1e-4, (fd, an)
+    return g
+
+
+def test_pointnet_cls_and_dgcnn_bga_is_training():
+    """the remaining in-scope model families in training mode: vanilla PointNet (two T-nets, regularised loss) and dgcnn_bga (joint heads)"""
+    from scanobjectnn_b200 import dgcnn, pointnet_cls
+    B, N = 8, 256
+    xyz = G.cu(make_clouds("ball", B, N, seed=12))
+    labels = G.cu(np.array([2, 9, 0, 14, 5, 5, 7, 1], dtype=np.int64))
+    p = pointnet_cls.init_params(seed=2)
+    with torch.no_grad():
+        p["transform_net1/transform_XYZ/weights"].normal_(0, 0.01)
+        p["transform_net2/transform_feat/weights"].normal_(0, 0.003)
+    logits, ep = pointnet_cls.get_model(xyz, True, bn_decay=0.5, params=p)
+    assert logits.shape == (B, 15) and logits.requires_grad and ep["transform"].shape == (B, 64, 64)
+
+    def run_pn():
+        lg, e2 = pointnet_cls._get_model_training(xyz, 0.5, 15, p, dropout=False)
+        return pointnet_cls.get_loss(lg, labels, e2)
+
+    g = _directional_check(p._flat, p, run_pn)
+    v = p._flat.views["transform_net2/transform_feat/weights"]
+    off = (v.data_ptr() - p._flat.flat.data_ptr()) // 4
+    assert float(g[off:off + v.numel()].abs().max()) > 0
+
+    q = dgcnn.init_params(seed=4, bga=True)
+    mask = G.cu((np.random.default_rng(1).random((B, N)) > 0.4).astype(np.int64))
+    cp, sp = dgcnn.get_model_bga(xyz, True, bn_decay=0.5, params=q)
+    assert cp.shape == (B, 15) and sp.shape == (B, N, 2) and cp.requires_grad and sp.requires_grad
+    _, _, ep = dgcnn._get_model_training(xyz, 0.5, 15, q, dropout=False, bga=True)
+    graphs = [ep[f"nn_idx{i}"] for i in range(5)]
+
+    def run_dg():
+        c2, s2, _ = dgcnn._get_model_training(xyz, 0.5, 15, q, dropout=False, graphs=graphs, bga=True)
+        f = torch.nn.functional
+        return 0.5 * f.cross_entropy(c2, labels) + 0.5 * f.cross_entropy(s2.reshape(-1, 2), mask.reshape(-1))
+
+    _directional_check(q._flat, q, run_dg)
