@@ -914,11 +914,15 @@ struct TcDense3 {
     static constexpr uint32_t kPiece = 128u * 128u;          // one 16-bit piece of a 128 x 64 block: 16 KB
 };
 
-template <int NP>
+// CP = channel tiles per CTA.  CP = 2 (fp16x2, N a multiple of 256): the x block of a K step is staged ONCE and multiplied with the
+// weight blocks of two 128-channel tiles (accumulators 0/1 and 2/3) -- the staging work per output halves and SA3's 512 -> 1024 layer
+// becomes a single wave of 128 CTAs instead of 1.7 waves of 256.
+template <int NP, int CP>
 __global__ void __launch_bounds__(TcDense3::kThreads, 1)
 tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
     if (a.run_if != nullptr && *a.run_if == 0u) return;
     constexpr uint32_t kBlock = NP * TcDense3::kPiece;       // 48 KB (bf16x3) or 32 KB (fp16x2)
+    constexpr int kAcc = 4 / CP;                             // TMEM accumulators (128 columns each) per channel tile
     uint32_t ovf = 0u;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_wfull[2];     // weight block landed (tx)
@@ -930,10 +934,10 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp_u = (int)warp_uniform((uint32_t)(tid >> 5));
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* wslot = base;                                   // 2 x 48 KB
-    uint8_t* xslot = base + 2 * kBlock;            // 2 x 48 KB
+    uint8_t* wslot = base;                                   // 2 stages x CP weight blocks
+    uint8_t* xslot = base + 2 * CP * kBlock;                 // 2 stages x 1 x block
     const int KB = a.Kp / 64;
-    const int nt = blockIdx.y;
+    const int nt = blockIdx.y * CP;                          // first channel tile of this CTA
     const long long row0 = (long long)blockIdx.x * 128;
     const uint8_t* img = a.image + (size_t)nt * KB * kBlock;
 
@@ -968,16 +972,19 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
             mbar_wait(&s_xfull[st], par);
             __syncwarp();
             fence_after_thread_sync();
-            const uint32_t d = tmem_base + (uint32_t)(kb & 3) * 128u;
-            const SmemDescBase wa = smem_desc_base(warp_uniform(smem_u32(wslot) + (uint32_t)st * kBlock));
             const SmemDescBase xb = smem_desc_base(warp_uniform(smem_u32(xslot) + (uint32_t)st * kBlock));
-            const uint32_t first = kb < 4 ? 0u : 1u;         // an accumulator's first block overwrites it
+            const uint32_t first = kb < kAcc ? 0u : 1u;      // an accumulator's first block overwrites it
 #pragma unroll
-            for (int t = 0; t < Split<NP>::kTerms; ++t)
+            for (int c = 0; c < CP; ++c) {
+                const uint32_t d = tmem_base + (uint32_t)(c * kAcc + (kb % kAcc)) * 128u;
+                const SmemDescBase wa = smem_desc_base(warp_uniform(smem_u32(wslot) + (uint32_t)(st * CP + c) * kBlock));
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
-                    mma_bf16_ss(d, smem_desc_at(wa, Split<NP>::w(t) * TcDense3::kPiece + s4 * 32), smem_desc_at(xb, Split<NP>::a(t) * TcDense3::kPiece + s4 * 32),
-                                idesc, (t | s4) ? 1u : first);
+                for (int t = 0; t < Split<NP>::kTerms; ++t)
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        mma_bf16_ss(d, smem_desc_at(wa, Split<NP>::w(t) * TcDense3::kPiece + s4 * 32),
+                                    smem_desc_at(xb, Split<NP>::a(t) * TcDense3::kPiece + s4 * 32), idesc, (t | s4) ? 1u : first);
+            }
             mma_commit(&s_free[st]);
         }
     } else {
@@ -1014,9 +1021,10 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
             if (kb >= 2) mbar_wait(&s_free[st], (uint32_t)(((kb - 2) >> 1) & 1));      // stage released by block kb-2's MMAs
             TC_STAMP(1);
             if (warp_u == 0 && lane == 0) {                                             // its weight slot is free too
-                mbar_expect_tx(&s_wfull[st], kBlock);
-                for (uint32_t o = 0; o < kBlock; o += 16384u)
-                    bulk_g2s(wslot + (uint32_t)st * kBlock + o, img + (size_t)kb * kBlock + o, 16384u, &s_wfull[st]);
+                mbar_expect_tx(&s_wfull[st], CP * kBlock);
+                for (int c = 0; c < CP; ++c)
+                    for (uint32_t o = 0; o < kBlock; o += 16384u)
+                        bulk_g2s(wslot + (uint32_t)(st * CP + c) * kBlock + o, img + ((size_t)c * KB + kb) * kBlock + o, 16384u, &s_wfull[st]);
             }
             uint8_t* xs = xslot + (uint32_t)st * kBlock;
 #pragma unroll
@@ -1041,8 +1049,11 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
 
         // ---- epilogue: lane = channel ----
         const int quarter = warp_u & 3, slot = warp_u >> 2;          // channels 32*quarter.., rows 32*slot..
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)slot * 32u;
-        const int ch = nt * 128 + quarter * 32 + lane;
+        const long long rbase = row0 + slot * 32;
+#pragma unroll 1
+        for (int ct = 0; ct < CP; ++ct) {                             // the CTA's channel tiles, one after the other
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ct * kAcc) * 128u + (uint32_t)slot * 32u;
+        const int ch = (nt + ct) * 128 + quarter * 32 + lane;
         float acc[32];
         {
             uint32_t d[32];
@@ -1050,7 +1061,7 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(d[q]);
-            const int nacc = KB < 4 ? KB : 4;
+            const int nacc = KB < kAcc ? KB : kAcc;
             for (int c = 1; c < nacc; ++c) {
                 tmem_ld32(taddr + (uint32_t)c * 128u, d);
                 tmem_ld_wait();
@@ -1074,7 +1085,6 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
             if (a.relu) x = fmaxf(x, 0.f);
             acc[q] = x;
         }
-        const long long rbase = row0 + slot * 32;
         if (a.pool_k == 1) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
@@ -1121,6 +1131,8 @@ tc_dense3_kernel(const __grid_constant__ TcDenseArgs a) {
                     atomicMax(reinterpret_cast<int*>(a.out) + (size_t)wg * a.N + ch, code);
                 }
             }
+        }
+        if (CP > 1) named_bar_sync(1, TcDense3::kPrepWarps * 32);       // s_red / s_st are reused by the next channel tile
         }
     }
     TC_STAMP(4);
@@ -1183,10 +1195,21 @@ static int launch_tc_dense_np(TcDenseArgs& a, int Nt, cudaStream_t st) {
     const bool big = a.pool_k > 128;
     if (big) { int rc0 = launch_fill_ord_neg_inf(a.rows / a.pool_k * a.N, a.out, st, a.run_if); if (rc0 != PSA_OK) return rc0; }
     if (Nt == 128 && a.Kp <= 512) {
-        // transposed kernel, both operands from shared memory
-        const size_t smem3 = 4 * (size_t)NP * TcDense3::kPiece + 1024;
-        PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        tc_dense3_kernel<NP><<<grid2, TcDense3::kThreads, smem3, st>>>(a);
+        // transposed kernel, both operands from shared memory; two channel tiles per CTA where the operands are small enough (fp16x2)
+        // and the halved grid still covers half of the SMs.  (Pairing always: +0.6 % clouds/s with four batches in flight -- SM-time
+        // per output drops -- but SA3 alone 63 -> 76 us, so small grids keep one tile per CTA.)
+        const bool pair = NP == 2 && (a.N % 256) == 0 && a.stat_partial == nullptr && (long long)grid2.x * (a.N / 256) >= kNumSMs / 2;
+        if (pair) {
+            constexpr int CPn = NP == 2 ? 2 : 1;
+            const size_t smem3 = (2 * CPn + 2) * (size_t)NP * TcDense3::kPiece + 1024;
+            grid2.y = a.N / (128 * CPn);
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel<NP, CPn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            tc_dense3_kernel<NP, CPn><<<grid2, TcDense3::kThreads, smem3, st>>>(a);
+        } else {
+            const size_t smem3 = 4 * (size_t)NP * TcDense3::kPiece + 1024;
+            PSA_CUDA(cudaFuncSetAttribute(tc_dense3_kernel<NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            tc_dense3_kernel<NP, 1><<<grid2, TcDense3::kThreads, smem3, st>>>(a);
+        }
     } else {
         const size_t smem2 = 4 * (size_t)tc_block_bytes(Nt, NP) + 1024;      // two slots of two 64-K blocks
         if (Nt == 128) {

@@ -46,7 +46,7 @@ def _kernels(sass, pattern):
     return ks
 
 
-@pytest.mark.parametrize("pattern,fixed", [("tc_sa_dual_kernel", 90), ("tc_dense3_kernel", 8), ("tc_dense2_kernel", 8)])
+@pytest.mark.parametrize("pattern,fixed", [("tc_sa_dual_kernel", 90), ("tc_dense3_kernel", 20), ("tc_dense2_kernel", 8)])
 def test_mma_issue_stays_on_the_uniform_datapath(sass, pattern, fixed):
     """R2UR count <= the kernel's fixed set-up moves + one per UTCHMMA.  (Healthy: dual 80-120 R2UR for 36-144 UTCHMMA, dense
     16-18 for 12-72; broken: 4-5 R2UR per UTCHMMA on top.)  Both operand splits (fp16x2: half the MMAs) are instantiated."""
