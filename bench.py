@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="batches kept in flight (1 = strictly one step at a time)")
+    ap.add_argument("--streams", type=int, default=6, help="batches kept in flight (1 = strictly one step at a time; measured 4: 93.9 k, 6: 95.8 k, 8: 95.4 k clouds/s)")
     ap.add_argument("--no-extra", action="store_true", help="skip the BGA / DGCNN / single-op / sweep measurements")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--train-steps", type=int, default=20)
