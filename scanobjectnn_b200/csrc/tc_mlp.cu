@@ -195,6 +195,45 @@ __device__ __forceinline__ void store_a_at(uint32_t a1, float (&h)[32], uint32_t
     }
 }
 
+// the same for activations held as 16 float2 (the dual kernel's row work runs on the packed FFMA2 / FADD2 pipe: two channels per
+// instruction); the fp16 residual h - f32(a1) is one FFMA2 with (-1, -1)
+template <int NP>
+__device__ __forceinline__ void store_a2_at(uint32_t a1, float2 (&h)[16], uint32_t ps, uint32_t& ovf) {
+    uint32_t p[16];
+    if constexpr (NP == 3) {
+        (void)ovf;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            p[q] = pack_bf16x2(h[q].x, h[q].y);
+            h[q].x -= __uint_as_float(p[q] << 16);
+            h[q].y -= __uint_as_float(p[q] & 0xffff0000u);
+        }
+        tmem_st16(a1, p);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            p[q] = pack_bf16x2(h[q].x, h[q].y);
+            h[q].x -= __uint_as_float(p[q] << 16);
+            h[q].y -= __uint_as_float(p[q] & 0xffff0000u);
+        }
+        tmem_st16(a1 + ps, p);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p[q] = pack_bf16x2(h[q].x, h[q].y);
+        tmem_st16(a1 + 2 * ps, p);
+    } else {
+        const float2 neg1 = make_float2(-1.f, -1.f);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            p[q] = pack_f16x2(h[q].x, h[q].y);
+            track_f16x2(ovf, p[q]);
+            h[q] = __ffma2_rn(unpack_f16x2(p[q]), neg1, h[q]);       // exact: a product with -1, then one rounding of the difference
+        }
+        tmem_st16(a1, p);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p[q] = pack_f16x2(h[q].x, h[q].y);
+        tmem_st16(a1 + ps, p);
+    }
+}
+
 // issuer warp (converged): D[128 x NT_] (+)= sum over the piece pairs of Split<NP>, KC blocks of 64 input channels.
 // a1_col: TMEM column of piece 1 of the A operand (pieces PS columns apart); d_col: accumulator (overwritten by the first MMA).
 template <int KC, int NT_, int PS, int NP>
@@ -266,16 +305,16 @@ __host__ __device__ inline TcDualLayout tc_dual_layout(const TcArgs& a) {
 // depends on the same row of A only, validity is per NEIGHBOURHOOD (K divides the tile), and outputs of neighbourhoods past the end are
 // never stored; their layer-1 inputs are zeros, so they carry finite values (no spurious range flag either).
 __device__ __forceinline__ void affine_chunk(const uint32_t (&d)[32], const float* __restrict__ sc_, const float* __restrict__ sh_, int relu,
-                                             float (&h)[32]) {
+                                             float2 (&h)[16]) {
     const float4* s4 = reinterpret_cast<const float4*>(sc_);
     const float4* t4 = reinterpret_cast<const float4*>(sh_);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 sc = s4[q], sh = t4[q];
-        float v0 = fmaf(__uint_as_float(d[4 * q + 0]), sc.x, sh.x), v1 = fmaf(__uint_as_float(d[4 * q + 1]), sc.y, sh.y);
-        float v2 = fmaf(__uint_as_float(d[4 * q + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(d[4 * q + 3]), sc.w, sh.w);
-        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-        h[4 * q + 0] = v0; h[4 * q + 1] = v1; h[4 * q + 2] = v2; h[4 * q + 3] = v3;
+        float2 v0 = __ffma2_rn(make_float2(__uint_as_float(d[4 * q + 0]), __uint_as_float(d[4 * q + 1])), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+        float2 v1 = __ffma2_rn(make_float2(__uint_as_float(d[4 * q + 2]), __uint_as_float(d[4 * q + 3])), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+        if (relu) { v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); }
+        h[2 * q] = v0; h[2 * q + 1] = v1;
     }
 }
 
@@ -439,29 +478,30 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 dx = __ldg(p) - __ldg(c); dy = __ldg(p + 1) - __ldg(c + 1); dz = __ldg(p + 2) - __ldg(c + 2);
                 if (a.uf) urow = a.uf + ((size_t)bi * a.n + j) * a.C1;
             }
+            const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
             for (int ch = cs; ch < a.C1 / 32; ch += 2) {
-                float h[32];
+                float2 h[16];                         // 32 channels, two per register pair: the chain below runs on the FFMA2 pipe
                 if (urow) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 u = __ldg(reinterpret_cast<const float4*>(urow + ch * 32) + q);
-                        h[4 * q] = u.x; h[4 * q + 1] = u.y; h[4 * q + 2] = u.z; h[4 * q + 3] = u.w;
+                        h[2 * q] = make_float2(u.x, u.y); h[2 * q + 1] = make_float2(u.z, u.w);
                     }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) h[q] = 0.f;
+                    for (int q = 0; q < 16; ++q) h[q] = make_float2(0.f, 0.f);
                 }
                 if (a.w1c != nullptr) {       // EdgeConv: the part of the first layer that acts on the centre x_i
+                    const float2 cx2 = make_float2(cx, cx), cy2 = make_float2(cy, cy), cz2 = make_float2(cz, cz);
                     const float4* cx4 = reinterpret_cast<const float4*>(w1c + ch * 32);
                     const float4* cy4 = reinterpret_cast<const float4*>(w1c + a.C1 + ch * 32);
                     const float4* cz4 = reinterpret_cast<const float4*>(w1c + 2 * a.C1 + ch * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 wx = cx4[q], wy = cy4[q], wz = cz4[q];
-                        h[4 * q + 0] = fmaf(cz, wz.x, fmaf(cy, wy.x, fmaf(cx, wx.x, h[4 * q + 0])));
-                        h[4 * q + 1] = fmaf(cz, wz.y, fmaf(cy, wy.y, fmaf(cx, wx.y, h[4 * q + 1])));
-                        h[4 * q + 2] = fmaf(cz, wz.z, fmaf(cy, wy.z, fmaf(cx, wx.z, h[4 * q + 2])));
-                        h[4 * q + 3] = fmaf(cz, wz.w, fmaf(cy, wy.w, fmaf(cx, wx.w, h[4 * q + 3])));
+                        h[2 * q] = __ffma2_rn(cz2, make_float2(wz.x, wz.y), __ffma2_rn(cy2, make_float2(wy.x, wy.y), __ffma2_rn(cx2, make_float2(wx.x, wx.y), h[2 * q])));
+                        h[2 * q + 1] = __ffma2_rn(cz2, make_float2(wz.z, wz.w),
+                                                  __ffma2_rn(cy2, make_float2(wy.z, wy.w), __ffma2_rn(cx2, make_float2(wx.z, wx.w), h[2 * q + 1])));
                     }
                 }
                 const float4* wx4 = reinterpret_cast<const float4*>(w1x + ch * 32);
@@ -472,14 +512,15 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float4 wx = wx4[q], wy = wy4[q], wz = wz4[q], sc = s4[q], sh = t4[q];
-                    float v0 = fmaf(fmaf(dz, wz.x, fmaf(dy, wy.x, fmaf(dx, wx.x, h[4 * q + 0]))), sc.x, sh.x);
-                    float v1 = fmaf(fmaf(dz, wz.y, fmaf(dy, wy.y, fmaf(dx, wx.y, h[4 * q + 1]))), sc.y, sh.y);
-                    float v2 = fmaf(fmaf(dz, wz.z, fmaf(dy, wy.z, fmaf(dx, wx.z, h[4 * q + 2]))), sc.z, sh.z);
-                    float v3 = fmaf(fmaf(dz, wz.w, fmaf(dy, wy.w, fmaf(dx, wx.w, h[4 * q + 3]))), sc.w, sh.w);
-                    if (a.relu1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                    h[4 * q + 0] = v0; h[4 * q + 1] = v1; h[4 * q + 2] = v2; h[4 * q + 3] = v3;      // rows past the end: see affine_chunk
+                    float2 v0 = __ffma2_rn(dz2, make_float2(wz.x, wz.y), __ffma2_rn(dy2, make_float2(wy.x, wy.y), __ffma2_rn(dx2, make_float2(wx.x, wx.y), h[2 * q])));
+                    float2 v1 = __ffma2_rn(dz2, make_float2(wz.z, wz.w),
+                                           __ffma2_rn(dy2, make_float2(wy.z, wy.w), __ffma2_rn(dx2, make_float2(wx.z, wx.w), h[2 * q + 1])));
+                    v0 = __ffma2_rn(v0, make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                    v1 = __ffma2_rn(v1, make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                    if (a.relu1) { v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); }
+                    h[2 * q] = v0; h[2 * q + 1] = v1;                    // rows past the end: see affine_chunk
                 }
-                store_a_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
+                store_a2_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
             }
         }
         tmem_st_wait();
@@ -491,7 +532,7 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
             if (l != last) {
                 // inner layer, one or two 64-wide tiles: the next A operand may only be written once ALL MMAs of this
                 // layer are done reading the current one, so the first tile's activations wait in registers
-                float h0[32], h1[32];
+                float2 h0[16], h1[16];
                 for (int nt = 0; nt < NT; ++nt) {
                     if (issuer) {
                         pipe_acquire(&s_token, lane);
@@ -512,8 +553,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], h1);
                     if (nt + 1 < NT) { fence_before_thread_sync(); group_bar(g); }       // D drained before the next tile lands in it
                 }
-                store_a_at<NP>(row_taddr + a1_col + cs * 16, h0, a_ps, ovf);
-                if (NT == 2) store_a_at<NP>(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps, ovf);
+                store_a2_at<NP>(row_taddr + a1_col + cs * 16, h0, a_ps, ovf);
+                if (NT == 2) store_a2_at<NP>(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps, ovf);
                 tmem_st_wait();
                 fence_before_thread_sync();
                 group_bar(g);
@@ -532,7 +573,10 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(d[q]);
                     } else {
-                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], v);
+                        float2 v2[16];
+                        affine_chunk(d, sl[l] + nt * kNt + cs * 32, tl[l] + nt * kNt + cs * 32, a.relu[l], v2);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) { v[2 * q] = v2[q].x; v[2 * q + 1] = v2[q].y; }
                     }
                     float mx = warp_colmax_32x32(v, lane);
                     if (quarters_per_group > 1) {
