@@ -397,7 +397,13 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
         for (int l = 0; l < a.nl; ++l) { sl[l] = p; tl[l] = p + a.Ntot[l]; p += 2 * a.Ntot[l]; }
     }
     float* w1c = t1 + a.C1;
-    for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) { w1x[i] = __ldg(a.w1x + i); w1c[i] = a.w1c ? __ldg(a.w1c + i) : 0.f; }
+    // the BN scale of layer 1 is folded into its xyz / centre weights (s (U + d.W) + t = (s U + t) + d.(s W)): one FFMA2 less per channel
+    // pair and, for levels without input features, no accumulator to clear
+    for (int i = tid; i < 3 * a.C1; i += TcDual::kThreads) {
+        const float sc = a.s1 ? __ldg(a.s1 + i % a.C1) : 1.f;
+        w1x[i] = __ldg(a.w1x + i) * sc;
+        w1c[i] = a.w1c ? __ldg(a.w1c + i) * sc : 0.f;
+    }
     for (int i = tid; i < a.C1; i += TcDual::kThreads) { s1[i] = a.s1 ? __ldg(a.s1 + i) : 1.f; t1[i] = __ldg(a.t1 + i); }
     if (tid == 0) { s_nonneg = 1; s_token = 0; }
     __syncthreads();
@@ -481,15 +487,22 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
             const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
             for (int ch = cs; ch < a.C1 / 32; ch += 2) {
                 float2 h[16];                         // 32 channels, two per register pair: the chain below runs on the FFMA2 pipe
+                const float4* s4 = reinterpret_cast<const float4*>(s1 + ch * 32);
+                const float4* t4 = reinterpret_cast<const float4*>(t1 + ch * 32);
                 if (urow) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 u = __ldg(reinterpret_cast<const float4*>(urow + ch * 32) + q);
-                        h[2 * q] = make_float2(u.x, u.y); h[2 * q + 1] = make_float2(u.z, u.w);
+                        const float4 sc = s4[q], sh = t4[q];
+                        h[2 * q] = __ffma2_rn(make_float2(u.x, u.y), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                        h[2 * q + 1] = __ffma2_rn(make_float2(u.z, u.w), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
                     }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) h[q] = make_float2(0.f, 0.f);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 sh = t4[q];
+                        h[2 * q] = make_float2(sh.x, sh.y); h[2 * q + 1] = make_float2(sh.z, sh.w);
+                    }
                 }
                 if (a.w1c != nullptr) {       // EdgeConv: the part of the first layer that acts on the centre x_i
                     const float2 cx2 = make_float2(cx, cx), cy2 = make_float2(cy, cy), cz2 = make_float2(cz, cz);
@@ -507,16 +520,12 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                 const float4* wx4 = reinterpret_cast<const float4*>(w1x + ch * 32);
                 const float4* wy4 = reinterpret_cast<const float4*>(w1x + a.C1 + ch * 32);
                 const float4* wz4 = reinterpret_cast<const float4*>(w1x + 2 * a.C1 + ch * 32);
-                const float4* s4 = reinterpret_cast<const float4*>(s1 + ch * 32);
-                const float4* t4 = reinterpret_cast<const float4*>(t1 + ch * 32);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 wx = wx4[q], wy = wy4[q], wz = wz4[q], sc = s4[q], sh = t4[q];
+                    const float4 wx = wx4[q], wy = wy4[q], wz = wz4[q];
                     float2 v0 = __ffma2_rn(dz2, make_float2(wz.x, wz.y), __ffma2_rn(dy2, make_float2(wy.x, wy.y), __ffma2_rn(dx2, make_float2(wx.x, wx.y), h[2 * q])));
                     float2 v1 = __ffma2_rn(dz2, make_float2(wz.z, wz.w),
                                            __ffma2_rn(dy2, make_float2(wy.z, wy.w), __ffma2_rn(dx2, make_float2(wx.z, wx.w), h[2 * q + 1])));
-                    v0 = __ffma2_rn(v0, make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
-                    v1 = __ffma2_rn(v1, make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
                     if (a.relu1) { v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); }
                     h[2 * q] = v0; h[2 * q + 1] = v1;                    // rows past the end: see affine_chunk
                 }
