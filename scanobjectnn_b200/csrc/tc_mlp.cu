@@ -29,6 +29,7 @@
 //   NP = 3 (psa_set_mlp_mode(2), the guarded rerun, the training forward): three bf16 pieces, six MMAs per product.
 // Levels the dual kernel cannot hold run on the fp32-FMA fused kernel of mlp.cu.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "mlp_internal.cuh"
@@ -81,6 +82,7 @@ struct TcArgs {
     unsigned int* tile_counter;   // zeroed before the launch: tiles are handed out dynamically (CTAs that start late or
                                   // share their SM with another stream's kernels simply take fewer)
     int np;                       // operand pieces: 2 (fp16x2) or 3 (bf16x3)
+    int tmode;                    // 1: the last layer runs TRANSPOSED (tc_sa_dual_kernel<3, 2>, see dual_dcol): lane = channel
     unsigned int* ovf;            // np = 2: set to 1 when an activation or weight left the fp16 range (the result is then invalid)
     const unsigned int* run_if;   // non-null: the launch is a no-op unless *run_if != 0 (the np = 3 rerun of a flagged launch)
     const unsigned int* wflag[kMaxTcLayers];   // np = 2: trailer word of each weight image
@@ -234,6 +236,31 @@ __device__ __forceinline__ void store_a2_at(uint32_t a1, float2 (&h)[16], uint32
     }
 }
 
+// tmode: 32 activations of row `row` (input channels [k0, k0 + 32)) split into NP pieces and written as the B operand of the transposed
+// last layer: [128 rows][64 k] K-major SWIZZLE_128B per piece (16 KB), four 16-byte chunks per piece (conflict-free per quarter warp)
+template <int NP>
+__device__ __forceinline__ void store_h_smem(uint8_t* hbase, int row, int k0, float2 (&h)[16], uint32_t& ovf) {
+    static_assert(NP == 2, "the transposed mode is instantiated for fp16x2 operands");
+    uint32_t p[16];
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    const uint32_t rbase = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        p[q] = pack_f16x2(h[q].x, h[q].y);
+        track_f16x2(ovf, p[q]);
+        h[q] = __ffma2_rn(unpack_f16x2(p[q]), neg1, h[q]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(hbase + rbase + ((((uint32_t)(k0 >> 3) + j) ^ (uint32_t)(row & 7)) << 4)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q] = pack_f16x2(h[q].x, h[q].y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(hbase + 16384u + rbase + ((((uint32_t)(k0 >> 3) + j) ^ (uint32_t)(row & 7)) << 4)) =
+            make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+}
+
 // issuer warp (converged): D[128 x NT_] (+)= sum over the piece pairs of Split<NP>, KC blocks of 64 input channels.
 // a1_col: TMEM column of piece 1 of the A operand (pieces PS columns apart); d_col: accumulator (overwritten by the first MMA).
 template <int KC, int NT_, int PS, int NP>
@@ -257,10 +284,14 @@ __device__ __forceinline__ void issue_tile_c(uint32_t tmem_base, uint32_t d_col,
 //   0  one D slot:            D 0..63 | A pieces 64 columns apart from 64
 //   1  levels whose layers are all <= 64 wide: D slots 0 and 64 | A pieces 32 columns apart from 128
 //   2  two-piece operands (NP = 2) of 128-wide layers leave 192..255 free: D slots 0 and 192 | A pieces at 64 and 128
+//   3  64-wide levels whose last layer is 128 wide, NP = 2: inner layer as in mode 1 (D 0..63, A pieces from 128); the LAST layer runs
+//      transposed, D^T[128 channels][128 rows] at 0..127 = W^T (A operand, shared memory) x H^T (B operand, shared memory, written by
+//      the previous epilogue) -- lane = channel: the max-pool is an in-thread reduction, the affine a per-thread scalar, the output
+//      store a coalesced 128-byte row segment
 template <int DB> __device__ __forceinline__ constexpr uint32_t dual_dcol(int dslot) { return dslot == 0 ? 0u : (DB == 2 ? 192u : 64u); }
 template <int NP, int DB>
 __device__ __forceinline__ void issue_tile(uint32_t gbase, uint32_t blocks_addr, int KC, int dslot) {
-    if constexpr (DB == 1) {
+    if constexpr (DB == 1 || DB == 3) {
         if (dslot == 0) issue_tile_c<1, TcDual::kNt, 32, NP>(gbase, 0, 128, blocks_addr);
         else issue_tile_c<1, TcDual::kNt, 32, NP>(gbase, 64, 128, blocks_addr);
     } else if constexpr (DB == 2) {
@@ -278,6 +309,7 @@ __device__ __forceinline__ void issue_tile(uint32_t gbase, uint32_t blocks_addr,
 }
 
 struct TcDualLayout {
+    uint32_t hbuf[2];            // tmode: per group, the last layer's B operand [128 rows][64 k] K-major SWIZZLE_128B, np pieces of 16 KB
     uint32_t w[kMaxTcLayers];    // resident layers
     uint32_t ring[2];            // per-group ring (one 64-channel tile of the streamed last layer)
     uint32_t ring_bytes;
@@ -294,6 +326,8 @@ __host__ __device__ inline TcDualLayout tc_dual_layout(const TcArgs& a) {
     L.ring_bytes = a.stream_last ? (uint32_t)(a.Kd[a.nl - 1] / 64) * tc_block_bytes(TcDual::kNt, a.np) : 0u;
     L.ring[0] = off; off += L.ring_bytes;
     L.ring[1] = off; off += L.ring_bytes;
+    L.hbuf[0] = off; if (a.tmode) off += (uint32_t)a.np * 16384u;
+    L.hbuf[1] = off; if (a.tmode) off += (uint32_t)a.np * 16384u;
     L.vec = off;
     off += 8u * a.C1 * 4u;       // w1x (3 C1), s1, t1, w1c (3 C1)
     for (int l = 0; l < a.nl; ++l) off += 2u * a.Ntot[l] * 4u;
@@ -440,7 +474,8 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
     const uint32_t tmem_base = warp_uniform(s_tmem) + (uint32_t)g * TcDual::kGroupCols;
     const uint32_t row_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t phase = 0, phase2 = 0;
-    constexpr uint32_t a1_col = DB == 1 ? 128u : TcDual::A1, a_ps = DB == 1 ? 32u : 64u;
+    constexpr uint32_t a1_col = (DB == 1 || DB == 3) ? 128u : TcDual::A1, a_ps = (DB == 1 || DB == 3) ? 32u : 64u;
+    uint8_t* hbuf = base + L.hbuf[g];           // DB == 3: B operand of the transposed last layer
     const bool pool_first = s_nonneg != 0;    // relu(s*d + t) is non-decreasing in d when s >= 0: max over rows commutes with it
     bool have_geo = false;                    // s_geo[g] holds this tile's geometry (written during the previous tile)
 
@@ -529,9 +564,15 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     if (a.relu1) { v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); }
                     h[2 * q] = v0; h[2 * q + 1] = v1;                    // rows past the end: see affine_chunk
                 }
-                store_a2_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
+                if constexpr (DB == 3) {
+                    if (a.nl == 1) store_h_smem<NP>(hbuf, row, ch * 32, h, ovf);      // layer 1 feeds the transposed layer directly
+                    else store_a2_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
+                } else {
+                    store_a2_at<NP>(row_taddr + a1_col + ch * 16, h, a_ps, ovf);
+                }
             }
         }
+        if constexpr (DB == 3) fence_proxy_async_smem();
         tmem_st_wait();
         fence_before_thread_sync();
         group_bar(g);
@@ -562,12 +603,92 @@ tc_sa_dual_kernel(const __grid_constant__ TcArgs a) {
                     else affine_chunk(d, sl[l] + kNt + cs * 32, tl[l] + kNt + cs * 32, a.relu[l], h1);
                     if (nt + 1 < NT) { fence_before_thread_sync(); group_bar(g); }       // D drained before the next tile lands in it
                 }
-                store_a2_at<NP>(row_taddr + a1_col + cs * 16, h0, a_ps, ovf);
-                if (NT == 2) store_a2_at<NP>(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps, ovf);
+                if constexpr (DB == 3) {
+                    store_h_smem<NP>(hbuf, row, cs * 32, h0, ovf);                    // NT == 1: the inner layer of this mode is 64 wide
+                    fence_proxy_async_smem();
+                } else {
+                    store_a2_at<NP>(row_taddr + a1_col + cs * 16, h0, a_ps, ovf);
+                    if (NT == 2) store_a2_at<NP>(row_taddr + a1_col + (2 + cs) * 16, h1, a_ps, ovf);
+                }
                 tmem_st_wait();
                 fence_before_thread_sync();
                 group_bar(g);
                 TC_STAMP(3);
+            } else if constexpr (DB == 3) {
+                // ---- last layer, transposed: D^T[128 ch][128 rows] = W^T . H^T, both operands from shared memory ----
+                if (issuer) {
+                    pipe_acquire(&s_token, lane);
+                    fence_after_thread_sync();
+                    const uint32_t idesc = make_idesc(Split<NP>::kFmt, 128, 128);
+                    const SmemDescBase wa = smem_desc_base(warp_uniform(smem_u32(base + L.w[l])));
+                    const SmemDescBase hb = smem_desc_base(warp_uniform(smem_u32(hbuf)));
+                    const uint32_t dT = warp_uniform(tmem_base);
+#pragma unroll
+                    for (int t = 0; t < Split<NP>::kTerms; ++t)
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; ++s4)
+                            mma_bf16_ss(dT, smem_desc_at(wa, Split<NP>::w(t) * 16384u + s4 * 32), smem_desc_at(hb, Split<NP>::a(t) * 16384u + s4 * 32), idesc,
+                                        (t | s4) ? 1u : 0u);
+                    mma_commit(&s_mbar[g]);
+                    pipe_release(&s_token, lane);
+                }
+                TC_STAMP(4);
+                {
+                    // the next tile's index -> point -> offset chain (two dependent L2 round trips) runs under these MMAs
+                    const long long ntile = (long long)s_tile[g][tpar];
+                    have_geo = ntile < ntiles;
+                    if (have_geo && cs == 0) {
+                        const long long ngid = ntile * G + row / a.K;
+                        float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ngid < a.groups) {
+                            const long long bi = ngid / a.m;
+                            const int j = __ldg(a.idx + ngid * a.K + (row % a.K));
+                            const float* p = a.xyz + ((size_t)bi * a.n + j) * 3;
+                            const float* c = a.new_xyz + (size_t)ngid * 3;
+                            gq.x = __ldg(p) - __ldg(c); gq.y = __ldg(p + 1) - __ldg(c + 1); gq.z = __ldg(p + 2) - __ldg(c + 2);
+                            gq.w = __int_as_float((int)(bi * a.n + j));
+                        }
+                        s_geo[g][row] = gq;
+                    }
+                }
+                mbar_wait(&s_mbar[g], phase);
+                phase ^= 1u;
+                fence_after_thread_sync();
+                TC_STAMP(5);
+                {
+                    // lane = channel (32 quarter + lane); this warp's half of the rows = columns [64 cs, 64 cs + 64): 64 / K neighbourhoods
+                    const int chn = quarter * 32 + lane;
+                    const float sc = sl[l][chn], sh = tl[l][chn];
+                    const int npg = 64 / a.K;                                        // K = 32: two neighbourhoods per half, K = 64: one
+                    for (int j = 0; j < npg; ++j) {
+                        float mx = -FLT_MAX;
+                        for (int c = 0; c < a.K / 32; ++c) {
+                            uint32_t d[32];
+                            tmem_ld32(row_taddr + (uint32_t)(cs * 64 + j * a.K + c * 32), d);
+                            tmem_ld_wait();
+                            if (pool_first) {
+#pragma unroll
+                                for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(d[q]));
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 32; ++q) {
+                                    float v = fmaf(__uint_as_float(d[q]), sc, sh);
+                                    if (a.relu[l]) v = fmaxf(v, 0.f);
+                                    mx = fmaxf(mx, v);
+                                }
+                            }
+                        }
+                        if (pool_first) {
+                            mx = fmaf(mx, sc, sh);
+                            if (a.relu[l]) mx = fmaxf(mx, 0.f);
+                        }
+                        const long long og = g0 + cs * npg + j;
+                        if (og < a.groups) a.out[(size_t)og * a.Ntot[l] + chn] = mx;      // 32 lanes = 128 contiguous bytes
+                    }
+                }
+                fence_before_thread_sync();
+                group_bar(g);
+                TC_STAMP(6);
             } else {
                 const bool streamed = a.stream_last != 0;
                 const int quarters_per_group = a.K / 32;        // 1, 2 or 4
@@ -1342,6 +1463,13 @@ static const uint8_t* prebuilt_image(const psa_mlp* mlp, int l, int row0, int Nt
     return nullptr;
 }
 
+// PSA_SA_TMODE=0 keeps the last layer of 64-wide levels in row form (A/B runs)
+static bool tmode_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PSA_SA_TMODE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 // Can this MLP / geometry run on the tensor-core kernel with `np` pieces per operand?  (otherwise the fp32-FMA fused kernel
 // in mlp.cu is used).  Whatever fits with three pieces fits with two; the guarded default needs both.
 bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out, int np) {
@@ -1364,9 +1492,16 @@ bool tc_sa_eligible(const psa_mlp* mlp, int c, int nsample, TcArgs* out, int np)
     }
     // two row groups per CTA, 64-wide tiles; the last layer is streamed per group if it does not fit; a level that does not fit
     // even then runs on the fp32-FMA fused kernel
-    a.dual = 1; a.ntcap = 64; a.stream_last = 0;
+    a.dual = 1; a.ntcap = 64; a.stream_last = 0; a.tmode = 0;
     if (tc_dual_layout(a).total + 1024 > 226u * 1024u) a.stream_last = 1;
     if (tc_dual_layout(a).total + 1024 > 226u * 1024u) return false;
+    // transposed last layer (lane = channel): 64-wide levels ending in a 128-wide layer, fp16x2 operands, whole neighbourhoods per half tile
+    bool t = np == 2 && !a.stream_last && C1 == 64 && a.Ntot[a.nl - 1] == 128 && (nsample == 32 || nsample == 64) && tmode_enabled();
+    for (int l = 0; l < a.nl; ++l) t = t && a.Kd[l] == 64;
+    if (t) {
+        a.tmode = 1;
+        if (tc_dual_layout(a).total + 1024 > 226u * 1024u) a.tmode = 0;
+    }
     *out = a;
     return true;
 }
@@ -1385,8 +1520,9 @@ size_t tc_sa_workspace_bytes(const TcArgs& a, int b, int n, int c) {
     return bytes;
 }
 
-// tile width (with the image-format flag of the current split) of the tensor layers of a level
-static int tc_sa_image_nt() { return TcDual::kNt | image_flag(g_tc_np); }
+// tile width (with the image-format flag of the current split) of tensor layer l of a level: 64-wide blocks, except the last layer of
+// a transposed-mode level, which is the A operand of an M = 128 MMA (one [128 ch][64 k] block)
+static int tc_sa_image_nt(const TcArgs& a, int l) { return ((a.tmode && l == a.nl - 1) ? 128 : TcDual::kNt) | image_flag(g_tc_np); }
 
 template <int NP>
 static int launch_tc_sa_np(TcArgs& a, cudaStream_t st) {
@@ -1396,6 +1532,13 @@ static int launch_tc_sa_np(TcArgs& a, cudaStream_t st) {
     long long ctas = (ntiles + 1) / 2;
     if (ctas > kNumSMs) ctas = kNumSMs;
     if (ctas < 1) ctas = 1;
+    if (a.tmode) {
+        if constexpr (NP == 2) {
+            PSA_CUDA(cudaFuncSetAttribute(tc_sa_dual_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_sa_dual_kernel<3, 2><<<(int)ctas, TcDual::kThreads, smem, st>>>(a);
+            return check_launch("tc_sa_dual_kernel");
+        }
+    }
     const bool pairs = !a.stream_last && (a.Ntot[a.nl - 1] % 128) == 0;            // tile pairs: an even number of resident 64-wide tiles
     bool narrow = a.C1 <= 64;
     for (int l = 0; l < a.nl; ++l) narrow = narrow && a.Kd[l] <= 64;
@@ -1453,8 +1596,8 @@ static int tc_sa_run(TcArgs& a, int b, int n, int m, int c, int nsample, const f
         for (int l = 0; l < t.nl; ++l) { t.s[l] = mlp->scale[1 + l]; t.t[l] = mlp->shift[1 + l]; t.relu[l] = mlp->relu[1 + l]; t.wflag[l] = nullptr; }
     };
     fill(a);
-    const int nt_img = tc_sa_image_nt();
     for (int l = 0; l < a.nl; ++l) {
+        const int nt_img = tc_sa_image_nt(a, l);
         const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, nt_img);
         uint8_t* own = a.np == 2 ? img2[l] : img3[l];
         if (pre == nullptr) { rc = build_image(a.Kd[l], a.Kd[l], a.Ntot[l], nt_img, mlp->weight[1 + l], own, st); if (rc != PSA_OK) return rc; }
@@ -1471,7 +1614,9 @@ static int tc_sa_run(TcArgs& a, int b, int n, int m, int c, int nsample, const f
     PSA_REQUIRE(tc_sa_eligible(mlp, c, nsample, &a3, 3), "sa_module: internal error (bf16x3 eligibility)");
     fill(a3);
     for (int l = 0; l < a3.nl; ++l) {
-        const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, nt_img);       // carries its bf16x3 twin behind the fp16x2 blocks
+        // a prebuilt fp16x2 image carries its bf16x3 twin behind it -- usable here if it has the 64-wide blocks of the row-form kernel
+        // (the last layer of a transposed-mode level does not: its twin is rebuilt, conditionally)
+        const uint8_t* pre = prebuilt_image(mlp, 1 + l, 0, TcDual::kNt | kImageF16x2);
         if (pre != nullptr) {
             a3.image[l] = pre + tc_image_alloc_bytes(a3.Kd[l], a3.Ntot[l], 2);
         } else {
@@ -1834,7 +1979,7 @@ extern "C" int psa_mlp_image_plan(int usage, long long rows, int pool_k, int c, 
     TcArgs a;
     if (!tc_sa_eligible(mlp, c, nsample, &a)) return PSA_OK;
     if (c > 0 && tc_dense_eligible(rows, c, a.C1, 1)) { nt[0] = tc_dense_nt(a.C1); row0[0] = 3; bytes[0] = tc_plan_image_bytes((c + 63) & ~63, a.C1); }
-    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(); row0[1 + l] = 0; bytes[1 + l] = tc_plan_image_bytes(a.Kd[l], a.Ntot[l]); }
+    for (int l = 0; l < a.nl; ++l) { nt[1 + l] = tc_sa_image_nt(a, l); row0[1 + l] = 0; bytes[1 + l] = tc_plan_image_bytes(a.Kd[l], a.Ntot[l]); }
     return PSA_OK;
 }
 
