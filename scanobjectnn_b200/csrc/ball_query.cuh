@@ -430,12 +430,12 @@ __device__ __forceinline__ int bq_extract_bitmap(unsigned* __restrict__ bitmap, 
     return cnt;
 }
 
-// Eight lanes per query, four queries per warp at once: the nsample lowest set bits of a bitmap of 8*WPS words (lane `sub`
+// LPQ lanes per query, 32/LPQ queries per warp at once: the nsample lowest set bits of a bitmap of LPQ*WPS words (lane `sub`
 // of the group owns words [sub*WPS, (sub+1)*WPS), read ONCE into registers) in ascending order -> idxrow[0..cnt), rest filled
 // with the first hit (0 if none).  Every lane of the warp must call (shuffles); groups with active == false do nothing else.
-template <int WPS>
-__device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict__ bitmap, int nsample, int* __restrict__ idxrow, int lane, bool active) {
-    const int sub = lane & 7;
+template <int LPQ, int WPS>
+__device__ __forceinline__ int bq_extract_bitmap_sub(const unsigned* __restrict__ bitmap, int nsample, int* __restrict__ idxrow, int lane, bool active) {
+    const int sub = lane & (LPQ - 1);
     unsigned w[WPS];
     int c = 0;
 #pragma unroll
@@ -445,17 +445,17 @@ __device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict
     }
     int incl = c;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o, 8);
+    for (int o = 1; o < LPQ; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o, LPQ);
         if (sub >= o) incl += v;
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 7, 8);
-    const unsigned have = (__ballot_sync(0xffffffffu, c > 0) >> (lane & 24)) & 0xffu;
+    const int total = __shfl_sync(0xffffffffu, incl, LPQ - 1, LPQ);
+    const unsigned have = (__ballot_sync(0xffffffffu, c > 0) >> (lane & (32 - LPQ))) & (LPQ == 32 ? 0xffffffffu : ((1u << (LPQ & 31)) - 1u));
     int firstbit = 0;
 #pragma unroll
     for (int i = WPS - 1; i >= 0; --i)
         if (w[i] != 0u) firstbit = (sub * WPS + i) * 32 + __ffs(w[i]) - 1;
-    const int first = __shfl_sync(0xffffffffu, firstbit, have ? __ffs(have) - 1 : 0, 8);
+    const int first = __shfl_sync(0xffffffffu, firstbit, have ? __ffs(have) - 1 : 0, LPQ);
     if (!active) return 0;
     int pos = incl - c;
 #pragma unroll
@@ -469,8 +469,12 @@ __device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict
     }
     const int cnt = min(total, nsample);
     const int fillv = have ? first : 0;
-    for (int l = cnt + sub; l < nsample; l += 8) idxrow[l] = fillv;
+    for (int l = cnt + sub; l < nsample; l += LPQ) idxrow[l] = fillv;
     return cnt;
+}
+template <int WPS>
+__device__ __forceinline__ int bq_extract_bitmap_sub8(const unsigned* __restrict__ bitmap, int nsample, int* __restrict__ idxrow, int lane, bool active) {
+    return bq_extract_bitmap_sub<8, WPS>(bitmap, nsample, idxrow, lane, active);
 }
 
 }  // namespace psa

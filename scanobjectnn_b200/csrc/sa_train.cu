@@ -209,6 +209,15 @@ __host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, int np, int
     return (size_t)n * 16 + (size_t)kF1Batch * f1s_bitmap_words(np, pptp) * 4 + ring;
 }
 
+// packed f32x2 arithmetic on 64-bit registers (aligned pairs by construction: the compiler never has to shuffle halves)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f2_sub(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ void f2_unpack_bits(u64 v, unsigned& lo, unsigned& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+
 template <int NV, bool HAS_U, int NP, int PPTP>
 __global__ void __launch_bounds__(kF1SThreads, 2)       // (3 CTAs per SM at 80 registers spills the point registers: 63 vs 57 us)
 sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
@@ -230,7 +239,16 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
     ssum[0] = ssum[1] = ssq[0] = ssq[1] = make_float2(0.f, 0.f);
 
     const long long T = (long long)a.b * a.m;
-    const long long q_begin = T * blockIdx.x / gridDim.x, q_end = T * (blockIdx.x + 1) / gridDim.x;
+    // a grid that is a multiple of the batch size gives every cloud the same number of CTAs: no CTA crosses a cloud boundary (a
+    // crossing costs a second cloud load + pipeline ramp; those CTAs used to finish ~6 us after the others)
+    long long q_begin, q_end;
+    if (gridDim.x % a.b == 0) {
+        const int cpc = gridDim.x / a.b, cl = blockIdx.x / cpc, ci = blockIdx.x % cpc;
+        q_begin = (long long)cl * a.m + (long long)a.m * ci / cpc;
+        q_end = (long long)cl * a.m + (long long)a.m * (ci + 1) / cpc;
+    } else {
+        q_begin = T * blockIdx.x / gridDim.x; q_end = T * (blockIdx.x + 1) / gridDim.x;
+    }
     // batches this CTA will run in total (the consumers' last kF1Ring EMPTY arrivals have no taker and are skipped)
     int total_batches = 0;
     for (long long q = q_begin; q < q_end;) {
@@ -248,99 +266,145 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             const long long cloud = q / a.m;
             const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
             const float* gx = a.xyz + (size_t)cloud * n * 3;
-            // ---- this cloud: PPTP points per thread in registers (point k = 32*(warp + NP*i) + lane), float4 copy in smem ----
+            // ---- this cloud: PPTP CONSECUTIVE points per thread in registers (point k = PPTP*(32*warp + lane) + i) as packed
+            //      f32x2 pairs (points 2j, 2j+1), so the lane's hit mask IS bits [PPTP*(32*warp+lane), +PPTP) of the query's
+            //      bitmap -- no ballots, no transposition; float4 copy of the cloud in shared memory for the row builder ----
+            // first batch's query centres: in flight together with the cloud (lane i of every producer warp holds query i of a batch;
+            // the search reads them through shuffles, the row builder through shared memory)
+            long long gq0 = q;                                                             // global query id of the batch
+            float ncx = 0.f, ncy = 0.f, ncz = 0.f;
+            if (lane < min(f1s_batch_size(0), (int)(seg_end - gq0))) {
+                const float* p2 = a.new_xyz + (size_t)(gq0 + lane) * 3;
+                ncx = __ldg(p2); ncy = __ldg(p2 + 1); ncz = __ldg(p2 + 2);
+            }
             named_bar_sync(15, PT);                                          // the previous cloud's float4 copy is no longer read
-            float2 px[PPTP / 2], py[PPTP / 2], pz[PPTP / 2];
+            u64 px[PPTP / 2], py[PPTP / 2], pz[PPTP / 2];
             unsigned valid = 0u;
-            const float pinf = __int_as_float(0x7f800000);
+            const int k0 = PPTP * tid;                                       // tid = 32 * warp + lane < PT
+            if (((n & 3) | (int)(reinterpret_cast<uintptr_t>(a.xyz) & 15)) == 0) {
+                // one round trip: the lane's PPTP points are 3*PPTP/4 consecutive float4 (16-byte aligned: n % 4 == 0), all loads in
+                // flight at once; registers and the shared-memory copy are both filled from them
+                constexpr int CH = PPTP == 32 ? 2 : 1;                       // 32 points per thread: two halves of 12 float4
+                constexpr int PH = PPTP / CH;
+                const float4* g4 = reinterpret_cast<const float4*>(gx);
+                const int nf4 = n * 3 / 4;
 #pragma unroll
-            for (int i = 0; i < PPTP; ++i) {
-                const int k = 32 * (warp + NP * i) + lane;
-                float x = pinf, y = pinf, z = pinf;         // slots past the cloud: +inf, out of reach of every finite query
-                if (k < n) {
-                    x = __ldg(gx + 3 * k); y = __ldg(gx + 3 * k + 1); z = __ldg(gx + 3 * k + 2);
-                    cloud4[k] = make_float4(x, y, z, __int_as_float(k));
-                    valid |= 1u << i;
+                for (int hh = 0; hh < CH; ++hh) {
+                    float f[3 * PH];
+#pragma unroll
+                    for (int v = 0; v < 3 * PH / 4; ++v) {
+                        const int fi = (k0 + hh * PH) * 3 / 4 + v;
+                        const float4 t = fi < nf4 ? __ldg(g4 + fi) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[4 * v] = t.x; f[4 * v + 1] = t.y; f[4 * v + 2] = t.z; f[4 * v + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < PH; ++i) {
+                        const int k = k0 + hh * PH + i;
+                        if (k < n) { valid |= 1u << (hh * PH + i); cloud4[k] = make_float4(f[3 * i], f[3 * i + 1], f[3 * i + 2], __int_as_float(k)); }
+                    }
+#pragma unroll
+                    for (int j = 0; j < PH / 2; ++j) {
+                        px[hh * PH / 2 + j] = f2_pack(f[6 * j], f[6 * j + 3]);
+                        py[hh * PH / 2 + j] = f2_pack(f[6 * j + 1], f[6 * j + 4]);
+                        pz[hh * PH / 2 + j] = f2_pack(f[6 * j + 2], f[6 * j + 5]);
+                    }
                 }
-                if (i & 1) { px[i >> 1].y = x; py[i >> 1].y = y; pz[i >> 1].y = z; }
-                else { px[i >> 1].x = x; py[i >> 1].x = y; pz[i >> 1].x = z; }
+            } else {
+                for (int k = tid; k < n; k += PT)
+                    cloud4[k] = make_float4(__ldg(gx + 3 * k), __ldg(gx + 3 * k + 1), __ldg(gx + 3 * k + 2), __int_as_float(k));
+#pragma unroll
+                for (int j = 0; j < PPTP / 2; ++j) {
+                    float c[6];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = k0 + 2 * j + h;
+                        c[3 * h] = c[3 * h + 1] = c[3 * h + 2] = 0.f;       // slots past the cloud: masked out by `valid`
+                        if (k < n) {
+                            c[3 * h] = __ldg(gx + 3 * k); c[3 * h + 1] = __ldg(gx + 3 * k + 1); c[3 * h + 2] = __ldg(gx + 3 * k + 2);
+                            valid |= 1u << (2 * j + h);
+                        }
+                    }
+                    px[j] = f2_pack(c[0], c[3]); py[j] = f2_pack(c[1], c[4]); pz[j] = f2_pack(c[2], c[5]);
+                }
             }
             named_bar_sync(15, PT);
 #ifdef PSA_F1_TIMING
             if (tid == 0 && a.tlog && q == q_begin) a.tlog[blockIdx.x * 8 + 1] = gtime();
 #endif
-            long long gq0 = q;                                                             // global query id of the batch
+            const u64 thr2 = f2_pack(a.thr, a.thr);
+            // the NEXT batch's centres are fetched under the current search
             for (int bi = 0; gq0 < seg_end; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
-                if (ring_pos >= kF1Ring) named_bar_sync(1 + kF1Ring + slot, kF1SThreads);   // slot drained by the consumers
                 int* sidx = reinterpret_cast<int*>(ring + slot * slot_bytes);
                 float4* sd = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
                 const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
                 float4* sctr = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * (sizeof(int) + sizeof(float4)));
-                // the batch's query centres: lane i of every producer warp loads query i ONCE (one global round trip per batch,
-                // not one per query), the search reads them through shuffles, the row builder through shared memory
-                float cqx = 0.f, cqy = 0.f, cqz = 0.f;
-                if (lane < nqb) {
-                    const float* p2 = a.new_xyz + (size_t)(gq0 + lane) * 3;
-                    cqx = __ldg(p2); cqy = __ldg(p2 + 1); cqz = __ldg(p2 + 2);
-                    if (warp == 0) sctr[lane] = make_float4(cqx, cqy, cqz, 0.f);
+                const float cqx = ncx, cqy = ncy, cqz = ncz;
+                {
+                    const long long gq1 = gq0 + nqb;
+                    if (gq1 < seg_end && lane < min(f1s_batch_size(bi + 1), (int)(seg_end - gq1))) {
+                        const float* p2 = a.new_xyz + (size_t)(gq1 + lane) * 3;
+                        ncx = __ldg(p2); ncy = __ldg(p2 + 1); ncz = __ldg(p2 + 2);
+                    }
                 }
-                // ---- exhaustive test: one ballot per 32-point word = that word of the query's bitmap ----
+                if (ring_pos >= kF1Ring) named_bar_sync(1 + kF1Ring + slot, kF1SThreads);   // slot drained by the consumers
+                if (warp == 0 && lane < nqb) sctr[lane] = make_float4(cqx, cqy, cqz, 0.f);
+                // ---- exhaustive test on the packed f32x2 pipe: per point pair 3 FADD2 + FMUL2 + 2 FFMA2 (the reference's
+                //      distance) + one FADD2 s = thr - d + two funnel shifts that push the SIGN of s into the lane's mask.
+                //      sign(s) = 1 <=> d > thr; d == thr gives +0 and a NaN distance the canonical (positive) NaN, i.e. both
+                //      count as inside exactly like !(d > thr) (tf_grouping_g.cu:20-21: max(sqrtf(NaN),1e-20f) < r holds) ----
                 if (!a.none) {
                     for (int qi = 0; qi < nqb; ++qi) {
                         const float qx = __shfl_sync(0xffffffffu, cqx, qi), qy = __shfl_sync(0xffffffffu, cqy, qi), qz = __shfl_sync(0xffffffffu, cqz, qi);
-                        const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
-                        unsigned* bm = bitmaps + qi * BW;
-                        unsigned mine = 0u;                                  // lane i keeps word i of this warp's share, stored once
-                        const bool qfinite = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;   // warp-uniform
-                        if (qfinite) {
+                        const u64 nqx = f2_pack(-qx, -qx), nqy = f2_pack(-qy, -qy), nqz = f2_pack(-qz, -qz);
+                        unsigned acc[PPTP / 8];                              // 8 points per chain: four short dependency chains
 #pragma unroll
-                            for (int i = 0; i < PPTP; i += 2) {
-                                const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
-                                // !(d > thr): a NaN distance (NaN point) counts as inside, exactly like the reference's max(sqrtf(NaN),1e-20f) < r
-                                const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr));
-                                const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr));
-                                if (lane == i) mine = w0;
-                                if (lane == i + 1) mine = w1;
-                            }
-                        } else {
-                            // non-finite query: every distance is NaN = inside; only the slots past the cloud must be masked out
+                        for (int g = 0; g < PPTP / 8; ++g) acc[g] = 0u;
 #pragma unroll
-                            for (int i = 0; i < PPTP; i += 2) {
-                                const float2 d = bq_dist2_pair(px[i >> 1], py[i >> 1], pz[i >> 1], nqx, nqy, nqz);
-                                const unsigned w0 = __ballot_sync(0xffffffffu, !(d.x > a.thr) && ((valid >> i) & 1u));
-                                const unsigned w1 = __ballot_sync(0xffffffffu, !(d.y > a.thr) && ((valid >> (i + 1)) & 1u));
-                                if (lane == i) mine = w0;
-                                if (lane == i + 1) mine = w1;
-                            }
+                        for (int j = PPTP / 2 - 1; j >= 0; --j) {            // descending: point i ends up at bit i of its chain
+                            const u64 dx = f2_add(px[j], nqx), dy = f2_add(py[j], nqy), dz = f2_add(pz[j], nqz);
+                            u64 t = f2_mul(dy, dy);
+                            t = f2_fma(dx, dx, t);
+                            t = f2_fma(dz, dz, t);
+                            unsigned slo, shi;
+                            f2_unpack_bits(f2_sub(thr2, t), slo, shi);
+                            acc[j >> 2] = __funnelshift_l(shi, acc[j >> 2], 1);
+                            acc[j >> 2] = __funnelshift_l(slo, acc[j >> 2], 1);
                         }
-                        if (lane < PPTP) bm[warp + NP * lane] = mine;         // one store instruction per query and warp
+                        unsigned outside = acc[0];
+#pragma unroll
+                        for (int g = 1; g < PPTP / 8; ++g) outside |= acc[g] << (8 * g);
+                        const unsigned inside = ~outside & valid;
+                        uint8_t* bm = reinterpret_cast<uint8_t*>(bitmaps + qi * BW) + (32 * warp + lane) * (PPTP / 8);
+                        if (PPTP == 8) *bm = (uint8_t)inside;
+                        else if (PPTP == 16) *reinterpret_cast<unsigned short*>(bm) = (unsigned short)inside;
+                        else *reinterpret_cast<unsigned*>(bm) = inside;
                     }
                 }
                 named_bar_sync(15, PT);                                                     // bitmaps complete
 #ifdef PSA_F1_TIMING
                 if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 4] = gtime();
 #endif
-                // ---- bitmaps -> ordered idx rows: 8 lanes per query, 4 queries per warp pass ----
-                for (int q0 = warp * 4; q0 < kF1Batch; q0 += NP * 4) {
-                    const int qi = q0 + (lane >> 3);
+                // ---- bitmaps -> ordered idx rows -> centred rows: LPQ = 32*NP/kF1Batch lanes per query, every producer warp busy;
+                //      a query's lanes extract its nsample first hits in index order and (after a __syncwarp: the group lives in
+                //      one warp) build its K rows grouped_xyz - new_xyz (pointnet_util.py:46) + the source index for the U gather ----
+                {
+                    constexpr int LPQ = 32 * NP / kF1Batch;                                 // 16 (NP = 4) or 8 (NP = 2)
+                    const int qi = warp * (32 / LPQ) + lane / LPQ, sub = lane & (LPQ - 1);
                     const bool act = qi < nqb;
-                    const int cnt = bq_extract_bitmap_sub8<BW / 8>(bitmaps + qi * BW, K, sidx + qi * K, lane, act);
-                    if (act && a.pts_cnt != nullptr && (lane & 7) == 0) a.pts_cnt[gq0 + qi] = cnt;
-                }
-                named_bar_sync(15, PT);                                                     // idx rows complete
-#ifdef PSA_F1_TIMING
-                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 7] = gtime();
-#endif
-                // ---- grouped_xyz - new_xyz (pointnet_util.py:46) of the batch's rows + the source index for the U gather ----
-                const int nrows = nqb * K;
-                int* gidx = a.idx + (size_t)gq0 * K;
-                for (int r = tid; r < nrows; r += PT) {
-                    const int j = sidx[r];
-                    const float4 ctr = sctr[r / K];
-                    const float4 pt = cloud4[j];
-                    gidx[r] = j;
-                    sd[r] = make_float4(pt.x - ctr.x, pt.y - ctr.y, pt.z - ctr.z, __int_as_float(j));
+                    const int cnt = bq_extract_bitmap_sub<LPQ, BW / LPQ>(bitmaps + qi * BW, K, sidx + qi * K, lane, act);
+                    if (act && a.pts_cnt != nullptr && sub == 0) a.pts_cnt[gq0 + qi] = cnt;
+                    __syncwarp();
+                    if (act) {
+                        const float4 ctr = sctr[qi];
+                        int* gidx = a.idx + (size_t)(gq0 + qi) * K;
+                        for (int r = sub; r < K; r += LPQ) {
+                            const int j = sidx[qi * K + r];
+                            const float4 pt = cloud4[j];
+                            gidx[r] = j;
+                            sd[qi * K + r] = make_float4(pt.x - ctr.x, pt.y - ctr.y, pt.z - ctr.z, __int_as_float(j));
+                        }
+                    }
                 }
                 __threadfence_block();
                 named_bar_arrive(1 + slot, kF1SThreads);                                    // FULL
@@ -361,6 +425,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         const int cw = warp - NP;
         constexpr int LPR = NV * 8;                    // 16 (C1 = 64) or 32 (C1 = 128)
         constexpr int RPI = 32 / LPR;                  // rows per store instruction: 2 or 1
+        constexpr int C1c = NV * 32;                   // = a.C1 (the launcher picks NV = C1 / 32)
         const int lr = lane / LPR, lc = (lane % LPR) * 4;
         const float4 wx4 = __ldg(reinterpret_cast<const float4*>(a.w1 + lc));
         const float4 wy4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + lc));
@@ -381,24 +446,37 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                 const int nrows = nqb * K;
                 float* outl = a.pre + (size_t)gq0 * K * C1 + lc;
                 named_bar_sync(1 + slot, kF1SThreads);                                      // FULL
-                // four rows per lane and trip: independent chains, stores of a warp instruction contiguous
-                for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI) {
+                // four rows per lane and trip: independent chains, stores of a warp instruction contiguous; C1 is a compile-time
+                // constant (immediate store offsets, one pointer bump per trip); row guards only when nrows is not a multiple of 4*RPI
+                auto row = [&](const float4 d, float* dst) {
+                    float2 s0 = ba, s1 = bb;
+                    if (HAS_U) {
+                        const float4 uu = __ldg(reinterpret_cast<const float4*>(ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1c));
+                        s0 = __fadd2_rn(s0, make_float2(uu.x, uu.y)); s1 = __fadd2_rn(s1, make_float2(uu.z, uu.w));
+                    }
+                    const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+                    const float2 v0 = __ffma2_rn(dz, wza, __ffma2_rn(dy, wya, __ffma2_rn(dx, wxa, s0)));
+                    const float2 v1 = __ffma2_rn(dz, wzb, __ffma2_rn(dy, wyb, __ffma2_rn(dx, wxb, s1)));
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(v0.x, v0.y, v1.x, v1.y));
+                    ssum[0] = __fadd2_rn(ssum[0], v0); ssum[1] = __fadd2_rn(ssum[1], v1);
+                    ssq[0] = __ffma2_rn(v0, v0, ssq[0]); ssq[1] = __ffma2_rn(v1, v1, ssq[1]);
+                };
+                if ((nrows & (4 * RPI - 1)) == 0) {
+                    const float4* sp = sd + cw * 4 * RPI + lr;
+                    float* op = outl + (size_t)(cw * 4 * RPI + lr) * C1c;
+                    for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI, sp += NC * 4 * RPI, op += (size_t)NC * 4 * RPI * C1c) {
+                        float4 d[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = r0 + u * RPI + lr;
-                        if (r < nrows) {
-                            const float4 d = sd[r];
-                            const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
-                            float2 s0 = ba, s1 = bb;
-                            if (HAS_U) {
-                                const float4 uu = __ldg(reinterpret_cast<const float4*>(ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1));
-                                s0 = __fadd2_rn(s0, make_float2(uu.x, uu.y)); s1 = __fadd2_rn(s1, make_float2(uu.z, uu.w));
-                            }
-                            const float2 v0 = __ffma2_rn(dz, wza, __ffma2_rn(dy, wya, __ffma2_rn(dx, wxa, s0)));
-                            const float2 v1 = __ffma2_rn(dz, wzb, __ffma2_rn(dy, wyb, __ffma2_rn(dx, wxb, s1)));
-                            __stcs(reinterpret_cast<float4*>(outl + (unsigned)r * (unsigned)C1), make_float4(v0.x, v0.y, v1.x, v1.y));
-                            ssum[0] = __fadd2_rn(ssum[0], v0); ssum[1] = __fadd2_rn(ssum[1], v1);
-                            ssq[0] = __ffma2_rn(v0, v0, ssq[0]); ssq[1] = __ffma2_rn(v1, v1, ssq[1]);
+                        for (int u = 0; u < 4; ++u) d[u] = sp[u * RPI];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) row(d[u], op + u * RPI * C1c);
+                    }
+                } else {
+                    for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = r0 + u * RPI + lr;
+                            if (r < nrows) row(sd[r], outl + (size_t)r * C1c);
                         }
                     }
                 }
@@ -456,15 +534,15 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             const int e4 = tid % E4, rl = tid / E4;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const float4* part4 = reinterpret_cast<const float4*>(a.partial);
-            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 8 * RL) {
-                float4 v[8];
+            for (unsigned p0 = rl; p0 < gridDim.x; p0 += 16 * RL) {
+                float4 v[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
                     const unsigned p = p0 + u * RL;
                     v[u] = p < gridDim.x ? __ldcg(part4 + (size_t)p * E4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+                for (int u = 0; u < 16; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
             }
             double* sred = reinterpret_cast<double*>(ring);                // RL x 2*C1 doubles <= 8 KB (the ring is >= 15 KB)
 #pragma unroll
@@ -782,6 +860,8 @@ static bool f1s_plan(int b, int n, int m, int nsample, int* np, int* pptp, int* 
     const long long batches = (T + kF1Batch - 1) / kF1Batch;
     const long long per_sm = 2;                                                   // matches the kernel's __launch_bounds__
     *ctas = (int)(batches < per_sm * kNumSMs ? batches : per_sm * kNumSMs);
+    // a whole number of CTAs per cloud when that keeps >= 90 % of the CTA slots busy (the kernel then never crosses a cloud boundary)
+    if (b > 0 && *ctas >= b && (*ctas / b) * b * 10 >= *ctas * 9) *ctas = (*ctas / b) * b;
     return true;
 }
 static bool f1_want_grid(int n, int m) { return bq_grid_fits(n) && n >= 256 && m >= 32; }

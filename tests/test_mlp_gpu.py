@@ -203,7 +203,11 @@ def test_pointnet2_cls_ssg_matches_oracle(kind, mlp_mode):
                                                  # CTA ranges that cross cloud boundaries (grid rebuilt mid-CTA), odd nsample
                                                  ("ball", 500, 37, 0.3, 13, 0, 64, 41), ("shell", 700, 333, 0.25, 32, 7, 128, 5),
                                                  # scan mode (cloud too small for the grid) and a 4096-point cloud (16 points per thread)
-                                                 ("ball", 200, 20, 0.4, 16, 0, 64, 4), ("ball", 4096, 1024, 0.15, 32, 0, 64, 2)])
+                                                 ("ball", 200, 20, 0.4, 16, 0, 64, 4), ("ball", 4096, 1024, 0.15, 32, 0, 64, 2),
+                                                 # n % 4 != 0: the scalar cloud load (no 16-byte alignment per cloud); tail of a 16-point lane
+                                                 ("ball", 301, 40, 0.3, 20, 0, 64, 3), ("shell", 1023, 100, 0.25, 32, 0, 64, 2),
+                                                 # B = 32 clouds: nine CTAs per cloud, none crosses a cloud boundary
+                                                 ("ball", 2048, 512, 0.2, 32, 0, 64, 32)])
 def test_sa_conv1_prebn_training_front(kind, n, m, r, k, c, c1, b):
     """variant F1: pre-BN conv1 output + BN batch statistics vs the fp64 restatement of
     query_ball_point -> group_point -> centre -> concat -> conv2d + bias_add (pointnet_util.py:44-50,117-123)."""
