@@ -158,8 +158,10 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
 // deterministic, one launch.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kF1SThreads = 256;
-constexpr int kF1Batch = 8;
-constexpr int kF1Ring = 3;
+constexpr int kF1WThreads = 384;           // streaming kernel: one warpgroup of search warps + two of worker warps
+constexpr int kF1NP = 4;
+constexpr int kF1Batch = 8;                // smallest full batch (two queries per worker warp, four worker warps): sizes the grid
+constexpr int kF1Ring = 3;                 // bitmap slots in flight (5 / 6 measured: no change -- the search warps never run ahead)
 constexpr int kF1Tickets = 64;
 
 // completion tickets of the statistics reduction: zero at load, reset by the last CTA of every launch; a launch uses
@@ -193,21 +195,32 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 
 // Batches of a cloud segment: 2, 4, then kF1Batch queries -- the first stores of a CTA start after a 2-query search.
-__host__ __device__ inline int f1s_batch_size(int t) { return t == 0 ? 2 : (t == 1 ? 4 : kF1Batch); }
-__host__ __device__ inline int f1s_num_batches(long long nq) {
+__host__ __device__ inline int f1s_batch_size(int t, int qb) { return t == 0 ? 2 : (t == 1 ? 4 : qb); }
+__host__ __device__ inline int f1s_num_batches(long long nq, int qb) {
     int t = 0;
-    for (long long done = 0; done < nq; ++t) done += f1s_batch_size(t);
+    for (long long done = 0; done < nq; ++t) done += f1s_batch_size(t, qb);
     return t;
 }
 
 // shared memory: cloud as float4 (x,y,z,bits(k)) | kF1Batch bitmaps of bw words | ring slots (idx rows | centred rows)
 __host__ __device__ inline int f1s_bitmap_words(int np, int pptp) { const int w = np * pptp; return w < 32 ? 32 : w; }
-__host__ __device__ inline size_t f1s_slot_bytes(int nsample) { return (size_t)kF1Batch * nsample * (sizeof(int) + sizeof(float4)) + kF1Batch * sizeof(float4); }
 __host__ __device__ inline size_t f1s_smem_bytes(int n, int nsample, int np, int pptp) {
-    size_t ring = kF1Ring * f1s_slot_bytes(nsample);
-    if (ring < 8192) ring = 8192;                   // the statistics epilogue reuses the ring: up to 8 KB of partials
-    return (size_t)n * 16 + (size_t)kF1Batch * f1s_bitmap_words(np, pptp) * 4 + ring;
+    // cloud copy | ring B: bitmaps + centres | ring R: idx rows + centred rows (reused by the statistics epilogue: up to 12 KB of partials)
+    size_t ringb = (size_t)kF1Ring * kF1Batch * (f1s_bitmap_words(np, pptp) * 4 + sizeof(float4));
+    size_t ringr = (size_t)kF1Ring * kF1Batch * nsample * (sizeof(int) + sizeof(float4));
+    if (ringr < 12288) ringr = 12288;
+    return (size_t)n * 16 + ringb + ringr;
 }
+
+#ifdef PSA_F1_TIMING
+__device__ __forceinline__ long long clock_after_smem(const volatile int* w) {
+    const int dep = *w;
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+}
+#define F1CLK() clock_after_smem(reinterpret_cast<const volatile int*>(centres))
+#endif
 
 // packed f32x2 arithmetic on 64-bit registers (aligned pairs by construction: the compiler never has to shuffle halves)
 typedef unsigned long long u64;
@@ -218,29 +231,54 @@ __device__ __forceinline__ u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %
 __device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ void f2_unpack_bits(u64 v, unsigned& lo, unsigned& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 
-template <int NV, bool HAS_U, int NP, int PPTP>
-__global__ void __launch_bounds__(kF1SThreads, 2)       // (3 CTAs per SM at 80 registers spills the point registers: 63 vs 57 us)
+template <int NV, bool HAS_U, int PPTP>
+__global__ void __launch_bounds__(kF1WThreads, 2)       // 80 registers at launch; setmaxnreg: search warps 128, the others 56
 sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
-    constexpr int NC = kF1SThreads / 32 - NP;              // consumer warps
-    constexpr int PT = NP * 32;                            // producer threads
+    // three pipelined stages, one warpgroup each (measured on the two-stage kernel: search 24 k, extraction + rows 18 k, conv + store 18 k
+    // cycles per CTA -- in series on the producer warps they set the kernel time, side by side the slowest one does):
+    //   warps 0-3  SEARCH : the cloud in registers, exhaustive packed-f32x2 test -> hit bitmaps            (ring B: bitmaps, centres)
+    //   warps 4-7  EXTRACT: bitmap -> nsample first hits in index order (idx, pts_cnt) -> centred rows     (ring R: rows)
+    //   warps 8-11 CONV   : rows -> conv1 + bias (+ U) -> 512-byte streaming stores, BN statistics in registers
+    constexpr int NP = kF1NP;                              // warps per stage
+    constexpr int QB = kF1Batch;                           // queries per batch
+    constexpr bool TWO = HAS_U;                            // levels with input features: two stages -- warps 0-3 search AND extract, warps 4-11 conv + store
+                                                           // (the U-row gather of the conv stage is what needs the warps there: 64 vs 83 us at SA2)
+    constexpr int CONV0 = TWO ? NP : 2 * NP;               // first conv warp
+    constexpr int NC = kF1WThreads / 32 - CONV0;           // conv warps: 4 or 8
+    constexpr int RCNT = TWO ? kF1WThreads : 2 * NP * 32;  // threads on the ring-R barriers
+    constexpr int PT = NP * 32;                            // threads per stage
     constexpr int BW = NP * PPTP < 32 ? 32 : NP * PPTP;    // bitmap words per query
+    constexpr int C1c = NV * 32;                           // = a.C1 (the launcher picks NV = C1 / 32)
+    constexpr int LPQ = 32 * NP / QB;                      // lanes per query in the extraction: 16
+    constexpr int BAR_BFULL = 1, BAR_BEMPTY = 1 + kF1Ring, BAR_RFULL = 1 + 2 * kF1Ring, BAR_REMPTY = 1 + 3 * kF1Ring, BAR_CLOUD = 1 + 4 * kF1Ring;
+    static_assert(BAR_CLOUD <= 15, "named barriers");
     extern __shared__ __align__(16) float smem_f[];
     const int n = a.n, K = a.nsample, C1 = a.C1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4* cloud4 = reinterpret_cast<float4*>(smem_f);
-    unsigned* bitmaps = reinterpret_cast<unsigned*>(cloud4 + n);                                  // kF1Batch x BW
-    uint8_t* ring = reinterpret_cast<uint8_t*>(bitmaps + kF1Batch * BW);
-    const size_t slot_bytes = f1s_slot_bytes(K);
+    unsigned* bitmaps = reinterpret_cast<unsigned*>(cloud4 + n);                                  // kF1Ring x QB x BW
+    float4* centres = reinterpret_cast<float4*>(bitmaps + kF1Ring * QB * BW);                     // kF1Ring x QB
+    uint8_t* ring = reinterpret_cast<uint8_t*>(centres + kF1Ring * QB);                           // ring R; reused by the statistics epilogue
+    const size_t slot_bytes = (size_t)QB * K * (sizeof(int) + sizeof(float4));                    // idx rows | centred rows
+    __shared__ int4 s_hdrB[kF1Ring];                       // (first query - q_begin, queries [0 = stop], last batch of a cloud with more to come, -)
+    __shared__ int2 s_hdrR[kF1Ring];                       // (first query - q_begin, queries [0 = stop])
 #ifdef PSA_F1_TIMING
-    if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 0] = gtime();
+    if (tid == 0 && a.tlog) {
+        a.tlog[blockIdx.x * 8 + 0] = gtime();
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.tlog[blockIdx.x * 8 + 7] = smid;
+    }
+    long long tacc[3] = {0, 0, 0};                         // per stage (thread 0 of the stage): waiting for input, waiting for output space, working
+    long long tc0 = 0, tc1 = 0;
 #endif
 
-    float2 ssum[2], ssq[2];                                // this lane's four channels (consumers)
+    float2 ssum[2], ssq[2];                                // this lane's four channels (conv warps)
     ssum[0] = ssum[1] = ssq[0] = ssq[1] = make_float2(0.f, 0.f);
 
     const long long T = (long long)a.b * a.m;
     // a grid that is a multiple of the batch size gives every cloud the same number of CTAs: no CTA crosses a cloud boundary (a
-    // crossing costs a second cloud load + pipeline ramp; those CTAs used to finish ~6 us after the others)
+    // crossing costs a second cloud load + pipeline ramp)
     long long q_begin, q_end;
     if (gridDim.x % a.b == 0) {
         const int cpc = gridDim.x / a.b, cl = blockIdx.x / cpc, ci = blockIdx.x % cpc;
@@ -249,35 +287,55 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
     } else {
         q_begin = T * blockIdx.x / gridDim.x; q_end = T * (blockIdx.x + 1) / gridDim.x;
     }
-    // batches this CTA will run in total (the consumers' last kF1Ring EMPTY arrivals have no taker and are skipped)
-    int total_batches = 0;
-    for (long long q = q_begin; q < q_end;) {
-        const long long cloud = q / a.m;
-        const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-        total_batches += f1s_num_batches(seg_end - q);
-        q = seg_end;
-    }
+
+    // bitmap -> the query's nsample first hits in index order (idx, pts_cnt) -> centred rows grouped_xyz - new_xyz (pointnet_util.py:46)
+    // + the source index for the U gather, into ring-R slot `slot`; LPQ lanes per query, executed by the PT threads of one stage
+    // (w, t = warp / thread index inside that stage); `release` runs once the bitmaps and centres have been read
+    auto extract_rows = [&](const int slot, const unsigned* bmq, const float4* ctrq, const long long gq0, const int nqb, const int w, auto release) {
+        int* sidx = reinterpret_cast<int*>(ring + slot * slot_bytes);
+        float4* sd = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)QB * K * sizeof(int));
+        const int qi = w * (32 / LPQ) + lane / LPQ, sub = lane & (LPQ - 1);
+        const bool act = qi < nqb;
+        const int cnt = bq_extract_bitmap_sub<LPQ, BW / LPQ>(bmq + (size_t)qi * BW, K, sidx + qi * K, lane, act);
+        const float4 ctr = act ? ctrq[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();                                                                       // the query's idx row is complete (one warp)
+        release();
+        if (act) {
+            if (a.pts_cnt != nullptr && sub == 0) a.pts_cnt[gq0 + qi] = cnt;
+            int* gidx = a.idx + (size_t)(gq0 + qi) * K;
+            for (int r = sub; r < K; r += LPQ) {
+                const int j = sidx[qi * K + r];
+                const float4 pt = cloud4[j];
+                gidx[r] = j;
+                sd[qi * K + r] = make_float4(pt.x - ctr.x, pt.y - ctr.y, pt.z - ctr.z, __int_as_float(j));
+            }
+        }
+    };
 
     if (warp < NP) {
-        // =========================================== PRODUCERS ===========================================
-        for (int i = tid; i < kF1Batch * BW; i += PT) bitmaps[i] = 0u;       // words no warp owns (BW > NP*PPTP) stay zero
+        // =========================================== SEARCH (+ EXTRACT when TWO) ===========================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");               // the cloud lives in registers
+        for (int i = tid; i < kF1Ring * QB * BW; i += PT) bitmaps[i] = 0u;   // words no warp owns (BW > NP*PPTP) stay zero
         int ring_pos = 0;
+        bool first_cloud = true;
         for (long long q = q_begin; q < q_end;) {
             const long long cloud = q / a.m;
             const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
             const float* gx = a.xyz + (size_t)cloud * n * 3;
-            // ---- this cloud: PPTP CONSECUTIVE points per thread in registers (point k = PPTP*(32*warp + lane) + i) as packed
-            //      f32x2 pairs (points 2j, 2j+1), so the lane's hit mask IS bits [PPTP*(32*warp+lane), +PPTP) of the query's
-            //      bitmap -- no ballots, no transposition; float4 copy of the cloud in shared memory for the row builder ----
-            // first batch's query centres: in flight together with the cloud (lane i of every producer warp holds query i of a batch;
-            // the search reads them through shuffles, the row builder through shared memory)
+            // first batch's query centres: in flight together with the cloud (lane i of every search warp holds query i of a batch)
             long long gq0 = q;                                                             // global query id of the batch
             float ncx = 0.f, ncy = 0.f, ncz = 0.f;
-            if (lane < min(f1s_batch_size(0), (int)(seg_end - gq0))) {
+            if (lane < min(f1s_batch_size(0, QB), (int)(seg_end - gq0))) {
                 const float* p2 = a.new_xyz + (size_t)(gq0 + lane) * 3;
                 ncx = __ldg(p2); ncy = __ldg(p2 + 1); ncz = __ldg(p2 + 2);
             }
-            named_bar_sync(15, PT);                                          // the previous cloud's float4 copy is no longer read
+            // ---- this cloud: PPTP CONSECUTIVE points per thread in registers (point k = PPTP*(32*warp + lane) + i) as packed
+            //      f32x2 pairs (points 2j, 2j+1), so the lane's hit mask IS bits [PPTP*(32*warp+lane), +PPTP) of the query's
+            //      bitmap -- no ballots, no transposition; float4 copy of the cloud in shared memory for the row builder ----
+            if (!first_cloud) {                                              // the extraction no longer reads the previous cloud's copy
+                if (TWO) named_bar_sync(15, PT); else named_bar_sync(BAR_CLOUD, 2 * PT);
+            }
+            first_cloud = false;
             u64 px[PPTP / 2], py[PPTP / 2], pz[PPTP / 2];
             unsigned valid = 0u;
             const int k0 = PPTP * tid;                                       // tid = 32 * warp + lane < PT
@@ -327,7 +385,6 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                     px[j] = f2_pack(c[0], c[3]); py[j] = f2_pack(c[1], c[4]); pz[j] = f2_pack(c[2], c[5]);
                 }
             }
-            named_bar_sync(15, PT);
 #ifdef PSA_F1_TIMING
             if (tid == 0 && a.tlog && q == q_begin) a.tlog[blockIdx.x * 8 + 1] = gtime();
 #endif
@@ -335,20 +392,26 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             // the NEXT batch's centres are fetched under the current search
             for (int bi = 0; gq0 < seg_end; ++bi, ++ring_pos) {
                 const int slot = ring_pos % kF1Ring;
-                int* sidx = reinterpret_cast<int*>(ring + slot * slot_bytes);
-                float4* sd = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
-                const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
-                float4* sctr = reinterpret_cast<float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * (sizeof(int) + sizeof(float4)));
+                const int nqb = min(f1s_batch_size(bi, QB), (int)(seg_end - gq0));
+                const int bslot = TWO ? (ring_pos & 1) : slot;                              // TWO: bitmaps double-buffered inside the stage
+                unsigned* bms = bitmaps + (size_t)bslot * QB * BW;
                 const float cqx = ncx, cqy = ncy, cqz = ncz;
                 {
                     const long long gq1 = gq0 + nqb;
-                    if (gq1 < seg_end && lane < min(f1s_batch_size(bi + 1), (int)(seg_end - gq1))) {
+                    if (gq1 < seg_end && lane < min(f1s_batch_size(bi + 1, QB), (int)(seg_end - gq1))) {
                         const float* p2 = a.new_xyz + (size_t)(gq1 + lane) * 3;
                         ncx = __ldg(p2); ncy = __ldg(p2 + 1); ncz = __ldg(p2 + 2);
                     }
                 }
-                if (ring_pos >= kF1Ring) named_bar_sync(1 + kF1Ring + slot, kF1SThreads);   // slot drained by the consumers
-                if (warp == 0 && lane < nqb) sctr[lane] = make_float4(cqx, cqy, cqz, 0.f);
+#ifdef PSA_F1_TIMING
+                tc0 = F1CLK();
+#endif
+                if (!TWO && ring_pos >= kF1Ring) named_bar_sync(BAR_BEMPTY + slot, 2 * PT); // slot drained by the extraction
+#ifdef PSA_F1_TIMING
+                tc1 = F1CLK(); tacc[1] += tc1 - tc0;
+#endif
+                if (warp == 0 && lane < nqb) centres[bslot * QB + lane] = make_float4(cqx, cqy, cqz, 0.f);
+                if (!TWO && tid == 0) s_hdrB[slot] = make_int4((int)(gq0 - q_begin), nqb, (gq0 + nqb == seg_end && seg_end < q_end) ? 1 : 0, 0);
                 // ---- exhaustive test on the packed f32x2 pipe: per point pair 3 FADD2 + FMUL2 + 2 FFMA2 (the reference's
                 //      distance) + one FADD2 s = thr - d + two funnel shifts that push the SIGN of s into the lane's mask.
                 //      sign(s) = 1 <=> d > thr; d == thr gives +0 and a NaN distance the canonical (positive) NaN, i.e. both
@@ -357,7 +420,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                     for (int qi = 0; qi < nqb; ++qi) {
                         const float qx = __shfl_sync(0xffffffffu, cqx, qi), qy = __shfl_sync(0xffffffffu, cqy, qi), qz = __shfl_sync(0xffffffffu, cqz, qi);
                         const u64 nqx = f2_pack(-qx, -qx), nqy = f2_pack(-qy, -qy), nqz = f2_pack(-qz, -qz);
-                        unsigned acc[PPTP / 8];                              // 8 points per chain: four short dependency chains
+                        unsigned acc[PPTP / 8];                              // 8 points per chain: short dependency chains
 #pragma unroll
                         for (int g = 0; g < PPTP / 8; ++g) acc[g] = 0u;
 #pragma unroll
@@ -375,57 +438,109 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
 #pragma unroll
                         for (int g = 1; g < PPTP / 8; ++g) outside |= acc[g] << (8 * g);
                         const unsigned inside = ~outside & valid;
-                        uint8_t* bm = reinterpret_cast<uint8_t*>(bitmaps + qi * BW) + (32 * warp + lane) * (PPTP / 8);
+                        uint8_t* bm = reinterpret_cast<uint8_t*>(bms + qi * BW) + (32 * warp + lane) * (PPTP / 8);
                         if (PPTP == 8) *bm = (uint8_t)inside;
                         else if (PPTP == 16) *reinterpret_cast<unsigned short*>(bm) = (unsigned short)inside;
                         else *reinterpret_cast<unsigned*>(bm) = inside;
                     }
                 }
-                named_bar_sync(15, PT);                                                     // bitmaps complete
-#ifdef PSA_F1_TIMING
-                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 4] = gtime();
-#endif
-                // ---- bitmaps -> ordered idx rows -> centred rows: LPQ = 32*NP/kF1Batch lanes per query, every producer warp busy;
-                //      a query's lanes extract its nsample first hits in index order and (after a __syncwarp: the group lives in
-                //      one warp) build its K rows grouped_xyz - new_xyz (pointnet_util.py:46) + the source index for the U gather ----
-                {
-                    constexpr int LPQ = 32 * NP / kF1Batch;                                 // 16 (NP = 4) or 8 (NP = 2)
-                    const int qi = warp * (32 / LPQ) + lane / LPQ, sub = lane & (LPQ - 1);
-                    const bool act = qi < nqb;
-                    const int cnt = bq_extract_bitmap_sub<LPQ, BW / LPQ>(bitmaps + qi * BW, K, sidx + qi * K, lane, act);
-                    if (act && a.pts_cnt != nullptr && sub == 0) a.pts_cnt[gq0 + qi] = cnt;
-                    __syncwarp();
-                    if (act) {
-                        const float4 ctr = sctr[qi];
-                        int* gidx = a.idx + (size_t)(gq0 + qi) * K;
-                        for (int r = sub; r < K; r += LPQ) {
-                            const int j = sidx[qi * K + r];
-                            const float4 pt = cloud4[j];
-                            gidx[r] = j;
-                            sd[qi * K + r] = make_float4(pt.x - ctr.x, pt.y - ctr.y, pt.z - ctr.z, __int_as_float(j));
-                        }
-                    }
+                if (TWO) {
+                    named_bar_sync(15, PT);                                                 // bitmaps + centres (+ the cloud copy) complete
+                    if (ring_pos >= kF1Ring) named_bar_sync(BAR_REMPTY + slot, RCNT);       // rows slot drained by the conv warps
+                    extract_rows(slot, bms, centres + bslot * QB, gq0, nqb, warp, [] {});
+                    if (tid == 0) s_hdrR[slot] = make_int2((int)(gq0 - q_begin), nqb);
+                    __threadfence_block();
+                    named_bar_arrive(BAR_RFULL + slot, RCNT);
+                } else {
+                    __threadfence_block();
+                    named_bar_arrive(BAR_BFULL + slot, 2 * PT);                             // bitmaps + centres (+ the cloud copy) ready
                 }
-                __threadfence_block();
-                named_bar_arrive(1 + slot, kF1SThreads);                                    // FULL
 #ifdef PSA_F1_TIMING
-                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 2] = gtime();
+                tacc[2] += F1CLK() - tc1;
+                if (tid == 0 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 4] = gtime();
 #endif
                 gq0 += nqb;
             }
             q = seg_end;
         }
+        // stop marker, then take the next stage's outstanding releases (every arrival has a taker: no barrier is left half full)
+        {
+            const int slot = ring_pos % kF1Ring;
+            if (TWO) {
+                if (ring_pos >= kF1Ring) named_bar_sync(BAR_REMPTY + slot, RCNT);
+                if (tid == 0) s_hdrR[slot] = make_int2(0, 0);
+                __threadfence_block();
+                named_bar_arrive(BAR_RFULL + slot, RCNT);
+                for (int p = ring_pos + 1; p <= ring_pos + kF1Ring; ++p)
+                    if (p >= kF1Ring) named_bar_sync(BAR_REMPTY + p % kF1Ring, RCNT);
+            } else {
+                if (ring_pos >= kF1Ring) named_bar_sync(BAR_BEMPTY + slot, 2 * PT);
+                if (tid == 0) s_hdrB[slot] = make_int4(0, 0, 0, 0);
+                __threadfence_block();
+                named_bar_arrive(BAR_BFULL + slot, 2 * PT);
+                for (int p = ring_pos + 1; p <= ring_pos + kF1Ring; ++p)
+                    if (p >= kF1Ring) named_bar_sync(BAR_BEMPTY + p % kF1Ring, 2 * PT);
+            }
+        }
 #ifdef PSA_F1_TIMING
-        if (tid == 0 && a.tlog) a.tlog[blockIdx.x * 8 + 3] = gtime();
+        if (tid == 0 && a.tlog) {
+            a.tlog[blockIdx.x * 8 + 3] = gtime();
+            unsigned long long* t2 = a.tlog + 3 * kNumSMs * 8 + blockIdx.x * 16;
+            t2[0] = 0; t2[1] = tacc[1]; t2[2] = tacc[2];
+        }
+#endif
+    } else if (!TWO && warp < 2 * NP) {
+        // =========================================== EXTRACT ===========================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int ew = warp - NP, et = tid - PT;
+        for (int ring_pos = 0;; ++ring_pos) {
+            const int slot = ring_pos % kF1Ring;
+#ifdef PSA_F1_TIMING
+            tc0 = F1CLK();
+#endif
+            named_bar_sync(BAR_BFULL + slot, 2 * PT);
+#ifdef PSA_F1_TIMING
+            tc1 = F1CLK(); tacc[0] += tc1 - tc0;
+#endif
+            const int4 hdr = s_hdrB[slot];
+            const int nqb = hdr.y;
+            if (ring_pos >= kF1Ring) named_bar_sync(BAR_REMPTY + slot, RCNT);               // rows slot drained by the conv warps
+#ifdef PSA_F1_TIMING
+            tc0 = F1CLK(); tacc[1] += tc0 - tc1;
+#endif
+            if (nqb == 0) {                                                                 // stop: pass it on, take the outstanding releases
+                named_bar_arrive(BAR_BEMPTY + slot, 2 * PT);
+                if (et == 0) s_hdrR[slot] = make_int2(0, 0);
+                __threadfence_block();
+                named_bar_arrive(BAR_RFULL + slot, RCNT);
+                for (int p = ring_pos + 1; p <= ring_pos + kF1Ring; ++p)
+                    if (p >= kF1Ring) named_bar_sync(BAR_REMPTY + p % kF1Ring, RCNT);
+                break;
+            }
+            extract_rows(slot, bitmaps + (size_t)slot * QB * BW, centres + slot * QB, q_begin + hdr.x, nqb, ew,
+                         [&] { named_bar_arrive(BAR_BEMPTY + slot, 2 * PT); });             // bitmaps + centres consumed
+            if (et == 0) s_hdrR[slot] = make_int2(hdr.x, nqb);
+            __threadfence_block();
+            named_bar_arrive(BAR_RFULL + slot, RCNT);
+            if (hdr.z) named_bar_arrive(BAR_CLOUD, 2 * PT);                                 // last batch of this cloud: its copy is free
+#ifdef PSA_F1_TIMING
+            tacc[2] += F1CLK() - tc0;
+#endif
+        }
+#ifdef PSA_F1_TIMING
+        if (tid == PT && a.tlog) {
+            unsigned long long* t2 = a.tlog + 3 * kNumSMs * 8 + blockIdx.x * 16;
+            t2[3] = tacc[0]; t2[4] = tacc[1]; t2[5] = tacc[2];
+        }
 #endif
     } else {
-        // =========================================== CONSUMERS ===========================================
+        // =========================================== CONV + STORE ===========================================
         // lane mapping: LPR = C1/4 lanes cover one row (4 consecutive channels each), so a warp store instruction writes
         // 32/LPR whole rows = 512 contiguous bytes; a lane's channels are fixed, its weights live in registers
-        const int cw = warp - NP;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int cw = warp - CONV0;
         constexpr int LPR = NV * 8;                    // 16 (C1 = 64) or 32 (C1 = 128)
         constexpr int RPI = 32 / LPR;                  // rows per store instruction: 2 or 1
-        constexpr int C1c = NV * 32;                   // = a.C1 (the launcher picks NV = C1 / 32)
         const int lr = lane / LPR, lc = (lane % LPR) * 4;
         const float4 wx4 = __ldg(reinterpret_cast<const float4*>(a.w1 + lc));
         const float4 wy4 = __ldg(reinterpret_cast<const float4*>(a.w1 + C1 + lc));
@@ -433,63 +548,75 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float2 wxa = make_float2(wx4.x, wx4.y), wxb = make_float2(wx4.z, wx4.w), wya = make_float2(wy4.x, wy4.y), wyb = make_float2(wy4.z, wy4.w);
         const float2 wza = make_float2(wz4.x, wz4.y), wzb = make_float2(wz4.z, wz4.w), ba = make_float2(b4.x, b4.y), bb = make_float2(b4.z, b4.w);
-        int ring_pos = 0;
-        for (long long q = q_begin; q < q_end;) {
-            const long long cloud = q / a.m;
-            const long long seg_end = min(q_end, (cloud + 1) * (long long)a.m);
-            const float* ucloud = HAS_U ? a.uf + (size_t)cloud * n * C1 + lc : nullptr;
-            long long gq0 = q;
-            for (int bi = 0; gq0 < seg_end; ++bi, ++ring_pos) {
-                const int slot = ring_pos % kF1Ring;
-                const float4* sd = reinterpret_cast<const float4*>(ring + slot * slot_bytes + (size_t)kF1Batch * K * sizeof(int));
-                const int nqb = min(f1s_batch_size(bi), (int)(seg_end - gq0));
-                const int nrows = nqb * K;
-                float* outl = a.pre + (size_t)gq0 * K * C1 + lc;
-                named_bar_sync(1 + slot, kF1SThreads);                                      // FULL
-                // four rows per lane and trip: independent chains, stores of a warp instruction contiguous; C1 is a compile-time
-                // constant (immediate store offsets, one pointer bump per trip); row guards only when nrows is not a multiple of 4*RPI
-                auto row = [&](const float4 d, float* dst) {
-                    float2 s0 = ba, s1 = bb;
-                    if (HAS_U) {
-                        const float4 uu = __ldg(reinterpret_cast<const float4*>(ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1c));
-                        s0 = __fadd2_rn(s0, make_float2(uu.x, uu.y)); s1 = __fadd2_rn(s1, make_float2(uu.z, uu.w));
-                    }
-                    const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
-                    const float2 v0 = __ffma2_rn(dz, wza, __ffma2_rn(dy, wya, __ffma2_rn(dx, wxa, s0)));
-                    const float2 v1 = __ffma2_rn(dz, wzb, __ffma2_rn(dy, wyb, __ffma2_rn(dx, wxb, s1)));
-                    __stcs(reinterpret_cast<float4*>(dst), make_float4(v0.x, v0.y, v1.x, v1.y));
-                    ssum[0] = __fadd2_rn(ssum[0], v0); ssum[1] = __fadd2_rn(ssum[1], v1);
-                    ssq[0] = __ffma2_rn(v0, v0, ssq[0]); ssq[1] = __ffma2_rn(v1, v1, ssq[1]);
-                };
-                if ((nrows & (4 * RPI - 1)) == 0) {
-                    const float4* sp = sd + cw * 4 * RPI + lr;
-                    float* op = outl + (size_t)(cw * 4 * RPI + lr) * C1c;
-                    for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI, sp += NC * 4 * RPI, op += (size_t)NC * 4 * RPI * C1c) {
-                        float4 d[4];
+        for (int ring_pos = 0;; ++ring_pos) {
+            const int slot = ring_pos % kF1Ring;
+            const float4* sd = reinterpret_cast<const float4*>(ring + slot * slot_bytes + (size_t)QB * K * sizeof(int));
+#ifdef PSA_F1_TIMING
+            tc0 = F1CLK();
+#endif
+            named_bar_sync(BAR_RFULL + slot, RCNT);
+#ifdef PSA_F1_TIMING
+            tc1 = F1CLK(); tacc[0] += tc1 - tc0;
+            if (tid == CONV0 * 32 && a.tlog && ring_pos == 0) a.tlog[blockIdx.x * 8 + 2] = gtime();
+#endif
+            const int2 hdr = s_hdrR[slot];
+            const int nqb = hdr.y;
+            if (nqb == 0) { named_bar_arrive(BAR_REMPTY + slot, RCNT); break; }               // stop marker
+            const long long gq0 = q_begin + hdr.x;
+            const int nrows = nqb * K;
+            float* outl = a.pre + (size_t)gq0 * K * C1c + lc;
+            const float* ucloud = HAS_U ? a.uf + (size_t)(gq0 / a.m) * n * C1c + lc : nullptr;
+            // four rows per lane and trip: independent chains, stores of a warp instruction contiguous; C1 is a compile-time
+            // constant (immediate store offsets, one pointer bump per trip); row guards only when nrows is not a multiple of 4*RPI
+            auto row = [&](const float4 d, float* dst) {
+                float2 s0 = ba, s1 = bb;
+                if (HAS_U) {
+                    const float4 uu = __ldg(reinterpret_cast<const float4*>(ucloud + (unsigned)__float_as_int(d.w) * (unsigned)C1c));
+                    s0 = __fadd2_rn(s0, make_float2(uu.x, uu.y)); s1 = __fadd2_rn(s1, make_float2(uu.z, uu.w));
+                }
+                const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+                const float2 v0 = __ffma2_rn(dz, wza, __ffma2_rn(dy, wya, __ffma2_rn(dx, wxa, s0)));
+                const float2 v1 = __ffma2_rn(dz, wzb, __ffma2_rn(dy, wyb, __ffma2_rn(dx, wxb, s1)));
+                __stcs(reinterpret_cast<float4*>(dst), make_float4(v0.x, v0.y, v1.x, v1.y));
+                ssum[0] = __fadd2_rn(ssum[0], v0); ssum[1] = __fadd2_rn(ssum[1], v1);
+                ssq[0] = __ffma2_rn(v0, v0, ssq[0]); ssq[1] = __ffma2_rn(v1, v1, ssq[1]);
+            };
+            if ((nrows & (4 * RPI - 1)) == 0) {
+                const float4* sp = sd + cw * 4 * RPI + lr;
+                float* op = outl + (size_t)(cw * 4 * RPI + lr) * C1c;
+                for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI, sp += NC * 4 * RPI, op += (size_t)NC * 4 * RPI * C1c) {
+                    float4 d[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) d[u] = sp[u * RPI];
+                    for (int u = 0; u < 4; ++u) d[u] = sp[u * RPI];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) row(d[u], op + u * RPI * C1c);
-                    }
-                } else {
-                    for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI) {
+                    for (int u = 0; u < 4; ++u) row(d[u], op + u * RPI * C1c);
+                }
+            } else {
+                for (int r0 = cw * 4 * RPI; r0 < nrows; r0 += NC * 4 * RPI) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int r = r0 + u * RPI + lr;
-                            if (r < nrows) row(sd[r], outl + (size_t)r * C1c);
-                        }
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = r0 + u * RPI + lr;
+                        if (r < nrows) row(sd[r], outl + (size_t)r * C1c);
                     }
                 }
-                if (ring_pos + kF1Ring < total_batches) named_bar_arrive(1 + kF1Ring + slot, kF1SThreads);   // EMPTY
-                gq0 += nqb;
             }
-            q = seg_end;
+            named_bar_arrive(BAR_REMPTY + slot, RCNT);
+#ifdef PSA_F1_TIMING
+            tacc[2] += F1CLK() - tc1;
+#endif
         }
 #ifdef PSA_F1_TIMING
-        if (tid == NP * 32 && a.tlog) a.tlog[blockIdx.x * 8 + 5] = gtime();
+        if (tid == CONV0 * 32 && a.tlog) {
+            a.tlog[blockIdx.x * 8 + 5] = gtime();
+            unsigned long long* t2 = a.tlog + 3 * kNumSMs * 8 + blockIdx.x * 16;
+            t2[6] = tacc[0]; t2[7] = 0; t2[8] = tacc[2];
+        }
 #endif
     }
 
+    // back to the launch allocation (80 registers each) for the common epilogue
+    if (warp < NP) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     if (a.stats != nullptr) {
         __syncthreads();                                   // ring memory is free: reuse it for the per-warp partials
         float* sstat = reinterpret_cast<float*>(ring);     // NC x 2 x C1
@@ -503,8 +630,8 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
                     ssum[p].x += __shfl_xor_sync(0xffffffffu, ssum[p].x, o); ssum[p].y += __shfl_xor_sync(0xffffffffu, ssum[p].y, o);
                     ssq[p].x += __shfl_xor_sync(0xffffffffu, ssq[p].x, o); ssq[p].y += __shfl_xor_sync(0xffffffffu, ssq[p].y, o);
                 }
-                if (warp >= NP && lane < LPR) {
-                    float* w = sstat + (size_t)(warp - NP) * 2 * C1;
+                if (warp >= CONV0 && lane < LPR) {
+                    float* w = sstat + (size_t)(warp - CONV0) * 2 * C1;
                     const int c = lane * 4 + 2 * p;
                     *reinterpret_cast<float2*>(w + c) = ssum[p];
                     *reinterpret_cast<float2*>(w + C1 + c) = ssq[p];
@@ -513,7 +640,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
         }
         __syncthreads();
         float* dst = a.partial + (size_t)blockIdx.x * 2 * C1;
-        for (int e = tid; e < 2 * C1; e += kF1SThreads) {
+        for (int e = tid; e < 2 * C1; e += kF1WThreads) {
             float t = 0.f;
 #pragma unroll
             for (int w = 0; w < NC; ++w) t += sstat[(size_t)w * 2 * C1 + e];      // fixed order
@@ -530,7 +657,7 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
             // thread (rl, e4): partial rows p = rl, rl + RL, ... of float4 column e4, sixteen loads in flight (the loop is
             // L2-latency-bound), fp64 accumulators in ascending p; then the RL row lanes in order through shared memory
             const int E4 = 2 * C1 / 4;                                     // 32 (C1 = 64) or 64 (C1 = 128)
-            const int RL = kF1SThreads / E4;                               // 8 or 4
+            const int RL = kF1WThreads / E4;                               // 8 or 4
             const int e4 = tid % E4, rl = tid / E4;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const float4* part4 = reinterpret_cast<const float4*>(a.partial);
@@ -544,11 +671,11 @@ sa_conv1_stream_kernel(const __grid_constant__ F1SArgs a) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
             }
-            double* sred = reinterpret_cast<double*>(ring);                // RL x 2*C1 doubles <= 8 KB (the ring is >= 15 KB)
+            double* sred = reinterpret_cast<double*>(ring);                // RL x 2*C1 doubles = 12 KB (the region is >= 12 KB)
 #pragma unroll
             for (int c = 0; c < 4; ++c) sred[(size_t)rl * 2 * C1 + e4 * 4 + c] = acc[c];
             __syncthreads();
-            for (int e = tid; e < 2 * C1; e += kF1SThreads) {
+            for (int e = tid; e < 2 * C1; e += kF1WThreads) {
                 double t = 0.0;
                 for (int r = 0; r < RL; ++r) t += sred[(size_t)r * 2 * C1 + e];
                 a.stats[e] = (float)t;
@@ -851,9 +978,9 @@ using namespace psa;
 // streaming kernel: producer layout (NP warps x PPTP points per thread), grid, shared memory, applicability
 static bool f1s_plan(int b, int n, int m, int nsample, int* np, int* pptp, int* ctas, size_t* smem) {
     if (n > 4096 || nsample > 128) return false;
-    // 32 * np * pptp >= n; at most 16 points per thread up to n = 2048 (48 registers of coordinates next to the consumers' weights)
-    *np = n <= 1024 ? 2 : 4;
-    *pptp = n <= 512 ? 8 : (n <= 2048 ? 16 : 32);
+    // four search warps (one warpgroup: setmaxnreg is per warpgroup), 32 * 4 * pptp >= n
+    *np = kF1NP;
+    *pptp = n <= 1024 ? 8 : (n <= 2048 ? 16 : 32);
     *smem = f1s_smem_bytes(n, nsample, *np, *pptp);
     if (*smem > 110 * 1024) return false;
     const long long T = (long long)b * m;
@@ -874,7 +1001,7 @@ extern "C" size_t psa_sa_conv1_prebn_workspace_bytes(int b, int n, int m, int c,
         f1_grid(b, m, &q, &g);
         size_t parts = (size_t)g.x * g.y;
         if (parts < 3 * (size_t)kNumSMs) parts = 3 * (size_t)kNumSMs;      // the streaming kernels run up to 3 CTAs per SM
-        bytes += parts * 2 * C1 * sizeof(float) + 256 + 3 * (size_t)kNumSMs * 8 * sizeof(unsigned long long);   // CTA partials (+ timing stamps of debug builds)
+        bytes += parts * 2 * C1 * sizeof(float) + 256 + 3 * (size_t)kNumSMs * 24 * sizeof(unsigned long long);   // CTA partials (+ timing stamps of debug builds)
     }
     return bytes;
 }
@@ -943,18 +1070,17 @@ extern "C" int psa_sa_conv1_prebn(int b, int n, int m, int c, float radius, int 
 #undef PSA_F1Y_LAUNCH
                 return check_launch("sa_conv1_sync_kernel");
             }
-#define PSA_F1S_LAUNCH(NV_, U_, NP_, PP_)                                                                                     \
+#define PSA_F1S_LAUNCH(NV_, U_, PP_)                                                                                          \
     do {                                                                                                                     \
-        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_stream_kernel<NV_, U_, NP_, PP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm)); \
-        sa_conv1_stream_kernel<NV_, U_, NP_, PP_><<<ctas, kF1SThreads, ssm, st>>>(s);                                        \
+        PSA_CUDA(cudaFuncSetAttribute(sa_conv1_stream_kernel<NV_, U_, PP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm)); \
+        sa_conv1_stream_kernel<NV_, U_, PP_><<<ctas, kF1WThreads, ssm, st>>>(s);                                             \
     } while (0)
-#define PSA_F1S_U(NV_, NP_, PP_) do { if (s.uf) PSA_F1S_LAUNCH(NV_, true, NP_, PP_); else PSA_F1S_LAUNCH(NV_, false, NP_, PP_); } while (0)
+#define PSA_F1S_U(NV_, PP_) do { if (s.uf) PSA_F1S_LAUNCH(NV_, true, PP_); else PSA_F1S_LAUNCH(NV_, false, PP_); } while (0)
 #define PSA_F1S_P(NV_)                                                                                                       \
     do {                                                                                                                     \
-        if (np == 4 && pptp == 32) PSA_F1S_U(NV_, 4, 32);                                                                    \
-        else if (np == 4) PSA_F1S_U(NV_, 4, 16);                                                                             \
-        else if (pptp == 16) PSA_F1S_U(NV_, 2, 16);                                                                          \
-        else PSA_F1S_U(NV_, 2, 8);                                                                                           \
+        if (pptp == 32) PSA_F1S_U(NV_, 32);                                                                                  \
+        else if (pptp == 16) PSA_F1S_U(NV_, 16);                                                                             \
+        else PSA_F1S_U(NV_, 8);                                                                                              \
     } while (0)
             if (C1 == 64) PSA_F1S_P(2); else PSA_F1S_P(4);
 #undef PSA_F1S_P

@@ -69,14 +69,23 @@ if os.environ.get("PSA_F1_TLOG"):
     launch()
     torch.cuda.synchronize()
     off = (256 + 3 * 148 * 2 * C1 * 4) // 4
-    raw = ws[off:off + 444 * 8 * 2].view(torch.int64).view(-1, 8).cpu().numpy()
-    raw = raw[raw[:, 0] > 0]
+    allraw = ws[off:off + 444 * 24 * 2].view(torch.int64).cpu().numpy()
+    raw = allraw[:444 * 8].reshape(-1, 8)
+    keep = raw[:, 0] > 0
+    ph = allraw[444 * 8:444 * 24].reshape(-1, 16)[keep]   # cycles per stage (barrier-ordered clock64 reads), summed over the CTA's batches
+    raw = raw[keep]
+    if os.environ.get("PSA_F1_TLOG_DUMP"):
+        import numpy as np
+        np.save(os.environ["PSA_F1_TLOG_DUMP"], raw)
     t0 = raw[:, 0].min()
     med = lambda c: float(sorted(raw[:, c] - t0)[len(raw) // 2]) / 1e3   # noqa: E731
     mx = lambda c: float((raw[:, c] - t0).max()) / 1e3                   # noqa: E731
     tl = {"ctas": int(len(raw)), "us_from_first_cta_start": {"cta_start_max": mx(0), "cloud_loaded_median": med(1), "cloud_loaded_max": mx(1),
           "first_search_done_median": med(4), "first_rows_ready_median": med(2), "first_rows_ready_max": mx(2),
-          "consumers_done_median": med(5), "consumers_done_max": mx(5), "cta_end_max": mx(6)}}
+          "consumers_done_median": med(5), "consumers_done_max": mx(5), "cta_end_max": mx(6)},
+          "kcycles_per_cta_median": {k: float(sorted(ph[:, c])[len(ph) // 2]) / 1e3 for c, k in
+                                     [(1, "search_wait_space"), (2, "search_work"), (3, "extract_wait_bitmaps"), (4, "extract_wait_space"), (5, "extract_work"),
+                                      (6, "conv_wait_rows"), (8, "conv_work")]}}
 nbytes = B * (12 * N + 12 * M) + 4 * B * M * K * C1 + 4 * B * M * K + 4 * B * M + (4 * B * N * C1 if c else 0)
 print(json.dumps({"variant": os.environ.get("PSA_F1_VARIANT", "0"), "shape": [B, N, M, K, C1, c], "alg_bytes": nbytes,
                   "isolated_us_median": iso[len(iso) // 2], "isolated_us_min": iso[0], "isolated_gbs": nbytes / iso[len(iso) // 2] / 1e3,
