@@ -4,7 +4,7 @@
 // (pointnet2/utils/tf_util.py:512-531, is_training=True), so the first 1x1 conv's PRE-BN output has to exist in HBM
 // once.  The reference gets there through query_ball_point -> group_point -> tile/sub -> concat -> cuDNN conv + bias_add:
 // four materialised (B,m,K,.) tensors.  This kernel does the whole front in ONE launch:
-//   ball query (index-exact, grouping.cu's warp scan) -> neighbour coordinates straight from the shared-memory copy of
+//   ball query (index-exact; exhaustive register search in the streaming kernel) -> neighbour coordinates from the shared-memory copy of
 //   the cloud -> centre -> conv1 (+ optional per-point feature products U = points . W1[3:,:]) + bias ->
 //   coalesced streaming store of (B,m,K,C1) + idx/pts_cnt + per-channel sum / sum-of-squares for the BN statistics.
 // HBM traffic = algorithmic traffic: B*(12n + 12m) in, 4*B*m*K*(C1+1) + 4*B*m out  (137.3 MB at B=32,N=2048,m=512,K=32,
@@ -140,20 +140,26 @@ sa_conv1_prebn_kernel(const __grid_constant__ F1Args a) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Streaming F1 kernel (round 2): the same front as above, organised so that the only thing the SMs do for most of the
-// launch is stream the (B,m,K,C1) tensor out.
-//   * persistent CTAs (2 per SM), each owning an equal contiguous range of the B*m queries (ranges may cross clouds);
-//   * warps 0..NP-1 = PRODUCERS.  No spatial grid: at these sizes (n <= 4096, ~100 queries per CTA) an exhaustive test
-//     out of REGISTERS is cheaper than building one -- a producer thread keeps PPTP points of the cloud in registers, and
-//     for every query of a batch tests them on the packed f32x2 pipe (same arithmetic as the reference, NaN counts as
-//     inside); lane l of a warp owns point 32*w + l of each 32-point word, so one ballot per word IS that word of the
-//     query's hit bitmap -- no atomics, no compaction.  The nsample lowest set bits are the reference's "first nsample in
-//     index order" (8 lanes per query read them out with popcount prefix sums), then idx / pts_cnt go to global memory
-//     and the centred coordinates (dx,dy,dz,j) of every row of the batch into a shared-memory ring slot;
-//   * the other warps = CONSUMERS: per step 4 rows x C1 channels -- one LDS.128 for the row's (dx,dy,dz,j), 6 FFMA2 per 4
-//     channels with the weights resident in registers, 128-byte streaming stores, BN statistics in registers;
-//   * ring of kF1Ring batches of kF1Batch queries, named barriers FULL/EMPTY per slot: the search of batch t+2 runs
-//     under the stores of batch t.  No CTA-wide barrier inside the main loop.
+// Streaming F1 kernel (round 2, default): the same front as above, organised so that the only thing the SMs do for most of
+// the launch is stream the (B,m,K,C1) tensor out.
+//   * persistent CTAs (2 per SM, 12 warps), each owning a contiguous range of the B*m queries; when the grid is a multiple of
+//     B every CTA stays inside one cloud (ranges that cross a cloud boundary reload the cloud and re-ramp the pipeline);
+//   * three warpgroups = three pipeline stages (registers re-partitioned with setmaxnreg: 128 / 56 / 56):
+//       SEARCH   warps 0-3.  No spatial grid: at these sizes (n <= 4096, ~60 queries per CTA) an exhaustive test out of
+//                REGISTERS is cheaper than building one.  A search thread keeps PPTP CONSECUTIVE points of the cloud in
+//                registers as packed f32x2 pairs and tests them against every query of a batch with the reference's
+//                arithmetic (NaN counts as inside); the SIGN of (thr - d) is shifted straight into the lane's hit mask, and
+//                because the lane's points are consecutive that mask IS bits [PPTP*tid, +PPTP) of the query's bitmap -- no
+//                ballots, no atomics, no compaction;
+//       EXTRACT  warps 4-7.  LPQ = 16 lanes per query read the nsample lowest set bits out in index order (popcount prefix
+//                sums: the reference's "first nsample in index order", padded with the first hit), write idx / pts_cnt to
+//                global memory and the centred rows (dx,dy,dz,j) of the batch into the rows ring;
+//       CONV     warps 8-11.  Per step 4 rows x C1 channels -- one LDS.128 for the row's (dx,dy,dz,j), 6 FFMA2 per 4 channels
+//                with the weights resident in registers, 128-byte streaming stores, BN statistics in registers.
+//     Levels WITH input features (HAS_U) run two stages instead: warps 0-3 search and extract, warps 4-11 convolve (the
+//     512-byte U-row gathers of the conv stage are what needs the warps there);
+//   * two rings of kF1Ring slots (bitmaps + centres | rows), named barriers FULL/EMPTY per slot; batches of 2, 4, then
+//     kF1Batch queries so the first stores leave early.  No CTA-wide barrier inside the main loop.
 // Statistics: per-CTA partials in a fixed order, the last CTA to finish (ticket) adds them in fp64 in CTA order:
 // deterministic, one launch.
 // ---------------------------------------------------------------------------------------------------------------------
