@@ -86,45 +86,48 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def cpu_forward_rate(n_clouds: int, repeats: int = 1, warm: bool = True):
-    """Oracle port of the SSG forward on the host cores: C restatement (OpenMP) for FPS / ball query / group,
-    numpy fp32 (multi-threaded BLAS) for conv+BN+ReLU+max.  Returns (clouds/s, cores, seconds)."""
-    import numpy as np
+class CpuForward:
+    """Oracle port of the SSG forward on the host cores: C restatement (OpenMP over the batch) for FPS / ball query / group,
+    fp32 GEMMs on every core for conv+BN+ReLU+max (oracle.mlp_oracle.pointnet2_cls_ssg_fast: one GEMM per layer over all
+    grouped rows through torch-CPU, batch norm folded, in-place ReLU).  Weights and clouds are made once, outside any timer."""
 
-    from oracle import mlp_oracle as mo
-    from scanobjectnn_b200 import pointnet2_cls_ssg
-    from scanobjectnn_b200.synthetic import make_clouds
+    def __init__(self):
+        from oracle import mlp_oracle as mo
+        from scanobjectnn_b200 import pointnet2_cls_ssg
+        from scanobjectnn_b200.synthetic import make_clouds
 
-    params = pointnet2_cls_ssg.init_params(seed=1, device="cpu", randomize_bn=True)
-    xyz = make_clouds("ball", n_clouds, N, seed=1001)
-    if warm:
-        mo.pointnet2_cls_ssg(xyz[:1], params, dtype=np.float32)      # warm-up (page in BLAS, OpenMP pool)
-    best = None
-    for _ in range(repeats):
+        self.mo = mo
+        self.cores = os.cpu_count() or 1
+        self.params = pointnet2_cls_ssg.init_params(seed=1, device="cpu", randomize_bn=True)
+        self.xyz = make_clouds("ball", B, N, seed=1001)
+        self.run(1)                                                   # warm-up (page in the GEMM library, thread pools)
+
+    def run(self, n_clouds: int) -> float:
+        """one forward over the first n_clouds clouds of the batch; returns seconds"""
         t0 = time.perf_counter()
-        mo.pointnet2_cls_ssg(xyz, params, dtype=np.float32)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_clouds / best, os.cpu_count() or 1, best
+        self.mo.pointnet2_cls_ssg_fast(self.xyz[:n_clouds], self.params, threads=self.cores)
+        return time.perf_counter() - t0
 
 
 def run_reference(args):
     """The reference arm: the CPU implementation of the same forward on the box's host cores (the reference's TF1 path
     is not installable here -- DESIGN.md section 4 -- so this is the oracle port: C/OpenMP restatement of the reference
-    kernels for FPS / ball query / group, numpy fp32 (multi-threaded BLAS) for conv+BN+ReLU+max).  Each step is a
+    kernels for FPS / ball query / group, one fp32 GEMM per layer on all cores (torch-CPU) for conv+BN+ReLU+max).  Each step is a
     bounded sample of the 32-cloud batch, sized so that the whole run stays within ~90 s of CPU work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    probe, cores, _ = cpu_forward_rate(8)                  # also the warm-up
+    cpu = CpuForward()
+    cores = cpu.cores
+    probe = 8 / min(cpu.run(8), cpu.run(8))                # clouds/s, also the warm-up at batch scale
     budget_s = 90.0
     sample = int(max(1, min(B, budget_s * probe / max(args.steps, 1))))
-    for _ in range(max(min(args.warmup, 3), 1)):
-        cpu_forward_rate(1)
+    for _ in range(max(args.warmup, 1)):
+        cpu.run(sample)
     t0 = time.perf_counter()
     done = 0
     for _ in range(args.steps):
-        cpu_forward_rate(sample, warm=False)
+        cpu.run(sample)
         done += sample
     dt = time.perf_counter() - t0
     value = done / dt
@@ -134,7 +137,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{sample} of the 32 clouds per step"},
         "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} clouds x {args.steps} steps ({dt:.1f} s), oracle port (C/OpenMP index ops + numpy fp32 MLP); "
+                         "sample": f"{sample} clouds x {args.steps} steps ({dt:.1f} s), oracle port (C/OpenMP index ops + fp32 GEMMs on all cores, torch-CPU); "
                                    "the reference's TF1 path is not installable here"},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -623,9 +626,11 @@ def main():
 
     cpu = None
     if solo and not args.no_cpu_baseline:
-        rate, cores, secs = cpu_forward_rate(B, repeats=3)
-        cpu = {"value": rate, "unit": "clouds/s", "cores": cores, "kind": "port",
-               "sample": f"the full 32-cloud batch, best of 3 forwards ({secs:.1f} s each): oracle port = C/OpenMP FPS+ball-query+group, numpy fp32 conv/BN/ReLU/max"}
+        cf = CpuForward()
+        secs = min(cf.run(B) for _ in range(5))
+        cpu = {"value": B / secs, "unit": "clouds/s", "cores": cf.cores, "kind": "port",
+               "sample": f"the full 32-cloud batch, best of 5 forwards ({secs:.2f} s each): oracle port = C/OpenMP FPS+ball-query+group, "
+                         "one fp32 GEMM per layer on all host cores (torch-CPU), folded BN, ReLU, max"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -177,3 +177,60 @@ def pointnet_cls(point_cloud, params, dtype=np.float64):
     net = net @ t2
     net = mlp_chain(net, params, ["conv3", "conv4", "conv5"], dtype=dtype).max(axis=1)
     return mlp_chain(net, params, ["fc1", "fc2", "fc3"], [True, True, False], dtype), t2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Host-speed fp32 evaluation of the same forward, for bench.py's CPU legs only (cpu_baseline, --impl reference).
+# Same semantics as pointnet2_cls_ssg above; organised the way a CPU build of the reference would run it (SURVEY 8d:
+# "grouped MLP via PyTorch-CPU fp32 with torch.set_num_threads(nproc)"): every 1x1 conv is ONE (rows x Cin) x (Cin x Cout)
+# GEMM on all host cores (oneDNN / MKL through torch), the inference batch norm is folded into the weights and the bias
+# (folded in float64, then rounded), ReLU in place, max over nsample as one reduction -- instead of numpy's batched 4-D matmul
+# (one small GEMM per neighbourhood) and separate elementwise passes.  tests/test_mlp_oracle_crosscheck.py holds it to the
+# fp64 evaluation.
+# ---------------------------------------------------------------------------------------------------------------------
+def _folded(params, scope):
+    w = _np(params[f"{scope}/weights"], np.float64)
+    w = w.reshape(-1, w.shape[-1])
+    b = _np(params[f"{scope}/biases"], np.float64)
+    if f"{scope}/bn/gamma" in params:
+        inv = _np(params[f"{scope}/bn/gamma"], np.float64) / np.sqrt(_np(params[f"{scope}/bn/moving_variance"], np.float64) + BN_EPS)
+        w = w * inv
+        b = (b - _np(params[f"{scope}/bn/moving_mean"], np.float64)) * inv + _np(params[f"{scope}/bn/beta"], np.float64)
+    return w.astype(np.float32), b.astype(np.float32)
+
+
+def _mlp_rows_fast(rows, params, scopes, relus=None):
+    """rows: torch fp32 (R, Cin) -> (R, Cout)."""
+    import torch
+
+    relus = relus or [True] * len(scopes)
+    for s, r in zip(scopes, relus):
+        w, b = _folded(params, s)
+        rows = torch.addmm(torch.from_numpy(b), rows, torch.from_numpy(w))
+        if r:
+            rows.relu_()
+    return rows
+
+
+def pointnet2_cls_ssg_fast(point_cloud, params, threads=None):
+    """pointnet2_cls_ssg (pointnet2/models/pointnet2_cls_ssg.py:23-47, is_training=False) in fp32 at host speed -> logits."""
+    import os
+
+    import torch
+
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    xyz = np.ascontiguousarray(point_cloud, np.float32)
+    bsz = xyz.shape[0]
+    with torch.no_grad():
+        cur_xyz, cur_pts = xyz, None
+        for scope, npoint, radius, nsample, mlp in (("layer1", 512, 0.2, 32, 3), ("layer2", 128, 0.4, 64, 3)):
+            new_xyz, new_points, _, _ = sample_and_group(npoint, radius, nsample, cur_xyz, cur_pts)
+            rows = torch.from_numpy(np.ascontiguousarray(new_points, np.float32)).reshape(-1, new_points.shape[-1])
+            y = _mlp_rows_fast(rows, params, [f"{scope}/conv{i}" for i in range(mlp)])
+            cur_pts = y.reshape(bsz * npoint, nsample, -1).amax(dim=1).reshape(bsz, npoint, -1).numpy()
+            cur_xyz = new_xyz
+        rows = torch.from_numpy(np.concatenate([cur_xyz, cur_pts], axis=2)).reshape(-1, 3 + cur_pts.shape[-1])
+        y = _mlp_rows_fast(rows, params, [f"layer3/conv{i}" for i in range(3)])
+        net = y.reshape(bsz, -1, y.shape[-1]).amax(dim=1)
+        net = _mlp_rows_fast(net, params, ["fc1", "fc2", "fc3"], [True, True, False])
+    return net.numpy()

@@ -13,11 +13,13 @@
 //             layout, dropped there by cp.async.bulk from pre-arranged images; D in TMEM.  Between layers the row warps
 //             pull D with tcgen05.ld, apply affine + ReLU and push the next A operand with tcgen05.st.
 //   max-pool  the last epilogue reduces each neighbourhood's rows with a transposing warp butterfly and writes
-//             (B,m,C_out) coalesced.
+//             (B,m,C_out) coalesced.  64-wide levels ending in a 128-wide layer (DB = 3, SA1) run the LAST layer transposed
+//             instead: H^T written to shared memory by the previous epilogue, D^T[channel][row] -- lane = channel, so the
+//             max-pool is an in-thread reduction, the affine a per-thread scalar and the stores coalesced row segments.
 //
 // Kernels (all templated on NP, the pieces per operand -- Split<NP> in tc_common.cuh):
 //   tc_sa_dual_kernel<DB,NP>  SA level, two row groups per CTA, per-group streamed last layer, tensor-pipe token, one or two D
-//                             slots (DB); optional centre weights = multi-layer EdgeConv over 3-D points
+//                             slots (DB = 0/1/2), DB = 3 = transposed last layer; optional centre weights = multi-layer EdgeConv over 3-D points
 //   tc_dense3_kernel<NP>      dense layer, transposed (lane = channel), both operands from shared memory; also the
 //                             training-mode forward (previous batch norm applied on load, statistics in the epilogue)
 //   tc_dense2_kernel<NT,NP>   dense layer, A from TMEM, warp-specialised pipeline (N = 64 or K > 512)

@@ -50,3 +50,16 @@ def test_dense_chain_restatement_agrees_with_torch_functional():
     g = _torch_layer(torch.from_numpy(x).double(), p, "c0")
     g = _torch_layer(g, p, "c1", relu=False)
     assert np.abs(g.numpy() - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_host_speed_fp32_forward_agrees_with_fp64_restatement():
+    """bench.py's CPU legs time mlp_oracle.pointnet2_cls_ssg_fast (one fp32 GEMM per layer, folded BN): same logits as the
+    float64 restatement of pointnet2_cls_ssg.py:23-47 to fp32 rounding."""
+    from scanobjectnn_b200 import pointnet2_cls_ssg
+
+    p = pointnet2_cls_ssg.init_params(seed=5, device="cpu", randomize_bn=True)
+    xyz = make_clouds("shell", 2, 1024, seed=77)
+    want, _ = mo.pointnet2_cls_ssg(xyz, p)
+    got = mo.pointnet2_cls_ssg_fast(xyz, p, threads=2)
+    assert got.shape == want.shape == (2, 15)
+    assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max())
