@@ -255,8 +255,9 @@ PSA_API int psa_sa_group_all_infer(int b, int n, int c, const float* xyz, const 
  *   2: three bf16 pieces per operand, six MMAs per product (small terms first) -- any magnitude, twice the tensor work.
  *   1: fp32-FMA kernels only.
  * Weight images (psa_prepare_weight_image) are format-specific: psa_mlp_image_plan returns the format of the current mode in its
- * nt values; images of the other format are ignored (rebuilt per call).  The switch is process-global and not synchronised:
- * set it before launching work, not concurrently with it. */
+ * nt values; images of the other format are ignored (rebuilt per call).  The switch is process-global (two atomics: changing it while
+ * other threads launch is race-free, but a call in flight may see either mode for its later layers): set it before launching
+ * work, not concurrently with it. */
 PSA_API int psa_set_mlp_mode(int mode);
 PSA_API int psa_get_mlp_mode(void);
 

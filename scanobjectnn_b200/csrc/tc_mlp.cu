@@ -33,6 +33,8 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "mlp_internal.cuh"
 #include "tc_common.cuh"
@@ -1334,7 +1336,7 @@ bool tc_dense_eligible(long long rows, int K, int N, int pool_k) {
 }
 
 // Operand split of the inference launches: 2 = fp16x2 with the np = 3 rerun guard (default), 3 = bf16x3 only (psa_set_mlp_mode(2)).
-static int g_tc_np = 2;
+static std::atomic<int> g_tc_np{2};        // process-wide settings: atomics, so that a concurrent psa_set_mlp_mode is a race-free (if unordered) switch
 int tc_np() { return g_tc_np; }
 
 // Workspace reservation for one dense layer's images: an fp16x2 image (used when the caller brought no prebuilt one) followed by
@@ -1636,7 +1638,7 @@ static int tc_sa_run(TcArgs& a, int b, int n, int m, int c, int nsample, const f
 
 using namespace psa;
 
-static int g_mlp_mode = 0;
+static std::atomic<int> g_mlp_mode{0};
 extern "C" PSA_API int psa_set_mlp_mode(int mode) {
     PSA_REQUIRE(mode == 0 || mode == 1 || mode == 2,
                 "set_mlp_mode: mode must be 0 (tensor cores, fp16x2 operands with the range guard), 1 (fp32 FMA kernels only) or 2 (tensor cores, bf16x3)");
