@@ -69,7 +69,7 @@ PSA_API int psa_gather_point_grad(int b, int n, int m, const float* out_g, const
                           size_t workspace_bytes, psa_stream_t stream);
 
 /* The three scatter-add gradients (GatherPointGrad, GroupPointGrad, ThreeInterpolateGrad) add the contributions of one
- * destination in ascending entry order -- the order of the reference's sequential CPU loops (test/*_cpu, tf_interpolate.cpp)
+ * destination in ascending entry order -- the order of the reference's sequential CPU loops (grouping/test/ ..._cpu, tf_interpolate.cpp)
  * -- instead of the float atomicAdd of its CUDA kernels: results are bit-reproducible.  They need a device scratch buffer of
  * this many bytes for the per-cloud (destination -> entries) lists: b clouds, n_dst destination points and `entries`
  * scattered rows per cloud (m; m*nsample; 3*n).  Out-of-range indices are dropped.  n_dst <= 51200. */

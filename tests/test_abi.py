@@ -74,3 +74,28 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
                 assert "liboracle" not in text and "oracle/_ref" not in text, f
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/psa.h compiles as C99 (no C++, no torch types) and a C program links against libpsa.so."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_psa.c"
+    src.write_text('#include "psa.h"\n#include <stddef.h>\n'
+                   "int main(void) {\n"
+                   "    /* taking the addresses forces the prototypes to resolve at link time; nothing is launched */\n"
+                   "    void* f[] = {(void*)psa_farthest_point_sample, (void*)psa_query_ball_point, (void*)psa_sa_module_infer, (void*)psa_sa_conv1_prebn,\n"
+                   "                 (void*)psa_three_nn_interpolate, (void*)psa_knn_graph, (void*)psa_last_error};\n"
+                   "    return (f[0] != NULL && psa_get_mlp_mode() >= 0) ? 0 : 1;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "scanobjectnn_b200")
+    exe = tmp_path / "use_psa"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-L", libdir, "-lpsa", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
