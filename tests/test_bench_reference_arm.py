@@ -3,6 +3,7 @@ unit / config of the GPU arm, a cpu_baseline object describing the run and an e2
 torchrun only rank 0 works and prints."""
 import json
 import os
+import socket
 import subprocess
 import sys
 
@@ -30,10 +31,16 @@ def test_reference_arm_single_process():
     _check(lines[0], 1)
 
 
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_reference_arm_under_torchrun_prints_once():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29561", "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3"],
+                        "--master-port", str(_free_port()), "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3"],
                        cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
