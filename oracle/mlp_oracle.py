@@ -199,13 +199,47 @@ def _folded(params, scope):
     return w.astype(np.float32), b.astype(np.float32)
 
 
+_FAST_WS = {}
+
+
+def _flat(i, numel):
+    """Reusable flat fp32 buffer number i (grown on demand): a fresh 100-300 MB output per layer costs more in page faults than
+    the GEMM that fills it (measured here: 45-400 ms fresh vs 18 ms into a resident buffer for 524288 x 64 x 128)."""
+    import torch
+
+    t = _FAST_WS.get(i)
+    if t is None or t.numel() < numel:
+        t = torch.empty(int(numel), dtype=torch.float32)
+        t.zero_()                                  # touch the pages once
+        _FAST_WS[i] = t
+    return t[:numel]
+
+
+def _layer_fast(out_flat, x, params, scope, relu=True, x2=None, split=None):
+    """relu(x . W' + b') with the folded weights of ``scope`` into a view of ``out_flat``; with x2/split the input is the
+    virtual concatenation [x2, x] (W' rows [0, split) act on x2) -- the concat tensor of pointnet_util.py:50 is never built."""
+    import torch
+
+    w, b = _folded(params, scope)
+    wt, bt = torch.from_numpy(w), torch.from_numpy(b)
+    out = out_flat[: x.shape[0] * w.shape[1]].view(x.shape[0], w.shape[1])
+    if x2 is None:
+        torch.addmm(bt, x, wt, out=out)
+    else:
+        torch.addmm(bt, x, wt[split:], out=out)
+        out.addmm_(x2, wt[:split])
+    if relu:
+        out.relu_()
+    return out
+
+
 def _mlp_rows_fast(rows, params, scopes, relus=None):
-    """rows: torch fp32 (R, Cin) -> (R, Cout)."""
+    """rows: torch fp32 (R, Cin) -> (R, Cout); small layers (group_all level, FC head): fresh outputs."""
     import torch
 
     relus = relus or [True] * len(scopes)
-    for s, r in zip(scopes, relus):
-        w, b = _folded(params, s)
+    for s_, r in zip(scopes, relus):
+        w, b = _folded(params, s_)
         rows = torch.addmm(torch.from_numpy(b), rows, torch.from_numpy(w))
         if r:
             rows.relu_()
@@ -213,7 +247,8 @@ def _mlp_rows_fast(rows, params, scopes, relus=None):
 
 
 def pointnet2_cls_ssg_fast(point_cloud, params, threads=None):
-    """pointnet2_cls_ssg (pointnet2/models/pointnet2_cls_ssg.py:23-47, is_training=False) in fp32 at host speed -> logits."""
+    """pointnet2_cls_ssg (pointnet2/models/pointnet2_cls_ssg.py:23-47, is_training=False) in fp32 at host speed -> logits.
+    Index ops: the C restatement (OpenMP over the batch); grouped MLPs: one GEMM per layer into reused buffers."""
     import os
 
     import torch
@@ -221,13 +256,28 @@ def pointnet2_cls_ssg_fast(point_cloud, params, threads=None):
     torch.set_num_threads(threads or os.cpu_count() or 1)
     xyz = np.ascontiguousarray(point_cloud, np.float32)
     bsz = xyz.shape[0]
+    lib = orc.lib()
     with torch.no_grad():
         cur_xyz, cur_pts = xyz, None
-        for scope, npoint, radius, nsample, mlp in (("layer1", 512, 0.2, 32, 3), ("layer2", 128, 0.4, 64, 3)):
-            new_xyz, new_points, _, _ = sample_and_group(npoint, radius, nsample, cur_xyz, cur_pts)
-            rows = torch.from_numpy(np.ascontiguousarray(new_points, np.float32)).reshape(-1, new_points.shape[-1])
-            y = _mlp_rows_fast(rows, params, [f"{scope}/conv{i}" for i in range(mlp)])
-            cur_pts = y.reshape(bsz * npoint, nsample, -1).amax(dim=1).reshape(bsz, npoint, -1).numpy()
+        for scope, npoint, radius, nsample in (("layer1", 512, 0.2, 32), ("layer2", 128, 0.4, 64)):
+            new_xyz = orc.gather_point(cur_xyz, orc.fps(cur_xyz, npoint))
+            idx, _ = orc.query_ball_point(radius, nsample, cur_xyz, new_xyz, contract=True)
+            rows = bsz * npoint * nsample
+            gx = torch.from_numpy((orc.group_point(cur_xyz, idx) - new_xyz[:, :, None, :]).reshape(rows, 3))
+            widths = [_folded(params, f"{scope}/conv{i}")[0].shape[1] for i in range(3)]
+            if cur_pts is None:
+                y = _layer_fast(_flat(0, rows * widths[0]), gx, params, f"{scope}/conv0")
+                nxt = 1
+            else:
+                c = cur_pts.shape[-1]
+                gf = _flat(0, rows * c).view(rows, c)                      # grouped features straight into the reused buffer
+                lib.orc_group_point(bsz, cur_pts.shape[1], c, npoint, nsample, orc._p(np.ascontiguousarray(cur_pts, np.float32)), orc._p(idx),
+                                    orc._p(gf.numpy()))
+                y = _layer_fast(_flat(1, rows * widths[0]), gf, params, f"{scope}/conv0", x2=gx, split=3)
+                nxt = 0
+            y = _layer_fast(_flat(nxt, rows * widths[1]), y, params, f"{scope}/conv1")
+            y = _layer_fast(_flat(2, rows * widths[2]), y, params, f"{scope}/conv2")
+            cur_pts = y.view(bsz * npoint, nsample, widths[2]).amax(dim=1).view(bsz, npoint, widths[2]).numpy()
             cur_xyz = new_xyz
         rows = torch.from_numpy(np.concatenate([cur_xyz, cur_pts], axis=2)).reshape(-1, 3 + cur_pts.shape[-1])
         y = _mlp_rows_fast(rows, params, [f"layer3/conv{i}" for i in range(3)])
