@@ -72,3 +72,23 @@ def test_index_kernels_use_packed_f32x2_and_redux(sass):
     fps = "\n".join(l for k, v in _kernels(sass, "fps_kernel").items() for l in v)
     assert re.search(r"\bFFMA2\b|\bFMUL2\b|\bFADD2\b", fps), "FPS lost its packed f32x2 distance math"
     assert re.search(r"\bREDUX\b|\bCREDUX\b", fps), "FPS lost its warp REDUX arg-max"
+
+
+def test_streaming_f1_kernel_keeps_its_code_shape(sass):
+    """sa_conv1_stream_kernel (north_star's named kernel): the search runs on the packed f32x2 pipe with funnel shifts
+    collecting the sign masks (no per-word ballots: VOTE only in the extraction's bookkeeping), the warpgroups re-partition their
+    registers with setmaxnreg, the output leaves in 128-bit evict-first streaming stores, and the 128-register search stage does not
+    spill beyond a few words."""
+    ks = _kernels(sass, "sa_conv1_stream_kernel")
+    assert len(ks) == 12, sorted(ks)                  # NV in {2, 4} x HAS_U x PPTP in {8, 16, 32}
+    for name, lines in ks.items():
+        text = "\n".join(lines)
+        pptp = int(re.search(r"ELi(\d+)EEEv", name).group(1))
+        pairs = pptp // 2                             # point pairs per thread = unrolled distance tests
+        assert _count(lines, "FMUL2") >= pairs and _count(lines, "FFMA2") >= 2 * pairs and _count(lines, "FADD2") >= 4 * pairs, name
+        assert _count(lines, r"SHF(\.\w+)*") >= 2 * pairs, f"{name}: the sign-mask funnel shifts are gone"
+        assert _count(lines, r"VOTE(\.\w+)*") <= 8, f"{name}: ballots are back in the search"
+        assert _count(lines, "USETMAXREG") >= 3, f"{name}: no setmaxnreg"
+        assert re.search(r"STG\.E\.EF\.128", text), f"{name}: output no longer leaves in 128-bit evict-first stores"
+        assert _count(lines, r"STL(\.\w+)*") <= 16 and _count(lines, r"LDL(\.\w+)*") <= 16, f"{name}: register spills"
+        assert not re.search(r"\bRED\b|\bATOMG\b.*\.F32", text), f"{name}: float atomics in the statistics"
