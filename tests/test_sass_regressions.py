@@ -92,3 +92,15 @@ def test_streaming_f1_kernel_keeps_its_code_shape(sass):
         assert re.search(r"STG\.E\.EF\.128", text), f"{name}: output no longer leaves in 128-bit evict-first stores"
         assert _count(lines, r"STL(\.\w+)*") <= 16 and _count(lines, r"LDL(\.\w+)*") <= 16, f"{name}: register spills"
         assert not re.search(r"\bRED\b|\bATOMG\b.*\.F32", text), f"{name}: float atomics in the statistics"
+
+
+def test_transposed_sa_level_pools_in_thread(sass):
+    """tc_sa_dual_kernel<3,2> (64-wide levels, last layer transposed: DESIGN.md 3.3): with lane = channel the max over a neighbourhood
+    is an in-thread FMNMX3 chain -- the shuffle butterfly of the row-form kernels (45-78 SHFL) must not come back -- and the last
+    layer's MMAs take both operands from shared memory (H written by the previous epilogue with swizzled STS)."""
+    (name, lines), = _kernels(sass, "tc_sa_dual_kernelILi3ELi2E").items()
+    assert _count(lines, "FMNMX3") >= 16, name
+    assert _count(lines, r"SHFL(\.\w+)*") <= 16, f"{name}: the max-pool shuffles are back"
+    assert _count(lines, r"STS(\.\w+)*") >= 40, f"{name}: H is no longer written to shared memory"
+    rows = [v for k, v in _kernels(sass, "tc_sa_dual_kernelILi1ELi2E").items()][0]
+    assert _count(rows, r"SHFL(\.\w+)*") > 2 * _count(lines, r"SHFL(\.\w+)*")
