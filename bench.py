@@ -97,7 +97,10 @@ class CpuForward:
         from scanobjectnn_b200.synthetic import make_clouds
 
         self.mo = mo
-        self.cores = os.cpu_count() or 1
+        try:
+            self.cores = len(os.sched_getaffinity(0)) or 1           # the cores this process may run on
+        except AttributeError:
+            self.cores = os.cpu_count() or 1
         self.params = pointnet2_cls_ssg.init_params(seed=1, device="cpu", randomize_bn=True)
         self.xyz = make_clouds("ball", B, N, seed=1001)
         self.run(1)                                                   # warm-up (page in the GEMM library, thread pools)
